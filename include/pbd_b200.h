@@ -1,0 +1,174 @@
+/* pbd_b200.h -- C-ABI of the B200-native parts-based detector hot path.
+ *
+ * This is the drop-in boundary for ONE path of wg-perception/PartsBasedDetector:
+ * PartsBasedDetector<T>::detect() (reference src/PartsBasedDetector.cpp:69-95), i.e.
+ *   HOGFeatures<T>::pyramid()            reference src/HOGFeatures.cpp:95-151, 168-341
+ *   SpatialConvolutionEngine::pdf()      reference src/SpatialConvolutionEngine.cpp:106-124
+ *   DynamicProgram<T>::min() / argmin()  reference src/DynamicProgram.cpp:67-173, 190-255
+ *   DistanceTransform<T>::compute()      reference include/DistanceTransform.hpp:203-245
+ * plus the model container/loader either side of it (Model / FileStorageModel,
+ * reference include/Model.hpp:49-122, src/FileStorageModel.cpp:42-159).
+ *
+ * Conventions: plain pointers and sizes only; every function returns PBD_OK (0) or a
+ * negative pbd_status and never throws; pbd_last_error() gives the message for the
+ * calling thread.  One pbd_detector per host thread (the reference detector is not
+ * re-entrant either: pyramid() mutates members, src/HOGFeatures.cpp:99,106-107).
+ * The CUDA path is the only implementation: there is no CPU fallback, creating a
+ * detector without a usable CUDA device fails with PBD_E_CUDA.
+ */
+#ifndef PBD_B200_H_
+#define PBD_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pbd_status {
+  PBD_OK = 0,
+  PBD_E_ARG = -1,      /* bad argument (null pointer, index out of range, bad shape)           */
+  PBD_E_IO = -2,       /* file cannot be opened (FileStorageModel::deserialize returns false)  */
+  PBD_E_FORMAT = -3,   /* file opened but is not a model in the expected format                */
+  PBD_E_CUDA = -4,     /* CUDA runtime error / no device                                        */
+  PBD_E_STATE = -5,    /* stage called out of order (e.g. pdf before pyramid)                   */
+  PBD_E_UNSUPPORTED = -6 /* e.g. image depth other than 8U (reference CV_Error, HOGFeatures.cpp:141-145) */
+} pbd_status;
+
+typedef struct pbd_model pbd_model;         /* reference: class Model (include/Model.hpp:49-122)          */
+typedef struct pbd_detector pbd_detector;   /* reference: PartsBasedDetector<float> after distributeModel */
+typedef struct pbd_candidates pbd_candidates; /* reference: std::vector<Candidate> (include/Candidate.hpp) */
+
+const char* pbd_last_error(void);
+const char* pbd_version(void);
+
+/* ------------------------------------------------------------------ model ---
+ * replaces FileStorageModel::deserialize / serialize (src/FileStorageModel.cpp:96-159 / 42-94).
+ * pbd_model_load_xml reads the `opencv_storage` XML written by cv::FileStorage.  One deliberate
+ * deviation from literal HEAD: a multi-valued <defid> is read in full (HEAD replaces it by [0] and
+ * then indexes out of bounds, src/FileStorageModel.cpp:148-152); empty/root <defid> -> [0].
+ * The .pbdm binary format is this library's own compact container of the same fields. */
+int pbd_model_load_xml(const char* path, pbd_model** out);
+int pbd_model_save_xml(const pbd_model* m, const char* path);
+int pbd_model_load_bin(const char* path, pbd_model** out);
+int pbd_model_save_bin(const pbd_model* m, const char* path);
+/* hdr = {interval, sbin, norient, flen, nfilters, nbias, ndefs, ncomponents};
+ * fdims = (rows kh, kw) per filter; filters = concatenated kh*kw*flen doubles (HWC, channel fastest);
+ * indexers = for each component: nparts, then per part: parentid, nf, nb, nd, filterid[nf], biasid[nb], defid[nd] */
+int pbd_model_create(const char* name, const int32_t* hdr, float thresh, const int32_t* fdims,
+                     const double* filters, const float* biasw, const int32_t* anchors,
+                     const float* defs, const int32_t* indexers, pbd_model** out);
+void pbd_model_free(pbd_model* m);
+
+/* getters mirroring Model's (include/Model.hpp:98-118) */
+const char* pbd_model_name(const pbd_model* m);
+int pbd_model_header(const pbd_model* m, int32_t hdr[8], float* thresh);
+int pbd_model_filter(const pbd_model* m, int i, int32_t* rows, int32_t* kw, const double** data);
+int pbd_model_bias(const pbd_model* m, const float** data, int32_t* n);
+int pbd_model_anchors(const pbd_model* m, const int32_t** xy, int32_t* n);
+int pbd_model_defs(const pbd_model* m, const float** w4, int32_t* n);
+int pbd_model_nparts(const pbd_model* m, int component);
+/* copies up to cap ints of the requested list; *n receives its full length.  which: 0 filterid, 1 biasid, 2 defid */
+int pbd_model_part(const pbd_model* m, int component, int part, int32_t* parentid, int which,
+                   int32_t* dst, int32_t cap, int32_t* n);
+
+/* --------------------------------------------------------------- detector ---
+ * replaces PartsBasedDetector<float>::distributeModel (src/PartsBasedDetector.cpp:102-127): uploads the
+ * filters (converted double->float as :115-117), the part tables and creates the stage pipelines.
+ * `stream` is a cudaStream_t (0 = the legacy default stream); all work of this detector is issued on it. */
+int pbd_create(const pbd_model* m, int device, void* stream, pbd_detector** out);
+void pbd_destroy(pbd_detector* d);
+
+/* options (defaults reproduce the reference):
+ *   "thresh"      detection threshold (default model thresh; DynamicProgram::thresh_)
+ *   "exact"       1 (default): responses use separately rounded multiply/add in the reference's summation
+ *                 order => bit-identical scores; 0: fused multiply-add (faster, scores differ in the last ulps)
+ *   "backptr"     0 (default): reference back-pointer composition (include/DistanceTransform.hpp:232-244),
+ *                 1: true 2-D argmax composition
+ *   "max_levels"  0 (default) = all pyramid levels, n = only the first n (finest) levels
+ *   "max_candidates" capacity of the candidate buffer per batch (default 65536) */
+int pbd_set_option(pbd_detector* d, const char* key, double value);
+int pbd_get_option(const pbd_detector* d, const char* key, double* value);
+
+/* whole path = PartsBasedDetector<T>::detect (src/PartsBasedDetector.cpp:69-95) on a batch of n equally
+ * sized 8-bit frames (c = 1 or 3 channels, BGR interleaved as cv::Mat 8UC3).  Host buffers; the call
+ * copies the frames to the device, runs all stages and returns the candidates of every frame.
+ * Like the reference, candidates are in (level, component, row-major hit) order per frame. */
+int pbd_detect_batch_u8(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c,
+                        size_t row_stride, size_t frame_stride, pbd_candidates** out);
+/* same, frames already resident in device memory (tightly packed n*h*w*c); result stays queued on the
+ * stream until pbd_candidates_* is called (which synchronises). */
+int pbd_detect_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, int h, int w, int c,
+                               pbd_candidates** out);
+/* enqueue only (no host sync, no candidate download): used for device-side timing */
+int pbd_enqueue_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, int h, int w, int c);
+int pbd_collect_candidates(pbd_detector* d, pbd_candidates** out);
+
+/* candidates: reference Candidate (include/Candidate.hpp:56-99) = per part cv::Rect + confidence,
+ * component; additionally the frame, pyramid level and per-part (x, y, mixture) in cell coordinates. */
+int pbd_candidates_count(const pbd_candidates* c);
+int pbd_candidates_nparts(const pbd_candidates* c, int i);
+int pbd_candidates_get(const pbd_candidates* c, int i, int32_t* frame, int32_t* level, int32_t* component,
+                       float* score, int32_t* xs, int32_t* ys, int32_t* ms, int32_t* rects_xywh);
+void pbd_candidates_free(pbd_candidates* c);
+/* Candidate::sort (include/Candidate.hpp:97-99): descending root score, stable */
+int pbd_candidates_sort(pbd_candidates* c);
+
+/* ------------------------------------------------------------ stage level ---
+ * The reference's plugin interfaces, one call per stage, operating on the detector's device buffers:
+ *   pbd_stage_pyramid  = IFeatures::pyramid        (include/IFeatures.hpp:49-73)
+ *   pbd_stage_pdf      = IConvolutionEngine::pdf   (include/IConvolutionEngine.hpp:44-68)
+ *   pbd_stage_dp_min   = DynamicProgram<T>::min    (include/DynamicProgram.hpp:74)
+ *   pbd_stage_dp_argmin= DynamicProgram<T>::argmin (include/DynamicProgram.hpp:75)
+ * Stages must run in this order after pbd_stage_pyramid (or after the corresponding pbd_set_* injection). */
+int pbd_stage_pyramid(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c,
+                      size_t row_stride, size_t frame_stride);
+int pbd_stage_pdf(pbd_detector* d);
+int pbd_stage_dp_min(pbd_detector* d);
+int pbd_stage_dp_argmin(pbd_detector* d, pbd_candidates** out);
+
+/* geometry of the current batch (IFeatures::nscales / scales, include/IFeatures.hpp:60-66) */
+int pbd_num_frames(const pbd_detector* d);
+int pbd_num_levels(const pbd_detector* d);
+int pbd_level_info(const pbd_detector* d, int level, int32_t* img_h, int32_t* img_w, int32_t* oh,
+                   int32_t* ow, float* scale);
+
+/* stage outputs copied to host (synchronises the stream) */
+int pbd_get_pyramid_image(pbd_detector* d, int frame, int level, uint8_t* dst);          /* img_h*img_w*c   */
+int pbd_get_features(pbd_detector* d, int frame, int level, float* dst);                 /* oh*ow*flen, HWC  */
+int pbd_get_response(pbd_detector* d, int frame, int level, int filter, float* dst);     /* oh*ow            */
+int pbd_get_rootv(pbd_detector* d, int frame, int level, int component, float* dst);     /* oh*ow            */
+int pbd_get_rooti(pbd_detector* d, int frame, int level, int component, int32_t* dst);   /* oh*ow            */
+/* Ix/Iy/Ik[level][component][part][parent mixture] as the reference's CV_32S Mats */
+int pbd_get_backptr(pbd_detector* d, int frame, int level, int component, int part, int parent_mixture,
+                    int32_t* ix, int32_t* iy, int32_t* ik);
+
+/* stage inputs injected from host (stage-isolated parity tests): define a batch of n frames with the given
+ * level table, then upload features and/or responses. */
+int pbd_set_levels(pbd_detector* d, int n_frames, int n_levels, const int32_t* ohow, const float* scales);
+int pbd_set_features(pbd_detector* d, int frame, int level, const float* src);
+int pbd_set_response(pbd_detector* d, int frame, int level, int filter, const float* src);
+
+/* ------------------------------------------------- standalone DT (config 5) ---
+ * Generalised distance transform of n_maps score maps of h x w (device pointers), one (w0..w3, ax, ay)
+ * per map: out[m] = DT(in[m]), ix/iy = back-pointers (uint16) with the reference composition.
+ * Reference: DistanceTransform<float>::compute, include/DistanceTransform.hpp:203-245. */
+int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int w, const float* h_defw4,
+                        const int32_t* h_anchor_xy, float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode);
+/* host-buffer convenience wrapper of the above (allocates, copies, runs, copies back) */
+int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy,
+                 float* out, int32_t* ix, int32_t* iy, int backptr_mode);
+
+/* ----------------------------------------------------------- measurement --- */
+/* number of kernels launched by this detector since creation (bench.py's gpu_launches) */
+long long pbd_launch_count(const pbd_detector* d);
+/* per-stage device time of the last pbd_detect_batch / pbd_enqueue call, measured with CUDA events on the
+ * detector's stream: ms[0..5] = h2d, pyramid, hog, pdf, dp_min, argmin.  Enabled by option "timing"=1. */
+int pbd_stage_times_ms(pbd_detector* d, float ms[6]);
+/* device bytes currently held by the detector */
+size_t pbd_device_bytes(const pbd_detector* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBD_B200_H_ */

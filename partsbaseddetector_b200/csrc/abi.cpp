@@ -1,0 +1,344 @@
+// abi.cpp -- extern "C" boundary (include/pbd_b200.h).  Exceptions never cross it.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+
+#include "../../include/pbd_b200.h"
+#include "engine.hpp"
+#include "model.hpp"
+
+using namespace pbd;
+
+struct pbd_model { Model m; };
+struct pbd_detector { std::unique_ptr<Engine> e; };
+struct pbd_candidates { std::vector<CandidateRec> v; };
+
+namespace {
+thread_local std::string g_err;
+
+template <typename F>
+int guarded(F f) {
+  try { f(); g_err.clear(); return PBD_OK; }
+  catch (const IoError& e) { g_err = e.what(); return PBD_E_IO; }
+  catch (const FormatError& e) { g_err = e.what(); return PBD_E_FORMAT; }
+  catch (const CudaError& e) { g_err = e.what(); return PBD_E_CUDA; }
+  catch (const StateError& e) { g_err = e.what(); return PBD_E_STATE; }
+  catch (const UnsupportedError& e) { g_err = e.what(); return PBD_E_UNSUPPORTED; }
+  catch (const ArgError& e) { g_err = e.what(); return PBD_E_ARG; }
+  catch (const std::bad_alloc&) { g_err = "out of host memory"; return PBD_E_ARG; }
+  catch (const std::exception& e) { g_err = e.what(); return PBD_E_ARG; }
+  catch (...) { g_err = "unknown error"; return PBD_E_ARG; }
+}
+#define REQUIRE(cond, msg) do { if (!(cond)) throw ArgError(msg); } while (0)
+}  // namespace
+
+extern "C" {
+
+const char* pbd_last_error(void) { return g_err.c_str(); }
+const char* pbd_version(void) { return "pbd_b200 0.1 (sm_100a)"; }
+
+int pbd_model_load_xml(const char* path, pbd_model** out) {
+  return guarded([&] { REQUIRE(path && out, "null argument"); auto m = std::make_unique<pbd_model>(); load_xml(path, m->m); *out = m.release(); });
+}
+int pbd_model_save_xml(const pbd_model* m, const char* path) { return guarded([&] { REQUIRE(m && path, "null argument"); save_xml(m->m, path); }); }
+int pbd_model_load_bin(const char* path, pbd_model** out) {
+  return guarded([&] { REQUIRE(path && out, "null argument"); auto m = std::make_unique<pbd_model>(); load_bin(path, m->m); *out = m.release(); });
+}
+int pbd_model_save_bin(const pbd_model* m, const char* path) { return guarded([&] { REQUIRE(m && path, "null argument"); save_bin(m->m, path); }); }
+
+int pbd_model_create(const char* name, const int32_t* hdr, float thresh, const int32_t* fdims, const double* filters,
+                     const float* biasw, const int32_t* anchors, const float* defs, const int32_t* indexers, pbd_model** out) {
+  return guarded([&] {
+    REQUIRE(hdr && fdims && filters && biasw && anchors && defs && indexers && out, "null argument");
+    auto pm = std::make_unique<pbd_model>();
+    Model& m = pm->m;
+    m.name = name ? name : "";
+    m.interval = hdr[0]; m.sbin = hdr[1]; m.norient = hdr[2]; m.flen = hdr[3];
+    const int nf = hdr[4], nb = hdr[5], nd = hdr[6], nc = hdr[7];
+    REQUIRE(nf > 0 && nb > 0 && nd >= 0 && nc > 0 && m.flen > 0, "bad header");
+    m.thresh = thresh;
+    size_t off = 0;
+    for (int i = 0; i < nf; ++i) {
+      REQUIRE(fdims[2 * i] > 0 && fdims[2 * i + 1] > 0, "bad filter dims");
+      m.frows.push_back(fdims[2 * i]); m.fkw.push_back(fdims[2 * i + 1]);
+      const size_t n = (size_t)fdims[2 * i] * fdims[2 * i + 1] * m.flen;
+      m.filters.emplace_back(filters + off, filters + off + n);
+      off += n;
+    }
+    m.biasw.assign(biasw, biasw + nb);
+    m.anchors.assign(anchors, anchors + 2 * (size_t)nd);
+    m.defs.assign(defs, defs + 4 * (size_t)nd);
+    const int32_t* ip = indexers;
+    m.comps.resize(nc);
+    for (int c = 0; c < nc; ++c) {
+      const int np = *ip++;
+      REQUIRE(np > 0, "component without parts");
+      m.comps[c].resize(np);
+      for (int p = 0; p < np; ++p) {
+        Part& P = m.comps[c][p];
+        P.parentid = *ip++;
+        const int a = *ip++, b = *ip++, d = *ip++;
+        REQUIRE(a >= 0 && b >= 0 && d >= 0, "bad indexer lengths");
+        P.filterid.assign(ip, ip + a); ip += a;
+        P.biasid.assign(ip, ip + b); ip += b;
+        P.defid.assign(ip, ip + d); ip += d;
+        if (P.defid.empty()) P.defid.push_back(0);
+      }
+    }
+    m.validate();
+    *out = pm.release();
+  });
+}
+void pbd_model_free(pbd_model* m) { delete m; }
+
+const char* pbd_model_name(const pbd_model* m) { return m ? m->m.name.c_str() : ""; }
+int pbd_model_header(const pbd_model* m, int32_t hdr[8], float* thresh) {
+  return guarded([&] {
+    REQUIRE(m && hdr, "null argument");
+    const Model& M = m->m;
+    hdr[0] = M.interval; hdr[1] = M.sbin; hdr[2] = M.norient; hdr[3] = M.flen; hdr[4] = M.nfilters(); hdr[5] = (int)M.biasw.size();
+    hdr[6] = M.ndefs(); hdr[7] = M.ncomponents();
+    if (thresh) *thresh = M.thresh;
+  });
+}
+int pbd_model_filter(const pbd_model* m, int i, int32_t* rows, int32_t* kw, const double** data) {
+  return guarded([&] {
+    REQUIRE(m && i >= 0 && i < m->m.nfilters(), "filter index out of range");
+    if (rows) *rows = m->m.frows[i];
+    if (kw) *kw = m->m.fkw[i];
+    if (data) *data = m->m.filters[i].data();
+  });
+}
+int pbd_model_bias(const pbd_model* m, const float** data, int32_t* n) {
+  return guarded([&] { REQUIRE(m && data && n, "null argument"); *data = m->m.biasw.data(); *n = (int)m->m.biasw.size(); });
+}
+int pbd_model_anchors(const pbd_model* m, const int32_t** xy, int32_t* n) {
+  return guarded([&] { REQUIRE(m && xy && n, "null argument"); *xy = m->m.anchors.data(); *n = (int)m->m.anchors.size() / 2; });
+}
+int pbd_model_defs(const pbd_model* m, const float** w4, int32_t* n) {
+  return guarded([&] { REQUIRE(m && w4 && n, "null argument"); *w4 = m->m.defs.data(); *n = m->m.ndefs(); });
+}
+int pbd_model_nparts(const pbd_model* m, int component) {
+  if (!m || component < 0 || component >= m->m.ncomponents()) { g_err = "component out of range"; return PBD_E_ARG; }
+  return (int)m->m.comps[component].size();
+}
+int pbd_model_part(const pbd_model* m, int component, int part, int32_t* parentid, int which, int32_t* dst, int32_t cap, int32_t* n) {
+  return guarded([&] {
+    REQUIRE(m && component >= 0 && component < m->m.ncomponents(), "component out of range");
+    const auto& parts = m->m.comps[component];
+    REQUIRE(part >= 0 && part < (int)parts.size(), "part out of range");
+    REQUIRE(which >= 0 && which <= 2, "bad list selector");
+    const Part& P = parts[part];
+    if (parentid) *parentid = P.parentid;
+    const std::vector<int>& v = which == 0 ? P.filterid : which == 1 ? P.biasid : P.defid;
+    if (n) *n = (int)v.size();
+    if (dst) for (int i = 0; i < cap && i < (int)v.size(); ++i) dst[i] = v[i];
+  });
+}
+
+int pbd_create(const pbd_model* m, int device, void* stream, pbd_detector** out) {
+  return guarded([&] {
+    REQUIRE(m && out, "null argument");
+    auto d = std::make_unique<pbd_detector>();
+    d->e = std::make_unique<Engine>(m->m, device, (cudaStream_t)stream);
+    *out = d.release();
+  });
+}
+void pbd_destroy(pbd_detector* d) { delete d; }
+
+int pbd_set_option(pbd_detector* d, const char* key, double value) {
+  return guarded([&] {
+    REQUIRE(d && key, "null argument");
+    Engine& e = *d->e;
+    const std::string k(key);
+    if (k == "thresh") e.thresh = value;
+    else if (k == "exact") e.exact = value != 0;
+    else if (k == "backptr") { REQUIRE(value == 0 || value == 1, "backptr must be 0 or 1"); e.backptr = (int)value; }
+    else if (k == "max_levels") { REQUIRE(value >= 0, "max_levels must be >= 0"); e.max_levels = (int)value; }
+    else if (k == "max_candidates") { REQUIRE(value >= 1 && value <= (1 << 24), "max_candidates out of range"); e.max_candidates = (int)value; }
+    else if (k == "timing") e.timing = value != 0;
+    else throw ArgError("unknown option '" + k + "'");
+  });
+}
+int pbd_get_option(const pbd_detector* d, const char* key, double* value) {
+  return guarded([&] {
+    REQUIRE(d && key && value, "null argument");
+    const Engine& e = *d->e;
+    const std::string k(key);
+    if (k == "thresh") *value = e.thresh;
+    else if (k == "exact") *value = e.exact;
+    else if (k == "backptr") *value = e.backptr;
+    else if (k == "max_levels") *value = e.max_levels;
+    else if (k == "max_candidates") *value = e.max_candidates;
+    else if (k == "timing") *value = e.timing;
+    else throw ArgError("unknown option '" + k + "'");
+  });
+}
+
+static void run_all(Engine& e) { e.run_pyramid(); e.run_pdf(); e.run_dp_min(); e.run_argmin(); }
+
+int pbd_detect_batch_u8(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c, size_t row_stride, size_t frame_stride,
+                        pbd_candidates** out) {
+  return guarded([&] {
+    REQUIRE(d && frames && out, "null argument");
+    Engine& e = *d->e;
+    e.set_frames_geometry(n, h, w, c);
+    e.upload_frames(frames, row_stride, frame_stride);
+    run_all(e);
+    auto cs = std::make_unique<pbd_candidates>();
+    e.collect(cs->v);
+    *out = cs.release();
+  });
+}
+int pbd_detect_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, int h, int w, int c, pbd_candidates** out) {
+  return guarded([&] {
+    REQUIRE(d && d_frames && out, "null argument");
+    Engine& e = *d->e;
+    e.set_frames_geometry(n, h, w, c);
+    e.use_device_frames(d_frames);
+    run_all(e);
+    auto cs = std::make_unique<pbd_candidates>();
+    e.collect(cs->v);
+    *out = cs.release();
+  });
+}
+int pbd_enqueue_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, int h, int w, int c) {
+  return guarded([&] {
+    REQUIRE(d && d_frames, "null argument");
+    Engine& e = *d->e;
+    e.set_frames_geometry(n, h, w, c);
+    e.use_device_frames(d_frames);
+    run_all(e);
+  });
+}
+int pbd_collect_candidates(pbd_detector* d, pbd_candidates** out) {
+  return guarded([&] { REQUIRE(d && out, "null argument"); auto cs = std::make_unique<pbd_candidates>(); d->e->collect(cs->v); *out = cs.release(); });
+}
+
+int pbd_candidates_count(const pbd_candidates* c) { return c ? (int)c->v.size() : 0; }
+int pbd_candidates_nparts(const pbd_candidates* c, int i) {
+  if (!c || i < 0 || i >= (int)c->v.size()) { g_err = "candidate index out of range"; return PBD_E_ARG; }
+  return (int)c->v[i].x.size();
+}
+int pbd_candidates_get(const pbd_candidates* c, int i, int32_t* frame, int32_t* level, int32_t* component, float* score, int32_t* xs,
+                       int32_t* ys, int32_t* ms, int32_t* rects_xywh) {
+  return guarded([&] {
+    REQUIRE(c && i >= 0 && i < (int)c->v.size(), "candidate index out of range");
+    const CandidateRec& C = c->v[i];
+    if (frame) *frame = C.frame;
+    if (level) *level = C.level;
+    if (component) *component = C.component;
+    if (score) *score = C.score;
+    const size_t np = C.x.size();
+    if (xs) memcpy(xs, C.x.data(), np * sizeof(int));
+    if (ys) memcpy(ys, C.y.data(), np * sizeof(int));
+    if (ms) memcpy(ms, C.m.data(), np * sizeof(int));
+    if (rects_xywh) memcpy(rects_xywh, C.rect.data(), np * 4 * sizeof(int));
+  });
+}
+void pbd_candidates_free(pbd_candidates* c) { delete c; }
+int pbd_candidates_sort(pbd_candidates* c) {
+  return guarded([&] {
+    REQUIRE(c, "null argument");
+    std::stable_sort(c->v.begin(), c->v.end(), [](const CandidateRec& a, const CandidateRec& b) { return a.score > b.score; });
+  });
+}
+
+int pbd_stage_pyramid(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c, size_t row_stride, size_t frame_stride) {
+  return guarded([&] {
+    REQUIRE(d && frames, "null argument");
+    Engine& e = *d->e;
+    e.set_frames_geometry(n, h, w, c);
+    e.upload_frames(frames, row_stride, frame_stride);
+    e.run_pyramid();
+  });
+}
+int pbd_stage_pdf(pbd_detector* d) { return guarded([&] { REQUIRE(d, "null argument"); d->e->run_pdf(); }); }
+int pbd_stage_dp_min(pbd_detector* d) { return guarded([&] { REQUIRE(d, "null argument"); d->e->run_dp_min(); }); }
+int pbd_stage_dp_argmin(pbd_detector* d, pbd_candidates** out) {
+  return guarded([&] {
+    REQUIRE(d && out, "null argument");
+    d->e->run_argmin();
+    auto cs = std::make_unique<pbd_candidates>();
+    d->e->collect(cs->v);
+    *out = cs.release();
+  });
+}
+
+int pbd_num_frames(const pbd_detector* d) { return d ? d->e->geom().n_frames : 0; }
+int pbd_num_levels(const pbd_detector* d) { return d ? d->e->geom().n_levels : 0; }
+int pbd_level_info(const pbd_detector* d, int level, int32_t* img_h, int32_t* img_w, int32_t* oh, int32_t* ow, float* scale) {
+  return guarded([&] {
+    REQUIRE(d && level >= 0 && level < d->e->geom().n_levels, "level out of range");
+    const LevelDesc& L = d->e->geom().lv[level];
+    if (img_h) *img_h = L.img_h;
+    if (img_w) *img_w = L.img_w;
+    if (oh) *oh = L.oh;
+    if (ow) *ow = L.ow;
+    if (scale) *scale = L.scale;
+  });
+}
+
+int pbd_get_pyramid_image(pbd_detector* d, int frame, int level, uint8_t* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_pyramid_image(frame, level, dst); }); }
+int pbd_get_features(pbd_detector* d, int frame, int level, float* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_features(frame, level, dst); }); }
+int pbd_get_response(pbd_detector* d, int frame, int level, int filter, float* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_response(frame, level, filter, dst); }); }
+int pbd_get_rootv(pbd_detector* d, int frame, int level, int component, float* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_rootv(frame, level, component, dst); }); }
+int pbd_get_rooti(pbd_detector* d, int frame, int level, int component, int32_t* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_rooti(frame, level, component, dst); }); }
+int pbd_get_backptr(pbd_detector* d, int frame, int level, int component, int part, int parent_mixture, int32_t* ix, int32_t* iy, int32_t* ik) {
+  return guarded([&] { REQUIRE(d && ix && iy && ik, "null argument"); d->e->get_backptr(frame, level, component, part, parent_mixture, ix, iy, ik); });
+}
+int pbd_set_levels(pbd_detector* d, int n_frames, int n_levels, const int32_t* ohow, const float* scales) {
+  return guarded([&] { REQUIRE(d && ohow && scales, "null argument"); d->e->set_levels_manual(n_frames, n_levels, ohow, scales); });
+}
+int pbd_set_features(pbd_detector* d, int frame, int level, const float* src) { return guarded([&] { REQUIRE(d && src, "null argument"); d->e->set_features(frame, level, src); }); }
+int pbd_set_response(pbd_detector* d, int frame, int level, int filter, const float* src) { return guarded([&] { REQUIRE(d && src, "null argument"); d->e->set_response(frame, level, filter, src); }); }
+
+static void cu(cudaError_t e, const char* what) { if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e)); }
+
+int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int w, const float* h_defw4, const int32_t* h_anchor_xy,
+                        float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode) {
+  return guarded([&] {
+    REQUIRE(d_in && h_defw4 && h_anchor_xy && d_out && d_ix && d_iy, "null argument");
+    REQUIRE(n_maps > 0 && h > 0 && w > 0 && h <= 4096 && w <= 4096, "map shape out of range (<= 4096)");
+    for (int i = 0; i < n_maps; ++i) REQUIRE(h_defw4[4 * i] > 0.f && h_defw4[4 * i + 2] > 0.f, "quadratic weights must be > 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t cells = (size_t)n_maps * h * w;
+    float *d_w = nullptr, *d_tmp = nullptr; int* d_a = nullptr; uint16_t *d_ixr = nullptr, *d_iyr = nullptr;
+    cu(cudaMalloc(&d_w, (size_t)n_maps * 4 * sizeof(float)), "cudaMalloc"); cu(cudaMalloc(&d_a, (size_t)n_maps * 2 * sizeof(int)), "cudaMalloc");
+    cu(cudaMalloc(&d_tmp, cells * sizeof(float)), "cudaMalloc"); cu(cudaMalloc(&d_ixr, cells * 2), "cudaMalloc"); cu(cudaMalloc(&d_iyr, cells * 2), "cudaMalloc");
+    cu(cudaMemcpyAsync(d_w, h_defw4, (size_t)n_maps * 4 * sizeof(float), cudaMemcpyHostToDevice, s), "H2D");
+    cu(cudaMemcpyAsync(d_a, h_anchor_xy, (size_t)n_maps * 2 * sizeof(int), cudaMemcpyHostToDevice, s), "H2D");
+    launch_dt2d_standalone(d_in, n_maps, h, w, d_w, d_a, d_tmp, d_out, d_ix, d_iy, d_ixr, d_iyr, backptr_mode, s);
+    cu(cudaGetLastError(), "dt2d launch");
+    cu(cudaStreamSynchronize(s), "dt2d sync");
+    cudaFree(d_w); cudaFree(d_a); cudaFree(d_tmp); cudaFree(d_ixr); cudaFree(d_iyr);
+  });
+}
+int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, float* out, int32_t* ix,
+                 int32_t* iy, int backptr_mode) {
+  return guarded([&] {
+    REQUIRE(in && out && ix && iy, "null argument");
+    const size_t cells = (size_t)n_maps * h * w;
+    float *d_in = nullptr, *d_out = nullptr; uint16_t *d_ix = nullptr, *d_iy = nullptr;
+    cu(cudaMalloc(&d_in, cells * 4), "cudaMalloc"); cu(cudaMalloc(&d_out, cells * 4), "cudaMalloc");
+    cu(cudaMalloc(&d_ix, cells * 2), "cudaMalloc"); cu(cudaMalloc(&d_iy, cells * 2), "cudaMalloc");
+    cu(cudaMemcpy(d_in, in, cells * 4, cudaMemcpyHostToDevice), "H2D");
+    const int rc = pbd_dt2d_f32_device(nullptr, d_in, n_maps, h, w, defw4, anchor_xy, d_out, d_ix, d_iy, backptr_mode);
+    std::vector<uint16_t> hx(cells), hy(cells);
+    if (rc == PBD_OK) {
+      cu(cudaMemcpy(out, d_out, cells * 4, cudaMemcpyDeviceToHost), "D2H");
+      cu(cudaMemcpy(hx.data(), d_ix, cells * 2, cudaMemcpyDeviceToHost), "D2H"); cu(cudaMemcpy(hy.data(), d_iy, cells * 2, cudaMemcpyDeviceToHost), "D2H");
+      for (size_t i = 0; i < cells; ++i) { ix[i] = hx[i]; iy[i] = hy[i]; }
+    }
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ix); cudaFree(d_iy);
+    if (rc != PBD_OK) throw CudaError(g_err);
+  });
+}
+
+long long pbd_launch_count(const pbd_detector* d) { return d ? d->e->launches() : 0; }
+int pbd_stage_times_ms(pbd_detector* d, float ms[6]) { return guarded([&] { REQUIRE(d && ms, "null argument"); d->e->stage_times(ms); }); }
+size_t pbd_device_bytes(const pbd_detector* d) { return d ? d->e->device_bytes() : 0; }
+
+}  // extern "C"

@@ -1,0 +1,576 @@
+// engine.cu -- see engine.hpp.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace pbd {
+
+namespace {
+inline int cv_round_f(float v) { return (int)lrintf(v); }          // cvRound: round half to even
+inline int cv_floor_f(float v) { int i = (int)v; return i - (i > v); }
+inline short sat_short(float v) { int i = cv_round_f(v); return (short)std::min(32767, std::max(-32768, i)); }
+}  // namespace
+
+// Level table of HOGFeatures<T>::pyramid (reference src/HOGFeatures.cpp:95-127, include/HOGFeatures.hpp:74-81)
+// and the per-level HOG sizes of features() (:174-176).  log/pow/floor resolve to the float overloads in the
+// reference (<cmath> + using namespace std), pow(float,int) promotes to double.
+int compute_pyramid_levels(int h, int w, int sbin, int interval, int max_levels, Geometry& g) {
+  const float sfactor = powf(2.0f, 1.0f / (float)interval);
+  const float fw = (float)w, fh = (float)h;
+  const float ns = 1 + floorf(logf(fminf(fh, fw) / (5.0f * (float)sbin)) / logf(sfactor));
+  int nscales = ns > 0 ? (int)ns : 0;
+  if (nscales > kMaxLevels) nscales = kMaxLevels;
+  std::vector<LevelDesc> lv(nscales);
+  for (auto& L : lv) { memset(&L, 0, sizeof(L)); }
+  for (int i = 0; i < interval && i < nscales; ++i) {
+    const float s = (float)(1.0f / pow((double)sfactor, i));
+    int cw = cv_round_f(fw * s), ch = cv_round_f(fh * s);
+    lv[i].img_w = cw; lv[i].img_h = ch; lv[i].scale = (float)(pow((double)sfactor, i) * sbin); lv[i].src_level = -1;
+    for (int j = i + interval; j < nscales; j += interval) {
+      cw = (cw + 1) / 2; ch = (ch + 1) / 2;
+      lv[j].img_w = cw; lv[j].img_h = ch; lv[j].scale = 2 * lv[j - interval].scale; lv[j].src_level = j - interval;
+    }
+  }
+  if (max_levels > 0 && nscales > max_levels) nscales = max_levels;
+  g.n_levels = nscales;
+  for (int l = 0; l < nscales; ++l) {
+    LevelDesc L = lv[l];
+    L.bw = (int)roundf((float)L.img_w / (float)sbin);
+    L.bh = (int)roundf((float)L.img_h / (float)sbin);
+    L.ow = std::max(L.bw - 2, 0);
+    L.oh = std::max(L.bh - 2, 0);
+    g.lv[l] = L;
+  }
+  return nscales;
+}
+
+void Engine::check_cuda(cudaError_t e, const char* what) const {
+  if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <typename T>
+void Engine::ensure(T*& p, size_t& cap, size_t n) {
+  if (n <= cap && p) return;
+  if (p) { check_cuda(cudaFree(p), "cudaFree"); dev_bytes_ -= cap * sizeof(T); p = nullptr; cap = 0; }
+  if (n == 0) n = 1;
+  check_cuda(cudaMalloc(&p, n * sizeof(T)), "cudaMalloc");
+  cap = n;
+  dev_bytes_ += n * sizeof(T);
+}
+
+Engine::Engine(const Model& m, int device, cudaStream_t stream) : thresh((double)m.thresh), model_(m), device_(device), stream_(stream) {
+  model_.validate();
+  if (model_.flen != 32 || model_.norient != 18) throw UnsupportedError("only flen=32 / norient=18 HOG models are supported");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) throw CudaError(std::string("no CUDA device available: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) throw ArgError("device index out of range");
+  check_cuda(cudaSetDevice(device), "cudaSetDevice");
+  build_tables();
+  check_cuda(cudaMalloc(&d_g_, sizeof(Geometry)), "cudaMalloc geometry");
+  check_cuda(cudaMalloc(&d_nhits_, sizeof(int)), "cudaMalloc nhits");
+  dev_bytes_ += sizeof(Geometry) + sizeof(int);
+  for (int i = 0; i < 7; ++i) { check_cuda(cudaEventCreate(&ev_[i]), "cudaEventCreate"); }
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  cudaStreamSynchronize(stream_);
+  void* ptrs[] = {d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
+                  d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.ixdt, b_.iyraw, b_.ik,
+                  b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_, d_rg_level_, d_rg_row0_,
+                  d_cg_level_, d_cg_col0_, d_hits_, d_nhits_, d_xym_, d_scratch_i_};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h_pinned_) cudaFreeHost(h_pinned_);
+  for (int i = 0; i < 7; ++i) if (ev_[i]) cudaEventDestroy(ev_[i]);
+}
+
+// Model -> device tables: filters (convertTo float, reference src/PartsBasedDetector.cpp:115-117), the DP job
+// list (reference Parts/ComponentPart indirection, include/Parts.hpp:103-189) and the backtrack tables.
+void Engine::build_tables() {
+  const Model& m = model_;
+  const int nf = m.nfilters();
+  // ---- filters ----
+  fb_.nfilters = nf; fb_.flen = m.flen;
+  fb_.uniform = 1; fb_.kh = m.frows[0]; fb_.kw = m.fkw[0]; fb_.khm = 0; fb_.kwm = 0;
+  for (int i = 0; i < nf; ++i) {
+    if (m.frows[i] != fb_.kh || m.fkw[i] != fb_.kw) fb_.uniform = 0;
+    fb_.khm = std::max(fb_.khm, m.frows[i]); fb_.kwm = std::max(fb_.kwm, m.fkw[i]);
+  }
+  fb_.ngroups = (nf + 7) / 8;
+  // generic layout [f][c][ky][kx]
+  std::vector<int> foff(nf), fkh(nf), fkw(nf);
+  size_t tot = 0;
+  for (int i = 0; i < nf; ++i) { foff[i] = (int)tot; fkh[i] = m.frows[i]; fkw[i] = m.fkw[i]; tot += (size_t)m.frows[i] * m.fkw[i] * m.flen; }
+  std::vector<float> wg(tot);
+  for (int i = 0; i < nf; ++i) {
+    const int kh = fkh[i], kw = fkw[i];
+    for (int ky = 0; ky < kh; ++ky) for (int kx = 0; kx < kw; ++kx) for (int c = 0; c < m.flen; ++c)
+      wg[foff[i] + ((size_t)c * kh + ky) * kw + kx] = (float)m.filters[i][((size_t)ky * kw + kx) * m.flen + c];
+  }
+  check_cuda(cudaMalloc(&d_wgeneric_, std::max<size_t>(tot, 1) * sizeof(float)), "cudaMalloc filters");
+  check_cuda(cudaMemcpy(d_wgeneric_, wg.data(), tot * sizeof(float), cudaMemcpyHostToDevice), "upload filters");
+  check_cuda(cudaMalloc(&d_foff_, nf * sizeof(int)), "cudaMalloc"); check_cuda(cudaMalloc(&d_fkh_, nf * sizeof(int)), "cudaMalloc");
+  check_cuda(cudaMalloc(&d_fkw_, nf * sizeof(int)), "cudaMalloc");
+  check_cuda(cudaMemcpy(d_foff_, foff.data(), nf * sizeof(int), cudaMemcpyHostToDevice), "upload");
+  check_cuda(cudaMemcpy(d_fkh_, fkh.data(), nf * sizeof(int), cudaMemcpyHostToDevice), "upload");
+  check_cuda(cudaMemcpy(d_fkw_, fkw.data(), nf * sizeof(int), cudaMemcpyHostToDevice), "upload");
+  dev_bytes_ += tot * sizeof(float) + 3 * nf * sizeof(int);
+  fb_.wg = d_wgeneric_; fb_.foff = d_foff_; fb_.fkh = d_fkh_; fb_.fkw = d_fkw_;
+  if (fb_.uniform) {   // packed layout [group][c][ky][kx][8]
+    const int kh = fb_.kh, kw = fb_.kw, taps = kh * kw;
+    std::vector<float> wp((size_t)fb_.ngroups * m.flen * taps * 8, 0.f);
+    for (int i = 0; i < nf; ++i) {
+      const int gq = i / 8, j = i % 8;
+      for (int c = 0; c < m.flen; ++c) for (int t = 0; t < taps; ++t)
+        wp[(((size_t)gq * m.flen + c) * taps + t) * 8 + j] = (float)m.filters[i][(size_t)t * m.flen + c];
+    }
+    check_cuda(cudaMalloc(&d_wpacked_, wp.size() * sizeof(float)), "cudaMalloc packed filters");
+    check_cuda(cudaMemcpy(d_wpacked_, wp.data(), wp.size() * sizeof(float), cudaMemcpyHostToDevice), "upload packed filters");
+    dev_bytes_ += wp.size() * sizeof(float);
+    fb_.w = d_wpacked_;
+  }
+  // ---- DP slots ----
+  const int ncomp = m.ncomponents();
+  h_parent_.assign((size_t)ncomp * kMaxParts, -1);
+  h_nparts_.assign(ncomp, 0);
+  h_cm_slot_.assign((size_t)ncomp * kMaxParts * kMaxMix, 0);
+  h_pm_slot_.assign((size_t)ncomp * kMaxParts * kMaxMix, 0);
+  std::vector<std::vector<std::vector<int>>> work_slot(ncomp);   // [c][p][m] or -1 (leaf)
+  nwork_ = ncm_ = npm_ = 0; max_parts_ = 0;
+  for (int c = 0; c < ncomp; ++c) {
+    const auto& parts = m.comps[c];
+    const int np = (int)parts.size();
+    if (np > kMaxParts) throw UnsupportedError("component has more parts than kMaxParts");
+    max_parts_ = std::max(max_parts_, np);
+    h_nparts_[c] = np;
+    std::vector<char> has_child(np, 0);
+    for (int p = 1; p < np; ++p) has_child[parts[p].parentid] = 1;
+    work_slot[c].resize(np);
+    for (int p = 0; p < np; ++p) {
+      const int nm = (int)parts[p].filterid.size();
+      if (nm > kMaxMix) throw UnsupportedError("part has more mixtures than kMaxMix");
+      h_parent_[(size_t)c * kMaxParts + p] = parts[p].parentid;
+      work_slot[c][p].assign(nm, -1);
+      if (has_child[p]) for (int mi = 0; mi < nm; ++mi) work_slot[c][p][mi] = nwork_++;
+      if (p > 0) {
+        for (int mi = 0; mi < nm; ++mi) h_cm_slot_[((size_t)c * kMaxParts + p) * kMaxMix + mi] = ncm_++;
+        const int pn = (int)parts[parts[p].parentid].filterid.size();
+        for (int pm = 0; pm < pn; ++pm) h_pm_slot_[((size_t)c * kMaxParts + p) * kMaxMix + pm] = npm_++;
+      }
+    }
+  }
+  // ---- jobs by wave: wave k holds part (np_c - 1 - k) of every component that still has one ----
+  jobs_.clear(); wave_first_.clear(); wave_count_.clear();
+  tmp_maps_ = 0;
+  for (int k = 0; k < max_parts_ - 1; ++k) {
+    wave_first_.push_back((int)jobs_.size());
+    int cnt = 0;
+    std::vector<std::vector<char>> dummy;
+    for (int c = 0; c < ncomp; ++c) {
+      const auto& parts = m.comps[c];
+      const int np = (int)parts.size();
+      const int p = np - 1 - k;
+      if (p < 1) continue;
+      const Part& P = parts[p];
+      const Part& Par = parts[P.parentid];
+      PartJob J;
+      memset(&J, 0, sizeof(J));
+      J.nmix = (int)P.filterid.size(); J.pnmix = (int)Par.filterid.size();
+      bool first_touch = true;                       // is p the highest-index child of its parent?
+      for (int q = p + 1; q < np; ++q) if (parts[q].parentid == P.parentid) first_touch = false;
+      J.first_touch = first_touch ? 1 : 0;
+      for (int mm = 0; mm < J.nmix; ++mm) {
+        const int ws = work_slot[c][p][mm];
+        J.in_is_work[mm] = ws >= 0; J.in_slot[mm] = ws >= 0 ? ws : P.filterid[mm];
+        const int did = P.defid[mm];
+        for (int t = 0; t < 4; ++t) J.w[mm][t] = m.defs[(size_t)did * 4 + t];
+        J.ax[mm] = m.anchors[did * 2]; J.ay[mm] = m.anchors[did * 2 + 1];
+        J.cm_slot[mm] = h_cm_slot_[((size_t)c * kMaxParts + p) * kMaxMix + mm];
+        for (int pm = 0; pm < J.pnmix; ++pm) J.bias[mm][pm] = m.biasw[P.biasid[mm] + pm];   // T4: flat indexing
+      }
+      for (int pm = 0; pm < J.pnmix; ++pm) {
+        J.out_work_slot[pm] = work_slot[c][P.parentid][pm];
+        J.out_resp_fid[pm] = Par.filterid[pm];
+        J.pm_slot[pm] = h_pm_slot_[((size_t)c * kMaxParts + p) * kMaxMix + pm];
+      }
+      J.tmp_base = cnt * kMaxMix;
+      jobs_.push_back(J);
+      ++cnt;
+    }
+    wave_count_.push_back(cnt);
+    tmp_maps_ = std::max(tmp_maps_, cnt * kMaxMix);
+  }
+  roots_.clear();
+  for (int c = 0; c < ncomp; ++c) {
+    const Part& R = m.comps[c][0];
+    RootJob J;
+    memset(&J, 0, sizeof(J));
+    J.nmix = (int)R.filterid.size();
+    for (int mi = 0; mi < J.nmix; ++mi) { const int ws = work_slot[c][0][mi]; J.in_is_work[mi] = ws >= 0; J.in_slot[mi] = ws >= 0 ? ws : R.filterid[mi]; }
+    J.bias = m.biasw[R.biasid[0]];
+    roots_.push_back(J);
+  }
+  auto up = [&](auto*& d, const auto& h) {
+    using T = std::remove_reference_t<decltype(h[0])>;
+    const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    check_cuda(cudaMalloc(&d, bytes), "cudaMalloc table");
+    if (!h.empty()) check_cuda(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice), "upload table");
+    dev_bytes_ += bytes;
+  };
+  up(d_jobs_, jobs_); up(d_roots_, roots_); up(d_parent_, h_parent_); up(d_nparts_, h_nparts_); up(d_cm_slot_, h_cm_slot_); up(d_pm_slot_, h_pm_slot_);
+}
+
+void Engine::need(int stage, const char* who) const {
+  if (stage_ < stage) throw StateError(std::string(who) + ": previous stage has not been run for the current batch");
+}
+
+void Engine::set_frames_geometry(int n, int h, int w, int c) {
+  if (n <= 0 || h <= 0 || w <= 0) throw ArgError("bad frame batch shape");
+  if (c != 1 && c != 3) throw UnsupportedError("frames must have 1 or 3 channels (reference src/HOGFeatures.cpp:171)");
+  if (have_images_ && g_.n_frames == n && g_.in_h == h && g_.in_w == w && g_.in_c == c && stage_ >= 1) {
+    const int nl = g_.n_levels;
+    Geometry probe{};
+    compute_pyramid_levels(h, w, model_.sbin, model_.interval, max_levels, probe);
+    if (probe.n_levels == nl) { stage_ = 1; return; }          // same geometry: keep buffers and tables
+  }
+  Geometry g{};
+  g.n_frames = n; g.in_h = h; g.in_w = w; g.in_c = c;
+  compute_pyramid_levels(h, w, model_.sbin, model_.interval, max_levels, g);
+  if (g.n_levels <= 0) throw ArgError("image too small for one pyramid level (min(h,w) < 5*sbin)");
+  long long img_off = 0; int block_off = 0, cell_off = 0, xo = 0, yo = 0;
+  for (int l = 0; l < g.n_levels; ++l) {
+    LevelDesc& L = g.lv[l];
+    if (L.img_h < 3 || L.img_w < 3) throw ArgError("pyramid level smaller than 3 pixels");
+    L.img_off = img_off; img_off += (long long)L.img_w * L.img_h * c;
+    img_off = (img_off + 15) / 16 * 16;
+    L.block_off = block_off; block_off += L.bw * L.bh;
+    L.cell_off = cell_off; cell_off += L.ow * L.oh;
+    if (L.src_level < 0) { L.xofs_off = xo; L.yofs_off = yo; xo += L.img_w; yo += L.img_h; }
+  }
+  g.img_bytes = img_off; g.blocks_total = block_off; g.cells_total = cell_off;
+  g_ = g;
+  have_images_ = true;
+  // resize coefficient tables, built exactly as cv::resize() does for INTER_LINEAR / 8U (fixed point, 11 bits)
+  std::vector<int> xofs(std::max(xo, 1)), yofs(std::max(yo, 1));
+  std::vector<short> xalpha((size_t)std::max(xo, 1) * 2), ybeta((size_t)std::max(yo, 1) * 2);
+  for (int l = 0; l < g.n_levels; ++l) {
+    const LevelDesc& L = g.lv[l];
+    if (L.src_level >= 0) continue;
+    const double scale_x = 1. / ((double)L.img_w / w), scale_y = 1. / ((double)L.img_h / h);
+    for (int dx = 0; dx < L.img_w; ++dx) {
+      float fx = (float)((dx + 0.5) * scale_x - 0.5);
+      int sx = cv_floor_f(fx);
+      fx -= sx;
+      if (sx < 0) { fx = 0; sx = 0; }
+      if (sx >= w - 1) { fx = 0; sx = w - 1; }
+      xofs[L.xofs_off + dx] = sx;
+      xalpha[2 * (size_t)(L.xofs_off + dx)] = sat_short((1.f - fx) * 2048.f);
+      xalpha[2 * (size_t)(L.xofs_off + dx) + 1] = sat_short(fx * 2048.f);
+    }
+    for (int dy = 0; dy < L.img_h; ++dy) {
+      float fy = (float)((dy + 0.5) * scale_y - 0.5);
+      int sy = cv_floor_f(fy);
+      fy -= sy;
+      yofs[L.yofs_off + dy] = sy;
+      ybeta[2 * (size_t)(L.yofs_off + dy)] = sat_short((1.f - fy) * 2048.f);
+      ybeta[2 * (size_t)(L.yofs_off + dy) + 1] = sat_short(fy * 2048.f);
+    }
+  }
+  ensure(d_xofs_, cap_xofs_, xofs.size()); ensure(d_yofs_, cap_yofs_, yofs.size());
+  ensure(d_xalpha_, cap_xalpha_, xalpha.size()); ensure(d_ybeta_, cap_ybeta_, ybeta.size());
+  check_cuda(cudaMemcpyAsync(d_xofs_, xofs.data(), xofs.size() * sizeof(int), cudaMemcpyHostToDevice, stream_), "upload xofs");
+  check_cuda(cudaMemcpyAsync(d_yofs_, yofs.data(), yofs.size() * sizeof(int), cudaMemcpyHostToDevice, stream_), "upload yofs");
+  check_cuda(cudaMemcpyAsync(d_xalpha_, xalpha.data(), xalpha.size() * sizeof(short), cudaMemcpyHostToDevice, stream_), "upload xalpha");
+  check_cuda(cudaMemcpyAsync(d_ybeta_, ybeta.data(), ybeta.size() * sizeof(short), cudaMemcpyHostToDevice, stream_), "upload ybeta");
+  check_cuda(cudaStreamSynchronize(stream_), "sync tables");     // host vectors go out of scope
+  build_batch_tables();
+  alloc_batch();
+  stage_ = 1;
+}
+
+void Engine::set_levels_manual(int n, int nlevels, const int32_t* ohow, const float* scales) {
+  if (n <= 0 || nlevels <= 0 || nlevels > kMaxLevels) throw ArgError("bad level table");
+  Geometry g{};
+  g.n_frames = n; g.n_levels = nlevels; g.in_c = 3;
+  int block_off = 0, cell_off = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    LevelDesc& L = g.lv[l];
+    L.oh = ohow[2 * l]; L.ow = ohow[2 * l + 1];
+    if (L.oh <= 0 || L.ow <= 0) throw ArgError("level with no cells");
+    L.bh = L.oh + 2; L.bw = L.ow + 2; L.scale = scales[l]; L.src_level = -1;
+    L.block_off = block_off; block_off += L.bw * L.bh;
+    L.cell_off = cell_off; cell_off += L.ow * L.oh;
+  }
+  g.blocks_total = block_off; g.cells_total = cell_off; g.img_bytes = 0;
+  g_ = g;
+  have_images_ = false;
+  build_batch_tables();
+  alloc_batch();
+  stage_ = 1;
+}
+
+void Engine::build_batch_tables() {
+  const Geometry& g = g_;
+  max_ow_ = max_oh_ = 0;
+  for (int l = 0; l < g.n_levels; ++l) { max_ow_ = std::max(max_ow_, g.lv[l].ow); max_oh_ = std::max(max_oh_, g.lv[l].oh); }
+  if (max_ow_ > kMaxDim || max_oh_ > kMaxDim) throw UnsupportedError("pyramid level larger than 1024 cells in one dimension");
+  int tx, ty;
+  response_tile_dims(response_has_fast_path(fb_) ? 1 : 0, &tx, &ty);
+  std::vector<int> tl, tf(g.n_levels), rgl, rgr, cgl, cgc;
+  for (int l = 0; l < g.n_levels; ++l) {
+    const LevelDesc& L = g.lv[l];
+    tf[l] = (int)tl.size();
+    const int nt = ((L.oh + ty - 1) / ty) * ((L.ow + tx - 1) / tx);
+    for (int i = 0; i < nt; ++i) tl.push_back(l);
+    for (int r = 0; r < L.oh; r += 32) { rgl.push_back(l); rgr.push_back(r); }
+    for (int c = 0; c < L.ow; c += 32) { cgl.push_back(l); cgc.push_back(c); }
+  }
+  ntiles_ = (int)tl.size(); nrg_ = (int)rgl.size(); ncg_ = (int)cgl.size();
+  auto up = [&](int*& d, size_t& cap, const std::vector<int>& h) {
+    ensure(d, cap, h.size());
+    if (!h.empty()) check_cuda(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, stream_), "upload batch table");
+  };
+  up(d_tile_level_, cap_tile_level_, tl); up(d_tile_first_, cap_tile_first_, tf);
+  up(d_rg_level_, cap_rg_level_, rgl); up(d_rg_row0_, cap_rg_row0_, rgr);
+  up(d_cg_level_, cap_cg_level_, cgl); up(d_cg_col0_, cap_cg_col0_, cgc);
+  check_cuda(cudaMemcpyAsync(d_g_, &g_, sizeof(Geometry), cudaMemcpyHostToDevice, stream_), "upload geometry");
+  check_cuda(cudaStreamSynchronize(stream_), "sync batch tables");
+}
+
+void Engine::alloc_batch() {
+  const Geometry& g = g_;
+  const size_t n = g.n_frames, ct = g.cells_total, bt = g.blocks_total;
+  const int ncomp = model_.ncomponents();
+  if (have_images_) {
+    ensure(b_.pyr, cap_pyr_, n * (size_t)g.img_bytes);
+    ensure(b_.hist, cap_hist_, n * bt * 18);
+    ensure(b_.norm, cap_norm_, n * bt);
+  }
+  ensure(b_.feat, cap_feat_, n * ct * 32);
+  ensure(b_.resp, cap_resp_, n * ct * model_.nfilters());
+  ensure(b_.work, cap_work_, n * ct * std::max(nwork_, 1));
+  ensure(b_.tmp, cap_tmp_, n * ct * std::max(tmp_maps_, 1));
+  ensure(b_.ixdt, cap_ixdt_, n * ct * std::max(ncm_, 1));
+  ensure(b_.iyraw, cap_iyraw_, n * ct * std::max(ncm_, 1));
+  ensure(b_.ik, cap_ik_, n * ct * std::max(npm_, 1));
+  ensure(b_.rootv, cap_rootv_, n * ct * ncomp);
+  ensure(b_.rooti, cap_rooti_, n * ct * ncomp);
+  ensure(d_hits_, cap_hits_, (size_t)max_candidates);
+  ensure(d_xym_, cap_xym_, (size_t)max_candidates * 3 * kMaxParts);
+}
+
+void Engine::upload_frames(const uint8_t* frames, size_t row_stride, size_t frame_stride) {
+  need(1, "upload_frames");
+  if (!have_images_) throw StateError("upload_frames: batch was defined by pbd_set_levels");
+  const size_t row = (size_t)g_.in_w * g_.in_c, fb = row * g_.in_h;
+  if (row_stride == 0) row_stride = row;
+  if (frame_stride == 0) frame_stride = row_stride * g_.in_h;
+  ensure(d_frames_own_, cap_frames_, fb * g_.n_frames);
+  if (timing) { check_cuda(cudaEventRecord(ev_[0], stream_), "event"); ev_valid_[0] = true; }
+  if (row_stride == row && frame_stride == fb) {
+    check_cuda(cudaMemcpyAsync(d_frames_own_, frames, fb * g_.n_frames, cudaMemcpyHostToDevice, stream_), "H2D frames");
+  } else {
+    for (int i = 0; i < g_.n_frames; ++i)
+      check_cuda(cudaMemcpy2DAsync(d_frames_own_ + fb * i, row, frames + frame_stride * i, row_stride, row, g_.in_h,
+                                   cudaMemcpyHostToDevice, stream_), "H2D frames (strided)");
+  }
+  b_.frames = d_frames_own_;
+}
+
+void Engine::use_device_frames(const uint8_t* d_frames) {
+  need(1, "use_device_frames");
+  if (timing) { check_cuda(cudaEventRecord(ev_[0], stream_), "event"); ev_valid_[0] = true; }
+  b_.frames = d_frames;
+}
+
+void Engine::run_pyramid() {
+  need(1, "pyramid");
+  if (!have_images_ || !b_.frames) throw StateError("pyramid: no frames");
+  if (timing) { check_cuda(cudaEventRecord(ev_[1], stream_), "event"); ev_valid_[1] = true; }
+  launches_ += launch_pyramid(g_, d_g_, b_, d_xofs_, d_xalpha_, d_yofs_, d_ybeta_, model_.interval, stream_);
+  if (timing) { check_cuda(cudaEventRecord(ev_[2], stream_), "event"); ev_valid_[2] = true; }
+  launches_ += launch_hog(g_, d_g_, b_, model_.sbin, stream_);
+  check_cuda(cudaGetLastError(), "pyramid/HOG launch");
+  stage_ = 2;
+}
+
+void Engine::run_pdf() {
+  need(2, "pdf");
+  if (timing) { check_cuda(cudaEventRecord(ev_[3], stream_), "event"); ev_valid_[3] = true; }
+  launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles_, exact, stream_);
+  check_cuda(cudaGetLastError(), "response launch");
+  stage_ = 3;
+}
+
+void Engine::run_dp_min() {
+  need(3, "dp_min");
+  if (timing) { check_cuda(cudaEventRecord(ev_[4], stream_), "event"); ev_valid_[4] = true; }
+  const int nf = model_.nfilters();
+  for (size_t wv = 0; wv < wave_first_.size(); ++wv) {
+    if (wave_count_[wv] == 0) continue;
+    const PartJob* dj = d_jobs_ + wave_first_[wv];
+    launches_ += launch_dt_rows_tab(g_, d_g_, b_, d_rg_level_, d_rg_row0_, nrg_, max_ow_, dj, wave_count_[wv], nf, nwork_, ncm_, tmp_maps_, stream_);
+    launches_ += launch_dt_cols_tab(g_, d_g_, b_, d_cg_level_, d_cg_col0_, ncg_, max_oh_, dj, wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, stream_);
+  }
+  // root scores (reference computes rootv/rooti at the end of min(), src/DynamicProgram.cpp:163-171)
+  launches_ += launch_root(g_, d_g_, b_, d_roots_, model_.ncomponents(), nf, nwork_, 0.f, nullptr, nullptr, 0, stream_);
+  check_cuda(cudaGetLastError(), "DP launch");
+  stage_ = 4;
+}
+
+void Engine::run_argmin() {
+  need(4, "argmin");
+  if (timing) { check_cuda(cudaEventRecord(ev_[5], stream_), "event"); ev_valid_[5] = true; }
+  ensure(d_hits_, cap_hits_, (size_t)max_candidates);
+  ensure(d_xym_, cap_xym_, (size_t)max_candidates * 3 * kMaxParts);
+  check_cuda(cudaMemsetAsync(d_nhits_, 0, sizeof(int), stream_), "memset nhits");
+  launches_ += launch_hits(g_, d_g_, b_, model_.ncomponents(), (float)thresh, d_hits_, d_nhits_, max_candidates, stream_);
+  BacktrackTables t{d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_};
+  launches_ += launch_backtrack(g_, d_g_, b_, t, model_.ncomponents(), ncm_, npm_, d_hits_, d_nhits_, max_candidates, backptr, d_xym_, stream_);
+  check_cuda(cudaGetLastError(), "argmin launch");
+  if (timing) { check_cuda(cudaEventRecord(ev_[6], stream_), "event"); ev_valid_[6] = true; }
+  stage_ = 5;
+}
+
+void Engine::collect(std::vector<CandidateRec>& out) {
+  need(5, "collect");
+  int nh = 0;
+  check_cuda(cudaMemcpyAsync(&nh, d_nhits_, sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H nhits");
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+  if (nh > max_candidates)
+    throw StateError("candidate buffer overflow: " + std::to_string(nh) + " hits > max_candidates=" + std::to_string(max_candidates));
+  std::vector<Hit> hits(nh);
+  std::vector<int> xym((size_t)nh * 3 * kMaxParts);
+  if (nh) {
+    check_cuda(cudaMemcpyAsync(hits.data(), d_hits_, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, stream_), "D2H hits");
+    check_cuda(cudaMemcpyAsync(xym.data(), d_xym_, xym.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H parts");
+    check_cuda(cudaStreamSynchronize(stream_), "sync");
+  }
+  // the reference's deterministic (single-threaded) order: frame, level, component, row-major hit
+  std::vector<int> order(nh);
+  for (int i = 0; i < nh; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    const Hit &A = hits[a], &B = hits[b];
+    if (A.frame != B.frame) return A.frame < B.frame;
+    if (A.level != B.level) return A.level < B.level;
+    if (A.comp != B.comp) return A.comp < B.comp;
+    if (A.y != B.y) return A.y < B.y;
+    return A.x < B.x;
+  });
+  out.clear();
+  out.reserve(nh);
+  for (int oi = 0; oi < nh; ++oi) {
+    const int i = order[oi];
+    const Hit& H = hits[i];
+    const auto& parts = model_.comps[H.comp];
+    const int np = (int)parts.size();
+    CandidateRec C;
+    C.frame = H.frame; C.level = H.level; C.component = H.comp; C.score = H.score;
+    const int* xs = xym.data() + (size_t)i * 3 * kMaxParts;
+    C.x.assign(xs, xs + np); C.y.assign(xs + kMaxParts, xs + kMaxParts + np); C.m.assign(xs + 2 * kMaxParts, xs + 2 * kMaxParts + np);
+    const float scale = g_.lv[H.level].scale;
+    C.rect.resize((size_t)np * 4);
+    for (int p = 0; p < np; ++p) {                  // reference src/DynamicProgram.cpp:238-244
+      const int ks = model_.frows[parts[p].filterid[C.m[p]]];          // xsize == ysize == rows (Parts.hpp:185-187)
+      const int x1 = cv_round_f((float)(C.x[p] - 1) * scale), y1 = cv_round_f((float)(C.y[p] - 1) * scale);
+      const int sz = cv_round_f((float)ks * scale);
+      const int x2 = x1 + sz - 1, y2 = y1 + sz - 1;
+      const int rx = std::min(x1, x2), ry = std::min(y1, y2);
+      C.rect[4 * p] = rx; C.rect[4 * p + 1] = ry; C.rect[4 * p + 2] = std::max(x1, x2) - rx; C.rect[4 * p + 3] = std::max(y1, y2) - ry;
+    }
+    out.push_back(std::move(C));
+  }
+}
+
+static void check_idx(bool ok, const char* what) { if (!ok) throw ArgError(std::string(what) + ": index out of range"); }
+
+void Engine::get_pyramid_image(int frame, int level, uint8_t* dst) {
+  need(2, "get_pyramid_image");
+  if (!have_images_) throw StateError("no pyramid images in a manually defined batch");
+  check_idx(frame >= 0 && frame < g_.n_frames && level >= 0 && level < g_.n_levels, "get_pyramid_image");
+  const LevelDesc& L = g_.lv[level];
+  check_cuda(cudaMemcpyAsync(dst, b_.pyr + (size_t)frame * g_.img_bytes + L.img_off, (size_t)L.img_w * L.img_h * g_.in_c,
+                             cudaMemcpyDeviceToHost, stream_), "D2H image");
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+}
+void Engine::get_features(int frame, int level, float* dst) {
+  need(2, "get_features");
+  check_idx(frame >= 0 && frame < g_.n_frames && level >= 0 && level < g_.n_levels, "get_features");
+  const LevelDesc& L = g_.lv[level];
+  check_cuda(cudaMemcpyAsync(dst, b_.feat + ((size_t)frame * g_.cells_total + L.cell_off) * 32, (size_t)L.oh * L.ow * 32 * sizeof(float),
+                             cudaMemcpyDeviceToHost, stream_), "D2H features");
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+}
+void Engine::get_response(int frame, int level, int filter, float* dst) {
+  need(3, "get_response");
+  check_idx(frame >= 0 && frame < g_.n_frames && level >= 0 && level < g_.n_levels && filter >= 0 && filter < model_.nfilters(), "get_response");
+  const LevelDesc& L = g_.lv[level];
+  check_cuda(cudaMemcpyAsync(dst, b_.resp + ((size_t)frame * model_.nfilters() + filter) * g_.cells_total + L.cell_off,
+                             (size_t)L.oh * L.ow * sizeof(float), cudaMemcpyDeviceToHost, stream_), "D2H response");
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+}
+void Engine::get_rootv(int frame, int level, int comp, float* dst) {
+  need(4, "get_rootv");
+  check_idx(frame >= 0 && frame < g_.n_frames && level >= 0 && level < g_.n_levels && comp >= 0 && comp < model_.ncomponents(), "get_rootv");
+  const LevelDesc& L = g_.lv[level];
+  check_cuda(cudaMemcpyAsync(dst, b_.rootv + ((size_t)frame * model_.ncomponents() + comp) * g_.cells_total + L.cell_off,
+                             (size_t)L.oh * L.ow * sizeof(float), cudaMemcpyDeviceToHost, stream_), "D2H rootv");
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+}
+void Engine::get_rooti(int frame, int level, int comp, int32_t* dst) {
+  need(4, "get_rooti");
+  check_idx(frame >= 0 && frame < g_.n_frames && level >= 0 && level < g_.n_levels && comp >= 0 && comp < model_.ncomponents(), "get_rooti");
+  const LevelDesc& L = g_.lv[level];
+  std::vector<uint8_t> tmp((size_t)L.oh * L.ow);
+  check_cuda(cudaMemcpyAsync(tmp.data(), b_.rooti + ((size_t)frame * model_.ncomponents() + comp) * g_.cells_total + L.cell_off, tmp.size(),
+                             cudaMemcpyDeviceToHost, stream_), "D2H rooti");
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+  for (size_t i = 0; i < tmp.size(); ++i) dst[i] = tmp[i];
+}
+void Engine::get_backptr(int frame, int level, int comp, int part, int pm, int32_t* ix, int32_t* iy, int32_t* ik) {
+  need(4, "get_backptr");
+  check_idx(frame >= 0 && frame < g_.n_frames && level >= 0 && level < g_.n_levels && comp >= 0 && comp < model_.ncomponents(), "get_backptr");
+  const auto& parts = model_.comps[comp];
+  check_idx(part >= 1 && part < (int)parts.size(), "get_backptr(part)");
+  check_idx(pm >= 0 && pm < (int)parts[parts[part].parentid].filterid.size(), "get_backptr(parent mixture)");
+  const LevelDesc& L = g_.lv[level];
+  const size_t n = (size_t)L.oh * L.ow;
+  ensure(d_scratch_i_, cap_scratch_i_, 3 * n);
+  launches_ += launch_expand_backptr(g_, b_, frame, level, ncm_, npm_, d_cm_slot_ + ((size_t)comp * kMaxParts + part) * kMaxMix,
+                                     h_pm_slot_[((size_t)comp * kMaxParts + part) * kMaxMix + pm], backptr, d_scratch_i_, d_scratch_i_ + n,
+                                     d_scratch_i_ + 2 * n, stream_);
+  check_cuda(cudaMemcpyAsync(ix, d_scratch_i_, n * sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H ix");
+  check_cuda(cudaMemcpyAsync(iy, d_scratch_i_ + n, n * sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H iy");
+  check_cuda(cudaMemcpyAsync(ik, d_scratch_i_ + 2 * n, n * sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H ik");
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+}
+void Engine::set_features(int frame, int level, const float* src) {
+  need(1, "set_features");
+  check_idx(frame >= 0 && frame < g_.n_frames && level >= 0 && level < g_.n_levels, "set_features");
+  const LevelDesc& L = g_.lv[level];
+  check_cuda(cudaMemcpyAsync(b_.feat + ((size_t)frame * g_.cells_total + L.cell_off) * 32, src, (size_t)L.oh * L.ow * 32 * sizeof(float),
+                             cudaMemcpyHostToDevice, stream_), "H2D features");
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+  stage_ = std::max(stage_, 2);
+}
+void Engine::set_response(int frame, int level, int filter, const float* src) {
+  need(1, "set_response");
+  check_idx(frame >= 0 && frame < g_.n_frames && level >= 0 && level < g_.n_levels && filter >= 0 && filter < model_.nfilters(), "set_response");
+  const LevelDesc& L = g_.lv[level];
+  check_cuda(cudaMemcpyAsync(b_.resp + ((size_t)frame * model_.nfilters() + filter) * g_.cells_total + L.cell_off, src,
+                             (size_t)L.oh * L.ow * sizeof(float), cudaMemcpyHostToDevice, stream_), "H2D response");
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+  stage_ = std::max(stage_, 3);
+}
+
+void Engine::stage_times(float ms[6]) {
+  for (int i = 0; i < 6; ++i) ms[i] = 0.f;
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+  for (int i = 0; i < 6; ++i)
+    if (ev_valid_[i] && ev_valid_[i + 1]) check_cuda(cudaEventElapsedTime(&ms[i], ev_[i], ev_[i + 1]), "event elapsed");
+}
+
+}  // namespace pbd

@@ -1,0 +1,181 @@
+// hog.cu -- HOGFeatures<float>::features<uint8_t> (reference src/HOGFeatures.cpp:168-341) as two kernels.
+//
+// hog_hist   one thread per HOG block (by,bx): gathers the (2*sbin)^2 pixel window that scatters into this
+//            block in the reference (bilinear scatter, :252-265), visiting pixels in raster order and adding
+//            the matching-orientation term with a separately rounded multiply and add.  Because every
+//            histogram bin receives its terms in the same order as the reference's sequential scatter,
+//            the float sums are bit-identical (no atomics, deterministic).  Also emits the block energy (:270-283).
+// hog_feat   one thread per output cell: 4 normalisers with double sqrt/divide (:292-299), 18 contrast-
+//            sensitive + 9 insensitive + 4 texture + 1 truncation features (:304-338), written HWC.
+// Both are HBM/L2-bound streaming kernels (48 B of image read and 128 B written per cell).
+#include "kernels.cuh"
+
+namespace pbd {
+namespace {
+
+__device__ __forceinline__ int find_level_by_block(const Geometry* g, int idx) {
+  int l = 0;
+  while (l + 1 < g->n_levels && idx >= g->lv[l + 1].block_off) ++l;
+  return l;
+}
+__device__ __forceinline__ int find_level_by_cell(const Geometry* g, int idx) {
+  int l = 0;
+  while (l + 1 < g->n_levels && idx >= g->lv[l + 1].cell_off) ++l;
+  return l;
+}
+
+template <int CN>
+__global__ void __launch_bounds__(128) hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr,
+                                                float* __restrict__ hist, float* __restrict__ norm, int sbin) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g->blocks_total) return;
+  const int frame = blockIdx.y;
+  const int l = find_level_by_block(g, idx);
+  const LevelDesc& L = g->lv[l];
+  const int local = idx - L.block_off;
+  const int bx = local % L.bw, by = local / L.bw;
+  const int cols = L.img_w, rows = L.img_h;
+  const int vis_w = L.bw * sbin, vis_h = L.bh * sbin;
+  const uint8_t* im = pyr + (size_t)frame * g->img_bytes + L.img_off;
+  const size_t stride = (size_t)cols * CN;
+
+  const float uu[9] = {(float)1.000, (float)0.9397, (float)0.7660, (float)0.5000, (float)0.1736,
+                       (float)-0.1736, (float)-0.5000, (float)-0.7660, (float)-0.9397};
+  const float vv[9] = {(float)0.000, (float)0.3420, (float)0.6428, (float)0.8660, (float)0.9848,
+                       (float)0.9848, (float)0.8660, (float)0.6428, (float)0.3420};
+  float h[18];
+#pragma unroll
+  for (int o = 0; o < 18; ++o) h[o] = 0.f;
+
+  // pixels with floor((p+0.5)/sbin - 0.5) in {b-1, b}; generous bounds, exact membership test below
+  const int y_lo = max(1, by * sbin - (sbin + 1) / 2 - 1), y_hi = min(vis_h - 2, by * sbin + (3 * sbin) / 2 + 1);
+  const int x_lo = max(1, bx * sbin - (sbin + 1) / 2 - 1), x_hi = min(vis_w - 2, bx * sbin + (3 * sbin) / 2 + 1);
+  const double dsb = (double)(float)sbin;
+  for (int y = y_lo; y <= y_hi; ++y) {
+    const float yp = (float)(((double)(float)y + 0.5) / dsb - 0.5);          // :252
+    const int iyp = (int)floorf(yp);
+    const float vy0 = __fsub_rn(yp, (float)iyp);
+    float wy;
+    if (iyp == by) wy = (float)(1.0 - (double)vy0);                           // vy1, :258
+    else if (iyp == by - 1) wy = vy0;
+    else continue;
+    const int sy = min(y, rows - 2);
+    const uint8_t* rowp = im + (size_t)sy * stride;
+    for (int x = x_lo; x <= x_hi; ++x) {
+      const float xp = (float)(((double)(float)x + 0.5) / dsb - 0.5);
+      const int ixp = (int)floorf(xp);
+      const float vx0 = __fsub_rn(xp, (float)ixp);
+      float wx;
+      if (ixp == bx) wx = (float)(1.0 - (double)vx0);
+      else if (ixp == bx - 1) wx = vx0;
+      else continue;
+      const int sx = min(x, cols - 2);
+      const uint8_t* s = rowp + sx * CN;
+      float dx, dy, v;
+      if (CN == 1) {                                                         // :207-212
+        dy = (float)((int)s[stride] - (int)*(s - stride));
+        dx = (float)((int)s[1] - (int)*(s - 1));
+        v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      } else {                                                               // :217-240
+        const float dyb = (float)((int)s[stride] - (int)*(s - stride));
+        const float dxb = (float)((int)s[3] - (int)*(s - 3));
+        const float vb = __fadd_rn(__fmul_rn(dxb, dxb), __fmul_rn(dyb, dyb));
+        const float dyg = (float)((int)s[stride + 1] - (int)*(s - stride + 1));
+        const float dxg = (float)((int)s[4] - (int)*(s - 2));
+        const float vg = __fadd_rn(__fmul_rn(dxg, dxg), __fmul_rn(dyg, dyg));
+        dy = (float)((int)s[stride + 2] - (int)*(s - stride + 2));
+        dx = (float)((int)s[5] - (int)*(s - 1));
+        v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (vg > v) { v = vg; dx = dxg; dy = dyg; }
+        if (vb > v) { v = vb; dx = dxb; dy = dyb; }
+      }
+      float best_dot = 0.f;                                                  // :243-249
+      int best_o = 0;
+#pragma unroll
+      for (int o = 0; o < 9; ++o) {
+        const float dot = __fadd_rn(__fmul_rn(uu[o], dx), __fmul_rn(vv[o], dy));
+        if (dot > best_dot) { best_dot = dot; best_o = o; }
+        else if (-dot > best_dot) { best_dot = -dot; best_o = o + 9; }
+      }
+      const float term = __fmul_rn(__fmul_rn(wy, wx), __fsqrt_rn(v));       // :260-265
+#pragma unroll
+      for (int o = 0; o < 18; ++o) h[o] = __fadd_rn(h[o], (o == best_o) ? term : 0.f);
+    }
+  }
+  float* hp = hist + ((size_t)frame * g->blocks_total + idx) * 18;
+#pragma unroll
+  for (int o = 0; o < 18; ++o) hp[o] = h[o];
+  float e = 0.f;                                                             // :270-283
+#pragma unroll
+  for (int o = 0; o < 9; ++o) { const float t = __fadd_rn(h[o], h[o + 9]); e = __fadd_rn(e, __fmul_rn(t, t)); }
+  norm[(size_t)frame * g->blocks_total + idx] = e;
+}
+
+__device__ __forceinline__ float normaliser(const float* p, int stride) {  // :292-299
+  const float s = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[stride]), p[stride + 1]);
+  return (float)__ddiv_rn(1.0, __dsqrt_rn(__dadd_rn((double)s, 0.0001)));
+}
+
+__global__ void __launch_bounds__(128) hog_feat(const Geometry* __restrict__ g, const float* __restrict__ hist,
+                                                const float* __restrict__ norm, float* __restrict__ feat) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g->cells_total) return;
+  const int frame = blockIdx.y;
+  const int l = find_level_by_cell(g, idx);
+  const LevelDesc& L = g->lv[l];
+  const int local = idx - L.cell_off;
+  const int x = local % L.ow, y = local / L.ow;
+  const float* nb = norm + (size_t)frame * g->blocks_total + L.block_off;
+  const int ns = L.bw;
+  const float n1 = normaliser(nb + (y + 1) * ns + (x + 1), ns);
+  const float n2 = normaliser(nb + y * ns + (x + 1), ns);
+  const float n3 = normaliser(nb + (y + 1) * ns + x, ns);
+  const float n4 = normaliser(nb + y * ns + x, ns);
+  const float* src = hist + ((size_t)frame * g->blocks_total + L.block_off + (size_t)(y + 1) * L.bw + (x + 1)) * 18;
+  float hv[18];
+#pragma unroll
+  for (int o = 0; o < 18; ++o) hv[o] = src[o];
+  float out[32];
+  float t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
+  const float clip = (float)0.2;
+#pragma unroll
+  for (int o = 0; o < 18; ++o) {                                             // :305-317
+    const float h1 = fminf(__fmul_rn(hv[o], n1), clip), h2 = fminf(__fmul_rn(hv[o], n2), clip);
+    const float h3 = fminf(__fmul_rn(hv[o], n3), clip), h4 = fminf(__fmul_rn(hv[o], n4), clip);
+    out[o] = __fmul_rn(0.5f, __fadd_rn(__fadd_rn(__fadd_rn(h1, h2), h3), h4));   // 0.5*sum is exact in either precision
+    t1 = __fadd_rn(t1, h1); t2 = __fadd_rn(t2, h2); t3 = __fadd_rn(t3, h3); t4 = __fadd_rn(t4, h4);
+  }
+#pragma unroll
+  for (int o = 0; o < 9; ++o) {                                              // :321-329
+    const float sum = __fadd_rn(hv[o], hv[o + 9]);
+    const float h1 = fminf(__fmul_rn(sum, n1), clip), h2 = fminf(__fmul_rn(sum, n2), clip);
+    const float h3 = fminf(__fmul_rn(sum, n3), clip), h4 = fminf(__fmul_rn(sum, n4), clip);
+    out[18 + o] = __fmul_rn(0.5f, __fadd_rn(__fadd_rn(__fadd_rn(h1, h2), h3), h4));
+  }
+  out[27] = (float)__dmul_rn(0.2357, (double)t1);                            // :332-335
+  out[28] = (float)__dmul_rn(0.2357, (double)t2);
+  out[29] = (float)__dmul_rn(0.2357, (double)t3);
+  out[30] = (float)__dmul_rn(0.2357, (double)t4);
+  out[31] = 0.f;                                                             // :338
+  float4* dst = reinterpret_cast<float4*>(feat + ((size_t)frame * g->cells_total + idx) * 32);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+}
+
+}  // namespace
+
+int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int sbin, cudaStream_t s) {
+  if (g.blocks_total <= 0) return 0;
+  dim3 gh((g.blocks_total + 127) / 128, g.n_frames);
+  if (g.in_c == 1) hog_hist<1><<<gh, 128, 0, s>>>(d_g, b.pyr, b.hist, b.norm, sbin);
+  else hog_hist<3><<<gh, 128, 0, s>>>(d_g, b.pyr, b.hist, b.norm, sbin);
+  int n = 1;
+  if (g.cells_total > 0) {
+    dim3 gf((g.cells_total + 127) / 128, g.n_frames);
+    hog_feat<<<gf, 128, 0, s>>>(d_g, b.hist, b.norm, b.feat);
+    ++n;
+  }
+  return n;
+}
+
+}  // namespace pbd

@@ -1,0 +1,140 @@
+// kernels.cuh -- device-side data layout shared by the stage kernels (sm_100a).
+//
+// HBM layout for one batch of n equally sized frames ("map-major over all levels"):
+//   pyr    u8   [n][img_bytes]            pyramid images, level l at LevelDesc::img_off
+//   hist   f32  [n][blocks_total][18]     orientation histograms per HOG block (+norm [n][blocks_total])
+//   feat   f32  [n][cells_total][flen]    HOG features, HWC (reference featm layout, src/HOGFeatures.cpp:180)
+//   resp   f32  [n][nfilters][cells_total]  part-filter responses, planar per filter
+//   work   f32  [n][nwork][cells_total]   working scores of non-leaf parts (response + child messages)
+//   tmp    f32  [n][njobs*MAXMIX][cells_total]  row-pass output of the part(s) currently processed
+//   ixdt   u16  [n][ncm][cells_total]     row-pass argmax per (component, part, child mixture)
+//   iyraw  u16  [n][ncm][cells_total]     column-pass argmax (not yet composed, see dt.cu)
+//   ik     u8   [n][npm][cells_total]     best child mixture per (component, part, parent mixture)
+//   rootv  f32  [n][ncomp][cells_total], rooti u8 [n][ncomp][cells_total]
+// where a cell index inside a map is LevelDesc::cell_off + y*ow + x.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pbd {
+
+constexpr int kMaxLevels = 96;
+constexpr int kMaxMix = 8;       // max mixtures per part (shipped models: <= 6)
+constexpr int kMaxParts = 80;    // max parts per component (shipped models: <= 68)
+
+struct LevelDesc {
+  int img_w, img_h;      // pyramid image size (pixels)
+  int bw, bh;            // HOG blocks  (reference `blocks`, src/HOGFeatures.cpp:174)
+  int ow, oh;            // HOG cells   (reference `outsize`, :175)
+  float scale;           // reference scales_[l], :118,124
+  int src_level;         // -1: resized from the input frame, else pyrDown of that level
+  long long img_off;     // byte offset of the level image inside one frame's pyramid buffer
+  int block_off;         // offset (in blocks) inside one frame's hist/norm arrays
+  int cell_off;          // offset (in cells) inside one map
+  int xofs_off, yofs_off;  // offsets into the resize tables (levels with src_level == -1)
+};
+
+struct Geometry {
+  int n_frames, n_levels;
+  int in_h, in_w, in_c;
+  long long img_bytes;     // per frame
+  int blocks_total, cells_total;
+  LevelDesc lv[kMaxLevels];
+};
+
+// One DP job = one non-root part of one component (reference src/DynamicProgram.cpp:95-161).
+struct PartJob {
+  int nmix, pnmix;
+  int in_slot[kMaxMix];      // child score map for mixture mm: response filter id, or work slot if in_is_work
+  int in_is_work[kMaxMix];
+  float w[kMaxMix][4];       // deformation weights (model defs), reference defw(mm)
+  int ax[kMaxMix], ay[kMaxMix];  // anchor
+  int cm_slot[kMaxMix];      // ixdt / iyraw slot of (c, p, mm)
+  float bias[kMaxMix][kMaxMix];  // [mm][pm] = biasw[biasid[p][mm] + pm]
+  int out_work_slot[kMaxMix];    // parent's working-score slot for parent mixture pm
+  int out_resp_fid[kMaxMix];     // parent's filter id (first-touch initialisation, reference :155)
+  int pm_slot[kMaxMix];      // ik slot of (c, p, pm)
+  int first_touch;           // 1: work = resp + msg, 0: work += msg
+  int tmp_base;              // first tmp map of this job (job_in_wave * kMaxMix)
+};
+
+struct RootJob {               // reference src/DynamicProgram.cpp:163-171
+  int nmix;
+  int in_slot[kMaxMix];
+  int in_is_work[kMaxMix];
+  float bias;
+};
+
+struct DeviceBuffers {
+  const uint8_t* frames;   // [n][h][w][c] input
+  uint8_t* pyr;
+  float* hist;
+  float* norm;
+  float* feat;
+  float* resp;
+  float* work;
+  float* tmp;
+  uint16_t* ixdt;
+  uint16_t* iyraw;
+  uint8_t* ik;
+  float* rootv;
+  uint8_t* rooti;
+};
+
+// candidate records produced by root_select / backtrack
+struct Hit {
+  int frame, level, comp, y, x;
+  float score;
+};
+
+// ---- launchers (each enqueues on `s`, returns the number of kernels launched) ----
+int launch_pyramid(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_xofs, const short* d_xalpha,
+                   const int* d_yofs, const short* d_ybeta, int interval, cudaStream_t s);
+int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int sbin, cudaStream_t s);
+
+// device copy of the model's filters (converted to float, reference src/PartsBasedDetector.cpp:115-117)
+struct FilterBank {
+  int nfilters, flen;
+  int uniform, kh, kw;         // uniform: all filters kh x kw -> packed fast path
+  int ngroups;                 // ceil(nfilters / 8)
+  const float* w;              // packed  [group][c][ky][kx][8], zero padded
+  const float* wg;             // generic [f] -> [c][ky][kx] at foff[f]
+  const int* foff;
+  const int* fkh;
+  const int* fkw;
+  int khm, kwm;                // largest filter (generic path halo)
+};
+int response_tile_dims(int uniform_fast, int* tx, int* ty);
+bool response_has_fast_path(const FilterBank& fb);
+int launch_response_tiles(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const FilterBank& fb, const int* d_tile_level,
+                          const int* d_tile_first, int ntiles, int exact, cudaStream_t s);
+
+int launch_dt_rows_tab(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_rg_level, const int* d_rg_row0, int nrg,
+                       int max_ow, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int tmp_maps, cudaStream_t s);
+int launch_dt_cols_tab(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_cg_level, const int* d_cg_col0, int ncg,
+                       int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps, cudaStream_t s);
+int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const RootJob* d_roots, int ncomp, int nfilters, int nwork,
+                float thresh, Hit* d_hits, int* d_nhits, int max_hits, cudaStream_t s);
+
+int launch_hits(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int ncomp, float thresh, Hit* d_hits, int* d_nhits,
+                int max_hits, cudaStream_t s);
+
+struct BacktrackTables {       // per component, flattened with strides kMaxParts / kMaxMix
+  const int* parent;           // [ncomp][kMaxParts]
+  const int* nparts;           // [ncomp]
+  const int* cm_slot;          // [ncomp][kMaxParts][kMaxMix]  ixdt/iyraw slot of (c, p, child mixture)
+  const int* pm_slot;          // [ncomp][kMaxParts][kMaxMix]  ik slot of (c, p, parent mixture)
+};
+int launch_backtrack(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const BacktrackTables& t, int ncomp, int ncm, int npm,
+                     const Hit* d_hits, const int* d_nhits, int max_hits, int backptr_mode, int* d_out_xym, cudaStream_t s);
+// materialise the reference's Ix/Iy/Ik Mats for one (frame, level, comp, part, parent mixture)
+int launch_expand_backptr(const Geometry& g, const DeviceBuffers& b, int frame, int level, int ncm, int npm, const int* d_cm_slots,
+                          int pm_slot, int backptr_mode, int* d_ix, int* d_iy, int* d_ik, cudaStream_t s);
+
+// standalone 2-D DT over n_maps maps of h x w (config 5 microbenchmark / pbd_dt2d_f32)
+int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const float* d_defw4, const int* d_anchor, float* d_tmp,
+                           float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
+                           cudaStream_t s);
+constexpr int kMaxDim = 1024;  // largest level width/height (cells) the DP kernels are instantiated for
+
+}  // namespace pbd

@@ -1,0 +1,95 @@
+// pyramid.cu -- image pyramid of HOGFeatures<T>::pyramid (reference src/HOGFeatures.cpp:109-127):
+// `interval` bilinear resizes of the input frame (cv::resize, INTER_LINEAR, 8U fixed point) followed by
+// chains of cv::pyrDown (5x5 binomial, BORDER_REFLECT_101, 8U).  Pure integer arithmetic => bit-exact.
+// HBM-bound: every output pixel is written once, sources are read through L1/L2 (a pyrDown tap
+// footprint is re-read by 6.25 outputs on average, all hits).
+#include "kernels.cuh"
+
+namespace pbd {
+namespace {
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+  return p;
+}
+
+// One thread per destination pixel of one resized level.  Coefficient tables are built on the host
+// exactly as OpenCV's resize() does (float coordinate, cvFloor, cvRound(f*2048) as int16).
+__global__ void __launch_bounds__(256) pyr_resize_u8(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames,
+                                                     uint8_t* __restrict__ pyr, const int* __restrict__ xofs,
+                                                     const short* __restrict__ xalpha, const int* __restrict__ yofs,
+                                                     const short* __restrict__ ybeta, int level) {
+  const LevelDesc& L = g->lv[level];
+  const int dw = L.img_w, dh = L.img_h, cn = g->in_c, sw = g->in_w, sh = g->in_h;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dw * dh) return;
+  const int dx = idx % dw, dy = idx / dw;
+  const int frame = blockIdx.y;
+  const uint8_t* S = frames + (size_t)frame * sh * sw * cn;
+  uint8_t* D = pyr + (size_t)frame * g->img_bytes + L.img_off + (size_t)idx * cn;
+  const int sx = xofs[L.xofs_off + dx], sx1 = min(sx + 1, sw - 1);
+  const int a0 = xalpha[2 * (L.xofs_off + dx)], a1 = xalpha[2 * (L.xofs_off + dx) + 1];
+  const int sy = yofs[L.yofs_off + dy];
+  const int sy0 = min(max(sy, 0), sh - 1), sy1 = min(max(sy + 1, 0), sh - 1);
+  const int b0 = ybeta[2 * (L.yofs_off + dy)], b1 = ybeta[2 * (L.yofs_off + dy) + 1];
+  const uint8_t* r0p = S + (size_t)sy0 * sw * cn;
+  const uint8_t* r1p = S + (size_t)sy1 * sw * cn;
+  for (int c = 0; c < cn; ++c) {
+    const int r0 = r0p[sx * cn + c] * a0 + r0p[sx1 * cn + c] * a1;
+    const int r1 = r1p[sx * cn + c] * a0 + r1p[sx1 * cn + c] * a1;
+    const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+    D[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// One thread per destination pixel: out = (sum_{i,j} k[i]k[j] src[2y+i-2][2x+j-2] + 128) >> 8, k = [1 4 6 4 1].
+__global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ g, uint8_t* __restrict__ pyr, int level) {
+  const LevelDesc& L = g->lv[level];
+  const LevelDesc& P = g->lv[L.src_level];
+  const int dw = L.img_w, dh = L.img_h, cn = g->in_c, sw = P.img_w, sh = P.img_h;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dw * dh) return;
+  const int x = idx % dw, y = idx / dw;
+  const int frame = blockIdx.y;
+  const uint8_t* S = pyr + (size_t)frame * g->img_bytes + P.img_off;
+  uint8_t* D = pyr + (size_t)frame * g->img_bytes + L.img_off + (size_t)idx * cn;
+  const int k[5] = {1, 4, 6, 4, 1};
+  int xs[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) xs[j] = reflect101(2 * x + j - 2, sw) * cn;
+  int acc[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const uint8_t* row = S + (size_t)reflect101(2 * y + i - 2, sh) * sw * cn;
+    for (int c = 0; c < cn; ++c) {
+      int h = 0;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) h += k[j] * row[xs[j] + c];
+      acc[c] += k[i] * h;
+    }
+  }
+  for (int c = 0; c < cn; ++c) D[c] = (uint8_t)((acc[c] + 128) >> 8);
+}
+
+}  // namespace
+
+int launch_pyramid(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_xofs, const short* d_xalpha,
+                   const int* d_yofs, const short* d_ybeta, int interval, cudaStream_t s) {
+  int launches = 0;
+  // resized levels depend only on the frame; pyrDown level l depends on level l - interval, so
+  // launching levels in increasing order on one stream satisfies every dependency.
+  for (int l = 0; l < g.n_levels; ++l) {
+    const LevelDesc& L = g.lv[l];
+    const int npx = L.img_w * L.img_h;
+    if (npx <= 0) continue;
+    dim3 grid((npx + 255) / 256, g.n_frames);
+    if (L.src_level < 0) pyr_resize_u8<<<grid, 256, 0, s>>>(d_g, b.frames, b.pyr, d_xofs, d_xalpha, d_yofs, d_ybeta, l);
+    else pyr_down_u8<<<grid, 256, 0, s>>>(d_g, b.pyr, l);
+    ++launches;
+  }
+  (void)interval;
+  return launches;
+}
+
+}  // namespace pbd

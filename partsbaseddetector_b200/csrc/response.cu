@@ -1,0 +1,289 @@
+// response.cu -- SpatialConvolutionEngine::pdf (reference src/SpatialConvolutionEngine.cpp:70-124) for all
+// filters x all levels x all frames of a batch in one launch.
+//
+//   resp[f](y,x) = sum_{c<32} R_c,   R_c = sum_{ky,kx} w_f[ky][kx][c] * F_c(y+ky-ay, x+kx-ax),  ay = kh/2, ax = kw/2
+// with F_c outside the map = 0 for c < 31 and 1 for c = 31 (the BORDER_CONSTANT engines built at
+// src/SpatialConvolutionEngine.cpp:147-156).  In EXACT mode every product and every sum is rounded
+// separately (__fmul_rn/__fadd_rn) and accumulated in the reference's order -- taps row-major inside a
+// channel (cv::Filter2D, src/filter.cpp:3898-3922), then channels 0..31 (:85-93) -- so the scores are
+// bit-identical to the CPU path.  In fast mode the taps are fused multiply-adds into one accumulator.
+//
+// This stage is a dense contraction (M = cells, N = filters, K = kh*kw*32 = 800; 325 FLOP per algorithmic
+// byte), so it is bounded by the FP32 issue rate, not by HBM.  Blocking (sm_100a, measured issue rates in
+// DESIGN.md): a CTA owns a TY x TX tile of cells of one level; the HOG tile plus halo is staged once into
+// shared memory, transposed from HWC to channel-planar so that a thread's P=4 adjacent cells are one
+// 128-bit load; filters are pre-packed on the host as [group of 8][channel][tap][8] and streamed through a
+// double-buffered cp.async stage, so a thread's 8 filter taps are two broadcast 128-bit loads.  Each
+// thread keeps 4 cells x 8 filters in registers: 64 FMUL+FADD (or 32..64 FFMA) per 6 shared-memory loads.
+#include "kernels.cuh"
+
+namespace pbd {
+namespace {
+
+constexpr int TX = 32, TY = 8;       // cells per CTA tile
+constexpr int P = 4, Q = 8;          // register tile: cells (along x) x filters
+constexpr int POSW = (TX / P) * TY / 32;   // warps covering the tile's cells (= 2)
+constexpr int WF = 3;                // filter groups (of Q) processed per pass by different warps
+constexpr int NT = POSW * WF * 32;   // threads per CTA (192)
+constexpr int CCH = 8;               // channels per weight stage
+
+struct TileRef { int level, ty, tx; };
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int KH, int KW, bool EXACT>
+__global__ void __launch_bounds__(NT, 2)
+part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level, const int* __restrict__ tile_first,
+              const float* __restrict__ feat, const float* __restrict__ wbank, int nfilters, int ngroups,
+              float* __restrict__ resp) {
+  constexpr int TAPS = KH * KW;
+  constexpr int HY = TY + KH - 1;                       // tile rows incl. halo
+  constexpr int ROWP = ((TX + KW - 1 + 3) / 4) * 4;     // padded row pitch (words), 16-byte aligned rows
+  constexpr int PLANE = HY * ROWP;
+  constexpr int WSLAB = CCH * TAPS * Q;                 // floats per (group, channel-chunk)
+  extern __shared__ __align__(16) float smem[];
+  float* sfeat = smem;                                  // [32][HY][ROWP]
+  float* sw = smem + 32 * PLANE;                        // [2][WF][CCH][TAPS][Q]
+
+  const int tile = blockIdx.x, frame = blockIdx.y;
+  const int l = tile_level[tile];
+  const LevelDesc& L = g->lv[l];
+  const int tiles_x = (L.ow + TX - 1) / TX;
+  const int tl = tile - tile_first[l];
+  const int y0 = (tl / tiles_x) * TY, x0 = (tl % tiles_x) * TX;
+  const int ow = L.ow, oh = L.oh;
+  constexpr int AY = KH / 2, AX = KW / 2;               // anchor, include/filterengine.hpp:310-318
+  const int tid = threadIdx.x;
+
+  // ---- stage the HOG tile (+halo), HWC -> channel-planar, border 0 (c<31) / 1 (c=31) ----
+  const float* fbase = feat + ((size_t)frame * g->cells_total + L.cell_off) * 32;
+  for (int i = tid; i < HY * ROWP * 8; i += NT) {
+    const int cq = i / (HY * ROWP);                     // channel quad 0..7
+    const int pos = i % (HY * ROWP);
+    const int ty = pos / ROWP, tx = pos % ROWP;
+    const int gy = y0 + ty - AY, gx = x0 + tx - AX;
+    float4 v;
+    if (gy >= 0 && gy < oh && gx >= 0 && gx < ow) v = __ldg(reinterpret_cast<const float4*>(fbase + ((size_t)gy * ow + gx) * 32 + cq * 4));
+    else v = make_float4(0.f, 0.f, 0.f, cq == 7 ? 1.f : 0.f);
+    sfeat[(cq * 4 + 0) * PLANE + pos] = v.x;
+    sfeat[(cq * 4 + 1) * PLANE + pos] = v.y;
+    sfeat[(cq * 4 + 2) * PLANE + pos] = v.z;
+    sfeat[(cq * 4 + 3) * PLANE + pos] = v.w;
+  }
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wpos = warp % POSW, wf = warp / POSW;       // which cells / which filter group of the pass
+  const int lx = lane & 7, ly = lane >> 3;
+  const int cy = wpos * 4 + ly;                         // tile-local cell row 0..7
+  const int cx = lx * P;                                // tile-local first cell column
+  const int npass = (ngroups + WF - 1) / WF;
+
+  auto stage_weights = [&](int pass, int chunk, int buf) {
+    // slab of group gq, channels [chunk*CCH, +CCH): contiguous WSLAB floats in the packed bank
+    for (int i = tid; i < WF * WSLAB / 4; i += NT) {
+      const int w = i / (WSLAB / 4), o = i % (WSLAB / 4);
+      int gq = pass * WF + w;
+      if (gq >= ngroups) gq = ngroups - 1;              // idle warps read a valid slab, results discarded
+      cp_async16(sw + ((size_t)buf * WF + w) * WSLAB + o * 4,
+                 wbank + ((size_t)gq * 32 + chunk * CCH) * TAPS * Q + o * 4);
+    }
+    cp_async_commit();
+  };
+
+  constexpr int NCH = 32 / CCH;
+  stage_weights(0, 0, 0);
+  int it = 0;                                           // global stage counter over (pass, chunk)
+  for (int pass = 0; pass < npass; ++pass) {
+    float acc[P][Q];
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+      for (int j = 0; j < Q; ++j) acc[i][j] = 0.f;
+
+    for (int chunk = 0; chunk < NCH; ++chunk, ++it) {
+      const int buf = it & 1;
+      // prefetch the next stage, then wait for the current one
+      const int nchunk = chunk + 1 == NCH ? 0 : chunk + 1;
+      const int npassi = chunk + 1 == NCH ? pass + 1 : pass;
+      if (npassi < npass) { stage_weights(npassi, nchunk, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      __syncthreads();                                  // weights (and, first time, the HOG tile) visible
+      const float* wsl = sw + ((size_t)buf * WF + wf) * WSLAB;
+#pragma unroll 1
+      for (int cl = 0; cl < CCH; ++cl) {
+        const int c = chunk * CCH + cl;
+        const float* fp = sfeat + c * PLANE + cy * ROWP + cx;
+        const float* wp = wsl + cl * TAPS * Q;
+        float r[P][Q];
+#pragma unroll
+        for (int ky = 0; ky < KH; ++ky) {
+          float xs[P + KW - 1];
+#pragma unroll
+          for (int i = 0; i < (P + KW - 1 + 3) / 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(fp + ky * ROWP + 4 * i);
+            if (4 * i + 0 < P + KW - 1) xs[4 * i + 0] = v.x;
+            if (4 * i + 1 < P + KW - 1) xs[4 * i + 1] = v.y;
+            if (4 * i + 2 < P + KW - 1) xs[4 * i + 2] = v.z;
+            if (4 * i + 3 < P + KW - 1) xs[4 * i + 3] = v.w;
+          }
+#pragma unroll
+          for (int kx = 0; kx < KW; ++kx) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wp + (ky * KW + kx) * Q);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + (ky * KW + kx) * Q + 4);
+            const float w[Q] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < P; ++i)
+#pragma unroll
+              for (int j = 0; j < Q; ++j) {
+                if (EXACT) {
+                  const float pr = __fmul_rn(w[j], xs[i + kx]);
+                  r[i][j] = (ky == 0 && kx == 0) ? pr : __fadd_rn(r[i][j], pr);
+                } else {
+                  acc[i][j] = __fmaf_rn(w[j], xs[i + kx], acc[i][j]);
+                }
+              }
+          }
+        }
+        if (EXACT) {
+#pragma unroll
+          for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int j = 0; j < Q; ++j) acc[i][j] = __fadd_rn(acc[i][j], r[i][j]);
+        }
+      }
+      __syncthreads();                                  // everyone done with `buf` before it is refilled
+    }
+    // ---- write the pass's responses: resp[frame][f][cell] ----
+    const int gq = pass * WF + wf;
+    const int gy = y0 + cy;
+    if (gq < ngroups && gy < oh) {
+#pragma unroll
+      for (int j = 0; j < Q; ++j) {
+        const int f = gq * Q + j;
+        if (f >= nfilters) break;
+        float* dst = resp + ((size_t)frame * nfilters + f) * g->cells_total + L.cell_off + (size_t)gy * ow + x0 + cx;
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+          if (x0 + cx + i < ow) dst[i] = acc[i][j];
+      }
+    }
+  }
+}
+
+// Generic fallback for models whose filters are not all the same size (e.g. 15x5 roots with 6x6 parts):
+// one thread per cell, loops over all filters; same arithmetic order, weights read through L1 (uniform).
+template <bool EXACT>
+__global__ void __launch_bounds__(128)
+part_response_generic(const Geometry* __restrict__ g, const int* __restrict__ tile_level, const int* __restrict__ tile_first,
+                      const float* __restrict__ feat, const float* __restrict__ wg, const int* __restrict__ foff,
+                      const int* __restrict__ fkh, const int* __restrict__ fkw, int nfilters, int khm, int kwm,
+                      float* __restrict__ resp) {
+  constexpr int GX = 16, GY = 8;
+  extern __shared__ __align__(16) float smem[];
+  const int HYm = GY + khm - 1, ROWm = GX + kwm - 1, PLANEm = HYm * ROWm + 1;
+  const int tile = blockIdx.x, frame = blockIdx.y;
+  const int l = tile_level[tile];
+  const LevelDesc& L = g->lv[l];
+  const int tiles_x = (L.ow + GX - 1) / GX;
+  const int tl = tile - tile_first[l];
+  const int y0 = (tl / tiles_x) * GY, x0 = (tl % tiles_x) * GX;
+  const int ow = L.ow, oh = L.oh;
+  const int aym = khm / 2, axm = kwm / 2;               // tile halo is laid out for the largest anchor
+  const float* fbase = feat + ((size_t)frame * g->cells_total + L.cell_off) * 32;
+  for (int i = threadIdx.x; i < HYm * ROWm * 32; i += blockDim.x) {
+    const int c = i % 32, pos = i / 32;
+    const int ty = pos / ROWm, tx = pos % ROWm;
+    const int gy = y0 + ty - aym, gx = x0 + tx - axm;
+    float v = (c == 31) ? 1.f : 0.f;
+    if (gy >= 0 && gy < oh && gx >= 0 && gx < ow) v = fbase[((size_t)gy * ow + gx) * 32 + c];
+    smem[c * PLANEm + pos] = v;
+  }
+  __syncthreads();
+  const int cx = threadIdx.x % GX, cy = threadIdx.x / GX;
+  const int gx = x0 + cx, gy = y0 + cy;
+  if (gx >= ow || gy >= oh) return;
+  for (int f = 0; f < nfilters; ++f) {
+    const int kh = fkh[f], kw = fkw[f];
+    const int ay = kh / 2, ax = kw / 2;
+    const float* w = wg + foff[f];                      // [c][ky][kx]
+    float acc = 0.f;
+    for (int c = 0; c < 32; ++c) {
+      const float* fp = smem + c * PLANEm + (cy + aym - ay) * ROWm + (cx + axm - ax);
+      float r = 0.f;
+      for (int ky = 0; ky < kh; ++ky)
+        for (int kx = 0; kx < kw; ++kx) {
+          const float wv = __ldg(w + (c * kh + ky) * kw + kx);
+          if (EXACT) r = __fadd_rn(r, __fmul_rn(wv, fp[ky * ROWm + kx]));
+          else acc = __fmaf_rn(wv, fp[ky * ROWm + kx], acc);
+        }
+      if (EXACT) acc = __fadd_rn(acc, r);
+    }
+    resp[((size_t)frame * nfilters + f) * g->cells_total + L.cell_off + (size_t)gy * ow + gx] = acc;
+  }
+}
+
+template <int KH, int KW>
+size_t fast_smem_bytes() {
+  constexpr int HY = TY + KH - 1, ROWP = ((TX + KW - 1 + 3) / 4) * 4;
+  return (size_t)(32 * HY * ROWP + 2 * WF * CCH * KH * KW * Q) * sizeof(float);
+}
+
+template <int KH, int KW>
+void launch_fast(const Geometry* d_g, const int* d_tl, const int* d_tf, int ntiles, int nframes, const DeviceBuffers& b,
+                 const FilterBank& fb, int exact, cudaStream_t s) {
+  const size_t smem = fast_smem_bytes<KH, KW>();
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(part_response<KH, KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(part_response<KH, KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  dim3 grid(ntiles, nframes);
+  if (exact) part_response<KH, KW, true><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, b.resp);
+  else part_response<KH, KW, false><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, b.resp);
+}
+
+}  // namespace
+
+}  // namespace pbd
+
+namespace pbd {
+
+bool response_has_fast_path(const FilterBank& fb) {
+  return fb.uniform && fb.flen == 32 && fb.kh == fb.kw && (fb.kh == 4 || fb.kh == 5 || fb.kh == 6);
+}
+
+int response_tile_dims(int uniform, int* tx, int* ty) {
+  if (uniform) { *tx = TX; *ty = TY; } else { *tx = 16; *ty = 8; }
+  return 0;
+}
+
+int launch_response_tiles(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const FilterBank& fb, const int* d_tile_level,
+                          const int* d_tile_first, int ntiles, int exact, cudaStream_t s) {
+  if (ntiles <= 0 || g.n_frames <= 0) return 0;
+  const int khm = fb.khm, kwm = fb.kwm;
+  if (response_has_fast_path(fb)) {
+    if (fb.kh == 5) launch_fast<5, 5>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, s);
+    else if (fb.kh == 4) launch_fast<4, 4>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, s);
+    else launch_fast<6, 6>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, s);
+    return 1;
+  }
+  const int HYm = 8 + khm - 1, ROWm = 16 + kwm - 1;
+  const size_t smem = (size_t)32 * (HYm * ROWm + 1) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(part_response_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(part_response_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid(ntiles, g.n_frames);
+  if (exact) part_response_generic<true><<<grid, 128, smem, s>>>(d_g, d_tile_level, d_tile_first, b.feat, fb.wg, fb.foff, fb.fkh, fb.fkw, fb.nfilters, khm, kwm, b.resp);
+  else part_response_generic<false><<<grid, 128, smem, s>>>(d_g, d_tile_level, d_tile_first, b.feat, fb.wg, fb.foff, fb.fkh, fb.fkw, fb.nfilters, khm, kwm, b.resp);
+  return 1;
+}
+
+}  // namespace pbd

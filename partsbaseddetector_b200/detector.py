@@ -1,0 +1,360 @@
+"""Host-side mirror of the reference's interface for the detect() path, over the C-ABI.
+
+Names follow the reference: `FileStorageModel.deserialize/serialize` (src/FileStorageModel.cpp),
+`PartsBasedDetector.distributeModel/detect` (src/PartsBasedDetector.cpp:69-127), `Candidate`
+(include/Candidate.hpp) and the stage interfaces `pyramid` (IFeatures), `pdf` (IConvolutionEngine),
+`min` / `argmin` (DynamicProgram).  Everything numeric happens in libpbd_b200.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .flatmodel import FlatModel, FlatPart
+
+
+class Model:
+    """reference `Model` (include/Model.hpp:49-122): owns a pbd_model handle."""
+
+    def __init__(self, handle=None):
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.lib().pbd_model_free(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise _lib.PbdError(-5, "model is empty; call deserialize() first")
+        return self._h
+
+    # --- getters (include/Model.hpp:98-118) ---
+    def _hdr(self):
+        hdr = np.zeros(8, np.int32)
+        th = C.c_float()
+        _lib.check(_lib.lib().pbd_model_header(self.handle, hdr, C.byref(th)))
+        return hdr, th.value
+
+    def name(self):
+        return _lib.lib().pbd_model_name(self.handle).decode()
+
+    def nscales(self):
+        return int(self._hdr()[0][0])          # the reference keeps `interval` in nscales_
+
+    def binsize(self):
+        return int(self._hdr()[0][1])
+
+    def norient(self):
+        return int(self._hdr()[0][2])
+
+    def flen(self):
+        return int(self._hdr()[0][3])
+
+    def thresh(self):
+        return self._hdr()[1]
+
+    def ncomponents(self):
+        return int(self._hdr()[0][7])
+
+    def to_flat(self):
+        L = _lib.lib()
+        hdr, th = self._hdr()
+        m = FlatModel(name=self.name(), interval=int(hdr[0]), thresh=float(np.float32(th)), sbin=int(hdr[1]),
+                      norient=int(hdr[2]), flen=int(hdr[3]))
+        for i in range(hdr[4]):
+            r, k = C.c_int(), C.c_int()
+            p = C.POINTER(C.c_double)()
+            _lib.check(L.pbd_model_filter(self.handle, i, C.byref(r), C.byref(k), C.byref(p)))
+            m.filters.append(np.ctypeslib.as_array(p, (r.value, k.value * m.flen)).copy())
+        n = C.c_int()
+        pf = C.POINTER(C.c_float)()
+        _lib.check(L.pbd_model_bias(self.handle, C.byref(pf), C.byref(n)))
+        m.biasw = np.ctypeslib.as_array(pf, (n.value,)).copy()
+        pi = C.POINTER(C.c_int)()
+        _lib.check(L.pbd_model_anchors(self.handle, C.byref(pi), C.byref(n)))
+        m.anchors = np.ctypeslib.as_array(pi, (n.value, 2)).copy() if n.value else np.zeros((0, 2), np.int32)
+        _lib.check(L.pbd_model_defs(self.handle, C.byref(pf), C.byref(n)))
+        m.defs = np.ctypeslib.as_array(pf, (n.value, 4)).copy() if n.value else np.zeros((0, 4), np.float32)
+        for c in range(hdr[7]):
+            parts = []
+            for p in range(L.pbd_model_nparts(self.handle, c)):
+                lists = []
+                par = C.c_int()
+                for which in range(3):
+                    buf = np.zeros(256, np.int32)
+                    cnt = C.c_int()
+                    _lib.check(L.pbd_model_part(self.handle, c, p, C.byref(par), which, buf, 256, C.byref(cnt)))
+                    lists.append([int(v) for v in buf[:cnt.value]])
+                parts.append(FlatPart(par.value, *lists))
+            m.comps.append(parts)
+        return m
+
+    @classmethod
+    def from_flat(cls, fm):
+        a = fm.to_arrays()
+        h = C.c_void_p()
+        _lib.check(_lib.lib().pbd_model_create(fm.name.encode(), a["hdr"], float(fm.thresh), a["fdims"], a["filters"], a["biasw"],
+                                               a["anchors"] if len(a["anchors"]) else np.zeros(2, np.int32),
+                                               a["defs"] if len(a["defs"]) else np.zeros(4, np.float32), a["indexers"], C.byref(h)))
+        return cls(h)
+
+    def save_bin(self, path):
+        _lib.check(_lib.lib().pbd_model_save_bin(self.handle, path.encode()))
+
+    @classmethod
+    def load_bin(cls, path):
+        h = C.c_void_p()
+        _lib.check(_lib.lib().pbd_model_load_bin(path.encode(), C.byref(h)))
+        return cls(h)
+
+
+class FileStorageModel(Model):
+    """reference FileStorageModel (src/FileStorageModel.cpp): XML (de)serialisation; bool returns."""
+
+    def deserialize(self, filename):
+        h = C.c_void_p()
+        rc = _lib.lib().pbd_model_load_xml(filename.encode(), C.byref(h))
+        if rc == -2:            # cannot open: the reference returns false (src/FileStorageModel.cpp:100-101)
+            return False
+        _lib.check(rc)
+        if self._h:
+            _lib.lib().pbd_model_free(self._h)
+        self._h = h
+        return True
+
+    def serialize(self, filename):
+        _lib.check(_lib.lib().pbd_model_save_xml(self.handle, filename.encode()))
+        return True
+
+
+class Candidate:
+    """reference Candidate (include/Candidate.hpp:56-99) + frame/level/part locations."""
+
+    __slots__ = ("frame", "level", "component_", "confidence_", "parts_", "x", "y", "m")
+
+    def parts(self):
+        return self.parts_             # (nparts, 4) int32: cv::Rect x, y, width, height
+
+    def confidence(self):
+        return self.confidence_
+
+    def score(self):
+        return self.confidence_[0]
+
+    def component(self):
+        return self.component_
+
+    @staticmethod
+    def sort(cands):
+        cands.sort(key=lambda c: -float(c.score()))          # stable, descending (Candidate.hpp:97-99)
+
+
+def _unpack_candidates(handle, free=True):
+    L = _lib.lib()
+    out = []
+    n = L.pbd_candidates_count(handle)
+    for i in range(n):
+        npart = L.pbd_candidates_nparts(handle, i)
+        fr, lv, cp, sc = C.c_int(), C.c_int(), C.c_int(), C.c_float()
+        xs, ys, ms = (np.empty(npart, np.int32) for _ in range(3))
+        rc = np.empty(npart * 4, np.int32)
+        _lib.check(L.pbd_candidates_get(handle, i, C.byref(fr), C.byref(lv), C.byref(cp), C.byref(sc), xs, ys, ms, rc))
+        c = Candidate()
+        c.frame, c.level, c.component_ = fr.value, lv.value, cp.value
+        conf = np.zeros(npart, np.float32)
+        conf[0] = sc.value                                       # root = rootv, others 0.0 (DynamicProgram.cpp:241-244)
+        c.confidence_ = conf
+        c.parts_ = rc.reshape(npart, 4)
+        c.x, c.y, c.m = xs, ys, ms
+        out.append(c)
+    if free:
+        L.pbd_candidates_free(handle)
+    return out
+
+
+class PartsBasedDetector:
+    """reference PartsBasedDetector<float> (include/PartsBasedDetector.hpp:152-175)."""
+
+    def __init__(self, device=0, stream=0):
+        self._d = None
+        self._device = device
+        self._stream = stream
+        self._name = ""
+        self._model = None
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        if getattr(self, "_d", None):
+            _lib.lib().pbd_destroy(self._d)
+            self._d = None
+
+    @property
+    def handle(self):
+        if not self._d:
+            raise _lib.PbdError(-5, "distributeModel() has not been called")
+        return self._d
+
+    def distributeModel(self, model):
+        self.close()
+        d = C.c_void_p()
+        _lib.check(_lib.lib().pbd_create(model.handle, self._device, C.c_void_p(self._stream), C.byref(d)))
+        self._d = d
+        self._name = model.name()
+        self._model = model
+
+    def name(self):
+        return self._name
+
+    def set_option(self, key, value):
+        _lib.check(_lib.lib().pbd_set_option(self.handle, key.encode(), float(value)))
+
+    def get_option(self, key):
+        v = C.c_double()
+        _lib.check(_lib.lib().pbd_get_option(self.handle, key.encode(), C.byref(v)))
+        return v.value
+
+    # ---- whole path ----
+    @staticmethod
+    def _frames(im):
+        a = np.asarray(im)
+        if a.dtype != np.uint8:
+            raise _lib.PbdError(-6, "Unsupported image type (only 8-bit frames)")     # reference CV_Error
+        if a.ndim == 2:
+            a = a[None, :, :, None]
+        elif a.ndim == 3:
+            a = a[None] if a.shape[2] in (1, 3) else a[..., None]
+        return np.ascontiguousarray(a)
+
+    def detect(self, im, depth=None, candidates=None):
+        """detect(im[, depth], candidates): appends to `candidates` like the reference (never clears it).
+        `im` is one HxWx3 (BGR) / HxW frame or an NxHxWxC batch; `depth` is accepted and ignored (T7)."""
+        a = self._frames(im)
+        n, h, w, c = a.shape
+        out = C.c_void_p()
+        _lib.check(_lib.lib().pbd_detect_batch_u8(self.handle, a.ctypes.data, n, h, w, c, 0, 0, C.byref(out)))
+        res = _unpack_candidates(out)
+        if candidates is None:
+            return res
+        candidates.extend(res)
+        return candidates
+
+    def detect_device(self, dptr, n, h, w, c):
+        out = C.c_void_p()
+        _lib.check(_lib.lib().pbd_detect_batch_u8_device(self.handle, C.c_void_p(dptr), n, h, w, c, C.byref(out)))
+        return _unpack_candidates(out)
+
+    def enqueue_device(self, dptr, n, h, w, c):
+        _lib.check(_lib.lib().pbd_enqueue_batch_u8_device(self.handle, C.c_void_p(dptr), n, h, w, c))
+
+    def collect(self):
+        out = C.c_void_p()
+        _lib.check(_lib.lib().pbd_collect_candidates(self.handle, C.byref(out)))
+        return _unpack_candidates(out)
+
+    # ---- stage level (IFeatures / IConvolutionEngine / DynamicProgram) ----
+    def pyramid(self, im):
+        a = self._frames(im)
+        n, h, w, c = a.shape
+        _lib.check(_lib.lib().pbd_stage_pyramid(self.handle, a.ctypes.data, n, h, w, c, 0, 0))
+
+    def pdf(self):
+        _lib.check(_lib.lib().pbd_stage_pdf(self.handle))
+
+    def min(self):
+        _lib.check(_lib.lib().pbd_stage_dp_min(self.handle))
+
+    def argmin(self):
+        out = C.c_void_p()
+        _lib.check(_lib.lib().pbd_stage_dp_argmin(self.handle, C.byref(out)))
+        return _unpack_candidates(out)
+
+    def nscales(self):
+        return _lib.lib().pbd_num_levels(self.handle)
+
+    def level_info(self, l):
+        v = [C.c_int() for _ in range(4)]
+        s = C.c_float()
+        _lib.check(_lib.lib().pbd_level_info(self.handle, l, *[C.byref(x) for x in v], C.byref(s)))
+        return dict(img_h=v[0].value, img_w=v[1].value, oh=v[2].value, ow=v[3].value, scale=np.float32(s.value))
+
+    def scales(self):
+        return [self.level_info(l)["scale"] for l in range(self.nscales())]
+
+    def pyramid_image(self, frame, l, channels=3):
+        li = self.level_info(l)
+        out = np.empty(li["img_h"] * li["img_w"] * channels, np.uint8)
+        _lib.check(_lib.lib().pbd_get_pyramid_image(self.handle, frame, l, out))
+        return out.reshape(li["img_h"], li["img_w"], channels)
+
+    def features(self, frame, l):
+        li = self.level_info(l)
+        out = np.empty(li["oh"] * li["ow"] * 32, np.float32)
+        _lib.check(_lib.lib().pbd_get_features(self.handle, frame, l, out))
+        return out.reshape(li["oh"], li["ow"], 32)
+
+    def response(self, frame, l, f):
+        li = self.level_info(l)
+        out = np.empty(li["oh"] * li["ow"], np.float32)
+        _lib.check(_lib.lib().pbd_get_response(self.handle, frame, l, f, out))
+        return out.reshape(li["oh"], li["ow"])
+
+    def rootv(self, frame, l, c=0):
+        li = self.level_info(l)
+        out = np.empty(li["oh"] * li["ow"], np.float32)
+        _lib.check(_lib.lib().pbd_get_rootv(self.handle, frame, l, c, out))
+        return out.reshape(li["oh"], li["ow"])
+
+    def rooti(self, frame, l, c=0):
+        li = self.level_info(l)
+        out = np.empty(li["oh"] * li["ow"], np.int32)
+        _lib.check(_lib.lib().pbd_get_rooti(self.handle, frame, l, c, out))
+        return out.reshape(li["oh"], li["ow"])
+
+    def backptr(self, frame, l, c, p, m):
+        li = self.level_info(l)
+        n = li["oh"] * li["ow"]
+        ix, iy, ik = (np.empty(n, np.int32) for _ in range(3))
+        _lib.check(_lib.lib().pbd_get_backptr(self.handle, frame, l, c, p, m, ix, iy, ik))
+        s = (li["oh"], li["ow"])
+        return ix.reshape(s), iy.reshape(s), ik.reshape(s)
+
+    def set_levels(self, n_frames, ohow, scales):
+        ohow = np.ascontiguousarray(ohow, np.int32).reshape(-1)
+        scales = np.ascontiguousarray(scales, np.float32)
+        _lib.check(_lib.lib().pbd_set_levels(self.handle, n_frames, len(scales), ohow, scales))
+
+    def set_features(self, frame, l, arr):
+        _lib.check(_lib.lib().pbd_set_features(self.handle, frame, l, np.ascontiguousarray(arr, np.float32).reshape(-1)))
+
+    def set_response(self, frame, l, f, arr):
+        _lib.check(_lib.lib().pbd_set_response(self.handle, frame, l, f, np.ascontiguousarray(arr, np.float32).reshape(-1)))
+
+    def launch_count(self):
+        return int(_lib.lib().pbd_launch_count(self.handle))
+
+    def stage_times_ms(self):
+        ms = np.zeros(6, np.float32)
+        _lib.check(_lib.lib().pbd_stage_times_ms(self.handle, ms))
+        return dict(zip(["h2d", "pyramid", "hog", "pdf", "dp_min", "argmin"], [float(x) for x in ms]))
+
+    def device_bytes(self):
+        return int(_lib.lib().pbd_device_bytes(self.handle))
+
+
+def dt2d(score, defw4, anchor_xy, backptr_mode=0):
+    """Generalised 2-D distance transform of one or more maps on the GPU (DistanceTransform<float>::compute)."""
+    a = np.ascontiguousarray(score, np.float32)
+    if a.ndim == 2:
+        a = a[None]
+    n, h, w = a.shape
+    defw4 = np.ascontiguousarray(np.broadcast_to(np.asarray(defw4, np.float32).reshape(-1, 4), (n, 4)))
+    anchor = np.ascontiguousarray(np.broadcast_to(np.asarray(anchor_xy, np.int32).reshape(-1, 2), (n, 2)))
+    out = np.empty(n * h * w, np.float32)
+    ix = np.empty(n * h * w, np.int32)
+    iy = np.empty(n * h * w, np.int32)
+    _lib.check(_lib.lib().pbd_dt2d_f32(a.reshape(-1), n, h, w, defw4.reshape(-1), anchor.reshape(-1), out, ix, iy, backptr_mode))
+    return out.reshape(n, h, w), ix.reshape(n, h, w), iy.reshape(n, h, w)

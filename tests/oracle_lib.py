@@ -105,6 +105,7 @@ class OracleDetector:
             if img.ndim == 2:
                 img = img[:, :, None]
             h, w, c = img.shape
+            self._cn = c
             self.L.orc_run(self.h, img.ctypes.data, h, w, c, first, last)
         else:
             self.L.orc_run(self.h, None, 0, 0, 0, first, last)
@@ -131,7 +132,7 @@ class OracleDetector:
 
     def image(self, l):
         li = self.level_info(l)
-        out = np.empty((li["img_h"], li["img_w"], 3), np.uint8)
+        out = np.empty((li["img_h"], li["img_w"], getattr(self, "_cn", 3)), np.uint8)
         self.L.orc_get_image(self.h, l, out.reshape(-1))
         return out
 

@@ -1,0 +1,304 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle on the same seeded inputs.
+Bit-exact for every integer output (pyramid pixels, back-pointers, mixture ids, part locations, rects) and,
+in the default exact mode, for every float score as well; the fast mode is held to 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from conftest import GOLDEN, load_flat
+from partsbaseddetector_b200 import Model, PartsBasedDetector, PbdError, dt2d
+from partsbaseddetector_b200.synth import synth_frame, synth_frames, synth_score_map
+
+pytestmark = pytest.mark.gpu
+
+_det_cache = {}
+
+
+def detector(name):
+    if name not in _det_cache:
+        d = PartsBasedDetector(device=0)
+        d.distributeModel(Model.load_bin(os.path.join(GOLDEN, name + ".pbdm")))
+        _det_cache[name] = d
+    d = _det_cache[name]
+    for k, v in (("exact", 1), ("backptr", 0), ("max_levels", 0), ("thresh", load_flat(name).thresh)):
+        d.set_option(k, v)
+    return d
+
+
+def oracle(name, precision=32):
+    return oracle_lib.OracleDetector(load_flat(name), precision)
+
+
+def lowered_threshold(O, keep=60):
+    rv = np.concatenate([O.rootv(l, c).ravel() for l in range(O.nlevels()) for c in range(len(O.model.comps))])
+    return float(np.sort(rv)[-min(keep, rv.size)])
+
+
+def cand_key(c):
+    return (c["frame"], c["level"], c["component"], int(c["y"][0]), int(c["x"][0]))
+
+
+# ------------------------------------------------------------------------------------------ pyramid + HOG
+@pytest.mark.parametrize("shape", [(120, 160), (240, 320), (97, 131), (203, 77)])
+def test_pyramid_and_hog_bitexact(shape):
+    img = synth_frame(shape[0] + shape[1], *shape)
+    d, O = detector("Person_26parts"), oracle("Person_26parts")
+    d.pyramid(img)
+    O.run(img, 1, 1)
+    assert d.nscales() == O.nlevels()
+    for l in range(O.nlevels()):
+        a, b = d.level_info(l), O.level_info(l)
+        assert a == b
+        assert np.array_equal(d.pyramid_image(0, l), O.image(l)), "level %d image" % l
+        assert np.array_equal(d.features(0, l), O.features(l)), "level %d features" % l
+
+
+def test_hog_gray_and_sbin8():
+    img = synth_frame(5, 192, 256)[:, :, 1].copy()
+    d, O = detector("Person_8parts"), oracle("Person_8parts")          # sbin 8
+    d.pyramid(img)
+    O.run(img, 1, 1)
+    for l in range(O.nlevels()):
+        assert np.array_equal(d.pyramid_image(0, l, channels=1), O.image(l))
+        assert np.array_equal(d.features(0, l), O.features(l))
+
+
+def test_degenerate_frames():
+    d, O = detector("Person_26parts"), oracle("Person_26parts")
+    for img in (np.zeros((96, 128, 3), np.uint8), np.full((96, 128, 3), 255, np.uint8),
+                np.tile(np.arange(128, dtype=np.uint8)[None, :, None] * 2, (96, 1, 3))):
+        d.pyramid(img)
+        O.run(img, 1, 1)
+        for l in range(O.nlevels()):
+            assert np.array_equal(d.features(0, l), O.features(l))
+
+
+# ------------------------------------------------------------------------------------------ responses
+@pytest.mark.parametrize("name", ["Person_26parts", "Willowcoffee_5parts", "Face_frontal_sparse", "Person_8parts"])
+def test_responses_exact_and_fast(name):
+    fm = load_flat(name)
+    img = synth_frame(11, 144, 200)
+    d, O = detector(name), oracle(name)
+    O.run(img, 1, 2)
+    d.pyramid(img)
+    d.pdf()
+    nl = O.nlevels()
+    for l in (0, nl // 2, nl - 1):
+        for f in sorted(set([0, 1, fm.nfilters() // 2, fm.nfilters() - 1])):
+            assert np.array_equal(d.response(0, l, f), O.response(l, f)), (l, f)
+    d.set_option("exact", 0)
+    d.pyramid(img)
+    d.pdf()
+    for l in (0, nl - 1):
+        for f in (0, fm.nfilters() - 1):
+            ref = O.response(l, f)
+            assert np.allclose(d.response(0, l, f), ref, rtol=1e-5, atol=1e-6 * np.abs(ref).max())
+
+
+def test_responses_injected_random_features_all_filters():
+    # stage-isolated: random features (not HOG-like) on ragged level sizes, every filter compared
+    name = "Willowcoffee_5parts"
+    fm = load_flat(name)
+    d, O = detector(name), oracle(name)
+    ohow = [[9, 35], [33, 8], [4, 4], [17, 65]]
+    scales = [4.0, 5.0, 6.0, 8.0]
+    d.set_levels(1, ohow, scales)
+    O.set_levels(ohow, scales)
+    rng = np.random.default_rng(0)
+    for l, (oh, ow) in enumerate(ohow):
+        f = rng.standard_normal((oh, ow, 32)).astype(np.float32)
+        d.set_features(0, l, f)
+        O.set_features(l, f)
+    O.run(None, 2, 2)
+    d.pdf()
+    for l in range(len(ohow)):
+        for f in range(fm.nfilters()):
+            assert np.array_equal(d.response(0, l, f), O.response(l, f)), (l, f)
+
+
+# ------------------------------------------------------------------------------------------ distance transform
+@pytest.mark.parametrize("h,w", [(1, 1), (1, 17), (23, 1), (37, 53), (160, 158), (200, 330)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_dt2d_bitexact(h, w, mode):
+    rng = np.random.default_rng(h * 1000 + w)
+    n = 5
+    maps = np.stack([synth_score_map(i, h, w) for i in range(n)])
+    maps[3] = 0.25                                                    # flat map: exact ties everywhere
+    maps[4] = np.round(maps[4] * 2) / 2                               # heavily quantised: many ties
+    defw = np.stack([rng.uniform(0.01, 0.02, n), rng.uniform(-0.02, 0.02, n), rng.uniform(0.01, 0.02, n),
+                     rng.uniform(-0.02, 0.02, n)], axis=1).astype(np.float32)
+    anchors = np.stack([rng.integers(-3, 4, n), rng.integers(-2, 6, n)], axis=1).astype(np.int32)
+    out, ix, iy = dt2d(maps, defw, anchors, mode)
+    L = oracle_lib.lib()
+    for i in range(n):
+        o, x, y = np.empty((h, w), np.float32), np.empty((h, w), np.int32), np.empty((h, w), np.int32)
+        L.orc_dt2d_f32(maps[i].reshape(-1), h, w, defw[i], int(anchors[i, 0]), int(anchors[i, 1]), mode, o.reshape(-1), x.reshape(-1), y.reshape(-1))
+        assert np.array_equal(out[i], o), i
+        assert np.array_equal(ix[i], x), i
+        assert np.array_equal(iy[i], y), i
+
+
+def test_dt2d_rejects_bad_arguments():
+    with pytest.raises(PbdError):
+        dt2d(np.zeros((4, 4), np.float32), [0.0, 0.0, 0.01, 0.0], [0, 0])       # a = -w0 must be < 0
+
+
+# ------------------------------------------------------------------------------------------ DP + backtrack
+@pytest.mark.parametrize("name,shape", [("Person_26parts", (120, 160)), ("Willowcoffee_5parts", (144, 200)),
+                                        ("Face_frontal_sparse", (120, 160)), ("Person_8parts", (200, 260))])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_dp_and_candidates_bitexact(name, shape, mode):
+    fm = load_flat(name)
+    img = synth_frame(21, *shape)
+    d, O = detector(name), oracle(name)
+    O.set_backptr_mode(mode)
+    O.run(img, 1, 3)
+    thr = lowered_threshold(O)
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    d.set_option("backptr", mode)
+    d.set_option("thresh", thr)
+    cands = d.detect(img)
+    nl = O.nlevels()
+    for l in range(nl):
+        for c in range(len(fm.comps)):
+            assert np.array_equal(d.rootv(0, l, c), O.rootv(l, c)), ("rootv", l, c)
+            assert np.array_equal(d.rooti(0, l, c), O.rooti(l, c)), ("rooti", l, c)
+    for l in (0, nl - 1):
+        for c in range(len(fm.comps)):
+            for p in range(1, len(fm.comps[c])):
+                for pm in range(fm.nmix(c, fm.comps[c][p].parentid)):
+                    g, o = d.backptr(0, l, c, p, pm), O.backptr(l, c, p, pm)
+                    for a, b, what in zip(g, o, ("Ix", "Iy", "Ik")):
+                        assert np.array_equal(a, b), (what, l, c, p, pm)
+    oc = O.candidates()
+    assert len(cands) == len(oc) > 0
+    for g, o in zip(cands, oc):                                   # same deterministic order as the reference
+        assert (g.frame, g.level, g.component()) == (0, o["level"], o["component"])
+        assert np.array_equal(g.x, o["x"]) and np.array_equal(g.y, o["y"]) and np.array_equal(g.m, o["m"])
+        assert np.array_equal(g.parts(), o["rects"])
+        assert g.score() == o["score"] and np.all(g.confidence()[1:] == 0)
+
+
+def test_committed_golden_vectors():
+    g = np.load(os.path.join(GOLDEN, "oracle_golden.npz"))
+    d = detector("Person_26parts")
+    d.set_option("thresh", float(g["p26_thresh"]))
+    cands = d.detect(synth_frame(7, 120, 160))
+    assert d.nscales() == int(g["p26_nlevels"])
+    assert np.array_equal(d.pyramid_image(0, 2), g["p26_image2"])
+    assert np.array_equal(d.features(0, 0), g["p26_feat0"])
+    assert np.array_equal(d.response(0, 0, 17), g["p26_resp0_f17"])
+    assert np.array_equal(d.rootv(0, 0), g["p26_rootv0"]) and np.array_equal(d.rooti(0, 0), g["p26_rooti0"])
+    ix, iy, ik = d.backptr(0, 0, 0, 3, 2)
+    assert np.array_equal(ix, g["p26_ix_p3m2"]) and np.array_equal(iy, g["p26_iy_p3m2"]) and np.array_equal(ik, g["p26_ik_p3m2"])
+    got = np.array([[c.level] + list(c.x) + list(c.y) + list(c.m) for c in cands], np.int32)
+    assert np.array_equal(got, g["p26_cand_xyms"])
+    assert np.array_equal(np.array([c.score() for c in cands], np.float32), g["p26_cand_scores"])
+    assert np.array_equal(np.array([c.parts() for c in cands], np.int32), g["p26_cand_rects"])
+
+
+def test_fast_mode_integer_outputs_and_score_tolerance():
+    # fused multiply-add responses: scores within 1e-4 relative (north_star), integer outputs expected identical
+    name = "Person_26parts"
+    img = synth_frame(33, 240, 320)
+    d, O = detector(name), oracle(name)
+    O.run(img, 1, 3)
+    thr = lowered_threshold(O, 200)
+    O.set_thresh(thr + 1e-4)          # keep clear of the threshold so the candidate SET cannot flip on a 1e-7 score change
+    O.run(None, 4, 4)
+    d.set_option("exact", 0)
+    d.set_option("thresh", thr + 1e-4)
+    cands = d.detect(img)
+    oc = O.candidates()
+    gk = {(c.level, int(c.y[0]), int(c.x[0])): c for c in cands}
+    ok = {(c["level"], int(c["y"][0]), int(c["x"][0])): c for c in oc}
+    common = set(gk) & set(ok)
+    assert len(common) >= 0.98 * len(ok)
+    same = 0
+    for k in common:
+        g, o = gk[k], ok[k]
+        assert abs(g.score() - o["score"]) <= 1e-4 * abs(o["score"])
+        same += int(np.array_equal(g.x, o["x"]) and np.array_equal(g.y, o["y"]) and np.array_equal(g.m, o["m"]))
+    assert same >= 0.98 * len(common)
+
+
+# ------------------------------------------------------------------------------------------ batches, full size, properties
+def test_batch_equals_single_frames_vga():
+    name = "Person_26parts"
+    frames = synth_frames(3, 480, 640, start=100)
+    d = detector(name)
+    O = oracle(name)
+    O.run(frames[1], 1, 3)
+    thr = lowered_threshold(O, 80)
+    d.set_option("thresh", thr)
+    batch = d.detect(frames)
+    rv_batch = [d.rootv(f, 0).copy() for f in range(3)]
+    singles = []
+    for f in range(3):
+        c = d.detect(frames[f])
+        assert np.array_equal(d.rootv(0, 0), rv_batch[f])
+        singles += [(f, k.level, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score())) for k in c]
+    assert [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score())) for k in batch] == singles
+    # frame 1 of the batch against the oracle at full VGA size (14 levels)
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    oc = O.candidates()
+    b1 = [k for k in batch if k.frame == 1]
+    assert len(b1) == len(oc) > 0
+    for g, o in zip(b1, oc):
+        assert g.level == o["level"] and np.array_equal(g.x, o["x"]) and np.array_equal(g.y, o["y"]) and np.array_equal(g.m, o["m"])
+        assert g.score() == o["score"] and np.array_equal(g.parts(), o["rects"])
+
+
+def test_determinism_and_stage_api_equivalence():
+    d = detector("Person_26parts")
+    frames = synth_frames(2, 240, 320, start=7)
+    d.set_option("thresh", -1.2)
+    a = d.detect(frames)
+    b = d.detect(frames)
+    assert [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score())) for k in a] == \
+           [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score())) for k in b]
+    d.pyramid(frames)
+    d.pdf()
+    d.min()
+    c = d.argmin()
+    assert [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m)) for k in a] == [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m)) for k in c]
+
+
+def test_max_levels_and_candidate_sort():
+    d, O = detector("Person_26parts"), oracle("Person_26parts")
+    img = synth_frame(9, 240, 320)
+    d.set_option("max_levels", 4)
+    O.set_max_levels(4)
+    O.run(img, 1, 3)
+    thr = lowered_threshold(O, 30)
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    d.set_option("thresh", thr)
+    cands = d.detect(img)
+    assert d.nscales() == 4 and len(cands) == len(O.candidates())
+    from partsbaseddetector_b200 import Candidate
+    Candidate.sort(cands)
+    s = [float(c.score()) for c in cands]
+    assert s == sorted(s, reverse=True)
+
+
+def test_errors_and_state_machine():
+    d = detector("Person_26parts")
+    with pytest.raises(PbdError):
+        d.detect(np.zeros((8, 8, 3), np.uint8))                 # smaller than one pyramid level
+    with pytest.raises(PbdError):
+        d.detect(np.zeros((64, 64, 3), np.float32))             # unsupported depth
+    d.pyramid(synth_frame(1, 96, 128))
+    with pytest.raises(PbdError):
+        d.min()                                                 # pdf has not run
+    d.set_option("max_candidates", 4)
+    d.set_option("thresh", -100.0)
+    with pytest.raises(PbdError):
+        d.detect(synth_frame(1, 96, 128))                       # candidate buffer overflow is reported, not truncated
+    d.set_option("max_candidates", 65536)
+    with pytest.raises(PbdError):
+        d.set_option("nonsense", 1)
