@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the detect() hot path (person model, VGA, full pyramid) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W          # our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W  # the reference's CPU path (restated oracle, all host threads)
+
+One "step" = one pass of the whole path (image pyramid -> HOG -> part responses -> DT/DP -> backtrack) over one
+batch of synthetic 640x480 BGR frames per GPU.  Weak scaling: every rank processes its own batch; frames are
+independent, so there is no collective on the data path.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = os.path.join(ROOT, "tests", "golden", "Person_26parts.pbdm")
+H, W, C = 480, 640, 3
+METRIC = "frames/sec (person model, VGA, full pyramid)"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for (t, line) in self.lines:
+            if t < t0 or t > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except ValueError:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_frames_per_sec(frames, budget_s=20.0, max_frames=8, warmup=1):
+    """Times the restated reference CPU path (oracle, OpenMP over all host threads) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from partsbaseddetector_b200 import Model
+    fm = Model.load_bin(MODEL).to_flat()
+    O = oracle_lib.OracleDetector(fm, 32)
+    cores = oracle_lib.lib().orc_num_threads()
+    for i in range(warmup):
+        O.run(frames[i % len(frames)])
+    t0 = time.time()
+    n = 0
+    stage = {}
+    while n < max_frames and (time.time() - t0 < budget_s or n == 0):
+        O.run(frames[n % len(frames)])
+        for k, v in O.timings().items():
+            stage[k] = stage.get(k, 0.0) + v
+        n += 1
+    dt = time.time() - t0
+    return n / dt, cores, n, dt, {k: 1e3 * v / n for k, v in stage.items()}
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    from partsbaseddetector_b200.synth import synth_frames
+    per_step = 2                                   # frames per step: a bounded sample of the 32-frame workload
+    frames = synth_frames(per_step, H, W, start=0)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from partsbaseddetector_b200 import Model
+    O = oracle_lib.OracleDetector(Model.load_bin(MODEL).to_flat(), 32)
+    cores = oracle_lib.lib().orc_num_threads()
+    for _ in range(args.warmup):
+        for f in frames:
+            O.run(f)
+    t0 = time.time()
+    for _ in range(args.steps):
+        for f in frames:
+            O.run(f)
+    dt = time.time() - t0
+    fps = args.steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config_person.by_parts (Person_26parts), 640x480 BGR frames, full 14-level HOG pyramid", "frames_per_step": per_step,
+                   "impl_detail": "restated reference CPU path (oracle/pbd_oracle.cpp, OpenMP as the reference); the reference itself needs OpenCV C++/Boost and cannot be built here"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": "%d steps x %d synthetic VGA frames" % (args.steps, per_step)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from partsbaseddetector_b200 import Model, PartsBasedDetector
+    from partsbaseddetector_b200.synth import synth_frames
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path is the only implementation (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    # every rank gets its own frames (frame-parallel sharding: global frame index = rank*B + i)
+    uniq = min(B, args.unique_frames)
+    base = synth_frames(uniq, H, W, start=rank * B)
+    host = torch.empty((B, H, W, C), dtype=torch.uint8, pin_memory=True)
+    hnp = host.numpy()
+    for i in range(B):
+        hnp[i] = base[i % uniq]
+    dev = host.cuda(non_blocking=False)
+
+    det = PartsBasedDetector(device=local, stream=torch.cuda.current_stream().cuda_stream)
+    det.distributeModel(Model.load_bin(MODEL))
+    det.set_option("exact", 0 if args.fast else 1)
+    det.set_option("timing", 1)
+    # calibrate the detection threshold on the first batch so that ~50 candidates/frame come back (synthetic
+    # frames score below the model's -0.75: SURVEY.md section 8d); done once, outside every timed region
+    det.set_option("thresh", 1e9)
+    det.detect_device(dev.data_ptr(), B, H, W, C)
+    nl = det.nscales()
+    rv = np.concatenate([det.rootv(0, l).ravel() for l in range(nl)])
+    thr = float(np.sort(rv)[-50]) if args.thresh is None else args.thresh
+    det.set_option("thresh", thr)
+    cells = int(sum(det.level_info(l)["oh"] * det.level_info(l)["ow"] for l in range(nl)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: `value` ----
+    for _ in range(args.warmup):
+        det.enqueue_device(dev.data_ptr(), B, H, W, C)
+    ncand = len(det.collect())
+    stage_acc = {}
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    l0 = det.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        det.enqueue_device(dev.data_ptr(), B, H, W, C)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = det.launch_count() - l0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    # per-stage device time of the last step (events recorded by the library on the same stream)
+    stage_ms = det.stage_times_ms()
+    # the per-kernel average over the timed region for the dominant kernel: re-run K steps collecting the pdf stage time
+    pdf_ms = []
+    for _ in range(min(args.steps, 5)):
+        det.enqueue_device(dev.data_ptr(), B, H, W, C)
+        pdf_ms.append(det.stage_times_ms()["pdf"])
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- end to end through the public API with host buffers: `e2e` ----
+    for _ in range(max(1, args.warmup // 2)):
+        c = det.detect(hnp)
+    barrier()
+    t0 = time.time()
+    nc_total = 0
+    for _ in range(args.steps):
+        c = det.detect(hnp)                       # H2D of the batch + all stages + D2H of hit count and candidates
+        nc_total += len(c)
+    torch.cuda.synchronize()
+    e2e_s = time.time() - t0
+    t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_s = float(t2.item())
+    d2h = 4 + (nc_total // max(args.steps, 1)) * (24 + 3 * 80 * 4)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        fps = world * B * args.steps / (ms_max * 1e-3)
+        pdf_avg = float(np.mean(pdf_ms))
+        alg_bytes = 680.0 * cells * B                         # per launch: 128 B features read + 552 B responses written per cell
+        flops = 2.0 * 800 * 138 * cells * B
+        ach = alg_bytes / (pdf_avg * 1e-3) / 1e9
+        sm_mhz = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "config_person.by_parts (Person_26parts), 640x480 BGR frames, full 14-level HOG pyramid, 1xB200 per rank",
+                       "batch_per_gpu": B, "frame": [H, W, C], "levels": nl, "cells_per_frame": cells, "parallelism": "frame-parallel x%d, no collective" % world,
+                       "mode": "fast (FFMA)" if args.fast else "exact (bit-identical scores)", "thresh": thr, "candidates_per_step": ncand,
+                       "l2": "inputs larger than L2 (%.0f MB of responses per step)" % (552.0 * cells * B / 1e6)},
+            "clocks": clocks,
+            "e2e": {"value": world * B * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": B * H * W * C, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "part_response", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": peak_src, "ms_per_launch": pdf_avg,
+                         "note": "dense contraction (325 FLOP/B): FP32-issue-bound, not HBM-bound; see fp32",
+                         "fp32": {"achieved_tflops": flops / (pdf_avg * 1e-3) / 1e12, "peak_tflops": fp32_peak,
+                                  "frac": flops / (pdf_avg * 1e-3) / 1e12 / fp32_peak, "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz"}},
+            "stage_ms": stage_ms,
+        }
+        if world == 1 and not args.no_cpu:
+            cfps, cores, n, dt, cstage = cpu_frames_per_sec(base, budget_s=args.cpu_budget)
+            line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": "%d synthetic VGA frames in %.1f s (restated reference CPU path, OpenMP)" % (n, dt), "stage_ms": cstage}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--unique-frames", type=int, default=8, help="distinct synthetic frames generated per rank (tiled to the batch)")
+    ap.add_argument("--fast", action="store_true", help="fused multiply-add responses instead of the bit-exact mode")
+    ap.add_argument("--thresh", type=float, default=None)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -110,6 +110,9 @@ int pbd_candidates_count(const pbd_candidates* c);
 int pbd_candidates_nparts(const pbd_candidates* c, int i);
 int pbd_candidates_get(const pbd_candidates* c, int i, int32_t* frame, int32_t* level, int32_t* component,
                        float* score, int32_t* xs, int32_t* ys, int32_t* ms, int32_t* rects_xywh);
+/* bulk export of all candidates in one call: meta[i] = {frame, level, component, nparts}, scores[i] = root score,
+ * parts[i][p] = {x, y, mixture, rect.x, rect.y, rect.width, rect.height} for p < nparts (row stride max_nparts*7). */
+int pbd_candidates_export(const pbd_candidates* c, int32_t* meta4, float* scores, int32_t* parts7, int max_nparts);
 void pbd_candidates_free(pbd_candidates* c);
 /* Candidate::sort (include/Candidate.hpp:97-99): descending root score, stable */
 int pbd_candidates_sort(pbd_candidates* c);

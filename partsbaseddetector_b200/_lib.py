@@ -25,7 +25,7 @@ EXPORTS = [
     "pbd_model_filter", "pbd_model_bias", "pbd_model_anchors", "pbd_model_defs", "pbd_model_nparts",
     "pbd_model_part", "pbd_create", "pbd_destroy", "pbd_set_option", "pbd_get_option", "pbd_detect_batch_u8",
     "pbd_detect_batch_u8_device", "pbd_enqueue_batch_u8_device", "pbd_collect_candidates",
-    "pbd_candidates_count", "pbd_candidates_nparts", "pbd_candidates_get", "pbd_candidates_free",
+    "pbd_candidates_count", "pbd_candidates_nparts", "pbd_candidates_get", "pbd_candidates_export", "pbd_candidates_free",
     "pbd_candidates_sort", "pbd_stage_pyramid", "pbd_stage_pdf", "pbd_stage_dp_min", "pbd_stage_dp_argmin",
     "pbd_num_frames", "pbd_num_levels", "pbd_level_info", "pbd_get_pyramid_image", "pbd_get_features",
     "pbd_get_response", "pbd_get_rootv", "pbd_get_rooti", "pbd_get_backptr", "pbd_set_levels",
@@ -86,6 +86,7 @@ def lib():
     L.pbd_candidates_count.argtypes = [vp]
     L.pbd_candidates_nparts.argtypes = [vp, ci]
     L.pbd_candidates_get.argtypes = [vp, ci, P(ci), P(ci), P(ci), P(cf), _i32p, _i32p, _i32p, _i32p]
+    L.pbd_candidates_export.argtypes = [vp, _i32p, _f32p, _i32p, ci]
     L.pbd_candidates_free.argtypes = [vp]
     L.pbd_candidates_sort.argtypes = [vp]
     L.pbd_stage_pyramid.argtypes = [vp, vp, ci, ci, ci, ci, C.c_size_t, C.c_size_t]

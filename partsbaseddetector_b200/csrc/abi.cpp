@@ -238,6 +238,23 @@ int pbd_candidates_get(const pbd_candidates* c, int i, int32_t* frame, int32_t* 
     if (rects_xywh) memcpy(rects_xywh, C.rect.data(), np * 4 * sizeof(int));
   });
 }
+int pbd_candidates_export(const pbd_candidates* c, int32_t* meta4, float* scores, int32_t* parts7, int max_nparts) {
+  return guarded([&] {
+    REQUIRE(c && meta4 && scores && parts7 && max_nparts > 0, "null argument");
+    for (size_t i = 0; i < c->v.size(); ++i) {
+      const CandidateRec& C = c->v[i];
+      const int np = (int)C.x.size();
+      REQUIRE(np <= max_nparts, "max_nparts too small");
+      meta4[4 * i] = C.frame; meta4[4 * i + 1] = C.level; meta4[4 * i + 2] = C.component; meta4[4 * i + 3] = np;
+      scores[i] = C.score;
+      int32_t* row = parts7 + i * (size_t)max_nparts * 7;
+      for (int p = 0; p < np; ++p) {
+        row[7 * p] = C.x[p]; row[7 * p + 1] = C.y[p]; row[7 * p + 2] = C.m[p];
+        row[7 * p + 3] = C.rect[4 * p]; row[7 * p + 4] = C.rect[4 * p + 1]; row[7 * p + 5] = C.rect[4 * p + 2]; row[7 * p + 6] = C.rect[4 * p + 3];
+      }
+    }
+  });
+}
 void pbd_candidates_free(pbd_candidates* c) { delete c; }
 int pbd_candidates_sort(pbd_candidates* c) {
   return guarded([&] {

@@ -15,6 +15,7 @@
 // Iy[y][x] <- Iy[y][Ix[y][x]] (:232-244) and the per-parent-mixture gather (Math::reducePickIndex) are NOT
 // materialised: the raw row-pass / column-pass argmaxes are kept per child mixture (u16) and composed lazily
 // by the backtrack (backtrack.cu), which is what makes the DP write 5 B instead of 12 B per (cell, map).
+#include <algorithm>
 #include <cfloat>
 #include "kernels.cuh"
 
@@ -115,69 +116,83 @@ dt_rows(const Geometry* __restrict__ g, const int* __restrict__ rg_level, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Column pass + mixture maximum + parent accumulate: one lane per column of one (frame, job, level).
+// Column pass + mixture maximum + parent accumulate.  One CTA per (frame, job, level, 32 columns); warp w runs
+// the column transform of child mixture w (lane = column), so all mixtures of a part advance concurrently.
+// The evaluation phase proceeds in chunks of CH rows: every warp deposits its CH x 32 transformed values in
+// shared memory, then the warps split the parent mixtures and compute, per cell,
+//   max_mm(dt[mm] + bias[mm][pm])  (Math::reduceMax, strict >, first wins), Ik, and parent.score += max.
 // ---------------------------------------------------------------------------------------------------
-template <int MAXN>
-__global__ void __launch_bounds__(64)
+template <int MAXN, int CH>
+__global__ void __launch_bounds__(kMaxMix * 32)
 dt_cols(const Geometry* __restrict__ g, const int* __restrict__ cg_level, const int* __restrict__ cg_col0, int ncg,
         const PartJob* __restrict__ jobs, const float* __restrict__ resp, float* __restrict__ work,
         const float* __restrict__ tmp, unsigned short* __restrict__ iyraw, unsigned char* __restrict__ ik,
         int nfilters, int nwork, int ncm, int npm, int tmp_maps) {
-  const int cg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (cg >= ncg) return;
-  const int lane = threadIdx.x & 31;
+  __shared__ float sval[2][kMaxMix][CH][32];
+  const int cg = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const PartJob& J = jobs[blockIdx.y];
   const int frame = blockIdx.z;
   const LevelDesc& L = g->lv[cg_level[cg]];
   const int col = cg_col0[cg] + lane;
-  if (col >= L.ow) return;
   const int N = L.oh, ow = L.ow;
   const size_t ct = (size_t)g->cells_total;
   const int nmix = J.nmix, pnmix = J.pnmix;
+  const bool col_ok = col < ow;
+  const bool mine = col_ok && warp < nmix;      // this thread owns the column transform of mixture `warp`
 
-  Stack<MAXN> st[kMaxMix];
-  Quad f[kMaxMix];
-  int k[kMaxMix], os[kMaxMix];
-#pragma unroll
-  for (int mm = 0; mm < kMaxMix; ++mm) {
-    if (mm < nmix) {
-      const float* src = tmp + ((size_t)frame * tmp_maps + J.tmp_base + mm) * ct + L.cell_off + col;
-      f[mm] = make_quad(J.w[mm][2], J.w[mm][3]);
-      build_envelope<MAXN>(st[mm], N, f[mm], [&](int q) { return __ldg(src + (size_t)q * ow); });
-      k[mm] = 0;
-      os[mm] = J.ay[mm];
-    }
+  Stack<MAXN> st;
+  Quad f = make_quad(1.f, 0.f);
+  int os = 0;
+  unsigned short* iyp = nullptr;
+  if (mine) {
+    const float* src = tmp + ((size_t)frame * tmp_maps + J.tmp_base + warp) * ct + L.cell_off + col;
+    f = make_quad(J.w[warp][2], J.w[warp][3]);
+    build_envelope<MAXN>(st, N, f, [&](int q) { return __ldg(src + (size_t)q * ow); });
+    os = J.ay[warp];
+    iyp = iyraw + ((size_t)frame * ncm + J.cm_slot[warp]) * ct + L.cell_off + col;
   }
-  for (int q = 0; q < N; ++q) {
-    const size_t cell = (size_t)L.cell_off + (size_t)q * ow + col;
-    float val[kMaxMix];
-#pragma unroll
-    for (int mm = 0; mm < kMaxMix; ++mm) {
-      if (mm < nmix) {
-        const int pos = os[mm] + q;
-        int kk = k[mm];
-        while (st[mm].z[kk + 1] < (float)pos) ++kk;
-        k[mm] = kk;
-        const int v = st[mm].v[kk];
-        val[mm] = envelope(f[mm], pos - v, st[mm].y[kk]);
-        iyraw[((size_t)frame * ncm + J.cm_slot[mm]) * ct + cell] = (unsigned short)v;
+  int k = 0;
+  for (int q0 = 0; q0 < N; q0 += CH) {
+    const int buf = (q0 / CH) & 1;
+    if (mine) {
+#pragma unroll 1
+      for (int qq = 0; qq < CH && q0 + qq < N; ++qq) {          // :172-178
+        const int pos = os + q0 + qq;
+        while (st.z[k + 1] < (float)pos) ++k;
+        const int v = st.v[k];
+        sval[buf][warp][qq][lane] = envelope(f, pos - v, st.y[k]);
+        iyp[(size_t)(q0 + qq) * ow] = (unsigned short)v;
       }
     }
-    for (int pm = 0; pm < pnmix; ++pm) {                    // src/DynamicProgram.cpp:134-156
-      float best = -INFINITY;
-      int bi = 0;
+    __syncthreads();
+    if (col_ok) {
+      for (int pm = warp; pm < pnmix; pm += nwarps) {           // src/DynamicProgram.cpp:134-156
+        unsigned char* ikp = ik + ((size_t)frame * npm + J.pm_slot[pm]) * ct + L.cell_off + col;
+        float* wp = work + ((size_t)frame * nwork + J.out_work_slot[pm]) * ct + L.cell_off + col;
+        const float* rp = resp + ((size_t)frame * nfilters + J.out_resp_fid[pm]) * ct + L.cell_off + col;
+        float bias[kMaxMix];
 #pragma unroll
-      for (int mm = 0; mm < kMaxMix; ++mm) {
-        if (mm < nmix) {
-          const float wv = __fadd_rn(val[mm], J.bias[mm][pm]);     // scoresp[mm] + bias(mm)[m], :139
-          if (wv > best) { best = wv; bi = mm; }                   // reduceMax: strict >, first wins
+        for (int mm = 0; mm < kMaxMix; ++mm) bias[mm] = mm < nmix ? J.bias[mm][pm] : 0.f;
+        for (int qq = 0; qq < CH && q0 + qq < N; ++qq) {
+          float best = -INFINITY;
+          int bi = 0;
+#pragma unroll
+          for (int mm = 0; mm < kMaxMix; ++mm) {
+            if (mm < nmix) {
+              const float wv = __fadd_rn(sval[buf][mm][qq][lane], bias[mm]);   // scoresp[mm] + bias(mm)[m], :139
+              if (wv > best) { best = wv; bi = mm; }                            // reduceMax: strict >, first wins
+            }
+          }
+          const size_t o = (size_t)(q0 + qq) * ow;
+          ikp[o] = (unsigned char)bi;
+          const float base = J.first_touch ? __ldg(rp + o) : wp[o];
+          wp[o] = __fadd_rn(base, best);                                         // parent.score += maxv, :155-156
         }
       }
-      ik[((size_t)frame * npm + J.pm_slot[pm]) * ct + cell] = (unsigned char)bi;
-      float* wp = work + ((size_t)frame * nwork + J.out_work_slot[pm]) * ct + cell;
-      const float base = J.first_touch ? __ldg(resp + ((size_t)frame * nfilters + J.out_resp_fid[pm]) * ct + cell) : *wp;
-      *wp = __fadd_rn(base, best);                                  // parent.score += maxv, :155-156
     }
+    // double-buffered sval: the next chunk writes the other buffer, and the chunk after that is separated
+    // from these reads by the next __syncthreads
   }
 }
 
@@ -312,10 +327,12 @@ int launch_dt_rows_tab(const Geometry& g, const Geometry* d_g, const DeviceBuffe
 }
 
 int launch_dt_cols_tab(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_cg_level, const int* d_cg_col0, int ncg,
-                       int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps, cudaStream_t s) {
+                       int max_oh, const PartJob* d_jobs, int njobs, int max_mix, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
+                       cudaStream_t s) {
   if (ncg <= 0 || njobs <= 0) return 0;
-  dim3 grid((ncg + 1) / 2, njobs, g.n_frames);
-#define PBD_COLS(M) dt_cols<M><<<grid, 64, 0, s>>>(d_g, d_cg_level, d_cg_col0, ncg, d_jobs, b.resp, b.work, b.tmp, b.iyraw, b.ik, nfilters, nwork, ncm, npm, tmp_maps)
+  dim3 grid(ncg, njobs, g.n_frames);
+  const int threads = 32 * std::min(std::max(max_mix, 1), kMaxMix);
+#define PBD_COLS(M) dt_cols<M, 8><<<grid, threads, 0, s>>>(d_g, d_cg_level, d_cg_col0, ncg, d_jobs, b.resp, b.work, b.tmp, b.iyraw, b.ik, nfilters, nwork, ncm, npm, tmp_maps)
   if (max_oh <= 160) PBD_COLS(160);
   else if (max_oh <= 512) PBD_COLS(512);
   else PBD_COLS(1024);

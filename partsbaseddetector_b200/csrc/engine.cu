@@ -162,23 +162,42 @@ void Engine::build_tables() {
       }
     }
   }
-  // ---- jobs by wave: wave k holds part (np_c - 1 - k) of every component that still has one ----
-  jobs_.clear(); wave_first_.clear(); wave_count_.clear();
+  // ---- jobs by wave ----
+  // A part can run once all its children have run; siblings must deliver their messages to the parent in
+  // decreasing part index (the reference's float accumulation order, src/DynamicProgram.cpp:95,155-156), so a
+  // part also waits for its next-higher sibling.  wave(p) = max(max_child wave + 1, wave(next higher sibling) + 1).
+  jobs_.clear(); wave_first_.clear(); wave_count_.clear(); wave_maxmix_.clear();
   tmp_maps_ = 0;
-  for (int k = 0; k < max_parts_ - 1; ++k) {
+  std::vector<std::vector<int>> wave_of(ncomp);
+  int nwaves = 0;
+  for (int c = 0; c < ncomp; ++c) {
+    const auto& parts = m.comps[c];
+    const int np = (int)parts.size();
+    wave_of[c].assign(np, 0);
+    for (int p = np - 1; p >= 1; --p) {                 // children have larger indices than their parents
+      int t = 0;
+      for (int q = p + 1; q < np; ++q) {
+        if (parts[q].parentid == p) t = std::max(t, wave_of[c][q] + 1);                    // my children
+        if (parts[q].parentid == parts[p].parentid) t = std::max(t, wave_of[c][q] + 1);    // higher siblings first
+      }
+      wave_of[c][p] = t;
+      nwaves = std::max(nwaves, t + 1);
+    }
+  }
+  for (int k = 0; k < nwaves; ++k) {
     wave_first_.push_back((int)jobs_.size());
-    int cnt = 0;
-    std::vector<std::vector<char>> dummy;
+    int cnt = 0, mx = 1;
     for (int c = 0; c < ncomp; ++c) {
       const auto& parts = m.comps[c];
       const int np = (int)parts.size();
-      const int p = np - 1 - k;
-      if (p < 1) continue;
+      for (int p = np - 1; p >= 1; --p) {
+      if (wave_of[c][p] != k) continue;
       const Part& P = parts[p];
       const Part& Par = parts[P.parentid];
       PartJob J;
       memset(&J, 0, sizeof(J));
       J.nmix = (int)P.filterid.size(); J.pnmix = (int)Par.filterid.size();
+      mx = std::max(mx, std::max(J.nmix, 1));
       bool first_touch = true;                       // is p the highest-index child of its parent?
       for (int q = p + 1; q < np; ++q) if (parts[q].parentid == P.parentid) first_touch = false;
       J.first_touch = first_touch ? 1 : 0;
@@ -199,8 +218,10 @@ void Engine::build_tables() {
       J.tmp_base = cnt * kMaxMix;
       jobs_.push_back(J);
       ++cnt;
+      }
     }
     wave_count_.push_back(cnt);
+    wave_maxmix_.push_back(mx);
     tmp_maps_ = std::max(tmp_maps_, cnt * kMaxMix);
   }
   roots_.clear();
@@ -413,7 +434,8 @@ void Engine::run_dp_min() {
     if (wave_count_[wv] == 0) continue;
     const PartJob* dj = d_jobs_ + wave_first_[wv];
     launches_ += launch_dt_rows_tab(g_, d_g_, b_, d_rg_level_, d_rg_row0_, nrg_, max_ow_, dj, wave_count_[wv], nf, nwork_, ncm_, tmp_maps_, stream_);
-    launches_ += launch_dt_cols_tab(g_, d_g_, b_, d_cg_level_, d_cg_col0_, ncg_, max_oh_, dj, wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, stream_);
+    launches_ += launch_dt_cols_tab(g_, d_g_, b_, d_cg_level_, d_cg_col0_, ncg_, max_oh_, dj, wave_count_[wv], wave_maxmix_[wv], nf, nwork_, ncm_, npm_,
+                                    tmp_maps_, stream_);
   }
   // root scores (reference computes rootv/rooti at the end of min(), src/DynamicProgram.cpp:163-171)
   launches_ += launch_root(g_, d_g_, b_, d_roots_, model_.ncomponents(), nf, nwork_, 0.f, nullptr, nullptr, 0, stream_);

@@ -87,7 +87,7 @@ class Engine {
   float* d_wgeneric_ = nullptr;
   int *d_foff_ = nullptr, *d_fkh_ = nullptr, *d_fkw_ = nullptr;
   std::vector<PartJob> jobs_;                 // ordered by wave
-  std::vector<int> wave_first_, wave_count_;
+  std::vector<int> wave_first_, wave_count_, wave_maxmix_;
   std::vector<RootJob> roots_;
   PartJob* d_jobs_ = nullptr;
   RootJob* d_roots_ = nullptr;

@@ -152,23 +152,33 @@ class Candidate:
 
 
 def _unpack_candidates(handle, free=True):
+    """pbd_candidates -> list of Candidate (one bulk export call, then numpy views)."""
     L = _lib.lib()
-    out = []
     n = L.pbd_candidates_count(handle)
-    for i in range(n):
-        npart = L.pbd_candidates_nparts(handle, i)
-        fr, lv, cp, sc = C.c_int(), C.c_int(), C.c_int(), C.c_float()
-        xs, ys, ms = (np.empty(npart, np.int32) for _ in range(3))
-        rc = np.empty(npart * 4, np.int32)
-        _lib.check(L.pbd_candidates_get(handle, i, C.byref(fr), C.byref(lv), C.byref(cp), C.byref(sc), xs, ys, ms, rc))
-        c = Candidate()
-        c.frame, c.level, c.component_ = fr.value, lv.value, cp.value
-        conf = np.zeros(npart, np.float32)
-        conf[0] = sc.value                                       # root = rootv, others 0.0 (DynamicProgram.cpp:241-244)
-        c.confidence_ = conf
-        c.parts_ = rc.reshape(npart, 4)
-        c.x, c.y, c.m = xs, ys, ms
-        out.append(c)
+    out = []
+    if n:
+        mp = max(L.pbd_candidates_nparts(handle, 0), 1)
+        meta = np.empty((n, 4), np.int32)
+        scores = np.empty(n, np.float32)
+        while True:
+            parts = np.empty((n, mp, 7), np.int32)
+            rc = L.pbd_candidates_export(handle, meta.reshape(-1), scores, parts.reshape(-1), mp)
+            if rc == 0:
+                break
+            mp *= 2                                              # components with more parts than the first candidate
+            if mp > 4096:
+                _lib.check(rc)
+        conf = np.zeros((n, mp), np.float32)
+        conf[:, 0] = scores                                      # root = rootv, others 0.0 (DynamicProgram.cpp:241-244)
+        for i in range(n):
+            c = Candidate()
+            npart = int(meta[i, 3])
+            c.frame, c.level, c.component_ = int(meta[i, 0]), int(meta[i, 1]), int(meta[i, 2])
+            c.confidence_ = conf[i, :npart]
+            p = parts[i, :npart]
+            c.parts_ = p[:, 3:7]
+            c.x, c.y, c.m = p[:, 0], p[:, 1], p[:, 2]
+            out.append(c)
     if free:
         L.pbd_candidates_free(handle)
     return out

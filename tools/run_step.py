@@ -1,0 +1,33 @@
+"""Runs a few steps of the hot path (device-resident frames) -- the command profiled under ncu."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from partsbaseddetector_b200 import Model, PartsBasedDetector  # noqa: E402
+from partsbaseddetector_b200.synth import synth_frames  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--h", type=int, default=480)
+ap.add_argument("--w", type=int, default=640)
+ap.add_argument("--fast", action="store_true")
+ap.add_argument("--max-levels", type=int, default=0)
+a = ap.parse_args()
+frames = synth_frames(min(a.batch, 4), a.h, a.w)
+frames = np.ascontiguousarray(np.concatenate([frames] * ((a.batch + 3) // 4))[:a.batch])
+dev = torch.from_numpy(frames).cuda()
+det = PartsBasedDetector(device=0, stream=torch.cuda.current_stream().cuda_stream)
+det.distributeModel(Model.load_bin(os.path.join(ROOT, "tests", "golden", "Person_26parts.pbdm")))
+det.set_option("exact", 0 if a.fast else 1)
+det.set_option("max_levels", a.max_levels)
+det.set_option("thresh", -1.14)
+det.set_option("timing", 1)
+for _ in range(a.steps):
+    det.enqueue_device(dev.data_ptr(), a.batch, a.h, a.w, 3)
+torch.cuda.synchronize()
+print(det.stage_times_ms(), "launches", det.launch_count())
