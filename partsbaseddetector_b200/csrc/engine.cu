@@ -79,7 +79,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
   void* ptrs[] = {d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
-                  d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.ixdt, b_.iyraw, b_.ik,
+                  d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_, d_rg_level_, d_rg_row0_,
                   d_cg_level_, d_cg_col0_, d_hits_, d_nhits_, d_xym_, d_scratch_i_};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -374,6 +374,7 @@ void Engine::alloc_batch() {
   ensure(b_.resp, cap_resp_, n * ct * model_.nfilters());
   ensure(b_.work, cap_work_, n * ct * std::max(nwork_, 1));
   ensure(b_.tmp, cap_tmp_, n * ct * std::max(tmp_maps_, 1));
+  ensure(b_.val, cap_val_, n * ct * std::max(tmp_maps_, 1));
   ensure(b_.ixdt, cap_ixdt_, n * ct * std::max(ncm_, 1));
   ensure(b_.iyraw, cap_iyraw_, n * ct * std::max(ncm_, 1));
   ensure(b_.ik, cap_ik_, n * ct * std::max(npm_, 1));
@@ -438,7 +439,7 @@ void Engine::run_dp_min() {
                                     tmp_maps_, stream_);
   }
   // root scores (reference computes rootv/rooti at the end of min(), src/DynamicProgram.cpp:163-171)
-  launches_ += launch_root(g_, d_g_, b_, d_roots_, model_.ncomponents(), nf, nwork_, 0.f, nullptr, nullptr, 0, stream_);
+  launches_ += launch_root(g_, d_g_, b_, d_roots_, model_.ncomponents(), nf, nwork_, stream_);
   check_cuda(cudaGetLastError(), "DP launch");
   stage_ = 4;
 }

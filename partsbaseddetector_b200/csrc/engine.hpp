@@ -103,7 +103,7 @@ class Engine {
   DeviceBuffers b_{};
   uint8_t* d_frames_own_ = nullptr; size_t cap_frames_ = 0;
   uint8_t* h_pinned_ = nullptr; size_t cap_pinned_ = 0;
-  size_t cap_pyr_ = 0, cap_hist_ = 0, cap_norm_ = 0, cap_feat_ = 0, cap_resp_ = 0, cap_work_ = 0, cap_tmp_ = 0,
+  size_t cap_pyr_ = 0, cap_hist_ = 0, cap_norm_ = 0, cap_feat_ = 0, cap_resp_ = 0, cap_work_ = 0, cap_tmp_ = 0, cap_val_ = 0,
          cap_ixdt_ = 0, cap_iyraw_ = 0, cap_ik_ = 0, cap_rootv_ = 0, cap_rooti_ = 0;
   // tables depending on the batch geometry
   int *d_xofs_ = nullptr, *d_yofs_ = nullptr; short *d_xalpha_ = nullptr, *d_ybeta_ = nullptr;

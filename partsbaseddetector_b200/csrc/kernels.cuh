@@ -6,7 +6,7 @@
 //   feat   f32  [n][cells_total][flen]    HOG features, HWC (reference featm layout, src/HOGFeatures.cpp:180)
 //   resp   f32  [n][nfilters][cells_total]  part-filter responses, planar per filter
 //   work   f32  [n][nwork][cells_total]   working scores of non-leaf parts (response + child messages)
-//   tmp    f32  [n][njobs*MAXMIX][cells_total]  row-pass output of the part(s) currently processed
+//   tmp    f32  [n][njobs*MAXMIX][cells_total]  row-pass output of the part(s) currently processed (val: column-pass output)
 //   ixdt   u16  [n][ncm][cells_total]     row-pass argmax per (component, part, child mixture)
 //   iyraw  u16  [n][ncm][cells_total]     column-pass argmax (not yet composed, see dt.cu)
 //   ik     u8   [n][npm][cells_total]     best child mixture per (component, part, parent mixture)
@@ -73,7 +73,8 @@ struct DeviceBuffers {
   float* feat;
   float* resp;
   float* work;
-  float* tmp;
+  float* tmp;      // row-pass output
+  float* val;      // column-pass output (fully transformed child maps of the current wave)
   uint16_t* ixdt;
   uint16_t* iyraw;
   uint8_t* ik;
@@ -115,7 +116,7 @@ int launch_dt_cols_tab(const Geometry& g, const Geometry* d_g, const DeviceBuffe
                        int max_oh, const PartJob* d_jobs, int njobs, int max_mix, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
                        cudaStream_t s);
 int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const RootJob* d_roots, int ncomp, int nfilters, int nwork,
-                float thresh, Hit* d_hits, int* d_nhits, int max_hits, cudaStream_t s);
+                cudaStream_t s);
 
 int launch_hits(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int ncomp, float thresh, Hit* d_hits, int* d_nhits,
                 int max_hits, cudaStream_t s);
