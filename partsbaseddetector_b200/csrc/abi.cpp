@@ -322,15 +322,27 @@ int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int 
     for (int i = 0; i < n_maps; ++i) REQUIRE(h_defw4[4 * i] > 0.f && h_defw4[4 * i + 2] > 0.f, "quadratic weights must be > 0");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t cells = (size_t)n_maps * h * w;
-    float *d_w = nullptr, *d_tmp = nullptr; int* d_a = nullptr; uint16_t *d_ixr = nullptr, *d_iyr = nullptr;
-    cu(cudaMalloc(&d_w, (size_t)n_maps * 4 * sizeof(float)), "cudaMalloc"); cu(cudaMalloc(&d_a, (size_t)n_maps * 2 * sizeof(int)), "cudaMalloc");
+    PassGeom pgs[2];
+    memset(pgs, 0, sizeof(pgs));
+    pgs[0].n_levels = pgs[1].n_levels = 1;
+    pgs[0].nlines[0] = h; pgs[0].N[0] = w; pgs[1].nlines[0] = w; pgs[1].N[0] = h;
+    std::vector<PassMap> maps(2 * (size_t)n_maps);
+    for (int i = 0; i < n_maps; ++i) {
+      PassMap R{}, Cc{};
+      R.in_buf = 0; R.in_off = R.out_off = R.ptr_off = (unsigned long long)i * h * w;
+      R.w_sq = h_defw4[4 * i]; R.w_lin = h_defw4[4 * i + 1]; R.os = h_anchor_xy[2 * i];
+      Cc = R; Cc.w_sq = h_defw4[4 * i + 2]; Cc.w_lin = h_defw4[4 * i + 3]; Cc.os = h_anchor_xy[2 * i + 1];
+      maps[i] = R; maps[n_maps + i] = Cc;
+    }
+    float* d_tmp = nullptr; uint16_t *d_ixr = nullptr, *d_iyr = nullptr; PassGeom* d_pg = nullptr; PassMap* d_maps = nullptr;
+    cu(cudaMalloc(&d_pg, sizeof(pgs)), "cudaMalloc"); cu(cudaMalloc(&d_maps, maps.size() * sizeof(PassMap)), "cudaMalloc");
     cu(cudaMalloc(&d_tmp, cells * sizeof(float)), "cudaMalloc"); cu(cudaMalloc(&d_ixr, cells * 2), "cudaMalloc"); cu(cudaMalloc(&d_iyr, cells * 2), "cudaMalloc");
-    cu(cudaMemcpyAsync(d_w, h_defw4, (size_t)n_maps * 4 * sizeof(float), cudaMemcpyHostToDevice, s), "H2D");
-    cu(cudaMemcpyAsync(d_a, h_anchor_xy, (size_t)n_maps * 2 * sizeof(int), cudaMemcpyHostToDevice, s), "H2D");
-    launch_dt2d_standalone(d_in, n_maps, h, w, d_w, d_a, d_tmp, d_out, d_ix, d_iy, d_ixr, d_iyr, backptr_mode, s);
+    cu(cudaMemcpyAsync(d_pg, pgs, sizeof(pgs), cudaMemcpyHostToDevice, s), "H2D");
+    cu(cudaMemcpyAsync(d_maps, maps.data(), maps.size() * sizeof(PassMap), cudaMemcpyHostToDevice, s), "H2D");
+    launch_dt2d_standalone(d_in, n_maps, h, w, d_pg, d_maps, d_tmp, d_out, d_ix, d_iy, d_ixr, d_iyr, backptr_mode, s);
     cu(cudaGetLastError(), "dt2d launch");
     cu(cudaStreamSynchronize(s), "dt2d sync");
-    cudaFree(d_w); cudaFree(d_a); cudaFree(d_tmp); cudaFree(d_ixr); cudaFree(d_iyr);
+    cudaFree(d_pg); cudaFree(d_maps); cudaFree(d_tmp); cudaFree(d_ixr); cudaFree(d_iyr);
   });
 }
 int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, float* out, int32_t* ix,

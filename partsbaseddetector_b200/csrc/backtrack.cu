@@ -1,7 +1,7 @@
 // backtrack.cu -- DynamicProgram<float>::argmin (reference src/DynamicProgram.cpp:190-255): walk from each
 // root hit down the part tree through the back-pointers.  The DP (dt.cu) stores, per (component, part),
 //   ik[pm]     best child mixture for parent mixture pm at the parent's cell,
-//   ixdt[mm]   row-pass argmax of child mixture mm,   iyraw[mm]  column-pass argmax of child mixture mm,
+//   ixdt[mm]   row-pass argmax of child mixture mm (stored [x][y]),   iyraw[mm]  column-pass argmax ([y][x]),
 // and the reference's Ix/Iy/Ik Mats are recovered on the fly:
 //   Ik[p][pm](y,x) = k = ik[pm](y,x)
 //   Ix[p][pm](y,x) = ixdt[k](y,x)
@@ -37,12 +37,12 @@ backtrack(const Geometry* __restrict__ g, const int* __restrict__ parent, const 
     const int k = ik[((size_t)h.frame * npm + pm_slot[(h.comp * kMaxParts + p) * kMaxMix + m]) * ct + cell];
     const size_t cmb = ((size_t)h.frame * ncm + cm_slot[(h.comp * kMaxParts + p) * kMaxMix + k]) * ct;
     int xp, yp;
-    if (mode == 0) {
-      xp = ixdt[cmb + cell];
+    if (mode == 0) {                                                   // ixdt is stored transposed: [x][y]
+      xp = ixdt[cmb + L.cell_off + (size_t)x * L.oh + y];
       yp = iyraw[cmb + L.cell_off + (size_t)y * L.ow + xp];
     } else {
       yp = iyraw[cmb + cell];
-      xp = ixdt[cmb + L.cell_off + (size_t)yp * L.ow + x];
+      xp = ixdt[cmb + L.cell_off + (size_t)x * L.oh + yp];
     }
     xs[p] = xp; ys[p] = yp; ms[p] = k;
   }
@@ -59,12 +59,12 @@ expand_backptr(int cell_off, int oh, int ow, size_t ct, int frame, int ncm, int 
   const int k = ik[((size_t)frame * npm + pm_slot) * ct + cell];
   const size_t cmb = ((size_t)frame * ncm + cm_slots[k]) * ct;
   int xp, yp;
-  if (mode == 0) {
-    xp = ixdt[cmb + cell];
+  if (mode == 0) {                                                     // ixdt is stored transposed: [x][y]
+    xp = ixdt[cmb + cell_off + (size_t)x * oh + y];
     yp = iyraw[cmb + cell_off + (size_t)y * ow + xp];
   } else {
     yp = iyraw[cmb + cell];
-    xp = ixdt[cmb + cell_off + (size_t)yp * ow + x];
+    xp = ixdt[cmb + cell_off + (size_t)x * oh + yp];
   }
   ix[idx] = xp; iy[idx] = yp; ikout[idx] = k;
 }

@@ -30,22 +30,39 @@ namespace pbd {
 namespace {
 
 constexpr int kRing = 8;          // ring window (stack entries kept in shared memory per lane)
+constexpr int kPassWarps = 4;
 
 struct Quad {
   double a, b, a2;   // a2 = 2*a (exact), reference evaluates 2*a*(x1-x0) left to right
+  double r1;         // correctly rounded 1/(2a): reciprocal of the divisor for adjacent samples (x1-x0 = 1)
 };
 __device__ __forceinline__ Quad make_quad(float w_sq, float w_lin) {
   Quad f;
   f.a = (double)(-w_sq);          // Quadratic(-w[0], -w[1]), src/DynamicProgram.cpp:126-127
   f.b = (double)(-w_lin);
   f.a2 = __dmul_rn(2.0, f.a);
+  f.r1 = __drcp_rn(f.a2);
   return f;
 }
-// Quadratic::operator()(x0,x1,y0,y1), include/DistanceTransform.hpp:98-100
-__device__ __forceinline__ float isect(const Quad& f, int x0, int x1, float y0, float y1) {
+// Quadratic::operator()(x0,x1,y0,y1), include/DistanceTransform.hpp:98-100, result rounded to float as `T s = f(...)`
+__device__ __forceinline__ float isect(const Quad& f, int x0, int x1, double y0, double y1) {
   const int d = x1 - x0;
+  if (d == 1) {
+    // adjacent samples (the common case): b*1 = b and a*(x1^2-x0^2) = a*(2*x1-1) are the reference's own values;
+    // the quotient num/(2a) is formed with a Markstein correction step from the precomputed reciprocal.  It is
+    // within 1 ulp(double) of the correctly rounded quotient, so its float rounding equals the reference's
+    // double-division-then-float unless it lies within 2 ulp of a float rounding boundary (probability ~2^-27):
+    // those cases, and anything not comfortably normal, take the exact division below.
+    const double num = __dadd_rn(__dsub_rn(__dsub_rn(y1, y0), f.b), __dmul_rn(f.a, (double)(2 * x1 - 1)));
+    const double q0 = __dmul_rn(num, f.r1);
+    const double q1 = __fma_rn(__fma_rn(-f.a2, q0, num), f.r1, q0);
+    const int lo = __double2loint(q1) & 0x1FFFFFFF;
+    const double aq = fabs(q1);
+    if (abs(lo - 0x10000000) > 2 && aq < 1e30 && aq > 1e-30) return (float)q1;
+    return (float)__ddiv_rn(num, f.a2);
+  }
   const double dd = (double)d;
-  const double t = __dsub_rn(__dsub_rn((double)y1, (double)y0), __dmul_rn(f.b, dd));
+  const double t = __dsub_rn(__dsub_rn(y1, y0), __dmul_rn(f.b, dd));
   const double num = __dadd_rn(t, __dmul_rn(f.a, (double)(x1 * x1 - x0 * x0)));
   return (float)__ddiv_rn(num, __dmul_rn(f.a2, dd));
 }
@@ -54,17 +71,19 @@ __device__ __forceinline__ float envelope(const Quad& f, int x, float y) {
   return (float)__dadd_rn(__dadd_rn(__dmul_rn(f.a, (double)(x * x)), __dmul_rn(f.b, (double)x)), (double)y);
 }
 
-// per-warp shared-memory ring: [slot][lane]
+// per-warp shared-memory ring: [slot][lane]; vp = v | (v of the entry below << 16), 0xFFFF = none
 struct Ring {
   float z[kRing][32];
   float y[kRing][32];
-  unsigned short v[kRing][32];
+  unsigned int vp[kRing][32];
 };
 
 // One lane's 1-D transform.  loady(q) = src[q] (called for q = 0..N-1 in order, and again for deep-pop reloads);
 // emit(i, val, v) stores dst[i] = val, ptr[i] = v (may be called more than once for an i; the last call wins).
-template <int MAXN, typename LoadY, typename Emit>
-__device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, Ring& R, int lane, float* zb, unsigned short* vb,
+// zb/pb: backing store of the envelope as a linked list threaded through the sample index (zb[q] = break point of
+// the parabola pushed at q, pb[q] = the sample below it), written in lock step across lanes (coalesced).
+template <typename LoadY, typename Emit>
+__device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, Ring& R, int lane, float* zb, unsigned short* pb,
                                                 LoadY loady, Emit emit) {
   const float pos_lo = (float)os0, pos_hi = (float)(os0 + N - 1);
   auto retire = [&](int j, float znext) {
@@ -74,27 +93,30 @@ __device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, R
     const int lo = (zj < pos_lo) ? os0 : (int)floorf(fminf(zj, pos_hi + 1.f)) + 1;
     const int hi = (znext >= pos_hi) ? os0 + N - 1 : (int)floorf(fmaxf(znext, pos_lo - 1.f));
     if (lo > hi) return;
-    const int v = R.v[slot][lane];
+    const int v = R.vp[slot][lane] & 0xFFFF;
     const float y = R.y[slot][lane];
     for (int pos = lo; pos <= hi; ++pos) emit(pos - os0, envelope(f, pos - v, y), v);
   };
   int k = 0, ret = 0;
-  int vt = 0;
-  float yt = loady(0), zt = -INFINITY;
-  R.z[0][lane] = zt; R.y[0][lane] = yt; R.v[0][lane] = 0;
-  zb[0] = zt; vb[0] = 0;
+  int vt = 0, pt = 0xFFFF;
+  float ytf = loady(0), zt = -INFINITY;
+  double yt = (double)ytf;
+  R.z[0][lane] = zt; R.y[0][lane] = ytf; R.vp[0][lane] = 0xFFFF0000u;
+  zb[0] = zt; pb[0] = 0xFFFF;
   for (int q = 1; q < N; ++q) {                                   // :160-170
-    const float yq = loady(q);
+    const float yqf = loady(q);
+    const double yq = (double)yqf;
     float s = isect(f, vt, q, yt, yq);
     while (s <= zt && k > 0) {
       --k;
       const int slot = k & (kRing - 1);
       if (k < ret) {                                              // popped below the ring: reload from the backing store
         ret = k;
-        const int vv = vb[k];
-        R.v[slot][lane] = (unsigned short)vv; R.z[slot][lane] = zb[k]; R.y[slot][lane] = loady(vv);
+        const int vv = pt;                                        // the entry below the one just popped
+        R.vp[slot][lane] = (unsigned)vv | ((unsigned)pb[vv] << 16); R.z[slot][lane] = zb[vv]; R.y[slot][lane] = loady(vv);
       }
-      vt = R.v[slot][lane]; yt = R.y[slot][lane]; zt = R.z[slot][lane];
+      const unsigned vp = R.vp[slot][lane];
+      vt = vp & 0xFFFF; pt = vp >> 16; ytf = R.y[slot][lane]; yt = (double)ytf; zt = R.z[slot][lane];
       s = isect(f, vt, q, yt, yq);
     }
     ++k;
@@ -103,131 +125,75 @@ __device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, R
       ++ret;
     }
     const int slot = k & (kRing - 1);
-    R.v[slot][lane] = (unsigned short)q; R.y[slot][lane] = yq; R.z[slot][lane] = s;
-    zb[k] = s; vb[k] = (unsigned short)q;
-    vt = q; yt = yq; zt = s;
+    R.vp[slot][lane] = (unsigned)q | ((unsigned)vt << 16); R.y[slot][lane] = yqf; R.z[slot][lane] = s;
+    zb[q] = s; pb[q] = (unsigned short)vt;
+    pt = vt; vt = q; yt = yq; zt = s;
   }
   for (int j = ret; j <= k; ++j) retire(j, j < k ? R.z[(j + 1) & (kRing - 1)][lane] : INFINITY);
 }
 
-// Warp-cooperative source of one row per lane: the 32 rows are staged through a 32x32 shared-memory tile
-// (coalesced 128-byte loads, conflict-free transposed reads).  The main loop asks for q = 0,1,2,... in lock
-// step across the warp, so the tile is refilled every 32 columns; deep-pop reloads of older samples go to
-// global memory.  All 32 lanes must call get() for every q of the main sequence (inactive lanes included).
-struct RowTile {
-  float (*tile)[33];
-  const float* src0;     // first row of the group
-  const float* mine;     // this lane's row (a valid row for inactive lanes)
-  int nrows, N, lane, myrow, q0;
-  __device__ __forceinline__ float get(int q) {
+// ---------------------------------------------------------------------------------------------------
+// One pass of the separable transform over every map of a wave: each lane owns one contiguous line of N samples
+// of some (map, line); lines of all maps of a level are packed 32 per warp so that small pyramid levels still
+// fill their warps.  Input lines are staged through a 32x32 shared-memory tile (coalesced 128-byte loads,
+// conflict-free transposed reads); the output is written TRANSPOSED (out[i*nlines + line]), which makes the
+// stores of adjacent lanes adjacent in memory and hands the next pass contiguous lines again:
+//   rows pass:  in [y][x] (responses / working scores) -> tmp  [x][y], ixdt  [x][y]
+//   cols pass:  in tmp [x][y]                           -> val  [y][x], iyraw [y][x]
+// ---------------------------------------------------------------------------------------------------
+template <int MAXN>
+__global__ void __launch_bounds__(kPassWarps * 32)
+dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int nmaps, const float* __restrict__ inA, size_t strideA,
+        const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out, unsigned short* __restrict__ ptr,
+        size_t stride_ptr) {
+  __shared__ Ring rings[kPassWarps];
+  __shared__ float tiles[kPassWarps][32][33];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int w = blockIdx.x * kPassWarps + wib;                          // warp index -> (level, first item)
+  int l = 0, nlines = 0, items = 0;
+  for (; l < pg->n_levels; ++l) {
+    nlines = pg->nlines[l];
+    items = nlines * nmaps;
+    const int nw = (items + 31) >> 5;
+    if (w < nw) break;
+    w -= nw;
+  }
+  if (l >= pg->n_levels) return;                                  // warp-uniform
+  const int frame = blockIdx.y;
+  const int N = pg->N[l];
+  const size_t cell_off = (size_t)pg->cell_off[l];
+  const int t0 = w * 32;
+  const bool active = t0 + lane < items;
+  const int t = active ? t0 + lane : t0;                          // inactive lanes shadow the warp's first item and discard results
+  const int mi = t / nlines, line = t - mi * nlines;
+  const PassMap M = maps[mi];
+  const float* src = (M.in_buf ? inB + (size_t)frame * strideB : inA + (size_t)frame * strideA) + M.in_off + cell_off + (size_t)line * N;
+  float* dst = out + (size_t)frame * stride_out + M.out_off + cell_off + line;
+  unsigned short* dp = ptr + (size_t)frame * stride_ptr + M.ptr_off + cell_off + line;
+  const Quad f = make_quad(M.w_sq, M.w_lin);
+  float zb[MAXN];
+  unsigned short pb[MAXN];
+  float (*tile)[33] = tiles[wib];
+  int q0 = -64;
+  auto loady = [&](int q) -> float {
+    // the main loop asks for q = 0,1,2,... in lock step across the warp: refill the tile every 32 samples;
+    // deep-pop reloads of older samples go to global memory
     if (q >= q0 + 32 && (q & 31) == 0) {
       __syncwarp();
-      for (int i = 0; i < nrows; ++i)
-        if (q + lane < N) tile[i][lane] = __ldg(src0 + (size_t)i * N + q + lane);
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const float* p = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, i);
+        if (q + lane < N) tile[i][lane] = __ldg(p + q + lane);
+      }
       __syncwarp();
       q0 = q;
     }
-    if (q >= q0) return tile[myrow][q - q0];
-    return __ldg(mine + q);
-  }
-};
-
-// ---------------------------------------------------------------------------------------------------
-// Row pass: one lane per row of one (frame, job, child mixture, level) map; 32 rows per warp.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kRowWarps = 4;
-
-template <int MAXN>
-__global__ void __launch_bounds__(kRowWarps * 32)
-dt_rows(const Geometry* __restrict__ g, const int* __restrict__ rg_level, const int* __restrict__ rg_row0, int nrg,
-        const PartJob* __restrict__ jobs, const float* __restrict__ resp, const float* __restrict__ work,
-        float* __restrict__ tmp, unsigned short* __restrict__ ixdt, int nfilters, int nwork, int ncm, int tmp_maps) {
-  __shared__ Ring rings[kRowWarps];
-  __shared__ float tiles[kRowWarps][32][33];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rg = blockIdx.x * kRowWarps + wib;
-  const PartJob& J = jobs[blockIdx.y / kMaxMix];
-  const int mm = blockIdx.y % kMaxMix;
-  if (rg >= nrg || mm >= J.nmix) return;                           // warp-uniform
-  const int frame = blockIdx.z;
-  const LevelDesc& L = g->lv[rg_level[rg]];
-  const int row0 = rg_row0[rg];
-  const int N = L.ow;
-  const int nrows = min(32, L.oh - row0);
-  const bool active = lane < nrows;
-  const int myrow = active ? lane : 0;                             // inactive lanes shadow row 0 and discard their results
-  const size_t ct = (size_t)g->cells_total;
-  const float* src0 = (J.in_is_work[mm] ? work + ((size_t)frame * nwork + J.in_slot[mm]) * ct
-                                        : resp + ((size_t)frame * nfilters + J.in_slot[mm]) * ct) + L.cell_off + (size_t)row0 * N;
-  float* dst = tmp + ((size_t)frame * tmp_maps + J.tmp_base + mm) * ct + L.cell_off + (size_t)(row0 + myrow) * N;
-  unsigned short* ptr = ixdt + ((size_t)frame * ncm + J.cm_slot[mm]) * ct + L.cell_off + (size_t)(row0 + myrow) * N;
-  const Quad f = make_quad(J.w[mm][0], J.w[mm][1]);
-  float zb[MAXN];
-  unsigned short vb[MAXN];
-  RowTile T{tiles[wib], src0, src0 + (size_t)myrow * N, nrows, N, lane, myrow, -64};
-  envelope_stream<MAXN>(N, f, J.ax[mm], rings[wib], lane, zb, vb, [&](int q) { return T.get(q); },
-                        [&](int i, float val, int v) { if (active) { dst[i] = val; ptr[i] = (unsigned short)v; } });
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Column pass: one lane per column (coalesced loads and stores), one warp per 32 columns of one
-// (frame, job, child mixture, level) map.  Writes the transformed map (val) and the raw y back-pointer.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kColWarps = 4;
-
-// software prefetch of a strided column: the next 4 samples are kept in registers so that the load latency
-// does not sit on the sequential critical path
-struct ColStream {
-  const float* src;
-  size_t stride;
-  int N, next_q;
-  float p0, p1, p2, p3;
-  __device__ __forceinline__ void init() {
-    next_q = 0;
-    p0 = __ldg(src);
-    p1 = N > 1 ? __ldg(src + stride) : 0.f;
-    p2 = N > 2 ? __ldg(src + 2 * stride) : 0.f;
-    p3 = N > 3 ? __ldg(src + 3 * stride) : 0.f;
-  }
-  __device__ __forceinline__ float get(int q) {
-    if (q == next_q) {
-      const float r = p0;
-      p0 = p1; p1 = p2; p2 = p3;
-      p3 = (q + 4 < N) ? __ldg(src + (size_t)(q + 4) * stride) : 0.f;
-      ++next_q;
-      return r;
-    }
-    return __ldg(src + (size_t)q * stride);                        // deep-pop reload
-  }
-};
-
-template <int MAXN>
-__global__ void __launch_bounds__(kColWarps * 32)
-dt_cols(const Geometry* __restrict__ g, const int* __restrict__ cg_level, const int* __restrict__ cg_col0, int ncg,
-        const PartJob* __restrict__ jobs, const float* __restrict__ tmp, float* __restrict__ val,
-        unsigned short* __restrict__ iyraw, int ncm, int tmp_maps) {
-  __shared__ Ring rings[kColWarps];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cg = blockIdx.x * kColWarps + wib;
-  const PartJob& J = jobs[blockIdx.y / kMaxMix];
-  const int mm = blockIdx.y % kMaxMix;
-  if (cg >= ncg || mm >= J.nmix) return;
-  const int frame = blockIdx.z;
-  const LevelDesc& L = g->lv[cg_level[cg]];
-  const int col = cg_col0[cg] + lane;
-  if (col >= L.ow) return;
-  const int N = L.oh, ow = L.ow;
-  const size_t ct = (size_t)g->cells_total;
-  const size_t mapoff = ((size_t)frame * tmp_maps + J.tmp_base + mm) * ct + L.cell_off + col;
-  float* dst = val + mapoff;
-  unsigned short* ptr = iyraw + ((size_t)frame * ncm + J.cm_slot[mm]) * ct + L.cell_off + col;
-  const Quad f = make_quad(J.w[mm][2], J.w[mm][3]);
-  float zb[MAXN];
-  unsigned short vb[MAXN];
-  ColStream S{tmp + mapoff, (size_t)ow, N};
-  S.init();
-  envelope_stream<MAXN>(N, f, J.ay[mm], rings[wib], lane, zb, vb, [&](int q) { return S.get(q); },
-                        [&](int i, float v_, int v) { dst[(size_t)i * ow] = v_; ptr[(size_t)i * ow] = (unsigned short)v; });
+    if (q >= q0) return tile[lane][q - q0];
+    return __ldg(src + q);
+  };
+  envelope_stream(N, f, M.os, rings[wib], lane, zb, pb, loady, [&](int i, float val, int v) {
+    if (active) { dst[(size_t)i * nlines] = val; dp[(size_t)i * nlines] = (unsigned short)v; }
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -307,49 +273,9 @@ hits_select(const Geometry* __restrict__ g, int ncomp, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Standalone 2-D DT (pbd_dt2d_f32 / config-5 microbenchmark): rows, columns, composition.
+// Standalone 2-D DT (pbd_dt2d_f32 / config-5 microbenchmark) uses dt_pass twice plus this composition.
+// Layouts: ixraw is [x][y] (row-pass output, transposed), iyraw is [y][x].
 // ---------------------------------------------------------------------------------------------------
-template <int MAXN>
-__global__ void __launch_bounds__(kRowWarps * 32)
-dt2d_rows(const float* __restrict__ in, int h, int w, const float* __restrict__ defw4, const int* __restrict__ anchor,
-          float* __restrict__ tmp, unsigned short* __restrict__ ix) {
-  __shared__ Ring rings[kRowWarps];
-  __shared__ float tiles[kRowWarps][32][33];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * kRowWarps + wib) * 32;
-  if (row0 >= h) return;
-  const int m = blockIdx.y;
-  const int nrows = min(32, h - row0);
-  const bool active = lane < nrows;
-  const int myrow = active ? lane : 0;
-  const float* src0 = in + ((size_t)m * h + row0) * w;
-  float* dst = tmp + ((size_t)m * h + row0 + myrow) * w;
-  unsigned short* ptr = ix + ((size_t)m * h + row0 + myrow) * w;
-  const Quad f = make_quad(defw4[m * 4 + 0], defw4[m * 4 + 1]);
-  float zb[MAXN];
-  unsigned short vb[MAXN];
-  RowTile T{tiles[wib], src0, src0 + (size_t)myrow * w, nrows, w, lane, myrow, -64};
-  envelope_stream<MAXN>(w, f, anchor[m * 2 + 0], rings[wib], lane, zb, vb, [&](int q) { return T.get(q); },
-                        [&](int i, float val, int v) { if (active) { dst[i] = val; ptr[i] = (unsigned short)v; } });
-}
-template <int MAXN>
-__global__ void __launch_bounds__(kColWarps * 32)
-dt2d_cols(const float* __restrict__ tmp, int h, int w, const float* __restrict__ defw4, const int* __restrict__ anchor,
-          float* __restrict__ out, unsigned short* __restrict__ iy) {
-  __shared__ Ring rings[kColWarps];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col = (blockIdx.x * kColWarps + wib) * 32 + lane;
-  if (col >= w) return;
-  const int m = blockIdx.y;
-  const size_t base = (size_t)m * h * w + col;
-  const Quad f = make_quad(defw4[m * 4 + 2], defw4[m * 4 + 3]);
-  float zb[MAXN];
-  unsigned short vb[MAXN];
-  ColStream S{tmp + base, (size_t)w, h};
-  S.init();
-  envelope_stream<MAXN>(h, f, anchor[m * 2 + 1], rings[wib], lane, zb, vb, [&](int q) { return S.get(q); },
-                        [&](int i, float val, int v) { out[base + (size_t)i * w] = val; iy[base + (size_t)i * w] = (unsigned short)v; });
-}
 // mode 0 (reference, :232-244): Iy[y][x] <- Iyraw[y][Ix[y][x]];  mode 1: Ix[y][x] <- Ixraw[Iy[y][x]][x]
 __global__ void __launch_bounds__(256)
 dt2d_compose(int h, int w, const unsigned short* __restrict__ ixraw, const unsigned short* __restrict__ iyraw,
@@ -360,44 +286,48 @@ dt2d_compose(int h, int w, const unsigned short* __restrict__ ixraw, const unsig
   const size_t base = (size_t)m * h * w;
   const size_t c = base + (size_t)y * w + x;
   if (mode == 0) {
-    const int xi = ixraw[c];
+    const int xi = ixraw[base + (size_t)x * h + y];
     ix[c] = (unsigned short)xi;
     iy[c] = iyraw[base + (size_t)y * w + xi];
   } else {
     const int yi = iyraw[c];
     iy[c] = (unsigned short)yi;
-    ix[c] = ixraw[base + (size_t)yi * w + x];
+    ix[c] = ixraw[base + (size_t)x * h + yi];
   }
 }
 
 }  // namespace
 
-int launch_dt_rows_tab(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_rg_level, const int* d_rg_row0, int nrg,
-                       int max_ow, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int tmp_maps, cudaStream_t s) {
-  if (nrg <= 0 || njobs <= 0) return 0;
-  dim3 grid((nrg + kRowWarps - 1) / kRowWarps, njobs * kMaxMix, g.n_frames);
-#define PBD_ROWS(M) dt_rows<M><<<grid, kRowWarps * 32, 0, s>>>(d_g, d_rg_level, d_rg_row0, nrg, d_jobs, b.resp, b.work, b.tmp, b.ixdt, nfilters, nwork, ncm, tmp_maps)
-  if (max_ow <= 160) PBD_ROWS(160);
-  else if (max_ow <= 512) PBD_ROWS(512);
-  else PBD_ROWS(1024);
-#undef PBD_ROWS
-  return 1;
+template <typename... A>
+static void launch_pass(int maxn, dim3 grid, cudaStream_t s, A... args) {
+  if (maxn <= 160) dt_pass<160><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else if (maxn <= 512) dt_pass<512><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else if (maxn <= 1024) dt_pass<1024><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else dt_pass<4096><<<grid, kPassWarps * 32, 0, s>>>(args...);
 }
 
-int launch_dt_cols_tab(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_cg_level, const int* d_cg_col0, int ncg,
-                       int max_oh, const PartJob* d_jobs, int njobs, int max_mix, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
-                       cudaStream_t s) {
-  if (ncg <= 0 || njobs <= 0) return 0;
-  (void)max_mix;
-  dim3 grid((ncg + kColWarps - 1) / kColWarps, njobs * kMaxMix, g.n_frames);
-#define PBD_COLS(M) dt_cols<M><<<grid, kColWarps * 32, 0, s>>>(d_g, d_cg_level, d_cg_col0, ncg, d_jobs, b.tmp, b.val, b.iyraw, ncm, tmp_maps)
-  if (max_oh <= 160) PBD_COLS(160);
-  else if (max_oh <= 512) PBD_COLS(512);
-  else PBD_COLS(1024);
-#undef PBD_COLS
+// number of warps a pass needs for `nmaps` maps
+static int pass_warps(const PassGeom& pg, int nmaps) {
+  int w = 0;
+  for (int l = 0; l < pg.n_levels; ++l) w += (pg.nlines[l] * nmaps + 31) / 32;
+  return w;
+}
+
+int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
+                   const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
+                   int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
+                   cudaStream_t s) {
+  if (nmaps <= 0 || njobs <= 0 || g.cells_total <= 0) return 0;
+  const size_t ct = (size_t)g.cells_total;
+  dim3 gr((pass_warps(pg_rows, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
+  launch_pass(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
+              ct * tmp_maps, b.ixdt, ct * ncm);
+  dim3 gc((pass_warps(pg_cols, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
+  launch_pass(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
+              ct * tmp_maps, b.iyraw, ct * ncm);
   dim3 gm((g.cells_total + 255) / 256, njobs, g.n_frames);
   mix_max<<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
-  return 2;
+  return 3;
 }
 
 int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const RootJob* d_roots, int ncomp, int nfilters, int nwork,
@@ -416,17 +346,18 @@ int launch_hits(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, 
   return 1;
 }
 
-int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const float* d_defw4, const int* d_anchor, float* d_tmp,
-                           float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
+int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const PassGeom* d_pg2 /* [rows, cols] */, const PassMap* d_maps2,
+                           float* d_tmp, float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
                            cudaStream_t s) {
   if (n_maps <= 0 || h <= 0 || w <= 0) return 0;
-  dim3 gr((h + 32 * kRowWarps - 1) / (32 * kRowWarps), n_maps), gc((w + 32 * kColWarps - 1) / (32 * kColWarps), n_maps);
-  if (w <= 160) dt2d_rows<160><<<gr, kRowWarps * 32, 0, s>>>(d_in, h, w, d_defw4, d_anchor, d_tmp, d_ixraw);
-  else if (w <= 512) dt2d_rows<512><<<gr, kRowWarps * 32, 0, s>>>(d_in, h, w, d_defw4, d_anchor, d_tmp, d_ixraw);
-  else dt2d_rows<4096><<<gr, kRowWarps * 32, 0, s>>>(d_in, h, w, d_defw4, d_anchor, d_tmp, d_ixraw);
-  if (h <= 160) dt2d_cols<160><<<gc, kColWarps * 32, 0, s>>>(d_tmp, h, w, d_defw4, d_anchor, d_out, d_iyraw);
-  else if (h <= 512) dt2d_cols<512><<<gc, kColWarps * 32, 0, s>>>(d_tmp, h, w, d_defw4, d_anchor, d_out, d_iyraw);
-  else dt2d_cols<4096><<<gc, kColWarps * 32, 0, s>>>(d_tmp, h, w, d_defw4, d_anchor, d_out, d_iyraw);
+  // maps are launched in chunks so that the warp index stays small; every map is h*w cells
+  PassGeom pr{}, pc{};
+  pr.n_levels = pc.n_levels = 1;
+  pr.nlines[0] = h; pr.N[0] = w; pc.nlines[0] = w; pc.N[0] = h;
+  dim3 gr((pass_warps(pr, n_maps) + kPassWarps - 1) / kPassWarps, 1), gc((pass_warps(pc, n_maps) + kPassWarps - 1) / kPassWarps, 1);
+  launch_pass(w, gr, s, d_pg2, d_maps2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0);
+  launch_pass(h, gc, s, d_pg2 + 1, d_maps2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out, (size_t)0,
+              d_iyraw, (size_t)0);
   dim3 gx((w + 255) / 256, h, n_maps);
   dt2d_compose<<<gx, 256, 0, s>>>(h, w, d_ixraw, d_iyraw, d_ix, d_iy, backptr_mode);
   return 3;

@@ -81,7 +81,7 @@ Engine::~Engine() {
   void* ptrs[] = {d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_, d_rg_level_, d_rg_row0_,
-                  d_cg_level_, d_cg_col0_, d_hits_, d_nhits_, d_xym_, d_scratch_i_};
+                  d_cg_level_, d_cg_col0_, d_hits_, d_nhits_, d_xym_, d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, b_.val};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_pinned_) cudaFreeHost(h_pinned_);
   for (int i = 0; i < 7; ++i) if (ev_[i]) cudaEventDestroy(ev_[i]);
@@ -358,6 +358,41 @@ void Engine::build_batch_tables() {
   up(d_rg_level_, cap_rg_level_, rgl); up(d_rg_row0_, cap_rg_row0_, rgr);
   up(d_cg_level_, cap_cg_level_, cgl); up(d_cg_col0_, cap_cg_col0_, cgc);
   check_cuda(cudaMemcpyAsync(d_g_, &g_, sizeof(Geometry), cudaMemcpyHostToDevice, stream_), "upload geometry");
+  // separable-transform passes: geometry (rows: lines = rows of length ow; cols: lines = columns of length oh) and the
+  // per-wave map tables (offsets depend on cells_total)
+  memset(&pg_rows_, 0, sizeof(pg_rows_)); memset(&pg_cols_, 0, sizeof(pg_cols_));
+  pg_rows_.n_levels = pg_cols_.n_levels = g.n_levels;
+  for (int l = 0; l < g.n_levels; ++l) {
+    pg_rows_.nlines[l] = g.lv[l].oh; pg_rows_.N[l] = g.lv[l].ow; pg_rows_.cell_off[l] = g.lv[l].cell_off;
+    pg_cols_.nlines[l] = g.lv[l].ow; pg_cols_.N[l] = g.lv[l].oh; pg_cols_.cell_off[l] = g.lv[l].cell_off;
+  }
+  const PassGeom pgs[2] = {pg_rows_, pg_cols_};
+  if (!d_pg_) { check_cuda(cudaMalloc(&d_pg_, 2 * sizeof(PassGeom)), "cudaMalloc pass geometry"); dev_bytes_ += 2 * sizeof(PassGeom); }
+  check_cuda(cudaMemcpyAsync(d_pg_, pgs, sizeof(pgs), cudaMemcpyHostToDevice, stream_), "upload pass geometry");
+  std::vector<PassMap> mr, mc;
+  wave_map_first_.assign(wave_first_.size(), 0); wave_map_count_.assign(wave_first_.size(), 0);
+  const unsigned long long ct = (unsigned long long)g.cells_total;
+  for (size_t wv = 0; wv < wave_first_.size(); ++wv) {
+    wave_map_first_[wv] = (int)mr.size();
+    for (int j = 0; j < wave_count_[wv]; ++j) {
+      const PartJob& J = jobs_[wave_first_[wv] + j];
+      for (int mm = 0; mm < J.nmix; ++mm) {
+        PassMap R{}, C{};
+        R.in_buf = J.in_is_work[mm]; R.in_off = (unsigned long long)J.in_slot[mm] * ct;
+        R.out_off = (unsigned long long)(J.tmp_base + mm) * ct; R.ptr_off = (unsigned long long)J.cm_slot[mm] * ct;
+        R.w_sq = J.w[mm][0]; R.w_lin = J.w[mm][1]; R.os = J.ax[mm];
+        C.in_buf = 0; C.in_off = R.out_off; C.out_off = R.out_off; C.ptr_off = R.ptr_off;
+        C.w_sq = J.w[mm][2]; C.w_lin = J.w[mm][3]; C.os = J.ay[mm];
+        mr.push_back(R); mc.push_back(C);
+      }
+    }
+    wave_map_count_[wv] = (int)mr.size() - wave_map_first_[wv];
+  }
+  ensure(d_maps_rows_, cap_maps_rows_, mr.size()); ensure(d_maps_cols_, cap_maps_cols_, mc.size());
+  if (!mr.empty()) {
+    check_cuda(cudaMemcpyAsync(d_maps_rows_, mr.data(), mr.size() * sizeof(PassMap), cudaMemcpyHostToDevice, stream_), "upload pass maps");
+    check_cuda(cudaMemcpyAsync(d_maps_cols_, mc.data(), mc.size() * sizeof(PassMap), cudaMemcpyHostToDevice, stream_), "upload pass maps");
+  }
   check_cuda(cudaStreamSynchronize(stream_), "sync batch tables");
 }
 
@@ -433,10 +468,9 @@ void Engine::run_dp_min() {
   const int nf = model_.nfilters();
   for (size_t wv = 0; wv < wave_first_.size(); ++wv) {
     if (wave_count_[wv] == 0) continue;
-    const PartJob* dj = d_jobs_ + wave_first_[wv];
-    launches_ += launch_dt_rows_tab(g_, d_g_, b_, d_rg_level_, d_rg_row0_, nrg_, max_ow_, dj, wave_count_[wv], nf, nwork_, ncm_, tmp_maps_, stream_);
-    launches_ += launch_dt_cols_tab(g_, d_g_, b_, d_cg_level_, d_cg_col0_, ncg_, max_oh_, dj, wave_count_[wv], wave_maxmix_[wv], nf, nwork_, ncm_, npm_,
-                                    tmp_maps_, stream_);
+    launches_ += launch_dt_wave(g_, d_g_, b_, pg_rows_, d_pg_, pg_cols_, d_pg_ + 1, d_maps_rows_ + wave_map_first_[wv],
+                                d_maps_cols_ + wave_map_first_[wv], wave_map_count_[wv], max_ow_, max_oh_, d_jobs_ + wave_first_[wv],
+                                wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, stream_);
   }
   // root scores (reference computes rootv/rooti at the end of min(), src/DynamicProgram.cpp:163-171)
   launches_ += launch_root(g_, d_g_, b_, d_roots_, model_.ncomponents(), nf, nwork_, stream_);

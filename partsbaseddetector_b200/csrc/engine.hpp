@@ -112,6 +112,10 @@ class Engine {
   int *d_rg_level_ = nullptr, *d_rg_row0_ = nullptr; size_t cap_rg_level_ = 0, cap_rg_row0_ = 0; int nrg_ = 0;
   int *d_cg_level_ = nullptr, *d_cg_col0_ = nullptr; size_t cap_cg_level_ = 0, cap_cg_col0_ = 0; int ncg_ = 0;
   int max_ow_ = 0, max_oh_ = 0;
+  PassGeom pg_rows_{}, pg_cols_{};
+  PassGeom* d_pg_ = nullptr;                   // [rows, cols]
+  PassMap *d_maps_rows_ = nullptr, *d_maps_cols_ = nullptr; size_t cap_maps_rows_ = 0, cap_maps_cols_ = 0;
+  std::vector<int> wave_map_first_, wave_map_count_;
   // candidates
   Hit* d_hits_ = nullptr; size_t cap_hits_ = 0;
   int* d_nhits_ = nullptr;

@@ -7,7 +7,7 @@
 //   resp   f32  [n][nfilters][cells_total]  part-filter responses, planar per filter
 //   work   f32  [n][nwork][cells_total]   working scores of non-leaf parts (response + child messages)
 //   tmp    f32  [n][njobs*MAXMIX][cells_total]  row-pass output of the part(s) currently processed (val: column-pass output)
-//   ixdt   u16  [n][ncm][cells_total]     row-pass argmax per (component, part, child mixture)
+//   ixdt   u16  [n][ncm][cells_total]     row-pass argmax per (component, part, child mixture), stored TRANSPOSED [x][y] per level
 //   iyraw  u16  [n][ncm][cells_total]     column-pass argmax (not yet composed, see dt.cu)
 //   ik     u8   [n][npm][cells_total]     best child mixture per (component, part, parent mixture)
 //   rootv  f32  [n][ncomp][cells_total], rooti u8 [n][ncomp][cells_total]
@@ -110,11 +110,24 @@ bool response_has_fast_path(const FilterBank& fb);
 int launch_response_tiles(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const FilterBank& fb, const int* d_tile_level,
                           const int* d_tile_first, int ntiles, int exact, cudaStream_t s);
 
-int launch_dt_rows_tab(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_rg_level, const int* d_rg_row0, int nrg,
-                       int max_ow, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int tmp_maps, cudaStream_t s);
-int launch_dt_cols_tab(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_cg_level, const int* d_cg_col0, int ncg,
-                       int max_oh, const PartJob* d_jobs, int njobs, int max_mix, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
-                       cudaStream_t s);
+// Geometry of one separable-transform pass: per level the number of lines, their length and the map offset.
+struct PassGeom {
+  int n_levels;
+  int nlines[kMaxLevels];
+  int N[kMaxLevels];
+  int cell_off[kMaxLevels];
+};
+// One map of a pass (frame-independent): element offsets from the buffers' frame base.
+struct PassMap {
+  unsigned long long in_off, out_off, ptr_off;
+  int in_buf;                  // 0: buffer A, 1: buffer B (rows pass: A = responses, B = working scores)
+  float w_sq, w_lin;           // deformation weights of this direction
+  int os;                      // anchor of this direction
+};
+int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
+                   const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
+                   int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
+                   cudaStream_t s);
 int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const RootJob* d_roots, int ncomp, int nfilters, int nwork,
                 cudaStream_t s);
 
@@ -133,8 +146,9 @@ int launch_backtrack(const Geometry& g, const Geometry* d_g, const DeviceBuffers
 int launch_expand_backptr(const Geometry& g, const DeviceBuffers& b, int frame, int level, int ncm, int npm, const int* d_cm_slots,
                           int pm_slot, int backptr_mode, int* d_ix, int* d_iy, int* d_ik, cudaStream_t s);
 
-// standalone 2-D DT over n_maps maps of h x w (config 5 microbenchmark / pbd_dt2d_f32)
-int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const float* d_defw4, const int* d_anchor, float* d_tmp,
+// standalone 2-D DT over n_maps maps of h x w (config 5 microbenchmark / pbd_dt2d_f32); d_pg2 = {rows, cols} geometry,
+// d_maps2 = n_maps row-pass maps followed by n_maps column-pass maps
+int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const PassGeom* d_pg2, const PassMap* d_maps2, float* d_tmp,
                            float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
                            cudaStream_t s);
 constexpr int kMaxDim = 1024;  // largest level width/height (cells) the DP kernels are instantiated for
