@@ -163,7 +163,8 @@ def run_gpu_arm(args):
     B = args.batch
     # every rank gets its own frames (frame-parallel sharding: global frame index = rank*B + i)
     uniq = min(B, args.unique_frames)
-    base = synth_frames(uniq, H, W, start=rank * B)
+    from partsbaseddetector_b200.sharding import frame_range
+    base = synth_frames(uniq, H, W, start=frame_range(rank, world, B)[0])
     host = torch.empty((B, H, W, C), dtype=torch.uint8, pin_memory=True)
     hnp = host.numpy()
     for i in range(B):
@@ -218,10 +219,8 @@ def run_gpu_arm(args):
     for _ in range(min(args.steps, 5)):
         det.enqueue_device(dev.data_ptr(), B, H, W, C)
         pdf_ms.append(det.stage_times_ms()["pdf"])
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    from partsbaseddetector_b200.sharding import max_over_ranks
+    ms_max = max_over_ranks(ms, device="cuda")
 
     # ---- end to end through the public API with host buffers: `e2e` ----
     for _ in range(max(1, args.warmup // 2)):
@@ -234,10 +233,7 @@ def run_gpu_arm(args):
         nc_total += len(c)
     torch.cuda.synchronize()
     e2e_s = time.time() - t0
-    t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_s = float(t2.item())
+    e2e_s = max_over_ranks(e2e_s, device="cuda")
     d2h = 4 + (nc_total // max(args.steps, 1)) * (24 + 3 * 80 * 4)
 
     if rank == 0:

@@ -1,0 +1,196 @@
+// pbd_b200.hpp -- header-only C++ mirror of the reference's interface for the detect() path, over the C-ABI
+// (pbd_b200.h).  Class and method names follow wg-perception/PartsBasedDetector so that caller code such as
+// src/demo.cpp:55-118 keeps its shape:
+//
+//   FileStorageModel model;  model.deserialize("Person_26parts.xml");          // src/demo.cpp:64-82
+//   PartsBasedDetector<float> pbd;  pbd.distributeModel(model);                  // :85-86
+//   vectorCandidate candidates;  pbd.detect(im, depth, candidates);              // :103
+//   Candidate::sort(candidates);                                                 // :111
+//
+// Images are passed as `pbd_b200::Mat` (rows, cols, channels, step, 8-bit data pointer); when OpenCV headers are
+// available a cv::Mat converts implicitly.  All numerics run in libpbd_b200.so on the GPU in single precision
+// (the reference's PartsBasedDetector<float>, src/demo.cpp:85); PartsBasedDetector<double> is intentionally not provided.
+#ifndef PBD_B200_HPP_
+#define PBD_B200_HPP_
+#include <algorithm>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pbd_b200.h"
+
+#if defined(__has_include)
+#if __has_include(<opencv2/core/core.hpp>)
+#include <opencv2/core/core.hpp>
+#define PBD_B200_HAVE_OPENCV 1
+#endif
+#endif
+
+namespace pbd_b200 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) {
+  if (rc != PBD_OK) throw Error(rc, pbd_last_error());     // the reference throws cv::Exception / asserts
+}
+
+// minimal 8-bit image view (cv::Mat CV_8UC1 / CV_8UC3, BGR interleaved)
+struct Mat {
+  int rows = 0, cols = 0, channels = 3;
+  size_t step = 0;                 // bytes per row
+  const uint8_t* data = nullptr;
+  Mat() {}
+  Mat(int r, int c, int ch, const uint8_t* d, size_t s = 0) : rows(r), cols(c), channels(ch), step(s ? s : (size_t)c * ch), data(d) {}
+  bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+#ifdef PBD_B200_HAVE_OPENCV
+  Mat(const cv::Mat& m) : rows(m.rows), cols(m.cols), channels(m.channels()), step(m.step), data(m.data) {   // NOLINT: implicit on purpose
+    if (!m.empty() && m.depth() != CV_8U) throw Error(PBD_E_UNSUPPORTED, "Unsupported image type");         // src/HOGFeatures.cpp:141-145
+  }
+#endif
+};
+
+struct Rect { int x = 0, y = 0, width = 0, height = 0; };
+
+typedef std::vector<float> vectorf;
+
+// reference include/Model.hpp:49-122 (getters) + include/FileStorageModel.hpp
+class Model {
+ protected:
+  pbd_model* h_ = nullptr;
+  void need() const { if (!h_) throw Error(PBD_E_STATE, "model is empty"); }
+  void header(int32_t hdr[8], float* th) const { need(); check(pbd_model_header(h_, hdr, th)); }
+
+ public:
+  Model() {}
+  virtual ~Model() { pbd_model_free(h_); }
+  Model(const Model&) = delete;
+  Model& operator=(const Model&) = delete;
+  const pbd_model* handle() const { need(); return h_; }
+  std::string name() const { need(); return pbd_model_name(h_); }
+  int nscales() const { int32_t h[8]; header(h, nullptr); return h[0]; }   // the reference keeps `interval` here (Model.hpp:112)
+  int binsize() const { int32_t h[8]; header(h, nullptr); return h[1]; }
+  int norient() const { int32_t h[8]; header(h, nullptr); return h[2]; }
+  int flen() const { int32_t h[8]; header(h, nullptr); return h[3]; }
+  int ncomponents() const { int32_t h[8]; header(h, nullptr); return h[7]; }
+  float thresh() const { int32_t h[8]; float t; header(h, &t); return t; }
+  virtual bool serialize(const std::string& filename) const = 0;
+  virtual bool deserialize(const std::string& filename) = 0;
+};
+
+class FileStorageModel : public Model {     // reference src/FileStorageModel.cpp:42-159
+ public:
+  bool serialize(const std::string& filename) const override { need(); check(pbd_model_save_xml(h_, filename.c_str())); return true; }
+  bool deserialize(const std::string& filename) override {
+    pbd_model* m = nullptr;
+    const int rc = pbd_model_load_xml(filename.c_str(), &m);
+    if (rc == PBD_E_IO) return false;           // cannot open: `if (!ok) return false;` (:100-101)
+    check(rc);
+    pbd_model_free(h_);
+    h_ = m;
+    return true;
+  }
+};
+
+// reference include/Candidate.hpp:56-99 (+ frame, level and per-part cell locations / mixtures)
+class Candidate {
+  std::vector<Rect> parts_;
+  vectorf confidence_;
+  int component_ = 0;
+
+ public:
+  int frame = 0, level = 0;
+  std::vector<int> x, y, mixture;
+  const std::vector<Rect>& parts() const { return parts_; }
+  const vectorf& confidence() const { return confidence_; }
+  void addPart(Rect r, float confidence) { parts_.push_back(r); confidence_.push_back(confidence); }
+  float score() const { return confidence_.size() > 0 ? confidence_[0] : -std::numeric_limits<float>::infinity(); }
+  void setComponent(int c) { component_ = c; }
+  int component() const { return component_; }
+  static bool descending(const Candidate& c1, const Candidate& c2) { return c1.score() > c2.score(); }
+  static void sort(std::vector<Candidate>& candidates) { std::stable_sort(candidates.begin(), candidates.end(), descending); }
+  Rect boundingBox() const {
+    Rect hull = parts_.at(0);
+    for (const Rect& r : parts_) {
+      const int x0 = std::min(hull.x, r.x), y0 = std::min(hull.y, r.y);
+      const int x1 = std::max(hull.x + hull.width, r.x + r.width), y1 = std::max(hull.y + hull.height, r.y + r.height);
+      hull.x = x0; hull.y = y0; hull.width = x1 - x0; hull.height = y1 - y0;
+    }
+    return hull;
+  }
+};
+typedef std::vector<Candidate> vectorCandidate;
+
+// reference include/PartsBasedDetector.hpp:152-175
+template <typename T>
+class PartsBasedDetector {
+  static_assert(sizeof(T) == sizeof(float), "the CUDA path computes in single precision (reference PartsBasedDetector<float>)");
+  pbd_detector* d_ = nullptr;
+  std::string name_;
+
+  static void append(pbd_candidates* c, vectorCandidate& out) {
+    const int n = pbd_candidates_count(c);
+    std::vector<int32_t> xs, ys, ms, rc;
+    for (int i = 0; i < n; ++i) {
+      const int np = pbd_candidates_nparts(c, i);
+      xs.resize(np); ys.resize(np); ms.resize(np); rc.resize(4 * (size_t)np);
+      int32_t frame, level, comp;
+      float score;
+      check(pbd_candidates_get(c, i, &frame, &level, &comp, &score, xs.data(), ys.data(), ms.data(), rc.data()));
+      Candidate cand;
+      cand.setComponent(comp);
+      cand.frame = frame; cand.level = level;
+      cand.x.assign(xs.begin(), xs.end()); cand.y.assign(ys.begin(), ys.end()); cand.mixture.assign(ms.begin(), ms.end());
+      for (int p = 0; p < np; ++p) {
+        Rect r; r.x = rc[4 * p]; r.y = rc[4 * p + 1]; r.width = rc[4 * p + 2]; r.height = rc[4 * p + 3];
+        cand.addPart(r, p == 0 ? score : 0.0f);            // src/DynamicProgram.cpp:241-244
+      }
+      out.push_back(cand);                                  // appended, never cleared (:250)
+    }
+    pbd_candidates_free(c);
+  }
+
+ public:
+  explicit PartsBasedDetector(int device = 0, void* cuda_stream = nullptr) : device_(device), stream_(cuda_stream) {}
+  ~PartsBasedDetector() { pbd_destroy(d_); }
+  PartsBasedDetector(const PartsBasedDetector&) = delete;
+  PartsBasedDetector& operator=(const PartsBasedDetector&) = delete;
+
+  void distributeModel(Model& model) {                      // src/PartsBasedDetector.cpp:102-127
+    pbd_destroy(d_);
+    d_ = nullptr;
+    check(pbd_create(model.handle(), device_, stream_, &d_));
+    name_ = model.name();
+  }
+  const std::string& name() const { return name_; }
+  void setOption(const char* key, double v) { need(); check(pbd_set_option(d_, key, v)); }
+
+  void detect(const Mat& im, vectorCandidate& candidates) { detect(im, Mat(), candidates); }   // :54-56
+  void detect(const Mat& im, const Mat& depth, vectorCandidate& candidates) {                  // :69-95 (depth is ignored there too)
+    (void)depth;
+    need();
+    if (im.empty()) throw Error(PBD_E_ARG, "empty image");
+    pbd_candidates* c = nullptr;
+    check(pbd_detect_batch_u8(d_, im.data, 1, im.rows, im.cols, im.channels, im.step, 0, &c));
+    append(c, candidates);
+  }
+  // batch of n equally sized frames, frame_stride bytes apart (0 = tightly packed)
+  void detectBatch(const Mat& first, int n, size_t frame_stride, vectorCandidate& candidates) {
+    need();
+    pbd_candidates* c = nullptr;
+    check(pbd_detect_batch_u8(d_, first.data, n, first.rows, first.cols, first.channels, first.step, frame_stride, &c));
+    append(c, candidates);
+  }
+  pbd_detector* handle() { need(); return d_; }
+
+ private:
+  void need() const { if (!d_) throw Error(PBD_E_STATE, "distributeModel() has not been called"); }
+  int device_;
+  void* stream_;
+};
+
+}  // namespace pbd_b200
+#endif  // PBD_B200_HPP_

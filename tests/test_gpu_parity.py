@@ -302,3 +302,23 @@ def test_errors_and_state_machine():
     d.set_option("max_candidates", 65536)
     with pytest.raises(PbdError):
         d.set_option("nonsense", 1)
+
+
+def test_cpp_adapter_demo_matches_python(tmp_path):
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "demo")
+    libdir = os.path.join(ROOT, "partsbaseddetector_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "demo.cpp"),
+                           "-L" + libdir, "-lpbd_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    img = synth_frame(3, 120, 160)
+    ppm = tmp_path / "f.ppm"
+    ppm.write_bytes(b"P6\n160 120\n255\n" + np.ascontiguousarray(img[:, :, ::-1]).tobytes())
+    d = detector("Person_26parts")
+    d.set_option("thresh", -1.2)
+    cands = d.detect(img)
+    r = subprocess.run([exe, os.path.join(GOLDEN, "Person_26parts.pbdm"), str(ppm), "-1.2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "Number of candidates: %d" % len(cands) in r.stdout
+    best = max(cands, key=lambda c: float(c.score()))
+    assert ("best: score %.6f level %d" % (float(best.score()), best.level)) in r.stdout

@@ -1,0 +1,93 @@
+"""Host-side logic that needs no GPU: sharding across ranks (gloo, world_size 2), the C++ adapter header, synthetic inputs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from partsbaseddetector_b200.sharding import frame_range, split_frames
+from partsbaseddetector_b200.synth import synth_frame, synth_frames
+
+
+def test_frame_ranges_are_disjoint_and_cover():
+    for world in (1, 2, 4, 8):
+        seen = []
+        for r in range(world):
+            seen += list(frame_range(r, world, 32))
+        assert seen == list(range(32 * world))
+        parts = split_frames(256 + 3, world)
+        assert sum(len(p) for p in parts) == 259 and max(map(len, parts)) - min(map(len, parts)) <= 1
+        assert [i for p in parts for i in p] == list(range(259))
+    with pytest.raises(ValueError):
+        frame_range(2, 2, 8)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from partsbaseddetector_b200.sharding import frame_range, max_over_ranks, sum_over_ranks
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    frames = frame_range(rank, world, 4)
+    # every rank generates only its own frames; the "timing" of rank r is r+1 -> max over ranks must be `world`
+    digest = int(sum(int(synth_frame(i, 24, 32).sum()) for i in frames))
+    tmax = max_over_ranks(rank + 1.0)
+    total = sum_over_ranks(len(frames))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, list(frames), digest, tmax, total))
+
+
+def test_two_rank_sharding_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 1, 2, 3] and res[1][1] == [4, 5, 6, 7]
+    assert res[0][3] == res[1][3] == 2.0 and res[0][4] == res[1][4] == 8.0
+    ref = [int(sum(int(synth_frame(i, 24, 32).sum()) for i in r)) for r in ([0, 1, 2, 3], [4, 5, 6, 7])]
+    assert [res[0][2], res[1][2]] == ref
+
+
+def test_synthetic_frames_are_reproducible():
+    a, b = synth_frame(5, 48, 64), synth_frames(2, 48, 64, start=4)[1]
+    assert a.dtype == np.uint8 and a.shape == (48, 64, 3) and np.array_equal(a, b)
+    assert a.std() > 10                      # non-degenerate gradients
+
+
+def test_cpp_adapter_compiles_and_fails_loudly_without_gpu(tmp_path):
+    exe = str(tmp_path / "demo")
+    libdir = os.path.join(ROOT, "partsbaseddetector_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "demo.cpp"),
+                           "-L" + libdir, "-lpbd_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 255 and "Usage" in r.stdout                       # -1, src/demo.cpp:58-61
+    r = subprocess.run([exe, "model.mat", "x.ppm"], capture_output=True, text=True)
+    assert r.returncode == 254 and "Unsupported model format" in r.stdout    # -2
+    r = subprocess.run([exe, str(tmp_path / "missing.xml"), "x.ppm"], capture_output=True, text=True)
+    assert r.returncode == 253 and "Error deserializing" in r.stdout         # -3
+    import torch
+    if not torch.cuda.is_available():
+        ppm = tmp_path / "f.ppm"
+        im = synth_frame(3, 120, 160)[:, :, ::-1]
+        ppm.write_bytes(b"P6\n160 120\n255\n" + np.ascontiguousarray(im).tobytes())
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "Person_26parts.pbdm"), str(ppm)], capture_output=True, text=True)
+        assert r.returncode == 251 and "no CUDA device" in r.stdout          # the CUDA path is the only implementation
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                                  text=True, timeout=600)
+    import json
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "frames/s"
