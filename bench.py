@@ -234,7 +234,7 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     e2e_s = time.time() - t0
     e2e_s = max_over_ranks(e2e_s, device="cuda")
-    d2h = 4 + (nc_total // max(args.steps, 1)) * (24 + 3 * 80 * 4)
+    d2h = 4 + (nc_total // max(args.steps, 1)) * (24 + 3 * 26 * 4)      # hit count + per hit: Hit record + (x, y, mixture) x 26 parts
 
     if rank == 0:
         peaks, peak_src = measured_peaks()

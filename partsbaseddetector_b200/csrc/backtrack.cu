@@ -17,7 +17,7 @@ backtrack(const Geometry* __restrict__ g, const int* __restrict__ parent, const 
           const int* __restrict__ cm_slot, const int* __restrict__ pm_slot, const unsigned short* __restrict__ ixdt,
           const unsigned short* __restrict__ iyraw, const unsigned char* __restrict__ ik, const unsigned char* __restrict__ rooti,
           int ncomp, int ncm, int npm, const Hit* __restrict__ hits, const int* __restrict__ nhits, int max_hits, int mode,
-          int* __restrict__ out) {
+          int out_parts, int* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = min(*nhits, max_hits);
   if (i >= n) return;
@@ -25,9 +25,9 @@ backtrack(const Geometry* __restrict__ g, const int* __restrict__ parent, const 
   const LevelDesc& L = g->lv[h.level];
   const size_t ct = (size_t)g->cells_total;
   const int np = nparts[h.comp];
-  int* xs = out + (size_t)i * 3 * kMaxParts;
-  int* ys = xs + kMaxParts;
-  int* ms = ys + kMaxParts;
+  int* xs = out + (size_t)i * 3 * out_parts;      // [hit][x|y|m][out_parts]
+  int* ys = xs + out_parts;
+  int* ms = ys + out_parts;
   xs[0] = h.x; ys[0] = h.y;
   ms[0] = rooti[((size_t)h.frame * ncomp + h.comp) * ct + L.cell_off + (size_t)h.y * L.ow + h.x];
   for (int p = 1; p < np; ++p) {                                        // :219-235
@@ -72,12 +72,12 @@ expand_backptr(int cell_off, int oh, int ow, size_t ct, int frame, int ncm, int 
 }  // namespace
 
 int launch_backtrack(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const BacktrackTables& t, int ncomp, int ncm, int npm,
-                     const Hit* d_hits, const int* d_nhits, int max_hits, int backptr_mode, int* d_out_xym, cudaStream_t s) {
+                     const Hit* d_hits, const int* d_nhits, int max_hits, int backptr_mode, int out_parts, int* d_out_xym, cudaStream_t s) {
   (void)g;
   if (max_hits <= 0) return 0;
   // the hit count lives on the device; launch for the capacity and let surplus threads exit
   backtrack<<<(max_hits + 63) / 64, 64, 0, s>>>(d_g, t.parent, t.nparts, t.cm_slot, t.pm_slot, b.ixdt, b.iyraw, b.ik, b.rooti, ncomp, ncm,
-                                                npm, d_hits, d_nhits, max_hits, backptr_mode, d_out_xym);
+                                                npm, d_hits, d_nhits, max_hits, backptr_mode, out_parts, d_out_xym);
   return 1;
 }
 

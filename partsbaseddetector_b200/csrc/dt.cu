@@ -31,6 +31,14 @@ namespace {
 
 constexpr int kRing = 8;          // ring window (stack entries kept in shared memory per lane)
 constexpr int kPassWarps = 4;
+constexpr int kTileW = 16;        // samples per line staged per shared-memory tile
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 struct Quad {
   double a, b, a2;   // a2 = 2*a (exact), reference evaluates 2*a*(x1-x0) left to right
@@ -147,7 +155,7 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
         const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out, unsigned short* __restrict__ ptr,
         size_t stride_ptr) {
   __shared__ Ring rings[kPassWarps];
-  __shared__ float tiles[kPassWarps][32][33];
+  __shared__ float tiles[kPassWarps][2][32][kTileW + 1];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int w = blockIdx.x * kPassWarps + wib;                          // warp index -> (level, first item)
   int l = 0, nlines = 0, items = 0;
@@ -173,22 +181,30 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
   const Quad f = make_quad(M.w_sq, M.w_lin);
   float zb[MAXN];
   unsigned short pb[MAXN];
-  float (*tile)[33] = tiles[wib];
-  int q0 = -64;
+  // Input staging: the warp's 32 lines are read kTileW samples at a time into a double-buffered shared-memory tile
+  // with cp.async (each lane copies 16 of the 32 x kTileW elements; a line's kTileW samples are one 64-byte run), the
+  // next tile being in flight while the current one is consumed.  The main loop asks for q = 0,1,2,... in lock
+  // step across the warp; deep-pop reloads of older samples go to global memory.
+  const int c_col = lane & (kTileW - 1), c_row0 = lane / kTileW;  // this lane copies rows c_row0 + 2*i
+  auto prefetch = [&](int q, int buf) {
+#pragma unroll
+    for (int i = 0; i < 32 * kTileW / 32; ++i) {
+      const int r = c_row0 + i * (32 / kTileW);
+      const float* p = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
+      if (q + c_col < N) cp_async4(&tiles[wib][buf][r][c_col], p + q + c_col);
+    }
+    cp_async_commit();
+  };
+  int q0 = -kTileW;
   auto loady = [&](int q) -> float {
-    // the main loop asks for q = 0,1,2,... in lock step across the warp: refill the tile every 32 samples;
-    // deep-pop reloads of older samples go to global memory
-    if (q >= q0 + 32 && (q & 31) == 0) {
-      __syncwarp();
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const float* p = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, i);
-        if (q + lane < N) tile[i][lane] = __ldg(p + q + lane);
-      }
+    if (q >= q0 + kTileW && (q & (kTileW - 1)) == 0) {
+      if (q == 0) prefetch(0, 0);
+      cp_async_wait_all();
       __syncwarp();
       q0 = q;
+      if (q + kTileW < N) prefetch(q + kTileW, ((q / kTileW) + 1) & 1);
     }
-    if (q >= q0) return tile[lane][q - q0];
+    if (q >= q0) return tiles[wib][(q / kTileW) & 1][lane][q - q0];
     return __ldg(src + q);
   };
   envelope_stream(N, f, M.os, rings[wib], lane, zb, pb, loady, [&](int i, float val, int v) {

@@ -486,7 +486,7 @@ void Engine::run_argmin() {
   check_cuda(cudaMemsetAsync(d_nhits_, 0, sizeof(int), stream_), "memset nhits");
   launches_ += launch_hits(g_, d_g_, b_, model_.ncomponents(), (float)thresh, d_hits_, d_nhits_, max_candidates, stream_);
   BacktrackTables t{d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_};
-  launches_ += launch_backtrack(g_, d_g_, b_, t, model_.ncomponents(), ncm_, npm_, d_hits_, d_nhits_, max_candidates, backptr, d_xym_, stream_);
+  launches_ += launch_backtrack(g_, d_g_, b_, t, model_.ncomponents(), ncm_, npm_, d_hits_, d_nhits_, max_candidates, backptr, max_parts_, d_xym_, stream_);
   check_cuda(cudaGetLastError(), "argmin launch");
   if (timing) { check_cuda(cudaEventRecord(ev_[6], stream_), "event"); ev_valid_[6] = true; }
   stage_ = 5;
@@ -500,7 +500,8 @@ void Engine::collect(std::vector<CandidateRec>& out) {
   if (nh > max_candidates)
     throw StateError("candidate buffer overflow: " + std::to_string(nh) + " hits > max_candidates=" + std::to_string(max_candidates));
   std::vector<Hit> hits(nh);
-  std::vector<int> xym((size_t)nh * 3 * kMaxParts);
+  const int ps = max_parts_;
+  std::vector<int> xym((size_t)nh * 3 * ps);
   if (nh) {
     check_cuda(cudaMemcpyAsync(hits.data(), d_hits_, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, stream_), "D2H hits");
     check_cuda(cudaMemcpyAsync(xym.data(), d_xym_, xym.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H parts");
@@ -526,8 +527,8 @@ void Engine::collect(std::vector<CandidateRec>& out) {
     const int np = (int)parts.size();
     CandidateRec C;
     C.frame = H.frame; C.level = H.level; C.component = H.comp; C.score = H.score;
-    const int* xs = xym.data() + (size_t)i * 3 * kMaxParts;
-    C.x.assign(xs, xs + np); C.y.assign(xs + kMaxParts, xs + kMaxParts + np); C.m.assign(xs + 2 * kMaxParts, xs + 2 * kMaxParts + np);
+    const int* xs = xym.data() + (size_t)i * 3 * ps;
+    C.x.assign(xs, xs + np); C.y.assign(xs + ps, xs + ps + np); C.m.assign(xs + 2 * ps, xs + 2 * ps + np);
     const float scale = g_.lv[H.level].scale;
     C.rect.resize((size_t)np * 4);
     for (int p = 0; p < np; ++p) {                  // reference src/DynamicProgram.cpp:238-244

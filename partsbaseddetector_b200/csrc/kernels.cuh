@@ -141,7 +141,7 @@ struct BacktrackTables {       // per component, flattened with strides kMaxPart
   const int* pm_slot;          // [ncomp][kMaxParts][kMaxMix]  ik slot of (c, p, parent mixture)
 };
 int launch_backtrack(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const BacktrackTables& t, int ncomp, int ncm, int npm,
-                     const Hit* d_hits, const int* d_nhits, int max_hits, int backptr_mode, int* d_out_xym, cudaStream_t s);
+                     const Hit* d_hits, const int* d_nhits, int max_hits, int backptr_mode, int out_parts, int* d_out_xym, cudaStream_t s);
 // materialise the reference's Ix/Iy/Ik Mats for one (frame, level, comp, part, parent mixture)
 int launch_expand_backptr(const Geometry& g, const DeviceBuffers& b, int frame, int level, int ncm, int npm, const int* d_cm_slots,
                           int pm_slot, int backptr_mode, int* d_ix, int* d_iy, int* d_ik, cudaStream_t s);

@@ -148,18 +148,54 @@ class Candidate:
 
     @staticmethod
     def sort(cands):
-        cands.sort(key=lambda c: -float(c.score()))          # stable, descending (Candidate.hpp:97-99)
+        """In place on a list; a CandidateList is returned as a new sorted list."""
+        if isinstance(cands, list):
+            cands.sort(key=lambda c: -float(c.score()))      # stable, descending (Candidate.hpp:97-99)
+            return cands
+        return sorted(cands, key=lambda c: -float(c.score()))
+
+
+class CandidateList:
+    """Read-only sequence of Candidate backed by the arrays of one bulk export; Candidate objects are built on access.
+    `meta` = (n,4) frame/level/component/nparts, `scores` = (n,), `parts` = (n, max_parts, 7) x,y,mixture,rect."""
+
+    def __init__(self, meta, scores, parts):
+        self.meta, self.scores, self.parts = meta, scores, parts
+
+    def __len__(self):
+        return len(self.scores)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        c = Candidate()
+        npart = int(self.meta[i, 3])
+        c.frame, c.level, c.component_ = int(self.meta[i, 0]), int(self.meta[i, 1]), int(self.meta[i, 2])
+        conf = np.zeros(npart, np.float32)
+        conf[0] = self.scores[i]                                 # root = rootv, others 0.0 (DynamicProgram.cpp:241-244)
+        c.confidence_ = conf
+        p = self.parts[i, :npart]
+        c.parts_ = p[:, 3:7]
+        c.x, c.y, c.m = p[:, 0], p[:, 1], p[:, 2]
+        return c
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
 
 
 def _unpack_candidates(handle, free=True):
-    """pbd_candidates -> list of Candidate (one bulk export call, then numpy views)."""
+    """pbd_candidates -> CandidateList (one bulk export call)."""
     L = _lib.lib()
     n = L.pbd_candidates_count(handle)
-    out = []
+    meta = np.empty((n, 4), np.int32)
+    scores = np.empty(n, np.float32)
+    parts = np.empty((n, 1, 7), np.int32)
     if n:
         mp = max(L.pbd_candidates_nparts(handle, 0), 1)
-        meta = np.empty((n, 4), np.int32)
-        scores = np.empty(n, np.float32)
         while True:
             parts = np.empty((n, mp, 7), np.int32)
             rc = L.pbd_candidates_export(handle, meta.reshape(-1), scores, parts.reshape(-1), mp)
@@ -168,20 +204,9 @@ def _unpack_candidates(handle, free=True):
             mp *= 2                                              # components with more parts than the first candidate
             if mp > 4096:
                 _lib.check(rc)
-        conf = np.zeros((n, mp), np.float32)
-        conf[:, 0] = scores                                      # root = rootv, others 0.0 (DynamicProgram.cpp:241-244)
-        for i in range(n):
-            c = Candidate()
-            npart = int(meta[i, 3])
-            c.frame, c.level, c.component_ = int(meta[i, 0]), int(meta[i, 1]), int(meta[i, 2])
-            c.confidence_ = conf[i, :npart]
-            p = parts[i, :npart]
-            c.parts_ = p[:, 3:7]
-            c.x, c.y, c.m = p[:, 0], p[:, 1], p[:, 2]
-            out.append(c)
     if free:
         L.pbd_candidates_free(handle)
-    return out
+    return CandidateList(meta, scores, parts)
 
 
 class PartsBasedDetector:
@@ -248,8 +273,8 @@ class PartsBasedDetector:
         _lib.check(_lib.lib().pbd_detect_batch_u8(self.handle, a.ctypes.data, n, h, w, c, 0, 0, C.byref(out)))
         res = _unpack_candidates(out)
         if candidates is None:
-            return res
-        candidates.extend(res)
+            return res                                   # CandidateList (lazy)
+        candidates.extend(res)                           # reference semantics: append to the caller's vector
         return candidates
 
     def detect_device(self, dptr, n, h, w, c):

@@ -281,7 +281,7 @@ def test_max_levels_and_candidate_sort():
     cands = d.detect(img)
     assert d.nscales() == 4 and len(cands) == len(O.candidates())
     from partsbaseddetector_b200 import Candidate
-    Candidate.sort(cands)
+    cands = Candidate.sort(list(cands))
     s = [float(c.score()) for c in cands]
     assert s == sorted(s, reverse=True)
 
