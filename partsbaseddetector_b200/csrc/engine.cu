@@ -451,13 +451,14 @@ void Engine::run_pyramid() {
   if (timing) { check_cuda(cudaEventRecord(ev_[2], stream_), "event"); ev_valid_[2] = true; }
   launches_ += launch_hog(g_, d_g_, b_, model_.sbin, stream_);
   check_cuda(cudaGetLastError(), "pyramid/HOG launch");
+  feat_from_hog_ = true;
   stage_ = 2;
 }
 
 void Engine::run_pdf() {
   need(2, "pdf");
   if (timing) { check_cuda(cudaEventRecord(ev_[3], stream_), "event"); ev_valid_[3] = true; }
-  launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles_, exact, stream_);
+  launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles_, exact, feat_from_hog_ ? 1 : 0, stream_);
   check_cuda(cudaGetLastError(), "response launch");
   stage_ = 3;
 }
@@ -612,6 +613,7 @@ void Engine::set_features(int frame, int level, const float* src) {
   check_cuda(cudaMemcpyAsync(b_.feat + ((size_t)frame * g_.cells_total + L.cell_off) * 32, src, (size_t)L.oh * L.ow * 32 * sizeof(float),
                              cudaMemcpyHostToDevice, stream_), "H2D features");
   check_cuda(cudaStreamSynchronize(stream_), "sync");
+  feat_from_hog_ = false;                         // injected features: channel 31 is not known to be zero
   stage_ = std::max(stage_, 2);
 }
 void Engine::set_response(int frame, int level, int filter, const float* src) {

@@ -99,6 +99,7 @@ class Engine {
   Geometry g_{};
   Geometry* d_g_ = nullptr;
   bool have_images_ = false;
+  bool feat_from_hog_ = false;
   int stage_ = 0;                              // 0 none, 1 geometry, 2 features, 3 responses, 4 dp, 5 argmin
   DeviceBuffers b_{};
   uint8_t* d_frames_own_ = nullptr; size_t cap_frames_ = 0;

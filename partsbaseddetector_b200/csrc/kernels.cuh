@@ -108,7 +108,7 @@ struct FilterBank {
 int response_tile_dims(int uniform_fast, int* tx, int* ty);
 bool response_has_fast_path(const FilterBank& fb);
 int launch_response_tiles(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const FilterBank& fb, const int* d_tile_level,
-                          const int* d_tile_first, int ntiles, int exact, cudaStream_t s);
+                          const int* d_tile_first, int ntiles, int exact, int trunc_zero, cudaStream_t s);
 
 // Geometry of one separable-transform pass: per level the number of lines, their length and the map offset.
 struct PassGeom {

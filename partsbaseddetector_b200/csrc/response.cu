@@ -39,7 +39,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int KH, int KW, bool EXACT>
 __global__ void __launch_bounds__(NT, 2)
 part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level, const int* __restrict__ tile_first,
-              const float* __restrict__ feat, const float* __restrict__ wbank, int nfilters, int ngroups,
+              const float* __restrict__ feat, const float* __restrict__ wbank, int nfilters, int ngroups, int trunc_zero,
               float* __restrict__ resp) {
   constexpr int TAPS = KH * KW;
   constexpr int HY = TY + KH - 1;                       // tile rows incl. halo
@@ -76,6 +76,11 @@ part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level
     sfeat[(cq * 4 + 3) * PLANE + pos] = v.w;
   }
 
+  // Channel 31 (truncation feature) is identically zero inside a map produced by the HOG stage (src/HOGFeatures.cpp:338;
+  // trunc_zero = 0 for features injected through pbd_set_features), so for a tile whose halo
+  // lies entirely inside the map its 25 products are all +-0 and acc + (+-0) == acc: the channel is skipped exactly.
+  const bool interior = trunc_zero && (y0 - AY >= 0) && (x0 - AX >= 0) && (y0 + TY - 1 - AY + KH - 1 < oh) && (x0 + ROWP - 1 - AX < ow);
+  const int nch_last = interior ? CCH - 1 : CCH;
   const int warp = tid >> 5, lane = tid & 31;
   const int wpos = warp % POSW, wf = warp / POSW;       // which cells / which filter group of the pass (group = POSW adjacent warps)
   constexpr int LX = TX / P, LY = 32 / LX;              // lanes along x / y inside a warp
@@ -116,8 +121,9 @@ part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level
       if (npassi < npass) { stage_weights(npassi, nchunk, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
       group_sync();                                     // this group's slab is visible to its warps
       const float* wsl = sw + ((size_t)buf * WF + wf) * WSLAB;
+      const int ncl = (chunk == 32 / CCH - 1) ? nch_last : CCH;
 #pragma unroll 1
-      for (int cl = 0; cl < CCH; ++cl) {
+      for (int cl = 0; cl < ncl; ++cl) {
         const int c = chunk * CCH + cl;
         const float* fp = sfeat + c * PLANE + cy * ROWP + cx;
         const float* wp = wsl + cl * TAPS * Q;
@@ -237,7 +243,7 @@ size_t fast_smem_bytes() {
 
 template <int KH, int KW>
 void launch_fast(const Geometry* d_g, const int* d_tl, const int* d_tf, int ntiles, int nframes, const DeviceBuffers& b,
-                 const FilterBank& fb, int exact, cudaStream_t s) {
+                 const FilterBank& fb, int exact, int trunc_zero, cudaStream_t s) {
   const size_t smem = fast_smem_bytes<KH, KW>();
   static bool configured = false;
   if (!configured) {
@@ -246,8 +252,8 @@ void launch_fast(const Geometry* d_g, const int* d_tl, const int* d_tf, int ntil
     configured = true;
   }
   dim3 grid(ntiles, nframes);
-  if (exact) part_response<KH, KW, true><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, b.resp);
-  else part_response<KH, KW, false><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, b.resp);
+  if (exact) part_response<KH, KW, true><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, trunc_zero, b.resp);
+  else part_response<KH, KW, false><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, trunc_zero, b.resp);
 }
 
 }  // namespace
@@ -266,13 +272,13 @@ int response_tile_dims(int uniform, int* tx, int* ty) {
 }
 
 int launch_response_tiles(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const FilterBank& fb, const int* d_tile_level,
-                          const int* d_tile_first, int ntiles, int exact, cudaStream_t s) {
+                          const int* d_tile_first, int ntiles, int exact, int trunc_zero, cudaStream_t s) {
   if (ntiles <= 0 || g.n_frames <= 0) return 0;
   const int khm = fb.khm, kwm = fb.kwm;
   if (response_has_fast_path(fb)) {
-    if (fb.kh == 5) launch_fast<5, 5>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, s);
-    else if (fb.kh == 4) launch_fast<4, 4>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, s);
-    else launch_fast<6, 6>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, s);
+    if (fb.kh == 5) launch_fast<5, 5>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, trunc_zero, s);
+    else if (fb.kh == 4) launch_fast<4, 4>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, trunc_zero, s);
+    else launch_fast<6, 6>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, trunc_zero, s);
     return 1;
   }
   const int HYm = 8 + khm - 1, ROWm = 16 + kwm - 1;

@@ -322,3 +322,49 @@ def test_cpp_adapter_demo_matches_python(tmp_path):
     assert "Number of candidates: %d" % len(cands) in r.stdout
     best = max(cands, key=lambda c: float(c.score()))
     assert ("best: score %.6f level %d" % (float(best.score()), best.level)) in r.stdout
+
+
+# ------------------------------------------------------------------------------------------ BASELINE.json full sizes
+def test_config4_1080p_ten_levels_bitexact():
+    """config 4: person model, 1920x1080, first 10 pyramid levels (340 400 cells)."""
+    name = "Person_26parts"
+    img = synth_frame(77, 1080, 1920)
+    d, O = detector(name), oracle(name)
+    d.set_option("max_levels", 10)
+    O.set_max_levels(10)
+    O.run(img, 1, 3)
+    thr = lowered_threshold(O, 120)
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    d.set_option("thresh", thr)
+    cands = d.detect(img)
+    assert d.nscales() == 10 and d.level_info(0)["ow"] == 478 and d.level_info(0)["oh"] == 268
+    for l in (0, 4, 9):
+        assert np.array_equal(d.rootv(0, l), O.rootv(l)) and np.array_equal(d.rooti(0, l), O.rooti(l))
+    g, o = d.backptr(0, 0, 0, 13, 1), O.backptr(0, 0, 13, 1)
+    assert all(np.array_equal(a, b) for a, b in zip(g, o))
+    oc = O.candidates()
+    assert len(cands) == len(oc) > 0
+    for a, b in zip(cands, oc):
+        assert a.level == b["level"] and np.array_equal(a.x, b["x"]) and np.array_equal(a.y, b["y"]) and np.array_equal(a.m, b["m"])
+        assert a.score() == b["score"] and np.array_equal(a.parts(), b["rects"])
+
+
+def test_config5_dt_4096_bitexact_and_properties():
+    """config 5 (one of the 156 maps): 4096x4096 score map through the standalone DT, against the oracle, plus
+    size-independent properties: out >= in + penalty at the anchor, and the exact back-pointers attain the output."""
+    h = w = 4096
+    m = synth_score_map(0, h, w)
+    defw = np.array([[0.013, -0.004, 0.017, 0.011]], np.float32)
+    anchor = np.array([[2, -1]], np.int32)
+    out, ix, iy = dt2d(m, defw, anchor, 1)
+    o, x, y = np.empty((h, w), np.float32), np.empty((h, w), np.int32), np.empty((h, w), np.int32)
+    oracle_lib.lib().orc_dt2d_f32(m.reshape(-1), h, w, defw[0], 2, -1, 1, o.reshape(-1), x.reshape(-1), y.reshape(-1))
+    assert np.array_equal(out[0], o) and np.array_equal(ix[0], x) and np.array_equal(iy[0], y)
+    a0, b0, a1, b1 = (-float(v) for v in defw[0])
+    yy, xx = np.mgrid[0:h:97, 0:w:89]                       # sampled cells
+    dx, dy = (xx + 2) - ix[0][yy, xx], (yy - 1) - iy[0][yy, xx]
+    att = m[iy[0][yy, xx], ix[0][yy, xx]] + a0 * dx * dx + b0 * dx + a1 * dy * dy + b1 * dy
+    assert np.allclose(att, out[0][yy, xx], rtol=1e-5, atol=1e-5)
+    inside = (xx + 2 < w) & (yy - 1 >= 0)
+    assert np.all(out[0][yy, xx][inside] >= m[np.clip(yy - 1, 0, h - 1), np.clip(xx + 2, 0, w - 1)][inside] - 1e-6)
