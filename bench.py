@@ -97,7 +97,7 @@ def cpu_frames_per_sec(frames, budget_s=20.0, max_frames=8, warmup=1):
     from partsbaseddetector_b200 import Model
     fm = Model.load_bin(MODEL).to_flat()
     O = oracle_lib.OracleDetector(fm, 32)
-    cores = oracle_lib.lib().orc_num_threads()
+    cores = oracle_lib.use_all_cores()
     for i in range(warmup):
         O.run(frames[i % len(frames)])
     t0 = time.time()
@@ -123,7 +123,7 @@ def run_reference_arm(args):
     import oracle_lib
     from partsbaseddetector_b200 import Model
     O = oracle_lib.OracleDetector(Model.load_bin(MODEL).to_flat(), 32)
-    cores = oracle_lib.lib().orc_num_threads()
+    cores = oracle_lib.use_all_cores()
     for _ in range(args.warmup):
         for f in frames:
             O.run(f)
@@ -263,6 +263,35 @@ def run_gpu_arm(args):
                                   "frac": flops / (pdf_avg * 1e-3) / 1e12 / fp32_peak, "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz"}},
             "stage_ms": stage_ms,
         }
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, scaled to this batch)
+        tp = os.path.join(ROOT, "profiles", "part_response_traffic.json")
+        if os.path.exists(tp):
+            tr = json.load(open(tp))
+            line["roofline"]["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * B / tr["batch"]
+            line["roofline"]["traffic_source"] = tr.get("source", "ncu")
+        # the HBM-bound remainder of the step, for context: algorithmic bytes / stage time
+        dp_bytes = (133 * 20.0 + (133 * 4.0 + 131 * 9.0)) * cells * B
+        hog_bytes = (48.0 + 76.0 + 76.0 + 128.0) * cells * B
+        line["roofline_other"] = {
+            "dp_min (dt_pass x2 + mix_max, 11 waves)": {"alg_GBps": dp_bytes / (stage_ms["dp_min"] * 1e-3) / 1e9, "frac_of_hbm": dp_bytes / (stage_ms["dp_min"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                                         "bound": "latency of the sequential fp64 envelope chain, not HBM"},
+            "hog (hog_hist + hog_feat)": {"alg_GBps": hog_bytes / (stage_ms["hog"] * 1e-3) / 1e9, "frac_of_hbm": hog_bytes / (stage_ms["hog"] * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        }
+        if args.also_fast:
+            det.set_option("exact", 0)
+            for _ in range(3):
+                det.enqueue_device(dev.data_ptr(), B, H, W, C)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                det.enqueue_device(dev.data_ptr(), B, H, W, C)
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1)
+            line["fast_mode"] = {"value": B * args.steps / (fms * 1e-3), "unit": "frames/s", "ms_per_step": fms / args.steps,
+                                 "pdf_ms": det.stage_times_ms()["pdf"], "note": "exact=0: FFMA responses (scores within 1e-6 relative, same candidates on the test frames); single rank"}
+            det.set_option("exact", 0 if args.fast else 1)
         if world == 1 and not args.no_cpu:
             cfps, cores, n, dt, cstage = cpu_frames_per_sec(base, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -285,6 +314,7 @@ def main():
     ap.add_argument("--fast", action="store_true", help="fused multiply-add responses instead of the bit-exact mode")
     ap.add_argument("--thresh", type=float, default=None)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--also-fast", action="store_true", default=True, help="also report the fused-multiply-add mode (rank 0 only)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

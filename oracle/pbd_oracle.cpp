@@ -13,16 +13,18 @@
 // Every function names the reference file:line it restates.  OpenCV routines
 // the reference calls (cv::resize, cv::pyrDown, FilterEngine/Filter2D,
 // cv::transpose, Mat + scalar, cvRound) are restated from their published
-// algorithm and pinned against the cv2 4.13 wheel in tests/test_oracle_*.py.
+// algorithm and pinned against the cv2 4.13 wheel in tests/test_oracle_pins.py.
 //
 // Pinning status ("parity pinned by cv2 + brute force, unpinned by reference
 // tests"): the reference ships no golden vectors or unit tests for this path
 // (test/CMakeLists.txt only instantiates the ORK pipeline), so the pins are:
-//   * image pyramid  == cv2.resize / cv2.pyrDown, bit-exact   (tests/test_oracle_pyramid.py)
-//   * responses      == sum_c cv2.filter2D to 1e-5            (tests/test_oracle_response.py)
-//   * DT             == brute-force max, value and 1-D argmax (tests/test_oracle_dt.py)
-//   * DP             == exhaustive enumeration on a toy model (tests/test_oracle_dp.py)
-//   * HOG            == independent numpy transcription       (tests/test_oracle_hog.py)
+// (all in tests/test_oracle_pins.py)
+//   * image pyramid  == cv2.resize / cv2.pyrDown, bit-exact
+//   * responses      == sum_c cv2.filter2D to 1e-5 (1e-11 in double)
+//   * DT             == brute-force max, value and 1-D argmax
+//   * DP             == exhaustive enumeration on a toy model
+//   * HOG            == independent numpy formulation (1e-9 in double)
+//   * committed golden vectors tests/golden/oracle_golden.npz
 //
 // Build: see oracle/Makefile (-O2 -fopenmp -ffp-contract=off, no -march: the
 // reference sets no arch flags, so x86-64 baseline SSE2 => no FMA contraction).
@@ -789,6 +791,13 @@ void orc_destroy(void* hv) { Handle* h = (Handle*)hv; delete h->f; delete h->d; 
 void orc_set_thresh(void* hv, double t) { Handle* h = (Handle*)hv; DISPATCH(h, D.thresh = t, D.thresh = t); }
 void orc_set_backptr_mode(void* hv, int m) { Handle* h = (Handle*)hv; DISPATCH(h, D.backptr_mode = m, D.backptr_mode = m); }
 void orc_set_max_levels(void* hv, int m) { Handle* h = (Handle*)hv; DISPATCH(h, D.max_levels = m, D.max_levels = m); }
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

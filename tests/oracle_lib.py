@@ -53,6 +53,7 @@ def lib():
     L.orc_set_backptr_mode.argtypes = [C.c_void_p, C.c_int]
     L.orc_set_max_levels.argtypes = [C.c_void_p, C.c_int]
     L.orc_num_threads.restype = C.c_int
+    L.orc_set_num_threads.argtypes = [C.c_int]
     L.orc_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.orc_set_levels.argtypes = [C.c_void_p, C.c_int, _i32p, _f32p]
     L.orc_set_features.argtypes = [C.c_void_p, C.c_int, _f64p]
@@ -72,6 +73,34 @@ def lib():
     L.orc_get_timings.argtypes = [C.c_void_p, _f64p]
     _lib = L
     return L
+
+
+def physical_cores():
+    """Number of physical cores this process may run on (SMT siblings counted once)."""
+    try:
+        allowed = os.sched_getaffinity(0)
+        cores = set()
+        cpu = phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("processor"):
+                cpu = int(line.split(":")[1])
+            elif line.startswith("physical id"):
+                phys = int(line.split(":")[1])
+            elif line.startswith("core id"):
+                core = int(line.split(":")[1])
+                if cpu in allowed:
+                    cores.add((phys, core))
+        return max(len(cores), 1) if cores else max(len(allowed), 1)
+    except (OSError, ValueError, AttributeError):
+        return os.cpu_count() or 1
+
+
+def use_all_cores():
+    """The reference parallelises with OpenMP over all host threads; launchers such as torchrun export OMP_NUM_THREADS=1,
+    so the thread count is set explicitly (one thread per physical core)."""
+    n = physical_cores()
+    lib().orc_set_num_threads(n)
+    return n
 
 
 class OracleDetector:
