@@ -116,6 +116,13 @@ int pbd_candidates_export(const pbd_candidates* c, int32_t* meta4, float* scores
 void pbd_candidates_free(pbd_candidates* c);
 /* Candidate::sort (include/Candidate.hpp:97-99): descending root score, stable */
 int pbd_candidates_sort(pbd_candidates* c);
+/* Candidate::nonMaximaSuppression (include/Candidate.hpp:277-304): greedy box painting over the candidates in their
+ * current order (callers sort first, ros/Node.cpp:192-196), applied independently per frame of the batch.  A candidate is
+ * dropped when more than `overlap` of its (image-clipped) bounding box has already been painted by kept candidates. */
+int pbd_candidates_nms(pbd_candidates* c, int im_h, int im_w, float overlap);
+/* build a candidate set from arrays (layout of pbd_candidates_export); for callers that post-process their own lists */
+int pbd_candidates_create(int n, int max_nparts, const int32_t* meta4, const float* scores, const int32_t* parts7,
+                          pbd_candidates** out);
 
 /* ------------------------------------------------------------ stage level ---
  * The reference's plugin interfaces, one call per stage, operating on the detector's device buffers:

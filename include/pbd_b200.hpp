@@ -112,6 +112,25 @@ class Candidate {
   int component() const { return component_; }
   static bool descending(const Candidate& c1, const Candidate& c2) { return c1.score() > c2.score(); }
   static void sort(std::vector<Candidate>& candidates) { std::stable_sort(candidates.begin(), candidates.end(), descending); }
+  // reference include/Candidate.hpp:277-304: greedy box painting in the given order (sort first)
+  static void nonMaximaSuppression(const Mat& im, std::vector<Candidate>& candidates, const float overlap = 0.0f) {
+    const int W = im.cols, H = im.rows;
+    std::vector<uint8_t> scratch((size_t)W * H, 0);
+    size_t keep = 0;
+    for (size_t n = 0; n < candidates.size(); ++n) {
+      const Rect hull = candidates[n].boundingBox();
+      int bx = std::max(hull.x, 0), by = std::max(hull.y, 0);
+      int bw = std::min(hull.x + hull.width, W) - bx, bh = std::min(hull.y + hull.height, H) - by;
+      if (bw <= 0 || bh <= 0) { bx = by = bw = bh = 0; }
+      double sum = 0;
+      for (int y = by; y < by + bh; ++y) for (int x = bx; x < bx + bw; ++x) sum += scratch[(size_t)y * W + x];
+      if (sum / (bw * bh) > overlap) continue;
+      for (int y = by; y < by + bh; ++y) std::fill(scratch.begin() + (size_t)y * W + bx, scratch.begin() + (size_t)y * W + bx + bw, (uint8_t)1);
+      if (keep != n) candidates[keep] = candidates[n];
+      keep++;
+    }
+    candidates.resize(keep);
+  }
   Rect boundingBox() const {
     Rect hull = parts_.at(0);
     for (const Rect& r : parts_) {

@@ -748,6 +748,34 @@ void orc_dt2d_f64(const double* src, int M, int N, const float* w4, int osx, int
   std::memcpy(Iy, iy.d.data(), iy.d.size() * sizeof(int));
 }
 
+// Candidate::nonMaximaSuppression (reference include/Candidate.hpp:277-304) over boundingBox() (:104-110) with
+// cv::Rect's | and & operators; rects = n x nparts x (x, y, width, height); keep receives the kept indices.
+int orc_nms(const int* rects, int n, int nparts, int im_h, int im_w, float overlap, int* keep) {
+  std::vector<uint8_t> scratch((size_t)im_h * im_w, 0);          // cv::Mat::zeros(im.size(), CV_8U)
+  int nk = 0;
+  for (int i = 0; i < n; ++i) {
+    const int* r = rects + (size_t)i * nparts * 4;
+    int hx = r[0], hy = r[1], hw = r[2], hh = r[3];              // hull = parts_[0]
+    for (int p = 0; p < nparts; ++p) {                           // hull = hull | parts_[n]
+      const int* q = r + 4 * p;
+      if (hw <= 0 || hh <= 0) { hx = q[0]; hy = q[1]; hw = q[2]; hh = q[3]; }
+      else if (q[2] > 0 && q[3] > 0) {
+        const int x1 = std::min(hx, q[0]), y1 = std::min(hy, q[1]);
+        hw = std::max(hx + hw, q[0] + q[2]) - x1; hh = std::max(hy + hh, q[1] + q[3]) - y1; hx = x1; hy = y1;
+      }
+    }
+    int bx = std::max(hx, 0), by = std::max(hy, 0);              // box = hull & Rect(0,0,w,h)
+    int bw = std::min(hx + hw, im_w) - bx, bh = std::min(hy + hh, im_h) - by;
+    if (bw <= 0 || bh <= 0) { bx = by = bw = bh = 0; }
+    double sum = 0;                                               // cv::sum(scratch(box))[0]
+    for (int y = by; y < by + bh; ++y) for (int x = bx; x < bx + bw; ++x) sum += scratch[(size_t)y * im_w + x];
+    if (sum / (bw * bh) > overlap) continue;                     // boxsum[0] / box.area() > overlap
+    for (int y = by; y < by + bh; ++y) for (int x = bx; x < bx + bw; ++x) scratch[(size_t)y * im_w + x] = 1;
+    keep[nk++] = i;
+  }
+  return nk;
+}
+
 // ---- detector handle ----
 // hdr = {interval, sbin, norient, flen, nfilters, nbias, ndefs, ncomp}; fdims = (kh,kw) per filter;
 // indexers = for c: nparts, then for p: parentid, nf, nb, nd, filterid[nf], biasid[nb], defid[nd]

@@ -26,7 +26,7 @@ EXPORTS = [
     "pbd_model_part", "pbd_create", "pbd_destroy", "pbd_set_option", "pbd_get_option", "pbd_detect_batch_u8",
     "pbd_detect_batch_u8_device", "pbd_enqueue_batch_u8_device", "pbd_collect_candidates",
     "pbd_candidates_count", "pbd_candidates_nparts", "pbd_candidates_get", "pbd_candidates_export", "pbd_candidates_free",
-    "pbd_candidates_sort", "pbd_stage_pyramid", "pbd_stage_pdf", "pbd_stage_dp_min", "pbd_stage_dp_argmin",
+    "pbd_candidates_sort", "pbd_candidates_nms", "pbd_candidates_create", "pbd_stage_pyramid", "pbd_stage_pdf", "pbd_stage_dp_min", "pbd_stage_dp_argmin",
     "pbd_num_frames", "pbd_num_levels", "pbd_level_info", "pbd_get_pyramid_image", "pbd_get_features",
     "pbd_get_response", "pbd_get_rootv", "pbd_get_rooti", "pbd_get_backptr", "pbd_set_levels",
     "pbd_set_features", "pbd_set_response", "pbd_dt2d_f32_device", "pbd_dt2d_f32", "pbd_launch_count",
@@ -89,6 +89,8 @@ def lib():
     L.pbd_candidates_export.argtypes = [vp, _i32p, _f32p, _i32p, ci]
     L.pbd_candidates_free.argtypes = [vp]
     L.pbd_candidates_sort.argtypes = [vp]
+    L.pbd_candidates_nms.argtypes = [vp, ci, ci, cf]
+    L.pbd_candidates_create.argtypes = [ci, ci, _i32p, _f32p, _i32p, P(vp)]
     L.pbd_stage_pyramid.argtypes = [vp, vp, ci, ci, ci, ci, C.c_size_t, C.c_size_t]
     L.pbd_stage_pdf.argtypes = [vp]
     L.pbd_stage_dp_min.argtypes = [vp]

@@ -263,6 +263,70 @@ int pbd_candidates_sort(pbd_candidates* c) {
   });
 }
 
+namespace {
+struct IRect { int x, y, w, h; };
+inline bool rect_empty(const IRect& r) { return r.w <= 0 || r.h <= 0; }
+inline IRect rect_or(IRect a, const IRect& b) {            // cv::Rect operator|
+  if (rect_empty(a)) return b;
+  if (rect_empty(b)) return a;
+  const int x1 = std::min(a.x, b.x), y1 = std::min(a.y, b.y);
+  a.w = std::max(a.x + a.w, b.x + b.w) - x1; a.h = std::max(a.y + a.h, b.y + b.h) - y1; a.x = x1; a.y = y1;
+  return a;
+}
+inline IRect rect_and(IRect a, const IRect& b) {           // cv::Rect operator&
+  const int x1 = std::max(a.x, b.x), y1 = std::max(a.y, b.y);
+  a.w = std::min(a.x + a.w, b.x + b.w) - x1; a.h = std::min(a.y + a.h, b.y + b.h) - y1; a.x = x1; a.y = y1;
+  if (a.w <= 0 || a.h <= 0) a = IRect{0, 0, 0, 0};
+  return a;
+}
+}  // namespace
+
+int pbd_candidates_nms(pbd_candidates* c, int im_h, int im_w, float overlap) {
+  return guarded([&] {
+    REQUIRE(c && im_h > 0 && im_w > 0, "bad argument");
+    std::vector<CandidateRec> kept;
+    kept.reserve(c->v.size());
+    std::vector<uint8_t> scratch((size_t)im_h * im_w);
+    const IRect bounds{0, 0, im_w, im_h};
+    int cur_frame = -1 << 30;
+    for (const CandidateRec& C : c->v) {
+      if (C.frame != cur_frame) { std::fill(scratch.begin(), scratch.end(), 0); cur_frame = C.frame; }   // one scratch image per frame
+      const int np = (int)C.x.size();
+      IRect hull{C.rect[0], C.rect[1], C.rect[2], C.rect[3]};                       // Candidate::boundingBox, :104-110
+      for (int p = 0; p < np; ++p) hull = rect_or(hull, IRect{C.rect[4 * p], C.rect[4 * p + 1], C.rect[4 * p + 2], C.rect[4 * p + 3]});
+      const IRect box = rect_and(hull, bounds);
+      long long sum = 0;
+      for (int y = box.y; y < box.y + box.h; ++y) { const uint8_t* r = &scratch[(size_t)y * im_w + box.x]; for (int x = 0; x < box.w; ++x) sum += r[x]; }
+      const double ratio = (double)sum / (box.w * box.h);                             // boxsum[0] / box.area() (NaN for an empty box => kept)
+      if (ratio > (double)overlap) continue;
+      for (int y = box.y; y < box.y + box.h; ++y) memset(&scratch[(size_t)y * im_w + box.x], 1, (size_t)box.w);
+      kept.push_back(C);
+    }
+    c->v.swap(kept);
+  });
+}
+
+int pbd_candidates_create(int n, int max_nparts, const int32_t* meta4, const float* scores, const int32_t* parts7, pbd_candidates** out) {
+  return guarded([&] {
+    REQUIRE(n >= 0 && max_nparts > 0 && out && (n == 0 || (meta4 && scores && parts7)), "bad argument");
+    auto cs = std::make_unique<pbd_candidates>();
+    cs->v.resize(n);
+    for (int i = 0; i < n; ++i) {
+      CandidateRec& C = cs->v[i];
+      C.frame = meta4[4 * i]; C.level = meta4[4 * i + 1]; C.component = meta4[4 * i + 2];
+      const int np = meta4[4 * i + 3];
+      REQUIRE(np > 0 && np <= max_nparts, "bad part count");
+      C.score = scores[i];
+      const int32_t* row = parts7 + (size_t)i * max_nparts * 7;
+      for (int p = 0; p < np; ++p) {
+        C.x.push_back(row[7 * p]); C.y.push_back(row[7 * p + 1]); C.m.push_back(row[7 * p + 2]);
+        for (int t = 0; t < 4; ++t) C.rect.push_back(row[7 * p + 3 + t]);
+      }
+    }
+    *out = cs.release();
+  });
+}
+
 int pbd_stage_pyramid(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c, size_t row_stride, size_t frame_stride) {
   return guarded([&] {
     REQUIRE(d && frames, "null argument");

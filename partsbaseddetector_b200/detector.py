@@ -154,6 +154,45 @@ class Candidate:
             return cands
         return sorted(cands, key=lambda c: -float(c.score()))
 
+    def boundingBox(self):
+        """cv::Rect hull of the part boxes (include/Candidate.hpp:104-110) as (x, y, width, height)."""
+        p = self.parts_
+        x0, y0 = int(p[:, 0].min()), int(p[:, 1].min())
+        return (x0, y0, int((p[:, 0] + p[:, 2]).max()) - x0, int((p[:, 1] + p[:, 3]).max()) - y0)
+
+    @staticmethod
+    def nonMaximaSuppression(im, candidates, overlap=0.0):
+        """Candidate::nonMaximaSuppression (include/Candidate.hpp:277-304).  `im` is an image (or its (h, w) shape);
+        `candidates` a list of Candidate or a CandidateList in the order to be processed (sort first).  A list is
+        filtered in place (and returned), a CandidateList yields a new CandidateList."""
+        shape = im if isinstance(im, tuple) else np.asarray(im).shape
+        h, w = int(shape[0]), int(shape[1])
+        n = len(candidates)
+        if isinstance(candidates, CandidateList):
+            meta, scores, parts = candidates.meta, candidates.scores, candidates.parts
+        else:
+            mp = max([len(c.x) for c in candidates] + [1])
+            meta = np.zeros((n, 4), np.int32)
+            scores = np.zeros(n, np.float32)
+            parts = np.zeros((n, mp, 7), np.int32)
+            for i, c in enumerate(candidates):
+                k = len(c.x)
+                meta[i] = (c.frame, c.level, c.component_, k)
+                scores[i] = c.score()
+                parts[i, :k, 0], parts[i, :k, 1], parts[i, :k, 2] = c.x, c.y, c.m
+                parts[i, :k, 3:7] = c.parts_
+        hnd = C.c_void_p()
+        L = _lib.lib()
+        mp = parts.shape[1]
+        _lib.check(L.pbd_candidates_create(n, mp, np.ascontiguousarray(meta).reshape(-1), np.ascontiguousarray(scores),
+                                           np.ascontiguousarray(parts).reshape(-1), C.byref(hnd)))
+        _lib.check(L.pbd_candidates_nms(hnd, h, w, float(overlap)))
+        out = _unpack_candidates(hnd)
+        if isinstance(candidates, CandidateList):
+            return out
+        candidates[:] = list(out)
+        return candidates
+
 
 class CandidateList:
     """Read-only sequence of Candidate backed by the arrays of one bulk export; Candidate objects are built on access.

@@ -91,3 +91,40 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "frames/s"
+
+
+def test_nms_matches_oracle_restatement():
+    """Candidate::nonMaximaSuppression (include/Candidate.hpp:277-304): library implementation vs the oracle's restatement
+    on random candidate sets (host code: no GPU needed)."""
+    import oracle_lib
+    from partsbaseddetector_b200 import Candidate
+    from partsbaseddetector_b200.detector import CandidateList
+    rng = np.random.default_rng(5)
+    L = oracle_lib.lib()
+    for trial in range(6):
+        n, nparts, h, w = int(rng.integers(1, 120)), int(rng.integers(1, 9)), 120, 160
+        rects = np.zeros((n, nparts, 4), np.int32)
+        cx, cy = rng.integers(-20, w + 20, n), rng.integers(-20, h + 20, n)
+        for p in range(nparts):
+            rects[:, p, 0] = cx + rng.integers(-15, 15, n)
+            rects[:, p, 1] = cy + rng.integers(-15, 15, n)
+            rects[:, p, 2] = rng.integers(5, 30, n)
+            rects[:, p, 3] = rng.integers(5, 30, n)
+        scores = np.sort(rng.standard_normal(n).astype(np.float32))[::-1].copy()
+        overlap = float([0.0, 0.1, 0.5][trial % 3])
+        keep = np.zeros(n, np.int32)
+        nk = L.orc_nms(np.ascontiguousarray(rects).reshape(-1), n, nparts, h, w, overlap, keep)
+        meta = np.zeros((n, 4), np.int32)
+        meta[:, 3] = nparts
+        parts = np.zeros((n, nparts, 7), np.int32)
+        parts[:, :, 3:7] = rects
+        parts[:, :, 0] = np.arange(n)[:, None]            # tag candidates by index in x[0]
+        out = Candidate.nonMaximaSuppression((h, w), CandidateList(meta, scores, parts), overlap)
+        assert [int(c.x[0]) for c in out] == keep[:nk].tolist()
+        lst = list(CandidateList(meta, scores, parts))
+        Candidate.nonMaximaSuppression(np.zeros((h, w, 3), np.uint8), lst, overlap)
+        assert [int(c.x[0]) for c in lst] == keep[:nk].tolist()
+    # boundingBox
+    c = CandidateList(meta, scores, parts)[0]
+    x0, y0 = rects[0, :, 0].min(), rects[0, :, 1].min()
+    assert c.boundingBox() == (x0, y0, (rects[0, :, 0] + rects[0, :, 2]).max() - x0, (rects[0, :, 1] + rects[0, :, 3]).max() - y0)
