@@ -1,10 +1,12 @@
 // hog.cu -- HOGFeatures<float>::features<uint8_t> (reference src/HOGFeatures.cpp:168-341) as two kernels.
 //
-// hog_hist   one thread per HOG block (by,bx): gathers the (2*sbin)^2 pixel window that scatters into this
-//            block in the reference (bilinear scatter, :252-265), visiting pixels in raster order and adding
-//            the matching-orientation term with a separately rounded multiply and add.  Because every
-//            histogram bin receives its terms in the same order as the reference's sequential scatter,
-//            the float sums are bit-identical (no atomics, deterministic).  Also emits the block energy (:270-283).
+// hog_hist   CTA = 16x8 HOG blocks.  Phase 1 computes gradient magnitude and snapped orientation of every pixel of the
+//            tile's footprint exactly once into shared memory.  Phase 2: one thread per block (by,bx) gathers the
+//            (2*sbin)^2 pixel window that scatters into this block in the reference (bilinear scatter, :252-265),
+//            visiting pixels in raster order and adding the term into its shared-memory histogram with a separately
+//            rounded multiply and add.  Because every bin receives its terms in the same order as the reference's
+//            sequential scatter, the float sums are bit-identical (no atomics, deterministic).  Also emits the
+//            block energy (:270-283).
 // hog_feat   one thread per output cell: 4 normalisers with double sqrt/divide (:292-299), 18 contrast-
 //            sensitive + 9 insensitive + 4 texture + 1 truncation features (:304-338), written HWC.
 // Both are HBM/L2-bound streaming kernels (48 B of image read and 128 B written per cell).
@@ -13,70 +15,67 @@
 namespace pbd {
 namespace {
 
-__device__ __forceinline__ int find_level_by_block(const Geometry* g, int idx) {
-  int l = 0;
-  while (l + 1 < g->n_levels && idx >= g->lv[l + 1].block_off) ++l;
-  return l;
-}
 __device__ __forceinline__ int find_level_by_cell(const Geometry* g, int idx) {
   int l = 0;
   while (l + 1 < g->n_levels && idx >= g->lv[l + 1].cell_off) ++l;
   return l;
 }
 
+// (T)(((T)p + 0.5) / (T)sbin - 0.5), reference :252-253 (double intermediates).  For power-of-two bin sizes the
+// division is an exact scaling, so it is replaced by the (equally exact) multiplication with 1/sbin.
+__device__ __forceinline__ float bin_coord(int p, int sbin, double dsb, double inv_sb, bool pow2) {
+  const double t = (double)(float)p + 0.5;
+  return (float)((pow2 ? __dmul_rn(t, inv_sb) : __ddiv_rn(t, dsb)) - 0.5);
+}
+
+constexpr int HB_X = 16, HB_Y = 8;                 // HOG blocks per CTA (one thread per block)
+
 template <int CN>
-__global__ void __launch_bounds__(128) hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr,
-                                                float* __restrict__ hist, float* __restrict__ norm, int sbin) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= g->blocks_total) return;
+__global__ void __launch_bounds__(HB_X * HB_Y)
+hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float* __restrict__ hist, float* __restrict__ norm, int sbin) {
+  extern __shared__ __align__(16) unsigned char hsm[];
+  // ---- which tile of which level ----
+  int tile = blockIdx.x, l = 0, tiles_x = 0;
+  for (; l < g->n_levels; ++l) {
+    tiles_x = (g->lv[l].bw + HB_X - 1) / HB_X;
+    const int nt = tiles_x * ((g->lv[l].bh + HB_Y - 1) / HB_Y);
+    if (tile < nt) break;
+    tile -= nt;
+  }
+  if (l >= g->n_levels) return;
   const int frame = blockIdx.y;
-  const int l = find_level_by_block(g, idx);
   const LevelDesc& L = g->lv[l];
-  const int local = idx - L.block_off;
-  const int bx = local % L.bw, by = local / L.bw;
+  const int bx0 = (tile % tiles_x) * HB_X, by0 = (tile / tiles_x) * HB_Y;
   const int cols = L.img_w, rows = L.img_h;
   const int vis_w = L.bw * sbin, vis_h = L.bh * sbin;
   const uint8_t* im = pyr + (size_t)frame * g->img_bytes + L.img_off;
   const size_t stride = (size_t)cols * CN;
+  // pixel region that can scatter into this tile's blocks: floor((p+0.5)/sbin - 0.5) in {b-1, b}
+  const int marg = (sbin + 1) / 2 + 1;
+  const int px0 = bx0 * sbin - marg, py0 = by0 * sbin - marg;
+  const int PW = HB_X * sbin + sbin + 2 * marg, PH = HB_Y * sbin + sbin + 2 * marg;
+  float* smag = reinterpret_cast<float*>(hsm);                       // [PH][PW] gradient magnitude (sqrt(v)); < 0 = pixel not visited
+  float* shist = smag + PH * PW;                                     // [18][HB_X*HB_Y] histogram of each thread's block
+  unsigned char* sbo = reinterpret_cast<unsigned char*>(shist + 18 * HB_X * HB_Y);   // [PH][PW] snapped orientation
 
   const float uu[9] = {(float)1.000, (float)0.9397, (float)0.7660, (float)0.5000, (float)0.1736,
                        (float)-0.1736, (float)-0.5000, (float)-0.7660, (float)-0.9397};
   const float vv[9] = {(float)0.000, (float)0.3420, (float)0.6428, (float)0.8660, (float)0.9848,
                        (float)0.9848, (float)0.8660, (float)0.6428, (float)0.3420};
-  float h[18];
-#pragma unroll
-  for (int o = 0; o < 18; ++o) h[o] = 0.f;
-
-  // pixels with floor((p+0.5)/sbin - 0.5) in {b-1, b}; generous bounds, exact membership test below
-  const int y_lo = max(1, by * sbin - (sbin + 1) / 2 - 1), y_hi = min(vis_h - 2, by * sbin + (3 * sbin) / 2 + 1);
-  const int x_lo = max(1, bx * sbin - (sbin + 1) / 2 - 1), x_hi = min(vis_w - 2, bx * sbin + (3 * sbin) / 2 + 1);
-  const double dsb = (double)(float)sbin;
-  for (int y = y_lo; y <= y_hi; ++y) {
-    const float yp = (float)(((double)(float)y + 0.5) / dsb - 0.5);          // :252
-    const int iyp = (int)floorf(yp);
-    const float vy0 = __fsub_rn(yp, (float)iyp);
-    float wy;
-    if (iyp == by) wy = (float)(1.0 - (double)vy0);                           // vy1, :258
-    else if (iyp == by - 1) wy = vy0;
-    else continue;
-    const int sy = min(y, rows - 2);
-    const uint8_t* rowp = im + (size_t)sy * stride;
-    for (int x = x_lo; x <= x_hi; ++x) {
-      const float xp = (float)(((double)(float)x + 0.5) / dsb - 0.5);
-      const int ixp = (int)floorf(xp);
-      const float vx0 = __fsub_rn(xp, (float)ixp);
-      float wx;
-      if (ixp == bx) wx = (float)(1.0 - (double)vx0);
-      else if (ixp == bx - 1) wx = vx0;
-      else continue;
-      const int sx = min(x, cols - 2);
-      const uint8_t* s = rowp + sx * CN;
+  // ---- phase 1: per pixel gradient, channel pick, orientation snap (each pixel of the region exactly once) ----
+  for (int i = threadIdx.x; i < PW * PH; i += HB_X * HB_Y) {
+    const int x = px0 + i % PW, y = py0 + i / PW;
+    float mag = -1.f;
+    int best_o = 0;
+    if (x >= 1 && x <= vis_w - 2 && y >= 1 && y <= vis_h - 2) {       // the reference's pixel loops, :202-203
+      const int sx = min(x, cols - 2), sy = min(y, rows - 2);
+      const uint8_t* s = im + (size_t)sy * stride + sx * CN;
       float dx, dy, v;
-      if (CN == 1) {                                                         // :207-212
+      if (CN == 1) {                                                   // :207-212
         dy = (float)((int)s[stride] - (int)*(s - stride));
         dx = (float)((int)s[1] - (int)*(s - 1));
         v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-      } else {                                                               // :217-240
+      } else {                                                         // :217-240
         const float dyb = (float)((int)s[stride] - (int)*(s - stride));
         const float dxb = (float)((int)s[3] - (int)*(s - 3));
         const float vb = __fadd_rn(__fmul_rn(dxb, dxb), __fmul_rn(dyb, dyb));
@@ -89,23 +88,59 @@ __global__ void __launch_bounds__(128) hog_hist(const Geometry* __restrict__ g, 
         if (vg > v) { v = vg; dx = dxg; dy = dyg; }
         if (vb > v) { v = vb; dx = dxb; dy = dyb; }
       }
-      float best_dot = 0.f;                                                  // :243-249
-      int best_o = 0;
+      float best_dot = 0.f;                                            // :243-249
 #pragma unroll
       for (int o = 0; o < 9; ++o) {
         const float dot = __fadd_rn(__fmul_rn(uu[o], dx), __fmul_rn(vv[o], dy));
         if (dot > best_dot) { best_dot = dot; best_o = o; }
         else if (-dot > best_dot) { best_dot = -dot; best_o = o + 9; }
       }
-      const float term = __fmul_rn(__fmul_rn(wy, wx), __fsqrt_rn(v));       // :260-265
+      mag = __fsqrt_rn(v);                                             // :260
+    }
+    smag[i] = mag;
+    sbo[i] = (unsigned char)best_o;
+  }
 #pragma unroll
-      for (int o = 0; o < 18; ++o) h[o] = __fadd_rn(h[o], (o == best_o) ? term : 0.f);
+  for (int o = 0; o < 18; ++o) shist[o * (HB_X * HB_Y) + threadIdx.x] = 0.f;
+  __syncthreads();
+
+  // ---- phase 2: one thread per block gathers its window in raster order (bit-identical to the sequential scatter) ----
+  const int bx = bx0 + threadIdx.x % HB_X, by = by0 + threadIdx.x / HB_X;
+  if (bx >= L.bw || by >= L.bh) return;
+  const double dsb = (double)(float)sbin, inv_sb = 1.0 / dsb;
+  const bool pow2 = (sbin & (sbin - 1)) == 0;
+  const int y_lo = max(1, by * sbin - marg), y_hi = min(vis_h - 2, by * sbin + sbin + marg - 1);
+  const int x_lo = max(1, bx * sbin - marg), x_hi = min(vis_w - 2, bx * sbin + sbin + marg - 1);
+  float* myh = shist + threadIdx.x;
+  for (int y = y_lo; y <= y_hi; ++y) {
+    const float yp = bin_coord(y, sbin, dsb, inv_sb, pow2);            // :252
+    const int iyp = (int)floorf(yp);
+    const float vy0 = __fsub_rn(yp, (float)iyp);
+    float wy;
+    if (iyp == by) wy = (float)(1.0 - (double)vy0);                    // vy1, :258
+    else if (iyp == by - 1) wy = vy0;
+    else continue;
+    const float* mrow = smag + (y - py0) * PW - px0;
+    const unsigned char* brow = sbo + (y - py0) * PW - px0;
+    for (int x = x_lo; x <= x_hi; ++x) {
+      const float xp = bin_coord(x, sbin, dsb, inv_sb, pow2);
+      const int ixp = (int)floorf(xp);
+      const float vx0 = __fsub_rn(xp, (float)ixp);
+      float wx;
+      if (ixp == bx) wx = (float)(1.0 - (double)vx0);
+      else if (ixp == bx - 1) wx = vx0;
+      else continue;
+      const float term = __fmul_rn(__fmul_rn(wy, wx), mrow[x]);         // :262-265
+      float* hb = myh + brow[x] * (HB_X * HB_Y);
+      *hb = __fadd_rn(*hb, term);
     }
   }
+  const int idx = L.block_off + by * L.bw + bx;
   float* hp = hist + ((size_t)frame * g->blocks_total + idx) * 18;
+  float h[18];
 #pragma unroll
-  for (int o = 0; o < 18; ++o) hp[o] = h[o];
-  float e = 0.f;                                                             // :270-283
+  for (int o = 0; o < 18; ++o) { h[o] = myh[o * (HB_X * HB_Y)]; hp[o] = h[o]; }
+  float e = 0.f;                                                       // :270-283
 #pragma unroll
   for (int o = 0; o < 9; ++o) { const float t = __fadd_rn(h[o], h[o + 9]); e = __fadd_rn(e, __fmul_rn(t, t)); }
   norm[(size_t)frame * g->blocks_total + idx] = e;
@@ -166,9 +201,20 @@ __global__ void __launch_bounds__(128) hog_feat(const Geometry* __restrict__ g, 
 
 int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int sbin, cudaStream_t s) {
   if (g.blocks_total <= 0) return 0;
-  dim3 gh((g.blocks_total + 127) / 128, g.n_frames);
-  if (g.in_c == 1) hog_hist<1><<<gh, 128, 0, s>>>(d_g, b.pyr, b.hist, b.norm, sbin);
-  else hog_hist<3><<<gh, 128, 0, s>>>(d_g, b.pyr, b.hist, b.norm, sbin);
+  int ntiles = 0;
+  for (int l = 0; l < g.n_levels; ++l) ntiles += ((g.lv[l].bw + HB_X - 1) / HB_X) * ((g.lv[l].bh + HB_Y - 1) / HB_Y);
+  const int marg = (sbin + 1) / 2 + 1;
+  const int PW = HB_X * sbin + sbin + 2 * marg, PH = HB_Y * sbin + sbin + 2 * marg;
+  const size_t smem = (size_t)PW * PH * 5 + (size_t)18 * HB_X * HB_Y * 4 + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(hog_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(hog_hist<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 gh(ntiles, g.n_frames);
+  if (g.in_c == 1) hog_hist<1><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin);
+  else hog_hist<3><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin);
   int n = 1;
   if (g.cells_total > 0) {
     dim3 gf((g.cells_total + 127) / 128, g.n_frames);
