@@ -13,7 +13,7 @@ using namespace pbd;
 
 struct pbd_model { Model m; };
 struct pbd_detector { std::unique_ptr<Engine> e; };
-struct pbd_candidates { std::vector<CandidateRec> v; };
+struct pbd_candidates { CandidateSet s; };
 
 namespace {
 thread_local std::string g_err;
@@ -185,10 +185,10 @@ int pbd_detect_batch_u8(pbd_detector* d, const uint8_t* frames, int n, int h, in
     REQUIRE(d && frames && out, "null argument");
     Engine& e = *d->e;
     e.set_frames_geometry(n, h, w, c);
-    e.upload_frames(frames, row_stride, frame_stride);
-    run_all(e);
+    e.upload_and_pyramid(frames, row_stride, frame_stride);
+    e.run_pdf(); e.run_dp_min(); e.run_argmin();
     auto cs = std::make_unique<pbd_candidates>();
-    e.collect(cs->v);
+    e.collect(cs->s);
     *out = cs.release();
   });
 }
@@ -200,7 +200,7 @@ int pbd_detect_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, 
     e.use_device_frames(d_frames);
     run_all(e);
     auto cs = std::make_unique<pbd_candidates>();
-    e.collect(cs->v);
+    e.collect(cs->s);
     *out = cs.release();
   });
 }
@@ -214,44 +214,45 @@ int pbd_enqueue_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n,
   });
 }
 int pbd_collect_candidates(pbd_detector* d, pbd_candidates** out) {
-  return guarded([&] { REQUIRE(d && out, "null argument"); auto cs = std::make_unique<pbd_candidates>(); d->e->collect(cs->v); *out = cs.release(); });
+  return guarded([&] { REQUIRE(d && out, "null argument"); auto cs = std::make_unique<pbd_candidates>(); d->e->collect(cs->s); *out = cs.release(); });
 }
 
-int pbd_candidates_count(const pbd_candidates* c) { return c ? (int)c->v.size() : 0; }
+int pbd_candidates_count(const pbd_candidates* c) { return c ? c->s.n : 0; }
 int pbd_candidates_nparts(const pbd_candidates* c, int i) {
-  if (!c || i < 0 || i >= (int)c->v.size()) { g_err = "candidate index out of range"; return PBD_E_ARG; }
-  return (int)c->v[i].x.size();
+  if (!c || i < 0 || i >= c->s.n) { g_err = "candidate index out of range"; return PBD_E_ARG; }
+  return c->s.meta[(size_t)i * 4 + 3];
 }
 int pbd_candidates_get(const pbd_candidates* c, int i, int32_t* frame, int32_t* level, int32_t* component, float* score, int32_t* xs,
                        int32_t* ys, int32_t* ms, int32_t* rects_xywh) {
   return guarded([&] {
-    REQUIRE(c && i >= 0 && i < (int)c->v.size(), "candidate index out of range");
-    const CandidateRec& C = c->v[i];
-    if (frame) *frame = C.frame;
-    if (level) *level = C.level;
-    if (component) *component = C.component;
-    if (score) *score = C.score;
-    const size_t np = C.x.size();
-    if (xs) memcpy(xs, C.x.data(), np * sizeof(int));
-    if (ys) memcpy(ys, C.y.data(), np * sizeof(int));
-    if (ms) memcpy(ms, C.m.data(), np * sizeof(int));
-    if (rects_xywh) memcpy(rects_xywh, C.rect.data(), np * 4 * sizeof(int));
+    REQUIRE(c && i >= 0 && i < c->s.n, "candidate index out of range");
+    const CandidateSet& S = c->s;
+    if (frame) *frame = S.meta[(size_t)i * 4];
+    if (level) *level = S.meta[(size_t)i * 4 + 1];
+    if (component) *component = S.meta[(size_t)i * 4 + 2];
+    if (score) *score = S.score[i];
+    const int np = S.meta[(size_t)i * 4 + 3];
+    for (int p = 0; p < np; ++p) {
+      const int* o = S.part(i, p);
+      if (xs) xs[p] = o[0];
+      if (ys) ys[p] = o[1];
+      if (ms) ms[p] = o[2];
+      if (rects_xywh) { rects_xywh[4 * p] = o[3]; rects_xywh[4 * p + 1] = o[4]; rects_xywh[4 * p + 2] = o[5]; rects_xywh[4 * p + 3] = o[6]; }
+    }
   });
 }
 int pbd_candidates_export(const pbd_candidates* c, int32_t* meta4, float* scores, int32_t* parts7, int max_nparts) {
   return guarded([&] {
     REQUIRE(c && meta4 && scores && parts7 && max_nparts > 0, "null argument");
-    for (size_t i = 0; i < c->v.size(); ++i) {
-      const CandidateRec& C = c->v[i];
-      const int np = (int)C.x.size();
+    const CandidateSet& S = c->s;
+    if (S.n == 0) return;
+    memcpy(meta4, S.meta.data(), (size_t)S.n * 4 * sizeof(int));
+    memcpy(scores, S.score.data(), (size_t)S.n * sizeof(float));
+    if (max_nparts == S.stride) { memcpy(parts7, S.parts.data(), S.parts.size() * sizeof(int)); return; }
+    for (int i = 0; i < S.n; ++i) {
+      const int np = S.meta[(size_t)i * 4 + 3];
       REQUIRE(np <= max_nparts, "max_nparts too small");
-      meta4[4 * i] = C.frame; meta4[4 * i + 1] = C.level; meta4[4 * i + 2] = C.component; meta4[4 * i + 3] = np;
-      scores[i] = C.score;
-      int32_t* row = parts7 + i * (size_t)max_nparts * 7;
-      for (int p = 0; p < np; ++p) {
-        row[7 * p] = C.x[p]; row[7 * p + 1] = C.y[p]; row[7 * p + 2] = C.m[p];
-        row[7 * p + 3] = C.rect[4 * p]; row[7 * p + 4] = C.rect[4 * p + 1]; row[7 * p + 5] = C.rect[4 * p + 2]; row[7 * p + 6] = C.rect[4 * p + 3];
-      }
+      memcpy(parts7 + (size_t)i * max_nparts * 7, S.part(i, 0), (size_t)np * 7 * sizeof(int));
     }
   });
 }
@@ -259,7 +260,10 @@ void pbd_candidates_free(pbd_candidates* c) { delete c; }
 int pbd_candidates_sort(pbd_candidates* c) {
   return guarded([&] {
     REQUIRE(c, "null argument");
-    std::stable_sort(c->v.begin(), c->v.end(), [](const CandidateRec& a, const CandidateRec& b) { return a.score > b.score; });
+    std::vector<int> order(c->s.n);
+    for (int i = 0; i < c->s.n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->s.score[a] > c->s.score[b]; });
+    c->s.select(order);
   });
 }
 
@@ -284,25 +288,27 @@ inline IRect rect_and(IRect a, const IRect& b) {           // cv::Rect operator&
 int pbd_candidates_nms(pbd_candidates* c, int im_h, int im_w, float overlap) {
   return guarded([&] {
     REQUIRE(c && im_h > 0 && im_w > 0, "bad argument");
-    std::vector<CandidateRec> kept;
-    kept.reserve(c->v.size());
+    const CandidateSet& S = c->s;
+    std::vector<int> kept;
+    kept.reserve(S.n);
     std::vector<uint8_t> scratch((size_t)im_h * im_w);
     const IRect bounds{0, 0, im_w, im_h};
     int cur_frame = -1 << 30;
-    for (const CandidateRec& C : c->v) {
-      if (C.frame != cur_frame) { std::fill(scratch.begin(), scratch.end(), 0); cur_frame = C.frame; }   // one scratch image per frame
-      const int np = (int)C.x.size();
-      IRect hull{C.rect[0], C.rect[1], C.rect[2], C.rect[3]};                       // Candidate::boundingBox, :104-110
-      for (int p = 0; p < np; ++p) hull = rect_or(hull, IRect{C.rect[4 * p], C.rect[4 * p + 1], C.rect[4 * p + 2], C.rect[4 * p + 3]});
+    for (int i = 0; i < S.n; ++i) {
+      const int frame = S.meta[(size_t)i * 4], np = S.meta[(size_t)i * 4 + 3];
+      if (frame != cur_frame) { std::fill(scratch.begin(), scratch.end(), 0); cur_frame = frame; }   // one scratch image per frame
+      const int* p0 = S.part(i, 0);
+      IRect hull{p0[3], p0[4], p0[5], p0[6]};                                        // Candidate::boundingBox, :104-110
+      for (int p = 0; p < np; ++p) { const int* o = S.part(i, p); hull = rect_or(hull, IRect{o[3], o[4], o[5], o[6]}); }
       const IRect box = rect_and(hull, bounds);
       long long sum = 0;
       for (int y = box.y; y < box.y + box.h; ++y) { const uint8_t* r = &scratch[(size_t)y * im_w + box.x]; for (int x = 0; x < box.w; ++x) sum += r[x]; }
       const double ratio = (double)sum / (box.w * box.h);                             // boxsum[0] / box.area() (NaN for an empty box => kept)
       if (ratio > (double)overlap) continue;
       for (int y = box.y; y < box.y + box.h; ++y) memset(&scratch[(size_t)y * im_w + box.x], 1, (size_t)box.w);
-      kept.push_back(C);
+      kept.push_back(i);
     }
-    c->v.swap(kept);
+    c->s.select(kept);
   });
 }
 
@@ -310,18 +316,12 @@ int pbd_candidates_create(int n, int max_nparts, const int32_t* meta4, const flo
   return guarded([&] {
     REQUIRE(n >= 0 && max_nparts > 0 && out && (n == 0 || (meta4 && scores && parts7)), "bad argument");
     auto cs = std::make_unique<pbd_candidates>();
-    cs->v.resize(n);
-    for (int i = 0; i < n; ++i) {
-      CandidateRec& C = cs->v[i];
-      C.frame = meta4[4 * i]; C.level = meta4[4 * i + 1]; C.component = meta4[4 * i + 2];
-      const int np = meta4[4 * i + 3];
-      REQUIRE(np > 0 && np <= max_nparts, "bad part count");
-      C.score = scores[i];
-      const int32_t* row = parts7 + (size_t)i * max_nparts * 7;
-      for (int p = 0; p < np; ++p) {
-        C.x.push_back(row[7 * p]); C.y.push_back(row[7 * p + 1]); C.m.push_back(row[7 * p + 2]);
-        for (int t = 0; t < 4; ++t) C.rect.push_back(row[7 * p + 3 + t]);
-      }
+    cs->s.resize(n, max_nparts);
+    for (int i = 0; i < n; ++i) REQUIRE(meta4[4 * i + 3] > 0 && meta4[4 * i + 3] <= max_nparts, "bad part count");
+    if (n) {
+      memcpy(cs->s.meta.data(), meta4, (size_t)n * 4 * sizeof(int));
+      memcpy(cs->s.score.data(), scores, (size_t)n * sizeof(float));
+      memcpy(cs->s.parts.data(), parts7, (size_t)n * max_nparts * 7 * sizeof(int));
     }
     *out = cs.release();
   });
@@ -343,7 +343,7 @@ int pbd_stage_dp_argmin(pbd_detector* d, pbd_candidates** out) {
     REQUIRE(d && out, "null argument");
     d->e->run_argmin();
     auto cs = std::make_unique<pbd_candidates>();
-    d->e->collect(cs->v);
+    d->e->collect(cs->s);
     *out = cs.release();
   });
 }

@@ -84,6 +84,7 @@ Engine::~Engine() {
                   d_cg_level_, d_cg_col0_, d_hits_, d_nhits_, d_xym_, d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, b_.val};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_pinned_) cudaFreeHost(h_pinned_);
+  if (copy_stream_) { cudaStreamDestroy(copy_stream_); for (auto& e : copy_ev_) cudaEventDestroy(e); cudaEventDestroy(main_ev_); }
   for (int i = 0; i < 7; ++i) if (ev_[i]) cudaEventDestroy(ev_[i]);
 }
 
@@ -437,6 +438,45 @@ void Engine::upload_frames(const uint8_t* frames, size_t row_stride, size_t fram
   b_.frames = d_frames_own_;
 }
 
+// Host frames: the H2D copy is issued in chunks on a copy stream and the image pyramid + HOG of each chunk start as soon
+// as its frames have landed, so the transfer of chunk i+1 overlaps the feature stage of chunk i.
+void Engine::upload_and_pyramid(const uint8_t* frames, size_t row_stride, size_t frame_stride) {
+  need(1, "upload_and_pyramid");
+  if (!have_images_) throw StateError("upload_and_pyramid: batch was defined by pbd_set_levels");
+  const size_t row = (size_t)g_.in_w * g_.in_c, fb = row * g_.in_h;
+  if (row_stride == 0) row_stride = row;
+  if (frame_stride == 0) frame_stride = row_stride * g_.in_h;
+  const int n = g_.n_frames;
+  if (timing || n < 8 || row_stride != row || frame_stride != fb) {       // per-stage timing wants separable stages
+    upload_frames(frames, row_stride, frame_stride);
+    run_pyramid();
+    return;
+  }
+  ensure(d_frames_own_, cap_frames_, fb * n);
+  b_.frames = d_frames_own_;
+  if (!copy_stream_) {
+    check_cuda(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : copy_ev_) check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    check_cuda(cudaEventCreateWithFlags(&main_ev_, cudaEventDisableTiming), "cudaEventCreate");
+  }
+  // the copy stream must not overwrite frames still being read by work already queued on the main stream
+  check_cuda(cudaEventRecord(main_ev_, stream_), "event");
+  check_cuda(cudaStreamWaitEvent(copy_stream_, main_ev_, 0), "wait");
+  const int nchunks = 4;
+  for (int c = 0; c < nchunks; ++c) {
+    const int f0 = (int)((long long)n * c / nchunks), f1 = (int)((long long)n * (c + 1) / nchunks);
+    if (f1 <= f0) continue;
+    check_cuda(cudaMemcpyAsync(d_frames_own_ + fb * f0, frames + fb * f0, fb * (f1 - f0), cudaMemcpyHostToDevice, copy_stream_), "H2D frames");
+    check_cuda(cudaEventRecord(copy_ev_[c], copy_stream_), "event");
+    check_cuda(cudaStreamWaitEvent(stream_, copy_ev_[c], 0), "wait");
+    launches_ += launch_pyramid(g_, d_g_, b_, d_xofs_, d_xalpha_, d_yofs_, d_ybeta_, f0, f1 - f0, stream_);
+    launches_ += launch_hog(g_, d_g_, b_, model_.sbin, f0, f1 - f0, stream_);
+  }
+  check_cuda(cudaGetLastError(), "pyramid/HOG launch");
+  feat_from_hog_ = true;
+  stage_ = 2;
+}
+
 void Engine::use_device_frames(const uint8_t* d_frames) {
   need(1, "use_device_frames");
   if (timing) { check_cuda(cudaEventRecord(ev_[0], stream_), "event"); ev_valid_[0] = true; }
@@ -447,9 +487,9 @@ void Engine::run_pyramid() {
   need(1, "pyramid");
   if (!have_images_ || !b_.frames) throw StateError("pyramid: no frames");
   if (timing) { check_cuda(cudaEventRecord(ev_[1], stream_), "event"); ev_valid_[1] = true; }
-  launches_ += launch_pyramid(g_, d_g_, b_, d_xofs_, d_xalpha_, d_yofs_, d_ybeta_, model_.interval, stream_);
+  launches_ += launch_pyramid(g_, d_g_, b_, d_xofs_, d_xalpha_, d_yofs_, d_ybeta_, 0, g_.n_frames, stream_);
   if (timing) { check_cuda(cudaEventRecord(ev_[2], stream_), "event"); ev_valid_[2] = true; }
-  launches_ += launch_hog(g_, d_g_, b_, model_.sbin, stream_);
+  launches_ += launch_hog(g_, d_g_, b_, model_.sbin, 0, g_.n_frames, stream_);
   check_cuda(cudaGetLastError(), "pyramid/HOG launch");
   feat_from_hog_ = true;
   stage_ = 2;
@@ -493,24 +533,25 @@ void Engine::run_argmin() {
   stage_ = 5;
 }
 
-void Engine::collect(std::vector<CandidateRec>& out) {
+void Engine::collect(CandidateSet& out) {
   need(5, "collect");
   int nh = 0;
   check_cuda(cudaMemcpyAsync(&nh, d_nhits_, sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H nhits");
   check_cuda(cudaStreamSynchronize(stream_), "sync");
   if (nh > max_candidates)
     throw StateError("candidate buffer overflow: " + std::to_string(nh) + " hits > max_candidates=" + std::to_string(max_candidates));
-  std::vector<Hit> hits(nh);
   const int ps = max_parts_;
-  std::vector<int> xym((size_t)nh * 3 * ps);
+  h_hits_.resize(nh);
+  h_xym_.resize((size_t)nh * 3 * ps);
   if (nh) {
-    check_cuda(cudaMemcpyAsync(hits.data(), d_hits_, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, stream_), "D2H hits");
-    check_cuda(cudaMemcpyAsync(xym.data(), d_xym_, xym.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H parts");
+    check_cuda(cudaMemcpyAsync(h_hits_.data(), d_hits_, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, stream_), "D2H hits");
+    check_cuda(cudaMemcpyAsync(h_xym_.data(), d_xym_, h_xym_.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H parts");
     check_cuda(cudaStreamSynchronize(stream_), "sync");
   }
   // the reference's deterministic (single-threaded) order: frame, level, component, row-major hit
   std::vector<int> order(nh);
   for (int i = 0; i < nh; ++i) order[i] = i;
+  const std::vector<Hit>& hits = h_hits_;
   std::sort(order.begin(), order.end(), [&](int a, int b) {
     const Hit &A = hits[a], &B = hits[b];
     if (A.frame != B.frame) return A.frame < B.frame;
@@ -519,28 +560,26 @@ void Engine::collect(std::vector<CandidateRec>& out) {
     if (A.y != B.y) return A.y < B.y;
     return A.x < B.x;
   });
-  out.clear();
-  out.reserve(nh);
+  out.resize(nh, ps);
   for (int oi = 0; oi < nh; ++oi) {
     const int i = order[oi];
     const Hit& H = hits[i];
     const auto& parts = model_.comps[H.comp];
     const int np = (int)parts.size();
-    CandidateRec C;
-    C.frame = H.frame; C.level = H.level; C.component = H.comp; C.score = H.score;
-    const int* xs = xym.data() + (size_t)i * 3 * ps;
-    C.x.assign(xs, xs + np); C.y.assign(xs + ps, xs + ps + np); C.m.assign(xs + 2 * ps, xs + 2 * ps + np);
+    out.meta[(size_t)oi * 4] = H.frame; out.meta[(size_t)oi * 4 + 1] = H.level; out.meta[(size_t)oi * 4 + 2] = H.comp; out.meta[(size_t)oi * 4 + 3] = np;
+    out.score[oi] = H.score;
+    const int* xs = h_xym_.data() + (size_t)i * 3 * ps;
     const float scale = g_.lv[H.level].scale;
-    C.rect.resize((size_t)np * 4);
     for (int p = 0; p < np; ++p) {                  // reference src/DynamicProgram.cpp:238-244
-      const int ks = model_.frows[parts[p].filterid[C.m[p]]];          // xsize == ysize == rows (Parts.hpp:185-187)
-      const int x1 = cv_round_f((float)(C.x[p] - 1) * scale), y1 = cv_round_f((float)(C.y[p] - 1) * scale);
+      int* o = out.part(oi, p);
+      const int x = xs[p], y = xs[ps + p], mix = xs[2 * ps + p];
+      const int ks = model_.frows[parts[p].filterid[mix]];             // xsize == ysize == rows (Parts.hpp:185-187)
+      const int x1 = cv_round_f((float)(x - 1) * scale), y1 = cv_round_f((float)(y - 1) * scale);
       const int sz = cv_round_f((float)ks * scale);
       const int x2 = x1 + sz - 1, y2 = y1 + sz - 1;
       const int rx = std::min(x1, x2), ry = std::min(y1, y2);
-      C.rect[4 * p] = rx; C.rect[4 * p + 1] = ry; C.rect[4 * p + 2] = std::max(x1, x2) - rx; C.rect[4 * p + 3] = std::max(y1, y2) - ry;
+      o[0] = x; o[1] = y; o[2] = mix; o[3] = rx; o[4] = ry; o[5] = std::max(x1, x2) - rx; o[6] = std::max(y1, y2) - ry;
     }
-    out.push_back(std::move(C));
   }
 }
 

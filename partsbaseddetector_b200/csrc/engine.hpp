@@ -3,6 +3,7 @@
 // src/PartsBasedDetector.cpp:102-127): owns the feature engine, the convolution engine, the part
 // tables and the dynamic program -- here as device buffers, tables and kernel launches.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -18,11 +19,30 @@ struct StateError : std::runtime_error { using std::runtime_error::runtime_error
 struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; };
 struct UnsupportedError : std::runtime_error { using std::runtime_error::runtime_error; };
 
-struct CandidateRec {
-  int frame, level, component;
-  float score;
-  std::vector<int> x, y, m;       // per part: cell location and mixture id
-  std::vector<int> rect;          // per part: cv::Rect x, y, width, height
+// Flat (SoA) candidate set: one allocation per field instead of per candidate.
+struct CandidateSet {
+  int n = 0, stride = 1;           // stride = part slots per candidate
+  std::vector<int> meta;           // n x 4: frame, level, component, nparts
+  std::vector<float> score;        // n: root score (reference confidence_[0])
+  std::vector<int> parts;          // n x stride x 7: x, y, mixture, rect.x, rect.y, rect.width, rect.height
+  void resize(int n_, int stride_) {
+    n = n_; stride = stride_ > 0 ? stride_ : 1;
+    meta.assign((size_t)n * 4, 0); score.assign(n, 0.f); parts.assign((size_t)n * stride * 7, 0);
+  }
+  int* part(int i, int p) { return parts.data() + ((size_t)i * stride + p) * 7; }
+  const int* part(int i, int p) const { return parts.data() + ((size_t)i * stride + p) * 7; }
+  // keep the candidates listed in `order`, in that order
+  void select(const std::vector<int>& order) {
+    CandidateSet o;
+    o.resize((int)order.size(), stride);
+    for (size_t k = 0; k < order.size(); ++k) {
+      const int i = order[k];
+      for (int t = 0; t < 4; ++t) o.meta[k * 4 + t] = meta[(size_t)i * 4 + t];
+      o.score[k] = score[i];
+      std::copy(parts.begin() + (size_t)i * stride * 7, parts.begin() + (size_t)(i + 1) * stride * 7, o.parts.begin() + k * (size_t)stride * 7);
+    }
+    *this = std::move(o);
+  }
 };
 
 class Engine {
@@ -41,13 +61,14 @@ class Engine {
   void set_levels_manual(int n, int nlevels, const int32_t* ohow, const float* scales);
   void upload_frames(const uint8_t* frames, size_t row_stride, size_t frame_stride);   // host -> device (async, pinned staging)
   void use_device_frames(const uint8_t* d_frames);
+  void upload_and_pyramid(const uint8_t* frames, size_t row_stride, size_t frame_stride);   // chunked H2D overlapped with pyramid + HOG
 
   // ---- stages (enqueue only) ----
   void run_pyramid();      // image pyramid + HOG  (IFeatures::pyramid)
   void run_pdf();          // IConvolutionEngine::pdf
   void run_dp_min();       // DynamicProgram::min
   void run_argmin();       // DynamicProgram::argmin (device part: hits + backtrack)
-  void collect(std::vector<CandidateRec>& out);   // syncs, downloads and orders the candidates
+  void collect(CandidateSet& out);   // syncs, downloads and orders the candidates
 
   // ---- accessors (sync) ----
   const Geometry& geom() const { return g_; }
@@ -122,6 +143,10 @@ class Engine {
   int* d_nhits_ = nullptr;
   int* d_xym_ = nullptr; size_t cap_xym_ = 0;
   int* d_scratch_i_ = nullptr; size_t cap_scratch_i_ = 0;
+  std::vector<Hit> h_hits_;                    // host staging reused across batches
+  std::vector<int> h_xym_;
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t copy_ev_[4] = {}, main_ev_ = nullptr;
   // timing
   cudaEvent_t ev_[7] = {};
   bool ev_valid_[7] = {};

@@ -32,7 +32,7 @@ constexpr int HB_X = 16, HB_Y = 8;                 // HOG blocks per CTA (one th
 
 template <int CN>
 __global__ void __launch_bounds__(HB_X * HB_Y)
-hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float* __restrict__ hist, float* __restrict__ norm, int sbin) {
+hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float* __restrict__ hist, float* __restrict__ norm, int sbin, int frame0) {
   extern __shared__ __align__(16) unsigned char hsm[];
   // ---- which tile of which level ----
   int tile = blockIdx.x, l = 0, tiles_x = 0;
@@ -43,7 +43,7 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float*
     tile -= nt;
   }
   if (l >= g->n_levels) return;
-  const int frame = blockIdx.y;
+  const int frame = frame0 + blockIdx.y;
   const LevelDesc& L = g->lv[l];
   const int bx0 = (tile % tiles_x) * HB_X, by0 = (tile / tiles_x) * HB_Y;
   const int cols = L.img_w, rows = L.img_h;
@@ -152,10 +152,10 @@ __device__ __forceinline__ float normaliser(const float* p, int stride) {  // :2
 }
 
 __global__ void __launch_bounds__(128) hog_feat(const Geometry* __restrict__ g, const float* __restrict__ hist,
-                                                const float* __restrict__ norm, float* __restrict__ feat) {
+                                                const float* __restrict__ norm, float* __restrict__ feat, int frame0) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g->cells_total) return;
-  const int frame = blockIdx.y;
+  const int frame = frame0 + blockIdx.y;
   const int l = find_level_by_cell(g, idx);
   const LevelDesc& L = g->lv[l];
   const int local = idx - L.cell_off;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) hog_feat(const Geometry* __restrict__ g, 
 
 }  // namespace
 
-int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int sbin, cudaStream_t s) {
+int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int sbin, int frame0, int nframes, cudaStream_t s) {
   if (g.blocks_total <= 0) return 0;
   int ntiles = 0;
   for (int l = 0; l < g.n_levels; ++l) ntiles += ((g.lv[l].bw + HB_X - 1) / HB_X) * ((g.lv[l].bh + HB_Y - 1) / HB_Y);
@@ -212,13 +212,13 @@ int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, i
     cudaFuncSetAttribute(hog_hist<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  dim3 gh(ntiles, g.n_frames);
-  if (g.in_c == 1) hog_hist<1><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin);
-  else hog_hist<3><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin);
+  dim3 gh(ntiles, nframes);
+  if (g.in_c == 1) hog_hist<1><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin, frame0);
+  else hog_hist<3><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin, frame0);
   int n = 1;
   if (g.cells_total > 0) {
-    dim3 gf((g.cells_total + 127) / 128, g.n_frames);
-    hog_feat<<<gf, 128, 0, s>>>(d_g, b.hist, b.norm, b.feat);
+    dim3 gf((g.cells_total + 127) / 128, nframes);
+    hog_feat<<<gf, 128, 0, s>>>(d_g, b.hist, b.norm, b.feat, frame0);
     ++n;
   }
   return n;

@@ -90,8 +90,8 @@ struct Hit {
 
 // ---- launchers (each enqueues on `s`, returns the number of kernels launched) ----
 int launch_pyramid(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_xofs, const short* d_xalpha,
-                   const int* d_yofs, const short* d_ybeta, int interval, cudaStream_t s);
-int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int sbin, cudaStream_t s);
+                   const int* d_yofs, const short* d_ybeta, int frame0, int nframes, cudaStream_t s);
+int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int sbin, int frame0, int nframes, cudaStream_t s);
 
 // device copy of the model's filters (converted to float, reference src/PartsBasedDetector.cpp:115-117)
 struct FilterBank {

@@ -19,13 +19,13 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 __global__ void __launch_bounds__(256) pyr_resize_u8(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames,
                                                      uint8_t* __restrict__ pyr, const int* __restrict__ xofs,
                                                      const short* __restrict__ xalpha, const int* __restrict__ yofs,
-                                                     const short* __restrict__ ybeta, int level) {
+                                                     const short* __restrict__ ybeta, int level, int frame0) {
   const LevelDesc& L = g->lv[level];
   const int dw = L.img_w, dh = L.img_h, cn = g->in_c, sw = g->in_w, sh = g->in_h;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= dw * dh) return;
   const int dx = idx % dw, dy = idx / dw;
-  const int frame = blockIdx.y;
+  const int frame = frame0 + blockIdx.y;
   const uint8_t* S = frames + (size_t)frame * sh * sw * cn;
   uint8_t* D = pyr + (size_t)frame * g->img_bytes + L.img_off + (size_t)idx * cn;
   const int sx = xofs[L.xofs_off + dx], sx1 = min(sx + 1, sw - 1);
@@ -44,14 +44,14 @@ __global__ void __launch_bounds__(256) pyr_resize_u8(const Geometry* __restrict_
 }
 
 // One thread per destination pixel: out = (sum_{i,j} k[i]k[j] src[2y+i-2][2x+j-2] + 128) >> 8, k = [1 4 6 4 1].
-__global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ g, uint8_t* __restrict__ pyr, int level) {
+__global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ g, uint8_t* __restrict__ pyr, int level, int frame0) {
   const LevelDesc& L = g->lv[level];
   const LevelDesc& P = g->lv[L.src_level];
   const int dw = L.img_w, dh = L.img_h, cn = g->in_c, sw = P.img_w, sh = P.img_h;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= dw * dh) return;
   const int x = idx % dw, y = idx / dw;
-  const int frame = blockIdx.y;
+  const int frame = frame0 + blockIdx.y;
   const uint8_t* S = pyr + (size_t)frame * g->img_bytes + P.img_off;
   uint8_t* D = pyr + (size_t)frame * g->img_bytes + L.img_off + (size_t)idx * cn;
   const int k[5] = {1, 4, 6, 4, 1};
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ 
 }  // namespace
 
 int launch_pyramid(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_xofs, const short* d_xalpha,
-                   const int* d_yofs, const short* d_ybeta, int interval, cudaStream_t s) {
+                   const int* d_yofs, const short* d_ybeta, int frame0, int nframes, cudaStream_t s) {
   int launches = 0;
   // resized levels depend only on the frame; pyrDown level l depends on level l - interval, so
   // launching levels in increasing order on one stream satisfies every dependency.
@@ -83,12 +83,11 @@ int launch_pyramid(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
     const LevelDesc& L = g.lv[l];
     const int npx = L.img_w * L.img_h;
     if (npx <= 0) continue;
-    dim3 grid((npx + 255) / 256, g.n_frames);
-    if (L.src_level < 0) pyr_resize_u8<<<grid, 256, 0, s>>>(d_g, b.frames, b.pyr, d_xofs, d_xalpha, d_yofs, d_ybeta, l);
-    else pyr_down_u8<<<grid, 256, 0, s>>>(d_g, b.pyr, l);
+    dim3 grid((npx + 255) / 256, nframes);
+    if (L.src_level < 0) pyr_resize_u8<<<grid, 256, 0, s>>>(d_g, b.frames, b.pyr, d_xofs, d_xalpha, d_yofs, d_ybeta, l, frame0);
+    else pyr_down_u8<<<grid, 256, 0, s>>>(d_g, b.pyr, l, frame0);
     ++launches;
   }
-  (void)interval;
   return launches;
 }
 
