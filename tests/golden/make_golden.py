@@ -22,7 +22,7 @@ from partsbaseddetector_b200.synth import synth_frame  # noqa: E402
 import oracle_lib  # noqa: E402
 import refmodel  # noqa: E402
 
-MODELS = ["Person_26parts", "Willowcoffee_5parts", "Person_8parts", "Face_frontal_sparse"]
+MODELS = ["Person_26parts", "Willowcoffee_5parts", "Person_8parts", "Face_frontal_sparse", "Face_99filters"]
 
 
 def digest(a):

@@ -368,3 +368,32 @@ def test_config5_dt_4096_bitexact_and_properties():
     assert np.allclose(att, out[0][yy, xx], rtol=1e-5, atol=1e-5)
     inside = (xx + 2 < w) & (yy - 1 >= 0)
     assert np.all(out[0][yy, xx][inside] >= m[np.clip(yy - 1, 0, h - 1), np.clip(xx + 2, 0, w - 1)][inside] - 1e-6)
+
+
+def test_config1_face_qvga_single_scale():
+    """BASELINE.json config 1: face model (Face_99filters stands in for the missing Face_68parts named by
+    conf/config_face.by_parts:31), one 320x240 frame, level 0 only: 13 components, 39/68 single-mixture parts, 99 shared filters."""
+    name = "Face_99filters"
+    fm = load_flat(name)
+    img = synth_frame(31, 240, 320)
+    d, O = detector(name), oracle(name)
+    d.set_option("max_levels", 1)
+    O.set_max_levels(1)
+    O.run(img, 1, 3)
+    thr = lowered_threshold(O, 40)
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    d.set_option("thresh", thr)
+    cands = d.detect(img)
+    assert d.nscales() == 1 and (d.level_info(0)["oh"], d.level_info(0)["ow"]) == (58, 78)
+    for c in range(len(fm.comps)):
+        assert np.array_equal(d.rootv(0, 0, c), O.rootv(0, c)) and np.array_equal(d.rooti(0, 0, c), O.rooti(0, c)), c
+    for (c, p) in ((0, 1), (3, 20), (12, len(fm.comps[12]) - 1)):
+        g, o = d.backptr(0, 0, c, p, 0), O.backptr(0, c, p, 0)
+        assert all(np.array_equal(a, b) for a, b in zip(g, o)), (c, p)
+    oc = O.candidates()
+    assert len(cands) == len(oc) > 0
+    for a, b in zip(cands, oc):
+        assert (a.level, a.component()) == (b["level"], b["component"])
+        assert np.array_equal(a.x, b["x"]) and np.array_equal(a.y, b["y"]) and np.array_equal(a.m, b["m"])
+        assert a.score() == b["score"] and np.array_equal(a.parts(), b["rects"])
