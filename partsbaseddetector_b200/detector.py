@@ -20,9 +20,12 @@ class Model:
         self._h = handle
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            _lib.lib().pbd_model_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().pbd_model_free(self._h)
+                self._h = None
+        except Exception:          # interpreter shutdown: module globals may already be gone
+            pass
 
     @property
     def handle(self):
@@ -259,7 +262,10 @@ class PartsBasedDetector:
         self._model = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:          # interpreter shutdown: module globals may already be gone
+            pass
 
     def close(self):
         if getattr(self, "_d", None):

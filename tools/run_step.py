@@ -30,4 +30,8 @@ det.set_option("timing", 1)
 for _ in range(a.steps):
     det.enqueue_device(dev.data_ptr(), a.batch, a.h, a.w, 3)
 torch.cuda.synchronize()
-print(det.stage_times_ms(), "launches", det.launch_count())
+st = det.stage_times_ms()
+tot = sum(st.values())
+print("batch %d %dx%d levels %d: stage_ms %s total %.3f ms => %.1f frames/s (last step, per-stage events), launches %d"
+      % (a.batch, a.h, a.w, det.nscales(), {k: round(v, 3) for k, v in st.items()}, tot, a.batch / tot * 1e3, det.launch_count()))
+det.close()
