@@ -117,7 +117,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     from partsbaseddetector_b200.synth import synth_frames
-    per_step = 2                                   # frames per step: a bounded sample of the 32-frame workload
+    per_step = 2                                   # frames per step: a bounded sample of the 64-frame workload
     frames = synth_frames(per_step, H, W, start=0)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
@@ -311,7 +311,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (measured: 32 -> 1555, 64 -> 1636, 256 -> 1709 frames/s)")
     ap.add_argument("--unique-frames", type=int, default=8, help="distinct synthetic frames generated per rank (tiled to the batch)")
     ap.add_argument("--fast", action="store_true", help="fused multiply-add responses instead of the bit-exact mode")
     ap.add_argument("--thresh", type=float, default=None)

@@ -80,10 +80,9 @@ Engine::~Engine() {
   cudaStreamSynchronize(stream_);
   void* ptrs[] = {d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
-                  b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_, d_rg_level_, d_rg_row0_,
-                  d_cg_level_, d_cg_col0_, d_hits_, d_nhits_, d_xym_, d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, b_.val};
+                  b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
+                  d_hits_, d_nhits_, d_xym_, d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, b_.val};
   for (void* p : ptrs) if (p) cudaFree(p);
-  if (h_pinned_) cudaFreeHost(h_pinned_);
   if (copy_stream_) { cudaStreamDestroy(copy_stream_); for (auto& e : copy_ev_) cudaEventDestroy(e); cudaEventDestroy(main_ev_); }
   for (int i = 0; i < 7; ++i) if (ev_[i]) cudaEventDestroy(ev_[i]);
 }
@@ -341,23 +340,19 @@ void Engine::build_batch_tables() {
   if (max_ow_ > kMaxDim || max_oh_ > kMaxDim) throw UnsupportedError("pyramid level larger than 1024 cells in one dimension");
   int tx, ty;
   response_tile_dims(response_has_fast_path(fb_) ? 1 : 0, &tx, &ty);
-  std::vector<int> tl, tf(g.n_levels), rgl, rgr, cgl, cgc;
+  std::vector<int> tl, tf(g.n_levels);
   for (int l = 0; l < g.n_levels; ++l) {
     const LevelDesc& L = g.lv[l];
     tf[l] = (int)tl.size();
     const int nt = ((L.oh + ty - 1) / ty) * ((L.ow + tx - 1) / tx);
     for (int i = 0; i < nt; ++i) tl.push_back(l);
-    for (int r = 0; r < L.oh; r += 32) { rgl.push_back(l); rgr.push_back(r); }
-    for (int c = 0; c < L.ow; c += 32) { cgl.push_back(l); cgc.push_back(c); }
   }
-  ntiles_ = (int)tl.size(); nrg_ = (int)rgl.size(); ncg_ = (int)cgl.size();
+  ntiles_ = (int)tl.size();
   auto up = [&](int*& d, size_t& cap, const std::vector<int>& h) {
     ensure(d, cap, h.size());
     if (!h.empty()) check_cuda(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, stream_), "upload batch table");
   };
   up(d_tile_level_, cap_tile_level_, tl); up(d_tile_first_, cap_tile_first_, tf);
-  up(d_rg_level_, cap_rg_level_, rgl); up(d_rg_row0_, cap_rg_row0_, rgr);
-  up(d_cg_level_, cap_cg_level_, cgl); up(d_cg_col0_, cap_cg_col0_, cgc);
   check_cuda(cudaMemcpyAsync(d_g_, &g_, sizeof(Geometry), cudaMemcpyHostToDevice, stream_), "upload geometry");
   // separable-transform passes: geometry (rows: lines = rows of length ow; cols: lines = columns of length oh) and the
   // per-wave map tables (offsets depend on cells_total)

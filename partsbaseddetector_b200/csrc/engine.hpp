@@ -59,7 +59,7 @@ class Engine {
   // ---- batch set-up ----
   void set_frames_geometry(int n, int h, int w, int c);                 // pyramid geometry of HOGFeatures::pyramid
   void set_levels_manual(int n, int nlevels, const int32_t* ohow, const float* scales);
-  void upload_frames(const uint8_t* frames, size_t row_stride, size_t frame_stride);   // host -> device (async, pinned staging)
+  void upload_frames(const uint8_t* frames, size_t row_stride, size_t frame_stride);   // host -> device (async)
   void use_device_frames(const uint8_t* d_frames);
   void upload_and_pyramid(const uint8_t* frames, size_t row_stride, size_t frame_stride);   // chunked H2D overlapped with pyramid + HOG
 
@@ -124,15 +124,12 @@ class Engine {
   int stage_ = 0;                              // 0 none, 1 geometry, 2 features, 3 responses, 4 dp, 5 argmin
   DeviceBuffers b_{};
   uint8_t* d_frames_own_ = nullptr; size_t cap_frames_ = 0;
-  uint8_t* h_pinned_ = nullptr; size_t cap_pinned_ = 0;
   size_t cap_pyr_ = 0, cap_hist_ = 0, cap_norm_ = 0, cap_feat_ = 0, cap_resp_ = 0, cap_work_ = 0, cap_tmp_ = 0, cap_val_ = 0,
          cap_ixdt_ = 0, cap_iyraw_ = 0, cap_ik_ = 0, cap_rootv_ = 0, cap_rooti_ = 0;
   // tables depending on the batch geometry
   int *d_xofs_ = nullptr, *d_yofs_ = nullptr; short *d_xalpha_ = nullptr, *d_ybeta_ = nullptr;
   size_t cap_xofs_ = 0, cap_yofs_ = 0, cap_xalpha_ = 0, cap_ybeta_ = 0;
   int *d_tile_level_ = nullptr, *d_tile_first_ = nullptr; size_t cap_tile_level_ = 0, cap_tile_first_ = 0; int ntiles_ = 0;
-  int *d_rg_level_ = nullptr, *d_rg_row0_ = nullptr; size_t cap_rg_level_ = 0, cap_rg_row0_ = 0; int nrg_ = 0;
-  int *d_cg_level_ = nullptr, *d_cg_col0_ = nullptr; size_t cap_cg_level_ = 0, cap_cg_col0_ = 0; int ncg_ = 0;
   int max_ow_ = 0, max_oh_ = 0;
   PassGeom pg_rows_{}, pg_cols_{};
   PassGeom* d_pg_ = nullptr;                   // [rows, cols]

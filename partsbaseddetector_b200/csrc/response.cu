@@ -27,8 +27,6 @@ constexpr int WF = 6;                // filter groups (of Q) processed per pass 
 constexpr int NT = POSW * WF * 32;   // threads per CTA (192)
 constexpr int CCH = 8;               // channels per weight stage
 
-struct TileRef { int level, ty, tx; };
-
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
