@@ -137,6 +137,9 @@ int pbd_stage_pdf(pbd_detector* d);
 int pbd_stage_dp_min(pbd_detector* d);
 int pbd_stage_dp_argmin(pbd_detector* d, pbd_candidates** out);
 
+/* level table HOGFeatures<T>::pyramid would build for an h x w image (src/HOGFeatures.cpp:95-127 and :174-176), without a
+ * device: returns the number of levels and fills up to `cap` entries of (img_h, img_w, oh, ow) and the scales. */
+int pbd_pyramid_geometry(int h, int w, int sbin, int interval, int max_levels, int cap, int32_t* dims4, float* scales);
 /* geometry of the current batch (IFeatures::nscales / scales, include/IFeatures.hpp:60-66) */
 int pbd_num_frames(const pbd_detector* d);
 int pbd_num_levels(const pbd_detector* d);

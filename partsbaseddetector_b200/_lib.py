@@ -27,7 +27,7 @@ EXPORTS = [
     "pbd_detect_batch_u8_device", "pbd_enqueue_batch_u8_device", "pbd_collect_candidates",
     "pbd_candidates_count", "pbd_candidates_nparts", "pbd_candidates_get", "pbd_candidates_export", "pbd_candidates_free",
     "pbd_candidates_sort", "pbd_candidates_nms", "pbd_candidates_create", "pbd_stage_pyramid", "pbd_stage_pdf", "pbd_stage_dp_min", "pbd_stage_dp_argmin",
-    "pbd_num_frames", "pbd_num_levels", "pbd_level_info", "pbd_get_pyramid_image", "pbd_get_features",
+    "pbd_pyramid_geometry", "pbd_num_frames", "pbd_num_levels", "pbd_level_info", "pbd_get_pyramid_image", "pbd_get_features",
     "pbd_get_response", "pbd_get_rootv", "pbd_get_rooti", "pbd_get_backptr", "pbd_set_levels",
     "pbd_set_features", "pbd_set_response", "pbd_dt2d_f32_device", "pbd_dt2d_f32", "pbd_launch_count",
     "pbd_stage_times_ms", "pbd_device_bytes",
@@ -95,6 +95,7 @@ def lib():
     L.pbd_stage_pdf.argtypes = [vp]
     L.pbd_stage_dp_min.argtypes = [vp]
     L.pbd_stage_dp_argmin.argtypes = [vp, P(vp)]
+    L.pbd_pyramid_geometry.argtypes = [ci, ci, ci, ci, ci, ci, _i32p, _f32p]
     L.pbd_num_frames.argtypes = [vp]
     L.pbd_num_levels.argtypes = [vp]
     L.pbd_level_info.argtypes = [vp, ci, P(ci), P(ci), P(ci), P(ci), P(cf)]

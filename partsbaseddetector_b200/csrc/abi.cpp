@@ -348,6 +348,17 @@ int pbd_stage_dp_argmin(pbd_detector* d, pbd_candidates** out) {
   });
 }
 
+int pbd_pyramid_geometry(int h, int w, int sbin, int interval, int max_levels, int cap, int32_t* dims4, float* scales) {
+  if (h <= 0 || w <= 0 || sbin <= 0 || interval <= 0 || cap < 0 || (cap > 0 && (!dims4 || !scales))) { g_err = "bad argument"; return PBD_E_ARG; }
+  Geometry g{};
+  const int n = compute_pyramid_levels(h, w, sbin, interval, max_levels, g);
+  for (int l = 0; l < n && l < cap; ++l) {
+    dims4[4 * l] = g.lv[l].img_h; dims4[4 * l + 1] = g.lv[l].img_w; dims4[4 * l + 2] = g.lv[l].oh; dims4[4 * l + 3] = g.lv[l].ow;
+    scales[l] = g.lv[l].scale;
+  }
+  return n;
+}
+
 int pbd_num_frames(const pbd_detector* d) { return d ? d->e->geom().n_frames : 0; }
 int pbd_num_levels(const pbd_detector* d) { return d ? d->e->geom().n_levels : 0; }
 int pbd_level_info(const pbd_detector* d, int level, int32_t* img_h, int32_t* img_w, int32_t* oh, int32_t* ow, float* scale) {

@@ -206,12 +206,9 @@ int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, i
   const int marg = (sbin + 1) / 2 + 1;
   const int PW = HB_X * sbin + sbin + 2 * marg, PH = HB_Y * sbin + sbin + 2 * marg;
   const size_t smem = (size_t)PW * PH * 5 + (size_t)18 * HB_X * HB_Y * 4 + 16;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(hog_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(hog_hist<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  // per launch: the attribute is per device and a process may drive several devices
+  if (g.in_c == 1) cudaFuncSetAttribute(hog_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  else cudaFuncSetAttribute(hog_hist<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 gh(ntiles, nframes);
   if (g.in_c == 1) hog_hist<1><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin, frame0);
   else hog_hist<3><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin, frame0);

@@ -243,12 +243,9 @@ template <int KH, int KW>
 void launch_fast(const Geometry* d_g, const int* d_tl, const int* d_tf, int ntiles, int nframes, const DeviceBuffers& b,
                  const FilterBank& fb, int exact, int trunc_zero, cudaStream_t s) {
   const size_t smem = fast_smem_bytes<KH, KW>();
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(part_response<KH, KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(part_response<KH, KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  // per launch: the attribute is per device and a process may drive several devices
+  if (exact) cudaFuncSetAttribute(part_response<KH, KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  else cudaFuncSetAttribute(part_response<KH, KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ntiles, nframes);
   if (exact) part_response<KH, KW, true><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, trunc_zero, b.resp);
   else part_response<KH, KW, false><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, trunc_zero, b.resp);
@@ -281,12 +278,8 @@ int launch_response_tiles(const Geometry& g, const Geometry* d_g, const DeviceBu
   }
   const int HYm = 8 + khm - 1, ROWm = 16 + kwm - 1;
   const size_t smem = (size_t)32 * (HYm * ROWm + 1) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(part_response_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(part_response_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  if (exact) cudaFuncSetAttribute(part_response_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  else cudaFuncSetAttribute(part_response_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ntiles, g.n_frames);
   if (exact) part_response_generic<true><<<grid, 128, smem, s>>>(d_g, d_tile_level, d_tile_first, b.feat, fb.wg, fb.foff, fb.fkh, fb.fkw, fb.nfilters, khm, kwm, b.resp);
   else part_response_generic<false><<<grid, 128, smem, s>>>(d_g, d_tile_level, d_tile_first, b.feat, fb.wg, fb.foff, fb.fkh, fb.fkw, fb.nfilters, khm, kwm, b.resp);

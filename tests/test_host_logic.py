@@ -128,3 +128,33 @@ def test_nms_matches_oracle_restatement():
     c = CandidateList(meta, scores, parts)[0]
     x0, y0 = rects[0, :, 0].min(), rects[0, :, 1].min()
     assert c.boundingBox() == (x0, y0, (rects[0, :, 0] + rects[0, :, 2]).max() - x0, (rects[0, :, 1] + rects[0, :, 3]).max() - y0)
+
+
+def test_pyramid_geometry_matches_oracle_over_many_sizes():
+    """Level tables (image sizes, HOG cell counts, scales) of the product's host code vs the oracle's restatement of
+    src/HOGFeatures.cpp:95-127,174-176 for ~1500 image sizes incl. exact powers of two of 5*sbin (floor(log/log) edge cases)."""
+    import oracle_lib
+    from partsbaseddetector_b200 import _lib
+    L, O = _lib.lib(), oracle_lib.lib()
+    rng = np.random.default_rng(1)
+    sizes = [(480, 640), (1080, 1920), (240, 320), (20, 20), (40, 40), (80, 80), (160, 160), (320, 320), (640, 640), (1280, 1280), (2560, 2560),
+             (40, 999), (159, 161), (161, 159), (21, 4000)]
+    sizes += [(int(h), int(w)) for h, w in zip(rng.integers(20, 2200, 700), rng.integers(20, 2200, 700))]
+    for sbin, interval in ((4, 3), (8, 3), (4, 10), (8, 10)):
+        for (h, w) in sizes:
+            if min(h, w) < 5 * sbin:
+                continue
+            dims = np.zeros(4 * 96, np.int32)
+            sc = np.zeros(96, np.float32)
+            n = L.pbd_pyramid_geometry(h, w, sbin, interval, 0, 96, dims, sc)
+            wh = np.zeros(2 * 96, np.int32)
+            osc = np.zeros(96, np.float32)
+            on = O.orc_pyramid_geometry(h, w, sbin, interval, 96, wh, osc)
+            assert n == on, (h, w, sbin, interval)
+            for l in range(min(n, 96)):
+                assert (dims[4 * l + 1], dims[4 * l]) == (wh[2 * l], wh[2 * l + 1]), (h, w, l)
+                assert sc[l] == osc[l]
+                oh, ow = oracle_lib.C.c_int(), oracle_lib.C.c_int()
+                O.orc_hog_dims(int(dims[4 * l]), int(dims[4 * l + 1]), sbin, oracle_lib.C.byref(oh), oracle_lib.C.byref(ow))
+                assert (dims[4 * l + 2], dims[4 * l + 3]) == (oh.value, ow.value)
+    assert L.pbd_pyramid_geometry(0, 10, 4, 3, 0, 0, dims, sc) < 0
