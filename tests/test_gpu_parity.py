@@ -397,3 +397,25 @@ def test_config1_face_qvga_single_scale():
         assert (a.level, a.component()) == (b["level"], b["component"])
         assert np.array_equal(a.x, b["x"]) and np.array_equal(a.y, b["y"]) and np.array_equal(a.m, b["m"])
         assert a.score() == b["score"] and np.array_equal(a.parts(), b["rects"])
+
+
+def test_large_batch_indexing():
+    """70 frames (7 distinct, cycled) in one batch: every frame's root scores and candidates equal the single-frame run
+    (exercises the frame strides of every buffer beyond the small batches used elsewhere)."""
+    d = detector("Person_26parts")
+    base = synth_frames(7, 144, 192, start=300)
+    batch = np.ascontiguousarray(np.stack([base[i % 7] for i in range(70)]))
+    d.set_option("thresh", -1.25)
+    singles = []
+    for i in range(7):
+        c = d.detect(base[i])
+        singles.append(([(k.level, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score())) for k in c], d.rootv(0, 0).copy(), d.rootv(0, d.nscales() - 1).copy()))
+    allc = d.detect(batch)
+    per_frame = {}
+    for k in allc:
+        per_frame.setdefault(k.frame, []).append((k.level, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score())))
+    assert sum(len(s[0]) for s in singles) > 0
+    for f in range(70):
+        assert per_frame.get(f, []) == singles[f % 7][0], f
+    for f in (0, 33, 69):
+        assert np.array_equal(d.rootv(f, 0), singles[f % 7][1]) and np.array_equal(d.rootv(f, d.nscales() - 1), singles[f % 7][2])
