@@ -10,11 +10,11 @@
 // Streaming formulation (bit-identical to build-then-scan).  In the reference's second loop parabola k is
 // chosen for exactly the integer positions pos with z[k] < pos <= z[k+1].  On real score maps almost every
 // sample stays on the envelope (measured: stack depth ~0.95 N, 5-8 % pops), so instead of materialising the
-// whole stack and re-reading it, the top W entries live in a per-lane shared-memory ring; when a push
-// overflows the ring the oldest entry is *retired*: its position range is evaluated and written at once.
-// A pop that digs below the ring (rare) reloads the entry from a write-mostly backing store in local
-// memory and marks it un-retired, so its (now longer) range is simply written again later; the last write
-// to every position is therefore the one the reference's scan would produce.
+// whole stack and re-reading it, the range of the current top is evaluated and stored the moment the next
+// sample is pushed (see envelope_stream); a pop just causes the affected positions to be stored again by
+// their new owner, and the last store to every position is the one the reference's scan would produce.
+// The newest 8 stack entries live in a per-lane shared-memory ring for pops; deeper pops (rare) go to a
+// write-mostly backing store in local memory.
 //
 // 2-D transform (compute, :203-245) = dt_rows (x direction, anchor x) then dt_cols (y direction, anchor y);
 // mix_max then forms, per cell and parent mixture,  max_mm(dt[mm] + bias[mm][pm])  (Math::reduceMax,
@@ -88,24 +88,27 @@ struct Ring {
 
 // One lane's 1-D transform.  loady(q) = src[q] (called for q = 0..N-1 in order, and again for deep-pop reloads);
 // emit(i, val, v) stores dst[i] = val, ptr[i] = v (may be called more than once for an i; the last call wins).
-// zb/pb: backing store of the envelope as a linked list threaded through the sample index (zb[q] = break point of
-// the parabola pushed at q, pb[q] = the sample below it), written in lock step across lanes (coalesced).
+//
+// Eager emission: when sample q is pushed with break point s, the previous top P (still in registers) owns exactly the
+// integer positions z_P < pos <= s, and they are evaluated and stored at once.  If q (or P) is popped later, the positions
+// are simply stored again by their new owner: every position's FINAL owner E_i emits when its final successor E_{i+1} is
+// pushed, and since break points increase up the stack no later emission (all above E_{i+1}) can touch a position
+// <= z_{E_{i+1}}, so the last store to every position is the reference's scan result.
+//
+// The ring holds the newest 8 stack entries for pops (5-8 % of the steps); zb/pb are the backing store of the whole
+// envelope as a linked list threaded through the sample index (zb[q] = break point of the parabola pushed at q,
+// pb[q] = the sample below it), written in lock step across lanes (coalesced) and read only by pops deeper than the ring.
 template <typename LoadY, typename Emit>
 __device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, Ring& R, int lane, float* zb, unsigned short* pb,
                                                 LoadY loady, Emit emit) {
   const float pos_lo = (float)os0, pos_hi = (float)(os0 + N - 1);
-  auto retire = [&](int j, float znext) {
-    const int slot = j & (kRing - 1);
-    const float zj = R.z[slot][lane];
-    // integer positions with zj < pos <= znext, clipped to [os0, os0+N-1]
-    const int lo = (zj < pos_lo) ? os0 : (int)floorf(fminf(zj, pos_hi + 1.f)) + 1;
-    const int hi = (znext >= pos_hi) ? os0 + N - 1 : (int)floorf(fmaxf(znext, pos_lo - 1.f));
-    if (lo > hi) return;
-    const int v = R.vp[slot][lane] & 0xFFFF;
-    const float y = R.y[slot][lane];
+  auto emit_range = [&](float zlo, float zhi, int v, float y) {
+    // integer positions with zlo < pos <= zhi, clipped to [os0, os0+N-1]
+    const int lo = (zlo < pos_lo) ? os0 : (int)floorf(fminf(zlo, pos_hi + 1.f)) + 1;
+    const int hi = (zhi >= pos_hi) ? os0 + N - 1 : (int)floorf(fmaxf(zhi, pos_lo - 1.f));
     for (int pos = lo; pos <= hi; ++pos) emit(pos - os0, envelope(f, pos - v, y), v);
   };
-  int k = 0, ret = 0;
+  int k = 0, base = 0;                                            // stack depth of the top; lowest depth still valid in the ring
   int vt = 0, pt = 0xFFFF;
   float ytf = loady(0), zt = -INFINITY;
   double yt = (double)ytf;
@@ -118,8 +121,8 @@ __device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, R
     while (s <= zt && k > 0) {
       --k;
       const int slot = k & (kRing - 1);
-      if (k < ret) {                                              // popped below the ring: reload from the backing store
-        ret = k;
+      if (k < base) {                                             // popped below the ring: reload from the backing store
+        base = k;
         const int vv = pt;                                        // the entry below the one just popped
         R.vp[slot][lane] = (unsigned)vv | ((unsigned)pb[vv] << 16); R.z[slot][lane] = zb[vv]; R.y[slot][lane] = loady(vv);
       }
@@ -127,17 +130,15 @@ __device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, R
       vt = vp & 0xFFFF; pt = vp >> 16; ytf = R.y[slot][lane]; yt = (double)ytf; zt = R.z[slot][lane];
       s = isect(f, vt, q, yt, yq);
     }
+    emit_range(zt, s, vt, ytf);                                   // the top's positions up to the new break point
     ++k;
-    if (k - ret == kRing) {                                       // ring full: retire the oldest entry
-      retire(ret, R.z[(ret + 1) & (kRing - 1)][lane]);
-      ++ret;
-    }
+    base = max(base, k - (kRing - 1));                            // the slot of depth k - kRing is overwritten
     const int slot = k & (kRing - 1);
     R.vp[slot][lane] = (unsigned)q | ((unsigned)vt << 16); R.y[slot][lane] = yqf; R.z[slot][lane] = s;
     zb[q] = s; pb[q] = (unsigned short)vt;
-    pt = vt; vt = q; yt = yq; zt = s;
+    pt = vt; vt = q; ytf = yqf; yt = yq; zt = s;
   }
-  for (int j = ret; j <= k; ++j) retire(j, j < k ? R.z[(j + 1) & (kRing - 1)][lane] : INFINITY);
+  emit_range(zt, INFINITY, vt, ytf);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -405,7 +405,10 @@ def test_large_batch_indexing():
     d = detector("Person_26parts")
     base = synth_frames(7, 144, 192, start=300)
     batch = np.ascontiguousarray(np.stack([base[i % 7] for i in range(70)]))
-    d.set_option("thresh", -1.25)
+    d.set_option("thresh", 1e9)
+    d.detect(base[0])
+    rv = np.concatenate([d.rootv(0, l).ravel() for l in range(d.nscales())])
+    d.set_option("thresh", float(np.sort(rv)[-30]))            # ~30 candidates per frame
     singles = []
     for i in range(7):
         c = d.detect(base[i])
