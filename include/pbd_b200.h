@@ -104,6 +104,14 @@ int pbd_detect_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, 
 int pbd_enqueue_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, int h, int w, int c);
 int pbd_collect_candidates(pbd_detector* d, pbd_candidates** out);
 
+/* pipelined variant for streams of batches: pbd_submit_batch_u8 enqueues the H2D copy (own copy stream, double-buffered
+ * frame storage) and all stages of a batch and returns a ticket without waiting; pbd_collect_ticket waits for that batch
+ * only and downloads its candidates on a separate stream, so transfer, compute and candidate download of consecutive batches
+ * overlap.  At most two batches may be in flight.  `frames` must be tightly packed, should be pinned host memory and must stay
+ * untouched until its ticket has been collected.  Results equal pbd_detect_batch_u8's. */
+int pbd_submit_batch_u8(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c, int* ticket);
+int pbd_collect_ticket(pbd_detector* d, int ticket, pbd_candidates** out);
+
 /* candidates: reference Candidate (include/Candidate.hpp:56-99) = per part cv::Rect + confidence,
  * component; additionally the frame, pyramid level and per-part (x, y, mixture) in cell coordinates. */
 int pbd_candidates_count(const pbd_candidates* c);

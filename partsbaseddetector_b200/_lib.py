@@ -24,7 +24,7 @@ EXPORTS = [
     "pbd_model_save_bin", "pbd_model_create", "pbd_model_free", "pbd_model_name", "pbd_model_header",
     "pbd_model_filter", "pbd_model_bias", "pbd_model_anchors", "pbd_model_defs", "pbd_model_nparts",
     "pbd_model_part", "pbd_create", "pbd_destroy", "pbd_set_option", "pbd_get_option", "pbd_detect_batch_u8",
-    "pbd_detect_batch_u8_device", "pbd_enqueue_batch_u8_device", "pbd_collect_candidates",
+    "pbd_detect_batch_u8_device", "pbd_enqueue_batch_u8_device", "pbd_collect_candidates", "pbd_submit_batch_u8", "pbd_collect_ticket",
     "pbd_candidates_count", "pbd_candidates_nparts", "pbd_candidates_get", "pbd_candidates_export", "pbd_candidates_free",
     "pbd_candidates_sort", "pbd_candidates_nms", "pbd_candidates_create", "pbd_stage_pyramid", "pbd_stage_pdf", "pbd_stage_dp_min", "pbd_stage_dp_argmin",
     "pbd_pyramid_geometry", "pbd_num_frames", "pbd_num_levels", "pbd_level_info", "pbd_get_pyramid_image", "pbd_get_features",
@@ -83,6 +83,8 @@ def lib():
     L.pbd_detect_batch_u8_device.argtypes = [vp, vp, ci, ci, ci, ci, P(vp)]
     L.pbd_enqueue_batch_u8_device.argtypes = [vp, vp, ci, ci, ci, ci]
     L.pbd_collect_candidates.argtypes = [vp, P(vp)]
+    L.pbd_submit_batch_u8.argtypes = [vp, vp, ci, ci, ci, ci, P(ci)]
+    L.pbd_collect_ticket.argtypes = [vp, ci, P(vp)]
     L.pbd_candidates_count.argtypes = [vp]
     L.pbd_candidates_nparts.argtypes = [vp, ci]
     L.pbd_candidates_get.argtypes = [vp, ci, P(ci), P(ci), P(ci), P(cf), _i32p, _i32p, _i32p, _i32p]

@@ -217,6 +217,18 @@ int pbd_collect_candidates(pbd_detector* d, pbd_candidates** out) {
   return guarded([&] { REQUIRE(d && out, "null argument"); auto cs = std::make_unique<pbd_candidates>(); d->e->collect(cs->s); *out = cs.release(); });
 }
 
+int pbd_submit_batch_u8(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c, int* ticket) {
+  return guarded([&] { REQUIRE(d && frames && ticket, "null argument"); *ticket = d->e->submit(frames, n, h, w, c); });
+}
+int pbd_collect_ticket(pbd_detector* d, int ticket, pbd_candidates** out) {
+  return guarded([&] {
+    REQUIRE(d && out, "null argument");
+    auto cs = std::make_unique<pbd_candidates>();
+    d->e->collect_ticket(ticket, cs->s);
+    *out = cs.release();
+  });
+}
+
 int pbd_candidates_count(const pbd_candidates* c) { return c ? c->s.n : 0; }
 int pbd_candidates_nparts(const pbd_candidates* c, int i) {
   if (!c || i < 0 || i >= c->s.n) { g_err = "candidate index out of range"; return PBD_E_ARG; }

@@ -70,8 +70,12 @@ Engine::Engine(const Model& m, int device, cudaStream_t stream) : thresh((double
   check_cuda(cudaSetDevice(device), "cudaSetDevice");
   build_tables();
   check_cuda(cudaMalloc(&d_g_, sizeof(Geometry)), "cudaMalloc geometry");
-  check_cuda(cudaMalloc(&d_nhits_, sizeof(int)), "cudaMalloc nhits");
-  dev_bytes_ += sizeof(Geometry) + sizeof(int);
+  for (ResultSlot& S : slots_) {
+    check_cuda(cudaMalloc(&S.d_nhits, sizeof(int)), "cudaMalloc nhits");
+    check_cuda(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming), "cudaEventCreate");
+  }
+  for (auto& e : frames_free_ev_) check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+  dev_bytes_ += sizeof(Geometry) + 2 * sizeof(int);
   for (int i = 0; i < 7; ++i) { check_cuda(cudaEventCreate(&ev_[i]), "cudaEventCreate"); }
 }
 
@@ -81,8 +85,12 @@ Engine::~Engine() {
   void* ptrs[] = {d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
-                  d_hits_, d_nhits_, d_xym_, d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, b_.val};
+                  d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, b_.val, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
+                  slots_[1].d_hits, slots_[1].d_nhits, slots_[1].d_xym};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (ResultSlot& S : slots_) if (S.done) cudaEventDestroy(S.done);
+  for (auto& e : frames_free_ev_) if (e) cudaEventDestroy(e);
+  if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
   if (copy_stream_) { cudaStreamDestroy(copy_stream_); for (auto& e : copy_ev_) cudaEventDestroy(e); cudaEventDestroy(main_ev_); }
   for (int i = 0; i < 7; ++i) if (ev_[i]) cudaEventDestroy(ev_[i]);
 }
@@ -411,8 +419,12 @@ void Engine::alloc_batch() {
   ensure(b_.ik, cap_ik_, n * ct * std::max(npm_, 1));
   ensure(b_.rootv, cap_rootv_, n * ct * ncomp);
   ensure(b_.rooti, cap_rooti_, n * ct * ncomp);
-  ensure(d_hits_, cap_hits_, (size_t)max_candidates);
-  ensure(d_xym_, cap_xym_, (size_t)max_candidates * 3 * kMaxParts);
+}
+
+void Engine::ensure_slot(ResultSlot& S) {
+  ensure(S.d_hits, S.cap_hits, (size_t)max_candidates);
+  ensure(S.d_xym, S.cap_xym, (size_t)max_candidates * 3 * std::max(max_parts_, 1));
+  S.max_candidates = max_candidates;
 }
 
 void Engine::upload_frames(const uint8_t* frames, size_t row_stride, size_t frame_stride) {
@@ -435,41 +447,82 @@ void Engine::upload_frames(const uint8_t* frames, size_t row_stride, size_t fram
 
 // Host frames: the H2D copy is issued in chunks on a copy stream and the image pyramid + HOG of each chunk start as soon
 // as its frames have landed, so the transfer of chunk i+1 overlaps the feature stage of chunk i.
+void Engine::chunked_upload_pyramid(const uint8_t* frames, uint8_t* d_dst, cudaEvent_t wait_before_copy, cudaEvent_t record_after) {
+  const size_t fb = (size_t)g_.in_w * g_.in_c * g_.in_h;
+  const int n = g_.n_frames;
+  b_.frames = d_dst;
+  if (!copy_stream_) {
+    check_cuda(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : copy_ev_) check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    check_cuda(cudaEventCreateWithFlags(&main_ev_, cudaEventDisableTiming), "cudaEventCreate");
+  }
+  // the copy stream must not overwrite frames still being read by work already queued
+  check_cuda(cudaStreamWaitEvent(copy_stream_, wait_before_copy, 0), "wait");
+  const int nchunks = n >= 8 ? 4 : 1;
+  for (int c = 0; c < nchunks; ++c) {
+    const int f0 = (int)((long long)n * c / nchunks), f1 = (int)((long long)n * (c + 1) / nchunks);
+    if (f1 <= f0) continue;
+    check_cuda(cudaMemcpyAsync(d_dst + fb * f0, frames + fb * f0, fb * (f1 - f0), cudaMemcpyHostToDevice, copy_stream_), "H2D frames");
+    check_cuda(cudaEventRecord(copy_ev_[c], copy_stream_), "event");
+    check_cuda(cudaStreamWaitEvent(stream_, copy_ev_[c], 0), "wait");
+    launches_ += launch_pyramid(g_, d_g_, b_, d_xofs_, d_xalpha_, d_yofs_, d_ybeta_, f0, f1 - f0, stream_);
+    launches_ += launch_hog(g_, d_g_, b_, model_.sbin, f0, f1 - f0, stream_);
+  }
+  if (record_after) check_cuda(cudaEventRecord(record_after, stream_), "event");   // frames consumed
+  check_cuda(cudaGetLastError(), "pyramid/HOG launch");
+  feat_from_hog_ = true;
+  stage_ = 2;
+}
+
 void Engine::upload_and_pyramid(const uint8_t* frames, size_t row_stride, size_t frame_stride) {
   need(1, "upload_and_pyramid");
   if (!have_images_) throw StateError("upload_and_pyramid: batch was defined by pbd_set_levels");
   const size_t row = (size_t)g_.in_w * g_.in_c, fb = row * g_.in_h;
   if (row_stride == 0) row_stride = row;
   if (frame_stride == 0) frame_stride = row_stride * g_.in_h;
-  const int n = g_.n_frames;
-  if (timing || n < 8 || row_stride != row || frame_stride != fb) {       // per-stage timing wants separable stages
+  if (timing || g_.n_frames < 8 || row_stride != row || frame_stride != fb) {       // per-stage timing wants separable stages
     upload_frames(frames, row_stride, frame_stride);
     run_pyramid();
     return;
   }
-  ensure(d_frames_own_, cap_frames_, fb * n);
-  b_.frames = d_frames_own_;
-  if (!copy_stream_) {
+  ensure(d_frames_own_, cap_frames_, fb * g_.n_frames);
+  if (!main_ev_) {
     check_cuda(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
     for (auto& e : copy_ev_) check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     check_cuda(cudaEventCreateWithFlags(&main_ev_, cudaEventDisableTiming), "cudaEventCreate");
   }
-  // the copy stream must not overwrite frames still being read by work already queued on the main stream
   check_cuda(cudaEventRecord(main_ev_, stream_), "event");
-  check_cuda(cudaStreamWaitEvent(copy_stream_, main_ev_, 0), "wait");
-  const int nchunks = 4;
-  for (int c = 0; c < nchunks; ++c) {
-    const int f0 = (int)((long long)n * c / nchunks), f1 = (int)((long long)n * (c + 1) / nchunks);
-    if (f1 <= f0) continue;
-    check_cuda(cudaMemcpyAsync(d_frames_own_ + fb * f0, frames + fb * f0, fb * (f1 - f0), cudaMemcpyHostToDevice, copy_stream_), "H2D frames");
-    check_cuda(cudaEventRecord(copy_ev_[c], copy_stream_), "event");
-    check_cuda(cudaStreamWaitEvent(stream_, copy_ev_[c], 0), "wait");
-    launches_ += launch_pyramid(g_, d_g_, b_, d_xofs_, d_xalpha_, d_yofs_, d_ybeta_, f0, f1 - f0, stream_);
-    launches_ += launch_hog(g_, d_g_, b_, model_.sbin, f0, f1 - f0, stream_);
-  }
-  check_cuda(cudaGetLastError(), "pyramid/HOG launch");
-  feat_from_hog_ = true;
-  stage_ = 2;
+  chunked_upload_pyramid(frames, d_frames_own_, main_ev_, nullptr);
+}
+
+// Pipelined API.  Frames must be tightly packed (and pinned for the copy to be asynchronous) and stay untouched until the
+// ticket has been collected.  At most two batches are in flight: the ticket returned is the result slot (0/1).
+int Engine::submit(const uint8_t* frames, int n, int h, int w, int c) {
+  set_frames_geometry(n, h, w, c);
+  const int slot = cur_slot_ ^ 1;
+  if (slots_[slot].pending) throw StateError("submit: two batches are already in flight; collect a ticket first");
+  cur_slot_ = slot;
+  const size_t fb = (size_t)w * c * h;
+  frames_buf_ ^= 1;
+  uint8_t*& dst = frames_buf_ ? d_frames_alt_ : d_frames_own_;
+  size_t& cap = frames_buf_ ? cap_frames_alt_ : cap_frames_;
+  ensure(dst, cap, fb * n);
+  // this frame buffer was last read by the pyramid stage of the batch before the previous one
+  chunked_upload_pyramid(frames, dst, frames_free_ev_[frames_buf_], frames_free_ev_[frames_buf_]);
+  run_pdf();
+  run_dp_min();
+  run_argmin();
+  slots_[slot].pending = true;
+  return slot;
+}
+
+void Engine::collect_ticket(int ticket, CandidateSet& out) {
+  if (ticket < 0 || ticket > 1 || !slots_[ticket].pending) throw ArgError("collect_ticket: no batch in flight for this ticket");
+  ResultSlot& S = slots_[ticket];
+  if (!d2h_stream_) check_cuda(cudaStreamCreateWithFlags(&d2h_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+  check_cuda(cudaStreamWaitEvent(d2h_stream_, S.done, 0), "wait");
+  download_slot(S, d2h_stream_, out);
+  S.pending = false;
 }
 
 void Engine::use_device_frames(const uint8_t* d_frames) {
@@ -517,31 +570,41 @@ void Engine::run_dp_min() {
 void Engine::run_argmin() {
   need(4, "argmin");
   if (timing) { check_cuda(cudaEventRecord(ev_[5], stream_), "event"); ev_valid_[5] = true; }
-  ensure(d_hits_, cap_hits_, (size_t)max_candidates);
-  ensure(d_xym_, cap_xym_, (size_t)max_candidates * 3 * kMaxParts);
-  check_cuda(cudaMemsetAsync(d_nhits_, 0, sizeof(int), stream_), "memset nhits");
-  launches_ += launch_hits(g_, d_g_, b_, model_.ncomponents(), (float)thresh, d_hits_, d_nhits_, max_candidates, stream_);
+  ResultSlot& S = slots_[cur_slot_];
+  ensure_slot(S);
+  check_cuda(cudaMemsetAsync(S.d_nhits, 0, sizeof(int), stream_), "memset nhits");
+  launches_ += launch_hits(g_, d_g_, b_, model_.ncomponents(), (float)thresh, S.d_hits, S.d_nhits, S.max_candidates, stream_);
   BacktrackTables t{d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_};
-  launches_ += launch_backtrack(g_, d_g_, b_, t, model_.ncomponents(), ncm_, npm_, d_hits_, d_nhits_, max_candidates, backptr, max_parts_, d_xym_, stream_);
+  launches_ += launch_backtrack(g_, d_g_, b_, t, model_.ncomponents(), ncm_, npm_, S.d_hits, S.d_nhits, S.max_candidates, backptr, max_parts_,
+                                S.d_xym, stream_);
   check_cuda(cudaGetLastError(), "argmin launch");
+  S.scales.resize(g_.n_levels);
+  for (int l = 0; l < g_.n_levels; ++l) S.scales[l] = g_.lv[l].scale;
+  check_cuda(cudaEventRecord(S.done, stream_), "event");
   if (timing) { check_cuda(cudaEventRecord(ev_[6], stream_), "event"); ev_valid_[6] = true; }
   stage_ = 5;
 }
 
 void Engine::collect(CandidateSet& out) {
   need(5, "collect");
+  download_slot(slots_[cur_slot_], stream_, out);
+}
+
+// Downloads the hits of a slot on stream `st` (which must already be ordered after the slot's `done` event) and builds the
+// candidate set in the reference's order.
+void Engine::download_slot(ResultSlot& S, cudaStream_t st, CandidateSet& out) {
   int nh = 0;
-  check_cuda(cudaMemcpyAsync(&nh, d_nhits_, sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H nhits");
-  check_cuda(cudaStreamSynchronize(stream_), "sync");
-  if (nh > max_candidates)
-    throw StateError("candidate buffer overflow: " + std::to_string(nh) + " hits > max_candidates=" + std::to_string(max_candidates));
+  check_cuda(cudaMemcpyAsync(&nh, S.d_nhits, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H nhits");
+  check_cuda(cudaStreamSynchronize(st), "sync");
+  if (nh > S.max_candidates)
+    throw StateError("candidate buffer overflow: " + std::to_string(nh) + " hits > max_candidates=" + std::to_string(S.max_candidates));
   const int ps = max_parts_;
   h_hits_.resize(nh);
   h_xym_.resize((size_t)nh * 3 * ps);
   if (nh) {
-    check_cuda(cudaMemcpyAsync(h_hits_.data(), d_hits_, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, stream_), "D2H hits");
-    check_cuda(cudaMemcpyAsync(h_xym_.data(), d_xym_, h_xym_.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H parts");
-    check_cuda(cudaStreamSynchronize(stream_), "sync");
+    check_cuda(cudaMemcpyAsync(h_hits_.data(), S.d_hits, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st), "D2H hits");
+    check_cuda(cudaMemcpyAsync(h_xym_.data(), S.d_xym, h_xym_.size() * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H parts");
+    check_cuda(cudaStreamSynchronize(st), "sync");
   }
   // the reference's deterministic (single-threaded) order: frame, level, component, row-major hit
   std::vector<int> order(nh);
@@ -564,7 +627,7 @@ void Engine::collect(CandidateSet& out) {
     out.meta[(size_t)oi * 4] = H.frame; out.meta[(size_t)oi * 4 + 1] = H.level; out.meta[(size_t)oi * 4 + 2] = H.comp; out.meta[(size_t)oi * 4 + 3] = np;
     out.score[oi] = H.score;
     const int* xs = h_xym_.data() + (size_t)i * 3 * ps;
-    const float scale = g_.lv[H.level].scale;
+    const float scale = S.scales[H.level];
     for (int p = 0; p < np; ++p) {                  // reference src/DynamicProgram.cpp:238-244
       int* o = out.part(oi, p);
       const int x = xs[p], y = xs[ps + p], mix = xs[2 * ps + p];

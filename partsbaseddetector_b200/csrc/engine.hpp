@@ -68,7 +68,11 @@ class Engine {
   void run_pdf();          // IConvolutionEngine::pdf
   void run_dp_min();       // DynamicProgram::min
   void run_argmin();       // DynamicProgram::argmin (device part: hits + backtrack)
-  void collect(CandidateSet& out);   // syncs, downloads and orders the candidates
+  void collect(CandidateSet& out);
+  // pipelined API: submit() enqueues H2D (own copy stream, double-buffered frames) + all stages and returns a ticket (0/1);
+  // collect_ticket() waits for that batch only and downloads its candidates on a separate stream.
+  int submit(const uint8_t* frames, int n, int h, int w, int c);
+  void collect_ticket(int ticket, CandidateSet& out);   // syncs, downloads and orders the candidates
 
   // ---- accessors (sync) ----
   const Geometry& geom() const { return g_; }
@@ -89,12 +93,16 @@ class Engine {
   int device() const { return device_; }
 
  private:
+  struct ResultSlot;
   void check_cuda(cudaError_t e, const char* what) const;
   template <typename T> void ensure(T*& p, size_t& cap, size_t n);
   void alloc_batch();
   void build_tables();
   void build_batch_tables();
   void need(int stage, const char* who) const;
+  void ensure_slot(ResultSlot& S);
+  void download_slot(ResultSlot& S, cudaStream_t st, CandidateSet& out);
+  void chunked_upload_pyramid(const uint8_t* frames, uint8_t* d_dst, cudaEvent_t wait_before_copy, cudaEvent_t record_after);
 
   Model model_;
   int device_;
@@ -136,9 +144,23 @@ class Engine {
   PassMap *d_maps_rows_ = nullptr, *d_maps_cols_ = nullptr; size_t cap_maps_rows_ = 0, cap_maps_cols_ = 0;
   std::vector<int> wave_map_first_, wave_map_count_;
   // candidates
-  Hit* d_hits_ = nullptr; size_t cap_hits_ = 0;
-  int* d_nhits_ = nullptr;
-  int* d_xym_ = nullptr; size_t cap_xym_ = 0;
+  // Result slots: the synchronous API uses slot 0; the pipelined submit/collect API alternates between the two so that the
+  // candidates of batch i can be downloaded while batch i+1 is being computed.
+  struct ResultSlot {
+    Hit* d_hits = nullptr; size_t cap_hits = 0;
+    int* d_nhits = nullptr;
+    int* d_xym = nullptr; size_t cap_xym = 0;
+    cudaEvent_t done = nullptr;               // recorded after the backtrack of the batch that filled the slot
+    std::vector<float> scales;                // per-level scales of that batch (candidate rects)
+    int max_candidates = 0;
+    bool pending = false;
+  };
+  ResultSlot slots_[2];
+  int cur_slot_ = 0;
+  cudaStream_t d2h_stream_ = nullptr;
+  uint8_t* d_frames_alt_ = nullptr; size_t cap_frames_alt_ = 0;   // second frame buffer of the pipelined API
+  cudaEvent_t frames_free_ev_[2] = {};         // recorded when the pyramid stage has consumed frame buffer 0 / 1
+  int frames_buf_ = 0;
   int* d_scratch_i_ = nullptr; size_t cap_scratch_i_ = 0;
   std::vector<Hit> h_hits_;                    // host staging reused across batches
   std::vector<int> h_xym_;

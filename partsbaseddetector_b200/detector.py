@@ -322,6 +322,33 @@ class PartsBasedDetector:
         candidates.extend(res)                           # reference semantics: append to the caller's vector
         return candidates
 
+    # ---- pipelined (streaming) API: submit batch i+1 before collecting batch i ----
+    def submit(self, im):
+        """Enqueue H2D + all stages for a batch of frames without waiting; returns a ticket.  `im` must stay untouched (and
+        should be pinned memory) until collect_ticket(ticket)."""
+        a = self._frames(im)
+        n, h, w, c = a.shape
+        t = C.c_int()
+        _lib.check(_lib.lib().pbd_submit_batch_u8(self.handle, a.ctypes.data, n, h, w, c, C.byref(t)))
+        return t.value, a            # keep a reference to the frames alive with the ticket
+
+    def collect_ticket(self, ticket):
+        t = ticket[0] if isinstance(ticket, tuple) else ticket
+        out = C.c_void_p()
+        _lib.check(_lib.lib().pbd_collect_ticket(self.handle, t, C.byref(out)))
+        return _unpack_candidates(out)
+
+    def detect_stream(self, batches):
+        """Generator over an iterable of frame batches: yields each batch's CandidateList, keeping two batches in flight."""
+        prev = None
+        for b in batches:
+            cur = self.submit(b)
+            if prev is not None:
+                yield self.collect_ticket(prev)
+            prev = cur
+        if prev is not None:
+            yield self.collect_ticket(prev)
+
     def detect_device(self, dptr, n, h, w, c):
         out = C.c_void_p()
         _lib.check(_lib.lib().pbd_detect_batch_u8_device(self.handle, C.c_void_p(dptr), n, h, w, c, C.byref(out)))

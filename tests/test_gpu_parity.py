@@ -422,3 +422,25 @@ def test_large_batch_indexing():
         assert per_frame.get(f, []) == singles[f % 7][0], f
     for f in (0, 33, 69):
         assert np.array_equal(d.rootv(f, 0), singles[f % 7][1]) and np.array_equal(d.rootv(f, d.nscales() - 1), singles[f % 7][2])
+
+
+def test_pipelined_submit_collect_equals_detect():
+    """pbd_submit_batch_u8 / pbd_collect_ticket with two batches in flight give the same candidates as detect()."""
+    d = detector("Person_26parts")
+    batches = [np.ascontiguousarray(synth_frames(9, 144, 192, start=400 + 9 * i)) for i in range(5)]
+    d.set_option("thresh", 1e9)
+    d.detect(batches[0])
+    rv = np.concatenate([d.rootv(0, l).ravel() for l in range(d.nscales())])
+    d.set_option("thresh", float(np.sort(rv)[-25]))
+    key = lambda c: [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score())) for k in c]
+    ref = [key(d.detect(b)) for b in batches]
+    got = [key(c) for c in d.detect_stream(batches)]
+    assert got == ref and sum(map(len, ref)) > 0
+    t0 = d.submit(batches[0])
+    t1 = d.submit(batches[1])
+    with pytest.raises(PbdError):
+        d.submit(batches[2])                      # only two batches may be in flight
+    assert key(d.collect_ticket(t1)) == ref[1] and key(d.collect_ticket(t0)) == ref[0]
+    with pytest.raises(PbdError):
+        d.collect_ticket(t0)
+    assert key(d.detect(batches[3])) == ref[3]     # the synchronous API still works afterwards
