@@ -203,6 +203,20 @@ class PartsBasedDetector {
     check(pbd_detect_batch_u8(d_, first.data, n, first.rows, first.cols, first.channels, first.step, frame_stride, &c));
     append(c, candidates);
   }
+  // pipelined variant (pbd_submit_batch_u8 / pbd_collect_ticket): submit batch i+1 before collecting batch i; `first` must be
+  // tightly packed, should be pinned and must stay untouched until its ticket has been collected
+  int submitBatch(const Mat& first, int n) {
+    need();
+    int ticket = -1;
+    check(pbd_submit_batch_u8(d_, first.data, n, first.rows, first.cols, first.channels, &ticket));
+    return ticket;
+  }
+  void collectTicket(int ticket, vectorCandidate& candidates) {
+    need();
+    pbd_candidates* c = nullptr;
+    check(pbd_collect_ticket(d_, ticket, &c));
+    append(c, candidates);
+  }
   pbd_detector* handle() { need(); return d_; }
 
  private:
