@@ -444,3 +444,38 @@ def test_pipelined_submit_collect_equals_detect():
     with pytest.raises(PbdError):
         d.collect_ticket(t0)
     assert key(d.detect(batches[3])) == ref[3]     # the synchronous API still works afterwards
+
+
+@pytest.mark.parametrize("kind", ["zeros", "saturated", "ramp", "checker", "noise"])
+def test_degenerate_frames_end_to_end(kind):
+    """Flat / saturated / periodic frames give constant or exactly repeating score maps: every distance transform is full of
+    exact ties, the hardest case for reproducing the reference's break-point rounding.  Everything is compared bit for bit."""
+    h, w = 132, 180
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = {"zeros": np.zeros((h, w, 3), np.uint8),
+           "saturated": np.full((h, w, 3), 255, np.uint8),
+           "ramp": np.stack([(xx * 255 // (w - 1)).astype(np.uint8)] * 3, axis=-1),
+           "checker": np.stack([(((xx // 8 + yy // 8) % 2) * 200).astype(np.uint8)] * 3, axis=-1),
+           "noise": np.random.default_rng(9).integers(0, 256, (h, w, 3)).astype(np.uint8)}[kind]
+    img = np.ascontiguousarray(img)
+    name = "Person_26parts"
+    d, O = detector(name), oracle(name)
+    O.run(img, 1, 3)
+    rv = np.concatenate([O.rootv(l).ravel() for l in range(O.nlevels())])
+    thr = float(np.sort(np.unique(rv))[-min(5, np.unique(rv).size)]) - 1e-6     # a handful of distinct top scores (ties included)
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    d.set_option("thresh", thr)
+    d.set_option("max_candidates", 1 << 20)
+    cands = d.detect(img)
+    for l in range(O.nlevels()):
+        assert np.array_equal(d.rootv(0, l), O.rootv(l)) and np.array_equal(d.rooti(0, l), O.rooti(l)), l
+    for p, pm in ((1, 0), (13, 2), (25, 4)):
+        g, o = d.backptr(0, 0, 0, p, pm), O.backptr(0, 0, p, pm)
+        assert all(np.array_equal(a, b) for a, b in zip(g, o)), (p, pm)
+    oc = O.candidates()
+    assert len(cands) == len(oc) > 0
+    for a, b in zip(cands, oc):
+        assert a.level == b["level"] and np.array_equal(a.x, b["x"]) and np.array_equal(a.y, b["y"]) and np.array_equal(a.m, b["m"])
+        assert a.score() == b["score"]
+    d.set_option("max_candidates", 65536)
