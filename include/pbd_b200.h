@@ -86,7 +86,9 @@ void pbd_destroy(pbd_detector* d);
  *   "backptr"     0 (default): reference back-pointer composition (include/DistanceTransform.hpp:232-244),
  *                 1: true 2-D argmax composition
  *   "max_levels"  0 (default) = all pyramid levels, n = only the first n (finest) levels
- *   "max_candidates" capacity of the candidate buffer per batch (default 65536) */
+ *   "max_candidates" capacity of the candidate buffer per batch (default 65536)
+ *   "timing"      1: record per-stage CUDA events (pbd_stage_times_ms); disables the chunked H2D/pyramid overlap
+ * Environment defaults read at pbd_create: PBD_EXACT=0|1, PBD_BACKPTR=reference|exact, PBD_MAX_LEVELS=n. */
 int pbd_set_option(pbd_detector* d, const char* key, double value);
 int pbd_get_option(const pbd_detector* d, const char* key, double* value);
 

@@ -1,5 +1,6 @@
 // abi.cpp -- extern "C" boundary (include/pbd_b200.h).  Exceptions never cross it.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -143,6 +144,10 @@ int pbd_create(const pbd_model* m, int device, void* stream, pbd_detector** out)
     REQUIRE(m && out, "null argument");
     auto d = std::make_unique<pbd_detector>();
     d->e = std::make_unique<Engine>(m->m, device, (cudaStream_t)stream);
+    // process-wide defaults from the environment (SURVEY.md section 5 "config / flags"); pbd_set_option overrides them
+    if (const char* v = getenv("PBD_EXACT")) d->e->exact = atoi(v) != 0;
+    if (const char* v = getenv("PBD_BACKPTR")) d->e->backptr = (strcmp(v, "exact") == 0 || strcmp(v, "1") == 0) ? 1 : 0;
+    if (const char* v = getenv("PBD_MAX_LEVELS")) d->e->max_levels = std::max(0, atoi(v));
     *out = d.release();
   });
 }

@@ -479,3 +479,15 @@ def test_degenerate_frames_end_to_end(kind):
         assert a.level == b["level"] and np.array_equal(a.x, b["x"]) and np.array_equal(a.y, b["y"]) and np.array_equal(a.m, b["m"])
         assert a.score() == b["score"]
     d.set_option("max_candidates", 65536)
+
+
+def test_environment_defaults(monkeypatch):
+    monkeypatch.setenv("PBD_EXACT", "0")
+    monkeypatch.setenv("PBD_BACKPTR", "exact")
+    monkeypatch.setenv("PBD_MAX_LEVELS", "3")
+    d = PartsBasedDetector(device=0)
+    d.distributeModel(Model.load_bin(os.path.join(GOLDEN, "Willowcoffee_5parts.pbdm")))
+    assert (d.get_option("exact"), d.get_option("backptr"), d.get_option("max_levels")) == (0.0, 1.0, 3.0)
+    d.pyramid(synth_frame(1, 200, 260))
+    assert d.nscales() == 3
+    d.close()
