@@ -13,7 +13,8 @@
 // DESIGN.md): a CTA owns a TY x TX tile of cells of one level; the HOG tile plus halo is staged once into
 // shared memory, transposed from HWC to channel-planar so that a thread's P=4 adjacent cells are one
 // 128-bit load; filters are pre-packed on the host as [group of 8][channel][tap][8] and streamed through a
-// double-buffered cp.async stage, so a thread's 8 filter taps are two broadcast 128-bit loads.  Each
+// double-buffered TMA bulk-copy stage (cp.async.bulk + mbarrier, one 6.4 KB copy per filter group and channel chunk),
+// so a thread's 8 filter taps are two broadcast 128-bit loads.  Each
 // thread keeps 4 cells x 8 filters in registers: 64 FMUL+FADD (or 32..64 FFMA) per 6 shared-memory loads.
 #include "kernels.cuh"
 
@@ -27,12 +28,26 @@ constexpr int WF = 6;                // filter groups (of Q) processed per pass 
 constexpr int NT = POSW * WF * 32;   // threads per CTA (192)
 constexpr int CCH = 8;               // channels per weight stage
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: one elected lane moves a whole weight slab ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
 
 template <int KH, int KW, bool EXACT>
 __global__ void __launch_bounds__(NT, 2)
@@ -90,18 +105,24 @@ part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level
   // Weight slabs are private to a filter group: the POSW warps that share group `wf` stage and consume the slab
   // themselves and synchronise on their own named barrier, so the groups of a CTA never wait for each other.
   const int gtid = tid - wf * (POSW * 32);               // thread index inside the group (warps wf*POSW .. +POSW-1)
+  // The slab of (group, channel chunk) is one contiguous WSLAB*4-byte run of the packed bank: a single TMA bulk copy issued
+  // by the group's first lane, completion signalled on the group's mbarrier of that buffer.
+  __shared__ __align__(8) unsigned long long wbar[2][WF];
   auto stage_weights = [&](int pass, int chunk, int buf) {
+    if (gtid != 0) return;
     int gq = pass * WF + wf;
     if (gq >= ngroups) gq = ngroups - 1;                  // idle groups read a valid slab, results discarded
     const float* srcw = wbank + ((size_t)gq * 32 + chunk * CCH) * TAPS * Q;   // contiguous WSLAB floats
     float* dstw = sw + ((size_t)buf * WF + wf) * WSLAB;
-    for (int o = gtid; o < WSLAB / 4; o += POSW * 32) cp_async16(dstw + o * 4, srcw + o * 4);
-    cp_async_commit();
+    mbar_expect_tx(&wbar[buf][wf], WSLAB * 4);
+    tma_bulk_g2s(dstw, srcw, WSLAB * 4, &wbar[buf][wf]);
   };
   auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(wf + 1), "n"(POSW * 32) : "memory"); };
 
   constexpr int NCH = 32 / CCH;
-  __syncthreads();                                      // HOG tile staged
+  if (tid < 2 * WF) mbar_init(&wbar[tid / WF][tid % WF], 1);
+  mbar_fence_init();
+  __syncthreads();                                      // HOG tile staged, barriers initialised
   stage_weights(0, 0, 0);
   int it = 0;                                           // global stage counter over (pass, chunk)
   for (int pass = 0; pass < npass; ++pass) {
@@ -116,8 +137,8 @@ part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level
       // prefetch the next stage, then wait for the current one
       const int nchunk = chunk + 1 == NCH ? 0 : chunk + 1;
       const int npassi = chunk + 1 == NCH ? pass + 1 : pass;
-      if (npassi < npass) { stage_weights(npassi, nchunk, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-      group_sync();                                     // this group's slab is visible to its warps
+      if (npassi < npass) stage_weights(npassi, nchunk, buf ^ 1);
+      mbar_wait(&wbar[buf][wf], (it >> 1) & 1);         // this group's slab has landed (n-th use of the buffer: parity n & 1)
       const float* wsl = sw + ((size_t)buf * WF + wf) * WSLAB;
       const int ncl = (chunk == 32 / CCH - 1) ? nch_last : CCH;
 #pragma unroll 1
