@@ -424,17 +424,25 @@ int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int 
       R.in_buf = 0; R.in_off = R.out_off = R.ptr_off = (unsigned long long)i * h * w;
       R.w_sq = h_defw4[4 * i]; R.w_lin = h_defw4[4 * i + 1]; R.os = h_anchor_xy[2 * i];
       Cc = R; Cc.w_sq = h_defw4[4 * i + 2]; Cc.w_lin = h_defw4[4 * i + 3]; Cc.os = h_anchor_xy[2 * i + 1];
+      R.tab_len = dt_table_len(w); R.tab_bias = dt_table_bias(w, R.os);
+      Cc.tab_len = dt_table_len(h); Cc.tab_bias = dt_table_bias(h, Cc.os);
       maps[i] = R; maps[n_maps + i] = Cc;
     }
-    float* d_tmp = nullptr; uint16_t *d_ixr = nullptr, *d_iyr = nullptr; PassGeom* d_pg = nullptr; PassMap* d_maps = nullptr;
+    float* d_tmp = nullptr; uint16_t *d_ixr = nullptr, *d_iyr = nullptr; PassGeom* d_pg = nullptr; PassMap* d_maps = nullptr; double* d_etab = nullptr;
     cu(cudaMalloc(&d_pg, sizeof(pgs)), "cudaMalloc"); cu(cudaMalloc(&d_maps, maps.size() * sizeof(PassMap)), "cudaMalloc");
+    cu(cudaMalloc(&d_etab, (size_t)n_maps * (dt_table_len(w) + dt_table_len(h)) * sizeof(double)), "cudaMalloc");
+    for (int i = 0; i < n_maps; ++i) {
+      maps[i].etab = d_etab + (size_t)i * dt_table_len(w);
+      maps[n_maps + i].etab = d_etab + (size_t)n_maps * dt_table_len(w) + (size_t)i * dt_table_len(h);
+    }
     cu(cudaMalloc(&d_tmp, cells * sizeof(float)), "cudaMalloc"); cu(cudaMalloc(&d_ixr, cells * 2), "cudaMalloc"); cu(cudaMalloc(&d_iyr, cells * 2), "cudaMalloc");
     cu(cudaMemcpyAsync(d_pg, pgs, sizeof(pgs), cudaMemcpyHostToDevice, s), "H2D");
     cu(cudaMemcpyAsync(d_maps, maps.data(), maps.size() * sizeof(PassMap), cudaMemcpyHostToDevice, s), "H2D");
+    launch_dt_tables(d_maps, 2 * n_maps, s);
     launch_dt2d_standalone(d_in, n_maps, h, w, d_pg, d_maps, d_tmp, d_out, d_ix, d_iy, d_ixr, d_iyr, backptr_mode, s);
     cu(cudaGetLastError(), "dt2d launch");
     cu(cudaStreamSynchronize(s), "dt2d sync");
-    cudaFree(d_pg); cudaFree(d_maps); cudaFree(d_tmp); cudaFree(d_ixr); cudaFree(d_iyr);
+    cudaFree(d_pg); cudaFree(d_maps); cudaFree(d_etab); cudaFree(d_tmp); cudaFree(d_ixr); cudaFree(d_iyr);
   });
 }
 int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, float* out, int32_t* ix,

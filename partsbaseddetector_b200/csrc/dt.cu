@@ -43,40 +43,55 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 struct Quad {
   double a, b, a2;   // a2 = 2*a (exact), reference evaluates 2*a*(x1-x0) left to right
   double r1;         // correctly rounded 1/(2a): reciprocal of the divisor for adjacent samples (x1-x0 = 1)
+  const double* E;   // E[x] = a*x^2 + b*x (both products and the sum rounded as the reference does), x = pos - v
 };
-__device__ __forceinline__ Quad make_quad(float w_sq, float w_lin) {
+__device__ __forceinline__ Quad make_quad(const PassMap& M) {
   Quad f;
-  f.a = (double)(-w_sq);          // Quadratic(-w[0], -w[1]), src/DynamicProgram.cpp:126-127
-  f.b = (double)(-w_lin);
+  f.a = (double)(-M.w_sq);          // Quadratic(-w[0], -w[1]), src/DynamicProgram.cpp:126-127
+  f.b = (double)(-M.w_lin);
   f.a2 = __dmul_rn(2.0, f.a);
   f.r1 = __drcp_rn(f.a2);
+  f.E = M.etab + M.tab_bias;
   return f;
 }
-// Quadratic::operator()(x0,x1,y0,y1), include/DistanceTransform.hpp:98-100, result rounded to float as `T s = f(...)`
-__device__ __forceinline__ float isect(const Quad& f, int x0, int x1, double y0, double y1) {
-  const int d = x1 - x0;
-  if (d == 1) {
-    // adjacent samples (the common case): b*1 = b and a*(x1^2-x0^2) = a*(2*x1-1) are the reference's own values;
-    // the quotient num/(2a) is formed with a Markstein correction step from the precomputed reciprocal.  It is
-    // within 1 ulp(double) of the correctly rounded quotient, so its float rounding equals the reference's
-    // double-division-then-float unless it lies within 2 ulp of a float rounding boundary (probability ~2^-27):
-    // those cases, and anything not comfortably normal, take the exact division below.
-    const double num = __dadd_rn(__dsub_rn(__dsub_rn(y1, y0), f.b), __dmul_rn(f.a, (double)(2 * x1 - 1)));
-    const double q0 = __dmul_rn(num, f.r1);
-    const double q1 = __fma_rn(__fma_rn(-f.a2, q0, num), f.r1, q0);
-    const int lo = __double2loint(q1) & 0x1FFFFFFF;
-    const double aq = fabs(q1);
-    if (abs(lo - 0x10000000) > 2 && aq < 1e30 && aq > 1e-30) return (float)q1;
-    return (float)__ddiv_rn(num, f.a2);
-  }
-  const double dd = (double)d;
+// the rare exact quotient: kept out of line so that the common path does not carry the division's instructions
+__device__ __noinline__ float quotient_exact(double num, double den) { return (float)__ddiv_rn(num, den); }
+
+// Quadratic::operator()(x0,x1,y0,y1), include/DistanceTransform.hpp:98-100, result rounded to float as `T s = f(...)`,
+// for adjacent samples x1 = x0 + 1 (the first intersection of every step: the previous sample is always the top).
+// b*1 = b and a*(x1^2-x0^2) = a*(2*x1-1) are the reference's own values; the quotient num/(2a) is formed with a Markstein
+// correction step from the precomputed reciprocal.  It is within 1 ulp(double) of the correctly rounded quotient, so its
+// float rounding equals the reference's double-division-then-float unless it lies within 2 ulp of a float rounding
+// boundary (probability ~2^-27): those cases, and anything outside 2^-100..2^100, take the exact division.
+__device__ __forceinline__ float isect_adjacent(const Quad& f, int x1, double y0, double y1) {
+  const double num = __dadd_rn(__dsub_rn(__dsub_rn(y1, y0), f.b), __dmul_rn(f.a, (double)(2 * x1 - 1)));
+  const double q0 = __dmul_rn(num, f.r1);
+  const double q1 = __fma_rn(__fma_rn(-f.a2, q0, num), f.r1, q0);
+  const int lo = __double2loint(q1) & 0x1FFFFFFF;
+  const unsigned ex = ((unsigned)__double2hiint(q1) & 0x7ff00000u) - ((1023u - 100u) << 20);
+  if (ex <= (200u << 20) && abs(lo - 0x10000000) > 2) return (float)q1;
+  return quotient_exact(num, f.a2);
+}
+// the general case (after a pop x1 - x0 >= 2)
+__device__ __forceinline__ float isect_far(const Quad& f, int x0, int x1, double y0, double y1) {
+  const double dd = (double)(x1 - x0);
   const double t = __dsub_rn(__dsub_rn(y1, y0), __dmul_rn(f.b, dd));
   const double num = __dadd_rn(t, __dmul_rn(f.a, (double)(x1 * x1 - x0 * x0)));
   return (float)__ddiv_rn(num, __dmul_rn(f.a2, dd));
 }
-// Quadratic::operator()(x,y), :102-104
-__device__ __forceinline__ float envelope(const Quad& f, int x, float y) {
-  return (float)__dadd_rn(__dadd_rn(__dmul_rn(f.a, (double)(x * x)), __dmul_rn(f.b, (double)x)), (double)y);
+
+// base[idx] accesses with a 32-bit index: one IMAD.WIDE forms the address (the compiler otherwise re-derives the 64-bit
+// base from its kernel-parameter components at every store)
+__device__ __forceinline__ double ld_table(const double* base, int idx) {
+  double v;
+  asm("{ .reg .u64 a; mad.wide.s32 a, %2, 8, %1; ld.global.nc.f64 %0, [a]; }" : "=d"(v) : "l"(base), "r"(idx));
+  return v;
+}
+__device__ __forceinline__ void st_f32(float* base, unsigned idx, float v) {
+  asm volatile("{ .reg .u64 a; mad.wide.u32 a, %1, 4, %0; st.global.f32 [a], %2; }" ::"l"(base), "r"(idx), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_u16(unsigned short* base, unsigned idx, unsigned short v) {
+  asm volatile("{ .reg .u64 a; mad.wide.u32 a, %1, 2, %0; st.global.u16 [a], %2; }" ::"l"(base), "r"(idx), "h"(v) : "memory");
 }
 
 // per-warp shared-memory ring: [slot][lane]; vp = v | (v of the entry below << 16), 0xFFFF = none
@@ -98,15 +113,20 @@ struct Ring {
 // The ring holds the newest 8 stack entries for pops (5-8 % of the steps); zb/pb are the backing store of the whole
 // envelope as a linked list threaded through the sample index (zb[q] = break point of the parabola pushed at q,
 // pb[q] = the sample below it), written in lock step across lanes (coalesced) and read only by pops deeper than the ring.
-template <typename LoadY, typename Emit>
-__device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, Ring& R, int lane, float* zb, unsigned short* pb,
-                                                LoadY loady, Emit emit) {
-  const float pos_lo = (float)os0, pos_hi = (float)(os0 + N - 1);
-  auto emit_range = [&](float zlo, float zhi, int v, float y) {
-    // integer positions with zlo < pos <= zhi, clipped to [os0, os0+N-1]
-    const int lo = (zlo < pos_lo) ? os0 : (int)floorf(fminf(zlo, pos_hi + 1.f)) + 1;
-    const int hi = (zhi >= pos_hi) ? os0 + N - 1 : (int)floorf(fmaxf(zhi, pos_lo - 1.f));
-    for (int pos = lo; pos <= hi; ++pos) emit(pos - os0, envelope(f, pos - v, y), v);
+template <typename LoadY, typename Reload, typename Emit>
+__device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, unsigned stride, Ring& R, int lane, float* zb, unsigned short* pb,
+                                                LoadY loady, Reload reload, Emit emit) {
+  const int pos_last = os0 + N - 1;
+  auto emit_range = [&](float zlo, float zhi, int v, double yd) {
+    // integer positions with zlo < pos <= zhi, clipped to [os0, os0+N-1] (the float -> int conversions saturate, so the
+    // -inf / +inf break points of the bottom and the top need no special case); value = Quadratic::operator()(pos - v, y),
+    // :102-104, = (a x^2 + b x) + y with the parenthesis taken from the map's table
+    const int lo = max(min(__float2int_rd(zlo), pos_last) + 1, os0);
+    const int hi = min(__float2int_rd(zhi), pos_last);
+    int x = lo - v;
+    unsigned off = (unsigned)(lo - os0) * stride;
+#pragma unroll 1
+    for (int pos = lo; pos <= hi; ++pos, ++x, off += stride) emit(off, (float)__dadd_rn(ld_table(f.E, x), yd), v);
   };
   int k = 0, base = 0;                                            // stack depth of the top; lowest depth still valid in the ring
   int vt = 0, pt = 0xFFFF;
@@ -117,20 +137,20 @@ __device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, R
   for (int q = 1; q < N; ++q) {                                   // :160-170
     const float yqf = loady(q);
     const double yq = (double)yqf;
-    float s = isect(f, vt, q, yt, yq);
+    float s = isect_adjacent(f, q, yt, yq);                       // the top is sample q - 1
     while (s <= zt && k > 0) {
       --k;
       const int slot = k & (kRing - 1);
       if (k < base) {                                             // popped below the ring: reload from the backing store
         base = k;
         const int vv = pt;                                        // the entry below the one just popped
-        R.vp[slot][lane] = (unsigned)vv | ((unsigned)pb[vv] << 16); R.z[slot][lane] = zb[vv]; R.y[slot][lane] = loady(vv);
+        R.vp[slot][lane] = (unsigned)vv | ((unsigned)pb[vv] << 16); R.z[slot][lane] = zb[vv]; R.y[slot][lane] = reload(vv);
       }
       const unsigned vp = R.vp[slot][lane];
       vt = vp & 0xFFFF; pt = vp >> 16; ytf = R.y[slot][lane]; yt = (double)ytf; zt = R.z[slot][lane];
-      s = isect(f, vt, q, yt, yq);
+      s = isect_far(f, vt, q, yt, yq);
     }
-    emit_range(zt, s, vt, ytf);                                   // the top's positions up to the new break point
+    emit_range(zt, s, vt, yt);                                   // the top's positions up to the new break point
     ++k;
     base = max(base, k - (kRing - 1));                            // the slot of depth k - kRing is overwritten
     const int slot = k & (kRing - 1);
@@ -138,7 +158,7 @@ __device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, R
     zb[q] = s; pb[q] = (unsigned short)vt;
     pt = vt; vt = q; ytf = yqf; yt = yq; zt = s;
   }
-  emit_range(zt, INFINITY, vt, ytf);
+  emit_range(zt, INFINITY, vt, yt);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -173,13 +193,13 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
   const size_t cell_off = (size_t)pg->cell_off[l];
   const int t0 = w * 32;
   const bool active = t0 + lane < items;
-  const int t = active ? t0 + lane : t0;                          // inactive lanes shadow the warp's first item and discard results
+  const int t = active ? t0 + lane : t0;                          // inactive lanes shadow the warp's first item
   const int mi = t / nlines, line = t - mi * nlines;
   const PassMap M = maps[mi];
   const float* src = (M.in_buf ? inB + (size_t)frame * strideB : inA + (size_t)frame * strideA) + M.in_off + cell_off + (size_t)line * N;
   float* dst = out + (size_t)frame * stride_out + M.out_off + cell_off + line;
   unsigned short* dp = ptr + (size_t)frame * stride_ptr + M.ptr_off + cell_off + line;
-  const Quad f = make_quad(M.w_sq, M.w_lin);
+  const Quad f = make_quad(M);
   float zb[MAXN];
   unsigned short pb[MAXN];
   // Input staging: the warp's 32 lines are read kTileW samples at a time into a double-buffered shared-memory tile
@@ -196,21 +216,33 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
     }
     cp_async_commit();
   };
-  int q0 = -kTileW;
+  // sequential reads: q = 0, 1, 2, ... in lock step across the warp; a new tile becomes current every kTileW samples
   auto loady = [&](int q) -> float {
-    if (q >= q0 + kTileW && (q & (kTileW - 1)) == 0) {
+    if ((q & (kTileW - 1)) == 0) {
       if (q == 0) prefetch(0, 0);
       cp_async_wait_all();
       __syncwarp();
-      q0 = q;
       if (q + kTileW < N) prefetch(q + kTileW, ((q / kTileW) + 1) & 1);
     }
-    if (q >= q0) return tiles[wib][(q / kTileW) & 1][lane][q - q0];
-    return __ldg(src + q);
+    return tiles[wib][(q / kTileW) & 1][lane][q & (kTileW - 1)];
   };
-  envelope_stream(N, f, M.os, rings[wib], lane, zb, pb, loady, [&](int i, float val, int v) {
-    if (active) { dst[(size_t)i * nlines] = val; dp[(size_t)i * nlines] = (unsigned short)v; }
+  // deep-pop reloads of older samples: global memory (the tile that held them may already be refilled)
+  auto reload = [&](int v) -> float { return __ldg(src + v); };
+  // inactive lanes recompute the warp's first item and store the same values to the same addresses as lane 0
+  asm volatile("" : "+l"(dst), "+l"(dp));                        // keep both bases as materialised 64-bit registers
+  envelope_stream(N, f, M.os, (unsigned)nlines, rings[wib], lane, zb, pb, loady, reload, [&](unsigned off, float val, int v) {
+    st_f32(dst, off, val); st_u16(dp, off, (unsigned short)v);
   });
+}
+
+// E[j] = a x^2 + b x for x = j - tab_bias, j in [0, tab_len): the position-independent part of Quadratic::operator()(x, y)
+__global__ void __launch_bounds__(128) dt_build_tables(const PassMap* __restrict__ maps) {
+  const PassMap M = maps[blockIdx.x];
+  const double a = (double)(-M.w_sq), b = (double)(-M.w_lin);
+  for (int j = threadIdx.x; j < M.tab_len; j += blockDim.x) {
+    const int x = j - M.tab_bias;
+    M.etab[j] = __dadd_rn(__dmul_rn(a, (double)(x * x)), __dmul_rn(b, (double)x));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -345,6 +377,12 @@ int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
   dim3 gm((g.cells_total + 255) / 256, njobs, g.n_frames);
   mix_max<<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
   return 3;
+}
+
+int launch_dt_tables(const PassMap* d_maps, int nmaps, cudaStream_t s) {
+  if (nmaps <= 0) return 0;
+  dt_build_tables<<<nmaps, 128, 0, s>>>(d_maps);
+  return 1;
 }
 
 int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const RootJob* d_roots, int ncomp, int nfilters, int nwork,

@@ -85,7 +85,7 @@ Engine::~Engine() {
   void* ptrs[] = {d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
-                  d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, b_.val, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
+                  d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
                   slots_[1].d_hits, slots_[1].d_nhits, slots_[1].d_xym};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (ResultSlot& S : slots_) if (S.done) cudaEventDestroy(S.done);
@@ -387,15 +387,25 @@ void Engine::build_batch_tables() {
         R.w_sq = J.w[mm][0]; R.w_lin = J.w[mm][1]; R.os = J.ax[mm];
         C.in_buf = 0; C.in_off = R.out_off; C.out_off = R.out_off; C.ptr_off = R.ptr_off;
         C.w_sq = J.w[mm][2]; C.w_lin = J.w[mm][3]; C.os = J.ay[mm];
+        R.tab_len = dt_table_len(max_ow_); R.tab_bias = dt_table_bias(max_ow_, R.os);
+        C.tab_len = dt_table_len(max_oh_); C.tab_bias = dt_table_bias(max_oh_, C.os);
         mr.push_back(R); mc.push_back(C);
       }
     }
     wave_map_count_[wv] = (int)mr.size() - wave_map_first_[wv];
   }
   ensure(d_maps_rows_, cap_maps_rows_, mr.size()); ensure(d_maps_cols_, cap_maps_cols_, mc.size());
+  ensure(d_etab_, cap_etab_, mr.size() * (size_t)(dt_table_len(max_ow_) + dt_table_len(max_oh_)));
+  for (size_t i = 0; i < mr.size(); ++i) {
+    mr[i].etab = d_etab_ + i * (size_t)dt_table_len(max_ow_);
+    mc[i].etab = d_etab_ + mr.size() * (size_t)dt_table_len(max_ow_) + i * (size_t)dt_table_len(max_oh_);
+  }
   if (!mr.empty()) {
     check_cuda(cudaMemcpyAsync(d_maps_rows_, mr.data(), mr.size() * sizeof(PassMap), cudaMemcpyHostToDevice, stream_), "upload pass maps");
     check_cuda(cudaMemcpyAsync(d_maps_cols_, mc.data(), mc.size() * sizeof(PassMap), cudaMemcpyHostToDevice, stream_), "upload pass maps");
+    launch_dt_tables(d_maps_rows_, (int)mr.size(), stream_);
+    launch_dt_tables(d_maps_cols_, (int)mc.size(), stream_);
+    check_cuda(cudaGetLastError(), "DT table launch");
   }
   check_cuda(cudaStreamSynchronize(stream_), "sync batch tables");
 }

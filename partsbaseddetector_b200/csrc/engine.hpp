@@ -142,6 +142,7 @@ class Engine {
   PassGeom pg_rows_{}, pg_cols_{};
   PassGeom* d_pg_ = nullptr;                   // [rows, cols]
   PassMap *d_maps_rows_ = nullptr, *d_maps_cols_ = nullptr; size_t cap_maps_rows_ = 0, cap_maps_cols_ = 0;
+  double* d_etab_ = nullptr; size_t cap_etab_ = 0;   // per-map parabola tables of both passes
   std::vector<int> wave_map_first_, wave_map_count_;
   // candidates
   // Result slots: the synchronous API uses slot 0; the pipelined submit/collect API alternates between the two so that the

@@ -123,7 +123,15 @@ struct PassMap {
   int in_buf;                  // 0: buffer A, 1: buffer B (rows pass: A = responses, B = working scores)
   float w_sq, w_lin;           // deformation weights of this direction
   int os;                      // anchor of this direction
+  // device table of the position-independent part of the parabola, etab[x + tab_bias] = a x^2 + b x for every
+  // x = pos - v a line of up to (tab_len + 1) / 2 samples can produce (filled by launch_dt_tables)
+  double* etab;
+  int tab_bias, tab_len;
 };
+// doubles a pass over lines of at most maxn samples needs per map, and the bias that goes with anchor `os`
+inline int dt_table_len(int maxn) { return 2 * maxn - 1; }
+inline int dt_table_bias(int maxn, int os) { return maxn - 1 - os; }
+int launch_dt_tables(const PassMap* d_maps, int nmaps, cudaStream_t s);
 int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
