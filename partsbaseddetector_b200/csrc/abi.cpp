@@ -145,7 +145,12 @@ int pbd_create(const pbd_model* m, int device, void* stream, pbd_detector** out)
     auto d = std::make_unique<pbd_detector>();
     d->e = std::make_unique<Engine>(m->m, device, (cudaStream_t)stream);
     // process-wide defaults from the environment (SURVEY.md section 5 "config / flags"); pbd_set_option overrides them
-    if (const char* v = getenv("PBD_EXACT")) d->e->exact = atoi(v) != 0;
+    if (const char* v = getenv("PBD_EXACT")) d->e->resp_mode = atoi(v) != 0 ? 0 : 1;
+    if (const char* v = getenv("PBD_RESPONSE_MODE")) {
+      if (!strcmp(v, "exact") || !strcmp(v, "0")) d->e->resp_mode = 0;
+      else if (!strcmp(v, "ffma") || !strcmp(v, "1")) d->e->resp_mode = 1;
+      else if (!strcmp(v, "tensor") || !strcmp(v, "2")) d->e->resp_mode = 2;
+    }
     if (const char* v = getenv("PBD_BACKPTR")) d->e->backptr = (strcmp(v, "exact") == 0 || strcmp(v, "1") == 0) ? 1 : 0;
     if (const char* v = getenv("PBD_MAX_LEVELS")) d->e->max_levels = std::max(0, atoi(v));
     *out = d.release();
@@ -159,7 +164,9 @@ int pbd_set_option(pbd_detector* d, const char* key, double value) {
     Engine& e = *d->e;
     const std::string k(key);
     if (k == "thresh") e.thresh = value;
-    else if (k == "exact") e.exact = value != 0;
+    else if (k == "exact") e.resp_mode = value != 0 ? 0 : 1;
+    else if (k == "response_mode") { REQUIRE(value == 0 || value == 1 || value == 2, "response_mode must be 0 (exact), 1 (ffma) or 2 (tensor)"); e.resp_mode = (int)value; }
+    else if (k == "tc_taps_per_partial") { REQUIRE(value >= 0 && value <= 1024, "tc_taps_per_partial out of range"); e.tc_taps_per_partial = (int)value; }
     else if (k == "backptr") { REQUIRE(value == 0 || value == 1, "backptr must be 0 or 1"); e.backptr = (int)value; }
     else if (k == "max_levels") { REQUIRE(value >= 0, "max_levels must be >= 0"); e.max_levels = (int)value; }
     else if (k == "max_candidates") { REQUIRE(value >= 1 && value <= (1 << 24), "max_candidates out of range"); e.max_candidates = (int)value; }
@@ -173,7 +180,9 @@ int pbd_get_option(const pbd_detector* d, const char* key, double* value) {
     const Engine& e = *d->e;
     const std::string k(key);
     if (k == "thresh") *value = e.thresh;
-    else if (k == "exact") *value = e.exact;
+    else if (k == "exact") *value = e.resp_mode == 0;
+    else if (k == "response_mode") *value = e.resp_mode;
+    else if (k == "tc_taps_per_partial") *value = e.tc_taps_per_partial;
     else if (k == "backptr") *value = e.backptr;
     else if (k == "max_levels") *value = e.max_levels;
     else if (k == "max_candidates") *value = e.max_candidates;

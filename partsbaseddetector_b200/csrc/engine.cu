@@ -68,6 +68,7 @@ Engine::Engine(const Model& m, int device, cudaStream_t stream) : thresh((double
   if (e != cudaSuccess || ndev <= 0) throw CudaError(std::string("no CUDA device available: ") + cudaGetErrorString(e));
   if (device < 0 || device >= ndev) throw ArgError("device index out of range");
   check_cuda(cudaSetDevice(device), "cudaSetDevice");
+  check_cuda(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
   build_tables();
   check_cuda(cudaMalloc(&d_g_, sizeof(Geometry)), "cudaMalloc geometry");
   for (ResultSlot& S : slots_) {
@@ -82,7 +83,7 @@ Engine::Engine(const Model& m, int device, cudaStream_t stream) : thresh((double
 Engine::~Engine() {
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
-  void* ptrs[] = {d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
+  void* ptrs[] = {d_wtc_, d_fhi_, d_flo_, d_tc_levels_, d_tc_tiles_, d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
                   d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
@@ -139,6 +140,15 @@ void Engine::build_tables() {
     check_cuda(cudaMemcpy(d_wpacked_, wp.data(), wp.size() * sizeof(float), cudaMemcpyHostToDevice), "upload packed filters");
     dev_bytes_ += wp.size() * sizeof(float);
     fb_.w = d_wpacked_;
+  }
+  if (response_tc_supported(fb_)) {   // tf32 hi/lo slabs of the tensor-core path
+    std::vector<std::vector<float>> ff(nf);
+    for (int i = 0; i < nf; ++i) ff[i].assign(m.filters[i].begin(), m.filters[i].end());
+    std::vector<float> wt;
+    response_tc_pack_weights(ff, fb_.kh * fb_.kw, wt);
+    check_cuda(cudaMalloc(&d_wtc_, wt.size() * sizeof(float)), "cudaMalloc tensor filters");
+    check_cuda(cudaMemcpy(d_wtc_, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice), "upload tensor filters");
+    dev_bytes_ += wt.size() * sizeof(float);
   }
   // ---- DP slots ----
   const int ncomp = m.ncomponents();
@@ -343,6 +353,7 @@ void Engine::set_levels_manual(int n, int nlevels, const int32_t* ohow, const fl
 
 void Engine::build_batch_tables() {
   const Geometry& g = g_;
+  ++geom_serial_;
   max_ow_ = max_oh_ = 0;
   for (int l = 0; l < g.n_levels; ++l) { max_ow_ = std::max(max_ow_, g.lv[l].ow); max_oh_ = std::max(max_oh_, g.lv[l].oh); }
   if (max_ow_ > kMaxDim || max_oh_ > kMaxDim) throw UnsupportedError("pyramid level larger than 1024 cells in one dimension");
@@ -553,10 +564,37 @@ void Engine::run_pyramid() {
   stage_ = 2;
 }
 
+// Strip layout, work list and border cells of the tensor-core path for the current batch geometry.
+void Engine::ensure_tc() {
+  std::vector<TcLevel> lv;
+  std::vector<TcTile> su;
+  long long slack = 0;
+  const long long frame_rows = response_tc_plan(g_, fb_.kh, fb_.kw, lv, su, &slack);
+  const size_t rows = (size_t)frame_rows * g_.n_frames + (size_t)slack;
+  const bool realloc = rows * 32 > cap_fhi_ || !d_fhi_;
+  if (tc_serial_ == geom_serial_ && !realloc) return;
+  ensure(d_fhi_, cap_fhi_, rows * 32); ensure(d_flo_, cap_flo_, rows * 32);
+  ensure(d_tc_levels_, cap_tc_levels_, lv.size()); ensure(d_tc_tiles_, cap_tc_tiles_, std::max<size_t>(su.size(), 1));
+  check_cuda(cudaMemcpyAsync(d_tc_levels_, lv.data(), lv.size() * sizeof(TcLevel), cudaMemcpyHostToDevice, stream_), "upload strip levels");
+  if (!su.empty()) check_cuda(cudaMemcpyAsync(d_tc_tiles_, su.data(), su.size() * sizeof(TcTile), cudaMemcpyHostToDevice, stream_), "upload work list");
+  launches_ += launch_tc_border_init(d_fhi_, d_flo_, (long long)(cap_fhi_ / 32), stream_);
+  check_cuda(cudaStreamSynchronize(stream_), "sync strip tables");       // host vectors go out of scope
+  tc_ntiles_ = (int)su.size(); tc_frame_rows_ = frame_rows; tc_serial_ = geom_serial_;
+}
+
 void Engine::run_pdf() {
   need(2, "pdf");
+  if (resp_mode == 2 && response_tc_supported(fb_)) {
+    ensure_tc();
+    if (timing) { check_cuda(cudaEventRecord(ev_[3], stream_), "event"); ev_valid_[3] = true; }
+    launches_ += launch_feat_split(g_, d_g_, d_tc_levels_, b_.feat, d_fhi_, d_flo_, tc_frame_rows_, stream_);
+    launches_ += launch_response_tc(g_, b_, fb_, d_fhi_, d_flo_, d_wtc_, d_tc_levels_, d_tc_tiles_, tc_ntiles_, tc_frame_rows_, num_sms_, tc_taps_per_partial, stream_);
+    check_cuda(cudaGetLastError(), "tensor response launch");
+    stage_ = 3;
+    return;
+  }
   if (timing) { check_cuda(cudaEventRecord(ev_[3], stream_), "event"); ev_valid_[3] = true; }
-  launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles_, exact, feat_from_hog_ ? 1 : 0, stream_);
+  launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles_, resp_mode == 0 ? 1 : 0, feat_from_hog_ ? 1 : 0, stream_);
   check_cuda(cudaGetLastError(), "response launch");
   stage_ = 3;
 }

@@ -54,7 +54,9 @@ class Engine {
 
   // options
   double thresh;
-  int exact = 1, backptr = 0, max_levels = 0, max_candidates = 65536, timing = 0;
+  // resp_mode: 0 exact (separately rounded multiply/add in the reference's order, bit-identical scores), 1 fused multiply-add,
+  // 2 tensor cores (tf32x3 split products, fp32 accumulate; falls back to 1 for models the tensor kernel does not cover)
+  int resp_mode = 0, tc_taps_per_partial = 0, backptr = 0, max_levels = 0, max_candidates = 65536, timing = 0;
 
   // ---- batch set-up ----
   void set_frames_geometry(int n, int h, int w, int c);                 // pyramid geometry of HOGFeatures::pyramid
@@ -101,6 +103,7 @@ class Engine {
   void build_batch_tables();
   void need(int stage, const char* who) const;
   void ensure_slot(ResultSlot& S);
+  void ensure_tc();
   void download_slot(ResultSlot& S, cudaStream_t st, CandidateSet& out);
   void chunked_upload_pyramid(const uint8_t* frames, uint8_t* d_dst, cudaEvent_t wait_before_copy, cudaEvent_t record_after);
 
@@ -114,6 +117,14 @@ class Engine {
   FilterBank fb_{};
   float* d_wpacked_ = nullptr;
   float* d_wgeneric_ = nullptr;
+  // tensor-core response path: packed tf32 hi/lo weight slabs, padded strip copies of the HOG cells, work list
+  float* d_wtc_ = nullptr;
+  float *d_fhi_ = nullptr, *d_flo_ = nullptr; size_t cap_fhi_ = 0, cap_flo_ = 0;
+  TcLevel* d_tc_levels_ = nullptr; size_t cap_tc_levels_ = 0;
+  TcTile* d_tc_tiles_ = nullptr; size_t cap_tc_tiles_ = 0;
+  int tc_ntiles_ = 0; long long tc_frame_rows_ = 0;
+  long long geom_serial_ = 0, tc_serial_ = -1;
+  int num_sms_ = 0;
   int *d_foff_ = nullptr, *d_fkh_ = nullptr, *d_fkw_ = nullptr;
   std::vector<PartJob> jobs_;                 // ordered by wave
   std::vector<int> wave_first_, wave_count_, wave_maxmix_;

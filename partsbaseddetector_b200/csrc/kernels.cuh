@@ -110,6 +110,22 @@ bool response_has_fast_path(const FilterBank& fb);
 int launch_response_tiles(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const FilterBank& fb, const int* d_tile_level,
                           const int* d_tile_first, int ntiles, int exact, int trunc_zero, cudaStream_t s);
 
+// ---- tensor-core response path (response_tc.cu): padded strip layout of the HOG cells + work list ----
+struct TcLevel { int R, Wp, ow, oh, cell_off; };   // R: strip row of real cell (0,0); Wp: strip rows per image row (ow + ax)
+struct TcTile { int level, q0; };                  // work item: 128 consecutive strip rows starting at q0
+}  // namespace pbd
+#include <vector>
+namespace pbd {
+bool response_tc_supported(const FilterBank& fb);
+int response_tc_np(int nfilters);
+void response_tc_pack_weights(const std::vector<std::vector<float>>& filters, int taps, std::vector<float>& out);
+long long response_tc_plan(const Geometry& g, int kh, int kw, std::vector<TcLevel>& levels, std::vector<TcTile>& tiles, long long* slack_rows);
+int launch_feat_split(const Geometry& g, const Geometry* d_g, const TcLevel* d_levels, const float* feat, float* fhi, float* flo,
+                      long long frame_rows, cudaStream_t s);
+int launch_tc_border_init(float* fhi, float* flo, long long rows, cudaStream_t s);
+int launch_response_tc(const Geometry& g, const DeviceBuffers& b, const FilterBank& fb, const float* fhi, const float* flo, const float* wpk,
+                       const TcLevel* d_levels, const TcTile* d_tiles, int n_tiles, long long frame_rows, int num_sms, int taps_per_partial, cudaStream_t s);
+
 // Geometry of one separable-transform pass: per level the number of lines, their length and the map offset.
 struct PassGeom {
   int n_levels;

@@ -1,0 +1,380 @@
+// response_tc.cu -- SpatialConvolutionEngine::pdf (reference src/SpatialConvolutionEngine.cpp:70-124) on the 5th-generation
+// tensor cores: response mode 2 ("tf32x3").
+//
+// The stage is the implicit GEMM  resp[cell][f] = sum_{tap, c} F[cell + tap][c] * w_f[tap][c]   (M = cells, N = filters,
+// K = kh*kw*32 = 800 for the person model).  Every fp32 operand is split as v = hi + lo with hi = tf32(v) and
+// lo = tf32(v - hi) and the three products hi*hi + lo*hi + hi*lo are formed by tcgen05.mma.kind::tf32 with fp32 accumulators
+// in tensor memory (the dropped lo*lo term is 2^-22 of a product).  The tensor core's accumulation TRUNCATES (rounds toward
+// zero at every MMA: measured -50 ulp on a 300-MMA chain), so the chains are kept short: the hi*hi products are summed on
+// the tensor core over `taps_per_partial` taps only (default one filter row) into ping-pong partial accumulators that the
+// epilogue warps add up in fp32 round-to-nearest registers, and the small lo terms go to an accumulator of their own
+// (2^-11 of the score, so its truncation is invisible).  Scores then agree with the reference to a few ulp (~3e-7).  The
+// mode is NOT bit-identical to the reference's separately rounded multiply/add chain -- that is response mode 0
+// (response.cu) -- and is held to the north-star tolerance (root scores 1e-4 relative, integer outputs identical) by the
+// parity tests.
+//
+// Layout.  feat_split writes the HOG cells of a level into a padded, flattened strip of 128-byte rows (one row = the 32
+// channels of one cell): real cell (y, x) of level l sits at row R_l + y*Wp + x, Wp = ow + ax, so that consecutive image
+// rows are separated by ax border cells (value 0, channel 31 = 1: the BORDER_CONSTANT engines of
+// src/SpatialConvolutionEngine.cpp:147-156) and ay / kh-1-ay border rows lie above / below.  In this layout the cells a tap
+// (ky, kx) needs for 128 CONSECUTIVE output rows are again 128 consecutive rows, shifted by (ky-ay)*Wp + (kx-ax).  The
+// rows are stored pre-swizzled (16-byte chunk c of row P at chunk c ^ (P & 7)) so that a plain 1-D TMA bulk copy
+// (cp.async.bulk, no tensor map) of an 8-row aligned run lands in shared memory in exactly the K-major SWIZZLE_128B
+// layout tcgen05.mma reads, and the kx shift is a descriptor START-ADDRESS offset of kx rows into the same staged strip
+// (the hardware swizzle is a function of the absolute shared-memory address: verified by tools/umma_probe.cu).
+//
+// Kernel (persistent, one CTA per SM, 8 warps; work item = one tile of 128 strip rows): warp 0 streams the A strips (per
+// filter row ky: 144 rows x {hi, lo}, double buffered), warp 1 streams the per-tap weight slabs ({hi, lo} x NP filters x
+// 128 B, 4 stages), one lane of warp 2 issues the MMAs (M = 128, N = NP, K = 8: 12 per tap), warps 4-7 read finished
+// partial accumulators (tcgen05.ld), sum them and store the planar response maps while the next partial / tile is being
+// multiplied.  All hand-offs are mbarriers (TMA complete_tx / tcgen05.commit / epilogue arrivals).
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace pbd {
+namespace {
+
+constexpr int TM = 128;                       // output rows (cells) per tile = UMMA M
+constexpr int STRIP_ROWS = 144;               // 128 + 7 (8-row alignment of the copy) + kw-1 <= 9
+constexpr int STRIP_BYTES = STRIP_ROWS * 128;
+constexpr int A_BUFS = 2, B_STAGES = 4;
+constexpr int NP_MAX = 160;                   // 3 accumulators of NP columns must fit the 512 TMEM columns
+constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
+  unsigned done = 0;
+  long long spins = 0;
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1ll << 27)) asm volatile("trap;\n");     // a broken hand-off must fail loudly, not hang the device
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, unsigned bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B operand descriptor: 128-byte rows, 8-row groups 1024 B apart; `saddr` may start at any row
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// ---- HOG cells [n][cells][32] (HWC) -> padded, pre-swizzled hi / lo strips ----
+__global__ void __launch_bounds__(256)
+feat_split(const Geometry* __restrict__ g, const TcLevel* __restrict__ lv, const float* __restrict__ feat, float* __restrict__ fhi,
+           float* __restrict__ flo, long long frame_rows) {
+  const int l = blockIdx.y, frame = blockIdx.z;
+  const LevelDesc& L = g->lv[l];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;        // (cell, chunk)
+  const int cell = i >> 3, c = i & 7;
+  if (cell >= L.ow * L.oh) return;
+  const int y = cell / L.ow, x = cell - y * L.ow;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)frame * g->cells_total + L.cell_off + cell) * 32) + c);
+  const long long P = (long long)frame * frame_rows + lv[l].R + (long long)y * lv[l].Wp + x;
+  float4 h, o;
+  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+  o.x = tf32_rna(v.x - h.x); o.y = tf32_rna(v.y - h.y); o.z = tf32_rna(v.z - h.z); o.w = tf32_rna(v.w - h.w);
+  const size_t off = (size_t)P * 32 + ((c ^ (int)(P & 7)) << 2);
+  *reinterpret_cast<float4*>(fhi + off) = h;
+  *reinterpret_cast<float4*>(flo + off) = o;
+}
+
+// every row that is not a real cell is a border cell: channels 0..30 = 0, channel 31 (chunk 7, word 3) = 1
+__global__ void __launch_bounds__(256) tc_border_init(float* __restrict__ fhi, long long rows) {
+  const long long P = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= rows) return;
+  fhi[(size_t)P * 32 + ((7 ^ (int)(P & 7)) << 2) + 3] = 1.f;
+}
+
+struct TcParams {
+  const float* fhi;
+  const float* flo;
+  const float* wpk;            // [taps][2][NP][32] pre-swizzled weight slabs
+  float* resp;
+  const TcLevel* levels;
+  const TcTile* tiles;
+  int n_tiles, n_frames;
+  long long frame_rows;
+  int cells_total, nfilters, NP, kh, kw;
+  int taps_per_partial;        // hi*hi products are summed on the tensor core over this many taps, then in fp32 RN registers
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int NP = p.NP;
+  const uint32_t slab_bytes = (uint32_t)NP * 128u;             // one part (hi or lo) of one tap
+  // A: [A_BUFS][2 parts][STRIP_BYTES], B: [B_STAGES][2 parts][slab_bytes]
+  const uint32_t sA = sbase, sB = sbase + (uint32_t)A_BUFS * 2u * STRIP_BYTES;
+  __shared__ __align__(8) unsigned long long bars[2 * A_BUFS + 2 * B_STAGES + 6];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t fullA = smem_u32(&bars[0]), emptyA = fullA + 8 * A_BUFS, fullB = emptyA + 8 * A_BUFS, emptyB = fullB + 8 * B_STAGES;
+  const uint32_t hFull = emptyB + 8 * B_STAGES, hEmpty = hFull + 16, cFull = hEmpty + 16, cEmpty = cFull + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2 * A_BUFS + 2 * B_STAGES; ++i) mbar_init(fullA + 8 * i, 1);
+    mbar_init(hFull, 1); mbar_init(hFull + 8, 1); mbar_init(hEmpty, 4); mbar_init(hEmpty + 8, 4);
+    mbar_init(cFull, 1); mbar_init(cEmpty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 3) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  const int kh = p.kh, kw = p.kw, ay = kh / 2, ax = kw / 2;   // anchor = centre, include/filterengine.hpp:310-318
+  const int taps = kh * kw, G = p.taps_per_partial;
+  const int total = p.n_tiles * p.n_frames;
+
+  if (warp == 0) {
+    // ===== A producer: per tile and filter row ky, one 144-row strip per part =====
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int frame = w / p.n_tiles;
+        const TcTile S = p.tiles[w - frame * p.n_tiles];
+        const int Wp = p.levels[S.level].Wp;
+        for (int ky = 0; ky < kh; ++ky, ++it) {
+          const int buf = it % A_BUFS;
+          mbar_wait(emptyA + 8 * buf, ((it / A_BUFS) & 1) ^ 1);
+          mbar_expect_tx(fullA + 8 * buf, 2u * STRIP_BYTES);
+          const long long pstart = (long long)S.q0 + (long long)(ky - ay) * Wp - ax;
+          const long long pa = (long long)frame * p.frame_rows + (pstart & ~7ll);
+          const uint32_t dst = sA + (uint32_t)buf * 2u * STRIP_BYTES;
+          bulk_g2s(dst, p.fhi + (size_t)pa * 32, STRIP_BYTES, fullA + 8 * buf);
+          bulk_g2s(dst + STRIP_BYTES, p.flo + (size_t)pa * 32, STRIP_BYTES, fullA + 8 * buf);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== B producer: one {hi, lo} weight slab per tap =====
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int tap = 0; tap < taps; ++tap, ++it) {
+          const int st = it % B_STAGES;
+          mbar_wait(emptyB + 8 * st, ((it / B_STAGES) & 1) ^ 1);
+          mbar_expect_tx(fullB + 8 * st, 2u * slab_bytes);
+          bulk_g2s(sB + (uint32_t)st * 2u * slab_bytes, p.wpk + (size_t)tap * 2 * NP * 32, 2u * slab_bytes, fullB + 8 * st);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== MMA issuer.  TMEM: columns [0,NP) and [NP,2NP) = ping-pong partial sums of hi*hi over G taps, [2NP,3NP) = the
+    // small lo*hi + hi*lo correction of the whole tile.  Short chains keep the tensor core's truncating accumulation
+    // (round toward zero at every step) below one ulp of the final score; the epilogue adds the partials in fp32 RN. =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      int itA = 0, itB = 0, hcount = 0, tcount = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
+        const int frame = w / p.n_tiles;
+        const TcTile S = p.tiles[w - frame * p.n_tiles];
+        const int Wp = p.levels[S.level].Wp;
+        const uint32_t dC = tmem + (uint32_t)(2 * NP);
+        for (int ky = 0; ky < kh; ++ky, ++itA) {
+          const int buf = itA % A_BUFS;
+          mbar_wait(fullA + 8 * buf, (itA / A_BUFS) & 1);
+          const long long pstart = (long long)S.q0 + (long long)(ky - ay) * Wp - ax;
+          for (int kx = 0; kx < kw; ++kx, ++itB) {
+            const int tap = ky * kw + kx;
+            const int st = itB % B_STAGES;
+            mbar_wait(fullB + 8 * st, (itB / B_STAGES) & 1);
+            const int hs = hcount & 1;
+            const bool hfirst = (tap % G) == 0;
+            if (hfirst) mbar_wait(hEmpty + 8 * hs, ((hcount >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t bhi = sB + (uint32_t)st * 2u * slab_bytes, blo = bhi + slab_bytes;
+            const uint32_t ahi = sA + (uint32_t)buf * 2u * STRIP_BYTES + ((uint32_t)(pstart & 7) + (uint32_t)kx) * 128u, alo = ahi + STRIP_BYTES;
+            const uint32_t dH = tmem + (uint32_t)(hs * NP);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(dH, umma_desc(ahi + k * 32), umma_desc(bhi + k * 32), idesc, (hfirst && k == 0) ? 0u : 1u);
+            if (tap == 0) { mbar_wait(cEmpty, (tcount & 1) ^ 1); tc_fence_after(); }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(dC, umma_desc(alo + k * 32), umma_desc(bhi + k * 32), idesc, (tap == 0 && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(dC, umma_desc(ahi + k * 32), umma_desc(blo + k * 32), idesc, 1u);
+            umma_commit(emptyB + 8 * st);                    // weight slab consumed once these MMAs retire
+            if ((tap + 1) % G == 0 || tap == taps - 1) { umma_commit(hFull + 8 * hs); ++hcount; }
+          }
+          umma_commit(emptyA + 8 * buf);                     // strip buffer consumed
+        }
+        umma_commit(cFull);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM lanes 32*(warp%4).. ; sums the partial accumulators in registers, then -> resp[frame][f][cell] =====
+    const int q = warp & 3;
+    const int nparts = (taps + G - 1) / G;
+    int hcount = 0, tcount = 0;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
+      const int frame = w / p.n_tiles;
+      const TcTile S = p.tiles[w - frame * p.n_tiles];
+      const TcLevel L = p.levels[S.level];
+      float acc[NP_MAX];
+#pragma unroll
+      for (int j = 0; j < NP_MAX; ++j) acc[j] = 0.f;
+      for (int part = 0; part <= nparts; ++part) {
+        uint32_t taddr;
+        int hs = 0;
+        if (part < nparts) {
+          hs = hcount & 1;
+          mbar_wait(hFull + 8 * hs, (hcount >> 1) & 1);
+          taddr = lane_base + (uint32_t)(hs * NP);
+        } else {
+          mbar_wait(cFull, tcount & 1);
+          taddr = lane_base + (uint32_t)(2 * NP);
+        }
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < NP_MAX; c0 += 16) {
+          if (c0 < NP) {
+            uint32_t v[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(part < nparts ? hEmpty + 8 * hs : cEmpty);
+        if (part < nparts) ++hcount;
+      }
+      const int r = S.q0 - L.R + q * 32 + lane;             // row relative to real cell (0, 0)
+      const int y = r / L.Wp, x = r - y * L.Wp;
+      if (y < L.oh && x < L.ow) {
+        float* dst = p.resp + (size_t)frame * p.nfilters * p.cells_total + L.cell_off + (size_t)y * L.ow + x;
+#pragma unroll
+        for (int j = 0; j < NP_MAX; ++j)
+          if (j < p.nfilters) dst[(size_t)j * p.cells_total] = acc[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
+}
+
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+bool response_tc_supported(const FilterBank& fb) {
+  return fb.uniform && fb.flen == 32 && fb.kw >= 1 && fb.kw <= 10 && fb.kh >= 1 && round_up(fb.nfilters, 16) <= NP_MAX;
+}
+int response_tc_np(int nfilters) { return round_up(nfilters, 16); }
+
+// round to tf32 (10 explicit mantissa bits), ties away from zero like cvt.rna.tf32.f32
+static float host_tf32(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return v;
+  u = (u + 0x1000u) & ~0x1FFFu;
+  memcpy(&v, &u, 4);
+  return v;
+}
+
+// filters[f] = [tap][c] (HWC taps) -> [tap][part][NP][32] slabs, 16-byte chunk c of filter row n stored at chunk c ^ (n & 7)
+void response_tc_pack_weights(const std::vector<std::vector<float>>& filters, int taps, std::vector<float>& out) {
+  const int nf = (int)filters.size(), NP = response_tc_np(nf);
+  out.assign((size_t)taps * 2 * NP * 32, 0.f);
+  for (int t = 0; t < taps; ++t)
+    for (int n = 0; n < nf; ++n)
+      for (int c = 0; c < 32; ++c) {
+        const float v = filters[n][(size_t)t * 32 + c];
+        const float hi = host_tf32(v), lo = host_tf32(v - hi);
+        const size_t col = (size_t)(((c >> 2) ^ (n & 7)) << 2) + (c & 3);
+        out[(((size_t)t * 2 + 0) * NP + n) * 32 + col] = hi;
+        out[(((size_t)t * 2 + 1) * NP + n) * 32 + col] = lo;
+      }
+}
+
+// padded strip layout of one frame + the work list of one frame; returns rows per frame (multiple of 8)
+long long response_tc_plan(const Geometry& g, int kh, int kw, std::vector<TcLevel>& levels, std::vector<TcTile>& tiles, long long* slack_rows) {
+  const int ay = kh / 2, ax = kw / 2;
+  levels.assign(g.n_levels, TcLevel{});
+  tiles.clear();
+  long long base = 0;
+  int wp_max = 0;
+  for (int l = 0; l < g.n_levels; ++l) {
+    const LevelDesc& L = g.lv[l];
+    TcLevel T{};
+    T.Wp = L.ow + ax; T.ow = L.ow; T.oh = L.oh; T.cell_off = L.cell_off;
+    T.R = (int)base + ay * T.Wp + ax;
+    levels[l] = T;
+    wp_max = std::max(wp_max, T.Wp);
+    const int n_out = (L.oh - 1) * T.Wp + L.ow;                   // first to last real cell
+    const int ntiles = (n_out + TM - 1) / TM;
+    for (int k = 0; k < ntiles; ++k) tiles.push_back(TcTile{l, T.R + k * TM});
+    base += round_up((L.oh + kh - 1) * T.Wp + ax, 8);
+  }
+  *slack_rows = (long long)TM + (long long)kh * wp_max + 32;   // phantom rows of a level's last tile read past its block
+  return base;
+}
+
+int launch_feat_split(const Geometry& g, const Geometry* d_g, const TcLevel* d_levels, const float* feat, float* fhi, float* flo, long long frame_rows,
+                      cudaStream_t s) {
+  int maxc = 0;
+  for (int l = 0; l < g.n_levels; ++l) maxc = std::max(maxc, g.lv[l].ow * g.lv[l].oh);
+  if (maxc == 0) return 0;
+  dim3 grid((maxc * 8 + 255) / 256, g.n_levels, g.n_frames);
+  feat_split<<<grid, 256, 0, s>>>(d_g, d_levels, feat, fhi, flo, frame_rows);
+  return 1;
+}
+
+int launch_tc_border_init(float* fhi, float* flo, long long rows, cudaStream_t s) {
+  cudaMemsetAsync(fhi, 0, (size_t)rows * 128, s);
+  cudaMemsetAsync(flo, 0, (size_t)rows * 128, s);
+  tc_border_init<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(fhi, rows);
+  return 1;
+}
+
+int launch_response_tc(const Geometry& g, const DeviceBuffers& b, const FilterBank& fb, const float* fhi, const float* flo, const float* wpk,
+                       const TcLevel* d_levels, const TcTile* d_tiles, int n_tiles, long long frame_rows, int num_sms, int taps_per_partial,
+                       cudaStream_t s) {
+  if (n_tiles <= 0 || g.n_frames <= 0) return 0;
+  TcParams p{};
+  p.fhi = fhi; p.flo = flo; p.wpk = wpk; p.resp = b.resp; p.levels = d_levels; p.tiles = d_tiles;
+  p.n_tiles = n_tiles; p.n_frames = g.n_frames; p.frame_rows = frame_rows; p.cells_total = g.cells_total;
+  p.nfilters = fb.nfilters; p.NP = response_tc_np(fb.nfilters); p.kh = fb.kh; p.kw = fb.kw;
+  p.taps_per_partial = taps_per_partial > 0 ? taps_per_partial : fb.kw;
+  const size_t smem = 1024 + (size_t)A_BUFS * 2 * STRIP_BYTES + (size_t)B_STAGES * 2 * p.NP * 128;
+  cudaFuncSetAttribute(part_response_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long total = (long long)n_tiles * g.n_frames;
+  const int grid = (int)std::min<long long>(total, num_sms);
+  part_response_tc<<<grid, NTHREADS, smem, s>>>(p);
+  return 1;
+}
+
+}  // namespace pbd

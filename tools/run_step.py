@@ -16,6 +16,8 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--h", type=int, default=480)
 ap.add_argument("--w", type=int, default=640)
 ap.add_argument("--fast", action="store_true")
+ap.add_argument("--mode", type=int, default=-1, help="response mode 0 exact, 1 ffma, 2 tensor")
+ap.add_argument("--G", type=int, default=0)
 ap.add_argument("--max-levels", type=int, default=0)
 a = ap.parse_args()
 frames = synth_frames(min(a.batch, 4), a.h, a.w)
@@ -24,6 +26,9 @@ dev = torch.from_numpy(frames).cuda()
 det = PartsBasedDetector(device=0, stream=torch.cuda.current_stream().cuda_stream)
 det.distributeModel(Model.load_bin(os.path.join(ROOT, "tests", "golden", "Person_26parts.pbdm")))
 det.set_option("exact", 0 if a.fast else 1)
+if a.mode >= 0:
+    det.set_option("response_mode", a.mode)
+    det.set_option("tc_taps_per_partial", a.G)
 det.set_option("max_levels", a.max_levels)
 det.set_option("thresh", -1.14)
 det.set_option("timing", 1)
