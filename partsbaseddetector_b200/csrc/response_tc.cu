@@ -31,6 +31,8 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -50,24 +52,35 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, unsigned parity) {
+  unsigned done;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, unsigned parity) {
+  for (long long spins = 0; !mbar_try(bar, parity); ++spins)
+    if (spins > (1ll << 26)) asm volatile("trap;\n");      // a broken hand-off must fail loudly, not hang the device
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
-  unsigned done = 0;
-  long long spins = 0;
-  while (true) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) break;
-    if (++spins > (1ll << 27)) asm volatile("trap;\n");     // a broken hand-off must fail loudly, not hang the device
-  }
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, unsigned bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// K-major SWIZZLE_128B operand descriptor: 128-byte rows, 8-row groups 1024 B apart; `saddr` may start at any row
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+// K-major SWIZZLE_128B operand descriptor: 128-byte rows, 8-row groups 1024 B apart.  Low word = (start address >> 4) | LBO
+// (1 << 16, unused for swizzled K-major), high word = SBO (1024 >> 4) | version 1 (bit 46) | SWIZZLE_128B (2 << 61) = constant.
+// The start address may be ANY row of a staged strip (absolute-address swizzle, tools/umma_probe.cu).
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n}\n" ::"r"(tmem_d), "r"(da_lo), "r"(db_lo), "r"(idesc), "r"(acc), "r"(kDescHi)
+      : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xFFFFFFFF;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
@@ -118,9 +131,9 @@ struct TcParams {
   int n_tiles, n_frames;
   long long frame_rows;
   int cells_total, nfilters, NP, kh, kw;
-  int taps_per_partial;        // hi*hi products are summed on the tensor core over this many taps, then in fp32 RN registers
 };
 
+template <bool PER_TAP>
 __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -150,7 +163,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
   const uint32_t tmem = tmem_base_s;
 
   const int kh = p.kh, kw = p.kw, ay = kh / 2, ax = kw / 2;   // anchor = centre, include/filterengine.hpp:310-318
-  const int taps = kh * kw, G = p.taps_per_partial;
+  const int taps = kh * kw, G = PER_TAP ? 1 : kw;
   const int total = p.n_tiles * p.n_frames;
 
   if (warp == 0) {
@@ -187,45 +200,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
       }
     }
   } else if (warp == 2) {
-    // ===== MMA issuer.  TMEM: columns [0,NP) and [NP,2NP) = ping-pong partial sums of hi*hi over G taps, [2NP,3NP) = the
-    // small lo*hi + hi*lo correction of the whole tile.  Short chains keep the tensor core's truncating accumulation
-    // (round toward zero at every step) below one ulp of the final score; the epilogue adds the partials in fp32 RN. =====
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-      int itA = 0, itB = 0, hcount = 0, tcount = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
-        const int frame = w / p.n_tiles;
-        const TcTile S = p.tiles[w - frame * p.n_tiles];
-        const int Wp = p.levels[S.level].Wp;
-        const uint32_t dC = tmem + (uint32_t)(2 * NP);
-        for (int ky = 0; ky < kh; ++ky, ++itA) {
-          const int buf = itA % A_BUFS;
-          mbar_wait(fullA + 8 * buf, (itA / A_BUFS) & 1);
-          const long long pstart = (long long)S.q0 + (long long)(ky - ay) * Wp - ax;
-          for (int kx = 0; kx < kw; ++kx, ++itB) {
-            const int tap = ky * kw + kx;
-            const int st = itB % B_STAGES;
-            mbar_wait(fullB + 8 * st, (itB / B_STAGES) & 1);
-            const int hs = hcount & 1;
-            const bool hfirst = (tap % G) == 0;
-            if (hfirst) mbar_wait(hEmpty + 8 * hs, ((hcount >> 1) & 1) ^ 1);
+    // ===== MMA issuer.  The whole warp runs the loop (operands stay in uniform registers), one elected lane issues; the loop
+    // body is kept to a few dozen instructions per tap because a single warp's instruction latency, not the tensor pipe,
+    // bounds the kernel otherwise.  TMEM: columns [0,NP) and [NP,2NP) = ping-pong partial sums of hi*hi over one tap
+    // (PER_TAP) or one filter row, [2NP,3NP) = the small lo*hi + hi*lo correction of the whole tile.  Short chains keep the
+    // tensor core's truncating accumulation below one ulp of the final score; the epilogue adds the partials in fp32 RN. =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t dC = tmem + (uint32_t)(2 * NP);
+    const uint32_t a_lo_off = STRIP_BYTES >> 4, b_lo_off = slab_bytes >> 4;
+    uint32_t bufA = 0, phA = 0, stB = 0, phB = 0, hs = 0, phH = 1, phC = 1;       // ring positions and wait parities
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int frame = w / p.n_tiles;
+      const TcTile S = p.tiles[w - frame * p.n_tiles];
+      const int Wp = p.levels[S.level].Wp;
+      int prow = S.q0 - ay * Wp - ax;                          // first strip row of filter row ky (>= 0 by construction)
+      for (int ky = 0; ky < kh; ++ky, prow += Wp) {
+        mbar_wait(fullA + 8 * bufA, phA);
+        // descriptor low words = (start address >> 4) | LBO; one strip row = 128 B adds 8, a k-step of 8 tf32 = 32 B adds 2
+        uint32_t ahi = ((sA + bufA * 2u * STRIP_BYTES + (uint32_t)(prow & 7) * 128u) >> 4) | 0x10000u;
+        for (int kx = 0; kx < kw; ++kx, ahi += 8) {
+          mbar_wait(fullB + 8 * stB, phB);
+          const bool hfirst = PER_TAP || kx == 0, hlast = PER_TAP || kx == kw - 1;
+          if (hfirst) mbar_wait(hEmpty + 8 * hs, phH);
+          tc_fence_after();
+          const uint32_t bhi = ((sB + stB * 2u * slab_bytes) >> 4) | 0x10000u;
+          const uint32_t dH = tmem + hs * (uint32_t)NP;
+          const bool first = (ky | kx) == 0, last = ky == kh - 1 && kx == kw - 1;
+          if (first) {                                       // the correction accumulator of the previous tile must have been read
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(dH, ahi + 2 * k, bhi + 2 * k, idesc, k == 0 ? 0u : 1u);
+            }
+            __syncwarp();
+            mbar_wait(cEmpty, phC);
+            phC ^= 1;
             tc_fence_after();
-            const uint32_t bhi = sB + (uint32_t)st * 2u * slab_bytes, blo = bhi + slab_bytes;
-            const uint32_t ahi = sA + (uint32_t)buf * 2u * STRIP_BYTES + ((uint32_t)(pstart & 7) + (uint32_t)kx) * 128u, alo = ahi + STRIP_BYTES;
-            const uint32_t dH = tmem + (uint32_t)(hs * NP);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(dH, umma_desc(ahi + k * 32), umma_desc(bhi + k * 32), idesc, (hfirst && k == 0) ? 0u : 1u);
-            if (tap == 0) { mbar_wait(cEmpty, (tcount & 1) ^ 1); tc_fence_after(); }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(dC, umma_desc(alo + k * 32), umma_desc(bhi + k * 32), idesc, (tap == 0 && k == 0) ? 0u : 1u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(dC, umma_desc(ahi + k * 32), umma_desc(blo + k * 32), idesc, 1u);
-            umma_commit(emptyB + 8 * st);                    // weight slab consumed once these MMAs retire
-            if ((tap + 1) % G == 0 || tap == taps - 1) { umma_commit(hFull + 8 * hs); ++hcount; }
           }
-          umma_commit(emptyA + 8 * buf);                     // strip buffer consumed
+          if (elect_one()) {
+            if (!first) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(dH, ahi + 2 * k, bhi + 2 * k, idesc, (hfirst && k == 0) ? 0u : 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + a_lo_off + 2 * k, bhi + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + 2 * k, bhi + b_lo_off + 2 * k, idesc, 1u);
+            umma_commit(emptyB + 8 * stB);                   // weight slab consumed once these MMAs retire
+            if (hlast) umma_commit(hFull + 8 * hs);
+            if (kx == kw - 1) umma_commit(emptyA + 8 * bufA);  // strip buffer consumed
+            if (last) umma_commit(cFull);
+          }
+          __syncwarp();
+          if (hlast) { phH ^= hs; hs ^= 1; }                 // parity flips every second partial
+          if (++stB == B_STAGES) { stB = 0; phB ^= 1; }
         }
-        umma_commit(cFull);
+        if (++bufA == A_BUFS) { bufA = 0; phA ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -368,12 +397,14 @@ int launch_response_tc(const Geometry& g, const DeviceBuffers& b, const FilterBa
   p.fhi = fhi; p.flo = flo; p.wpk = wpk; p.resp = b.resp; p.levels = d_levels; p.tiles = d_tiles;
   p.n_tiles = n_tiles; p.n_frames = g.n_frames; p.frame_rows = frame_rows; p.cells_total = g.cells_total;
   p.nfilters = fb.nfilters; p.NP = response_tc_np(fb.nfilters); p.kh = fb.kh; p.kw = fb.kw;
-  p.taps_per_partial = taps_per_partial > 0 ? taps_per_partial : fb.kw;
   const size_t smem = 1024 + (size_t)A_BUFS * 2 * STRIP_BYTES + (size_t)B_STAGES * 2 * p.NP * 128;
-  cudaFuncSetAttribute(part_response_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool per_tap = taps_per_partial == 1;      // hi*hi chains of one tap (most accurate) or of one filter row (default)
+  if (per_tap) cudaFuncSetAttribute(part_response_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  else cudaFuncSetAttribute(part_response_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long total = (long long)n_tiles * g.n_frames;
   const int grid = (int)std::min<long long>(total, num_sms);
-  part_response_tc<<<grid, NTHREADS, smem, s>>>(p);
+  if (per_tap) part_response_tc<true><<<grid, NTHREADS, smem, s>>>(p);
+  else part_response_tc<false><<<grid, NTHREADS, smem, s>>>(p);
   return 1;
 }
 

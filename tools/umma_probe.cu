@@ -105,6 +105,84 @@ probe(const float* __restrict__ A, const float* __restrict__ B, float* __restric
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem));
 }
 
+// Issue pattern of part_response_tc without any data movement: per "tap" 4 MMAs into a ping-pong accumulator and 8 into a third
+// one, operands taken from varying rows / slabs of shared memory, optionally one tcgen05.commit per tap.  Measures the tensor
+// pipe's sustained pace for that pattern (cycles per MMA).
+__global__ void __launch_bounds__(128, 1) pattern(int taps, int mode, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) unsigned long long bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 200 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0.f;
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  __shared__ volatile int done_flag;
+  if (tid == 0) done_flag = 0;
+  __syncthreads();
+  if (warp != 0 && (mode & 8)) {         // other warps poll an mbarrier that never completes, like idle pipeline roles do
+    unsigned done = 0;
+    while (!done_flag)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(&bar[1])), "r"(0u) : "memory");
+  }
+  if (warp != 0 && (mode & 16)) {        // other warps read tensor memory continuously, like the epilogue does
+    unsigned sink = 0;
+    while (!done_flag) {
+      uint32_t v[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                     "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                   : "r"(tmem_base_s + ((uint32_t)(warp * 32) << 16) + 300u));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      sink += v[3];
+    }
+    if (sink == 77u) cycles[3] = 1;
+  }
+  if (tid == 0) {
+    long long commit_cycles = 0;
+    unsigned busy = (unsigned)taps;
+    const long long t0 = clock64();
+    for (int tap = 0; tap < taps; ++tap) {
+      const uint32_t a_hi = base + (uint32_t)((tap / 5) & 1) * 36864u + (uint32_t)(3 + tap % 5) * 128u, a_lo = a_hi + 18432u;
+      const uint32_t b_hi = base + 73728u + (uint32_t)(tap & 3) * 36864u, b_lo = b_hi + 18432u;
+      const uint32_t dH = (mode & 2) ? tmem : tmem + (uint32_t)(((tap / 5) & 1) * N), dC = (mode & 2) ? tmem : tmem + 2 * N;
+      for (int k = 0; k < 4; ++k) mma_tf32(dH, make_desc(a_hi + k * 32, 0), make_desc(b_hi + k * 32, 0), idesc, 1u);
+      for (int k = 0; k < 4; ++k) mma_tf32(dC, make_desc(a_lo + k * 32, 0), make_desc(b_hi + k * 32, 0), idesc, 1u);
+      for (int k = 0; k < 4; ++k) mma_tf32(dC, make_desc(a_hi + k * 32, 0), make_desc(b_lo + k * 32, 0), idesc, 1u);
+      long long tc0 = clock64();
+      if (mode & 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar[1])) : "memory");
+      commit_cycles += clock64() - tc0;
+      if (mode & 4) {                      // ~500 cycles of dependent busy work per tap (stands for waits / bookkeeping)
+        for (int i = 0; i < 100; ++i) busy = busy * 1664525u + 1013904223u;
+      }
+    }
+    if (busy == 12345u) cycles[2] = 1;
+    cycles[1] = commit_cycles;
+    done_flag = 1;
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar[0])) : "memory");
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(&bar[0])), "r"(0u) : "memory");
+    *cycles = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
+}
+
 int main() {
   std::vector<float> hA(AROWS * KROW), hB(N * KROW), hD(M * N);
   srand(7);
@@ -114,7 +192,7 @@ int main() {
   long long* dcyc;
   int* derr;
   CK(cudaMalloc(&dA, hA.size() * 4)); CK(cudaMalloc(&dB, hB.size() * 4)); CK(cudaMalloc(&dD, hD.size() * 4));
-  CK(cudaMalloc(&dcyc, 8)); CK(cudaMalloc(&derr, 4));
+  CK(cudaMalloc(&dcyc, 64)); CK(cudaMalloc(&derr, 4));
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice));
   const int smem = (AROWS + N) * 128 + 1024;
@@ -138,6 +216,19 @@ int main() {
       }
     printf("shift %2d base_offset %d reps %4d: %s mismatches %d / %d, timeout %d, %lld cycles (%.1f per MMA)\n", c.shift, c.bo, c.reps,
            bad ? "FAIL" : "ok  ", bad, M * N, err, cyc, (double)cyc / (4.0 * c.reps));
+  }
+  const int psmem = 222 * 1024;
+  CK(cudaFuncSetAttribute(pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
+  for (int mode : {1, 5, 9, 13, 17, 29}) {
+    for (int grid : {1}) {
+      pattern<<<grid, 128, psmem>>>(500, mode, dcyc);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("pattern launch failed: %s\n", cudaGetErrorString(e)); return 1; }
+      long long cyc[2];
+      CK(cudaMemcpy(cyc, dcyc, 16, cudaMemcpyDeviceToHost));
+      printf("pattern mode %2d (commit per tap %d, busy work per tap %d, polling warps %d, LDTM warps %d) grid %3d: %.1f cycles per tap (MMA floor 864), of which in commit %.1f\n",
+             mode, mode & 1, (mode >> 2) & 1, (mode >> 3) & 1, (mode >> 4) & 1, grid, (double)cyc[0] / 500.0, (double)cyc[1] / 500.0);
+    }
   }
   return 0;
 }
