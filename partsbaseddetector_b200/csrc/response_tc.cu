@@ -148,12 +148,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < 2 * A_BUFS + 2 * B_STAGES; ++i) mbar_init(fullA + 8 * i, 1);
+    for (int i = 0; i < A_BUFS; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 2); }   // both MMA warps release
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 2); }
     mbar_init(hFull, 1); mbar_init(hFull + 8, 1); mbar_init(hEmpty, 4); mbar_init(hEmpty + 8, 4);
     mbar_init(cFull, 1); mbar_init(cEmpty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 3) {
+  if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(&tmem_base_s)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
@@ -199,12 +200,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
         }
       }
     }
-  } else if (warp == 2) {
-    // ===== MMA issuer.  The whole warp runs the loop (operands stay in uniform registers), one elected lane issues; the loop
-    // body is kept to a few dozen instructions per tap because a single warp's instruction latency, not the tensor pipe,
-    // bounds the kernel otherwise.  TMEM: columns [0,NP) and [NP,2NP) = ping-pong partial sums of hi*hi over one tap
-    // (PER_TAP) or one filter row, [2NP,3NP) = the small lo*hi + hi*lo correction of the whole tile.  Short chains keep the
-    // tensor core's truncating accumulation below one ulp of the final score; the epilogue adds the partials in fp32 RN. =====
+  } else if (warp == 2 || warp == 3) {
+    // ===== MMA issuers.  Two warps, because a single warp's instruction latency (not the tensor pipe) bounds the kernel when
+    // one warp issues all 12 MMAs of a tap: warp 2 issues the hi*hi products (4 per tap) into the ping-pong partial
+    // accumulators [0,NP) / [NP,2NP) -- chains of one tap (PER_TAP) or one filter row -- and warp 3 the lo*hi + hi*lo
+    // corrections (8 per tap) into [2NP,3NP) for the whole tile; the two chains are independent, so the warps need no
+    // ordering between them.  Each warp runs its loop convergently (operands stay in uniform registers), one elected lane
+    // issues.  Short hi*hi chains keep the tensor core's truncating accumulation below one ulp of the final score; the
+    // epilogue adds the partials in fp32 RN. =====
+    const bool isH = warp == 2;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     const uint32_t dC = tmem + (uint32_t)(2 * NP);
     const uint32_t a_lo_off = STRIP_BYTES >> 4, b_lo_off = slab_bytes >> 4;
@@ -214,44 +218,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
       const TcTile S = p.tiles[w - frame * p.n_tiles];
       const int Wp = p.levels[S.level].Wp;
       int prow = S.q0 - ay * Wp - ax;                          // first strip row of filter row ky (>= 0 by construction)
+      if (!isH) { mbar_wait(cEmpty, phC); phC ^= 1; }          // the correction accumulator of the previous tile has been read
       for (int ky = 0; ky < kh; ++ky, prow += Wp) {
         mbar_wait(fullA + 8 * bufA, phA);
         // descriptor low words = (start address >> 4) | LBO; one strip row = 128 B adds 8, a k-step of 8 tf32 = 32 B adds 2
         uint32_t ahi = ((sA + bufA * 2u * STRIP_BYTES + (uint32_t)(prow & 7) * 128u) >> 4) | 0x10000u;
         for (int kx = 0; kx < kw; ++kx, ahi += 8) {
           mbar_wait(fullB + 8 * stB, phB);
-          const bool hfirst = PER_TAP || kx == 0, hlast = PER_TAP || kx == kw - 1;
-          if (hfirst) mbar_wait(hEmpty + 8 * hs, phH);
-          tc_fence_after();
           const uint32_t bhi = ((sB + stB * 2u * slab_bytes) >> 4) | 0x10000u;
-          const uint32_t dH = tmem + hs * (uint32_t)NP;
-          const bool first = (ky | kx) == 0, last = ky == kh - 1 && kx == kw - 1;
-          if (first) {                                       // the correction accumulator of the previous tile must have been read
+          if (isH) {
+            const bool hfirst = PER_TAP || kx == 0, hlast = PER_TAP || kx == kw - 1;
+            if (hfirst) mbar_wait(hEmpty + 8 * hs, phH);
+            tc_fence_after();
+            const uint32_t dH = tmem + hs * (uint32_t)NP;
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(dH, ahi + 2 * k, bhi + 2 * k, idesc, k == 0 ? 0u : 1u);
+              for (int k = 0; k < 4; ++k) umma_tf32(dH, ahi + 2 * k, bhi + 2 * k, idesc, (hfirst && k == 0) ? 0u : 1u);
+              umma_commit(emptyB + 8 * stB);                 // weight slab consumed once these MMAs retire (and warp 3's)
+              if (hlast) umma_commit(hFull + 8 * hs);
+              if (kx == kw - 1) umma_commit(emptyA + 8 * bufA);
             }
             __syncwarp();
-            mbar_wait(cEmpty, phC);
-            phC ^= 1;
+            if (hlast) { phH ^= hs; hs ^= 1; }               // parity flips every second partial
+          } else {
             tc_fence_after();
-          }
-          if (elect_one()) {
-            if (!first) {
+            const bool first = (ky | kx) == 0;
+            if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(dH, ahi + 2 * k, bhi + 2 * k, idesc, (hfirst && k == 0) ? 0u : 1u);
+              for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + a_lo_off + 2 * k, bhi + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + 2 * k, bhi + b_lo_off + 2 * k, idesc, 1u);
+              umma_commit(emptyB + 8 * stB);
+              if (kx == kw - 1) umma_commit(emptyA + 8 * bufA);
+              if (ky == kh - 1 && kx == kw - 1) umma_commit(cFull);
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + a_lo_off + 2 * k, bhi + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + 2 * k, bhi + b_lo_off + 2 * k, idesc, 1u);
-            umma_commit(emptyB + 8 * stB);                   // weight slab consumed once these MMAs retire
-            if (hlast) umma_commit(hFull + 8 * hs);
-            if (kx == kw - 1) umma_commit(emptyA + 8 * bufA);  // strip buffer consumed
-            if (last) umma_commit(cFull);
+            __syncwarp();
           }
-          __syncwarp();
-          if (hlast) { phH ^= hs; hs ^= 1; }                 // parity flips every second partial
           if (++stB == B_STAGES) { stB = 0; phB ^= 1; }
         }
         if (++bufA == A_BUFS) { bufA = 0; phA ^= 1; }
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
 }
 
 inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
