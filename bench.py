@@ -147,6 +147,38 @@ def run_reference_arm(args):
     return 0
 
 
+def parity_gate(det, frame, mode):
+    """One synthetic VGA frame through the CUDA path and the CPU oracle: integer outputs (part locations, mixture ids, rects, root
+    mixture maps) must be identical, root scores within 1e-4 relative (north star); bit-identical in exact mode.  Fails loudly."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from partsbaseddetector_b200 import Model
+    O = oracle_lib.OracleDetector(Model.load_bin(MODEL).to_flat(), 32)
+    oracle_lib.use_all_cores()
+    O.run(frame, 1, 3)
+    nl = O.nlevels()
+    rv = np.sort(np.concatenate([O.rootv(l).ravel() for l in range(nl)]))
+    k = rv.size - 60
+    thr = float(0.5 * (float(rv[k - 1]) + float(rv[k])))          # between two neighbouring root scores: ~60 candidates
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    oc = O.candidates()
+    det.set_option("thresh", thr)
+    cands = det.detect(frame)
+    worst, flips, ncell = 0.0, 0, 0
+    for l in range(nl):
+        ref, got = O.rootv(l), det.rootv(0, l)
+        worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
+        flips += int((det.rooti(0, l) != O.rooti(l)).sum())      # root-mixture arg-max map: can only differ at score near-ties
+        ncell += ref.size
+    same = len(cands) == len(oc) and all(g.level == o["level"] and np.array_equal(g.x, o["x"]) and np.array_equal(g.y, o["y"]) and
+                                         np.array_equal(g.m, o["m"]) and np.array_equal(g.parts(), o["rects"]) for g, o in zip(cands, oc))
+    if not same or worst > 1e-4 or (mode == "exact" and (worst != 0.0 or flips)):
+        raise SystemExit("bench.py parity gate failed: identical candidates %s, max relative root-score error %.3g, root-mixture flips %d" % (same, worst, flips))
+    return {"checked": "1 synthetic VGA frame, all 14 levels, vs the CPU oracle", "candidates": len(oc), "candidate_integer_outputs_identical": True,
+            "max_rel_root_score_error": worst, "tolerance": 1e-4, "root_mixture_map_cells_differing": flips, "root_mixture_map_cells": ncell}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_gpu_arm(args):
     import torch
@@ -173,7 +205,8 @@ def run_gpu_arm(args):
 
     det = PartsBasedDetector(device=local, stream=torch.cuda.current_stream().cuda_stream)
     det.distributeModel(Model.load_bin(MODEL))
-    det.set_option("exact", 0 if args.fast else 1)
+    mode = {"exact": 0, "ffma": 1, "tensor": 2}[args.mode]
+    det.set_option("response_mode", mode)
     det.set_option("timing", 1)
     # calibrate the detection threshold on the first batch so that ~50 candidates/frame come back (synthetic
     # frames score below the model's -0.75: SURVEY.md section 8d); done once, outside every timed region
@@ -184,6 +217,8 @@ def run_gpu_arm(args):
     thr = float(np.sort(rv)[-50]) if args.thresh is None else args.thresh
     det.set_option("thresh", thr)
     cells = int(sum(det.level_info(l)["oh"] * det.level_info(l)["ow"] for l in range(nl)))
+    parity = parity_gate(det, base[0], args.mode) if rank == 0 and not args.no_cpu else None
+    det.set_option("thresh", thr)
 
     def barrier():
         if world > 1:
@@ -214,11 +249,15 @@ def run_gpu_arm(args):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     # per-stage device time of the last step (events recorded by the library on the same stream)
     stage_ms = det.stage_times_ms()
-    # the per-kernel average over the timed region for the dominant kernel: re-run K steps collecting the pdf stage time
-    pdf_ms = []
-    for _ in range(min(args.steps, 5)):
+    # per-kernel averages (events after every kernel of the pdf / dp_min stages) over a few more steps of the same workload
+    det.set_option("timing", 2)
+    kt = {}
+    nk = min(args.steps, 5)
+    for _ in range(nk):
         det.enqueue_device(dev.data_ptr(), B, H, W, C)
-        pdf_ms.append(det.stage_times_ms()["pdf"])
+        for k, v in det.kernel_times_ms().items():
+            kt[k] = kt.get(k, 0.0) + v / nk
+    det.set_option("timing", 1)
     from partsbaseddetector_b200.sharding import max_over_ranks
     ms_max = max_over_ranks(ms, device="cuda")
 
@@ -251,47 +290,85 @@ def run_gpu_arm(args):
     if rank == 0:
         peaks, peak_src = measured_peaks()
         fps = world * B * args.steps / (ms_max * 1e-3)
-        pdf_avg = float(np.mean(pdf_ms))
-        alg_bytes = 680.0 * cells * B                         # per launch: 128 B features read + 552 B responses written per cell
-        flops = 2.0 * 800 * 138 * cells * B
-        ach = alg_bytes / (pdf_avg * 1e-3) / 1e9
         sm_mhz = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        mode_txt = {"exact": "exact (separately rounded multiply/add, bit-identical scores)", "ffma": "ffma (FP32 fused multiply-add responses)",
+                    "tensor": "tensor (tcgen05 tf32x3 split products + fp32 accumulate for the part responses; scores within 2e-6 relative, "
+                              "integer outputs identical to the CPU oracle -- checked in `parity`)"}[args.mode]
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.mode != "tensor" else "f32 (part responses as tf32x3 tensor-core products with fp32 accumulation; everything else f32/f64 as the reference)",
             "data": "synthetic",
             "config": {"workload": "config_person.by_parts (Person_26parts), 640x480 BGR frames, full 14-level HOG pyramid, 1xB200 per rank",
                        "batch_per_gpu": B, "frame": [H, W, C], "levels": nl, "cells_per_frame": cells, "parallelism": "frame-parallel x%d, no collective" % world,
-                       "mode": "fast (FFMA)" if args.fast else "exact (bit-identical scores)", "thresh": thr, "candidates_per_step": ncand,
+                       "mode": mode_txt, "thresh": thr, "candidates_per_step": ncand,
                        "l2": "inputs larger than L2 (%.0f MB of responses per step)" % (552.0 * cells * B / 1e6)},
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": B * H * W * C, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "part_response", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                         "traffic": None, "peak_source": peak_src, "ms_per_launch": pdf_avg,
-                         "note": "dense contraction (325 FLOP/B): FP32-issue-bound, not HBM-bound; see fp32",
-                         "fp32": {"achieved_tflops": flops / (pdf_avg * 1e-3) / 1e12, "peak_tflops": fp32_peak,
-                                  "frac": flops / (pdf_avg * 1e-3) / 1e12 / fp32_peak, "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz"}},
-            "stage_ms": stage_ms,
+            "stage_ms": stage_ms, "kernel_ms": kt,
         }
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, scaled to this batch)
-        tp = os.path.join(ROOT, "profiles", "part_response_traffic.json")
+        if parity is not None:
+            line["parity"] = parity
+        # ---- rooflines.  Algorithmic work per cell from DESIGN.md section 3 / SURVEY.md section 8d ----
+        nmaps = 133                                               # (part, mixture) child maps of the person model = DTs per level
+        nlaunch_dt = 22                                           # 11 waves x (rows, columns)
+        dt_ms = kt.get("dt_rows", 0.0) + kt.get("dt_cols", 0.0)
+        dt_bytes = 2 * nmaps * 10.0 * cells * B                   # per pass and map cell: 4 B read, 4 B value + 2 B arg-max written
+        resp_ms = kt.get("part_response", 0.0)
+        resp_flops = 2.0 * 800 * 138 * cells * B                  # the reference's multiply-adds
+        roof_dt = {"kernel": "dt_pass (22 launches per step: 11 waves x rows/columns)", "bound": "hbm", "achieved": dt_bytes / (dt_ms * 1e-3) / 1e9 if dt_ms else None,
+                   "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dt_bytes / (dt_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if dt_ms else None, "traffic": None,
+                   "peak_source": peak_src, "ms_per_launch": dt_ms / nlaunch_dt, "share_of_step": dt_ms / (ms_max / args.steps),
+                   "note": "sequential lower-envelope scan with fp64 break points, one lane per line: bounded by instruction issue (63 % of issue slots busy, "
+                           "62 % lane utilisation in the ncu capture), not by HBM"}
+        tp = os.path.join(ROOT, "profiles", "dt_pass_traffic.json")
         if os.path.exists(tp):
             tr = json.load(open(tp))
-            line["roofline"]["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * B / tr["batch"]
-            line["roofline"]["traffic_source"] = tr.get("source", "ncu")
-        # the HBM-bound remainder of the step, for context: algorithmic bytes / stage time
-        dp_bytes = (133 * 20.0 + (133 * 4.0 + 131 * 9.0)) * cells * B
+            roof_dt["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["launches"] * B / tr["batch"]
+            roof_dt["traffic_source"] = tr.get("source", "ncu")
+        if args.mode == "tensor":
+            hw_flops = 3.0 * 2 * 800 * 144 * 128 * ((cells * 1.04) // 128) * B      # 3 tf32 products, 144 padded filters, ~4 % strip padding
+            tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2
+            roof_resp = {"kernel": "part_response_tc", "bound": "tensor", "achieved": hw_flops / (resp_ms * 1e-3) / 1e12 if resp_ms else None, "peak": tf32_peak,
+                         "unit": "TFLOP/s", "frac": hw_flops / (resp_ms * 1e-3) / 1e12 / tf32_peak if resp_ms else None, "traffic": None, "ms_per_launch": resp_ms,
+                         "peak_source": peak_src + " cuBLAS bf16 burst / 2 (tf32 issues at half the bf16 rate; nominal dense tf32 1100)",
+                         "algorithmic_tflops": resp_flops / (resp_ms * 1e-3) / 1e12 if resp_ms else None,
+                         "note": "hardware tf32 FLOP/s of the three split products; algorithmic_tflops counts the reference's fp32 multiply-adds once"}
+            tp = os.path.join(ROOT, "profiles", "part_response_tc_traffic.json")
+        else:
+            fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+            ach = 680.0 * cells * B / (resp_ms * 1e-3) / 1e9 if resp_ms else None
+            roof_resp = {"kernel": "part_response", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"] if ach else None,
+                         "traffic": None, "peak_source": peak_src, "ms_per_launch": resp_ms,
+                         "note": "dense contraction (325 FLOP/B): FP32-issue-bound, not HBM-bound; see fp32",
+                         "fp32": {"achieved_tflops": resp_flops / (resp_ms * 1e-3) / 1e12 if resp_ms else None, "peak_tflops": fp32_peak,
+                                  "frac": resp_flops / (resp_ms * 1e-3) / 1e12 / fp32_peak if resp_ms else None, "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz"}}
+            tp = os.path.join(ROOT, "profiles", "part_response_traffic.json")
+        if os.path.exists(tp):
+            tr = json.load(open(tp))
+            roof_resp["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * B / tr["batch"]
+            roof_resp["traffic_source"] = tr.get("source", "ncu")
+        roof_resp["share_of_step"] = resp_ms / (ms_max / args.steps)
+        # `roofline` = the kernel with the largest share of the step; the other one is reported beside it
+        if dt_ms >= resp_ms:
+            line["roofline"], line["roofline_part_response"] = roof_dt, roof_resp
+        else:
+            line["roofline"], line["roofline_dt_pass"] = roof_resp, roof_dt
+        # the HBM-bound remainder of the step, for context: algorithmic bytes / kernel time
+        mm_bytes = (133 * 4.0 + 131 * 9.0) * cells * B
         hog_bytes = (48.0 + 76.0 + 76.0 + 128.0) * cells * B
         line["roofline_other"] = {
-            "dp_min (dt_pass x2 + mix_max, 11 waves)": {"alg_GBps": dp_bytes / (stage_ms["dp_min"] * 1e-3) / 1e9, "frac_of_hbm": dp_bytes / (stage_ms["dp_min"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                                         "bound": "latency of the sequential fp64 envelope chain, not HBM"},
+            "mix_max (11 launches)": {"alg_GBps": mm_bytes / (kt["mix_max"] * 1e-3) / 1e9 if kt.get("mix_max") else None,
+                                      "frac_of_hbm": mm_bytes / (kt["mix_max"] * 1e-3) / 1e9 / peaks["hbm_gbs"] if kt.get("mix_max") else None},
             "hog (hog_hist + hog_feat)": {"alg_GBps": hog_bytes / (stage_ms["hog"] * 1e-3) / 1e9, "frac_of_hbm": hog_bytes / (stage_ms["hog"] * 1e-3) / 1e9 / peaks["hbm_gbs"]},
         }
-        if args.also_fast:
-            det.set_option("timing", 1)
-            det.set_option("exact", 0)
+        # the other response modes on the same workload (single rank, device-resident), for comparison
+        others = {}
+        for om in ("exact", "ffma", "tensor"):
+            if om == args.mode or (om == "ffma" and not args.also_fast):
+                continue
+            det.set_option("response_mode", {"exact": 0, "ffma": 1, "tensor": 2}[om])
             for _ in range(3):
                 det.enqueue_device(dev.data_ptr(), B, H, W, C)
             torch.cuda.synchronize()
@@ -302,9 +379,9 @@ def run_gpu_arm(args):
             f1.record()
             torch.cuda.synchronize()
             fms = f0.elapsed_time(f1)
-            line["fast_mode"] = {"value": B * args.steps / (fms * 1e-3), "unit": "frames/s", "ms_per_step": fms / args.steps,
-                                 "pdf_ms": det.stage_times_ms()["pdf"], "note": "exact=0: FFMA responses (scores within 1e-6 relative, same candidates on the test frames); single rank"}
-            det.set_option("exact", 0 if args.fast else 1)
+            others[om] = {"value": B * args.steps / (fms * 1e-3), "unit": "frames/s", "ms_per_step": fms / args.steps, "pdf_ms": det.stage_times_ms()["pdf"]}
+        det.set_option("response_mode", mode)
+        line["other_response_modes"] = others
         if world == 1 and not args.no_cpu:
             cfps, cores, n, dt, cstage = cpu_frames_per_sec(base, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -322,12 +399,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (measured: 32 -> 1555, 64 -> 1636, 256 -> 1709 frames/s)")
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--unique-frames", type=int, default=8, help="distinct synthetic frames generated per rank (tiled to the batch)")
-    ap.add_argument("--fast", action="store_true", help="fused multiply-add responses instead of the bit-exact mode")
+    ap.add_argument("--mode", default="tensor", choices=["tensor", "exact", "ffma"],
+                    help="part-response arithmetic: tensor = tcgen05 tf32x3 (default; scores within 2e-6, integer outputs identical to the oracle), "
+                         "exact = bit-identical scores on the FP32 pipes, ffma = fused multiply-add on the FP32 pipes")
     ap.add_argument("--thresh", type=float, default=None)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--also-fast", action="store_true", default=True, help="also report the fused-multiply-add mode (rank 0 only)")
+    ap.add_argument("--also-fast", action="store_true", default=False, help="also time the fused-multiply-add mode (rank 0 only)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -81,14 +81,22 @@ void pbd_destroy(pbd_detector* d);
 
 /* options (defaults reproduce the reference):
  *   "thresh"      detection threshold (default model thresh; DynamicProgram::thresh_)
- *   "exact"       1 (default): responses use separately rounded multiply/add in the reference's summation
- *                 order => bit-identical scores; 0: fused multiply-add (faster, scores differ in the last ulps)
+ *   "response_mode"  how the part-filter responses (IConvolutionEngine::pdf) are computed:
+ *                 0 (default): separately rounded multiply/add in the reference's summation order => bit-identical scores;
+ *                 1: fused multiply-add on the FP32 pipes (scores differ in the last ulps);
+ *                 2: 5th-generation tensor cores (tcgen05, tf32x3 split products with fp32 accumulation; scores within ~4e-7
+ *                    relative of the reference, integer outputs identical on every test frame; 8x faster than mode 0).
+ *                    Models with non-uniform filter sizes fall back to mode 1.
+ *   "exact"       alias kept for compatibility: 1 = response_mode 0, 0 = response_mode 1
+ *   "tc_taps_per_partial"  response_mode 2: 0 (default) sums the hi*hi products of one filter row on the tensor core before the
+ *                 fp32 round-to-nearest summation (score bias ~4 ulp), 1 sums tap by tap (bias < 1 ulp, 25 % slower)
  *   "backptr"     0 (default): reference back-pointer composition (include/DistanceTransform.hpp:232-244),
  *                 1: true 2-D argmax composition
  *   "max_levels"  0 (default) = all pyramid levels, n = only the first n (finest) levels
  *   "max_candidates" capacity of the candidate buffer per batch (default 65536)
  *   "timing"      1: record per-stage CUDA events (pbd_stage_times_ms); disables the chunked H2D/pyramid overlap
- * Environment defaults read at pbd_create: PBD_EXACT=0|1, PBD_BACKPTR=reference|exact, PBD_MAX_LEVELS=n. */
+ * Environment defaults read at pbd_create: PBD_EXACT=0|1, PBD_RESPONSE_MODE=exact|ffma|tensor, PBD_BACKPTR=reference|exact,
+ * PBD_MAX_LEVELS=n. */
 int pbd_set_option(pbd_detector* d, const char* key, double value);
 int pbd_get_option(const pbd_detector* d, const char* key, double* value);
 
@@ -188,6 +196,9 @@ long long pbd_launch_count(const pbd_detector* d);
 /* per-stage device time of the last pbd_detect_batch / pbd_enqueue call, measured with CUDA events on the
  * detector's stream: ms[0..5] = h2d, pyramid, hog, pdf, dp_min, argmin.  Enabled by option "timing"=1. */
 int pbd_stage_times_ms(pbd_detector* d, float ms[6]);
+/* "timing" = 2 additionally records an event after every kernel of the pdf and dp_min stages; device time of the last batch per
+ * kernel (summed over the waves of the DP): 0 feat_split, 1 part_response, 2 dt_pass rows, 3 dt_pass columns, 4 mix_max, 5 root_select */
+int pbd_kernel_times_ms(pbd_detector* d, float ms[6]);
 /* device bytes currently held by the detector */
 size_t pbd_device_bytes(const pbd_detector* d);
 

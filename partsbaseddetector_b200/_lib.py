@@ -30,7 +30,7 @@ EXPORTS = [
     "pbd_pyramid_geometry", "pbd_num_frames", "pbd_num_levels", "pbd_level_info", "pbd_get_pyramid_image", "pbd_get_features",
     "pbd_get_response", "pbd_get_rootv", "pbd_get_rooti", "pbd_get_backptr", "pbd_set_levels",
     "pbd_set_features", "pbd_set_response", "pbd_dt2d_f32_device", "pbd_dt2d_f32", "pbd_launch_count",
-    "pbd_stage_times_ms", "pbd_device_bytes",
+    "pbd_stage_times_ms", "pbd_kernel_times_ms", "pbd_device_bytes",
 ]
 
 
@@ -115,6 +115,7 @@ def lib():
     L.pbd_launch_count.argtypes = [vp]
     L.pbd_launch_count.restype = C.c_longlong
     L.pbd_stage_times_ms.argtypes = [vp, _f32p]
+    L.pbd_kernel_times_ms.argtypes = [vp, _f32p]
     L.pbd_device_bytes.argtypes = [vp]
     L.pbd_device_bytes.restype = C.c_size_t
     _lib = L

@@ -170,7 +170,7 @@ int pbd_set_option(pbd_detector* d, const char* key, double value) {
     else if (k == "backptr") { REQUIRE(value == 0 || value == 1, "backptr must be 0 or 1"); e.backptr = (int)value; }
     else if (k == "max_levels") { REQUIRE(value >= 0, "max_levels must be >= 0"); e.max_levels = (int)value; }
     else if (k == "max_candidates") { REQUIRE(value >= 1 && value <= (1 << 24), "max_candidates out of range"); e.max_candidates = (int)value; }
-    else if (k == "timing") e.timing = value != 0;
+    else if (k == "timing") e.timing = value >= 2 ? 2 : (value != 0);
     else throw ArgError("unknown option '" + k + "'");
   });
 }
@@ -477,6 +477,7 @@ int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, 
 
 long long pbd_launch_count(const pbd_detector* d) { return d ? d->e->launches() : 0; }
 int pbd_stage_times_ms(pbd_detector* d, float ms[6]) { return guarded([&] { REQUIRE(d && ms, "null argument"); d->e->stage_times(ms); }); }
+int pbd_kernel_times_ms(pbd_detector* d, float ms[6]) { return guarded([&] { REQUIRE(d && ms, "null argument"); d->e->kernel_times(ms); }); }
 size_t pbd_device_bytes(const pbd_detector* d) { return d ? d->e->device_bytes() : 0; }
 
 }  // extern "C"

@@ -365,17 +365,20 @@ static int pass_warps(const PassGeom& pg, int nmaps) {
 int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
-                   cudaStream_t s) {
+                   cudaStream_t s, void (*mark)(void*, int), void* mark_ctx) {
   if (nmaps <= 0 || njobs <= 0 || g.cells_total <= 0) return 0;
   const size_t ct = (size_t)g.cells_total;
   dim3 gr((pass_warps(pg_rows, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
   launch_pass(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
               ct * tmp_maps, b.ixdt, ct * ncm);
+  if (mark) mark(mark_ctx, 2);
   dim3 gc((pass_warps(pg_cols, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
   launch_pass(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
               ct * tmp_maps, b.iyraw, ct * ncm);
+  if (mark) mark(mark_ctx, 3);
   dim3 gm((g.cells_total + 255) / 256, njobs, g.n_frames);
   mix_max<<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
+  if (mark) mark(mark_ctx, 4);
   return 3;
 }
 

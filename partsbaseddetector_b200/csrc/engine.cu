@@ -94,6 +94,31 @@ Engine::~Engine() {
   if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
   if (copy_stream_) { cudaStreamDestroy(copy_stream_); for (auto& e : copy_ev_) cudaEventDestroy(e); cudaEventDestroy(main_ev_); }
   for (int i = 0; i < 7; ++i) if (ev_[i]) cudaEventDestroy(ev_[i]);
+  for (cudaEvent_t e : kev_) cudaEventDestroy(e);
+}
+
+// timing == 2: records an event that closes the interval of kernel `tag` (-1 opens the first interval)
+void Engine::kmark(int tag) {
+  if (timing < 2) return;
+  if (kev_n_ == kev_.size()) {
+    cudaEvent_t e;
+    check_cuda(cudaEventCreate(&e), "cudaEventCreate");
+    kev_.push_back(e); kev_tag_.push_back(-1);
+  }
+  kev_tag_[kev_n_] = tag;
+  check_cuda(cudaEventRecord(kev_[kev_n_++], stream_), "event");
+}
+
+void Engine::kernel_times(float ms[kKernelTimes]) {
+  for (int i = 0; i < kKernelTimes; ++i) ms[i] = 0.f;
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+  for (size_t i = 1; i < kev_n_; ++i) {
+    const int tag = kev_tag_[i];
+    if (tag < 0 || tag >= kKernelTimes) continue;
+    float t = 0.f;
+    check_cuda(cudaEventElapsedTime(&t, kev_[i - 1], kev_[i]), "event elapsed");
+    ms[tag] += t;
+  }
 }
 
 // Model -> device tables: filters (convertTo float, reference src/PartsBasedDetector.cpp:115-117), the DP job
@@ -587,14 +612,19 @@ void Engine::run_pdf() {
   if (resp_mode == 2 && response_tc_supported(fb_)) {
     ensure_tc();
     if (timing) { check_cuda(cudaEventRecord(ev_[3], stream_), "event"); ev_valid_[3] = true; }
+    kev_n_ = 0; kmark(-1);
     launches_ += launch_feat_split(g_, d_g_, d_tc_levels_, b_.feat, d_fhi_, d_flo_, tc_frame_rows_, stream_);
+    kmark(0);
     launches_ += launch_response_tc(g_, b_, fb_, d_fhi_, d_flo_, d_wtc_, d_tc_levels_, d_tc_tiles_, tc_ntiles_, tc_frame_rows_, num_sms_, tc_taps_per_partial, stream_);
+    kmark(1);
     check_cuda(cudaGetLastError(), "tensor response launch");
     stage_ = 3;
     return;
   }
   if (timing) { check_cuda(cudaEventRecord(ev_[3], stream_), "event"); ev_valid_[3] = true; }
+  kev_n_ = 0; kmark(-1);
   launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles_, resp_mode == 0 ? 1 : 0, feat_from_hog_ ? 1 : 0, stream_);
+  kmark(1);
   check_cuda(cudaGetLastError(), "response launch");
   stage_ = 3;
 }
@@ -603,14 +633,18 @@ void Engine::run_dp_min() {
   need(3, "dp_min");
   if (timing) { check_cuda(cudaEventRecord(ev_[4], stream_), "event"); ev_valid_[4] = true; }
   const int nf = model_.nfilters();
+  if (kev_n_ > 4096) kev_n_ = 0;          // dp_min re-run many times without a pdf stage in between
+  kmark(-1);
+  auto mark = [](void* self, int tag) { static_cast<Engine*>(self)->kmark(tag); };
   for (size_t wv = 0; wv < wave_first_.size(); ++wv) {
     if (wave_count_[wv] == 0) continue;
     launches_ += launch_dt_wave(g_, d_g_, b_, pg_rows_, d_pg_, pg_cols_, d_pg_ + 1, d_maps_rows_ + wave_map_first_[wv],
                                 d_maps_cols_ + wave_map_first_[wv], wave_map_count_[wv], max_ow_, max_oh_, d_jobs_ + wave_first_[wv],
-                                wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, stream_);
+                                wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, stream_, timing >= 2 ? +mark : nullptr, this);
   }
   // root scores (reference computes rootv/rooti at the end of min(), src/DynamicProgram.cpp:163-171)
   launches_ += launch_root(g_, d_g_, b_, d_roots_, model_.ncomponents(), nf, nwork_, stream_);
+  kmark(5);
   check_cuda(cudaGetLastError(), "DP launch");
   stage_ = 4;
 }

@@ -91,6 +91,10 @@ class Engine {
   long long launches() const { return launches_; }
   size_t device_bytes() const { return dev_bytes_; }
   void stage_times(float ms[6]);
+  // per-kernel device time of the last batch run with timing == 2 (summed over the waves of the DP):
+  // 0 feat_split, 1 part_response, 2 dt_pass rows, 3 dt_pass cols, 4 mix_max, 5 root_select
+  static constexpr int kKernelTimes = 6;
+  void kernel_times(float ms[kKernelTimes]);
   cudaStream_t stream() const { return stream_; }
   int device() const { return device_; }
 
@@ -181,6 +185,11 @@ class Engine {
   // timing
   cudaEvent_t ev_[7] = {};
   bool ev_valid_[7] = {};
+  // timing == 2: one event after every kernel of the pdf / dp_min stages; kev_tag_[i] = kernel id of the interval ending at event i
+  std::vector<cudaEvent_t> kev_;
+  std::vector<int> kev_tag_;
+  size_t kev_n_ = 0;
+  void kmark(int tag);
 };
 
 // geometry helpers shared with the ABI (pyramid level table of HOGFeatures::pyramid)

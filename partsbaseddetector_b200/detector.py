@@ -448,6 +448,12 @@ class PartsBasedDetector:
         _lib.check(_lib.lib().pbd_stage_times_ms(self.handle, ms))
         return dict(zip(["h2d", "pyramid", "hog", "pdf", "dp_min", "argmin"], [float(x) for x in ms]))
 
+    def kernel_times_ms(self):
+        """Per-kernel device time of the last batch run with set_option("timing", 2)."""
+        ms = np.zeros(6, np.float32)
+        _lib.check(_lib.lib().pbd_kernel_times_ms(self.handle, ms))
+        return dict(zip(["feat_split", "part_response", "dt_rows", "dt_cols", "mix_max", "root_select"], [float(x) for x in ms]))
+
     def device_bytes(self):
         return int(_lib.lib().pbd_device_bytes(self.handle))
 
