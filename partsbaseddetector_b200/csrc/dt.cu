@@ -248,33 +248,66 @@ __global__ void __launch_bounds__(128) dt_build_tables(const PassMap* __restrict
 // ---------------------------------------------------------------------------------------------------
 // Mixture maximum + parent accumulate (src/DynamicProgram.cpp:134-156), elementwise over all cells of all levels.
 // ---------------------------------------------------------------------------------------------------
+// V = cells per thread: 4 (128-bit loads / stores, one 32-bit store of four Ik bytes) when cells_total is a multiple of 4 so that
+// every map base stays 16-byte aligned, else 1.  The job's bias matrix and slot tables are staged in shared memory once per block.
+template <int V>
 __global__ void __launch_bounds__(256)
 mix_max(const Geometry* __restrict__ g, const PartJob* __restrict__ jobs, const float* __restrict__ resp, float* __restrict__ work,
         const float* __restrict__ val, unsigned char* __restrict__ ik, int nfilters, int nwork, int npm, int tmp_maps) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ PartJob J;
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + blockIdx.y);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = threadIdx.x; i < (int)(sizeof(PartJob) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (idx >= g->cells_total) return;
-  const PartJob& J = jobs[blockIdx.y];
   const int frame = blockIdx.z;
   const size_t ct = (size_t)g->cells_total;
   const int nmix = J.nmix, pnmix = J.pnmix;
-  float v[kMaxMix];
+  float v[kMaxMix][V];
 #pragma unroll
-  for (int mm = 0; mm < kMaxMix; ++mm)
-    v[mm] = mm < nmix ? __ldg(val + ((size_t)frame * tmp_maps + J.tmp_base + mm) * ct + idx) : 0.f;
+  for (int mm = 0; mm < kMaxMix; ++mm) {
+    if (mm < nmix) {
+      const float* p = val + ((size_t)frame * tmp_maps + J.tmp_base + mm) * ct + idx;
+      if (V == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[mm][0] = t.x; v[mm][1 % V] = t.y; v[mm][2 % V] = t.z; v[mm][3 % V] = t.w;
+      } else {
+        v[mm][0] = __ldg(p);
+      }
+    }
+  }
   for (int pm = 0; pm < pnmix; ++pm) {
-    float best = -INFINITY;
-    int bi = 0;
+    float best[V];
+    int bi[V];
+#pragma unroll
+    for (int c = 0; c < V; ++c) { best[c] = -INFINITY; bi[c] = 0; }
 #pragma unroll
     for (int mm = 0; mm < kMaxMix; ++mm) {
       if (mm < nmix) {
-        const float wv = __fadd_rn(v[mm], J.bias[mm][pm]);         // scoresp[mm] + bias(mm)[m], :139
-        if (wv > best) { best = wv; bi = mm; }                      // reduceMax: strict >, first wins
+        const float bs = J.bias[mm][pm];
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+          const float wv = __fadd_rn(v[mm][c], bs);                 // scoresp[mm] + bias(mm)[m], :139
+          if (wv > best[c]) { best[c] = wv; bi[c] = mm; }           // reduceMax: strict >, first wins
+        }
       }
     }
-    ik[((size_t)frame * npm + J.pm_slot[pm]) * ct + idx] = (unsigned char)bi;
+    unsigned char* ikp = ik + ((size_t)frame * npm + J.pm_slot[pm]) * ct + idx;
     float* wp = work + ((size_t)frame * nwork + J.out_work_slot[pm]) * ct + idx;
-    const float base = J.first_touch ? __ldg(resp + ((size_t)frame * nfilters + J.out_resp_fid[pm]) * ct + idx) : *wp;
-    *wp = __fadd_rn(base, best);                                    // parent.score += maxv, :155-156
+    const float* bp = J.first_touch ? resp + ((size_t)frame * nfilters + J.out_resp_fid[pm]) * ct + idx : wp;
+    if (V == 4) {
+      *reinterpret_cast<uchar4*>(ikp) = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1 % V], (unsigned char)bi[2 % V], (unsigned char)bi[3 % V]);
+      const float4 b4 = *reinterpret_cast<const float4*>(bp);
+      float4 o;                                                     // parent.score += maxv, :155-156
+      o.x = __fadd_rn(b4.x, best[0]); o.y = __fadd_rn(b4.y, best[1 % V]); o.z = __fadd_rn(b4.z, best[2 % V]); o.w = __fadd_rn(b4.w, best[3 % V]);
+      *reinterpret_cast<float4*>(wp) = o;
+    } else {
+      *ikp = (unsigned char)bi[0];
+      *wp = __fadd_rn(*bp, best[0]);
+    }
   }
 }
 
@@ -376,8 +409,13 @@ int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
   launch_pass(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
               ct * tmp_maps, b.iyraw, ct * ncm);
   if (mark) mark(mark_ctx, 3);
-  dim3 gm((g.cells_total + 255) / 256, njobs, g.n_frames);
-  mix_max<<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
+  if (g.cells_total % 4 == 0) {
+    dim3 gm((g.cells_total / 4 + 255) / 256, njobs, g.n_frames);
+    mix_max<4><<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
+  } else {
+    dim3 gm((g.cells_total + 255) / 256, njobs, g.n_frames);
+    mix_max<1><<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
+  }
   if (mark) mark(mark_ctx, 4);
   return 3;
 }

@@ -98,13 +98,16 @@ __device__ __forceinline__ float tf32_rna(float v) {
 __global__ void __launch_bounds__(256)
 feat_split(const Geometry* __restrict__ g, const TcLevel* __restrict__ lv, const float* __restrict__ feat, float* __restrict__ fhi,
            float* __restrict__ flo, long long frame_rows) {
-  const int l = blockIdx.y, frame = blockIdx.z;
+  const int frame = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;        // (cell of the frame, 16-byte chunk)
+  const int gcell = i >> 3, c = i & 7;
+  if (gcell >= g->cells_total) return;
+  int l = 0;
+  while (l + 1 < g->n_levels && gcell >= g->lv[l + 1].cell_off) ++l;
   const LevelDesc& L = g->lv[l];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;        // (cell, chunk)
-  const int cell = i >> 3, c = i & 7;
-  if (cell >= L.ow * L.oh) return;
+  const int cell = gcell - L.cell_off;
   const int y = cell / L.ow, x = cell - y * L.ow;
-  const float4 v = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)frame * g->cells_total + L.cell_off + cell) * 32) + c);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)frame * g->cells_total + gcell) * 32) + c);
   const long long P = (long long)frame * frame_rows + lv[l].R + (long long)y * lv[l].Wp + x;
   float4 h, o;
   h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
@@ -376,10 +379,8 @@ long long response_tc_plan(const Geometry& g, int kh, int kw, std::vector<TcLeve
 
 int launch_feat_split(const Geometry& g, const Geometry* d_g, const TcLevel* d_levels, const float* feat, float* fhi, float* flo, long long frame_rows,
                       cudaStream_t s) {
-  int maxc = 0;
-  for (int l = 0; l < g.n_levels; ++l) maxc = std::max(maxc, g.lv[l].ow * g.lv[l].oh);
-  if (maxc == 0) return 0;
-  dim3 grid((maxc * 8 + 255) / 256, g.n_levels, g.n_frames);
+  if (g.cells_total <= 0) return 0;
+  dim3 grid((g.cells_total * 8 + 255) / 256, g.n_frames);
   feat_split<<<grid, 256, 0, s>>>(d_g, d_levels, feat, fhi, flo, frame_rows);
   return 1;
 }
