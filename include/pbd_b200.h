@@ -94,9 +94,13 @@ void pbd_destroy(pbd_detector* d);
  *                 1: true 2-D argmax composition
  *   "max_levels"  0 (default) = all pyramid levels, n = only the first n (finest) levels
  *   "max_candidates" capacity of the candidate buffer per batch (default 65536)
- *   "timing"      1: record per-stage CUDA events (pbd_stage_times_ms); disables the chunked H2D/pyramid overlap
+ *   "timing"      1: record per-stage CUDA events (pbd_stage_times_ms); disables the chunked H2D/pyramid overlap;
+ *                 2: additionally one event after every kernel of the pdf / dp_min stages (pbd_kernel_times_ms)
+ *   "dp_streams"  1..8 (default 2): the DP stage processes the batch as this many groups of frames on concurrent CUDA streams
+ *                 (forked from and joined back into the detector's stream) so that kernel tails of one group overlap the
+ *                 other's work; results do not depend on it.  Batches under 8 frames and timing == 2 use one stream.
  * Environment defaults read at pbd_create: PBD_EXACT=0|1, PBD_RESPONSE_MODE=exact|ffma|tensor, PBD_BACKPTR=reference|exact,
- * PBD_MAX_LEVELS=n. */
+ * PBD_MAX_LEVELS=n, PBD_DP_STREAMS=n. */
 int pbd_set_option(pbd_detector* d, const char* key, double value);
 int pbd_get_option(const pbd_detector* d, const char* key, double* value);
 

@@ -53,9 +53,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(SO_PATH):
+    path = os.environ.get("PBD_B200_LIB") or SO_PATH      # developer knob: A/B a differently compiled build of the same library
+    if path == SO_PATH and not os.path.exists(SO_PATH):
         build()
-    L = C.CDLL(SO_PATH)
+    L = C.CDLL(path)
     vp, ci, cf, cd = C.c_void_p, C.c_int, C.c_float, C.c_double
     P = C.POINTER
     L.pbd_last_error.restype = C.c_char_p

@@ -153,6 +153,7 @@ int pbd_create(const pbd_model* m, int device, void* stream, pbd_detector** out)
     }
     if (const char* v = getenv("PBD_BACKPTR")) d->e->backptr = (strcmp(v, "exact") == 0 || strcmp(v, "1") == 0) ? 1 : 0;
     if (const char* v = getenv("PBD_MAX_LEVELS")) d->e->max_levels = std::max(0, atoi(v));
+    if (const char* v = getenv("PBD_DP_STREAMS")) d->e->dp_streams = std::min(8, std::max(1, atoi(v)));
     *out = d.release();
   });
 }
@@ -171,6 +172,7 @@ int pbd_set_option(pbd_detector* d, const char* key, double value) {
     else if (k == "max_levels") { REQUIRE(value >= 0, "max_levels must be >= 0"); e.max_levels = (int)value; }
     else if (k == "max_candidates") { REQUIRE(value >= 1 && value <= (1 << 24), "max_candidates out of range"); e.max_candidates = (int)value; }
     else if (k == "timing") e.timing = value >= 2 ? 2 : (value != 0);
+    else if (k == "dp_streams") { REQUIRE(value >= 1 && value <= 8, "dp_streams must be 1..8"); e.dp_streams = (int)value; }
     else throw ArgError("unknown option '" + k + "'");
   });
 }
@@ -187,6 +189,7 @@ int pbd_get_option(const pbd_detector* d, const char* key, double* value) {
     else if (k == "max_levels") *value = e.max_levels;
     else if (k == "max_candidates") *value = e.max_candidates;
     else if (k == "timing") *value = e.timing;
+    else if (k == "dp_streams") *value = e.dp_streams;
     else throw ArgError("unknown option '" + k + "'");
   });
 }

@@ -25,11 +25,14 @@
 #include <algorithm>
 #include <cfloat>
 #include "kernels.cuh"
+#include "dt_envelope.cuh"
 
 namespace pbd {
 namespace {
 
-constexpr int kRing = 8;          // ring window (stack entries kept in shared memory per lane)
+using env::Ring;
+using env::Quad;
+static_assert(env::kRcp == kDtRcp && env::kTabPad == kDtTabPad, "table layout constants of kernels.cuh and dt_envelope.cuh differ");
 constexpr int kPassWarps = 4;
 constexpr int kTileW = 16;        // samples per line staged per shared-memory tile
 
@@ -40,125 +43,13 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-struct Quad {
-  double a, b, a2;   // a2 = 2*a (exact), reference evaluates 2*a*(x1-x0) left to right
-  double r1;         // correctly rounded 1/(2a): reciprocal of the divisor for adjacent samples (x1-x0 = 1)
-  const double* E;   // E[x] = a*x^2 + b*x (both products and the sum rounded as the reference does), x = pos - v
-};
-__device__ __forceinline__ Quad make_quad(const PassMap& M) {
-  Quad f;
-  f.a = (double)(-M.w_sq);          // Quadratic(-w[0], -w[1]), src/DynamicProgram.cpp:126-127
-  f.b = (double)(-M.w_lin);
-  f.a2 = __dmul_rn(2.0, f.a);
-  f.r1 = __drcp_rn(f.a2);
-  f.E = M.etab + M.tab_bias;
-  return f;
-}
-// the rare exact quotient: kept out of line so that the common path does not carry the division's instructions
-__device__ __noinline__ float quotient_exact(double num, double den) { return (float)__ddiv_rn(num, den); }
-
-// Quadratic::operator()(x0,x1,y0,y1), include/DistanceTransform.hpp:98-100, result rounded to float as `T s = f(...)`,
-// for adjacent samples x1 = x0 + 1 (the first intersection of every step: the previous sample is always the top).
-// b*1 = b and a*(x1^2-x0^2) = a*(2*x1-1) are the reference's own values; the quotient num/(2a) is formed with a Markstein
-// correction step from the precomputed reciprocal.  It is within 1 ulp(double) of the correctly rounded quotient, so its
-// float rounding equals the reference's double-division-then-float unless it lies within 2 ulp of a float rounding
-// boundary (probability ~2^-27): those cases, and anything outside 2^-100..2^100, take the exact division.
-__device__ __forceinline__ float isect_adjacent(const Quad& f, int x1, double y0, double y1) {
-  const double num = __dadd_rn(__dsub_rn(__dsub_rn(y1, y0), f.b), __dmul_rn(f.a, (double)(2 * x1 - 1)));
-  const double q0 = __dmul_rn(num, f.r1);
-  const double q1 = __fma_rn(__fma_rn(-f.a2, q0, num), f.r1, q0);
-  const int lo = __double2loint(q1) & 0x1FFFFFFF;
-  const unsigned ex = ((unsigned)__double2hiint(q1) & 0x7ff00000u) - ((1023u - 100u) << 20);
-  if (ex <= (200u << 20) && abs(lo - 0x10000000) > 2) return (float)q1;
-  return quotient_exact(num, f.a2);
-}
-// the general case (after a pop x1 - x0 >= 2)
-__device__ __forceinline__ float isect_far(const Quad& f, int x0, int x1, double y0, double y1) {
-  const double dd = (double)(x1 - x0);
-  const double t = __dsub_rn(__dsub_rn(y1, y0), __dmul_rn(f.b, dd));
-  const double num = __dadd_rn(t, __dmul_rn(f.a, (double)(x1 * x1 - x0 * x0)));
-  return (float)__ddiv_rn(num, __dmul_rn(f.a2, dd));
-}
-
-// base[idx] accesses with a 32-bit index: one IMAD.WIDE forms the address (the compiler otherwise re-derives the 64-bit
-// base from its kernel-parameter components at every store)
-__device__ __forceinline__ double ld_table(const double* base, int idx) {
-  double v;
-  asm("{ .reg .u64 a; mad.wide.s32 a, %2, 8, %1; ld.global.nc.f64 %0, [a]; }" : "=d"(v) : "l"(base), "r"(idx));
-  return v;
-}
+// base[idx] stores with a 32-bit index (the compiler otherwise re-derives the 64-bit base from its kernel-parameter
+// components at every store)
 __device__ __forceinline__ void st_f32(float* base, unsigned idx, float v) {
   asm volatile("{ .reg .u64 a; mad.wide.u32 a, %1, 4, %0; st.global.f32 [a], %2; }" ::"l"(base), "r"(idx), "f"(v) : "memory");
 }
 __device__ __forceinline__ void st_u16(unsigned short* base, unsigned idx, unsigned short v) {
   asm volatile("{ .reg .u64 a; mad.wide.u32 a, %1, 2, %0; st.global.u16 [a], %2; }" ::"l"(base), "r"(idx), "h"(v) : "memory");
-}
-
-// per-warp shared-memory ring: [slot][lane]; vp = v | (v of the entry below << 16), 0xFFFF = none
-struct Ring {
-  float z[kRing][32];
-  float y[kRing][32];
-  unsigned int vp[kRing][32];
-};
-
-// One lane's 1-D transform.  loady(q) = src[q] (called for q = 0..N-1 in order, and again for deep-pop reloads);
-// emit(i, val, v) stores dst[i] = val, ptr[i] = v (may be called more than once for an i; the last call wins).
-//
-// Eager emission: when sample q is pushed with break point s, the previous top P (still in registers) owns exactly the
-// integer positions z_P < pos <= s, and they are evaluated and stored at once.  If q (or P) is popped later, the positions
-// are simply stored again by their new owner: every position's FINAL owner E_i emits when its final successor E_{i+1} is
-// pushed, and since break points increase up the stack no later emission (all above E_{i+1}) can touch a position
-// <= z_{E_{i+1}}, so the last store to every position is the reference's scan result.
-//
-// The ring holds the newest 8 stack entries for pops (5-8 % of the steps); zb/pb are the backing store of the whole
-// envelope as a linked list threaded through the sample index (zb[q] = break point of the parabola pushed at q,
-// pb[q] = the sample below it), written in lock step across lanes (coalesced) and read only by pops deeper than the ring.
-template <typename LoadY, typename Reload, typename Emit>
-__device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, unsigned stride, Ring& R, int lane, float* zb, unsigned short* pb,
-                                                LoadY loady, Reload reload, Emit emit) {
-  const int pos_last = os0 + N - 1;
-  auto emit_range = [&](float zlo, float zhi, int v, double yd) {
-    // integer positions with zlo < pos <= zhi, clipped to [os0, os0+N-1] (the float -> int conversions saturate, so the
-    // -inf / +inf break points of the bottom and the top need no special case); value = Quadratic::operator()(pos - v, y),
-    // :102-104, = (a x^2 + b x) + y with the parenthesis taken from the map's table
-    const int lo = max(min(__float2int_rd(zlo), pos_last) + 1, os0);
-    const int hi = min(__float2int_rd(zhi), pos_last);
-    int x = lo - v;
-    unsigned off = (unsigned)(lo - os0) * stride;
-#pragma unroll 1
-    for (int pos = lo; pos <= hi; ++pos, ++x, off += stride) emit(off, (float)__dadd_rn(ld_table(f.E, x), yd), v);
-  };
-  int k = 0, base = 0;                                            // stack depth of the top; lowest depth still valid in the ring
-  int vt = 0, pt = 0xFFFF;
-  float ytf = loady(0), zt = -INFINITY;
-  double yt = (double)ytf;
-  R.z[0][lane] = zt; R.y[0][lane] = ytf; R.vp[0][lane] = 0xFFFF0000u;
-  zb[0] = zt; pb[0] = 0xFFFF;
-  for (int q = 1; q < N; ++q) {                                   // :160-170
-    const float yqf = loady(q);
-    const double yq = (double)yqf;
-    float s = isect_adjacent(f, q, yt, yq);                       // the top is sample q - 1
-    while (s <= zt && k > 0) {
-      --k;
-      const int slot = k & (kRing - 1);
-      if (k < base) {                                             // popped below the ring: reload from the backing store
-        base = k;
-        const int vv = pt;                                        // the entry below the one just popped
-        R.vp[slot][lane] = (unsigned)vv | ((unsigned)pb[vv] << 16); R.z[slot][lane] = zb[vv]; R.y[slot][lane] = reload(vv);
-      }
-      const unsigned vp = R.vp[slot][lane];
-      vt = vp & 0xFFFF; pt = vp >> 16; ytf = R.y[slot][lane]; yt = (double)ytf; zt = R.z[slot][lane];
-      s = isect_far(f, vt, q, yt, yq);
-    }
-    emit_range(zt, s, vt, yt);                                   // the top's positions up to the new break point
-    ++k;
-    base = max(base, k - (kRing - 1));                            // the slot of depth k - kRing is overwritten
-    const int slot = k & (kRing - 1);
-    R.vp[slot][lane] = (unsigned)q | ((unsigned)vt << 16); R.y[slot][lane] = yqf; R.z[slot][lane] = s;
-    zb[q] = s; pb[q] = (unsigned short)vt;
-    pt = vt; vt = q; ytf = yqf; yt = yq; zt = s;
-  }
-  emit_range(zt, INFINITY, vt, yt);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -170,8 +61,11 @@ __device__ __forceinline__ void envelope_stream(int N, const Quad& f, int os0, u
 //   rows pass:  in [y][x] (responses / working scores) -> tmp  [x][y], ixdt  [x][y]
 //   cols pass:  in tmp [x][y]                           -> val  [y][x], iyraw [y][x]
 // ---------------------------------------------------------------------------------------------------
+#ifndef PBD_DT_MINBLOCKS
+#define PBD_DT_MINBLOCKS 6        // 80 registers: 6 CTAs of 4 warps per SM (7 CTAs at 72 registers measured 9 % slower)
+#endif
 template <int MAXN>
-__global__ void __launch_bounds__(kPassWarps * 32)
+__global__ void __launch_bounds__(kPassWarps * 32, PBD_DT_MINBLOCKS)
 dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int nmaps, const float* __restrict__ inA, size_t strideA,
         const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out, unsigned short* __restrict__ ptr,
         size_t stride_ptr) {
@@ -199,7 +93,7 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
   const float* src = (M.in_buf ? inB + (size_t)frame * strideB : inA + (size_t)frame * strideA) + M.in_off + cell_off + (size_t)line * N;
   float* dst = out + (size_t)frame * stride_out + M.out_off + cell_off + line;
   unsigned short* dp = ptr + (size_t)frame * stride_ptr + M.ptr_off + cell_off + line;
-  const Quad f = make_quad(M);
+  const Quad f = env::make_quad(M.w_sq, M.w_lin, M.etab + M.tab_bias, M.etab + (M.tab_len - kDtRcp));
   float zb[MAXN];
   unsigned short pb[MAXN];
   // Input staging: the warp's 32 lines are read kTileW samples at a time into a double-buffered shared-memory tile
@@ -230,19 +124,19 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
   auto reload = [&](int v) -> float { return __ldg(src + v); };
   // inactive lanes recompute the warp's first item and store the same values to the same addresses as lane 0
   asm volatile("" : "+l"(dst), "+l"(dp));                        // keep both bases as materialised 64-bit registers
-  envelope_stream(N, f, M.os, (unsigned)nlines, rings[wib], lane, zb, pb, loady, reload, [&](unsigned off, float val, int v) {
+  env::envelope_stream(N, f, M.os, (unsigned)nlines, rings[wib], lane, zb, pb, loady, reload, [&](unsigned off, float val, int v) {
     st_f32(dst, off, val); st_u16(dp, off, (unsigned short)v);
   });
 }
 
-// E[j] = a x^2 + b x for x = j - tab_bias, j in [0, tab_len): the position-independent part of Quadratic::operator()(x, y)
+// E[j] = a x^2 + b x for x = j - tab_bias, j in [0, tab_len - kDtRcp): the position-independent part of Quadratic::operator()(x, y);
+// the last kDtRcp entries are the reciprocals 1/(2a*dd) used by the pop path
 __global__ void __launch_bounds__(128) dt_build_tables(const PassMap* __restrict__ maps) {
   const PassMap M = maps[blockIdx.x];
   const double a = (double)(-M.w_sq), b = (double)(-M.w_lin);
-  for (int j = threadIdx.x; j < M.tab_len; j += blockDim.x) {
-    const int x = j - M.tab_bias;
-    M.etab[j] = __dadd_rn(__dmul_rn(a, (double)(x * x)), __dmul_rn(b, (double)x));
-  }
+  const int ne = M.tab_len - kDtRcp;
+  for (int j = threadIdx.x; j < M.tab_len; j += blockDim.x)
+    M.etab[j] = j < ne ? env::table_E(a, b, j - M.tab_bias) : env::table_rcp(a, j - ne);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -1,0 +1,211 @@
+// dt_envelope.cuh -- one lane's 1-D generalised distance transform (DistanceTransform<float>::computeRow, reference
+// include/DistanceTransform.hpp:152-182) in streaming form.  Included by dt.cu (device code) and, compiled by plain g++
+// with -ffp-contract=off, by tests/dt_envelope_host.cpp: the CPU suite drives exactly this control flow (ring overflow,
+// deep pops, table look-ups, reciprocal quotients) against the oracle before any GPU sees it.  Every floating-point
+// operation is an explicit round-to-nearest IEEE operation on both sides, so the two compilations agree bit for bit.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define PBD_ENV_FN __device__ __forceinline__
+#define PBD_ENV_NOINLINE __device__ __noinline__
+#else
+#define PBD_ENV_FN inline
+#define PBD_ENV_NOINLINE inline
+#endif
+
+namespace pbd {
+namespace env {
+
+constexpr int kRing = 8;          // ring window (stack entries kept in shared memory per lane)
+constexpr int kRcp = 32;          // reciprocals 1/(2a*dd) tabulated for sample distances dd < kRcp
+constexpr int kTabPad = 2;        // the two look-ahead entries past the largest offset a line can produce
+
+#if defined(__CUDA_ARCH__)
+PBD_ENV_FN double dadd(double a, double b) { return __dadd_rn(a, b); }
+PBD_ENV_FN double dsub(double a, double b) { return __dsub_rn(a, b); }
+PBD_ENV_FN double dmul(double a, double b) { return __dmul_rn(a, b); }
+PBD_ENV_FN double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+PBD_ENV_FN double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+PBD_ENV_FN double drcp(double a) { return __drcp_rn(a); }
+PBD_ENV_FN int f2i_floor(float v) { return __float2int_rd(v); }           // saturating, NaN -> 0
+PBD_ENV_FN int dlo(double v) { return __double2loint(v); }
+PBD_ENV_FN int dhi(double v) { return __double2hiint(v); }
+// base[idx] with a 32-bit index: one IMAD.WIDE forms the address
+PBD_ENV_FN double ld_table(const double* base, int idx) {
+  double v;
+  asm("{ .reg .u64 a; mad.wide.s32 a, %2, 8, %1; ld.global.nc.f64 %0, [a]; }" : "=d"(v) : "l"(base), "r"(idx));
+  return v;
+}
+#else
+PBD_ENV_FN double dadd(double a, double b) { return a + b; }
+PBD_ENV_FN double dsub(double a, double b) { return a - b; }
+PBD_ENV_FN double dmul(double a, double b) { return a * b; }
+PBD_ENV_FN double dfma(double a, double b, double c) { return std::fma(a, b, c); }
+PBD_ENV_FN double ddiv(double a, double b) { return a / b; }
+PBD_ENV_FN double drcp(double a) { return 1.0 / a; }
+PBD_ENV_FN int f2i_floor(float v) {
+  if (v != v) return 0;
+  if (v >= 2147483648.f) return INT32_MAX;
+  if (v <= -2147483648.f) return INT32_MIN;
+  return (int)std::floor(v);
+}
+PBD_ENV_FN int dlo(double v) { uint64_t u; std::memcpy(&u, &v, 8); return (int)(uint32_t)u; }
+PBD_ENV_FN int dhi(double v) { uint64_t u; std::memcpy(&u, &v, 8); return (int)(uint32_t)(u >> 32); }
+PBD_ENV_FN double ld_table(const double* base, int idx) { return base[idx]; }
+#endif
+PBD_ENV_FN int imin(int a, int b) { return a < b ? a : b; }
+PBD_ENV_FN int imax(int a, int b) { return a > b ? a : b; }
+
+struct Quad {
+  double a, b, a2;     // a2 = 2*a (exact), reference evaluates 2*a*(x1-x0) left to right
+  double r1;           // correctly rounded 1/(2a): reciprocal of the divisor for adjacent samples (x1-x0 = 1)
+  const double* E;     // E[x] = a*x^2 + b*x (both products and the sum rounded as the reference does), x = pos - v
+  const double* Rcp;   // Rcp[dd] = correctly rounded 1/RN(2a*dd), 1 <= dd < kRcp
+};
+// Quadratic(-w[0], -w[1]), reference src/DynamicProgram.cpp:126-127
+PBD_ENV_FN Quad make_quad(float w_sq, float w_lin, const double* E, const double* Rcp) {
+  Quad f;
+  f.a = (double)(-w_sq);
+  f.b = (double)(-w_lin);
+  f.a2 = dmul(2.0, f.a);
+  f.r1 = drcp(f.a2);
+  f.E = E;
+  f.Rcp = Rcp;
+  return f;
+}
+// table entries (dt_build_tables on the device, the host test fills its own copy with the same functions)
+PBD_ENV_FN double table_E(double a, double b, int x) { return dadd(dmul(a, (double)(x * x)), dmul(b, (double)x)); }
+PBD_ENV_FN double table_rcp(double a, int dd) { return dd > 0 ? drcp(dmul(dmul(2.0, a), (double)dd)) : 0.0; }
+
+// the rare exact quotient: kept out of line so that the common path does not carry the division's instructions
+PBD_ENV_NOINLINE float quotient_exact(double num, double den) { return (float)ddiv(num, den); }
+
+// (float)(num/den) given r = RN(1/den): q1 is the quotient after one Markstein correction step, within 1 ulp(double) of the
+// correctly rounded num/den, so its float rounding equals the reference's double-division-then-float unless it lies within
+// 2 ulp of a float rounding boundary (probability ~2^-27): those cases, and anything outside 2^-100..2^100 (zero, infinities,
+// NaN and every intermediate under/overflow included), take the exact division.
+PBD_ENV_FN float quotient_to_float(double num, double den, double r) {
+  const double q0 = dmul(num, r);
+  const double q1 = dfma(dfma(-den, q0, num), r, q0);
+  const int lo = dlo(q1) & 0x1FFFFFFF;
+  const unsigned ex = ((unsigned)dhi(q1) & 0x7ff00000u) - ((1023u - 100u) << 20);
+  const int d = lo - 0x10000000;
+  if (ex <= (200u << 20) && (d > 2 || d < -2)) return (float)q1;
+  return quotient_exact(num, den);
+}
+
+// Quadratic::operator()(x0,x1,y0,y1), include/DistanceTransform.hpp:98-100, result rounded to float as `T s = f(...)`,
+// for adjacent samples x1 = x0 + 1 (the first intersection of every step: the previous sample is always the top).
+// b*1 = b and a*(x1^2-x0^2) = a*(2*x1-1) are the reference's own values.
+PBD_ENV_FN float isect_adjacent(const Quad& f, int x1, double y0, double y1) {
+  const double num = dadd(dsub(dsub(y1, y0), f.b), dmul(f.a, (double)(2 * x1 - 1)));
+  return quotient_to_float(num, f.a2, f.r1);
+}
+// the general case (after a pop x1 - x0 >= 2): ((y1 - y0) - b (x1 - x0) + a (x1^2 - x0^2)) / (2 a (x1 - x0)), every operation
+// rounded as the reference's double expression (the integer factors are exact in double); the divisor's reciprocal is
+// tabulated for x1 - x0 < kRcp
+PBD_ENV_FN float isect_far(const Quad& f, int x0, int x1, double y0, double y1) {
+  const int ddi = x1 - x0;
+  const double dd = (double)ddi;
+  const double t = dsub(dsub(y1, y0), dmul(f.b, dd));
+  const double num = dadd(t, dmul(f.a, (double)(ddi * (x1 + x0))));
+  const double den = dmul(f.a2, dd);
+  if (ddi < kRcp) return quotient_to_float(num, den, ld_table(f.Rcp, ddi));
+  return quotient_exact(num, den);
+}
+
+// per-warp shared-memory ring: [slot][lane]; vp = v | (v of the entry below << 16), 0xFFFF = none
+struct Ring {
+  float z[kRing][32];
+  float y[kRing][32];
+  unsigned int vp[kRing][32];
+};
+
+// One lane's 1-D transform.  loady(q) = src[q] (called for q = 0..N-1 in order, in lock step across the warp); reload(v) =
+// src[v] for deep-pop reloads; emit(off, val, v) stores dst[off] = val, ptr[off] = v with off = (pos - os0) * stride (may be
+// called more than once for a position; the last call wins).
+//
+// Eager emission: when sample q is pushed with break point s, the previous top P (still in registers) owns exactly the
+// integer positions z_P < pos <= s, and they are evaluated and stored at once.  If q (or P) is popped later, the positions
+// are simply stored again by their new owner: every position's FINAL owner E_i emits when its final successor E_{i+1} is
+// pushed, and since break points increase up the stack no later emission (all above E_{i+1}) can touch a position
+// <= z_{E_{i+1}}, so the last store to every position is the reference's scan result (:171-181).
+//
+// The first position `lo` the top will emit is known as soon as the top is (floor of its own break point + 1), so the two
+// table entries most emissions need (a step emits 1.0 positions on average, rarely more than 2) are loaded one step ahead
+// (e0, e1): their latency hides behind the next step's intersection arithmetic.
+//
+// The ring holds the newest 8 stack entries for pops (2-3 % of the lane steps); zb/pb are the backing store of the whole
+// envelope as a linked list threaded through the sample index (zb[q] = break point of the parabola pushed at q,
+// pb[q] = the sample below it), written in lock step across lanes (coalesced) and read only by pops deeper than the ring.
+template <typename LoadY, typename Reload, typename Emit>
+PBD_ENV_FN void envelope_stream(int N, const Quad& f, int os0, unsigned stride, Ring& R, int lane, float* zb, unsigned short* pb,
+                                LoadY loady, Reload reload, Emit emit) {
+  const int pos_last = os0 + N - 1;
+  // positions lo..hi of parabola v (value y): Quadratic::operator()(pos - v, y), :102-104, = (a x^2 + b x) + y with the
+  // parenthesis taken from the map's table; e0 / e1 are the table entries of lo and lo + 1
+  auto emit_run = [&](int lo, int hi, int v, double yd, double e0, double e1) {
+    if (hi >= lo) {
+      unsigned off = (unsigned)(lo - os0) * stride;
+      emit(off, (float)dadd(e0, yd), v);
+      if (hi > lo) {
+        off += stride;
+        emit(off, (float)dadd(e1, yd), v);
+        int x = lo - v + 2;
+#pragma unroll 1
+        for (int pos = lo + 2; pos <= hi; ++pos, ++x) {
+          off += stride;
+          emit(off, (float)dadd(ld_table(f.E, x), yd), v);
+        }
+      }
+    }
+  };
+  int k = 0, base = 0;                                            // stack depth of the top; lowest depth still valid in the ring
+  int vt = 0, pt = 0xFFFF;                                        // the top's sample and the sample below it
+  float ytf = loady(0), zt = -INFINITY;
+  double yt = (double)ytf;
+  R.z[0][lane] = zt; R.y[0][lane] = ytf; R.vp[0][lane] = 0xFFFF0000u;
+  zb[0] = zt; pb[0] = 0xFFFF;
+  // first position the top owns: max(min(floor(zt), pos_last) + 1, os0) (the float -> int conversion saturates, so the
+  // -inf / +inf break points of the bottom and the top need no special case)
+  int lo = os0;
+  double e0 = ld_table(f.E, lo - vt), e1 = ld_table(f.E, lo - vt + 1);
+  for (int q = 1; q < N; ++q) {                                   // :160-170
+    const float yqf = loady(q);
+    const double yq = (double)yqf;
+    float s = isect_adjacent(f, q, yt, yq);                       // the top is sample q - 1
+    if (s <= zt && k > 0) {
+      do {
+        --k;
+        const int slot = k & (kRing - 1);
+        if (k < base) {                                           // popped below the ring: reload from the backing store
+          base = k;
+          const int vv = pt;                                      // the entry below the one just popped
+          R.vp[slot][lane] = (unsigned)vv | ((unsigned)pb[vv] << 16); R.z[slot][lane] = zb[vv]; R.y[slot][lane] = reload(vv);
+        }
+        const unsigned vp = R.vp[slot][lane];
+        vt = vp & 0xFFFF; pt = vp >> 16; ytf = R.y[slot][lane]; yt = (double)ytf; zt = R.z[slot][lane];
+        s = isect_far(f, vt, q, yt, yq);
+      } while (s <= zt && k > 0);
+      lo = imax(imin(f2i_floor(zt), pos_last) + 1, os0);
+      e0 = ld_table(f.E, lo - vt); e1 = ld_table(f.E, lo - vt + 1);
+    }
+    const int hi = imin(f2i_floor(s), pos_last);
+    emit_run(lo, hi, vt, yt, e0, e1);                             // the top's positions up to the new break point
+    ++k;
+    base = imax(base, k - (kRing - 1));                           // the slot of depth k - kRing is overwritten
+    const int slot = k & (kRing - 1);
+    R.vp[slot][lane] = (unsigned)q | ((unsigned)vt << 16); R.y[slot][lane] = yqf; R.z[slot][lane] = s;
+    zb[q] = s; pb[q] = (unsigned short)vt;
+    pt = vt; vt = q; ytf = yqf; yt = yq; zt = s;
+    lo = imax(hi + 1, os0);                                       // = max(min(floor(s), pos_last) + 1, os0)
+    e0 = ld_table(f.E, lo - q); e1 = ld_table(f.E, lo - q + 1);
+  }
+  emit_run(lo, pos_last, vt, yt, e0, e1);
+}
+
+}  // namespace env
+}  // namespace pbd

@@ -92,6 +92,9 @@ Engine::~Engine() {
   for (ResultSlot& S : slots_) if (S.done) cudaEventDestroy(S.done);
   for (auto& e : frames_free_ev_) if (e) cudaEventDestroy(e);
   if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
+  for (cudaStream_t st : dp_aux_) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : dp_join_) cudaEventDestroy(ev);
+  if (dp_fork_) cudaEventDestroy(dp_fork_);
   if (copy_stream_) { cudaStreamDestroy(copy_stream_); for (auto& e : copy_ev_) cudaEventDestroy(e); cudaEventDestroy(main_ev_); }
   for (int i = 0; i < 7; ++i) if (ev_[i]) cudaEventDestroy(ev_[i]);
   for (cudaEvent_t e : kev_) cudaEventDestroy(e);
@@ -636,11 +639,41 @@ void Engine::run_dp_min() {
   if (kev_n_ > 4096) kev_n_ = 0;          // dp_min re-run many times without a pdf stage in between
   kmark(-1);
   auto mark = [](void* self, int tag) { static_cast<Engine*>(self)->kmark(tag); };
+  // Frames are independent, so the batch is cut into `dp_streams` groups of frames whose waves run on separate streams: the
+  // tail of every launch (the last CTAs of the long level-0 lines) overlaps the other group's kernels instead of leaving SMs
+  // idle.  Per-kernel timing (timing == 2) keeps everything on one stream so that its intervals stay meaningful.
+  const int nsplit = (timing >= 2 || g_.n_frames < 2 * kMinFramesPerDpGroup) ? 1 : std::max(1, std::min(dp_streams, g_.n_frames / kMinFramesPerDpGroup));
+  const size_t ct = (size_t)g_.cells_total;
+  if (nsplit > 1) {
+    while ((int)dp_aux_.size() < nsplit - 1) {
+      cudaStream_t st; cudaEvent_t ev;
+      check_cuda(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
+      check_cuda(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+      dp_aux_.push_back(st); dp_join_.push_back(ev);
+    }
+    if (!dp_fork_) check_cuda(cudaEventCreateWithFlags(&dp_fork_, cudaEventDisableTiming), "cudaEventCreate");
+    check_cuda(cudaEventRecord(dp_fork_, stream_), "event");
+    for (int i = 0; i + 1 < nsplit; ++i) check_cuda(cudaStreamWaitEvent(dp_aux_[i], dp_fork_, 0), "wait");
+  }
   for (size_t wv = 0; wv < wave_first_.size(); ++wv) {
     if (wave_count_[wv] == 0) continue;
-    launches_ += launch_dt_wave(g_, d_g_, b_, pg_rows_, d_pg_, pg_cols_, d_pg_ + 1, d_maps_rows_ + wave_map_first_[wv],
-                                d_maps_cols_ + wave_map_first_[wv], wave_map_count_[wv], max_ow_, max_oh_, d_jobs_ + wave_first_[wv],
-                                wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, stream_, timing >= 2 ? +mark : nullptr, this);
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const int f0 = (int)((long long)g_.n_frames * sp / nsplit), f1 = (int)((long long)g_.n_frames * (sp + 1) / nsplit);
+      Geometry gs = g_;
+      gs.n_frames = f1 - f0;
+      DeviceBuffers bs = b_;
+      bs.resp += (size_t)f0 * ct * nf; bs.work += (size_t)f0 * ct * nwork_; bs.tmp += (size_t)f0 * ct * tmp_maps_; bs.val += (size_t)f0 * ct * tmp_maps_;
+      bs.ixdt += (size_t)f0 * ct * ncm_; bs.iyraw += (size_t)f0 * ct * ncm_; bs.ik += (size_t)f0 * ct * npm_;
+      const int n = launch_dt_wave(gs, d_g_, bs, pg_rows_, d_pg_, pg_cols_, d_pg_ + 1, d_maps_rows_ + wave_map_first_[wv],
+                                   d_maps_cols_ + wave_map_first_[wv], wave_map_count_[wv], max_ow_, max_oh_, d_jobs_ + wave_first_[wv],
+                                   wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, sp == 0 ? stream_ : dp_aux_[sp - 1],
+                                   timing >= 2 ? +mark : nullptr, this);
+      launches_ += n;
+    }
+  }
+  for (int i = 0; i + 1 < nsplit; ++i) {
+    check_cuda(cudaEventRecord(dp_join_[i], dp_aux_[i]), "event");
+    check_cuda(cudaStreamWaitEvent(stream_, dp_join_[i], 0), "wait");
   }
   // root scores (reference computes rootv/rooti at the end of min(), src/DynamicProgram.cpp:163-171)
   launches_ += launch_root(g_, d_g_, b_, d_roots_, model_.ncomponents(), nf, nwork_, stream_);

@@ -57,6 +57,9 @@ class Engine {
   // resp_mode: 0 exact (separately rounded multiply/add in the reference's order, bit-identical scores), 1 fused multiply-add,
   // 2 tensor cores (tf32x3 split products, fp32 accumulate; falls back to 1 for models the tensor kernel does not cover)
   int resp_mode = 0, tc_taps_per_partial = 0, backptr = 0, max_levels = 0, max_candidates = 65536, timing = 0;
+  // the DP stage runs the batch as this many groups of frames on concurrent streams (1 = single stream)
+  int dp_streams = 2;
+  static constexpr int kMinFramesPerDpGroup = 4;
 
   // ---- batch set-up ----
   void set_frames_geometry(int n, int h, int w, int c);                 // pyramid geometry of HOGFeatures::pyramid
@@ -174,6 +177,9 @@ class Engine {
   ResultSlot slots_[2];
   int cur_slot_ = 0;
   cudaStream_t d2h_stream_ = nullptr;
+  std::vector<cudaStream_t> dp_aux_;           // extra streams of the DP stage's frame groups
+  std::vector<cudaEvent_t> dp_join_;
+  cudaEvent_t dp_fork_ = nullptr;
   uint8_t* d_frames_alt_ = nullptr; size_t cap_frames_alt_ = 0;   // second frame buffer of the pipelined API
   cudaEvent_t frames_free_ev_[2] = {};         // recorded when the pyramid stage has consumed frame buffer 0 / 1
   int frames_buf_ = 0;

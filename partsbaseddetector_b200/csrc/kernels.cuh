@@ -140,12 +140,14 @@ struct PassMap {
   float w_sq, w_lin;           // deformation weights of this direction
   int os;                      // anchor of this direction
   // device table of the position-independent part of the parabola, etab[x + tab_bias] = a x^2 + b x for every
-  // x = pos - v a line of up to (tab_len + 1) / 2 samples can produce (filled by launch_dt_tables)
+  // x = pos - v a line of up to maxn samples can produce (+ kDtTabPad look-ahead entries), followed by kDtRcp reciprocals
+  // 1/(2a*dd); tab_len = dt_table_len(maxn) (filled by launch_dt_tables)
   double* etab;
   int tab_bias, tab_len;
 };
 // doubles a pass over lines of at most maxn samples needs per map, and the bias that goes with anchor `os`
-inline int dt_table_len(int maxn) { return 2 * maxn - 1; }
+constexpr int kDtTabPad = 2, kDtRcp = 32;     // look-ahead entries past the largest offset; tabulated reciprocals (dt_envelope.cuh)
+inline int dt_table_len(int maxn) { return 2 * maxn - 1 + kDtTabPad + kDtRcp; }
 inline int dt_table_bias(int maxn, int os) { return maxn - 1 - os; }
 int launch_dt_tables(const PassMap* d_maps, int nmaps, cudaStream_t s);
 int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,

@@ -1,0 +1,43 @@
+// Host build of the product's streaming envelope (partsbaseddetector_b200/csrc/dt_envelope.cuh) for the CPU test suite:
+// g++ -O2 -ffp-contract=off.  Test infrastructure only -- the product runs this header as device code inside dt_pass.
+#include <cstdint>
+#include <vector>
+
+#include "../partsbaseddetector_b200/csrc/dt_envelope.cuh"
+
+using namespace pbd::env;
+
+extern "C" {
+// 32 lines of N samples each (src[line][q]) go through one "warp": the lanes run one after the other over the same Ring
+// object (each lane only touches its own column).  maxn >= N sizes the tables exactly as the device does
+// (dt_table_len / dt_table_bias of kernels.cuh).  dst/ptr are written [line][pos - os]; every position not stored stays
+// at the caller's fill value.  *stores (optional) counts the emit calls.
+int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int os, int maxn, float* dst, uint16_t* ptr, long long* stores) {
+  if (N < 1 || N > maxn || nlines < 1 || nlines > 32) return -1;
+  const int ne = 2 * maxn - 1 + kTabPad, bias = maxn - 1 - os;
+  std::vector<double> tab(ne + kRcp);
+  const double a = (double)(-w_sq), b = (double)(-w_lin);
+  for (int j = 0; j < ne; ++j) tab[j] = table_E(a, b, j - bias);
+  for (int j = 0; j < kRcp; ++j) tab[ne + j] = table_rcp(a, j);
+  const Quad f = make_quad(w_sq, w_lin, tab.data() + bias, tab.data() + ne);
+  Ring R;
+  std::vector<float> zb(N);
+  std::vector<unsigned short> pb(N);
+  long long n = 0;
+  for (int lane = 0; lane < nlines; ++lane) {
+    const float* s = src + (size_t)lane * N;
+    float* d = dst + (size_t)lane * N;
+    uint16_t* p = ptr + (size_t)lane * N;
+    envelope_stream(N, f, os, 1u, R, lane, zb.data(), pb.data(), [&](int q) { return s[q]; }, [&](int v) { return s[v]; },
+                    [&](unsigned off, float val, int v) {
+                      if (off >= (unsigned)N) __builtin_trap();
+                      d[off] = val; p[off] = (uint16_t)v; ++n;
+                    });
+  }
+  if (stores) *stores = n;
+  return 0;
+}
+// the two quotient paths side by side (for the reciprocal / Markstein test)
+float envh_quotient_fast(double num, double den) { return quotient_to_float(num, den, drcp(den)); }
+float envh_quotient_exact(double num, double den) { return quotient_exact(num, den); }
+}

@@ -253,6 +253,38 @@ def test_batch_equals_single_frames_vga():
         assert g.score() == o["score"] and np.array_equal(g.parts(), o["rects"])
 
 
+@pytest.mark.parametrize("nframes", [8, 11, 17])
+def test_dp_frame_groups_on_concurrent_streams_do_not_change_results(nframes):
+    # the DP stage runs the batch as dp_streams groups of frames on concurrent streams (engine.cu run_dp_min): every output of
+    # every frame must equal the single-stream result bit for bit, and frame 0 / the last frame must equal the oracle
+    name = "Person_26parts"
+    frames = synth_frames(nframes, 120, 168, start=300)
+    d, O = detector(name), oracle(name)
+    O.run(frames[nframes - 1], 1, 3)
+    thr = lowered_threshold(O, 40)
+    d.set_option("thresh", thr)
+    ref = None
+    for ns in (1, 2, 3, 4):
+        d.set_option("dp_streams", ns)
+        assert d.get_option("dp_streams") == ns
+        cands = d.detect(frames)
+        got = {"cands": [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score())) for k in cands],
+               "rootv": [d.rootv(f, l).copy() for f in range(nframes) for l in range(d.nscales())],
+               "rooti": [d.rooti(f, l).copy() for f in range(nframes) for l in range(d.nscales())],
+               "bp": [np.stack(d.backptr(f, 0, 0, p, m)) for f in (0, nframes // 2, nframes - 1) for p, m in ((3, 2), (25, 0), (12, 4))]}
+        if ref is None:
+            ref = got
+            continue
+        assert got["cands"] == ref["cands"] and len(got["cands"]) > 0
+        for key in ("rootv", "rooti", "bp"):
+            assert all(np.array_equal(a, b) for a, b in zip(got[key], ref[key])), (ns, key)
+    for l in range(O.nlevels()):
+        assert np.array_equal(d.rootv(nframes - 1, l), O.rootv(l))
+    d.set_option("dp_streams", 2)
+    with pytest.raises(PbdError):
+        d.set_option("dp_streams", 0)
+
+
 def test_determinism_and_stage_api_equivalence():
     d = detector("Person_26parts")
     frames = synth_frames(2, 240, 320, start=7)
