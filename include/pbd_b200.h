@@ -50,6 +50,15 @@ const char* pbd_version(void);
  * The .pbdm binary format is this library's own compact container of the same fields. */
 int pbd_model_load_xml(const char* path, pbd_model** out);
 int pbd_model_save_xml(const pbd_model* m, const char* path);
+/* FileStorageModel as cv::FileStorage behaves: XML or YAML (%YAML:1.0 as OpenCV writes it), the parser chosen from the content, the
+ * writer from the extension (.yml / .yaml -> YAML, otherwise XML) */
+int pbd_model_load_storage(const char* path, pbd_model** out);
+int pbd_model_save_storage(const pbd_model* m, const char* path);
+/* replaces MatlabIOModel::deserialize (src/MatlabIOModel.cpp:71-188): reads the training code's `model` struct from a MATLAB
+ * Level-5 MAT-file (native reader: compressed variables, small elements, any numeric storage type; no cvmatio).  1-based ids
+ * become 0-based, filters w(m, n, c) are flattened to rows of n*C + c as the reference does; an empty (root) defid -> [0] as
+ * in pbd_model_load_xml.  PBD_E_IO if the file cannot be opened (the reference returns false), PBD_E_FORMAT otherwise. */
+int pbd_model_load_mat(const char* path, pbd_model** out);
 int pbd_model_load_bin(const char* path, pbd_model** out);
 int pbd_model_save_bin(const pbd_model* m, const char* path);
 /* hdr = {interval, sbin, norient, flen, nfilters, nbias, ndefs, ncomponents};

@@ -83,11 +83,25 @@ class Model {
 
 class FileStorageModel : public Model {     // reference src/FileStorageModel.cpp:42-159
  public:
-  bool serialize(const std::string& filename) const override { need(); check(pbd_model_save_xml(h_, filename.c_str())); return true; }
+  bool serialize(const std::string& filename) const override { need(); check(pbd_model_save_storage(h_, filename.c_str())); return true; }
   bool deserialize(const std::string& filename) override {
     pbd_model* m = nullptr;
-    const int rc = pbd_model_load_xml(filename.c_str(), &m);
+    const int rc = pbd_model_load_storage(filename.c_str(), &m);
     if (rc == PBD_E_IO) return false;           // cannot open: `if (!ok) return false;` (:100-101)
+    check(rc);
+    pbd_model_free(h_);
+    h_ = m;
+    return true;
+  }
+};
+
+class MatlabIOModel : public Model {        // reference src/MatlabIOModel.cpp:71-195 (native MAT-v5 reader, no cvmatio)
+ public:
+  bool serialize(const std::string&) const override { return false; }   // "TODO: implement" in the reference as well (:191-195)
+  bool deserialize(const std::string& filename) override {
+    pbd_model* m = nullptr;
+    const int rc = pbd_model_load_mat(filename.c_str(), &m);
+    if (rc == PBD_E_IO) return false;           // cannot open: `if (!ok) return false;` (:76-77)
     check(rc);
     pbd_model_free(h_);
     h_ = m;

@@ -20,7 +20,7 @@ _f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
 
 # every symbol include/pbd_b200.h declares (checked by tests/test_abi_symbols.py)
 EXPORTS = [
-    "pbd_last_error", "pbd_version", "pbd_model_load_xml", "pbd_model_save_xml", "pbd_model_load_bin",
+    "pbd_last_error", "pbd_version", "pbd_model_load_xml", "pbd_model_save_xml", "pbd_model_load_storage", "pbd_model_save_storage", "pbd_model_load_mat", "pbd_model_load_bin",
     "pbd_model_save_bin", "pbd_model_create", "pbd_model_free", "pbd_model_name", "pbd_model_header",
     "pbd_model_filter", "pbd_model_bias", "pbd_model_anchors", "pbd_model_defs", "pbd_model_nparts",
     "pbd_model_part", "pbd_create", "pbd_destroy", "pbd_set_option", "pbd_get_option", "pbd_detect_batch_u8",
@@ -62,6 +62,9 @@ def lib():
     L.pbd_last_error.restype = C.c_char_p
     L.pbd_version.restype = C.c_char_p
     L.pbd_model_load_xml.argtypes = [C.c_char_p, P(vp)]
+    L.pbd_model_load_mat.argtypes = [C.c_char_p, P(vp)]
+    L.pbd_model_load_storage.argtypes = [C.c_char_p, P(vp)]
+    L.pbd_model_save_storage.argtypes = [vp, C.c_char_p]
     L.pbd_model_save_xml.argtypes = [vp, C.c_char_p]
     L.pbd_model_load_bin.argtypes = [C.c_char_p, P(vp)]
     L.pbd_model_save_bin.argtypes = [vp, C.c_char_p]

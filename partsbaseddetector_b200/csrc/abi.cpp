@@ -44,6 +44,13 @@ int pbd_model_load_xml(const char* path, pbd_model** out) {
   return guarded([&] { REQUIRE(path && out, "null argument"); auto m = std::make_unique<pbd_model>(); load_xml(path, m->m); *out = m.release(); });
 }
 int pbd_model_save_xml(const pbd_model* m, const char* path) { return guarded([&] { REQUIRE(m && path, "null argument"); save_xml(m->m, path); }); }
+int pbd_model_load_storage(const char* path, pbd_model** out) {
+  return guarded([&] { REQUIRE(path && out, "null argument"); auto m = std::make_unique<pbd_model>(); load_storage(path, m->m); *out = m.release(); });
+}
+int pbd_model_save_storage(const pbd_model* m, const char* path) { return guarded([&] { REQUIRE(m && path, "null argument"); save_storage(m->m, path); }); }
+int pbd_model_load_mat(const char* path, pbd_model** out) {
+  return guarded([&] { REQUIRE(path && out, "null argument"); auto m = std::make_unique<pbd_model>(); load_mat(path, m->m); *out = m.release(); });
+}
 int pbd_model_load_bin(const char* path, pbd_model** out) {
   return guarded([&] { REQUIRE(path && out, "null argument"); auto m = std::make_unique<pbd_model>(); load_bin(path, m->m); *out = m.release(); });
 }

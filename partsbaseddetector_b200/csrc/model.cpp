@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <strings.h>
 #include <memory>
 #include <stdexcept>
 
@@ -167,19 +168,26 @@ void Model::validate() const {
   }
 }
 
+// the schema of FileStorageModel::serialize (reference src/FileStorageModel.cpp:42-94), from a parsed XML or YAML tree
+static void model_from_tree(const XNode* root, Model& m);
+
 void load_xml(const std::string& path, Model& m) {
   const std::string text = slurp(path);
   XParser xp(text);
   xp.skip_misc();
   std::unique_ptr<XNode> root = xp.element();
   if (root->name != "opencv_storage") throw FormatError("XML: root element is not <opencv_storage>");
+  model_from_tree(root.get(), m);
+}
+
+static void model_from_tree(const XNode* root, Model& m) {
   m = Model();
   if (const XNode* n = root->child("name")) m.name = trimmed(n);
-  m.interval = (int)scalar(root.get(), "interval");
-  m.thresh = (float)scalar(root.get(), "thresh");
-  m.sbin = (int)scalar(root.get(), "sbin");
-  m.norient = (int)scalar(root.get(), "norient");
-  m.flen = (int)scalar(root.get(), "flen");
+  m.interval = (int)scalar(root, "interval");
+  m.thresh = (float)scalar(root, "thresh");
+  m.sbin = (int)scalar(root, "sbin");
+  m.norient = (int)scalar(root, "norient");
+  m.flen = (int)scalar(root, "flen");
   const XNode* fw = root->child("filtersw");
   if (!fw) throw FormatError("XML: missing <filtersw>");
   for (auto& k : fw->kids) {
@@ -224,6 +232,177 @@ void load_xml(const std::string& path, Model& m) {
     m.comps.push_back(std::move(parts));
   }
   m.validate();
+}
+
+// ---- opencv_storage YAML (cv::FileStorage picks the format by file extension; %YAML:1.0 subset it writes) ----------
+namespace {
+struct YLine { int indent; char* b; char* e; };      // content without indentation / trailing white space
+
+struct YParser {
+  std::vector<YLine> lines;
+  size_t i = 0;
+  [[noreturn]] static void fail(const std::string& what) { throw FormatError("YAML: " + what); }
+
+  explicit YParser(std::string& text) {
+    char* p = &text[0];
+    char* end = p + text.size();
+    while (p < end) {
+      char* nl = (char*)memchr(p, '\n', end - p);
+      char* le = nl ? nl : end;
+      char* b = p;
+      while (b < le && *b == ' ') ++b;
+      char* e = le;
+      while (e > b && (e[-1] == ' ' || e[-1] == '\r' || e[-1] == '\t')) --e;
+      const bool skip = b == e || *b == '#' || *b == '%' || (e - b == 3 && (!strncmp(b, "---", 3) || !strncmp(b, "...", 3)));
+      if (!skip) lines.push_back({(int)(b - p), b, e});
+      p = nl ? nl + 1 : end;
+    }
+  }
+  // value text starting at v on the current line (index li): a flow collection may continue over the following lines; brackets
+  // and commas are blanked so that the numeric scanner sees white-space separated values
+  void leaf(XNode* n, char* v, char* le) {
+    if (v < le && (*v == '[' || *v == '{')) {
+      int depth = 0;
+      char* tb = v + 1;
+      for (;;) {
+        for (char* c = v; c < le; ++c) {
+          if (*c == '[' || *c == '{') { ++depth; *c = ' '; }
+          else if (*c == ']' || *c == '}') { --depth; *c = ' '; if (depth == 0) { n->tb = tb; n->te = c; return; } }
+          else if (*c == ',') *c = ' ';
+        }
+        *le = ' ';                                    // join the continuation line (the line break is ordinary white space)
+        if (++i >= lines.size()) fail("unterminated flow sequence");
+        v = lines[i].b; le = lines[i].e;
+      }
+    }
+    n->tb = v; n->te = le;
+  }
+  // after "key:" / "- " the rest of the line: optional !!tag, then a scalar / flow value, or nothing (a nested block follows)
+  void value(XNode* n, char* v, char* le, int indent) {
+    while (v < le && *v == ' ') ++v;
+    if (le - v >= 2 && v[0] == '!' && v[1] == '!') {
+      char* t = v + 2;
+      while (v < le && *v != ' ') ++v;
+      n->type_id.assign(t, v);
+      while (v < le && *v == ' ') ++v;
+    }
+    if (v < le) { leaf(n, v, le); ++i; return; }
+    ++i;
+    if (i < lines.size() && (lines[i].indent > indent || (lines[i].indent == indent && lines[i].e - lines[i].b >= 1 && lines[i].b[0] == '-' &&
+                                                          (lines[i].e - lines[i].b == 1 || lines[i].b[1] == ' '))))
+      block(n, lines[i].indent);
+    else { n->tb = n->te = le; }                       // empty value
+  }
+  static bool is_dash(const YLine& l) { return *l.b == '-' && (l.e - l.b == 1 || l.b[1] == ' '); }
+  void block(XNode* parent, int indent) {
+    const bool seq = i < lines.size() && is_dash(lines[i]);
+    while (i < lines.size() && lines[i].indent >= indent) {
+      if (lines[i].indent > indent) fail("unexpected indentation");
+      if (is_dash(lines[i]) != seq) {                   // a sequence written at its key's own indentation ends at the next key
+        if (seq) return;
+        fail("sequence item inside a mapping");
+      }
+      char* b = lines[i].b;
+      char* e = lines[i].e;
+      auto n = std::make_unique<XNode>();
+      if (seq) {                                        // sequence item
+        n->name = "_";
+        XNode* raw = n.get();
+        parent->kids.push_back(std::move(n));
+        // the item's nested map (if any) is indented relative to the dash
+        value(raw, b + 1, e, indent);
+      } else {
+        char* c = b;
+        while (c < e && !(*c == ':' && (c + 1 == e || c[1] == ' '))) ++c;
+        if (c == e) fail("expected 'key: value' in line '" + std::string(b, e) + "'");
+        n->name.assign(b, c);
+        XNode* raw = n.get();
+        parent->kids.push_back(std::move(n));
+        value(raw, c + 1, e, indent);
+      }
+    }
+  }
+};
+
+void yaml_number(FILE* f, double v) {
+  if (std::isnan(v)) { fputs(".Nan", f); return; }
+  if (std::isinf(v)) { fputs(v > 0 ? ".Inf" : "-.Inf", f); return; }
+  char buf[40];
+  snprintf(buf, sizeof(buf), "%.17g", v);
+  fputs(buf, f);
+  if (!strpbrk(buf, ".eE")) fputc('.', f);             // cv::FileStorage marks reals with a decimal point ("3.")
+}
+}  // namespace
+
+bool is_yaml_path(const std::string& path) {
+  auto ends = [&](const char* suf) { const size_t n = strlen(suf); return path.size() >= n && !strcasecmp(path.c_str() + path.size() - n, suf); };
+  return ends(".yml") || ends(".yaml");
+}
+
+void load_yaml(const std::string& path, Model& m) {
+  std::string text = slurp(path);
+  text.push_back('\n');
+  YParser yp(text);
+  XNode root;
+  root.name = "opencv_storage";
+  if (!yp.lines.empty()) yp.block(&root, yp.lines[0].indent);
+  model_from_tree(&root, m);
+}
+
+void load_storage(const std::string& path, Model& m) {
+  const std::string text = slurp(path);
+  size_t a = text.find_first_not_of(" \n\r\t");
+  if (a != std::string::npos && text[a] == '<') load_xml(path, m); else load_yaml(path, m);
+}
+
+void save_yaml(const Model& m, const std::string& path) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw IoError("cannot open '" + path + "' for writing: " + strerror(errno));
+  bool plain = !m.name.empty();
+  for (char ch : m.name) if (!isalnum((unsigned char)ch) && ch != '_' && ch != '-') plain = false;
+  fprintf(f, "%%YAML:1.0\n---\n");
+  if (plain) fprintf(f, "name: %s\n", m.name.c_str()); else fprintf(f, "name: \"%s\"\n", m.name.c_str());
+  fprintf(f, "interval: %d\nthresh: ", m.interval);
+  yaml_number(f, (double)m.thresh);
+  fprintf(f, "\nsbin: %d\nnorient: %d\nflen: %d\nfiltersw:\n", m.sbin, m.norient, m.flen);
+  for (int i = 0; i < m.nfilters(); ++i) {
+    fprintf(f, "   - !!opencv-matrix\n      rows: %d\n      cols: %d\n      dt: d\n      data: [ ", m.frows[i], m.fkw[i] * m.flen);
+    for (size_t j = 0; j < m.filters[i].size(); ++j) {
+      if (j) fputs(j % 3 ? ", " : ",\n          ", f);
+      yaml_number(f, m.filters[i][j]);
+    }
+    fputs(" ]\n", f);
+  }
+  auto flow_f = [&](const char* key, const float* v, size_t n, const char* cont) {
+    fprintf(f, "%s[ ", key);
+    for (size_t j = 0; j < n; ++j) { if (j) fputs(j % 4 ? ", " : cont, f); yaml_number(f, (double)v[j]); }
+    fputs(n ? " ]\n" : "]\n", f);
+  };
+  auto flow_i = [&](const char* key, const int* v, size_t n, const char* cont) {
+    fprintf(f, "%s[", key);
+    for (size_t j = 0; j < n; ++j) fprintf(f, "%s%d", j ? (j % 16 ? ", " : cont) : " ", v[j]);
+    fputs(n ? " ]\n" : "]\n", f);
+  };
+  flow_f("biasw: ", m.biasw.data(), m.biasw.size(), ",\n    ");
+  flow_i("anchors: ", m.anchors.data(), m.anchors.size(), ",\n    ");
+  fputs("defs:\n", f);
+  for (int j = 0; j < m.ndefs(); ++j) flow_f("   - ", m.defs.data() + 4 * j, 4, ",\n       ");
+  fputs("indexers:\n", f);
+  for (size_t c = 0; c < m.comps.size(); ++c) {
+    fprintf(f, "   component-%zu:\n", c);
+    for (size_t p = 0; p < m.comps[c].size(); ++p) {
+      const Part& P = m.comps[c][p];
+      fprintf(f, "      part-%zu:\n         parentid: %d\n", p, P.parentid);
+      flow_i("         filterid: ", P.filterid.data(), P.filterid.size(), ",\n             ");
+      flow_i("         biasid: ", P.biasid.data(), P.biasid.size(), ",\n             ");
+      if (p == 0) fputs("         defid: []\n", f); else flow_i("         defid: ", P.defid.data(), P.defid.size(), ",\n             ");
+    }
+  }
+  if (fclose(f) != 0) throw IoError("write failed on '" + path + "'");
+}
+
+void save_storage(const Model& m, const std::string& path) {
+  if (is_yaml_path(path)) save_yaml(m, path); else save_xml(m, path);
 }
 
 void save_xml(const Model& m, const std::string& path) {

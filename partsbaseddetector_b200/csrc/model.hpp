@@ -35,6 +35,15 @@ struct Model {
 // opencv_storage XML (what cv::FileStorage writes/reads for the reference's schema)
 void load_xml(const std::string& path, Model& m);     // throws IoError / FormatError
 void save_xml(const Model& m, const std::string& path);
+// the same schema in cv::FileStorage's YAML flavour (%YAML:1.0); load_storage picks the parser from the content, save_storage
+// the writer from the extension (.yml / .yaml -> YAML, anything else -> XML) as cv::FileStorage::open does
+void load_yaml(const std::string& path, Model& m);
+void save_yaml(const Model& m, const std::string& path);
+void load_storage(const std::string& path, Model& m);
+void save_storage(const Model& m, const std::string& path);
+// MATLAB Level-5 MAT-file holding the training code's `model` struct (reference MatlabIOModel::deserialize,
+// src/MatlabIOModel.cpp:71-188; native reader in matfile.cpp, no cvmatio)
+void load_mat(const std::string& path, Model& m);     // throws IoError / FormatError
 // compact little-endian container of the same fields ("PBDM" v1)
 void load_bin(const std::string& path, Model& m);
 void save_bin(const Model& m, const std::string& path);

@@ -114,11 +114,12 @@ class Model:
 
 
 class FileStorageModel(Model):
-    """reference FileStorageModel (src/FileStorageModel.cpp): XML (de)serialisation; bool returns."""
+    """reference FileStorageModel (src/FileStorageModel.cpp): XML / YAML (de)serialisation as cv::FileStorage (format from the
+    content on reading, from the extension on writing); bool returns."""
 
     def deserialize(self, filename):
         h = C.c_void_p()
-        rc = _lib.lib().pbd_model_load_xml(filename.encode(), C.byref(h))
+        rc = _lib.lib().pbd_model_load_storage(filename.encode(), C.byref(h))
         if rc == -2:            # cannot open: the reference returns false (src/FileStorageModel.cpp:100-101)
             return False
         _lib.check(rc)
@@ -128,8 +129,27 @@ class FileStorageModel(Model):
         return True
 
     def serialize(self, filename):
-        _lib.check(_lib.lib().pbd_model_save_xml(self.handle, filename.encode()))
+        _lib.check(_lib.lib().pbd_model_save_storage(self.handle, filename.encode()))
         return True
+
+
+class MatlabIOModel(Model):
+    """reference MatlabIOModel (src/MatlabIOModel.cpp:71-188): reads the Matlab training code's `model` struct from a version-5
+    .mat file (native reader inside libpbd_b200.so; the reference needs cvmatio).  serialize() is a stub in the reference too."""
+
+    def deserialize(self, filename):
+        h = C.c_void_p()
+        rc = _lib.lib().pbd_model_load_mat(filename.encode(), C.byref(h))
+        if rc == -2:            # cannot open: `if (!ok) return false;` (src/MatlabIOModel.cpp:76-77)
+            return False
+        _lib.check(rc)
+        if self._h:
+            _lib.lib().pbd_model_free(self._h)
+        self._h = h
+        return True
+
+    def serialize(self, filename):
+        return False            # src/MatlabIOModel.cpp:191-195: "TODO: implement", returns false
 
 
 class Candidate:

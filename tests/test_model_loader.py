@@ -101,3 +101,86 @@ def test_flat_model_round_trip_and_validation():
     bad.defs[0, 0] = 0.0                     # a = -w0 must be < 0 for the distance transform
     with pytest.raises(PbdError):
         Model.from_flat(bad)
+
+
+# ---------------------------------------------------------------------------------------- YAML flavour of cv::FileStorage
+def write_model_with_cv2(fm, path):
+    """FileStorageModel::serialize (reference src/FileStorageModel.cpp:42-94) through cv2.FileStorage itself: the format is
+    chosen by the extension, so the same calls give the XML or the YAML flavour."""
+    import cv2
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_WRITE)
+    fs.write("name", fm.name)
+    for k in ("interval", "thresh", "sbin", "norient", "flen"):
+        fs.write(k, float(fm.thresh) if k == "thresh" else int(getattr(fm, k)))
+    fs.startWriteStruct("filtersw", cv2.FILE_NODE_SEQ)
+    for f in fm.filters:
+        fs.write("", np.ascontiguousarray(f, np.float64))
+    fs.endWriteStruct()
+
+    def flow(name, values, conv):
+        fs.startWriteStruct(name, cv2.FILE_NODE_SEQ | cv2.FILE_NODE_FLOW)
+        for v in values:
+            fs.write("", conv(v))
+        fs.endWriteStruct()
+    flow("biasw", fm.biasw, float)
+    flow("anchors", np.asarray(fm.anchors).reshape(-1), int)
+    fs.startWriteStruct("defs", cv2.FILE_NODE_SEQ)
+    for d in np.asarray(fm.defs).reshape(-1, 4):
+        flow("", d, float)
+    fs.endWriteStruct()
+    fs.startWriteStruct("indexers", cv2.FILE_NODE_MAP)
+    for c, parts in enumerate(fm.comps):
+        fs.startWriteStruct("component-%d" % c, cv2.FILE_NODE_MAP)
+        for p, part in enumerate(parts):
+            fs.startWriteStruct("part-%d" % p, cv2.FILE_NODE_MAP)
+            fs.write("parentid", int(part.parentid))
+            flow("filterid", part.filterid, int)
+            flow("biasid", part.biasid, int)
+            flow("defid", [] if part.parentid < 0 else part.defid, int)
+            fs.endWriteStruct()
+        fs.endWriteStruct()
+    fs.endWriteStruct()
+    fs.release()
+
+
+@pytest.mark.parametrize("name", ["Person_26parts", "Person_8parts", "Face_99filters", "Willowcoffee_5parts", "Face_frontal_sparse"])
+@pytest.mark.parametrize("ext", [".yml", ".yaml", ".xml"])
+def test_yaml_and_xml_written_by_cv2_are_read_and_ours_are_read_by_cv2(name, ext, tmp_path):
+    import refmodel
+    from conftest import load_flat
+    fm = load_flat(name)
+    theirs = str(tmp_path / ("cv2" + ext))
+    write_model_with_cv2(fm, theirs)
+    if ext != ".xml":
+        assert open(theirs).read().startswith("%YAML")
+    m = FileStorageModel()
+    assert m.deserialize(theirs)
+    assert_same_model(m.to_flat(), fm)
+    ours = str(tmp_path / ("ours" + ext))
+    assert m.serialize(ours)                                   # format from the extension, as cv::FileStorage::open
+    assert open(ours).read().startswith("%YAML" if ext != ".xml" else "<?xml")
+    assert_same_model(refmodel.load_xml_cv2(ours), fm)         # cv2 reads what the product wrote
+    m2 = FileStorageModel()
+    assert m2.deserialize(ours)
+    assert_same_model(m2.to_flat(), fm)
+
+
+def test_yaml_details(tmp_path):
+    # quoted names, comments, a document end marker, block sequences at the key's own indentation, CRLF line ends
+    text = ('%YAML:1.0\r\n---\r\n# a comment\r\nname: "two words"\r\ninterval: 2\r\nthresh: -1\r\nsbin: 4\r\nnorient: 18\r\nflen: 32\r\n'
+            'filtersw:\r\n- !!opencv-matrix\r\n  rows: 1\r\n  cols: 32\r\n  dt: d\r\n  data: [ 1., -2.5e-1,\r\n     3., .Inf,\r\n' + ' 7.,' * 27 + ' 9. ]\r\n'
+            'biasw: [ 0.5 ]\r\nanchors: [ 0, 0 ]\r\ndefs:\r\n- [ 0.1, 0., 0.2, 0. ]\r\n'
+            'indexers:\r\n  component-0:\r\n    part-0:\r\n      parentid: -1\r\n      filterid: [ 0 ]\r\n      biasid: [ 0 ]\r\n      defid: []\r\n...\r\n')
+    p = tmp_path / "d.yml"
+    p.write_bytes(text.encode())
+    m = FileStorageModel()
+    assert m.deserialize(str(p))
+    fm = m.to_flat()
+    assert fm.name == "two words" and fm.interval == 2 and fm.thresh == -1.0 and fm.flen == 32
+    assert fm.filters[0].tolist() == [[1.0, -0.25, 3.0, float("inf")] + [7.0] * 27 + [9.0]]
+    assert fm.comps[0][0].defid == [0] and fm.comps[0][0].filterid == [0]
+    bad = tmp_path / "bad.yml"
+    bad.write_text("%YAML:1.0\n---\nname: x\nfiltersw: [ 1, 2\n")
+    with pytest.raises(PbdError) as e:
+        FileStorageModel().deserialize(str(bad))
+    assert e.value.code == -3
