@@ -105,6 +105,11 @@ void pbd_destroy(pbd_detector* d);
  *   "max_candidates" capacity of the candidate buffer per batch (default 65536)
  *   "timing"      1: record per-stage CUDA events (pbd_stage_times_ms); disables the chunked H2D/pyramid overlap;
  *                 2: additionally one event after every kernel of the pdf / dp_min stages (pbd_kernel_times_ms)
+ *   "nms_overlap" < 0 (default): detect returns the raw candidate list in the reference's order, as PartsBasedDetector::detect;
+ *                 0 <= v < 1: what the reference's callers do next (ros/Node.cpp:192-196) happens on the device -- per frame the
+ *                 candidates are sorted by descending score (ties: raw-list order) and greedily suppressed by
+ *                 Candidate::nonMaximaSuppression (include/Candidate.hpp:277-304) with overlap v; only the survivors are
+ *                 downloaded, frame by frame in that order.  Needs real frames (not pbd_set_levels) and <= 32 components.
  *   "dp_streams"  1..8 (default 2): the DP stage processes the batch as this many groups of frames on concurrent CUDA streams
  *                 (forked from and joined back into the detector's stream) so that kernel tails of one group overlap the
  *                 other's work; results do not depend on it.  Batches under 8 frames and timing == 2 use one stream.

@@ -179,6 +179,7 @@ int pbd_set_option(pbd_detector* d, const char* key, double value) {
     else if (k == "max_levels") { REQUIRE(value >= 0, "max_levels must be >= 0"); e.max_levels = (int)value; }
     else if (k == "max_candidates") { REQUIRE(value >= 1 && value <= (1 << 24), "max_candidates out of range"); e.max_candidates = (int)value; }
     else if (k == "timing") e.timing = value >= 2 ? 2 : (value != 0);
+    else if (k == "nms_overlap") { REQUIRE(value < 1.0, "nms_overlap must be < 1 (negative = off)"); e.nms_overlap = value; }
     else if (k == "dp_streams") { REQUIRE(value >= 1 && value <= 8, "dp_streams must be 1..8"); e.dp_streams = (int)value; }
     else throw ArgError("unknown option '" + k + "'");
   });
@@ -197,6 +198,7 @@ int pbd_get_option(const pbd_detector* d, const char* key, double* value) {
     else if (k == "max_candidates") *value = e.max_candidates;
     else if (k == "timing") *value = e.timing;
     else if (k == "dp_streams") *value = e.dp_streams;
+    else if (k == "nms_overlap") *value = e.nms_overlap;
     else throw ArgError("unknown option '" + k + "'");
   });
 }

@@ -87,7 +87,9 @@ Engine::~Engine() {
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
                   d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
-                  slots_[1].d_hits, slots_[1].d_nhits, slots_[1].d_xym};
+                  slots_[1].d_hits, slots_[1].d_nhits, slots_[1].d_xym, d_ksize_, nms_.boxes, nms_.keys, nms_.skeys, nms_.sidx, nms_.kept_idx,
+                  nms_.frame_count, nms_.fill, nms_.kept_count, nms_.out_off, nms_.seg_off, nms_.scratch, slots_[0].d_hits_out,
+                  slots_[0].d_xym_out, slots_[0].d_total, slots_[1].d_hits_out, slots_[1].d_xym_out, slots_[1].d_total};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (ResultSlot& S : slots_) if (S.done) cudaEventDestroy(S.done);
   for (auto& e : frames_free_ev_) if (e) cudaEventDestroy(e);
@@ -182,6 +184,7 @@ void Engine::build_tables() {
   const int ncomp = m.ncomponents();
   h_parent_.assign((size_t)ncomp * kMaxParts, -1);
   h_nparts_.assign(ncomp, 0);
+  h_ksize_.assign((size_t)ncomp * kMaxParts * kMaxMix, 0);
   h_cm_slot_.assign((size_t)ncomp * kMaxParts * kMaxMix, 0);
   h_pm_slot_.assign((size_t)ncomp * kMaxParts * kMaxMix, 0);
   std::vector<std::vector<std::vector<int>>> work_slot(ncomp);   // [c][p][m] or -1 (leaf)
@@ -192,6 +195,9 @@ void Engine::build_tables() {
     if (np > kMaxParts) throw UnsupportedError("component has more parts than kMaxParts");
     max_parts_ = std::max(max_parts_, np);
     h_nparts_[c] = np;
+    for (int p = 0; p < np; ++p)
+      for (size_t mx = 0; mx < parts[p].filterid.size() && mx < (size_t)kMaxMix; ++mx)
+        h_ksize_[((size_t)c * kMaxParts + p) * kMaxMix + mx] = m.frows[parts[p].filterid[mx]];   // xsize == ysize == rows (Parts.hpp:185-187)
     std::vector<char> has_child(np, 0);
     for (int p = 1; p < np; ++p) has_child[parts[p].parentid] = 1;
     work_slot[c].resize(np);
@@ -287,7 +293,7 @@ void Engine::build_tables() {
     if (!h.empty()) check_cuda(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice), "upload table");
     dev_bytes_ += bytes;
   };
-  up(d_jobs_, jobs_); up(d_roots_, roots_); up(d_parent_, h_parent_); up(d_nparts_, h_nparts_); up(d_cm_slot_, h_cm_slot_); up(d_pm_slot_, h_pm_slot_);
+  up(d_jobs_, jobs_); up(d_roots_, roots_); up(d_parent_, h_parent_); up(d_nparts_, h_nparts_); up(d_ksize_, h_ksize_); up(d_cm_slot_, h_cm_slot_); up(d_pm_slot_, h_pm_slot_);
 }
 
 void Engine::need(int stage, const char* who) const {
@@ -474,6 +480,18 @@ void Engine::ensure_slot(ResultSlot& S) {
   ensure(S.d_hits, S.cap_hits, (size_t)max_candidates);
   ensure(S.d_xym, S.cap_xym, (size_t)max_candidates * 3 * std::max(max_parts_, 1));
   S.max_candidates = max_candidates;
+}
+
+void Engine::ensure_nms(ResultSlot& S) {
+  const size_t mh = (size_t)max_candidates, nf = (size_t)g_.n_frames;
+  ensure(nms_.boxes, cap_nms_boxes_, mh); ensure(nms_.keys, cap_nms_keys_, mh);
+  ensure(nms_.skeys, cap_nms_skeys_, 2 * mh); ensure(nms_.sidx, cap_nms_sidx_, 2 * mh); ensure(nms_.kept_idx, cap_nms_kept_, 2 * mh);
+  ensure(nms_.frame_count, cap_nms_fc_, nf); ensure(nms_.fill, cap_nms_fill_, nf); ensure(nms_.kept_count, cap_nms_kc_, nf);
+  ensure(nms_.out_off, cap_nms_oo_, nf); ensure(nms_.seg_off, cap_nms_so_, nf + 1);
+  ensure(nms_.scratch, cap_nms_scratch_, nms_scratch_words(g_));
+  ensure(S.d_hits_out, S.cap_hits_out, mh);
+  ensure(S.d_xym_out, S.cap_xym_out, mh * 3 * std::max(max_parts_, 1));
+  if (!S.d_total) { check_cuda(cudaMalloc(&S.d_total, sizeof(int)), "cudaMalloc"); dev_bytes_ += sizeof(int); }
 }
 
 void Engine::upload_frames(const uint8_t* frames, size_t row_stride, size_t frame_stride) {
@@ -692,6 +710,16 @@ void Engine::run_argmin() {
   BacktrackTables t{d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_};
   launches_ += launch_backtrack(g_, d_g_, b_, t, model_.ncomponents(), ncm_, npm_, S.d_hits, S.d_nhits, S.max_candidates, backptr, max_parts_,
                                 S.d_xym, stream_);
+  S.nms = nms_overlap >= 0.0;
+  if (S.nms) {
+    if (!have_images_) throw StateError("nms_overlap needs the frame size: not available for a batch defined by pbd_set_levels");
+    if (model_.ncomponents() > 32) throw UnsupportedError("device NMS supports at most 32 components");
+    ensure_nms(S);
+    NmsBuffers nb = nms_;
+    nb.hits_out = S.d_hits_out; nb.xym_out = S.d_xym_out; nb.total = S.d_total;
+    launches_ += launch_device_nms(g_, d_g_, nb, S.d_hits, S.d_nhits, S.max_candidates, S.d_xym, max_parts_, d_nparts_, d_ksize_, (float)nms_overlap,
+                                   stream_);
+  }
   check_cuda(cudaGetLastError(), "argmin launch");
   S.scales.resize(g_.n_levels);
   for (int l = 0; l < g_.n_levels; ++l) S.scales[l] = g_.lv[l].scale;
@@ -714,18 +742,22 @@ void Engine::download_slot(ResultSlot& S, cudaStream_t st, CandidateSet& out) {
   if (nh > S.max_candidates)
     throw StateError("candidate buffer overflow: " + std::to_string(nh) + " hits > max_candidates=" + std::to_string(S.max_candidates));
   const int ps = max_parts_;
+  if (S.nms) {                                       // only the survivors of the device NMS come back, already in their final order
+    check_cuda(cudaMemcpyAsync(&nh, S.d_total, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H kept count");
+    check_cuda(cudaStreamSynchronize(st), "sync");
+  }
   h_hits_.resize(nh);
   h_xym_.resize((size_t)nh * 3 * ps);
   if (nh) {
-    check_cuda(cudaMemcpyAsync(h_hits_.data(), S.d_hits, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st), "D2H hits");
-    check_cuda(cudaMemcpyAsync(h_xym_.data(), S.d_xym, h_xym_.size() * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H parts");
+    check_cuda(cudaMemcpyAsync(h_hits_.data(), S.nms ? S.d_hits_out : S.d_hits, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st), "D2H hits");
+    check_cuda(cudaMemcpyAsync(h_xym_.data(), S.nms ? S.d_xym_out : S.d_xym, h_xym_.size() * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H parts");
     check_cuda(cudaStreamSynchronize(st), "sync");
   }
   // the reference's deterministic (single-threaded) order: frame, level, component, row-major hit
   std::vector<int> order(nh);
   for (int i = 0; i < nh; ++i) order[i] = i;
   const std::vector<Hit>& hits = h_hits_;
-  std::sort(order.begin(), order.end(), [&](int a, int b) {
+  if (!S.nms) std::sort(order.begin(), order.end(), [&](int a, int b) {
     const Hit &A = hits[a], &B = hits[b];
     if (A.frame != B.frame) return A.frame < B.frame;
     if (A.level != B.level) return A.level < B.level;

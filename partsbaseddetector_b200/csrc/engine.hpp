@@ -59,6 +59,9 @@ class Engine {
   int resp_mode = 0, tc_taps_per_partial = 0, backptr = 0, max_levels = 0, max_candidates = 65536, timing = 0;
   // the DP stage runs the batch as this many groups of frames on concurrent streams (1 = single stream)
   int dp_streams = 2;
+  // >= 0: detect() returns, per frame, the candidates sorted by score and greedily suppressed on the device (Candidate::sort +
+  // Candidate::nonMaximaSuppression with this overlap); < 0 (default): the raw candidate list, as the reference's detect()
+  double nms_overlap = -1.0;
   static constexpr int kMinFramesPerDpGroup = 4;
 
   // ---- batch set-up ----
@@ -141,6 +144,11 @@ class Engine {
   int nwork_ = 0, ncm_ = 0, npm_ = 0, tmp_maps_ = 0, max_parts_ = 0;
   std::vector<int> h_parent_, h_nparts_, h_cm_slot_, h_pm_slot_;
   int *d_parent_ = nullptr, *d_nparts_ = nullptr, *d_cm_slot_ = nullptr, *d_pm_slot_ = nullptr;
+  std::vector<int> h_ksize_; int* d_ksize_ = nullptr;         // filter rows of (component, part, mixture): candidate rectangles
+  NmsBuffers nms_{};
+  size_t cap_nms_boxes_ = 0, cap_nms_keys_ = 0, cap_nms_skeys_ = 0, cap_nms_sidx_ = 0, cap_nms_kept_ = 0, cap_nms_fc_ = 0, cap_nms_fill_ = 0,
+         cap_nms_kc_ = 0, cap_nms_oo_ = 0, cap_nms_so_ = 0, cap_nms_scratch_ = 0;
+  void ensure_nms(ResultSlot& S);
 
   // batch geometry + buffers
   Geometry g_{};
@@ -169,6 +177,10 @@ class Engine {
     Hit* d_hits = nullptr; size_t cap_hits = 0;
     int* d_nhits = nullptr;
     int* d_xym = nullptr; size_t cap_xym = 0;
+    Hit* d_hits_out = nullptr; size_t cap_hits_out = 0;      // device NMS: compacted survivors of the batch
+    int* d_xym_out = nullptr; size_t cap_xym_out = 0;
+    int* d_total = nullptr;
+    bool nms = false;                         // the batch in this slot went through the device NMS
     cudaEvent_t done = nullptr;               // recorded after the backtrack of the batch that filled the slot
     std::vector<float> scales;                // per-level scales of that batch (candidate rects)
     int max_candidates = 0;

@@ -177,6 +177,23 @@ int launch_expand_backptr(const Geometry& g, const DeviceBuffers& b, int frame, 
 int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const PassGeom* d_pg2, const PassMap* d_maps2, float* d_tmp,
                            float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
                            cudaStream_t s);
+// device-side Candidate::sort + nonMaximaSuppression (nms.cu): work buffers (shared by all batches of a detector) and the
+// compacted result of one batch (hits_out / xym_out / total: per result slot)
+struct NmsBuffers {
+  int4* boxes;                    // [max_hits] clipped bounding box per raw candidate
+  unsigned long long* keys;       // [max_hits]
+  unsigned long long* skeys;      // [2*max_hits] per-frame power-of-two sort segments
+  int *sidx, *kept_idx;           // [2*max_hits]
+  int *frame_count, *fill, *kept_count, *out_off;   // [n_frames]
+  int* seg_off;                   // [n_frames + 1]
+  unsigned int* scratch;          // [n_frames][in_h][ceil(in_w / 32)] painted pixels, one bit each
+  int* total;                     // [1] kept candidates of the batch
+  Hit* hits_out;                  // [max_hits]
+  int* xym_out;                   // [max_hits][3][out_parts]
+};
+size_t nms_scratch_words(const Geometry& g);
+int launch_device_nms(const Geometry& g, const Geometry* d_g, const NmsBuffers& nb, const Hit* d_hits, const int* d_nhits, int max_hits,
+                      const int* d_xym, int out_parts, const int* d_nparts, const int* d_ksize, float overlap, cudaStream_t s);
 constexpr int kMaxDim = 1024;  // largest level width/height (cells) the DP kernels are instantiated for
 
 }  // namespace pbd

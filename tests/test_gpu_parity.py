@@ -285,6 +285,40 @@ def test_dp_frame_groups_on_concurrent_streams_do_not_change_results(nframes):
         d.set_option("dp_streams", 0)
 
 
+@pytest.mark.parametrize("name,shape,keep", [("Person_26parts", (240, 320), 400), ("Face_99filters", (160, 200), 120), ("Person_8parts", (203, 177), 250)])
+def test_device_sort_and_nms_equal_host_sort_and_nms(name, shape, keep):
+    # option nms_overlap >= 0: Candidate::sort + Candidate::nonMaximaSuppression run on the device per frame and only the survivors
+    # are downloaded; the host versions (pbd_candidates_sort / pbd_candidates_nms, parity-tested against the oracle's restatement in
+    # test_host_logic.py) applied to the raw candidates of each frame must give the same list
+    from partsbaseddetector_b200 import Candidate
+    frames = synth_frames(5, shape[0], shape[1], start=900)
+    frames[3] = 0                                           # a flat frame: every score ties (canonical order decides)
+    d, O = detector(name), oracle(name)
+    if name == "Face_99filters":
+        d.set_option("max_levels", 1)
+        O.set_max_levels(1)
+    O.run(frames[0], 1, 3)
+    thr = lowered_threshold(O, keep)
+    d.set_option("thresh", thr)
+    d.set_option("nms_overlap", -1)
+    raw = [list(d.detect(frames[f])) for f in range(5)]
+    assert sum(len(r) for r in raw) > 50
+    sig = lambda k: (k.level, k.component_, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score()), k.parts().tobytes())
+    for ov in (0.0, 0.15, 0.6):
+        d.set_option("nms_overlap", ov)
+        got = list(d.detect(frames))
+        assert d.get_option("nms_overlap") == pytest.approx(ov)
+        for f in range(5):
+            want = Candidate.nonMaximaSuppression(frames[f], Candidate.sort(list(raw[f])), ov)
+            mine = [k for k in got if k.frame == f]
+            assert [sig(k) for k in mine] == [sig(k) for k in want], (ov, f, len(mine), len(want))
+        assert [k.frame for k in got] == sorted(k.frame for k in got)
+        # the streaming API goes through the same path
+        assert [sig(k) for k in d.collect_ticket(d.submit(frames))] == [sig(k) for k in got]
+    d.set_option("nms_overlap", -1)
+    assert len(d.detect(frames)) == sum(len(r) for r in raw)
+
+
 def test_determinism_and_stage_api_equivalence():
     d = detector("Person_26parts")
     frames = synth_frames(2, 240, 320, start=7)
