@@ -3,7 +3,7 @@
 // OpenCV's imread is not assumed; with OpenCV present pass a cv::Mat to detect() instead.
 //
 //   g++ -std=c++17 -Iinclude examples/demo.cpp -Lpartsbaseddetector_b200 -lpbd_b200 -Wl,-rpath,$PWD/partsbaseddetector_b200 -o demo
-//   ./demo model.xml|model.pbdm image.ppm [thresh]
+//   ./demo model.xml|model.yaml|model.mat|model.pbdm image.ppm [thresh]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,7 +47,8 @@ int main(int argc, char** argv) {
   const std::string mfile = argv[1];
   const std::string ext = mfile.substr(mfile.find_last_of('.') + 1);
   Model* model = nullptr;
-  if (ext == "xml" || ext == "yaml") model = new FileStorageModel;                                   // :64-72
+  if (ext == "xml" || ext == "yaml" || ext == "yml") model = new FileStorageModel;                   // :64-72
+  else if (ext == "mat") model = new MatlabIOModel;                                                  // :69-70
   else if (ext == "pbdm") model = new BinModel;
   else { printf("Unsupported model format: %s\n", ext.c_str()); return -2; }                         // :73-76
   try {
