@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 MODEL = os.path.join(ROOT, "tests", "golden", "Person_26parts.pbdm")
 H, W, C = 480, 640, 3
 METRIC = "frames/sec (person model, VGA, full pyramid)"
+MODES = {"exact": 0, "ffma": 1, "tensor": 2, "tensor16": 3}      # pbd_set_option("response_mode", ...)
 
 
 def env_int(name, default):
@@ -205,7 +206,7 @@ def run_gpu_arm(args):
 
     det = PartsBasedDetector(device=local, stream=torch.cuda.current_stream().cuda_stream)
     det.distributeModel(Model.load_bin(MODEL))
-    mode = {"exact": 0, "ffma": 1, "tensor": 2}[args.mode]
+    mode = MODES[args.mode]
     det.set_option("response_mode", mode)
     det.set_option("timing", 1)
     # calibrate the detection threshold on the first batch so that ~50 candidates/frame come back (synthetic
@@ -295,11 +296,14 @@ def run_gpu_arm(args):
         sm_mhz = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)
         mode_txt = {"exact": "exact (separately rounded multiply/add, bit-identical scores)", "ffma": "ffma (FP32 fused multiply-add responses)",
                     "tensor": "tensor (tcgen05 tf32x3 split products + fp32 accumulate for the part responses; scores within 2e-6 relative, "
-                              "integer outputs identical to the CPU oracle -- checked in `parity`)"}[args.mode]
+                              "integer outputs identical to the CPU oracle -- checked in `parity`)",
+                    "tensor16": "tensor16 (tcgen05 kind::f16 MMAs on fp16 hi/lo splits of the power-of-two pre-scaled fp32 operands: the same 11+11 "
+                                "significand bits and the same three products as tf32x3 at half the MMAs and operand bytes, fp32 accumulate; scores "
+                                "within 2e-6 relative, integer outputs identical to the CPU oracle -- checked in `parity`)"}[args.mode]
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.mode != "tensor" else "f32 (part responses as tf32x3 tensor-core products with fp32 accumulation; everything else f32/f64 as the reference)",
+            "dtype": "f32" if not args.mode.startswith("tensor") else "f32 (part responses as %s split tensor-core products with fp32 accumulation; everything else f32/f64 as the reference)" % ("tf32x3" if args.mode == "tensor" else "fp16x3"),
             "data": "synthetic",
             "config": {"workload": "config_person.by_parts (Person_26parts), 640x480 BGR frames, full 14-level HOG pyramid, 1xB200 per rank",
                        "batch_per_gpu": B, "frame": [H, W, C], "levels": nl, "cells_per_frame": cells, "parallelism": "frame-parallel x%d, no collective" % world,
@@ -330,15 +334,18 @@ def run_gpu_arm(args):
             # the capture holds launches of the largest wave: scale to this run's batch and to the average number of maps per launch
             roof_dt["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["launches"] * B / tr["batch"] * (nmaps / 11.0) / tr.get("maps_per_launch", nmaps / 11.0)
             roof_dt["traffic_source"] = tr.get("source", "ncu")
-        if args.mode == "tensor":
-            hw_flops = 3.0 * 2 * 800 * 144 * 128 * ((cells * 1.04) // 128) * B      # 3 tf32 products, 144 padded filters, ~4 % strip padding
-            tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2
-            roof_resp = {"kernel": "part_response_tc", "bound": "tensor", "achieved": hw_flops / (resp_ms * 1e-3) / 1e12 if resp_ms else None, "peak": tf32_peak,
-                         "unit": "TFLOP/s", "frac": hw_flops / (resp_ms * 1e-3) / 1e12 / tf32_peak if resp_ms else None, "traffic": None, "ms_per_launch": resp_ms,
-                         "peak_source": peak_src + " cuBLAS bf16 burst / 2 (tf32 issues at half the bf16 rate; nominal dense tf32 1100)",
+        if args.mode.startswith("tensor"):
+            hw_flops = 3.0 * 2 * 800 * 144 * 128 * ((cells * 1.04) // 128) * B      # 3 split products, 144 padded filters, ~4 % strip padding
+            f16 = args.mode == "tensor16"
+            tc_peak = peaks.get("bf16_tflops", 1590.0) / (1 if f16 else 2)
+            roof_resp = {"kernel": "part_response_tc<%s>" % ("f16" if f16 else "tf32"), "bound": "tensor", "achieved": hw_flops / (resp_ms * 1e-3) / 1e12 if resp_ms else None,
+                         "peak": tc_peak, "unit": "TFLOP/s", "frac": hw_flops / (resp_ms * 1e-3) / 1e12 / tc_peak if resp_ms else None, "traffic": None,
+                         "ms_per_launch": resp_ms,
+                         "peak_source": peak_src + (" cuBLAS bf16 burst (kind::f16 issues at the bf16 rate)" if f16 else
+                                                    " cuBLAS bf16 burst / 2 (tf32 issues at half the bf16 rate; nominal dense tf32 1100)"),
                          "algorithmic_tflops": resp_flops / (resp_ms * 1e-3) / 1e12 if resp_ms else None,
-                         "note": "hardware tf32 FLOP/s of the three split products; algorithmic_tflops counts the reference's fp32 multiply-adds once"}
-            tp = os.path.join(ROOT, "profiles", "part_response_tc_traffic.json")
+                         "note": "hardware FLOP/s of the three split products; algorithmic_tflops counts the reference's fp32 multiply-adds once"}
+            tp = os.path.join(ROOT, "profiles", "part_response_tc16_traffic.json" if f16 else "part_response_tc_traffic.json")
         else:
             fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
             ach = 680.0 * cells * B / (resp_ms * 1e-3) / 1e9 if resp_ms else None
@@ -368,10 +375,10 @@ def run_gpu_arm(args):
         }
         # the other response modes on the same workload (single rank, device-resident), for comparison
         others = {}
-        for om in ("exact", "ffma", "tensor"):
+        for om in ("exact", "ffma", "tensor", "tensor16"):
             if om == args.mode or (om == "ffma" and not args.also_fast):
                 continue
-            det.set_option("response_mode", {"exact": 0, "ffma": 1, "tensor": 2}[om])
+            det.set_option("response_mode", MODES[om])
             for _ in range(3):
                 det.enqueue_device(dev.data_ptr(), B, H, W, C)
             torch.cuda.synchronize()
@@ -404,9 +411,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--unique-frames", type=int, default=8, help="distinct synthetic frames generated per rank (tiled to the batch)")
-    ap.add_argument("--mode", default="tensor", choices=["tensor", "exact", "ffma"],
-                    help="part-response arithmetic: tensor = tcgen05 tf32x3 (default; scores within 2e-6, integer outputs identical to the oracle), "
-                         "exact = bit-identical scores on the FP32 pipes, ffma = fused multiply-add on the FP32 pipes")
+    ap.add_argument("--mode", default="tensor16", choices=["tensor16", "tensor", "exact", "ffma"],
+                    help="part-response arithmetic: tensor16 = tcgen05 fp16x3 (default) / tensor = tcgen05 tf32x3 (both: scores within 2e-6, integer "
+                         "outputs identical to the oracle), exact = bit-identical scores on the FP32 pipes, ffma = fused multiply-add on the FP32 pipes")
     ap.add_argument("--thresh", type=float, default=None)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--also-fast", action="store_true", default=False, help="also time the fused-multiply-add mode (rank 0 only)")

@@ -95,7 +95,11 @@ void pbd_destroy(pbd_detector* d);
  *                 1: fused multiply-add on the FP32 pipes (scores differ in the last ulps);
  *                 2: 5th-generation tensor cores (tcgen05, tf32x3 split products with fp32 accumulation; scores within ~4e-7
  *                    relative of the reference, integer outputs identical on every test frame; 8x faster than mode 0).
- *                    Models with non-uniform filter sizes fall back to mode 1.
+ *                 3: the same three split products as tcgen05 kind::f16 MMAs: the fp32 operands are pre-scaled by powers of two (features
+ *                    2^12, each filter so that its largest weight lies in [2^13, 2^14)) and split into fp16 hi + fp16 residual -- the same
+ *                    11 + 11 significand bits as the tf32 split -- which halves the MMAs and the operand bytes; the same accuracy and
+ *                    parity tests as mode 2, 1.4x faster.  Features must stay below 16 in magnitude (HOG features are <= 1).
+ *                    Models with non-uniform filter sizes fall back to mode 1 (modes 2 and 3).
  *   "exact"       alias kept for compatibility: 1 = response_mode 0, 0 = response_mode 1
  *   "tc_taps_per_partial"  response_mode 2: 0 (default) sums the hi*hi products of one filter row on the tensor core before the
  *                 fp32 round-to-nearest summation (score bias ~4 ulp), 1 sums tap by tap (bias < 1 ulp, 25 % slower)
@@ -113,7 +117,7 @@ void pbd_destroy(pbd_detector* d);
  *   "dp_streams"  1..8 (default 2): the DP stage processes the batch as this many groups of frames on concurrent CUDA streams
  *                 (forked from and joined back into the detector's stream) so that kernel tails of one group overlap the
  *                 other's work; results do not depend on it.  Batches under 8 frames and timing == 2 use one stream.
- * Environment defaults read at pbd_create: PBD_EXACT=0|1, PBD_RESPONSE_MODE=exact|ffma|tensor, PBD_BACKPTR=reference|exact,
+ * Environment defaults read at pbd_create: PBD_EXACT=0|1, PBD_RESPONSE_MODE=exact|ffma|tensor|tensor16, PBD_BACKPTR=reference|exact,
  * PBD_MAX_LEVELS=n, PBD_DP_STREAMS=n. */
 int pbd_set_option(pbd_detector* d, const char* key, double value);
 int pbd_get_option(const pbd_detector* d, const char* key, double* value);

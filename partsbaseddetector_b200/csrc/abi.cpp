@@ -157,6 +157,7 @@ int pbd_create(const pbd_model* m, int device, void* stream, pbd_detector** out)
       if (!strcmp(v, "exact") || !strcmp(v, "0")) d->e->resp_mode = 0;
       else if (!strcmp(v, "ffma") || !strcmp(v, "1")) d->e->resp_mode = 1;
       else if (!strcmp(v, "tensor") || !strcmp(v, "2")) d->e->resp_mode = 2;
+      else if (!strcmp(v, "tensor16") || !strcmp(v, "3")) d->e->resp_mode = 3;
     }
     if (const char* v = getenv("PBD_BACKPTR")) d->e->backptr = (strcmp(v, "exact") == 0 || strcmp(v, "1") == 0) ? 1 : 0;
     if (const char* v = getenv("PBD_MAX_LEVELS")) d->e->max_levels = std::max(0, atoi(v));
@@ -173,7 +174,7 @@ int pbd_set_option(pbd_detector* d, const char* key, double value) {
     const std::string k(key);
     if (k == "thresh") e.thresh = value;
     else if (k == "exact") e.resp_mode = value != 0 ? 0 : 1;
-    else if (k == "response_mode") { REQUIRE(value == 0 || value == 1 || value == 2, "response_mode must be 0 (exact), 1 (ffma) or 2 (tensor)"); e.resp_mode = (int)value; }
+    else if (k == "response_mode") { REQUIRE(value == 0 || value == 1 || value == 2 || value == 3, "response_mode must be 0 (exact), 1 (ffma), 2 (tensor tf32) or 3 (tensor fp16)"); e.resp_mode = (int)value; }
     else if (k == "tc_taps_per_partial") { REQUIRE(value >= 0 && value <= 1024, "tc_taps_per_partial out of range"); e.tc_taps_per_partial = (int)value; }
     else if (k == "backptr") { REQUIRE(value == 0 || value == 1, "backptr must be 0 or 1"); e.backptr = (int)value; }
     else if (k == "max_levels") { REQUIRE(value >= 0, "max_levels must be >= 0"); e.max_levels = (int)value; }

@@ -83,7 +83,7 @@ Engine::Engine(const Model& m, int device, cudaStream_t stream) : thresh((double
 Engine::~Engine() {
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
-  void* ptrs[] = {d_wtc_, d_fhi_, d_flo_, d_tc_levels_, d_tc_tiles_, d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
+  void* ptrs[] = {d_wtc_, d_wtc16_, d_f16_, d_fhi_, d_flo_, d_tc_levels_, d_tc_tiles_, d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
                   d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
@@ -179,6 +179,11 @@ void Engine::build_tables() {
     check_cuda(cudaMalloc(&d_wtc_, wt.size() * sizeof(float)), "cudaMalloc tensor filters");
     check_cuda(cudaMemcpy(d_wtc_, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice), "upload tensor filters");
     dev_bytes_ += wt.size() * sizeof(float);
+    std::vector<uint16_t> w16;
+    response_tc_pack_weights_f16(ff, fb_.kh * fb_.kw, w16, wtc16_scales_);
+    check_cuda(cudaMalloc(&d_wtc16_, w16.size() * sizeof(uint16_t)), "cudaMalloc tensor filters (fp16)");
+    check_cuda(cudaMemcpy(d_wtc16_, w16.data(), w16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice), "upload tensor filters (fp16)");
+    dev_bytes_ += w16.size() * sizeof(uint16_t);
   }
   // ---- DP slots ----
   const int ncomp = m.ncomponents();
@@ -611,12 +616,24 @@ void Engine::run_pyramid() {
 }
 
 // Strip layout, work list and border cells of the tensor-core path for the current batch geometry.
-void Engine::ensure_tc() {
+void Engine::ensure_tc(bool f16) {
   std::vector<TcLevel> lv;
   std::vector<TcTile> su;
   long long slack = 0;
   const long long frame_rows = response_tc_plan(g_, fb_.kh, fb_.kw, lv, su, &slack);
   const size_t rows = (size_t)frame_rows * g_.n_frames + (size_t)slack;
+  if (f16) {
+    const bool realloc16 = rows * 64 > cap_f16_ || !d_f16_;
+    if (tc16_serial_ == geom_serial_ && !realloc16) return;
+    ensure(d_f16_, cap_f16_, rows * 64);
+    ensure(d_tc_levels_, cap_tc_levels_, lv.size()); ensure(d_tc_tiles_, cap_tc_tiles_, std::max<size_t>(su.size(), 1));
+    check_cuda(cudaMemcpyAsync(d_tc_levels_, lv.data(), lv.size() * sizeof(TcLevel), cudaMemcpyHostToDevice, stream_), "upload strip levels");
+    if (!su.empty()) check_cuda(cudaMemcpyAsync(d_tc_tiles_, su.data(), su.size() * sizeof(TcTile), cudaMemcpyHostToDevice, stream_), "upload work list");
+    launches_ += launch_tc_border_init_f16(d_f16_, (long long)(cap_f16_ / 64), stream_);
+    check_cuda(cudaStreamSynchronize(stream_), "sync strip tables");
+    tc_ntiles_ = (int)su.size(); tc_frame_rows_ = frame_rows; tc16_serial_ = geom_serial_;
+    return;
+  }
   const bool realloc = rows * 32 > cap_fhi_ || !d_fhi_;
   if (tc_serial_ == geom_serial_ && !realloc) return;
   ensure(d_fhi_, cap_fhi_, rows * 32); ensure(d_flo_, cap_flo_, rows * 32);
@@ -630,13 +647,19 @@ void Engine::ensure_tc() {
 
 void Engine::run_pdf() {
   need(2, "pdf");
-  if (resp_mode == 2 && response_tc_supported(fb_)) {
-    ensure_tc();
+  if ((resp_mode == 2 || resp_mode == 3) && response_tc_supported(fb_)) {
+    const bool f16 = resp_mode == 3;
+    ensure_tc(f16);
     if (timing) { check_cuda(cudaEventRecord(ev_[3], stream_), "event"); ev_valid_[3] = true; }
     kev_n_ = 0; kmark(-1);
-    launches_ += launch_feat_split(g_, d_g_, d_tc_levels_, b_.feat, d_fhi_, d_flo_, tc_frame_rows_, stream_);
+    if (f16) launches_ += launch_feat_split_f16(g_, d_g_, d_tc_levels_, b_.feat, d_f16_, tc_frame_rows_, stream_);
+    else launches_ += launch_feat_split(g_, d_g_, d_tc_levels_, b_.feat, d_fhi_, d_flo_, tc_frame_rows_, stream_);
     kmark(0);
-    launches_ += launch_response_tc(g_, b_, fb_, d_fhi_, d_flo_, d_wtc_, d_tc_levels_, d_tc_tiles_, tc_ntiles_, tc_frame_rows_, num_sms_, tc_taps_per_partial, stream_);
+    if (f16)
+      launches_ += launch_response_tc(g_, b_, fb_, reinterpret_cast<const float*>(d_f16_), nullptr, reinterpret_cast<const float*>(d_wtc16_), d_tc_levels_,
+                                      d_tc_tiles_, tc_ntiles_, tc_frame_rows_, num_sms_, tc_taps_per_partial, stream_, wtc16_scales_.data());
+    else
+      launches_ += launch_response_tc(g_, b_, fb_, d_fhi_, d_flo_, d_wtc_, d_tc_levels_, d_tc_tiles_, tc_ntiles_, tc_frame_rows_, num_sms_, tc_taps_per_partial, stream_);
     kmark(1);
     check_cuda(cudaGetLastError(), "tensor response launch");
     stage_ = 3;

@@ -55,7 +55,8 @@ class Engine {
   // options
   double thresh;
   // resp_mode: 0 exact (separately rounded multiply/add in the reference's order, bit-identical scores), 1 fused multiply-add,
-  // 2 tensor cores (tf32x3 split products, fp32 accumulate; falls back to 1 for models the tensor kernel does not cover)
+  // 2 tensor cores (tf32x3 split products, fp32 accumulate; falls back to 1 for models the tensor kernel does not cover),
+  // 3 tensor cores with fp16 split operands (the same 11 + 11 significand bits, power-of-two pre-scaling; half the MMAs of mode 2)
   int resp_mode = 0, tc_taps_per_partial = 0, backptr = 0, max_levels = 0, max_candidates = 65536, timing = 0;
   // the DP stage runs the batch as this many groups of frames on concurrent streams (1 = single stream)
   int dp_streams = 2;
@@ -113,7 +114,7 @@ class Engine {
   void build_batch_tables();
   void need(int stage, const char* who) const;
   void ensure_slot(ResultSlot& S);
-  void ensure_tc();
+  void ensure_tc(bool f16);
   void download_slot(ResultSlot& S, cudaStream_t st, CandidateSet& out);
   void chunked_upload_pyramid(const uint8_t* frames, uint8_t* d_dst, cudaEvent_t wait_before_copy, cudaEvent_t record_after);
 
@@ -130,6 +131,9 @@ class Engine {
   // tensor-core response path: packed tf32 hi/lo weight slabs, padded strip copies of the HOG cells, work list
   float* d_wtc_ = nullptr;
   float *d_fhi_ = nullptr, *d_flo_ = nullptr; size_t cap_fhi_ = 0, cap_flo_ = 0;
+  uint16_t* d_f16_ = nullptr; size_t cap_f16_ = 0;             // response mode 3: fp16 [hi | lo'] strips
+  uint16_t* d_wtc16_ = nullptr; std::vector<float> wtc16_scales_;   // ... and weight slabs (+ the per-filter output scales, kernel parameters)
+  long long tc16_serial_ = -1;
   TcLevel* d_tc_levels_ = nullptr; size_t cap_tc_levels_ = 0;
   TcTile* d_tc_tiles_ = nullptr; size_t cap_tc_tiles_ = 0;
   int tc_ntiles_ = 0; long long tc_frame_rows_ = 0;

@@ -123,8 +123,14 @@ long long response_tc_plan(const Geometry& g, int kh, int kw, std::vector<TcLeve
 int launch_feat_split(const Geometry& g, const Geometry* d_g, const TcLevel* d_levels, const float* feat, float* fhi, float* flo,
                       long long frame_rows, cudaStream_t s);
 int launch_tc_border_init(float* fhi, float* flo, long long rows, cudaStream_t s);
+// fp16 flavour of the tensor path (response mode 3)
+void response_tc_pack_weights_f16(const std::vector<std::vector<float>>& filters, int taps, std::vector<uint16_t>& out, std::vector<float>& out_scales);
+int launch_feat_split_f16(const Geometry& g, const Geometry* d_g, const TcLevel* d_levels, const float* feat, uint16_t* strips, long long frame_rows,
+                          cudaStream_t s);
+int launch_tc_border_init_f16(uint16_t* strips, long long rows, cudaStream_t s);
 int launch_response_tc(const Geometry& g, const DeviceBuffers& b, const FilterBank& fb, const float* fhi, const float* flo, const float* wpk,
-                       const TcLevel* d_levels, const TcTile* d_tiles, int n_tiles, long long frame_rows, int num_sms, int taps_per_partial, cudaStream_t s);
+                       const TcLevel* d_levels, const TcTile* d_tiles, int n_tiles, long long frame_rows, int num_sms, int taps_per_partial, cudaStream_t s,
+                       const float* f16_scales = nullptr);
 
 // Geometry of one separable-transform pass: per level the number of lines, their length and the map offset.
 struct PassGeom {

@@ -22,13 +22,16 @@ SCORE_TOL = 2e-6       # relative root-score tolerance asserted (north star: 1e-
 _det = {}
 
 
-def detector(name, per_tap=0):
+MODES = [2, 3]          # 2: tf32x3 operands, 3: fp16 split operands with power-of-two pre-scaling (half the MMAs)
+
+
+def detector(name, per_tap=0, mode=2):
     if name not in _det:
         d = PartsBasedDetector(device=0)
         d.distributeModel(Model.load_bin(os.path.join(GOLDEN, name + ".pbdm")))
         _det[name] = d
     d = _det[name]
-    for k, v in (("response_mode", 2), ("tc_taps_per_partial", per_tap), ("backptr", 0), ("max_levels", 0), ("thresh", load_flat(name).thresh)):
+    for k, v in (("response_mode", mode), ("tc_taps_per_partial", per_tap), ("backptr", 0), ("max_levels", 0), ("thresh", load_flat(name).thresh)):
         d.set_option(k, v)
     return d
 
@@ -44,10 +47,11 @@ def lowered_threshold(O, keep):
 
 @pytest.mark.parametrize("name", ["Person_26parts", "Willowcoffee_5parts", "Face_frontal_sparse", "Person_8parts", "Face_99filters"])
 @pytest.mark.parametrize("per_tap", [0, 1])
-def test_responses_all_filters_all_levels(name, per_tap):
+@pytest.mark.parametrize("mode", MODES)
+def test_responses_all_filters_all_levels(name, per_tap, mode):
     fm = load_flat(name)
     img = synth_frame(11, 144, 200)
-    d, O = detector(name, per_tap), oracle(name)
+    d, O = detector(name, per_tap, mode), oracle(name)
     O.run(img, 1, 2)
     d.pyramid(img)
     d.pdf()
@@ -60,12 +64,13 @@ def test_responses_all_filters_all_levels(name, per_tap):
     assert worst <= RESP_TOL, worst
 
 
-def test_responses_injected_features_ragged_levels():
+@pytest.mark.parametrize("mode", MODES)
+def test_responses_injected_features_ragged_levels(mode):
     # stage-isolated: random signed features (channel 31 non-zero inside the map) on ragged level sizes incl. single rows and
     # columns and maps smaller than the filter; every filter compared
     name = "Willowcoffee_5parts"
     fm = load_flat(name)
-    d, O = detector(name), oracle(name)
+    d, O = detector(name, 0, mode), oracle(name)
     ohow = [[9, 35], [33, 8], [4, 4], [17, 65], [1, 1], [1, 40], [37, 1], [2, 3], [130, 131]]
     scales = [4.0 + i for i in range(len(ohow))]
     d.set_levels(1, ohow, scales)
@@ -84,10 +89,11 @@ def test_responses_injected_features_ragged_levels():
 
 
 @pytest.mark.parametrize("shape,seed", [((240, 320), 33), ((480, 640), 101), ((203, 177), 5)])
-def test_full_path_integer_outputs_identical_and_scores(shape, seed):
+@pytest.mark.parametrize("mode", MODES)
+def test_full_path_integer_outputs_identical_and_scores(shape, seed, mode):
     name = "Person_26parts"
     img = synth_frame(seed, *shape)
-    d, O = detector(name), oracle(name)
+    d, O = detector(name, 0, mode), oracle(name)
     O.run(img, 1, 3)
     thr = lowered_threshold(O, 150)
     rv_all = np.sort(np.concatenate([O.rootv(l).ravel() for l in range(O.nlevels())]))
@@ -115,10 +121,11 @@ def test_full_path_integer_outputs_identical_and_scores(shape, seed):
         assert flips <= 1e-4 * 3 * gi[0].size, (p, m, flips)
 
 
-def test_batch_of_frames_matches_single_frames():
+@pytest.mark.parametrize("mode", MODES)
+def test_batch_of_frames_matches_single_frames(mode):
     name = "Person_26parts"
     frames = synth_frames(5, 240, 320, start=40)
-    d = detector(name)
+    d = detector(name, 0, mode)
     d.set_option("thresh", -1.2)
     batch = d.detect(frames)
     rv = [d.rootv(f, 1).copy() for f in range(5)]
@@ -130,11 +137,12 @@ def test_batch_of_frames_matches_single_frames():
     assert [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m), float(k.score())) for k in batch] == singles
 
 
-def test_flat_frames_keep_exact_ties():
+@pytest.mark.parametrize("mode", MODES)
+def test_flat_frames_keep_exact_ties(mode):
     # constant frames: every interior cell sees identical operands, so the tensor path must return identical scores there (ties
     # stay ties) and the integer outputs must equal the oracle's
     name = "Person_26parts"
-    d, O = detector(name), oracle(name)
+    d, O = detector(name, 0, mode), oracle(name)
     for img in (np.zeros((120, 160, 3), np.uint8), np.full((120, 160, 3), 200, np.uint8)):
         O.run(img, 1, 3)
         thr = lowered_threshold(O, 40)

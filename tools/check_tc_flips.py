@@ -13,7 +13,7 @@ G = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 path = os.path.join(ROOT, "tests", "golden", "Person_26parts.pbdm")
 d = PartsBasedDetector(device=0)
 d.distributeModel(Model.load_bin(path))
-d.set_option("response_mode", 2)
+d.set_option("response_mode", int(os.environ.get("PBD_TC_MODE", "3")))      # 2: tf32x3, 3: fp16x3
 d.set_option("tc_taps_per_partial", G)
 O = oracle_lib.OracleDetector(Model.load_bin(path).to_flat(), 32)
 oracle_lib.use_all_cores()

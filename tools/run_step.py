@@ -16,7 +16,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--h", type=int, default=480)
 ap.add_argument("--w", type=int, default=640)
 ap.add_argument("--fast", action="store_true")
-ap.add_argument("--mode", type=int, default=-1, help="response mode 0 exact, 1 ffma, 2 tensor")
+ap.add_argument("--mode", type=int, default=-1, help="response mode 0 exact, 1 ffma, 2 tensor (tf32), 3 tensor (fp16)")
 ap.add_argument("--G", type=int, default=0)
 ap.add_argument("--max-levels", type=int, default=0)
 a = ap.parse_args()
