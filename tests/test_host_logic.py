@@ -71,8 +71,10 @@ def test_cpp_adapter_compiles_and_fails_loudly_without_gpu(tmp_path):
                            "-L" + libdir, "-lpbd_b200", "-Wl,-rpath," + libdir, "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 255 and "Usage" in r.stdout                       # -1, src/demo.cpp:58-61
-    r = subprocess.run([exe, "model.mat", "x.ppm"], capture_output=True, text=True)
+    r = subprocess.run([exe, "model.txt", "x.ppm"], capture_output=True, text=True)
     assert r.returncode == 254 and "Unsupported model format" in r.stdout    # -2
+    r = subprocess.run([exe, str(tmp_path / "missing.mat"), "x.ppm"], capture_output=True, text=True)
+    assert r.returncode == 253 and "Error deserializing" in r.stdout         # .mat goes to MatlabIOModel (src/demo.cpp:69-70)
     r = subprocess.run([exe, str(tmp_path / "missing.xml"), "x.ppm"], capture_output=True, text=True)
     assert r.returncode == 253 and "Error deserializing" in r.stdout         # -3
     import torch
