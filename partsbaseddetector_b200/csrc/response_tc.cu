@@ -46,6 +46,8 @@ constexpr int TM = 128;                       // output rows (cells) per tile = 
 constexpr int STRIP_ROWS = 144;               // 128 + 7 (8-row alignment of the copy) + kw-1 <= 9
 constexpr int STRIP_BYTES = STRIP_ROWS * 128;
 constexpr int A_BUFS = 2, B_STAGES = 4;
+constexpr int A_BUFS_F16 = 4;                 // fp16 flavour: a strip is 18 KB, so four filter rows fit (a strip load takes longer than one
+                                              // row's MMAs: with two buffers the issuing warp waits for every strip)
 constexpr int B_STAGES_F16 = 8;               // fp16 flavour: one 128-byte-row slab per tap instead of two => twice the taps in flight
 constexpr int NP_MAX = 160;                   // 3 accumulators of NP columns must fit the 512 TMEM columns
 constexpr int NTHREADS = 256;
@@ -204,17 +206,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
   const uint32_t slab_bytes = (uint32_t)NP * 128u;             // one part (hi or lo) of one tap; fp16: the whole tap
   constexpr uint32_t AP = F16 ? 1u : 2u;                       // parts per A buffer / B stage
   constexpr int BS = F16 ? B_STAGES_F16 : B_STAGES;
-  // A: [A_BUFS][AP parts][STRIP_BYTES], B: [BS][AP parts][slab_bytes]
-  const uint32_t sA = sbase, sB = sbase + (uint32_t)A_BUFS * AP * STRIP_BYTES;
-  __shared__ __align__(8) unsigned long long bars[2 * A_BUFS + 2 * B_STAGES_F16 + 6];
+  constexpr int AB = F16 ? A_BUFS_F16 : A_BUFS;
+  // A: [AB][AP parts][STRIP_BYTES], B: [BS][AP parts][slab_bytes]
+  const uint32_t sA = sbase, sB = sbase + (uint32_t)AB * AP * STRIP_BYTES;
+  __shared__ __align__(8) unsigned long long bars[2 * A_BUFS_F16 + 2 * B_STAGES_F16 + 6];
   __shared__ uint32_t tmem_base_s;
-  const uint32_t fullA = smem_u32(&bars[0]), emptyA = fullA + 8 * A_BUFS, fullB = emptyA + 8 * A_BUFS, emptyB = fullB + 8 * BS;
+  const uint32_t fullA = smem_u32(&bars[0]), emptyA = fullA + 8 * AB, fullB = emptyA + 8 * AB, emptyB = fullB + 8 * BS;
   const uint32_t hFull = emptyB + 8 * BS, hEmpty = hFull + 16, cFull = hEmpty + 16, cEmpty = cFull + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     constexpr unsigned releasers = F16 ? 1 : 2;               // tf32: both MMA warps release; fp16: one warp issues everything
-    for (int i = 0; i < A_BUFS; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, releasers); }
+    for (int i = 0; i < AB; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, releasers); }
     for (int i = 0; i < BS; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, releasers); }
     mbar_init(hFull, 1); mbar_init(hFull + 8, 1); mbar_init(hEmpty, 4); mbar_init(hEmpty + 8, 4);
     mbar_init(cFull, 1); mbar_init(cEmpty, 4);
@@ -242,8 +245,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
         const TcTile S = p.tiles[w - frame * p.n_tiles];
         const int Wp = p.levels[S.level].Wp;
         for (int ky = 0; ky < kh; ++ky, ++it) {
-          const int buf = it % A_BUFS;
-          mbar_wait(emptyA + 8 * buf, ((it / A_BUFS) & 1) ^ 1);
+          const int buf = it % AB;
+          mbar_wait(emptyA + 8 * buf, ((it / AB) & 1) ^ 1);
           mbar_expect_tx(fullA + 8 * buf, F16 ? (uint32_t)STRIP_BYTES : 2u * STRIP_BYTES);
           const long long pstart = (long long)S.q0 + (long long)(ky - ay) * Wp - ax;
           const long long pa = (long long)frame * p.frame_rows + (pstart & ~7ll);
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
           }
           if (++stB == BS) { stB = 0; phB ^= 1; }
         }
-        if (++bufA == A_BUFS) { bufA = 0; phA ^= 1; }
+        if (++bufA == AB) { bufA = 0; phA ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -366,19 +369,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
           taddr = lane_base + (uint32_t)(2 * NP);
         }
         tc_fence_after();
+        // three 16-column loads in flight per wait (one TMEM round trip per 48 columns instead of per 16)
 #pragma unroll
-        for (int c0 = 0; c0 < NP_MAX; c0 += 16) {
+        for (int c0 = 0; c0 < NP_MAX; c0 += 48) {
           if (c0 < NP) {
-            uint32_t v[16];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                         : "r"(taddr + c0));
+            uint32_t v[48];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              if (c0 + 16 * b < NP) {
+                uint32_t* w = v + 16 * b;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+                               "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                             : "r"(taddr + c0 + 16 * b));
+              }
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
-            }
+            for (int j = 0; j < 48; ++j)
+              if (c0 + j < NP_MAX) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
           }
         }
         tc_fence_before();
@@ -530,7 +539,7 @@ int launch_response_tc(const Geometry& g, const DeviceBuffers& b, const FilterBa
   p.nfilters = fb.nfilters; p.NP = response_tc_np(fb.nfilters); p.kh = fb.kh; p.kw = fb.kw;
   const bool per_tap = taps_per_partial == 1;      // hi*hi chains of one tap (most accurate) or of one filter row (default)
   const bool f16 = f16_scales != nullptr;
-  const size_t smem = f16 ? 1024 + (size_t)A_BUFS * STRIP_BYTES + (size_t)B_STAGES_F16 * p.NP * 128
+  const size_t smem = f16 ? 1024 + (size_t)A_BUFS_F16 * STRIP_BYTES + (size_t)B_STAGES_F16 * p.NP * 128
                           : 1024 + (size_t)A_BUFS * 2 * STRIP_BYTES + (size_t)B_STAGES * 2 * p.NP * 128;
   if (f16) for (int j = 0; j < p.NP; ++j) p.out_scale[j] = f16_scales[j];
   const long long total = (long long)n_tiles * g.n_frames;
