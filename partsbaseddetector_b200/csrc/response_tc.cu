@@ -357,7 +357,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
       float acc[NP_MAX];
 #pragma unroll
       for (int j = 0; j < NP_MAX; ++j) acc[j] = 0.f;
-      for (int part = 0; part <= nparts; ++part) {                      // the partial sums, then the correction accumulator
+      // the partial sums and the correction accumulator.  The last partial and the correction accumulator complete together; the
+      // correction accumulator is drained first because the next tile's first tap already needs it (the partial's slot only two
+      // filter rows later)
+      for (int step = 0; step <= nparts; ++step) {
+        const int part = step == nparts - 1 ? nparts : (step == nparts ? nparts - 1 : step);
         uint32_t taddr;
         int hs = 0;
         if (part < nparts) {
