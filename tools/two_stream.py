@@ -14,7 +14,7 @@ from partsbaseddetector_b200.synth import synth_frames  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=10)
-ap.add_argument("--mode", type=int, default=2)
+ap.add_argument("--mode", type=int, default=3)
 a = ap.parse_args()
 H, W = 480, 640
 frames = synth_frames(8, H, W)
