@@ -131,6 +131,8 @@ void parse_matrix(const uint8_t* data, size_t size, bool swap, MatArray& a, int 
   size_t off = name.next;
   const size_t cnt = a.numel();
   if (cnt > (size_t)1 << 28) throw FormatError("MAT file: array too large");
+  // containers: every element needs at least an 8-byte tag inside this element's payload
+  if ((a.cls == mxCELL || a.cls == mxSTRUCT || a.cls == mxOBJECT) && cnt > size / 8) throw FormatError("MAT file: container larger than its data element");
   switch (a.cls) {
     case mxCELL:
       a.cells.resize(cnt);
@@ -153,6 +155,7 @@ void parse_matrix(const uint8_t* data, size_t size, bool swap, MatArray& a, int 
         a.fields.emplace_back(s, strnlen(s, flen));
       }
       off = fn.next;
+      if (nf > size / 8 || cnt * nf > size / 8) throw FormatError("MAT file: struct array larger than its data element");
       a.fvals.resize(cnt * nf);
       for (size_t i = 0; i < cnt * nf; ++i) {
         Element c = read_element(r, off);

@@ -99,6 +99,12 @@ def test_name_defaults_to_file_stem_and_errors(tmp_path):
     with pytest.raises(PbdError):
         MatlabIOModel().deserialize(str(tmp_path / "nobias.mat"))
     raw = open(path, "rb").read()
+    # a cell array claiming 2^27 elements in a 100-byte element must be rejected, not allocated
+    w = MatWriter(False)
+    huge = w.element(6, struct.pack("<II", 1, 0)) + w.element(5, struct.pack("<2i", 1, 1 << 27)) + w.element(1, b"model")
+    (tmp_path / "huge.mat").write_bytes(w.file({})[:128] + w.element(14, huge))
+    with pytest.raises(PbdError):
+        MatlabIOModel().deserialize(str(tmp_path / "huge.mat"))
     (tmp_path / "trunc.mat").write_bytes(raw[: len(raw) // 2])
     with pytest.raises(PbdError):
         MatlabIOModel().deserialize(str(tmp_path / "trunc.mat"))
