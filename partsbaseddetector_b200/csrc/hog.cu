@@ -56,7 +56,11 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float*
   const int PW = HB_X * sbin + sbin + 2 * marg, PH = HB_Y * sbin + sbin + 2 * marg;
   float* smag = reinterpret_cast<float*>(hsm);                       // [PH][PW] gradient magnitude (sqrt(v)); < 0 = pixel not visited
   float* shist = smag + PH * PW;                                     // [18][HB_X*HB_Y] histogram of each thread's block
-  unsigned char* sbo = reinterpret_cast<unsigned char*>(shist + 18 * HB_X * HB_Y);   // [PH][PW] snapped orientation
+  float* sfx = shist + 18 * HB_X * HB_Y;                             // [PW] fractional bin coordinate vx0 of every column of the region
+  float* sfy = sfx + PW;                                             // [PH] ... vy0 of every row
+  int* sbx = reinterpret_cast<int*>(sfy + PH);                       // [PW] floor(xp) of every column, [PH] floor(yp) of every row
+  int* sby = sbx + PW;
+  unsigned char* sbo = reinterpret_cast<unsigned char*>(sby + PH);   // [PH][PW] snapped orientation
 
   const float uu[9] = {(float)1.000, (float)0.9397, (float)0.7660, (float)0.5000, (float)0.1736,
                        (float)-0.1736, (float)-0.5000, (float)-0.7660, (float)-0.9397};
@@ -102,20 +106,30 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float*
   }
 #pragma unroll
   for (int o = 0; o < 18; ++o) shist[o * (HB_X * HB_Y) + threadIdx.x] = 0.f;
+  {
+    // bilinear bin coordinates (:252-257) depend on the pixel column / row only: once per CTA instead of once per (block, pixel)
+    const double dsb = (double)(float)sbin, inv_sb = 1.0 / dsb;
+    const bool pow2 = (sbin & (sbin - 1)) == 0;
+    for (int i = threadIdx.x; i < PW + PH; i += HB_X * HB_Y) {
+      const bool isx = i < PW;
+      const int p = isx ? px0 + i : py0 + (i - PW);
+      const float c = bin_coord(p, sbin, dsb, inv_sb, pow2);
+      const int ic = (int)floorf(c);
+      const float f = __fsub_rn(c, (float)ic);
+      if (isx) { sfx[i] = f; sbx[i] = ic; } else { sfy[i - PW] = f; sby[i - PW] = ic; }
+    }
+  }
   __syncthreads();
 
   // ---- phase 2: one thread per block gathers its window in raster order (bit-identical to the sequential scatter) ----
   const int bx = bx0 + threadIdx.x % HB_X, by = by0 + threadIdx.x / HB_X;
   if (bx >= L.bw || by >= L.bh) return;
-  const double dsb = (double)(float)sbin, inv_sb = 1.0 / dsb;
-  const bool pow2 = (sbin & (sbin - 1)) == 0;
   const int y_lo = max(1, by * sbin - marg), y_hi = min(vis_h - 2, by * sbin + sbin + marg - 1);
   const int x_lo = max(1, bx * sbin - marg), x_hi = min(vis_w - 2, bx * sbin + sbin + marg - 1);
   float* myh = shist + threadIdx.x;
   for (int y = y_lo; y <= y_hi; ++y) {
-    const float yp = bin_coord(y, sbin, dsb, inv_sb, pow2);            // :252
-    const int iyp = (int)floorf(yp);
-    const float vy0 = __fsub_rn(yp, (float)iyp);
+    const int iyp = sby[y - py0];                                      // :252
+    const float vy0 = sfy[y - py0];
     float wy;
     if (iyp == by) wy = (float)(1.0 - (double)vy0);                    // vy1, :258
     else if (iyp == by - 1) wy = vy0;
@@ -123,9 +137,8 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float*
     const float* mrow = smag + (y - py0) * PW - px0;
     const unsigned char* brow = sbo + (y - py0) * PW - px0;
     for (int x = x_lo; x <= x_hi; ++x) {
-      const float xp = bin_coord(x, sbin, dsb, inv_sb, pow2);
-      const int ixp = (int)floorf(xp);
-      const float vx0 = __fsub_rn(xp, (float)ixp);
+      const int ixp = sbx[x - px0];
+      const float vx0 = sfx[x - px0];
       float wx;
       if (ixp == bx) wx = (float)(1.0 - (double)vx0);
       else if (ixp == bx - 1) wx = vx0;
@@ -205,7 +218,7 @@ int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, i
   for (int l = 0; l < g.n_levels; ++l) ntiles += ((g.lv[l].bw + HB_X - 1) / HB_X) * ((g.lv[l].bh + HB_Y - 1) / HB_Y);
   const int marg = (sbin + 1) / 2 + 1;
   const int PW = HB_X * sbin + sbin + 2 * marg, PH = HB_Y * sbin + sbin + 2 * marg;
-  const size_t smem = (size_t)PW * PH * 5 + (size_t)18 * HB_X * HB_Y * 4 + 16;
+  const size_t smem = (size_t)PW * PH * 5 + (size_t)18 * HB_X * HB_Y * 4 + (size_t)(PW + PH) * 8 + 16;   // + the coordinate tables
   // per launch: the attribute is per device and a process may drive several devices
   if (g.in_c == 1) cudaFuncSetAttribute(hog_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   else cudaFuncSetAttribute(hog_hist<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
