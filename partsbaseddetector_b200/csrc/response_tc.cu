@@ -196,8 +196,8 @@ struct TcParams {
 
 // F16 = false: tf32 operands, fhi / flo strips, three split products per tap (4 + 8 MMAs).
 // F16 = true:  fp16 operands, one strip of [F_hi | F_lo] rows and ONE weight slab of [W_hi | W_lo] rows per tap; the three products
-//              F_hi W_hi, F_lo W_hi, F_hi W_lo are K-halves of those rows (2 MMAs of K = 16 each), issued by one warp: 6 MMAs per tap
-//              instead of 12 and half the operand bytes through L2 and shared memory.
+//              F_hi W_hi, F_lo W_hi, F_hi W_lo are K-halves of those rows (2 MMAs of K = 16 each): 6 MMAs per tap instead of 12 and half
+//              the operand bytes through L2 and shared memory.
 template <bool PER_TAP, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    constexpr unsigned releasers = F16 ? 1 : 2;               // tf32: both MMA warps release; fp16: one warp issues everything
+    constexpr unsigned releasers = 2;                         // both MMA warps release
     for (int i = 0; i < AB; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, releasers); }
     for (int i = 0; i < BS; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, releasers); }
     mbar_init(hFull, 1); mbar_init(hFull + 8, 1); mbar_init(hEmpty, 4); mbar_init(hEmpty + 8, 4);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
         }
       }
     }
-  } else if (warp == 2 || (warp == 3 && !F16)) {
+  } else if (warp == 2 || warp == 3) {
     // ===== MMA issuers.  Two warps, because a single warp's instruction latency (not the tensor pipe) bounds the kernel when
     // one warp issues all 12 MMAs of a tap: warp 2 issues the hi*hi products (4 per tap) into the ping-pong partial
     // accumulators [0,NP) / [NP,2NP) -- chains of one tap (PER_TAP) or one filter row -- and warp 3 the lo*hi + hi*lo
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
       const TcTile S = p.tiles[w - frame * p.n_tiles];
       const int Wp = p.levels[S.level].Wp;
       int prow = S.q0 - ay * Wp - ax;                          // first strip row of filter row ky (>= 0 by construction)
-      if (!isH || F16) { mbar_wait(cEmpty, phC); phC ^= 1; }   // the correction accumulator of the previous tile has been read
+      if (!isH) { mbar_wait(cEmpty, phC); phC ^= 1; }          // the correction accumulator of the previous tile has been read
       for (int ky = 0; ky < kh; ++ky, prow += Wp) {
         mbar_wait(fullA + 8 * bufA, phA);
         // descriptor low words = (start address >> 4) | LBO; one strip row = 128 B adds 8, a k-step of 8 tf32 = 32 B adds 2
@@ -307,17 +307,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
                 if (!F16) umma_tf32(dH, ahi + 2 * k, bhi + 2 * k, idesc, (hfirst && k == 0) ? 0u : 1u);
               }
               if (F16) {
-                // k-steps 0, 1 = hi half, 2, 3 = lo half of the 128-byte rows.  F_hi W_hi goes to the ping-pong partial accumulator,
-                // the two small products (2^-11 of it) to the correction accumulator of the tile, where the tensor core's truncating
-                // accumulation costs nothing: the main chain is 2 MMAs per tap
-                const bool first = (ky | kx) == 0;
+                // k-steps 0, 1 = hi half, 2, 3 = lo half of the 128-byte rows.  F_hi W_hi goes to the ping-pong partial accumulator
+                // (2 MMAs per tap); warp 3 issues the two small products (2^-11 of it) into the correction accumulator of the tile,
+                // where the tensor core's truncating accumulation costs nothing
 #pragma unroll
                 for (int k = 0; k < 2; ++k) umma_f16(dH, ahi + 2 * k, bhi + 2 * k, idesc, (hfirst && k == 0) ? 0u : 1u);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) umma_f16(dC, ahi + 4 + 2 * k, bhi + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) umma_f16(dC, ahi + 2 * k, bhi + 4 + 2 * k, idesc, 1u);
-                if (ky == kh - 1 && kx == kw - 1) umma_commit(cFull);
               }
               umma_commit(emptyB + 8 * stB);                 // weight slab consumed once these MMAs retire (and warp 3's)
               if (hlast) umma_commit(hFull + 8 * hs);
@@ -329,10 +323,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) part_response_tc(const TcParams p
             tc_fence_after();
             const bool first = (ky | kx) == 0;
             if (elect_one()) {
+              if (F16) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + a_lo_off + 2 * k, bhi + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+                for (int k = 0; k < 2; ++k) umma_f16(dC, ahi + 4 + 2 * k, bhi + 2 * k, idesc, (first && k == 0) ? 0u : 1u);      // F_lo W_hi
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + 2 * k, bhi + b_lo_off + 2 * k, idesc, 1u);
+                for (int k = 0; k < 2; ++k) umma_f16(dC, ahi + 2 * k, bhi + 4 + 2 * k, idesc, 1u);                               // F_hi W_lo
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + a_lo_off + 2 * k, bhi + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(dC, ahi + 2 * k, bhi + b_lo_off + 2 * k, idesc, 1u);
+              }
               umma_commit(emptyB + 8 * stB);
               if (kx == kw - 1) umma_commit(emptyA + 8 * bufA);
               if (ky == kh - 1 && kx == kw - 1) umma_commit(cFull);
