@@ -125,8 +125,9 @@ struct Ring {
 };
 
 // One lane's 1-D transform.  loady(q) = src[q] (called for q = 0..N-1 in order, in lock step across the warp); reload(v) =
-// src[v] for deep-pop reloads; emit(off, val, v) stores dst[off] = val, ptr[off] = v with off = (pos - os0) * stride (may be
-// called more than once for a position; the last call wins).
+// src[v] for deep-pop reloads; emit(i, val, v) records dst[i] = val, ptr[i] = v for the position index i = pos - os0 in [0, N)
+// (may be called more than once for an index; the last call wins; a run of calls has consecutive indices and never starts
+// beyond the highest index emitted so far + 1); tick(q) is called once per sample step q = 1..N-1, in lock step across the warp.
 //
 // Eager emission: when sample q is pushed with break point s, the previous top P (still in registers) owns exactly the
 // integer positions z_P < pos <= s, and they are evaluated and stored at once.  If q (or P) is popped later, the positions
@@ -141,25 +142,21 @@ struct Ring {
 // The ring holds the newest 8 stack entries for pops (2-3 % of the lane steps); zb/pb are the backing store of the whole
 // envelope as a linked list threaded through the sample index (zb[q] = break point of the parabola pushed at q,
 // pb[q] = the sample below it), written in lock step across lanes (coalesced) and read only by pops deeper than the ring.
-template <typename LoadY, typename Reload, typename Emit>
-PBD_ENV_FN void envelope_stream(int N, const Quad& f, int os0, unsigned stride, Ring& R, int lane, float* zb, unsigned short* pb,
-                                LoadY loady, Reload reload, Emit emit) {
+template <typename LoadY, typename Reload, typename Emit, typename Tick>
+PBD_ENV_FN void envelope_stream(int N, const Quad& f, int os0, Ring& R, int lane, float* zb, unsigned short* pb,
+                                LoadY loady, Reload reload, Emit emit, Tick tick) {
   const int pos_last = os0 + N - 1;
   // positions lo..hi of parabola v (value y): Quadratic::operator()(pos - v, y), :102-104, = (a x^2 + b x) + y with the
   // parenthesis taken from the map's table; e0 / e1 are the table entries of lo and lo + 1
   auto emit_run = [&](int lo, int hi, int v, double yd, double e0, double e1) {
     if (hi >= lo) {
-      unsigned off = (unsigned)(lo - os0) * stride;
-      emit(off, (float)dadd(e0, yd), v);
+      int i = lo - os0;
+      emit(i, (float)dadd(e0, yd), v);
       if (hi > lo) {
-        off += stride;
-        emit(off, (float)dadd(e1, yd), v);
+        emit(++i, (float)dadd(e1, yd), v);
         int x = lo - v + 2;
 #pragma unroll 1
-        for (int pos = lo + 2; pos <= hi; ++pos, ++x) {
-          off += stride;
-          emit(off, (float)dadd(ld_table(f.E, x), yd), v);
-        }
+        for (int pos = lo + 2; pos <= hi; ++pos, ++x) emit(++i, (float)dadd(ld_table(f.E, x), yd), v);
       }
     }
   };
@@ -174,6 +171,7 @@ PBD_ENV_FN void envelope_stream(int N, const Quad& f, int os0, unsigned stride, 
   int lo = os0;
   double e0 = ld_table(f.E, lo - vt), e1 = ld_table(f.E, lo - vt + 1);
   for (int q = 1; q < N; ++q) {                                   // :160-170
+    tick(q);
     const float yqf = loady(q);
     const double yq = (double)yqf;
     float s = isect_adjacent(f, q, yt, yq);                       // the top is sample q - 1
@@ -206,6 +204,40 @@ PBD_ENV_FN void envelope_stream(int N, const Quad& f, int os0, unsigned stride, 
   }
   emit_run(lo, pos_last, vt, yt, e0, e1);
 }
+
+// Write-back window between the eager emission and global memory.  The lanes of a warp run in lock step over the samples, but the
+// positions they emit at a given step differ by a few (and some are emitted twice), so direct stores hit 3-5 different 128-byte lines
+// per instruction -- measured as 30 % of dt_pass.  Each lane therefore parks its last W emissions in a shared-memory column and every
+// step writes back exactly the index (q - D) - os0: the 32 lanes of a warp then store 32 consecutive floats (their lines are
+// consecutive), one line per instruction.  Purely lane-local bookkeeping: `hi` = highest index emitted, `done` = highest index written
+// back; an emission at or below `done` (a late rewrite after a deep pop, or a lane that lags) goes to global memory directly.
+template <int W, int D>
+struct OutWindow {
+  float* sval;              // this lane's column of the window: slot s at sval[s * 32]
+  unsigned short* sptr;
+  int hi, done;
+  PBD_ENV_FN void init(float* sv, unsigned short* sp) { sval = sv; sptr = sp; hi = -1; done = -1; }
+  template <typename Store>
+  PBD_ENV_FN void write_back_to(int upto, Store store) {
+    while (done < upto) {
+      ++done;
+      const int s = done & (W - 1);
+      store(done, sval[s * 32], sptr[s * 32]);
+    }
+  }
+  template <typename Store>
+  PBD_ENV_FN void put(int i, float val, int v, Store store) {
+    if (i <= done) { store(i, val, (unsigned short)v); return; }
+    if (i > done + W) write_back_to(i - W, store);            // a burst longer than the window (every index up to hi >= i - 1 is valid)
+    const int s = i & (W - 1);
+    sval[s * 32] = val; sptr[s * 32] = (unsigned short)v;
+    hi = imax(hi, i);
+  }
+  template <typename Store>
+  PBD_ENV_FN void step(int q, int os0, Store store) { write_back_to(imin(q - D - os0, hi), store); }
+  template <typename Store>
+  PBD_ENV_FN void finish(Store store) { write_back_to(hi, store); }
+};
 
 }  // namespace env
 }  // namespace pbd

@@ -12,7 +12,9 @@ extern "C" {
 // object (each lane only touches its own column).  maxn >= N sizes the tables exactly as the device does
 // (dt_table_len / dt_table_bias of kernels.cuh).  dst/ptr are written [line][pos - os]; every position not stored stays
 // at the caller's fill value.  *stores (optional) counts the emit calls.
-int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int os, int maxn, float* dst, uint16_t* ptr, long long* stores) {
+// window = 0: emissions go straight to dst/ptr; window = 1: through the product's write-back window (OutWindow<8, 5>, as dt_pass)
+int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int os, int maxn, float* dst, uint16_t* ptr, long long* stores,
+              int window) {
   if (N < 1 || N > maxn || nlines < 1 || nlines > 32) return -1;
   const int ne = 2 * maxn - 1 + kTabPad, bias = maxn - 1 - os;
   std::vector<double> tab(ne + kRcp);
@@ -28,11 +30,22 @@ int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int 
     const float* s = src + (size_t)lane * N;
     float* d = dst + (size_t)lane * N;
     uint16_t* p = ptr + (size_t)lane * N;
-    envelope_stream(N, f, os, 1u, R, lane, zb.data(), pb.data(), [&](int q) { return s[q]; }, [&](int v) { return s[v]; },
-                    [&](unsigned off, float val, int v) {
-                      if (off >= (unsigned)N) __builtin_trap();
-                      d[off] = val; p[off] = (uint16_t)v; ++n;
-                    });
+    auto store = [&](int i, float val, unsigned short v) {
+      if (i < 0 || i >= N) __builtin_trap();
+      d[i] = val; p[i] = v; ++n;
+    };
+    if (!window) {
+      envelope_stream(N, f, os, R, lane, zb.data(), pb.data(), [&](int q) { return s[q]; }, [&](int v) { return s[v]; },
+                      [&](int i, float val, int v) { store(i, val, (unsigned short)v); }, [](int) {});
+    } else {
+      float wval[8 * 32];
+      unsigned short wptr[8 * 32];
+      OutWindow<8, 5> win;
+      win.init(wval + lane, wptr + lane);
+      envelope_stream(N, f, os, R, lane, zb.data(), pb.data(), [&](int q) { return s[q]; }, [&](int v) { return s[v]; },
+                      [&](int i, float val, int v) { win.put(i, val, v, store); }, [&](int q) { win.step(q, os, store); });
+      win.finish(store);
+    }
   }
   if (stores) *stores = n;
   return 0;

@@ -26,7 +26,7 @@ def envlib():
         _lib = C.CDLL(out)
         f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
         u16p = np.ctypeslib.ndpointer(np.uint16, flags="C")
-        _lib.envh_dt1d.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, f32p, u16p, C.POINTER(C.c_longlong)]
+        _lib.envh_dt1d.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, f32p, u16p, C.POINTER(C.c_longlong), C.c_int]
         _lib.envh_quotient_fast.argtypes = [C.c_double, C.c_double]
         _lib.envh_quotient_fast.restype = C.c_float
         _lib.envh_quotient_exact.argtypes = [C.c_double, C.c_double]
@@ -35,19 +35,25 @@ def envlib():
 
 
 def run_both(src, w_sq, w_lin, os_, maxn=None):
+    """Direct emission and emission through the write-back window (what dt_pass does) against the oracle; returns the number of
+    stores of the direct variant."""
     nl, N = src.shape
     maxn = maxn or N
-    dst = np.full((nl, N), np.nan, np.float32)
-    ptr = np.full((nl, N), 0xFFFF, np.uint16)
-    stores = C.c_longlong(0)
-    assert envlib().envh_dt1d(np.ascontiguousarray(src), nl, N, w_sq, w_lin, os_, maxn, dst, ptr, C.byref(stores)) == 0
     L = oracle_lib.lib()
-    for i in range(nl):
-        rd, rp = np.empty(N, np.float32), np.empty(N, np.int32)
-        L.orc_dt1d_f32(np.ascontiguousarray(src[i]), N, -float(np.float32(w_sq)), -float(np.float32(w_lin)), os_, rd, rp)
-        assert np.array_equal(dst[i], rd), (i, N, os_)
-        assert np.array_equal(ptr[i].astype(np.int32), rp), (i, N, os_)
-    return stores.value
+    counts = []
+    for window in (0, 1):
+        dst = np.full((nl, N), np.nan, np.float32)
+        ptr = np.full((nl, N), 0xFFFF, np.uint16)
+        stores = C.c_longlong(0)
+        assert envlib().envh_dt1d(np.ascontiguousarray(src), nl, N, w_sq, w_lin, os_, maxn, dst, ptr, C.byref(stores), window) == 0
+        for i in range(nl):
+            rd, rp = np.empty(N, np.float32), np.empty(N, np.int32)
+            L.orc_dt1d_f32(np.ascontiguousarray(src[i]), N, -float(np.float32(w_sq)), -float(np.float32(w_lin)), os_, rd, rp)
+            assert np.array_equal(dst[i], rd), (window, i, N, os_)
+            assert np.array_equal(ptr[i].astype(np.int32), rp), (window, i, N, os_)
+        counts.append(stores.value)
+    assert counts[1] >= nl * N                     # through the window every index is written back at least once
+    return counts[0]
 
 
 def gen(rng, kind, nl, N):
