@@ -219,6 +219,7 @@ struct OutWindow {
   PBD_ENV_FN void init(float* sv, unsigned short* sp) { sval = sv; sptr = sp; hi = -1; done = -1; }
   template <typename Store>
   PBD_ENV_FN void write_back_to(int upto, Store store) {
+#pragma unroll 1
     while (done < upto) {
       ++done;
       const int s = done & (W - 1);
