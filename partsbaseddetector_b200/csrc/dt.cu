@@ -34,7 +34,9 @@ using env::Ring;
 using env::Quad;
 static_assert(env::kRcp == kDtRcp && env::kTabPad == kDtTabPad, "table layout constants of kernels.cuh and dt_envelope.cuh differ");
 constexpr int kPassWarps = 4;
-constexpr int kOutWindow = 8, kOutLag = 5;  // emissions parked per lane; a position is written back kOutLag samples after "its" sample
+#ifdef PBD_DT_WINDOWED_STORES
+constexpr int kOutWindow = 8, kOutLag = 5;  // experiment: emissions parked per lane / write-back lag in samples
+#endif
 constexpr int kTileW = 16;        // samples per line staged per shared-memory tile
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
@@ -71,8 +73,6 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
         const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out, unsigned short* __restrict__ ptr,
         size_t stride_ptr) {
   __shared__ Ring rings[kPassWarps];
-  __shared__ float wval[kPassWarps][kOutWindow][32];              // write-back window of the emissions (env::OutWindow)
-  __shared__ unsigned short wptr[kPassWarps][kOutWindow][32];
   __shared__ float tiles[kPassWarps][2][32][kTileW + 1];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int w = blockIdx.x * kPassWarps + wib;                          // warp index -> (level, first item)
@@ -127,18 +127,23 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
   auto reload = [&](int v) -> float { return __ldg(src + v); };
   // inactive lanes recompute the warp's first item and store the same values to the same addresses as lane 0
   asm volatile("" : "+l"(dst), "+l"(dp));                        // keep both bases as materialised 64-bit registers
-  // emissions go through a per-lane write-back window so that the warp stores one position index per step: 32 consecutive floats
-  // (out[i * nlines + line], the warp's lines are consecutive) instead of 3-5 partially written lines per store instruction
   auto store = [&](int i, float val, unsigned short v) {
     const unsigned off = (unsigned)i * (unsigned)nlines;
     st_f32(dst, off, val); st_u16(dp, off, v);
   };
   const int os0 = M.os;
-#ifdef PBD_DT_DIRECT_STORES                    // A/B switch (tools/build_variant.sh): every emission straight to global memory
-  (void)wval; (void)wptr;
+#ifndef PBD_DT_WINDOWED_STORES
+  // every emission straight to global memory (the default, see below)
   env::envelope_stream(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
                        [&](int i, float val, int v) { store(i, val, (unsigned short)v); }, [](int) {});
 #else
+  // A/B switch (tools/build_variant.sh ... -DPBD_DT_WINDOWED_STORES): emissions through a per-lane shared-memory write-back window
+  // (env::OutWindow) so that a warp stores one position index per step, 32 consecutive floats.  Measured on B200 (round 1): the
+  // stores do become coalesced, but the window's bookkeeping (~20 more instructions per step in an issue-bound kernel) costs more
+  // than the transactions it saves: dt_pass 7.33 -> 9.45 ms per 64 frames.  Kept as an experiment; bit-identical results (GPU parity
+  // suite and tests/test_dt_envelope_host.py).
+  __shared__ float wval[kPassWarps][kOutWindow][32];
+  __shared__ unsigned short wptr[kPassWarps][kOutWindow][32];
   env::OutWindow<kOutWindow, kOutLag> win;
   win.init(&wval[wib][0][lane], &wptr[wib][0][lane]);
   env::envelope_stream(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
