@@ -132,7 +132,12 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
     st_f32(dst, off, val); st_u16(dp, off, v);
   };
   const int os0 = M.os;
-#ifndef PBD_DT_WINDOWED_STORES
+#if defined(PBD_DT_SCAN)
+  // A/B switch (tools/build_variant.sh ... -DPBD_DT_SCAN=4): lagged-scan emission (env::envelope_scan<LAG>), one position per lane and
+  // step, the same index in all lanes.  Bit-identical on the host (tests/test_dt_envelope_host.py); not yet measured on a GPU.
+  env::envelope_scan<PBD_DT_SCAN>(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
+                                  [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
+#elif !defined(PBD_DT_WINDOWED_STORES)
   // every emission straight to global memory (the default, see below)
   env::envelope_stream(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
                        [&](int i, float val, int v) { store(i, val, (unsigned short)v); }, [](int) {});

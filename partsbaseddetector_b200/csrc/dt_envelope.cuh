@@ -205,6 +205,86 @@ PBD_ENV_FN void envelope_stream(int N, const Quad& f, int os0, Ring& R, int lane
   emit_run(lo, pos_last, vt, yt, e0, e1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Lagged-scan variant (an experiment for the next round; not used by dt_pass yet).  Same stack construction as envelope_stream,
+// but instead of emitting the top's whole range when its successor is pushed (and again after every pop), every step emits exactly
+// the positions up to q - LAG through a cursor that walks up the stack: in steady state ONE position per lane per step, the same
+// position index in all lanes of a warp (coalesced stores, no repeated stores).  The invariant is "every position below `pe` has
+// been emitted according to the CURRENT stack"; a push or pop that changes the owner of an already emitted position (a break point
+// more than LAG positions behind its sample: rare) rewinds `pe` and the cursor, and the lane catches up in the same step.  Emission
+// order is ascending except after a rewind; the last emission of an index is the reference's scan result, as in envelope_stream.
+template <int LAG, typename LoadY, typename Reload, typename Emit>
+PBD_ENV_FN void envelope_scan(int N, const Quad& f, int os0, Ring& R, int lane, float* zb, unsigned short* pb, LoadY loady, Reload reload,
+                              Emit emit) {
+  const int pos_last = os0 + N - 1;
+  int k = 0, base = 0;                                            // stack depth of the top; lowest depth still valid in the ring
+  int vt = 0, pt = 0xFFFF;                                        // the top's sample and the sample below it
+  float ytf = loady(0), zt = -INFINITY;
+  double yt = (double)ytf;
+  R.z[0][lane] = zt; R.y[0][lane] = ytf; R.vp[0][lane] = 0xFFFF0000u;
+  zb[0] = zt; pb[0] = 0xFFFF;
+  // cursor: `pe` = next position to emit; (kc, vc, yc) = a stack entry with z[kc] < pe; zhi = z[kc + 1] (+inf for the top)
+  int pe = os0, kc = 0, vc = 0;
+  double yc = yt;
+  float zhi = INFINITY;
+  auto first_after = [&](float z) { return imax(imin(f2i_floor(z), pos_last) + 1, os0); };   // first position > z, clipped (saturating)
+  auto emit_upto = [&](int target) {
+#pragma unroll 1
+    while (pe <= target) {
+#pragma unroll 1
+      while (zhi < (float)pe) {                                   // :176 `while (z[k+1] < q) k++`
+        ++kc;
+        if (kc == k) { vc = vt; yc = yt; zhi = INFINITY; }
+        else if (kc >= base) {
+          const int slot = kc & (kRing - 1);
+          vc = R.vp[slot][lane] & 0xFFFF; yc = (double)R.y[slot][lane]; zhi = R.z[(kc + 1) & (kRing - 1)][lane];
+        } else {                                                  // the cursor is below the ring (rare): walk down the backing store
+          int d = base;
+          const unsigned vpw = R.vp[base & (kRing - 1)][lane];
+          int above = vpw & 0xFFFF, below = vpw >> 16;             // samples at depth d and d - 1
+#pragma unroll 1
+          while (d > kc + 1) { above = below; below = pb[above]; --d; }
+          vc = below; yc = (double)reload(vc); zhi = zb[above];
+        }
+      }
+      emit(pe - os0, (float)dadd(ld_table(f.E, pe - vc), yc), vc);
+      ++pe;
+    }
+  };
+  for (int q = 1; q < N; ++q) {                                   // :160-170
+    const float yqf = loady(q);
+    const double yq = (double)yqf;
+    float s = isect_adjacent(f, q, yt, yq);                       // the top is sample q - 1
+    if (s <= zt && k > 0) {
+      do {
+        --k;
+        const int slot = k & (kRing - 1);
+        if (k < base) {                                           // popped below the ring: reload from the backing store
+          base = k;
+          const int vv = pt;
+          R.vp[slot][lane] = (unsigned)vv | ((unsigned)pb[vv] << 16); R.z[slot][lane] = zb[vv]; R.y[slot][lane] = reload(vv);
+        }
+        const unsigned vp = R.vp[slot][lane];
+        vt = vp & 0xFFFF; pt = vp >> 16; ytf = R.y[slot][lane]; yt = (double)ytf; zt = R.z[slot][lane];
+        s = isect_far(f, vt, q, yt, yq);
+      } while (s <= zt && k > 0);
+      // everything above the new top T is gone: positions beyond z_T have to be (re-)emitted by T or by q
+      if (kc > k) { kc = k; vc = vt; yc = yt; }
+      pe = imin(pe, first_after(zt));
+    }
+    ++k;                                                          // push q
+    base = imax(base, k - (kRing - 1));
+    const int slot = k & (kRing - 1);
+    R.vp[slot][lane] = (unsigned)q | ((unsigned)vt << 16); R.y[slot][lane] = yqf; R.z[slot][lane] = s;
+    zb[q] = s; pb[q] = (unsigned short)vt;
+    if (kc == k - 1) zhi = s;                                     // the cursor's entry is the old top: its range now ends at s
+    pe = imin(pe, first_after(s));                                // positions beyond s belong to q from now on
+    pt = vt; vt = q; ytf = yqf; yt = yq; zt = s;
+    emit_upto(imin(q - LAG, pos_last));
+  }
+  emit_upto(pos_last);
+}
+
 // Write-back window between the eager emission and global memory.  The lanes of a warp run in lock step over the samples, but the
 // positions they emit at a given step differ by a few (and some are emitted twice), so direct stores hit 3-5 different 128-byte lines
 // per instruction -- measured as 30 % of dt_pass.  Each lane therefore parks its last W emissions in a shared-memory column and every

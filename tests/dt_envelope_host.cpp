@@ -12,7 +12,8 @@ extern "C" {
 // object (each lane only touches its own column).  maxn >= N sizes the tables exactly as the device does
 // (dt_table_len / dt_table_bias of kernels.cuh).  dst/ptr are written [line][pos - os]; every position not stored stays
 // at the caller's fill value.  *stores (optional) counts the emit calls.
-// window = 0: emissions go straight to dst/ptr; window = 1: through the product's write-back window (OutWindow<8, 5>, as dt_pass)
+// window = 0: emissions go straight to dst/ptr; window = 1: through the write-back window (OutWindow<8, 5>);
+// window = 2 / 3 / 4: the lagged-scan variant envelope_scan with LAG = 4 / 1 / 12
 int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int os, int maxn, float* dst, uint16_t* ptr, long long* stores,
               int window) {
   if (N < 1 || N > maxn || nlines < 1 || nlines > 32) return -1;
@@ -34,7 +35,13 @@ int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int 
       if (i < 0 || i >= N) __builtin_trap();
       d[i] = val; p[i] = v; ++n;
     };
-    if (!window) {
+    if (window >= 2) {
+      auto ld = [&](int q) { return s[q]; };
+      auto em = [&](int i, float val, int v) { store(i, val, (unsigned short)v); };
+      if (window == 2) envelope_scan<4>(N, f, os, R, lane, zb.data(), pb.data(), ld, ld, em);
+      else if (window == 3) envelope_scan<1>(N, f, os, R, lane, zb.data(), pb.data(), ld, ld, em);
+      else envelope_scan<12>(N, f, os, R, lane, zb.data(), pb.data(), ld, ld, em);
+    } else if (!window) {
       envelope_stream(N, f, os, R, lane, zb.data(), pb.data(), [&](int q) { return s[q]; }, [&](int v) { return s[v]; },
                       [&](int i, float val, int v) { store(i, val, (unsigned short)v); }, [](int) {});
     } else {

@@ -41,7 +41,7 @@ def run_both(src, w_sq, w_lin, os_, maxn=None):
     maxn = maxn or N
     L = oracle_lib.lib()
     counts = []
-    for window in (0, 1):
+    for window in (0, 1, 2, 3, 4):                 # direct, write-back window, lagged scan with LAG = 4 / 1 / 12
         dst = np.full((nl, N), np.nan, np.float32)
         ptr = np.full((nl, N), 0xFFFF, np.uint16)
         stores = C.c_longlong(0)
@@ -52,7 +52,8 @@ def run_both(src, w_sq, w_lin, os_, maxn=None):
             assert np.array_equal(dst[i], rd), (window, i, N, os_)
             assert np.array_equal(ptr[i].astype(np.int32), rp), (window, i, N, os_)
         counts.append(stores.value)
-    assert counts[1] >= nl * N                     # through the window every index is written back at least once
+    assert min(counts[1:]) >= nl * N               # every variant stores every index at least once
+    run_both.last_counts = counts
     return counts[0]
 
 
