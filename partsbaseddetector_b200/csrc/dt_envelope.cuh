@@ -16,6 +16,11 @@
 #define PBD_ENV_NOINLINE inline
 #endif
 
+// statistics hook of the host test build (counts loop iterations per step); expands to nothing in the product
+#ifndef PBD_ENV_STAT
+#define PBD_ENV_STAT(name)
+#endif
+
 namespace pbd {
 namespace env {
 
@@ -178,6 +183,7 @@ PBD_ENV_FN void envelope_stream(int N, const Quad& f, int os0, Ring& R, int lane
     if (s <= zt && k > 0) {
       do {
         --k;
+        PBD_ENV_STAT(pop)
         const int slot = k & (kRing - 1);
         if (k < base) {                                           // popped below the ring: reload from the backing store
           base = k;
@@ -234,6 +240,7 @@ PBD_ENV_FN void envelope_scan(int N, const Quad& f, int os0, Ring& R, int lane, 
 #pragma unroll 1
       while (zhi < (float)pe) {                                   // :176 `while (z[k+1] < q) k++`
         ++kc;
+        PBD_ENV_STAT(adv)
         if (kc == k) { vc = vt; yc = yt; zhi = INFINITY; }
         else if (kc >= base) {
           const int slot = kc & (kRing - 1);
@@ -258,6 +265,7 @@ PBD_ENV_FN void envelope_scan(int N, const Quad& f, int os0, Ring& R, int lane, 
     if (s <= zt && k > 0) {
       do {
         --k;
+        PBD_ENV_STAT(pop)
         const int slot = k & (kRing - 1);
         if (k < base) {                                           // popped below the ring: reload from the backing store
           base = k;

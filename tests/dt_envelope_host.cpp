@@ -3,6 +3,9 @@
 #include <cstdint>
 #include <vector>
 
+// per-step loop statistics of the lock-step (warp) execution model: see envh_stats below
+static thread_local int g_stat_pop = 0, g_stat_adv = 0;
+#define PBD_ENV_STAT(name) ++g_stat_##name;
 #include "../partsbaseddetector_b200/csrc/dt_envelope.cuh"
 
 using namespace pbd::env;
@@ -55,6 +58,37 @@ int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int 
     }
   }
   if (stores) *stores = n;
+  return 0;
+}
+// Loop iterations per (line, sample step) of one variant (0 = eager envelope_stream, 2 = envelope_scan<4>): pops, emissions and cursor
+// advances, each [nlines][N] (step q = everything between loady(q) and loady(q + 1); the tail after the last sample counts for
+// step N - 1).  A warp executes max-over-its-32-lines iterations of each loop, which is what tools/dt_warp_model.py evaluates.
+int envh_stats(const float* src, int nlines, int N, float w_sq, float w_lin, int os, int variant, int* pops, int* emits, int* advs) {
+  const int maxn = N;
+  const int ne = 2 * maxn - 1 + kTabPad, bias = maxn - 1 - os;
+  std::vector<double> tab(ne + kRcp);
+  const double a = (double)(-w_sq), b = (double)(-w_lin);
+  for (int j = 0; j < ne; ++j) tab[j] = table_E(a, b, j - bias);
+  for (int j = 0; j < kRcp; ++j) tab[ne + j] = table_rcp(a, j);
+  const Quad f = make_quad(w_sq, w_lin, tab.data() + bias, tab.data() + ne);
+  Ring R;
+  std::vector<float> zb(N);
+  std::vector<unsigned short> pb(N);
+  for (int line = 0; line < nlines; ++line) {
+    const float* s = src + (size_t)line * N;
+    int* P = pops + (size_t)line * N; int* E = emits + (size_t)line * N; int* A = advs + (size_t)line * N;
+    for (int q = 0; q < N; ++q) P[q] = E[q] = A[q] = 0;
+    int cur = 0, ne_cur = 0;
+    g_stat_pop = g_stat_adv = 0;
+    auto flush = [&]() { P[cur] += g_stat_pop; A[cur] += g_stat_adv; E[cur] += ne_cur; g_stat_pop = g_stat_adv = 0; ne_cur = 0; };
+    auto ld = [&](int q) { if (q >= 1) { flush(); cur = q; } return s[q]; };   // step q starts with its load
+    auto rl = [&](int v) { return s[v]; };
+    auto em = [&](int, float, int) { ++ne_cur; };
+    if (variant == 0) envelope_stream(N, f, os, R, line & 31, zb.data(), pb.data(), ld, rl, em, [](int) {});
+    else envelope_scan<4>(N, f, os, R, line & 31, zb.data(), pb.data(), ld, rl, em);
+    flush();
+    // attribute the work done before sample 1 (none) and shift: step q's record holds the work triggered by sample q
+  }
   return 0;
 }
 // the two quotient paths side by side (for the reciprocal / Markstein test)
