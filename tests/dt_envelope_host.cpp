@@ -91,6 +91,57 @@ int envh_stats(const float* src, int nlines, int N, float w_sq, float w_lin, int
   }
   return 0;
 }
+// Prototype of the parallel-in-q schedule of the same algorithm: phase A computes every adjacent intersection
+// independently, phase B repairs the pop sites only (implicit stack: pred(q) = q - 1, z(q) = s_q unless q is a site), phase C emits per
+// surviving entry.  Written with the product header's primitives; must equal the oracle bit for bit.  stats[0..3] += sites, pop
+// iterations, surviving entries, candidate sites (s_q <= s_{q-1}).
+int envh_dt1d_parallel(const float* src, int nlines, int N, float w_sq, float w_lin, int os, float* dst, uint16_t* ptr, long long* stats) {
+  const int maxn = N;
+  const int ne = 2 * maxn - 1 + kTabPad, bias = maxn - 1 - os;
+  std::vector<double> tab(ne + kRcp);
+  const double a = (double)(-w_sq), b = (double)(-w_lin);
+  for (int j = 0; j < ne; ++j) tab[j] = table_E(a, b, j - bias);
+  for (int j = 0; j < kRcp; ++j) tab[ne + j] = table_rcp(a, j);
+  const Quad f = make_quad(w_sq, w_lin, tab.data() + bias, tab.data() + ne);
+  const int pos_last = os + N - 1;
+  std::vector<float> s(N), z(N);
+  std::vector<int> pred(N), alive;
+  for (int line = 0; line < nlines; ++line) {
+    const float* y = src + (size_t)line * N;
+    float* d = dst + (size_t)line * N;
+    uint16_t* p = ptr + (size_t)line * N;
+    // phase A: independent per q
+    s[0] = -INFINITY;
+    for (int q = 1; q < N; ++q) s[q] = isect_adjacent(f, q, (double)y[q - 1], (double)y[q]);
+    for (int q = 2; q < N; ++q) if (s[q] <= s[q - 1]) ++stats[3];
+    // phase B: sequential only at the pop sites
+    z[0] = -INFINITY; pred[0] = -1;
+    for (int q = 1; q < N; ++q) {
+      int v = q - 1;
+      float sq = s[q];
+      if (sq <= z[v] && v != 0) {                                 // the top q - 1 is not the bottom entry: :163 `while (s <= z[k])`
+        ++stats[0];
+        do {
+          v = pred[v];
+          ++stats[1];
+          sq = isect_far(f, v, q, (double)y[v], (double)y[q]);
+        } while (sq <= z[v] && v != 0);
+      }
+      z[q] = sq; pred[q] = v;
+    }
+    // phase C: per surviving entry (independent)
+    alive.clear();
+    for (int v = N - 1; v >= 0; v = pred[v]) alive.push_back(v);
+    stats[2] += (long long)alive.size();
+    for (size_t i = alive.size(); i-- > 0;) {
+      const int v = alive[i];
+      const float zlo = z[v], zhi = i == 0 ? INFINITY : z[alive[i - 1]];
+      const int lo = imax(imin(f2i_floor(zlo), pos_last) + 1, os), hi = imin(f2i_floor(zhi), pos_last);
+      for (int pos = lo; pos <= hi; ++pos) { d[pos - os] = (float)dadd(ld_table(f.E, pos - v), (double)y[v]); p[pos - os] = (uint16_t)v; }
+    }
+  }
+  return 0;
+}
 // the two quotient paths side by side (for the reciprocal / Markstein test)
 float envh_quotient_fast(double num, double den) { return quotient_to_float(num, den, drcp(den)); }
 float envh_quotient_exact(double num, double den) { return quotient_exact(num, den); }

@@ -27,6 +27,8 @@ def envlib():
         f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
         u16p = np.ctypeslib.ndpointer(np.uint16, flags="C")
         _lib.envh_dt1d.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, f32p, u16p, C.POINTER(C.c_longlong), C.c_int]
+        _lib.envh_dt1d_parallel.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, f32p, u16p,
+                                            np.ctypeslib.ndpointer(np.int64, flags="C")]
         _lib.envh_quotient_fast.argtypes = [C.c_double, C.c_double]
         _lib.envh_quotient_fast.restype = C.c_float
         _lib.envh_quotient_exact.argtypes = [C.c_double, C.c_double]
@@ -52,6 +54,16 @@ def run_both(src, w_sq, w_lin, os_, maxn=None):
             assert np.array_equal(dst[i], rd), (window, i, N, os_)
             assert np.array_equal(ptr[i].astype(np.int32), rp), (window, i, N, os_)
         counts.append(stores.value)
+    # the parallel-in-q schedule of the same algorithm (prototype for the next kernel generation)
+    dst = np.full((nl, N), np.nan, np.float32)
+    ptr = np.full((nl, N), 0xFFFF, np.uint16)
+    stats = np.zeros(4, np.int64)
+    assert envlib().envh_dt1d_parallel(np.ascontiguousarray(src), nl, N, w_sq, w_lin, os_, dst, ptr, stats) == 0
+    for i in range(nl):
+        rd, rp = np.empty(N, np.float32), np.empty(N, np.int32)
+        L.orc_dt1d_f32(np.ascontiguousarray(src[i]), N, -float(np.float32(w_sq)), -float(np.float32(w_lin)), os_, rd, rp)
+        assert np.array_equal(dst[i], rd) and np.array_equal(ptr[i].astype(np.int32), rp), ("parallel", i, N, os_)
+    run_both.last_stats = stats
     assert min(counts[1:]) >= nl * N               # every variant stores every index at least once
     run_both.last_counts = counts
     return counts[0]

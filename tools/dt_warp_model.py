@@ -56,3 +56,31 @@ for variant, name in ((0, "eager (envelope_stream)"), (2, "lagged scan (envelope
     else:
         est = 86 + 66 * t[0] + 13 * t[1] + 12 * t[2]
     print("%-32s estimated warp instructions per step: %.0f" % ("", est))
+
+# ---- parallel-in-q schedule: how much sequential work is left? ----
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C")
+L.envh_dt1d_parallel.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, f32p, u16p, i64p]
+samples = sites = pops = alive = cand = 0
+warp_sites = warp_pops = warps = 0
+for level in (0, 1, 3, 6):
+    for part in (25, 20, 13, 7):
+        P = fm.comps[0][part]
+        for fid, did in zip(P.filterid, P.defid):
+            resp = np.ascontiguousarray(O.response(level, fid))
+            w = fm.defs[did]
+            nl, N = resp.shape
+            per = np.zeros((nl, 4), np.int64)
+            dst, ptr = np.empty(N, np.float32), np.empty(N, np.uint16)
+            for i in range(nl):
+                L.envh_dt1d_parallel(resp[i], 1, N, float(w[0]), float(w[1]), int(fm.anchors[did][0]), dst, ptr, per[i])
+            samples += nl * N; sites += per[:, 0].sum(); pops += per[:, 1].sum(); alive += per[:, 2].sum(); cand += per[:, 3].sum()
+            nw = nl // 32
+            if nw:
+                blk = per[: nw * 32].reshape(nw, 32, 4)
+                warp_sites += blk[:, :, 0].max(axis=1).sum(); warp_pops += blk[:, :, 1].max(axis=1).sum(); warps += nw
+                wsamples = nw * N if level == 0 and part == 25 and fid == P.filterid[0] else None
+print("parallel-in-q schedule: pop sites %.3f per sample (candidates s_q <= s_{q-1}: %.3f), pop iterations %.3f per sample, surviving entries %.3f per sample"
+      % (sites / samples, cand / samples, pops / samples, alive / samples))
+print("lane per line, lock step over the i-th site of 32 lines: %.1f site rounds and %.1f pop iterations per warp and line "
+      "(lane average %.1f sites per line)" % (warp_sites / warps, warp_pops / warps, sites / (samples / 158.0) if samples else 0))
