@@ -211,6 +211,15 @@ int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int 
 /* host-buffer convenience wrapper of the above (allocates, copies, runs, copies back) */
 int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy,
                  float* out, int32_t* ix, int32_t* iy, int backptr_mode);
+/* The same transform with every table and scratch buffer owned by a plan, so that pbd_dt2d_plan_run only enqueues kernels on
+ * `stream` (no allocation, no synchronisation): what the DT microbenchmark times.  impl: 0 = default (1), 1 = streaming envelope
+ * (one lane per line, any length <= 4096; the kernels the detector runs), 2 = parallel-in-q (a warp per batch of lines in shared
+ * memory, lines <= 1024; bit-identical, kept as a measured alternative). */
+typedef struct pbd_dt2d_plan pbd_dt2d_plan;
+int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, int impl, pbd_dt2d_plan** out);
+int pbd_dt2d_plan_impl(const pbd_dt2d_plan* p);
+int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode);
+void pbd_dt2d_plan_destroy(pbd_dt2d_plan* p);
 
 /* ----------------------------------------------------------- measurement --- */
 /* number of kernels launched by this detector since creation (bench.py's gpu_launches) */

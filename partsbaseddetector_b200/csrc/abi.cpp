@@ -33,6 +33,22 @@ int guarded(F f) {
   catch (...) { g_err = "unknown error"; return PBD_E_ARG; }
 }
 #define REQUIRE(cond, msg) do { if (!(cond)) throw ArgError(msg); } while (0)
+
+// Every entry point that touches a detector makes the detector's device current for the duration of the call and restores the
+// caller's device afterwards: a process may hold detectors on several devices, and a host thread's current device is whatever its
+// last caller left behind.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  explicit DeviceGuard(int device) : dev(device) {
+    if (dev < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) throw CudaError("cudaSetDevice failed");
+  }
+  ~DeviceGuard() { if (dev >= 0 && prev >= 0 && prev != dev) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+inline int dev_of(const pbd_detector* d) { return d && d->e ? d->e->device() : -1; }
 }  // namespace
 
 extern "C" {
@@ -165,10 +181,13 @@ int pbd_create(const pbd_model* m, int device, void* stream, pbd_detector** out)
     *out = d.release();
   });
 }
-void pbd_destroy(pbd_detector* d) { delete d; }
+void pbd_destroy(pbd_detector* d) {
+  if (!d) return;
+  try { DeviceGuard dg_(dev_of(d)); delete d; } catch (...) { delete d; }
+}
 
 int pbd_set_option(pbd_detector* d, const char* key, double value) {
-  return guarded([&] {
+  return guarded([&] { DeviceGuard dg_(dev_of(d));
     REQUIRE(d && key, "null argument");
     Engine& e = *d->e;
     const std::string k(key);
@@ -182,11 +201,12 @@ int pbd_set_option(pbd_detector* d, const char* key, double value) {
     else if (k == "timing") e.timing = value >= 2 ? 2 : (value != 0);
     else if (k == "nms_overlap") { REQUIRE(value < 1.0, "nms_overlap must be < 1 (negative = off)"); e.nms_overlap = value; }
     else if (k == "dp_streams") { REQUIRE(value >= 1 && value <= 8, "dp_streams must be 1..8"); e.dp_streams = (int)value; }
+    else if (k == "graph") e.use_graph = value != 0;
     else throw ArgError("unknown option '" + k + "'");
   });
 }
 int pbd_get_option(const pbd_detector* d, const char* key, double* value) {
-  return guarded([&] {
+  return guarded([&] { DeviceGuard dg_(dev_of(d));
     REQUIRE(d && key && value, "null argument");
     const Engine& e = *d->e;
     const std::string k(key);
@@ -199,6 +219,7 @@ int pbd_get_option(const pbd_detector* d, const char* key, double* value) {
     else if (k == "max_candidates") *value = e.max_candidates;
     else if (k == "timing") *value = e.timing;
     else if (k == "dp_streams") *value = e.dp_streams;
+    else if (k == "graph") *value = e.use_graph;
     else if (k == "nms_overlap") *value = e.nms_overlap;
     else throw ArgError("unknown option '" + k + "'");
   });
@@ -208,7 +229,7 @@ static void run_all(Engine& e) { e.run_pyramid(); e.run_pdf(); e.run_dp_min(); e
 
 int pbd_detect_batch_u8(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c, size_t row_stride, size_t frame_stride,
                         pbd_candidates** out) {
-  return guarded([&] {
+  return guarded([&] { DeviceGuard dg_(dev_of(d));
     REQUIRE(d && frames && out, "null argument");
     Engine& e = *d->e;
     e.set_frames_geometry(n, h, w, c);
@@ -220,7 +241,7 @@ int pbd_detect_batch_u8(pbd_detector* d, const uint8_t* frames, int n, int h, in
   });
 }
 int pbd_detect_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, int h, int w, int c, pbd_candidates** out) {
-  return guarded([&] {
+  return guarded([&] { DeviceGuard dg_(dev_of(d));
     REQUIRE(d && d_frames && out, "null argument");
     Engine& e = *d->e;
     e.set_frames_geometry(n, h, w, c);
@@ -232,23 +253,20 @@ int pbd_detect_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, 
   });
 }
 int pbd_enqueue_batch_u8_device(pbd_detector* d, const uint8_t* d_frames, int n, int h, int w, int c) {
-  return guarded([&] {
+  return guarded([&] { DeviceGuard dg_(dev_of(d));
     REQUIRE(d && d_frames, "null argument");
-    Engine& e = *d->e;
-    e.set_frames_geometry(n, h, w, c);
-    e.use_device_frames(d_frames);
-    run_all(e);
+    d->e->enqueue_device(d_frames, n, h, w, c);
   });
 }
 int pbd_collect_candidates(pbd_detector* d, pbd_candidates** out) {
-  return guarded([&] { REQUIRE(d && out, "null argument"); auto cs = std::make_unique<pbd_candidates>(); d->e->collect(cs->s); *out = cs.release(); });
+  return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && out, "null argument"); auto cs = std::make_unique<pbd_candidates>(); d->e->collect(cs->s); *out = cs.release(); });
 }
 
 int pbd_submit_batch_u8(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c, int* ticket) {
-  return guarded([&] { REQUIRE(d && frames && ticket, "null argument"); *ticket = d->e->submit(frames, n, h, w, c); });
+  return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && frames && ticket, "null argument"); *ticket = d->e->submit(frames, n, h, w, c); });
 }
 int pbd_collect_ticket(pbd_detector* d, int ticket, pbd_candidates** out) {
-  return guarded([&] {
+  return guarded([&] { DeviceGuard dg_(dev_of(d));
     REQUIRE(d && out, "null argument");
     auto cs = std::make_unique<pbd_candidates>();
     d->e->collect_ticket(ticket, cs->s);
@@ -328,14 +346,21 @@ int pbd_candidates_nms(pbd_candidates* c, int im_h, int im_w, float overlap) {
   return guarded([&] {
     REQUIRE(c && im_h > 0 && im_w > 0, "bad argument");
     const CandidateSet& S = c->s;
-    std::vector<int> kept;
-    kept.reserve(S.n);
+    // Candidate::nonMaximaSuppression works on one image's candidates in list order.  A batch's list may interleave frames (a global
+    // score sort does), so the candidates are grouped by frame (stable: list order inside a frame is kept), the greedy painting runs
+    // per frame on its own scratch image, and the survivors are returned in the original list order.
+    std::vector<int> by_frame(S.n);
+    for (int i = 0; i < S.n; ++i) by_frame[i] = i;
+    std::stable_sort(by_frame.begin(), by_frame.end(), [&](int a, int b) { return S.meta[(size_t)a * 4] < S.meta[(size_t)b * 4]; });
+    std::vector<char> keep_flag(S.n, 0);
     std::vector<uint8_t> scratch((size_t)im_h * im_w);
     const IRect bounds{0, 0, im_w, im_h};
-    int cur_frame = -1 << 30;
-    for (int i = 0; i < S.n; ++i) {
+    int cur_frame = 0;
+    bool first = true;
+    for (int k = 0; k < S.n; ++k) {
+      const int i = by_frame[k];
       const int frame = S.meta[(size_t)i * 4], np = S.meta[(size_t)i * 4 + 3];
-      if (frame != cur_frame) { std::fill(scratch.begin(), scratch.end(), 0); cur_frame = frame; }   // one scratch image per frame
+      if (first || frame != cur_frame) { std::fill(scratch.begin(), scratch.end(), 0); cur_frame = frame; first = false; }
       const int* p0 = S.part(i, 0);
       IRect hull{p0[3], p0[4], p0[5], p0[6]};                                        // Candidate::boundingBox, :104-110
       for (int p = 0; p < np; ++p) { const int* o = S.part(i, p); hull = rect_or(hull, IRect{o[3], o[4], o[5], o[6]}); }
@@ -345,8 +370,11 @@ int pbd_candidates_nms(pbd_candidates* c, int im_h, int im_w, float overlap) {
       const double ratio = (double)sum / (box.w * box.h);                             // boxsum[0] / box.area() (NaN for an empty box => kept)
       if (ratio > (double)overlap) continue;
       for (int y = box.y; y < box.y + box.h; ++y) memset(&scratch[(size_t)y * im_w + box.x], 1, (size_t)box.w);
-      kept.push_back(i);
+      keep_flag[i] = 1;
     }
+    std::vector<int> kept;
+    kept.reserve(S.n);
+    for (int i = 0; i < S.n; ++i) if (keep_flag[i]) kept.push_back(i);
     c->s.select(kept);
   });
 }
@@ -367,7 +395,7 @@ int pbd_candidates_create(int n, int max_nparts, const int32_t* meta4, const flo
 }
 
 int pbd_stage_pyramid(pbd_detector* d, const uint8_t* frames, int n, int h, int w, int c, size_t row_stride, size_t frame_stride) {
-  return guarded([&] {
+  return guarded([&] { DeviceGuard dg_(dev_of(d));
     REQUIRE(d && frames, "null argument");
     Engine& e = *d->e;
     e.set_frames_geometry(n, h, w, c);
@@ -375,10 +403,10 @@ int pbd_stage_pyramid(pbd_detector* d, const uint8_t* frames, int n, int h, int 
     e.run_pyramid();
   });
 }
-int pbd_stage_pdf(pbd_detector* d) { return guarded([&] { REQUIRE(d, "null argument"); d->e->run_pdf(); }); }
-int pbd_stage_dp_min(pbd_detector* d) { return guarded([&] { REQUIRE(d, "null argument"); d->e->run_dp_min(); }); }
+int pbd_stage_pdf(pbd_detector* d) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d, "null argument"); d->e->run_pdf(); }); }
+int pbd_stage_dp_min(pbd_detector* d) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d, "null argument"); d->e->run_dp_min(); }); }
 int pbd_stage_dp_argmin(pbd_detector* d, pbd_candidates** out) {
-  return guarded([&] {
+  return guarded([&] { DeviceGuard dg_(dev_of(d));
     REQUIRE(d && out, "null argument");
     d->e->run_argmin();
     auto cs = std::make_unique<pbd_candidates>();
@@ -401,7 +429,7 @@ int pbd_pyramid_geometry(int h, int w, int sbin, int interval, int max_levels, i
 int pbd_num_frames(const pbd_detector* d) { return d ? d->e->geom().n_frames : 0; }
 int pbd_num_levels(const pbd_detector* d) { return d ? d->e->geom().n_levels : 0; }
 int pbd_level_info(const pbd_detector* d, int level, int32_t* img_h, int32_t* img_w, int32_t* oh, int32_t* ow, float* scale) {
-  return guarded([&] {
+  return guarded([&] { DeviceGuard dg_(dev_of(d));
     REQUIRE(d && level >= 0 && level < d->e->geom().n_levels, "level out of range");
     const LevelDesc& L = d->e->geom().lv[level];
     if (img_h) *img_h = L.img_h;
@@ -412,85 +440,152 @@ int pbd_level_info(const pbd_detector* d, int level, int32_t* img_h, int32_t* im
   });
 }
 
-int pbd_get_pyramid_image(pbd_detector* d, int frame, int level, uint8_t* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_pyramid_image(frame, level, dst); }); }
-int pbd_get_features(pbd_detector* d, int frame, int level, float* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_features(frame, level, dst); }); }
-int pbd_get_response(pbd_detector* d, int frame, int level, int filter, float* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_response(frame, level, filter, dst); }); }
-int pbd_get_rootv(pbd_detector* d, int frame, int level, int component, float* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_rootv(frame, level, component, dst); }); }
-int pbd_get_rooti(pbd_detector* d, int frame, int level, int component, int32_t* dst) { return guarded([&] { REQUIRE(d && dst, "null argument"); d->e->get_rooti(frame, level, component, dst); }); }
+int pbd_get_pyramid_image(pbd_detector* d, int frame, int level, uint8_t* dst) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && dst, "null argument"); d->e->get_pyramid_image(frame, level, dst); }); }
+int pbd_get_features(pbd_detector* d, int frame, int level, float* dst) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && dst, "null argument"); d->e->get_features(frame, level, dst); }); }
+int pbd_get_response(pbd_detector* d, int frame, int level, int filter, float* dst) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && dst, "null argument"); d->e->get_response(frame, level, filter, dst); }); }
+int pbd_get_rootv(pbd_detector* d, int frame, int level, int component, float* dst) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && dst, "null argument"); d->e->get_rootv(frame, level, component, dst); }); }
+int pbd_get_rooti(pbd_detector* d, int frame, int level, int component, int32_t* dst) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && dst, "null argument"); d->e->get_rooti(frame, level, component, dst); }); }
 int pbd_get_backptr(pbd_detector* d, int frame, int level, int component, int part, int parent_mixture, int32_t* ix, int32_t* iy, int32_t* ik) {
-  return guarded([&] { REQUIRE(d && ix && iy && ik, "null argument"); d->e->get_backptr(frame, level, component, part, parent_mixture, ix, iy, ik); });
+  return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && ix && iy && ik, "null argument"); d->e->get_backptr(frame, level, component, part, parent_mixture, ix, iy, ik); });
 }
 int pbd_set_levels(pbd_detector* d, int n_frames, int n_levels, const int32_t* ohow, const float* scales) {
-  return guarded([&] { REQUIRE(d && ohow && scales, "null argument"); d->e->set_levels_manual(n_frames, n_levels, ohow, scales); });
+  return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && ohow && scales, "null argument"); d->e->set_levels_manual(n_frames, n_levels, ohow, scales); });
 }
-int pbd_set_features(pbd_detector* d, int frame, int level, const float* src) { return guarded([&] { REQUIRE(d && src, "null argument"); d->e->set_features(frame, level, src); }); }
-int pbd_set_response(pbd_detector* d, int frame, int level, int filter, const float* src) { return guarded([&] { REQUIRE(d && src, "null argument"); d->e->set_response(frame, level, filter, src); }); }
+int pbd_set_features(pbd_detector* d, int frame, int level, const float* src) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && src, "null argument"); d->e->set_features(frame, level, src); }); }
+int pbd_set_response(pbd_detector* d, int frame, int level, int filter, const float* src) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && src, "null argument"); d->e->set_response(frame, level, filter, src); }); }
 
 static void cu(cudaError_t e, const char* what) { if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e)); }
 
-int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int w, const float* h_defw4, const int32_t* h_anchor_xy,
-                        float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode) {
+// ---- standalone 2-D distance transform: a plan owns every table and scratch buffer, so that a run allocates nothing ----
+}  // extern "C"
+namespace {
+struct DevBuf {                                 // RAII device allocation: error paths free what was allocated
+  void* p = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void alloc(size_t bytes) { cu(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc"); }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+}  // namespace
+extern "C" {
+struct pbd_dt2d_plan {
+  int n_maps = 0, h = 0, w = 0, impl = 0, device = 0;
+  LineGeom lg[2];
+  DevBuf geom, maps, etab, tmp, ixr, iyr;
+};
+
+int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, int impl, pbd_dt2d_plan** out) {
   return guarded([&] {
-    REQUIRE(d_in && h_defw4 && h_anchor_xy && d_out && d_ix && d_iy, "null argument");
-    REQUIRE(n_maps > 0 && h > 0 && w > 0 && h <= 4096 && w <= 4096, "map shape out of range (<= 4096)");
-    for (int i = 0; i < n_maps; ++i) REQUIRE(h_defw4[4 * i] > 0.f && h_defw4[4 * i + 2] > 0.f, "quadratic weights must be > 0");
-    cudaStream_t s = (cudaStream_t)stream;
+    REQUIRE(defw4 && anchor_xy && out, "null argument");
+    REQUIRE(n_maps > 0 && n_maps <= (1 << 20) && h > 0 && w > 0 && h <= 4096 && w <= 4096, "map shape out of range (<= 4096 x 4096, <= 2^20 maps)");
+    REQUIRE(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (streaming dt_pass) or 2 (parallel-in-q dt_lines)");
+    for (int i = 0; i < n_maps; ++i) {
+      REQUIRE(defw4[4 * i] > 0.f && defw4[4 * i + 2] > 0.f, "quadratic weights must be > 0");
+      REQUIRE(std::abs(anchor_xy[2 * i]) <= 4096 && std::abs(anchor_xy[2 * i + 1]) <= 4096, "anchor out of range");
+    }
+    auto P = std::make_unique<pbd_dt2d_plan>();
+    cu(cudaGetDevice(&P->device), "cudaGetDevice");
+    P->n_maps = n_maps; P->h = h; P->w = w;
+    P->impl = impl ? impl : 1;                 // measured on B200: the streaming kernels are the faster generation
+    REQUIRE(P->impl == 1 || std::max(h, w) <= kLinesMaxN, "impl 2 (parallel-in-q) handles lines of at most 1024 samples");
     const size_t cells = (size_t)n_maps * h * w;
-    PassGeom pgs[2];
-    memset(pgs, 0, sizeof(pgs));
-    pgs[0].n_levels = pgs[1].n_levels = 1;
-    pgs[0].nlines[0] = h; pgs[0].N[0] = w; pgs[1].nlines[0] = w; pgs[1].N[0] = h;
     std::vector<PassMap> maps(2 * (size_t)n_maps);
+    P->etab.alloc((size_t)n_maps * (dt_table_len(w) + dt_table_len(h)) * sizeof(double));
     for (int i = 0; i < n_maps; ++i) {
       PassMap R{}, Cc{};
       R.in_buf = 0; R.in_off = R.out_off = R.ptr_off = (unsigned long long)i * h * w;
-      R.w_sq = h_defw4[4 * i]; R.w_lin = h_defw4[4 * i + 1]; R.os = h_anchor_xy[2 * i];
-      Cc = R; Cc.w_sq = h_defw4[4 * i + 2]; Cc.w_lin = h_defw4[4 * i + 3]; Cc.os = h_anchor_xy[2 * i + 1];
+      R.w_sq = defw4[4 * i]; R.w_lin = defw4[4 * i + 1]; R.os = anchor_xy[2 * i];
+      Cc = R; Cc.w_sq = defw4[4 * i + 2]; Cc.w_lin = defw4[4 * i + 3]; Cc.os = anchor_xy[2 * i + 1];
       R.tab_len = dt_table_len(w); R.tab_bias = dt_table_bias(w, R.os);
       Cc.tab_len = dt_table_len(h); Cc.tab_bias = dt_table_bias(h, Cc.os);
+      R.etab = P->etab.as<double>() + (size_t)i * dt_table_len(w);
+      Cc.etab = P->etab.as<double>() + (size_t)n_maps * dt_table_len(w) + (size_t)i * dt_table_len(h);
       maps[i] = R; maps[n_maps + i] = Cc;
     }
-    float* d_tmp = nullptr; uint16_t *d_ixr = nullptr, *d_iyr = nullptr; PassGeom* d_pg = nullptr; PassMap* d_maps = nullptr; double* d_etab = nullptr;
-    cu(cudaMalloc(&d_pg, sizeof(pgs)), "cudaMalloc"); cu(cudaMalloc(&d_maps, maps.size() * sizeof(PassMap)), "cudaMalloc");
-    cu(cudaMalloc(&d_etab, (size_t)n_maps * (dt_table_len(w) + dt_table_len(h)) * sizeof(double)), "cudaMalloc");
-    for (int i = 0; i < n_maps; ++i) {
-      maps[i].etab = d_etab + (size_t)i * dt_table_len(w);
-      maps[n_maps + i].etab = d_etab + (size_t)n_maps * dt_table_len(w) + (size_t)i * dt_table_len(h);
+    P->maps.alloc(maps.size() * sizeof(PassMap));
+    P->tmp.alloc(cells * sizeof(float)); P->ixr.alloc(cells * 2); P->iyr.alloc(cells * 2);
+    cu(cudaMemcpy(P->maps.p, maps.data(), maps.size() * sizeof(PassMap), cudaMemcpyHostToDevice), "H2D");
+    if (P->impl == 1) {
+      PassGeom pgs[2];
+      memset(pgs, 0, sizeof(pgs));
+      pgs[0].n_levels = pgs[1].n_levels = 1;
+      pgs[0].nlines[0] = h; pgs[0].N[0] = w; pgs[1].nlines[0] = w; pgs[1].N[0] = h;
+      P->geom.alloc(sizeof(pgs));
+      cu(cudaMemcpy(P->geom.p, pgs, sizeof(pgs), cudaMemcpyHostToDevice), "H2D");
+    } else {
+      memset(P->lg, 0, sizeof(P->lg));
+      P->lg[0].n_levels = P->lg[1].n_levels = 1;
+      P->lg[0].nlines[0] = h; P->lg[0].N[0] = w; P->lg[1].nlines[0] = w; P->lg[1].N[0] = h;
+      int budget = 13312;
+      if (const char* v = getenv("PBD_DT_REGION")) budget = std::min(56 * 1024, std::max(256, atoi(v)));
+      plan_line_geom(P->lg[0], budget, false); plan_line_geom(P->lg[1], budget, true);
+      REQUIRE(4 * std::max(P->lg[0].region_bytes, P->lg[1].region_bytes) <= 227 * 1024, "line too long for the parallel-in-q kernels");
+      P->geom.alloc(sizeof(P->lg));
+      cu(cudaMemcpy(P->geom.p, P->lg, sizeof(P->lg), cudaMemcpyHostToDevice), "H2D");
     }
-    cu(cudaMalloc(&d_tmp, cells * sizeof(float)), "cudaMalloc"); cu(cudaMalloc(&d_ixr, cells * 2), "cudaMalloc"); cu(cudaMalloc(&d_iyr, cells * 2), "cudaMalloc");
-    cu(cudaMemcpyAsync(d_pg, pgs, sizeof(pgs), cudaMemcpyHostToDevice, s), "H2D");
-    cu(cudaMemcpyAsync(d_maps, maps.data(), maps.size() * sizeof(PassMap), cudaMemcpyHostToDevice, s), "H2D");
-    launch_dt_tables(d_maps, 2 * n_maps, s);
-    launch_dt2d_standalone(d_in, n_maps, h, w, d_pg, d_maps, d_tmp, d_out, d_ix, d_iy, d_ixr, d_iyr, backptr_mode, s);
-    cu(cudaGetLastError(), "dt2d launch");
-    cu(cudaStreamSynchronize(s), "dt2d sync");
-    cudaFree(d_pg); cudaFree(d_maps); cudaFree(d_etab); cudaFree(d_tmp); cudaFree(d_ixr); cudaFree(d_iyr);
+    launch_dt_tables(P->maps.as<PassMap>(), 2 * n_maps, nullptr);
+    cu(cudaGetLastError(), "dt table launch");
+    cu(cudaDeviceSynchronize(), "dt table sync");
+    *out = P.release();
   });
+}
+void pbd_dt2d_plan_destroy(pbd_dt2d_plan* p) { delete p; }
+int pbd_dt2d_plan_impl(const pbd_dt2d_plan* p) { return p ? p->impl : 0; }
+
+// enqueue only (no allocation, no synchronisation): rows pass, columns pass, back-pointer composition
+int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode) {
+  return guarded([&] {
+    REQUIRE(p && d_in && d_out && d_ix && d_iy, "null argument");
+    REQUIRE(backptr_mode == 0 || backptr_mode == 1, "backptr_mode must be 0 or 1");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->impl == 1) {
+      launch_dt2d_standalone(d_in, p->n_maps, p->h, p->w, p->geom.as<PassGeom>(), p->maps.as<PassMap>(), p->tmp.as<float>(), d_out, d_ix, d_iy,
+                             p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s);
+    } else {
+      launch_dt2d_lines(d_in, p->n_maps, p->h, p->w, p->lg[0], p->lg[1], p->geom.as<LineGeom>(), p->maps.as<PassMap>(), p->tmp.as<float>(), d_out,
+                        d_ix, d_iy, p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s);
+    }
+    cu(cudaGetLastError(), "dt2d launch");
+  });
+}
+
+int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int w, const float* h_defw4, const int32_t* h_anchor_xy,
+                        float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode) {
+  pbd_dt2d_plan* plan = nullptr;
+  int impl = 0;
+  if (const char* v = getenv("PBD_DT_IMPL")) impl = !strcmp(v, "stream") ? 1 : (!strcmp(v, "lines") ? 2 : 0);
+  int rc = pbd_dt2d_plan_create(n_maps, h, w, h_defw4, h_anchor_xy, impl, &plan);
+  if (rc != PBD_OK) return rc;
+  rc = pbd_dt2d_plan_run(plan, stream, d_in, d_out, d_ix, d_iy, backptr_mode);
+  if (rc == PBD_OK) rc = guarded([&] { cu(cudaStreamSynchronize((cudaStream_t)stream), "dt2d sync"); });
+  else cudaStreamSynchronize((cudaStream_t)stream);
+  pbd_dt2d_plan_destroy(plan);
+  return rc;
 }
 int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, float* out, int32_t* ix,
                  int32_t* iy, int backptr_mode) {
   return guarded([&] {
-    REQUIRE(in && out && ix && iy, "null argument");
+    REQUIRE(in && out && ix && iy && defw4 && anchor_xy, "null argument");
+    REQUIRE(n_maps > 0 && n_maps <= (1 << 20) && h > 0 && w > 0 && h <= 4096 && w <= 4096, "map shape out of range (<= 4096 x 4096, <= 2^20 maps)");
     const size_t cells = (size_t)n_maps * h * w;
-    float *d_in = nullptr, *d_out = nullptr; uint16_t *d_ix = nullptr, *d_iy = nullptr;
-    cu(cudaMalloc(&d_in, cells * 4), "cudaMalloc"); cu(cudaMalloc(&d_out, cells * 4), "cudaMalloc");
-    cu(cudaMalloc(&d_ix, cells * 2), "cudaMalloc"); cu(cudaMalloc(&d_iy, cells * 2), "cudaMalloc");
-    cu(cudaMemcpy(d_in, in, cells * 4, cudaMemcpyHostToDevice), "H2D");
-    const int rc = pbd_dt2d_f32_device(nullptr, d_in, n_maps, h, w, defw4, anchor_xy, d_out, d_ix, d_iy, backptr_mode);
-    std::vector<uint16_t> hx(cells), hy(cells);
-    if (rc == PBD_OK) {
-      cu(cudaMemcpy(out, d_out, cells * 4, cudaMemcpyDeviceToHost), "D2H");
-      cu(cudaMemcpy(hx.data(), d_ix, cells * 2, cudaMemcpyDeviceToHost), "D2H"); cu(cudaMemcpy(hy.data(), d_iy, cells * 2, cudaMemcpyDeviceToHost), "D2H");
-      for (size_t i = 0; i < cells; ++i) { ix[i] = hx[i]; iy[i] = hy[i]; }
-    }
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ix); cudaFree(d_iy);
+    DevBuf d_in, d_out, d_ix, d_iy;
+    d_in.alloc(cells * 4); d_out.alloc(cells * 4); d_ix.alloc(cells * 2); d_iy.alloc(cells * 2);
+    cu(cudaMemcpy(d_in.p, in, cells * 4, cudaMemcpyHostToDevice), "H2D");
+    const int rc = pbd_dt2d_f32_device(nullptr, d_in.as<float>(), n_maps, h, w, defw4, anchor_xy, d_out.as<float>(), d_ix.as<uint16_t>(), d_iy.as<uint16_t>(),
+                                       backptr_mode);
     if (rc != PBD_OK) throw CudaError(g_err);
+    std::vector<uint16_t> hx(cells), hy(cells);
+    cu(cudaMemcpy(out, d_out.p, cells * 4, cudaMemcpyDeviceToHost), "D2H");
+    cu(cudaMemcpy(hx.data(), d_ix.p, cells * 2, cudaMemcpyDeviceToHost), "D2H"); cu(cudaMemcpy(hy.data(), d_iy.p, cells * 2, cudaMemcpyDeviceToHost), "D2H");
+    for (size_t i = 0; i < cells; ++i) { ix[i] = hx[i]; iy[i] = hy[i]; }
   });
 }
 
 long long pbd_launch_count(const pbd_detector* d) { return d ? d->e->launches() : 0; }
-int pbd_stage_times_ms(pbd_detector* d, float ms[6]) { return guarded([&] { REQUIRE(d && ms, "null argument"); d->e->stage_times(ms); }); }
-int pbd_kernel_times_ms(pbd_detector* d, float ms[6]) { return guarded([&] { REQUIRE(d && ms, "null argument"); d->e->kernel_times(ms); }); }
+int pbd_stage_times_ms(pbd_detector* d, float ms[6]) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && ms, "null argument"); d->e->stage_times(ms); }); }
+int pbd_kernel_times_ms(pbd_detector* d, float ms[6]) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && ms, "null argument"); d->e->kernel_times(ms); }); }
 size_t pbd_device_bytes(const pbd_detector* d) { return d ? d->e->device_bytes() : 0; }
 
 }  // extern "C"

@@ -26,6 +26,7 @@
 #include <cfloat>
 #include "kernels.cuh"
 #include "dt_envelope.cuh"
+#include "dt_lines.cuh"
 
 namespace pbd {
 namespace {
@@ -165,6 +166,115 @@ __global__ void __launch_bounds__(128) dt_build_tables(const PassMap* __restrict
   const int ne = M.tab_len - kDtRcp;
   for (int j = threadIdx.x; j < M.tab_len; j += blockDim.x)
     M.etab[j] = j < ne ? env::table_E(a, b, j - M.tab_bias) : env::table_rcp(a, j - ne);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Parallel-in-q transform (dt_lines.cuh).  A warp owns a batch of b lines of one map: the batch is staged in the warp's
+// shared-memory region (y[line][q], conflict-free for both the lane = sample phases and the lane = line phase), transformed by
+// dtl::process_lines, and written back with the same access pattern it was read with -- all maps stay [y][x] in HBM:
+//   rows pass  (COLS = false): a line is an image row (contiguous); values and arg-maxes go straight to global memory, coalesced;
+//   cols pass  (COLS = true):  a line is an image column; the batch is a [N rows][b columns] tile, read and written as row
+//                              segments of b elements (b = 8 floats = one 32-byte sector), transposed through shared memory.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kLineWarps = 4;
+
+struct LineTask { int level, unit, blk; };
+// task index -> (level, unit, block of lines); units = maps (or jobs) per level
+__device__ __forceinline__ bool find_task(const LineGeom* __restrict__ lg, int units, int t, LineTask& T) {
+  const int nl = lg->n_levels;
+  for (int l = 0; l < nl; ++l) {
+    const int nblk = lg->nblk[l], nt = nblk * units;
+    if (t < nt) { T.level = l; T.unit = t / nblk; T.blk = t - T.unit * nblk; return true; }
+    t -= nt;
+  }
+  return false;
+}
+
+struct LineRegion { float* y; float* z; int* own; unsigned* bits; unsigned short* stash; };
+// alias: own shares the z array (lines of at most dtl::kAliasMaxN samples); the u16 stash exists in the column kernels only
+__device__ __forceinline__ LineRegion carve_region(unsigned char* base, int b, int N, bool alias) {
+  const int LS = dtl::line_stride(N), NW = (N + 31) >> 5;
+  LineRegion R;
+  R.y = reinterpret_cast<float*>(base);
+  R.z = R.y + b * LS;
+  R.own = alias ? reinterpret_cast<int*>(R.z) : reinterpret_cast<int*>(R.z + b * LS);
+  R.bits = reinterpret_cast<unsigned*>(R.own + b * LS);
+  R.stash = reinterpret_cast<unsigned short*>(R.bits + b * NW);
+  return R;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+
+// stage a [N][nb] column tile (columns x0 .. x0+nb-1 of a map with row pitch W) as y[c][r]; b = power of two; returns max |y|
+__device__ __forceinline__ float load_col_tile(const float* __restrict__ src, int W, int x0, int nb, int b, int N, float* y, int LS, int lane) {
+  const int c = lane & (b - 1), rstep = 32 / b;
+  float ymax = 0.f;
+  if (c < nb) {
+    const float* p = src + x0 + c;
+    float* d = y + c * LS;
+#pragma unroll 4
+    for (int r = lane / b; r < N; r += rstep) { const float v = __ldg(p + (size_t)r * W); d[r] = v; ymax = fmaxf(ymax, fabsf(v)); }
+  }
+  return warp_max(ymax);
+}
+
+template <bool COLS>
+__global__ void __launch_bounds__(kLineWarps * 32)
+dt_lines(const LineGeom* __restrict__ lg, const PassMap* __restrict__ maps, int nmaps, const float* __restrict__ inA, size_t strideA,
+         const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out, unsigned short* __restrict__ ptr,
+         size_t stride_ptr) {
+  extern __shared__ __align__(16) unsigned char smem_lines[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  LineTask T;
+  if (!find_task(lg, nmaps, blockIdx.x * kLineWarps + wib, T)) return;          // warp-uniform
+  const int frame = blockIdx.y;
+  const int N = lg->N[T.level], nlines = lg->nlines[T.level], b = lg->b[T.level];
+  const int line0 = T.blk * b, nb = min(b, nlines - line0);
+  const size_t cell_off = (size_t)lg->cell_off[T.level];
+  const PassMap M = maps[T.unit];
+  const float* src = (M.in_buf ? inB + (size_t)frame * strideB : inA + (size_t)frame * strideA) + M.in_off + cell_off;
+  float* dst = out + (size_t)frame * stride_out + M.out_off + cell_off;
+  unsigned short* dp = ptr + (size_t)frame * stride_ptr + M.ptr_off + cell_off;
+  const Quad f = env::make_quad(M.w_sq, M.w_lin, M.etab + M.tab_bias, M.etab + (M.tab_len - kDtRcp));
+  const LineRegion R = carve_region(smem_lines + (size_t)wib * lg->region_bytes, b, N, lg->alias != 0);
+  const int LS = dtl::line_stride(N), LSP = (LS + 1) & ~1;
+  const dtl::DevWarp w;
+  float ymax = 0.f;
+  if (!COLS) {
+    // the batch's rows are one contiguous run of nb * N floats
+    const float* s0 = src + (size_t)line0 * N;
+    for (int l = 0; l < nb; ++l) {
+      const float* sl = s0 + l * N;
+      float* yl = R.y + l * LS;
+#pragma unroll 4
+      for (int q = lane; q < N; q += 32) { const float v = __ldg(sl + q); yl[q] = v; ymax = fmaxf(ymax, fabsf(v)); }
+    }
+    ymax = warp_max(ymax);
+  } else {
+    ymax = load_col_tile(src, nlines, line0, nb, b, N, R.y, LS, lane);
+  }
+  __syncwarp();
+  if (!COLS) {
+    float* d0 = dst + (size_t)line0 * N;
+    unsigned short* p0 = dp + (size_t)line0 * N;
+    dtl::process_lines_any(w, f, N, M.os, nb, ymax, R.y, R.z, R.own, R.bits,
+                           [&](int l, int i, float val, int v) { d0[l * N + i] = val; p0[l * N + i] = (unsigned short)v; });
+  } else {
+    // values are parked in the position's own slot, arg-maxes in the u16 stash, then the tile is written as row segments
+    dtl::process_lines_any(w, f, N, M.os, nb, ymax, R.y, R.z, R.own, R.bits,
+                           [&](int l, int i, float val, int v) { R.own[l * LS + i] = __float_as_int(val); R.stash[l * LSP + i] = (unsigned short)v; });
+    __syncwarp();
+    const int c = lane & (b - 1), rstep = 32 / b;
+    if (c < nb)
+      for (int r = lane / b; r < N; r += rstep) {
+        const size_t o = (size_t)r * nlines + line0 + c;
+        dst[o] = __int_as_float(R.own[c * LS + r]);
+        dp[o] = R.stash[c * LSP + r];
+      }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -317,6 +427,41 @@ static int pass_warps(const PassGeom& pg, int nmaps) {
   return w;
 }
 
+// ---- parallel-in-q launch plan ------------------------------------------------------------------------------------------
+void plan_line_geom(LineGeom& lg, int budget_bytes, bool stash) {
+  int maxn = 1;
+  for (int l = 0; l < lg.n_levels; ++l) maxn = std::max(maxn, lg.N[l]);
+  lg.alias = maxn <= dtl::kAliasMaxN ? 1 : 0;
+  int region = 0;
+  for (int l = 0; l < lg.n_levels; ++l) {
+    const int lb = dtl::line_bytes(lg.N[l], lg.alias != 0, stash);
+    int b = 32;
+    while (b > 1 && (b * lb > budget_bytes || b / 2 >= lg.nlines[l])) b >>= 1;   // no wider than needed for the level's lines
+    lg.b[l] = b;
+    lg.nblk[l] = (lg.nlines[l] + b - 1) / b;
+    region = std::max(region, b * lb);
+  }
+  lg.region_bytes = (region + 15) / 16 * 16;
+}
+long long line_tasks(const LineGeom& lg, int units) {
+  long long t = 0;
+  for (int l = 0; l < lg.n_levels; ++l) t += (long long)lg.nblk[l] * units;
+  return t;
+}
+
+template <typename K>
+static void set_smem(K kernel, int bytes) {
+  // opt in to more than 48 KB of dynamic shared memory (idempotent; the attribute is per kernel and device)
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+template <bool COLS, typename... A>
+static void launch_lines(const LineGeom& lg, dim3 grid, cudaStream_t s, A... args) {
+  const int smem = kLineWarps * lg.region_bytes;
+  set_smem(dt_lines<COLS>, smem);
+  dt_lines<COLS><<<grid, kLineWarps * 32, smem, s>>>(args...);
+}
+
 int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
@@ -376,9 +521,53 @@ int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const Pa
   launch_pass(w, gr, s, d_pg2, d_maps2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0);
   launch_pass(h, gc, s, d_pg2 + 1, d_maps2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out, (size_t)0,
               d_iyraw, (size_t)0);
-  dim3 gx((w + 255) / 256, h, n_maps);
-  dt2d_compose<<<gx, 256, 0, s>>>(h, w, d_ixraw, d_iyraw, d_ix, d_iy, backptr_mode);
-  return 3;
+  for (int m0 = 0; m0 < n_maps; m0 += 65535) {                     // gridDim.z limit
+    const int nm = std::min(65535, n_maps - m0);
+    const size_t o = (size_t)m0 * h * w;
+    dim3 gx((w + 255) / 256, h, nm);
+    dt2d_compose<<<gx, 256, 0, s>>>(h, w, d_ixraw + o, d_iyraw + o, d_ix + o, d_iy + o, backptr_mode);
+  }
+  return 2 + (n_maps + 65534) / 65535;
+}
+
+
+namespace {
+// all maps [y][x]: mode 0 (reference, :232-244): Iy[y][x] <- Iyraw[y][Ix[y][x]];  mode 1: Ix[y][x] <- Ixraw[Iy[y][x]][x]
+__global__ void __launch_bounds__(256)
+dt2d_compose_yx(int h, int w, const unsigned short* __restrict__ ixraw, const unsigned short* __restrict__ iyraw,
+                unsigned short* __restrict__ ix, unsigned short* __restrict__ iy, int mode) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  const int y = blockIdx.y;
+  const size_t base = (size_t)blockIdx.z * h * w;
+  const size_t c = base + (size_t)y * w + x;
+  if (mode == 0) {
+    const int xi = ixraw[c];
+    ix[c] = (unsigned short)xi;
+    iy[c] = iyraw[base + (size_t)y * w + xi];
+  } else {
+    const int yi = iyraw[c];
+    iy[c] = (unsigned short)yi;
+    ix[c] = ixraw[base + (size_t)yi * w + x];
+  }
+}
+}  // namespace
+
+int launch_dt2d_lines(const float* d_in, int n_maps, int h, int w, const LineGeom& lg_rows, const LineGeom& lg_cols, const LineGeom* d_lg2,
+                      const PassMap* d_maps2, float* d_tmp, float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw,
+                      int backptr_mode, cudaStream_t s) {
+  if (n_maps <= 0 || h <= 0 || w <= 0) return 0;
+  dim3 gr((unsigned)((line_tasks(lg_rows, n_maps) + kLineWarps - 1) / kLineWarps), 1), gc((unsigned)((line_tasks(lg_cols, n_maps) + kLineWarps - 1) / kLineWarps), 1);
+  launch_lines<false>(lg_rows, gr, s, d_lg2, d_maps2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0);
+  launch_lines<true>(lg_cols, gc, s, d_lg2 + 1, d_maps2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out, (size_t)0,
+                     d_iyraw, (size_t)0);
+  for (int m0 = 0; m0 < n_maps; m0 += 65535) {                     // gridDim.z limit
+    const int nm = std::min(65535, n_maps - m0);
+    const size_t o = (size_t)m0 * h * w;
+    dim3 gx((w + 255) / 256, h, nm);
+    dt2d_compose_yx<<<gx, 256, 0, s>>>(h, w, d_ixraw + o, d_iyraw + o, d_ix + o, d_iy + o, backptr_mode);
+  }
+  return 2 + (n_maps + 65534) / 65535;
 }
 
 }  // namespace pbd

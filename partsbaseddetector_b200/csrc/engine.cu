@@ -67,21 +67,40 @@ Engine::Engine(const Model& m, int device, cudaStream_t stream) : thresh((double
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0) throw CudaError(std::string("no CUDA device available: ") + cudaGetErrorString(e));
   if (device < 0 || device >= ndev) throw ArgError("device index out of range");
+  // the caller's current device is restored on every exit; a constructor that throws frees what it had allocated (the destructor
+  // does not run for a partially constructed object)
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
   check_cuda(cudaSetDevice(device), "cudaSetDevice");
-  check_cuda(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
-  build_tables();
-  check_cuda(cudaMalloc(&d_g_, sizeof(Geometry)), "cudaMalloc geometry");
-  for (ResultSlot& S : slots_) {
-    check_cuda(cudaMalloc(&S.d_nhits, sizeof(int)), "cudaMalloc nhits");
-    check_cuda(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming), "cudaEventCreate");
+  try {
+    check_cuda(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
+    build_tables();
+    check_cuda(cudaMalloc(&d_g_, sizeof(Geometry)), "cudaMalloc geometry");
+    for (ResultSlot& S : slots_) {
+      check_cuda(cudaMalloc(&S.d_nhits, sizeof(int)), "cudaMalloc nhits");
+      check_cuda(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming), "cudaEventCreate");
+    }
+    for (auto& e : frames_free_ev_) check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    dev_bytes_ += sizeof(Geometry) + 2 * sizeof(int);
+    for (int i = 0; i < 7; ++i) { check_cuda(cudaEventCreate(&ev_[i]), "cudaEventCreate"); }
+  } catch (...) {
+    release();
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    throw;
   }
-  for (auto& e : frames_free_ev_) check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
-  dev_bytes_ += sizeof(Geometry) + 2 * sizeof(int);
-  for (int i = 0; i < 7; ++i) { check_cuda(cudaEventCreate(&ev_[i]), "cudaEventCreate"); }
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
 }
 
 Engine::~Engine() {
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
   cudaSetDevice(device_);
+  release();
+  if (prev >= 0 && prev != device_) cudaSetDevice(prev);
+}
+
+// frees every device allocation, stream and event of the engine (the detector's device is current)
+void Engine::release() {
   cudaStreamSynchronize(stream_);
   void* ptrs[] = {d_wtc_, d_wtc16_, d_f16_, d_fhi_, d_flo_, d_tc_levels_, d_tc_tiles_, d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
@@ -93,6 +112,7 @@ Engine::~Engine() {
   for (void* p : ptrs) if (p) cudaFree(p);
   for (ResultSlot& S : slots_) if (S.done) cudaEventDestroy(S.done);
   for (auto& e : frames_free_ev_) if (e) cudaEventDestroy(e);
+  if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
   if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
   for (cudaStream_t st : dp_aux_) cudaStreamDestroy(st);
   for (cudaEvent_t ev : dp_join_) cudaEventDestroy(ev);
@@ -318,6 +338,7 @@ void Engine::set_frames_geometry(int n, int h, int w, int c) {
   g.n_frames = n; g.in_h = h; g.in_w = w; g.in_c = c;
   compute_pyramid_levels(h, w, model_.sbin, model_.interval, max_levels, g);
   if (g.n_levels <= 0) throw ArgError("image too small for one pyramid level (min(h,w) < 5*sbin)");
+  stage_ = 0;                                   // from here on the old batch is gone: a failure below must not leave stale stages usable
   long long img_off = 0; int block_off = 0, cell_off = 0, xo = 0, yo = 0;
   for (int l = 0; l < g.n_levels; ++l) {
     LevelDesc& L = g.lv[l];
@@ -383,6 +404,7 @@ void Engine::set_levels_manual(int n, int nlevels, const int32_t* ohow, const fl
     L.cell_off = cell_off; cell_off += L.ow * L.oh;
   }
   g.blocks_total = block_off; g.cells_total = cell_off; g.img_bytes = 0;
+  stage_ = 0;
   g_ = g;
   have_images_ = false;
   build_batch_tables();
@@ -570,9 +592,9 @@ void Engine::upload_and_pyramid(const uint8_t* frames, size_t row_stride, size_t
 // Pipelined API.  Frames must be tightly packed (and pinned for the copy to be asynchronous) and stay untouched until the
 // ticket has been collected.  At most two batches are in flight: the ticket returned is the result slot (0/1).
 int Engine::submit(const uint8_t* frames, int n, int h, int w, int c) {
-  set_frames_geometry(n, h, w, c);
   const int slot = cur_slot_ ^ 1;
   if (slots_[slot].pending) throw StateError("submit: two batches are already in flight; collect a ticket first");
+  set_frames_geometry(n, h, w, c);
   cur_slot_ = slot;
   const size_t fb = (size_t)w * c * h;
   frames_buf_ ^= 1;
@@ -749,6 +771,52 @@ void Engine::run_argmin() {
   check_cuda(cudaEventRecord(S.done, stream_), "event");
   if (timing) { check_cuda(cudaEventRecord(ev_[6], stream_), "event"); ev_valid_[6] = true; }
   stage_ = 5;
+}
+
+void Engine::run_stages() {
+  run_pyramid();
+  run_pdf();
+  run_dp_min();
+  run_argmin();
+}
+
+// Device-resident frames through all stages.  With use_graph the launch sequence (about 100 kernels, the frame groups of the DP on
+// their forked streams included) is captured once per (frames pointer, geometry, options) and replayed: the first call runs eagerly
+// (it sizes every buffer and table), the second captures, every later call is one cudaGraphLaunch.
+void Engine::enqueue_device(const uint8_t* d_frames, int n, int h, int w, int c) {
+  set_frames_geometry(n, h, w, c);
+  use_device_frames(d_frames);
+  if (!use_graph || timing) { run_stages(); return; }
+  GraphKey k;
+  k.frames = d_frames; k.geom_serial = geom_serial_; k.n = n; k.resp_mode = resp_mode; k.backptr = backptr; k.max_candidates = max_candidates;
+  k.dp_streams = dp_streams; k.thresh = thresh; k.nms_overlap = nms_overlap;
+  if (graph_exec_ && k == graph_key_) {
+    check_cuda(cudaGraphLaunch(graph_exec_, stream_), "cudaGraphLaunch");
+    launches_ += graph_launches_;
+    cur_slot_ = graph_slot_;
+    stage_ = 5;
+    return;
+  }
+  if (!(k == warm_key_)) { warm_key_ = k; run_stages(); return; }          // first sight of this configuration: eager, allocates
+  if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+  const long long l0 = launches_;
+  cudaGraph_t g = nullptr;
+  check_cuda(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+  try {
+    run_stages();
+  } catch (...) {
+    cudaStreamEndCapture(stream_, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
+  }
+  check_cuda(cudaStreamEndCapture(stream_, &g), "cudaStreamEndCapture");
+  const cudaError_t ie = cudaGraphInstantiate(&graph_exec_, g, 0);
+  cudaGraphDestroy(g);
+  check_cuda(ie, "cudaGraphInstantiate");
+  graph_key_ = k;
+  graph_launches_ = launches_ - l0;
+  graph_slot_ = cur_slot_;
+  check_cuda(cudaGraphLaunch(graph_exec_, stream_), "cudaGraphLaunch");
 }
 
 void Engine::collect(CandidateSet& out) {

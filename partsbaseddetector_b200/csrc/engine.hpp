@@ -60,6 +60,9 @@ class Engine {
   int resp_mode = 0, tc_taps_per_partial = 0, backptr = 0, max_levels = 0, max_candidates = 65536, timing = 0;
   // the DP stage runs the batch as this many groups of frames on concurrent streams (1 = single stream)
   int dp_streams = 2;
+  // 1: enqueue_device() replays a CUDA graph of the whole path (captured on the second call with the same frames pointer, geometry and
+  // options; timing must be 0).  Removes the ~100 launch overheads per batch: what a single-frame call is bound by.
+  int use_graph = 0;
   // >= 0: detect() returns, per frame, the candidates sorted by score and greedily suppressed on the device (Candidate::sort +
   // Candidate::nonMaximaSuppression with this overlap); < 0 (default): the raw candidate list, as the reference's detect()
   double nms_overlap = -1.0;
@@ -80,6 +83,8 @@ class Engine {
   void collect(CandidateSet& out);
   // pipelined API: submit() enqueues H2D (own copy stream, double-buffered frames) + all stages and returns a ticket (0/1);
   // collect_ticket() waits for that batch only and downloads its candidates on a separate stream.
+  // all stages on device-resident frames, enqueue only (graph replay when use_graph is set); results via collect()
+  void enqueue_device(const uint8_t* d_frames, int n, int h, int w, int c);
   int submit(const uint8_t* frames, int n, int h, int w, int c);
   void collect_ticket(int ticket, CandidateSet& out);   // syncs, downloads and orders the candidates
 
@@ -95,6 +100,7 @@ class Engine {
   void set_features(int frame, int level, const float* src);
   void set_response(int frame, int level, int filter, const float* src);
 
+  void invalidate_geometry() { stage_ = 0; }     // an option that shapes the batch tables changed: rebuild them with the next batch
   long long launches() const { return launches_; }
   size_t device_bytes() const { return dev_bytes_; }
   void stage_times(float ms[6]);
@@ -108,6 +114,7 @@ class Engine {
  private:
   struct ResultSlot;
   void check_cuda(cudaError_t e, const char* what) const;
+  void release();
   template <typename T> void ensure(T*& p, size_t& cap, size_t n);
   void alloc_batch();
   void build_tables();
@@ -212,6 +219,22 @@ class Engine {
   std::vector<int> kev_tag_;
   size_t kev_n_ = 0;
   void kmark(int tag);
+  // CUDA-graph replay of enqueue_device(): the key is everything the captured launch sequence depends on
+  struct GraphKey {
+    const uint8_t* frames = nullptr;
+    long long geom_serial = -1;
+    int n = 0, resp_mode = -1, backptr = -1, max_candidates = 0, dp_streams = 0;
+    double thresh = 0, nms_overlap = 0;
+    bool operator==(const GraphKey& o) const {
+      return frames == o.frames && geom_serial == o.geom_serial && n == o.n && resp_mode == o.resp_mode && backptr == o.backptr &&
+             max_candidates == o.max_candidates && dp_streams == o.dp_streams && thresh == o.thresh && nms_overlap == o.nms_overlap;
+    }
+  };
+  GraphKey graph_key_{}, warm_key_{};
+  cudaGraphExec_t graph_exec_ = nullptr;
+  long long graph_launches_ = 0;
+  int graph_slot_ = 0;
+  void run_stages();
 };
 
 // geometry helpers shared with the ABI (pyramid level table of HOGFeatures::pyramid)

@@ -156,6 +156,22 @@ constexpr int kDtTabPad = 2, kDtRcp = 32;     // look-ahead entries past the lar
 inline int dt_table_len(int maxn) { return 2 * maxn - 1 + kDtTabPad + kDtRcp; }
 inline int dt_table_bias(int maxn, int os) { return maxn - 1 - os; }
 int launch_dt_tables(const PassMap* d_maps, int nmaps, cudaStream_t s);
+// Geometry of one pass of the parallel-in-q transform (dt_lines.cuh): lines of a level are processed in batches of b[l] lines per warp
+// (power of two <= 32, chosen so that a batch's state fits the warp's shared-memory region).  Rows pass: line = image row (element
+// (line, q) at cell_off + line*N + q); columns pass: line = image column (element at cell_off + q*nlines + line).
+struct LineGeom {
+  int n_levels;
+  int alias;                   // 1: every line has at most 256 samples, the ownership slots alias the break points (dt_lines.cuh)
+  int region_bytes;            // shared memory per warp
+  int nlines[kMaxLevels];
+  int N[kMaxLevels];
+  int cell_off[kMaxLevels];
+  int b[kMaxLevels];
+  int nblk[kMaxLevels];        // ceil(nlines / b)
+};
+// fills b / nblk / kreg / region_bytes from nlines / N for a per-warp shared-memory budget
+void plan_line_geom(LineGeom& lg, int budget_bytes, bool stash);   // stash: the kernel parks u16 arg-maxes per sample (column kernels)
+long long line_tasks(const LineGeom& lg, int units);     // warps (rows pass, units = maps) or CTAs (fused columns pass, units = jobs)
 int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
@@ -183,6 +199,11 @@ int launch_expand_backptr(const Geometry& g, const DeviceBuffers& b, int frame, 
 int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const PassGeom* d_pg2, const PassMap* d_maps2, float* d_tmp,
                            float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
                            cudaStream_t s);
+// the same transform through the parallel-in-q kernels (all maps [y][x]); d_lg2 = {rows, cols}
+int launch_dt2d_lines(const float* d_in, int n_maps, int h, int w, const LineGeom& lg_rows, const LineGeom& lg_cols, const LineGeom* d_lg2,
+                      const PassMap* d_maps2, float* d_tmp, float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw,
+                      int backptr_mode, cudaStream_t s);
+constexpr int kLinesMaxN = 1024;   // longest line the parallel-in-q kernels are used for (longer: the streaming dt_pass)
 // device-side Candidate::sort + nonMaximaSuppression (nms.cu): work buffers (shared by all batches of a detector) and the
 // compacted result of one batch (hits_out / xym_out / total: per result slot)
 struct NmsBuffers {

@@ -37,7 +37,15 @@ struct MatArray {
   std::vector<MatArray> cells;            // cell arrays: one entry per element (column-major)
   std::vector<std::string> fields;        // struct arrays: field names ...
   std::vector<MatArray> fvals;            // ... and values, element-major: fvals[e * nfields + f]
-  size_t numel() const { size_t n = 1; for (int d : dims) n *= (size_t)d; return dims.empty() ? 0 : n; }
+  // product of the dimensions, saturating at SIZE_MAX (every caller rejects counts above 2^28)
+  size_t numel() const {
+    size_t n = 1;
+    for (int d : dims) {
+      if (d != 0 && n > SIZE_MAX / (size_t)d) return SIZE_MAX;
+      n *= (size_t)d;
+    }
+    return dims.empty() ? 0 : n;
+  }
   const MatArray* field(size_t elem, const char* fname) const {
     for (size_t f = 0; f < fields.size(); ++f)
       if (fields[f] == fname) return &fvals[elem * fields.size() + f];
@@ -146,6 +154,7 @@ void parse_matrix(const uint8_t* data, size_t size, bool swap, MatArray& a, int 
     case mxSTRUCT: case mxOBJECT: {
       if (a.cls == mxOBJECT) off = read_element(r, off).next;          // class name
       Element fl = read_element(r, off);
+      if (fl.size < 4) throw FormatError("MAT file: bad struct field-name length element");
       const int flen = load_swapped<int32_t>(fl.data, swap);
       Element fn = read_element(r, fl.next);
       if (flen <= 0 || fn.size % (uint32_t)flen) throw FormatError("MAT file: bad struct field names");
@@ -186,6 +195,7 @@ void parse_matrix(const uint8_t* data, size_t size, bool swap, MatArray& a, int 
   }
 }
 
+constexpr size_t kMaxInflated = (size_t)1 << 30;      // a model file holds a few MB; bound what a hostile stream can allocate
 std::vector<uint8_t> inflate_all(const uint8_t* src, size_t n) {
   z_stream zs;
   std::memset(&zs, 0, sizeof(zs));
@@ -193,7 +203,10 @@ std::vector<uint8_t> inflate_all(const uint8_t* src, size_t n) {
   std::vector<uint8_t> out(std::max<size_t>(4096, n * 4));
   zs.next_in = const_cast<Bytef*>(src); zs.avail_in = (uInt)n;
   for (;;) {
-    if (zs.total_out == out.size()) out.resize(out.size() * 2);
+    if (zs.total_out == out.size()) {
+      if (out.size() >= kMaxInflated) { inflateEnd(&zs); throw FormatError("MAT file: compressed variable expands beyond 1 GiB"); }
+      out.resize(std::min(out.size() * 2, kMaxInflated));
+    }
     zs.next_out = out.data() + zs.total_out;
     zs.avail_out = (uInt)std::min<size_t>(out.size() - zs.total_out, (size_t)1 << 30);
     const int rc = inflate(&zs, Z_NO_FLUSH);

@@ -103,9 +103,10 @@ void for_each_number(const XNode* n, F f) {
     if (!*c) break;
     char* q = nullptr;
     double v;
-    if (c[0] == '.' && (c[1] == 'I' || c[1] == 'i' || c[1] == 'N' || c[1] == 'n')) {   // cv: .Inf / .NaN
-      v = (c[1] == 'I' || c[1] == 'i') ? INFINITY : NAN; q = const_cast<char*>(c) + 4;
-    } else if (c[0] == '-' && c[1] == '.' && (c[2] == 'I' || c[2] == 'i')) { v = -INFINITY; q = const_cast<char*>(c) + 5; }
+    // cv::FileStorage writes .Inf / -.Inf / .NaN; the tokens are matched in full so that a truncated one cannot run past the buffer
+    if (!strncasecmp(c, ".inf", 4)) { v = INFINITY; q = const_cast<char*>(c) + 4; }
+    else if (!strncasecmp(c, ".nan", 4)) { v = NAN; q = const_cast<char*>(c) + 4; }
+    else if (!strncasecmp(c, "-.inf", 5)) { v = -INFINITY; q = const_cast<char*>(c) + 5; }
     else v = strtod(c, &q);
     if (q == c) throw FormatError("XML: bad number in <" + n->name + ">");
     f(v);
@@ -504,15 +505,19 @@ void load_bin(const std::string& path, Model& m) {
   if (r.o + nl > s.size()) throw FormatError("PBDM: truncated");
   m.name.assign(s.data() + r.o, nl); r.o += nl;
   m.interval = r.get<int32_t>(); m.thresh = r.get<float>(); m.sbin = r.get<int32_t>(); m.norient = r.get<int32_t>(); m.flen = r.get<int32_t>();
+  // every count is bounded by the bytes that are left (each filter / component / part occupies at least 4 bytes)
   const uint32_t nf = r.get<uint32_t>();
+  if (nf > (s.size() - r.o) / 4) throw FormatError("PBDM: filter count exceeds the file size");
   for (uint32_t i = 0; i < nf; ++i) {
     m.frows.push_back(r.get<int32_t>()); m.fkw.push_back(r.get<int32_t>());
     std::vector<double> v; r.vec(v); m.filters.push_back(std::move(v));
   }
   r.vec(m.biasw); r.vec(m.anchors); r.vec(m.defs);
   const uint32_t nc = r.get<uint32_t>();
+  if (nc > (s.size() - r.o) / 4) throw FormatError("PBDM: component count exceeds the file size");
   for (uint32_t c = 0; c < nc; ++c) {
     const uint32_t np = r.get<uint32_t>();
+    if (np > (s.size() - r.o) / 4) throw FormatError("PBDM: part count exceeds the file size");
     std::vector<Part> parts(np);
     for (auto& P : parts) { P.parentid = r.get<int32_t>(); r.vec(P.filterid); r.vec(P.biasid); r.vec(P.defid); }
     m.comps.push_back(std::move(parts));

@@ -478,6 +478,37 @@ class PartsBasedDetector:
         return int(_lib.lib().pbd_device_bytes(self.handle))
 
 
+class Dt2dPlan:
+    """Standalone generalised 2-D distance transform (DistanceTransform<float>::compute) of n maps of h x w with all tables and
+    scratch buffers pre-allocated: run() only enqueues kernels (device pointers, e.g. torch tensors' data_ptr()).
+    impl: 0 default (1), 1 streaming envelope (any line length <= 4096; what the detector runs), 2 parallel-in-q (lines <= 1024)."""
+
+    def __init__(self, n, h, w, defw4, anchor_xy, impl=0):
+        self.n, self.h, self.w = n, h, w
+        defw4 = np.ascontiguousarray(np.broadcast_to(np.asarray(defw4, np.float32).reshape(-1, 4), (n, 4)))
+        anchor = np.ascontiguousarray(np.broadcast_to(np.asarray(anchor_xy, np.int32).reshape(-1, 2), (n, 2)))
+        self._p = C.c_void_p()
+        _lib.check(_lib.lib().pbd_dt2d_plan_create(n, h, w, defw4.reshape(-1), anchor.reshape(-1), impl, C.byref(self._p)))
+
+    def impl(self):
+        return _lib.lib().pbd_dt2d_plan_impl(self._p)
+
+    def run(self, d_in, d_out, d_ix, d_iy, backptr_mode=0, stream=0):
+        _lib.check(_lib.lib().pbd_dt2d_plan_run(self._p, C.c_void_p(stream), C.c_void_p(d_in), C.c_void_p(d_out), C.c_void_p(d_ix), C.c_void_p(d_iy),
+                                                backptr_mode))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            _lib.lib().pbd_dt2d_plan_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def dt2d(score, defw4, anchor_xy, backptr_mode=0):
     """Generalised 2-D distance transform of one or more maps on the GPU (DistanceTransform<float>::compute)."""
     a = np.ascontiguousarray(score, np.float32)

@@ -54,6 +54,35 @@ class FlatModel:
                     defs=np.ascontiguousarray(np.asarray(self.defs, np.float32).ravel()),
                     indexers=np.array(idx, np.int32))
 
+    @classmethod
+    def from_arrays(cls, a, name="", thresh=0.0):
+        """Inverse of to_arrays() (hdr / fdims / filters / biasw / anchors / defs / indexers)."""
+        hdr = [int(v) for v in a["hdr"]]
+        m = cls(name=str(name), interval=hdr[0], thresh=float(thresh), sbin=hdr[1], norient=hdr[2], flen=hdr[3])
+        fd = np.asarray(a["fdims"], np.int32).reshape(-1, 2)
+        flt = np.asarray(a["filters"], np.float64)
+        off = 0
+        for kh, kw in fd:
+            n = int(kh) * int(kw) * m.flen
+            m.filters.append(flt[off:off + n].reshape(int(kh), int(kw) * m.flen).copy())
+            off += n
+        m.biasw = np.asarray(a["biasw"], np.float32).copy()
+        m.anchors = np.asarray(a["anchors"], np.int32).reshape(-1, 2).copy()
+        m.defs = np.asarray(a["defs"], np.float32).reshape(-1, 4).copy()
+        ix = [int(v) for v in a["indexers"]]
+        i = 0
+        for _ in range(hdr[7]):
+            nparts = ix[i]; i += 1
+            parts = []
+            for _ in range(nparts):
+                par, nf, nb, nd = ix[i:i + 4]; i += 4
+                fid = ix[i:i + nf]; i += nf
+                bid = ix[i:i + nb]; i += nb
+                did = ix[i:i + nd]; i += nd
+                parts.append(FlatPart(par, fid, bid, did))
+            m.comps.append(parts)
+        return m
+
     def nfilters(self):
         return len(self.filters)
 

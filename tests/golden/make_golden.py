@@ -3,6 +3,8 @@
 
   *.pbdm                 compact binary copies of reference models/*.xml, written by the product's own XML
                          loader (checked field-by-field against cv2.FileStorage in tests/test_model_loader.py)
+  Person_26parts_flat.npz  the flat arrays of the north-star model as read by cv2.FileStorage (tests/refmodel.py): lets bench.py's
+                         reference arm build the CPU oracle without loading the product library
   oracle_golden.npz      outputs of the CPU oracle on small seeded inputs, produced here where the oracle's
                          OpenCV-dependent stages were pinned bit-exactly against cv2 4.13
 """
@@ -38,6 +40,8 @@ def main():
     out = {}
     # person model, 160x120 synthetic frame: every stage boundary
     fm = refmodel.load_xml_cv2(os.path.join(refmodel.REF_MODELS, "Person_26parts.xml"))
+    np.savez_compressed(os.path.join(HERE, "Person_26parts_flat.npz"), name=np.array(fm.name), thresh=np.float32(fm.thresh), **fm.to_arrays())
+    print("wrote Person_26parts_flat.npz")
     D = oracle_lib.OracleDetector(fm, 32)
     img = synth_frame(7, 120, 160)
     D.run(img, 1, 3)

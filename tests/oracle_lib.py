@@ -77,6 +77,14 @@ def lib():
     return L
 
 
+def load_flat_npz(path):
+    """FlatModel from a committed *_flat.npz fixture (tests/golden/make_golden.py): no product library involved."""
+    from partsbaseddetector_b200.flatmodel import FlatModel
+    with np.load(path) as z:
+        return FlatModel.from_arrays({k: z[k] for k in ("hdr", "fdims", "filters", "biasw", "anchors", "defs", "indexers")},
+                                     name=str(z["name"]), thresh=float(z["thresh"]))
+
+
 def physical_cores():
     """Number of physical cores this process may run on (SMT siblings counted once)."""
     try:

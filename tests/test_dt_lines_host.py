@@ -36,14 +36,15 @@ def check(src, w_sq, w_lin, os_, b, kreg):
     L = oracle_lib.lib()
     dst = np.full((nl, N), np.nan, np.float32)
     ptr = np.full((nl, N), 0xFFFF, np.uint16)
-    pops = C.c_longlong(0)
-    assert dtl().dtl_dt1d(np.ascontiguousarray(src), nl, N, w_sq, w_lin, os_, b, kreg, dst, ptr, C.byref(pops)) == 0
+    pops = (C.c_longlong * 2)(0, 0)
+    assert dtl().dtl_dt1d(np.ascontiguousarray(src), nl, N, w_sq, w_lin, os_, b, kreg, dst, ptr, pops) == 0
     for i in range(nl):
         rd, rp = np.empty(N, np.float32), np.empty(N, np.int32)
         L.orc_dt1d_f32(np.ascontiguousarray(src[i]), N, -float(np.float32(w_sq)), -float(np.float32(w_lin)), os_, rd, rp)
         assert np.array_equal(dst[i], rd), (i, N, os_, b, kreg)
         assert np.array_equal(ptr[i].astype(np.int32), rp), (i, N, os_, b, kreg)
-    return pops.value
+    check.exact = pops[1]
+    return pops[0]
 
 
 @pytest.mark.parametrize("kind", ["noise", "smooth", "spikes", "ties", "convex", "flat"])
@@ -69,6 +70,20 @@ def test_long_lines_and_extreme_anchors():
         check(gen(rng, "noise", 8, 33), 0.05, 0.01, os_, 8, 8)
     check(gen(rng, "noise", 8, 64), 5.0, 0.0, 0, 4, 8)        # steep parabolas: every sample owns its own position
     check(gen(rng, "noise", 8, 64), 1e-4, 0.0, 1, 8, 0)       # nearly flat: one or two winners for the whole line
+
+
+def test_fp32_certificates_fall_back_to_double_when_they_must():
+    rng = np.random.default_rng(23)
+    x = gen(rng, "smooth", 16, 158)
+    check(x, 0.012, 0.005, 1, 8, 8)
+    assert check.exact < 0.01 * x.size                          # score-map magnitudes: the double path is the exception
+    check(x * 3e4, 0.012, 0.005, 1, 8, 8)                       # huge magnitudes: eps > 1/2, nothing can be certified
+    assert check.exact >= x.size - 16 * 2
+    check(x * 1e-6, 0.012, 0.005, 1, 8, 8)                      # nearly flat: break points at half-integers + tiny offsets, still certified
+    q = np.round(x * 8) / 8
+    check(q.astype(np.float32), 0.0625, 0.0, 0, 4, 8)           # dyadic weights and values: break points exactly on integers / equal
+    assert check.exact > 0
+    check(gen(rng, "ties", 8, 200), 0.03125, 0.0, -2, 8, 8)
 
 
 def test_pop_sites_are_rare_on_smooth_maps():

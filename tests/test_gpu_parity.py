@@ -140,6 +140,41 @@ def test_dt2d_bitexact(h, w, mode):
         assert np.array_equal(iy[i], y), i
 
 
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("h,w", [(1, 1), (3, 2), (33, 65), (118, 158), (268, 478), (60, 700)])
+def test_dt2d_both_kernel_generations_bitexact(h, w, impl):
+    """The streaming envelope (impl 1: one lane per line) and the parallel-in-q kernels (impl 2: a warp per batch of lines in shared
+    memory; register window 8 / 16 / none by line length) against the oracle, through the pre-allocated plan API."""
+    import torch
+    from partsbaseddetector_b200 import Dt2dPlan
+    rng = np.random.default_rng(h * 977 + w + impl)
+    n = 7
+    maps = np.stack([synth_score_map(10 + i, h, w) for i in range(n)])
+    maps[4] = -1.5
+    maps[5] = np.round(maps[5] * 2) / 2
+    maps[6] = np.cumsum(np.cumsum(maps[6], axis=0), axis=1) * 0.01            # smooth ramps: long runs without pops, then bursts
+    defw = np.stack([rng.uniform(0.01, 0.08, n), rng.uniform(-0.02, 0.02, n), rng.uniform(0.01, 0.08, n), rng.uniform(-0.02, 0.02, n)], axis=1).astype(np.float32)
+    anchors = np.stack([rng.integers(-8, 9, n), rng.integers(-11, 13, n)], axis=1).astype(np.int32)
+    plan = Dt2dPlan(n, h, w, defw, anchors, impl)
+    assert plan.impl() == impl
+    d_in = torch.from_numpy(maps).cuda()
+    d_out = torch.empty_like(d_in)
+    d_ix = torch.empty((n, h, w), dtype=torch.int16, device="cuda")
+    d_iy = torch.empty_like(d_ix)
+    L = oracle_lib.lib()
+    for mode in (0, 1):
+        plan.run(d_in.data_ptr(), d_out.data_ptr(), d_ix.data_ptr(), d_iy.data_ptr(), mode, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        out, ix, iy = d_out.cpu().numpy(), d_ix.cpu().numpy().view(np.uint16), d_iy.cpu().numpy().view(np.uint16)
+        for i in range(n):
+            o, x, y = np.empty((h, w), np.float32), np.empty((h, w), np.int32), np.empty((h, w), np.int32)
+            L.orc_dt2d_f32(maps[i].reshape(-1), h, w, defw[i], int(anchors[i, 0]), int(anchors[i, 1]), mode, o.reshape(-1), x.reshape(-1), y.reshape(-1))
+            assert np.array_equal(out[i], o), (i, mode)
+            assert np.array_equal(ix[i].astype(np.int32), x), (i, mode)
+            assert np.array_equal(iy[i].astype(np.int32), y), (i, mode)
+    plan.close()
+
+
 def test_dt2d_rejects_bad_arguments():
     with pytest.raises(PbdError):
         dt2d(np.zeros((4, 4), np.float32), [0.0, 0.0, 0.01, 0.0], [0, 0])       # a = -w0 must be < 0

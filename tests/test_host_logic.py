@@ -132,6 +132,39 @@ def test_nms_matches_oracle_restatement():
     assert c.boundingBox() == (x0, y0, (rects[0, :, 0] + rects[0, :, 2]).max() - x0, (rects[0, :, 1] + rects[0, :, 3]).max() - y0)
 
 
+def test_batch_sort_then_nms_keeps_frames_independent():
+    """The documented batch flow Candidate.sort (a global score sort that interleaves frames) followed by nonMaximaSuppression must
+    equal per-frame sort + NMS: the scratch image is per frame, whatever the list order."""
+    from partsbaseddetector_b200 import Candidate
+    from partsbaseddetector_b200.detector import CandidateList
+    rng = np.random.default_rng(11)
+    h, w, nparts, nframes = 90, 120, 3, 4
+    n = 200
+    meta = np.zeros((n, 4), np.int32)
+    meta[:, 0] = rng.integers(0, nframes, n)
+    meta[:, 3] = nparts
+    parts = np.zeros((n, nparts, 7), np.int32)
+    parts[:, :, 3] = rng.integers(-10, w, (n, nparts)); parts[:, :, 4] = rng.integers(-10, h, (n, nparts))
+    parts[:, :, 5] = rng.integers(4, 25, (n, nparts)); parts[:, :, 6] = rng.integers(4, 25, (n, nparts))
+    parts[:, :, 0] = np.arange(n)[:, None]
+    scores = rng.permutation(n).astype(np.float32)               # distinct
+    # the advisor's minimal case: 2 frames x 2 identical boxes, interleaved by the sort, overlap 0 -> one survivor per frame
+    m2 = np.array([[0, 0, 0, 1], [1, 0, 0, 1], [0, 0, 0, 1], [1, 0, 0, 1]], np.int32)
+    p2 = np.zeros((4, 1, 7), np.int32); p2[:, 0, 3:7] = (10, 10, 20, 20)
+    out = Candidate.nonMaximaSuppression((h, w), CandidateList(m2, np.array([4, 3, 2, 1], np.float32), p2), 0.0)
+    assert [(c.frame, float(c.score())) for c in out] == [(0, 4.0), (1, 3.0)]
+    for overlap in (0.0, 0.3):
+        batch = Candidate.nonMaximaSuppression((h, w), CandidateList(*(a[np.argsort(-scores, kind="stable")] for a in (meta, scores, parts))), overlap)
+        got = sorted(int(c.x[0]) for c in batch)
+        want = []
+        for f in range(nframes):
+            sel = np.nonzero(meta[:, 0] == f)[0]
+            sel = sel[np.argsort(-scores[sel], kind="stable")]
+            want += [int(c.x[0]) for c in Candidate.nonMaximaSuppression((h, w), CandidateList(meta[sel], scores[sel], parts[sel]), overlap)]
+        assert got == sorted(want) and 0 < len(got) < n
+        assert [float(c.score()) for c in batch] == sorted((float(c.score()) for c in batch), reverse=True)   # list order survives
+
+
 def test_pyramid_geometry_matches_oracle_over_many_sizes():
     """Level tables (image sizes, HOG cell counts, scales) of the product's host code vs the oracle's restatement of
     src/HOGFeatures.cpp:95-127,174-176 for ~1500 image sizes incl. exact powers of two of 5*sbin (floor(log/log) edge cases)."""
