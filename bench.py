@@ -262,6 +262,9 @@ def run_gpu_arm(args):
     det.distributeModel(Model.load_bin(MODEL))
     det.set_option("max_candidates", 1 << 20)
     det.set_option("max_levels", cfg["max_levels"])
+    for kv in args.opt:                                        # experiments: --opt dt_scan=1
+        k, v = kv.split("=")
+        det.set_option(k, float(v))
     mode = MODES[args.mode]
     det.set_option("response_mode", mode)
     det.set_option("timing", 1)
@@ -519,7 +522,7 @@ def run_dt_arm(args):
         d_ix = torch.empty((nmaps, size, size), dtype=torch.int16, device="cuda")
         d_iy = torch.empty_like(d_ix)
         row = {"size": size, "maps": nmaps, "input_bytes": d_in.numel() * 4}
-        for impl, name in ((1, "streaming"), (2, "parallel_in_q")):
+        for impl, name in ((1, "streaming"), (3, "streaming_scan"), (2, "parallel_in_q")):
             if impl == 2 and size > 1024:
                 continue
             plan = Dt2dPlan(nmaps, size, size, defw, anchors, impl)
@@ -549,12 +552,12 @@ def run_dt_arm(args):
         del d_in, d_out, d_ix, d_iy
         torch.cuda.empty_cache()
     top = sweep[-1]
-    best = max((top.get("streaming") or {}).get("GBps", 0), (top.get("parallel_in_q") or {}).get("GBps", 0))
+    best = max((top.get(k) or {}).get("GBps", 0) for k in ("streaming", "streaming_scan", "parallel_in_q"))
     line = {"metric": "DT microbenchmark: algorithmic HBM GB/s (16 B per map cell), %d maps" % nmaps, "value": best, "unit": "GB/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
-            "ms_per_step": (top.get("streaming") or top.get("parallel_in_q"))["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp64 break points)",
+            "ms_per_step": min(top[k]["ms"] for k in ("streaming", "streaming_scan", "parallel_in_q") if k in top), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp64 break points)",
             "data": "synthetic", "config": {"workload": "DT microbench: %d fp32 score maps per size (26 parts x 6 mixtures), w0,w2~U[0.01,0.02], w1,w3~U[-0.02,0.02], anchors U{-3..3}xU{-2..5}" % nmaps,
                                             "config": "dt", "sizes": [r["size"] for r in sweep], "l2": "256 MB written between timed iterations; inputs of the larger sizes exceed L2"},
-            "roofline": {"kernel": "dt_pass (rows + columns) + dt2d_compose at %d^2" % top["size"], "bound": "hbm", "achieved": best, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "roofline": {"kernel": "best of dt_pass eager / dt_pass lagged-scan / dt_lines (rows + columns + dt2d_compose) at %d^2" % top["size"], "bound": "hbm", "achieved": best, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": best / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src},
             "sweep": sweep, "gpu_launches": 3 * steps}
     print(json.dumps(line))
@@ -581,6 +584,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--also-fast", action="store_true", default=False, help="also time the ffma and tf32 tensor modes (rank 0 only)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--opt", action="append", default=[], help="detector option key=value (pbd_set_option), for experiments")
     ap.add_argument("--dt-maps", type=int, default=156)
     ap.add_argument("--dt-sizes", default="256,512,1024,2048,4096")
     args = ap.parse_args()

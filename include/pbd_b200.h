@@ -118,7 +118,8 @@ void pbd_destroy(pbd_detector* d);
  *                 (forked from and joined back into the detector's stream) so that kernel tails of one group overlap the
  *                 other's work; results do not depend on it.  Batches under 8 frames and timing == 2 use one stream.
  * Environment defaults read at pbd_create: PBD_EXACT=0|1, PBD_RESPONSE_MODE=exact|ffma|tensor|tensor16, PBD_BACKPTR=reference|exact,
- * PBD_MAX_LEVELS=n, PBD_DP_STREAMS=n. */
+ * PBD_MAX_LEVELS=n, PBD_DP_STREAMS=n.  Further keys: "graph" (1: CUDA-graph replay of pbd_enqueue_batch_u8_device), "root_nms" (window
+ * sz > 0: root-map non-maxima suppression of src/nms.cpp before the backtrack; 0 = off, the reference's detect()). */
 int pbd_set_option(pbd_detector* d, const char* key, double value);
 int pbd_get_option(const pbd_detector* d, const char* key, double* value);
 
@@ -160,6 +161,12 @@ int pbd_candidates_sort(pbd_candidates* c);
  * current order (callers sort first, ros/Node.cpp:192-196), applied independently per frame of the batch.  A candidate is
  * dropped when more than `overlap` of its (image-clipped) bounding box has already been painted by kept candidates. */
 int pbd_candidates_nms(pbd_candidates* c, int im_h, int im_w, float overlap);
+/* SearchSpacePruning<T>::filterCandidatesByDepth (src/SearchSpacePruning.cpp:73-95; the call the reference keeps commented out at
+ * src/PartsBasedDetector.cpp:91-93, zfactor 0.03): drops every candidate with a part whose median depth differs from its parent's by
+ * more than |anchor| * zfactor (both medians > 0).  depth = im_h x im_w float image (row_stride_bytes 0 = packed) of the frame the
+ * candidates come from; boxes are clipped to it (the reference asserts on boxes that cross the border). */
+int pbd_candidates_filter_by_depth(pbd_candidates* c, const pbd_model* m, const float* depth, int im_h, int im_w, size_t row_stride_bytes,
+                                   float zfactor);
 /* build a candidate set from arrays (layout of pbd_candidates_export); for callers that post-process their own lists */
 int pbd_candidates_create(int n, int max_nparts, const int32_t* meta4, const float* scores, const int32_t* parts7,
                           pbd_candidates** out);
@@ -214,12 +221,33 @@ int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, 
 /* The same transform with every table and scratch buffer owned by a plan, so that pbd_dt2d_plan_run only enqueues kernels on
  * `stream` (no allocation, no synchronisation): what the DT microbenchmark times.  impl: 0 = default (1), 1 = streaming envelope
  * (one lane per line, any length <= 4096; the kernels the detector runs), 2 = parallel-in-q (a warp per batch of lines in shared
- * memory, lines <= 1024; bit-identical, kept as a measured alternative). */
+ * memory, lines <= 1024; bit-identical, kept as a measured alternative), 3 = streaming envelope with lagged-scan emission (one store
+ * per position: the variant for rough inputs such as the white-noise maps of the microbenchmark). */
 typedef struct pbd_dt2d_plan pbd_dt2d_plan;
 int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, int impl, pbd_dt2d_plan** out);
 int pbd_dt2d_plan_impl(const pbd_dt2d_plan* p);
 int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode);
 void pbd_dt2d_plan_destroy(pbd_dt2d_plan* p);
+
+/* --------------------------------------------------------------- ingest ---
+ * What the reference's callers do before detect(): cv::imread (src/demo.cpp:88-99) and cv_bridge::toCvCopy (ros/Node.cpp:165-176).
+ * Containers: PNG (zlib) and binary PNM; JPEG is not decoded here (PBD_E_UNSUPPORTED).  All host code. */
+/* header only: size, channels as stored (1, 2, 3, 4) and bits per sample (8 / 16) */
+int pbd_image_info(const uint8_t* bytes, size_t n, int32_t* h, int32_t* w, int32_t* channels, int32_t* bits);
+/* cv::imread(..., IMREAD_COLOR): packed 8-bit BGR (grey replicated, alpha dropped, 16-bit samples >> 8); dst_capacity in bytes */
+int pbd_image_decode_bgr8(const uint8_t* bytes, size_t n, uint8_t* dst, size_t dst_capacity, int32_t* h, int32_t* w);
+/* cv::imread(..., IMREAD_ANYDEPTH) of a depth image, times `scale` (the demo: 1/1000, mm -> m); dst_capacity in floats */
+int pbd_image_decode_depth_f32(const uint8_t* bytes, size_t n, float scale, float* dst, size_t dst_capacity, int32_t* h, int32_t* w);
+/* file variant; dst_capacity = 0 only queries the size */
+int pbd_imread_bgr8(const char* path, uint8_t* dst, size_t dst_capacity, int32_t* h, int32_t* w);
+/* sensor_msgs/Image payload (encoding bgr8 / rgb8 / bgra8 / rgba8 / mono8 / mono16 / bgr16 / rgb16 / 8UC1 / 8UC3 / 8UC4 / 16UC1) -> packed
+ * BGR8, as cv_bridge::toCvCopy(msg, enc::BGR8); step = bytes per row (0 = packed) */
+int pbd_ros_image_to_bgr8(const char* encoding, int h, int w, size_t step, int is_bigendian, const uint8_t* data, uint8_t* dst_bgr8);
+/* sensor_msgs/Image depth payload (32FC1 / 16UC1) -> packed float, as cv_bridge::toCvCopy(msg, enc::TYPE_32FC1) */
+int pbd_ros_depth_to_f32(const char* encoding, int h, int w, size_t step, int is_bigendian, const uint8_t* data, float* dst);
+/* pinned (page-locked, portable) host memory for the frame ring of pbd_submit_batch_u8 */
+int pbd_host_alloc_pinned(size_t bytes, void** out);
+void pbd_host_free_pinned(void* p);
 
 /* ----------------------------------------------------------- measurement --- */
 /* number of kernels launched by this detector since creation (bench.py's gpu_launches) */

@@ -776,6 +776,76 @@ int orc_nms(const int* rects, int n, int nparts, int im_h, int im_w, float overl
   return nk;
 }
 
+// nonMaximaSuppression(src, sz, dst, mask) of reference src/nms.cpp:84-129 (Neubeck / Van Gool block-wise strict local maxima):
+// the map is cut into (sz+1) x (sz+1) blocks; the block's first maximum (row-major, strict >) is a local maximum iff it is strictly
+// greater than every element of the (2 sz + 1)^2 window centred on it that lies outside the block.  mask (optional, non-zero =
+// eligible) restricts both searches; cv::minMaxLoc over an empty selection yields the value 0 at (-1, -1), which the reference
+// then offsets and may write out of bounds -- guarded here (such a block has no eligible element and produces no maximum unless
+// the reference's bogus comparison 0 > vnmax fires inside the map, which is replicated when the offset location is in range).
+void orc_rootmap_nms(const float* src, int M, int N, int sz, const uint8_t* mask, uint8_t* dst) {
+  for (size_t i = 0; i < (size_t)M * N; ++i) dst[i] = 0;
+  auto sel_max = [&](int y0, int y1, int x0, int x1, int by0, int by1, int bx0, int bx1, bool exclude, double& vmax, int& ym, int& xm) {
+    bool any = false;
+    vmax = 0; ym = -1; xm = -1;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        if (mask && !mask[(size_t)y * N + x]) continue;
+        if (exclude && y >= by0 && y < by1 && x >= bx0 && x < bx1) continue;
+        const double v = (double)src[(size_t)y * N + x];
+        if (!any || v > vmax) { vmax = v; ym = y; xm = x; any = true; }
+      }
+    return any;
+  };
+  for (int m = 0; m < M; m += sz + 1)
+    for (int n = 0; n < N; n += sz + 1) {
+      const int i1 = std::min(m + sz + 1, M), j1 = std::min(n + sz + 1, N);
+      double vc, vn;
+      int yc, xc, yn, xn;
+      const bool any = sel_max(m, i1, n, j1, 0, 0, 0, 0, false, vc, yc, xc);
+      if (!any) { yc = m - 1; xc = n - 1; }                        // ijmax = (-1,-1) + block origin (:101)
+      const int in0 = std::max(yc - sz, 0), in1 = std::min(yc + sz + 1, M), jn0 = std::max(xc - sz, 0), jn1 = std::min(xc + sz + 1, N);
+      // blockmask: zero over the block's rows/columns relative to the window (:111-114)
+      const int iis0 = m - in0, iis1 = std::min(m - in0 + sz + 1, in1 - in0), jis0 = n - jn0, jis1 = std::min(n - jn0 + sz + 1, jn1 - jn0);
+      sel_max(in0, in1, jn0, jn1, in0 + iis0, in0 + iis1, jn0 + jis0, jn0 + jis1, true, vn, yn, xn);
+      if (vc > vn && yc >= 0 && xc >= 0) dst[(size_t)yc * N + xc] = 255;
+    }
+}
+
+// SearchSpacePruning<T>::filterCandidatesByDepth (reference src/SearchSpacePruning.cpp:73-95) with Math::median
+// (include/Math.hpp:62-72: std::nth_element at size/2): a candidate survives iff for no part p = nparts-1 .. 1 both the child's and
+// the parent's box have a positive median depth that differ by more than |anchor(p, mixture 0)| * zfactor.  rects = n x nparts x
+// (x, y, w, h); parent / anchor0 = per part; boxes are clipped to the depth image here (the reference takes depth(box) unclipped
+// and asserts inside OpenCV when a box crosses the border); an empty box has median 0.  Candidates of a one-part component are
+// all dropped (the reference's loop never reaches its push_back).
+int orc_filter_by_depth(const int* rects, int n, int nparts, const int* parent, const int* anchor0_xy, const float* depth, int im_h, int im_w,
+                        float zfactor, int* keep) {
+  auto median = [&](const int* r) -> float {
+    int x0 = std::max(r[0], 0), y0 = std::max(r[1], 0), x1 = std::min(r[0] + r[2], im_w), y1 = std::min(r[1] + r[3], im_h);
+    if (x1 <= x0 || y1 <= y0) return 0.f;
+    std::vector<float> v;
+    v.reserve((size_t)(x1 - x0) * (y1 - y0));
+    for (int y = y0; y < y1; ++y) for (int x = x0; x < x1; ++x) v.push_back(depth[(size_t)y * im_w + x]);
+    std::nth_element(v.begin(), v.begin() + v.size() / 2, v.end());
+    return v[v.size() / 2];
+  };
+  int nk = 0;
+  for (int i = 0; i < n; ++i) {
+    const int* R = rects + (size_t)i * nparts * 4;
+    bool kept = false;
+    for (int p = nparts - 1; p >= 1; --p) {
+      const float cm = median(R + 4 * p), pm = median(R + 4 * parent[p]);
+      if (cm > 0 && pm > 0) {
+        const double nrm = std::sqrt((double)anchor0_xy[2 * p] * anchor0_xy[2 * p] + (double)anchor0_xy[2 * p + 1] * anchor0_xy[2 * p + 1]);
+        if (std::abs(cm - pm) > nrm * zfactor) break;
+      }
+      if (p == 1) kept = true;
+    }
+    keep[i] = kept ? 1 : 0;
+    nk += kept;
+  }
+  return nk;
+}
+
 // ---- detector handle ----
 // hdr = {interval, sbin, norient, flen, nfilters, nbias, ndefs, ncomp}; fdims = (kh,kw) per filter;
 // indexers = for c: nparts, then for p: parentid, nf, nb, nd, filterid[nf], biasid[nb], defid[nd]

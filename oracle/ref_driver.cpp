@@ -10,6 +10,8 @@
 //                                   bias(mm)[m] out of bounds when the child has fewer mixtures than the parent; callers only pass
 //                                   models for which the reference is defined)
 //   include/Candidate.hpp           Candidate::sort / nonMaximaSuppression
+//   src/nms.cpp                     nonMaximaSuppression(src, sz, dst, mask): block-wise strict local maxima of a score map
+//   src/SearchSpacePruning.cpp      SearchSpacePruning<T>::filterCandidatesByDepth (+ Math::median)
 // Not compiled: src/SpatialConvolutionEngine.cpp + src/filter.cpp (a 4 kLoC copy of OpenCV's FilterEngine that needs OpenCV's
 // internal headers; the response restatement stays pinned to cv2.filter2D at 1e-5 / 1e-11, tests/test_oracle_pins.py).
 #include <cstdint>
@@ -23,6 +25,8 @@
 #include "DynamicProgram.hpp"
 #include "HOGFeatures.hpp"
 #include "Math.hpp"
+#include "SearchSpacePruning.hpp"
+#include "nms.hpp"
 
 extern "C" {
 // the oracle's restatements of cv::resize (INTER_LINEAR, 8U) and cv::pyrDown (oracle/pbd_oracle.cpp)
@@ -182,6 +186,29 @@ void ref_dp_get_backptr(void* h, int level, int comp, int part, int pm, int* ix,
       const size_t o = (size_t)y * X.cols + x;
       ix[o] = X.at<int>(y, x); iy[o] = Y.at<int>(y, x); ik[o] = K.at<int>(y, x);
     }
+}
+// nonMaximaSuppression of src/nms.cpp:84-129 on one float map; mask may be null (the unmasked call)
+void ref_rootmap_nms(const float* src, int h, int w, int sz, const uint8_t* mask, uint8_t* dst) {
+  cv::Mat m(h, w, CV_32F), k, out;
+  std::memcpy(m.data, src, sizeof(float) * (size_t)h * w);
+  if (mask) { k = cv::Mat(h, w, CV_8U); std::memcpy(k.data, mask, (size_t)h * w); }
+  nonMaximaSuppression(m, sz, out, k);
+  for (int y = 0; y < h; ++y) std::memcpy(dst + (size_t)y * w, out.ptr(y), w);
+}
+// SearchSpacePruning<float>::filterCandidatesByDepth on the candidates of the last run (boxes must lie inside the depth image: the
+// reference takes depth(box) without clipping); keep[i] = 1 for the survivors, returns their number.  Math::median prints every box
+// to std::cerr (include/Math.hpp:70): the caller redirects fd 2.
+int ref_dp_filter_by_depth(void* h, const float* depth, int im_h, int im_w, float zfactor, int* keep) {
+  RefDP* D = (RefDP*)h;
+  cv::Mat d(im_h, im_w, CV_32F);
+  std::memcpy(d.data, depth, sizeof(float) * (size_t)im_h * im_w);
+  vectorCandidate c = D->cands;
+  for (size_t i = 0; i < c.size(); ++i) c[i].setScore((float)i);          // tag: the survivors are identified by their score slot
+  SearchSpacePruning<float> ssp;
+  ssp.filterCandidatesByDepth(D->parts, c, d, zfactor);
+  for (size_t i = 0; i < D->cands.size(); ++i) keep[i] = 0;
+  for (size_t i = 0; i < c.size(); ++i) keep[(int)c[i].score()] = 1;
+  return (int)c.size();
 }
 int ref_dp_candidate_nparts(void* h, int i) { return (int)((RefDP*)h)->cands[i].parts().size(); }
 // rects = nparts x (x, y, width, height); conf = nparts confidences; the reference's Candidate keeps neither level nor part indices

@@ -164,6 +164,22 @@ class FilterEngine;     // only named in types.hpp (vectorFilterEngine)
 template <typename T> class Mat_;
 template <typename T> class MatIterator_;
 
+struct Range {
+  int start, end;
+  Range() : start(0), end(0) {}
+  Range(int s, int e) : start(s), end(e) {}
+  int size() const { return end - start; }
+};
+// the slice of cv::MatExpr the reference uses: Mat_<T>::zeros / ones (optionally scaled).  Assigned to an existing matrix of the
+// same size and type it fills that matrix IN PLACE (OpenCV's MatOp_Initializer::assign), which is how `roi = Mat_::zeros(...)`
+// clears a region of interest in src/nms.cpp:114.
+struct MatInit {
+  int rows, cols, type;
+  double value;
+};
+inline MatInit operator*(double s, MatInit m) { m.value *= s; return m; }
+inline MatInit operator*(MatInit m, double s) { m.value *= s; return m; }
+
 // Reference-counted 2-D array header (continuous rows or a region of interest inside a parent buffer).
 class Mat {
  public:
@@ -178,6 +194,13 @@ class Mat {
   Mat(int r, int c, int type, void* ext, size_t step_ = 0) : flags(type), rows(r), cols(c), data((uchar*)ext) {
     step = step_ ? step_ : (size_t)c * elemSize();
   }
+  Mat(const MatInit& e) { create(e.rows, e.cols, e.type); setTo(Scalar_<double>(e.value)); }                 // NOLINT: implicit, as MatExpr -> Mat
+  Mat& operator=(const MatInit& e) {
+    if (!(data && rows == e.rows && cols == e.cols && flags == e.type)) create(e.rows, e.cols, e.type);
+    return setTo(Scalar_<double>(e.value));
+  }
+  Mat operator()(const Range& r, const Range& c) const;
+  Mat mul(const Mat& o) const;
   void create(int r, int c, int type) {
     if (data && r == rows && c == cols && type == flags && isContinuous()) return;
     flags = type; rows = r; cols = c;
@@ -229,9 +252,9 @@ class Mat {
     m.data = data + (size_t)r.y * step + (size_t)r.x * elemSize();
     return m;
   }
-  Mat& operator=(const Scalar& s) { return setTo(s); }
-  Mat& setTo(const Scalar& s);
-  Mat& setTo(const Scalar& s, const Mat& mask);
+  Mat& operator=(const Scalar_<double>& s) { return setTo(s); }
+  Mat& setTo(const Scalar_<double>& s);
+  Mat& setTo(const Scalar_<double>& s, const Mat& mask);
   template <typename T> MatIterator_<T> begin();
   template <typename T> MatIterator_<T> end();
 };
@@ -256,6 +279,9 @@ template <typename T> class MatIterator_ {
   bool operator==(const MatIterator_& o) const { return i == o.i; }
   bool operator!=(const MatIterator_& o) const { return i != o.i; }
   bool operator<(const MatIterator_& o) const { return i < o.i; }
+  bool operator<=(const MatIterator_& o) const { return i <= o.i; }
+  bool operator>(const MatIterator_& o) const { return i > o.i; }
+  bool operator>=(const MatIterator_& o) const { return i >= o.i; }
 };
 template <typename T> MatIterator_<T> Mat::begin() { return MatIterator_<T>(this, 0); }
 template <typename T> MatIterator_<T> Mat::end() { return MatIterator_<T>(this, total()); }
@@ -273,6 +299,21 @@ template <typename F> inline void by_depth(int depth, F f) {
 }
 }  // namespace shim
 
+inline Mat Mat::operator()(const Range& r, const Range& c) const {
+  Mat m = *this;
+  m.rows = r.size(); m.cols = c.size();
+  m.data = data + (size_t)r.start * step + (size_t)c.start * elemSize();
+  return m;
+}
+inline Mat Mat::mul(const Mat& o) const {                // elementwise product, saturated to the depth (8U masks: 255 * 255 -> 255)
+  assert(size() == o.size() && type() == o.type());
+  Mat out(rows, cols, flags);
+  shim::by_depth(depth(), [&](auto t) {
+    typedef decltype(t) T;
+    for (int y = 0; y < rows; ++y) { const T* a = ptr<T>(y); const T* b = o.ptr<T>(y); T* d = out.ptr<T>(y); for (int x = 0; x < cols * channels(); ++x) d[x] = saturate_cast<T>((double)a[x] * (double)b[x]); }
+  });
+  return out;
+}
 inline void Mat::convertTo(Mat& dst, int rtype) const {
   const int ddepth = rtype < 0 ? depth() : CV_MAT_DEPTH(rtype);
   Mat out(rows, cols, CV_MAKETYPE(ddepth, channels()));
@@ -313,6 +354,12 @@ template <typename T> class Mat_ : public Mat {
   explicit Mat_(Size s) : Mat(s, DataType<T>::type) {}
   Mat_(const Mat& m) { assign(m); }
   Mat_(const Mat_& m) : Mat(m) {}
+  Mat_(const MatInit& e) : Mat(e) {}                         // NOLINT
+  Mat_& operator=(const MatInit& e) { Mat::operator=(e); return *this; }
+  static MatInit zeros(Size s) { return MatInit{s.height, s.width, DataType<T>::type, 0.0}; }
+  static MatInit ones(Size s) { return MatInit{s.height, s.width, DataType<T>::type, 1.0}; }
+  Mat_ operator()(const Range& r, const Range& c) const { return Mat_(Mat::operator()(r, c)); }
+  Mat_ operator()(const Rect& r) const { return Mat_(Mat::operator()(r)); }
   Mat_& operator=(const Mat& m) { assign(m); return *this; }
   Mat_& operator=(const Mat_& m) { Mat::operator=(m); return *this; }
   void create(Size s) { Mat::create(s, DataType<T>::type); }
@@ -387,15 +434,33 @@ inline void transpose(const Mat& src, Mat& dst) {
   dst = out;
 }
 template <typename T> inline void transpose(const Mat_<T>& src, Mat_<T>& dst) { Mat out; transpose(static_cast<const Mat&>(src), out); dst = out; }
-inline void minMaxLoc(const Mat& m, double* minv, double* maxv, Point* = nullptr, Point* = nullptr) {
-  double lo = std::numeric_limits<double>::infinity(), hi = -lo;
+inline Mat noArray() { return Mat(); }
+// cv::minMaxLoc: first minimum / maximum in row-major order (strict comparisons); with a mask only its non-zero elements take part,
+// and if there is none the values are 0 and the locations (-1, -1) (core/src/stat.cpp, minMaxIdx)
+inline void minMaxLoc(const Mat& m, double* minv, double* maxv, Point* minloc = nullptr, Point* maxloc = nullptr, const Mat& mask = Mat()) {
+  double lo = 0, hi = 0;
+  Point lp(-1, -1), hp(-1, -1);
+  bool any = false;
   shim::by_depth(m.depth(), [&](auto t) {
     typedef decltype(t) T;
-    for (int y = 0; y < m.rows; ++y) { const T* p = m.ptr<T>(y); for (int x = 0; x < m.cols * m.channels(); ++x) { lo = std::min(lo, (double)p[x]); hi = std::max(hi, (double)p[x]); } }
+    for (int y = 0; y < m.rows; ++y) {
+      const T* p = m.ptr<T>(y);
+      const uchar* k = mask.empty() ? nullptr : mask.ptr<uchar>(y);
+      for (int x = 0; x < m.cols * m.channels(); ++x) {
+        if (k && !k[x]) continue;
+        const double v = (double)p[x];
+        if (!any) { lo = hi = v; lp = hp = Point(x, y); any = true; continue; }
+        if (v < lo) { lo = v; lp = Point(x, y); }
+        if (v > hi) { hi = v; hp = Point(x, y); }
+      }
+    }
   });
   if (minv) *minv = lo;
   if (maxv) *maxv = hi;
+  if (minloc) *minloc = lp;
+  if (maxloc) *maxloc = hp;
 }
+template <typename T> inline double norm(const Point_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y); }
 inline Scalar sum(const Mat& m) {
   Scalar s;
   shim::by_depth(m.depth(), [&](auto t) {

@@ -26,11 +26,12 @@ EXPORTS = [
     "pbd_model_part", "pbd_create", "pbd_destroy", "pbd_set_option", "pbd_get_option", "pbd_detect_batch_u8",
     "pbd_detect_batch_u8_device", "pbd_enqueue_batch_u8_device", "pbd_collect_candidates", "pbd_submit_batch_u8", "pbd_collect_ticket",
     "pbd_candidates_count", "pbd_candidates_nparts", "pbd_candidates_get", "pbd_candidates_export", "pbd_candidates_free",
-    "pbd_candidates_sort", "pbd_candidates_nms", "pbd_candidates_create", "pbd_stage_pyramid", "pbd_stage_pdf", "pbd_stage_dp_min", "pbd_stage_dp_argmin",
+    "pbd_candidates_sort", "pbd_candidates_nms", "pbd_candidates_filter_by_depth", "pbd_candidates_create", "pbd_stage_pyramid", "pbd_stage_pdf", "pbd_stage_dp_min", "pbd_stage_dp_argmin",
     "pbd_pyramid_geometry", "pbd_num_frames", "pbd_num_levels", "pbd_level_info", "pbd_get_pyramid_image", "pbd_get_features",
     "pbd_get_response", "pbd_get_rootv", "pbd_get_rooti", "pbd_get_backptr", "pbd_set_levels",
     "pbd_set_features", "pbd_set_response", "pbd_dt2d_f32_device", "pbd_dt2d_f32", "pbd_dt2d_plan_create", "pbd_dt2d_plan_impl",
-    "pbd_dt2d_plan_run", "pbd_dt2d_plan_destroy", "pbd_launch_count",
+    "pbd_dt2d_plan_run", "pbd_dt2d_plan_destroy", "pbd_image_info", "pbd_image_decode_bgr8", "pbd_image_decode_depth_f32", "pbd_imread_bgr8",
+    "pbd_ros_image_to_bgr8", "pbd_ros_depth_to_f32", "pbd_host_alloc_pinned", "pbd_host_free_pinned", "pbd_launch_count",
     "pbd_stage_times_ms", "pbd_kernel_times_ms", "pbd_device_bytes",
 ]
 
@@ -97,6 +98,7 @@ def lib():
     L.pbd_candidates_free.argtypes = [vp]
     L.pbd_candidates_sort.argtypes = [vp]
     L.pbd_candidates_nms.argtypes = [vp, ci, ci, cf]
+    L.pbd_candidates_filter_by_depth.argtypes = [vp, vp, _f32p, ci, ci, C.c_size_t, cf]
     L.pbd_candidates_create.argtypes = [ci, ci, _i32p, _f32p, _i32p, P(vp)]
     L.pbd_stage_pyramid.argtypes = [vp, vp, ci, ci, ci, ci, C.c_size_t, C.c_size_t]
     L.pbd_stage_pdf.argtypes = [vp]
@@ -122,6 +124,15 @@ def lib():
     L.pbd_dt2d_plan_run.argtypes = [vp, vp, vp, vp, vp, vp, ci]
     L.pbd_dt2d_plan_destroy.argtypes = [vp]
     L.pbd_dt2d_plan_destroy.restype = None
+    L.pbd_image_info.argtypes = [_u8p, C.c_size_t, P(ci), P(ci), P(ci), P(ci)]
+    L.pbd_image_decode_bgr8.argtypes = [_u8p, C.c_size_t, _u8p, C.c_size_t, P(ci), P(ci)]
+    L.pbd_image_decode_depth_f32.argtypes = [_u8p, C.c_size_t, cf, _f32p, C.c_size_t, P(ci), P(ci)]
+    L.pbd_imread_bgr8.argtypes = [C.c_char_p, vp, C.c_size_t, P(ci), P(ci)]
+    L.pbd_ros_image_to_bgr8.argtypes = [C.c_char_p, ci, ci, C.c_size_t, ci, _u8p, _u8p]
+    L.pbd_ros_depth_to_f32.argtypes = [C.c_char_p, ci, ci, C.c_size_t, ci, _u8p, _f32p]
+    L.pbd_host_alloc_pinned.argtypes = [C.c_size_t, P(vp)]
+    L.pbd_host_free_pinned.argtypes = [vp]
+    L.pbd_host_free_pinned.restype = None
     L.pbd_launch_count.argtypes = [vp]
     L.pbd_launch_count.restype = C.c_longlong
     L.pbd_stage_times_ms.argtypes = [vp, _f32p]

@@ -1,5 +1,6 @@
 // abi.cpp -- extern "C" boundary (include/pbd_b200.h).  Exceptions never cross it.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -8,6 +9,7 @@
 
 #include "../../include/pbd_b200.h"
 #include "engine.hpp"
+#include "ingest.hpp"
 #include "model.hpp"
 
 using namespace pbd;
@@ -202,6 +204,8 @@ int pbd_set_option(pbd_detector* d, const char* key, double value) {
     else if (k == "nms_overlap") { REQUIRE(value < 1.0, "nms_overlap must be < 1 (negative = off)"); e.nms_overlap = value; }
     else if (k == "dp_streams") { REQUIRE(value >= 1 && value <= 8, "dp_streams must be 1..8"); e.dp_streams = (int)value; }
     else if (k == "graph") e.use_graph = value != 0;
+    else if (k == "dt_scan") e.dt_scan = value != 0;
+    else if (k == "root_nms") { REQUIRE(value >= 0 && value <= 64, "root_nms window must be 0 (off) .. 64"); e.root_nms = (int)value; }
     else throw ArgError("unknown option '" + k + "'");
   });
 }
@@ -220,6 +224,8 @@ int pbd_get_option(const pbd_detector* d, const char* key, double* value) {
     else if (k == "timing") *value = e.timing;
     else if (k == "dp_streams") *value = e.dp_streams;
     else if (k == "graph") *value = e.use_graph;
+    else if (k == "dt_scan") *value = e.dt_scan;
+    else if (k == "root_nms") *value = e.root_nms;
     else if (k == "nms_overlap") *value = e.nms_overlap;
     else throw ArgError("unknown option '" + k + "'");
   });
@@ -379,6 +385,46 @@ int pbd_candidates_nms(pbd_candidates* c, int im_h, int im_w, float overlap) {
   });
 }
 
+// SearchSpacePruning<T>::filterCandidatesByDepth (reference src/SearchSpacePruning.cpp:73-95, the call commented out at
+// src/PartsBasedDetector.cpp:91-93) with Math::median (include/Math.hpp:62-72).  Host code: candidates and depth image are host data.
+int pbd_candidates_filter_by_depth(pbd_candidates* c, const pbd_model* m, const float* depth, int im_h, int im_w, size_t row_stride_bytes, float zfactor) {
+  return guarded([&] {
+    REQUIRE(c && m && depth && im_h > 0 && im_w > 0, "bad argument");
+    if (row_stride_bytes == 0) row_stride_bytes = (size_t)im_w * sizeof(float);
+    REQUIRE(row_stride_bytes >= (size_t)im_w * sizeof(float) && row_stride_bytes % sizeof(float) == 0, "bad depth row stride");
+    const size_t pitch = row_stride_bytes / sizeof(float);
+    const CandidateSet& S = c->s;
+    const Model& M = m->m;
+    std::vector<float> buf;
+    auto median = [&](const int* o) -> float {                    // o = part record: rect at o[3..6]; the box is clipped to the image
+      const int x0 = std::max(o[3], 0), y0 = std::max(o[4], 0), x1 = std::min(o[3] + o[5], im_w), y1 = std::min(o[4] + o[6], im_h);
+      if (x1 <= x0 || y1 <= y0) return 0.f;
+      buf.clear();
+      for (int y = y0; y < y1; ++y) buf.insert(buf.end(), depth + (size_t)y * pitch + x0, depth + (size_t)y * pitch + x1);
+      std::nth_element(buf.begin(), buf.begin() + buf.size() / 2, buf.end());
+      return buf[buf.size() / 2];
+    };
+    std::vector<int> kept;
+    for (int i = 0; i < S.n; ++i) {
+      const int comp = S.meta[(size_t)i * 4 + 2], np = S.meta[(size_t)i * 4 + 3];
+      REQUIRE(comp >= 0 && comp < M.ncomponents() && np == (int)M.comps[comp].size(), "candidate does not belong to this model");
+      const auto& parts = M.comps[comp];
+      bool keep = false;
+      for (int p = np - 1; p >= 1; --p) {
+        const float cm = median(S.part(i, p)), pm = median(S.part(i, parts[p].parentid));
+        if (cm > 0 && pm > 0) {
+          const int did = parts[p].defid[0];                       // part.anchor(0)
+          const double ax = M.anchors[did * 2], ay = M.anchors[did * 2 + 1];
+          if (std::abs(cm - pm) > std::sqrt(ax * ax + ay * ay) * zfactor) break;
+        }
+        if (p == 1) keep = true;
+      }
+      if (keep) kept.push_back(i);
+    }
+    c->s.select(kept);
+  });
+}
+
 int pbd_candidates_create(int n, int max_nparts, const int32_t* meta4, const float* scores, const int32_t* parts7, pbd_candidates** out) {
   return guarded([&] {
     REQUIRE(n >= 0 && max_nparts > 0 && out && (n == 0 || (meta4 && scores && parts7)), "bad argument");
@@ -480,7 +526,7 @@ int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int
   return guarded([&] {
     REQUIRE(defw4 && anchor_xy && out, "null argument");
     REQUIRE(n_maps > 0 && n_maps <= (1 << 20) && h > 0 && w > 0 && h <= 4096 && w <= 4096, "map shape out of range (<= 4096 x 4096, <= 2^20 maps)");
-    REQUIRE(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (streaming dt_pass) or 2 (parallel-in-q dt_lines)");
+    REQUIRE(impl >= 0 && impl <= 3, "impl must be 0 (default), 1 (streaming, eager emission), 2 (parallel-in-q) or 3 (streaming, lagged-scan emission)");
     for (int i = 0; i < n_maps; ++i) {
       REQUIRE(defw4[4 * i] > 0.f && defw4[4 * i + 2] > 0.f, "quadratic weights must be > 0");
       REQUIRE(std::abs(anchor_xy[2 * i]) <= 4096 && std::abs(anchor_xy[2 * i + 1]) <= 4096, "anchor out of range");
@@ -489,7 +535,7 @@ int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int
     cu(cudaGetDevice(&P->device), "cudaGetDevice");
     P->n_maps = n_maps; P->h = h; P->w = w;
     P->impl = impl ? impl : 1;                 // measured on B200: the streaming kernels are the faster generation
-    REQUIRE(P->impl == 1 || std::max(h, w) <= kLinesMaxN, "impl 2 (parallel-in-q) handles lines of at most 1024 samples");
+    REQUIRE(P->impl != 2 || std::max(h, w) <= kLinesMaxN, "impl 2 (parallel-in-q) handles lines of at most 1024 samples");
     const size_t cells = (size_t)n_maps * h * w;
     std::vector<PassMap> maps(2 * (size_t)n_maps);
     P->etab.alloc((size_t)n_maps * (dt_table_len(w) + dt_table_len(h)) * sizeof(double));
@@ -507,7 +553,7 @@ int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int
     P->maps.alloc(maps.size() * sizeof(PassMap));
     P->tmp.alloc(cells * sizeof(float)); P->ixr.alloc(cells * 2); P->iyr.alloc(cells * 2);
     cu(cudaMemcpy(P->maps.p, maps.data(), maps.size() * sizeof(PassMap), cudaMemcpyHostToDevice), "H2D");
-    if (P->impl == 1) {
+    if (P->impl != 2) {
       PassGeom pgs[2];
       memset(pgs, 0, sizeof(pgs));
       pgs[0].n_levels = pgs[1].n_levels = 1;
@@ -540,9 +586,9 @@ int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* 
     REQUIRE(p && d_in && d_out && d_ix && d_iy, "null argument");
     REQUIRE(backptr_mode == 0 || backptr_mode == 1, "backptr_mode must be 0 or 1");
     cudaStream_t s = (cudaStream_t)stream;
-    if (p->impl == 1) {
+    if (p->impl != 2) {
       launch_dt2d_standalone(d_in, p->n_maps, p->h, p->w, p->geom.as<PassGeom>(), p->maps.as<PassMap>(), p->tmp.as<float>(), d_out, d_ix, d_iy,
-                             p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s);
+                             p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s, p->impl == 3);
     } else {
       launch_dt2d_lines(d_in, p->n_maps, p->h, p->w, p->lg[0], p->lg[1], p->geom.as<LineGeom>(), p->maps.as<PassMap>(), p->tmp.as<float>(), d_out,
                         d_ix, d_iy, p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s);
@@ -555,7 +601,7 @@ int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int 
                         float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode) {
   pbd_dt2d_plan* plan = nullptr;
   int impl = 0;
-  if (const char* v = getenv("PBD_DT_IMPL")) impl = !strcmp(v, "stream") ? 1 : (!strcmp(v, "lines") ? 2 : 0);
+  if (const char* v = getenv("PBD_DT_IMPL")) impl = !strcmp(v, "stream") ? 1 : (!strcmp(v, "lines") ? 2 : (!strcmp(v, "scan") ? 3 : 0));
   int rc = pbd_dt2d_plan_create(n_maps, h, w, h_defw4, h_anchor_xy, impl, &plan);
   if (rc != PBD_OK) return rc;
   rc = pbd_dt2d_plan_run(plan, stream, d_in, d_out, d_ix, d_iy, backptr_mode);
@@ -582,6 +628,36 @@ int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, 
     for (size_t i = 0; i < cells; ++i) { ix[i] = hx[i]; iy[i] = hy[i]; }
   });
 }
+
+// ---- ingest: image containers, sensor_msgs/Image encodings, pinned frame buffers (ingest.cpp) ----
+int pbd_image_info(const uint8_t* bytes, size_t n, int32_t* h, int32_t* w, int32_t* channels, int32_t* bits) {
+  return guarded([&] { REQUIRE(bytes, "null argument"); int hh, ww, cc, bb; image_info(bytes, n, &hh, &ww, &cc, &bb); if (h) *h = hh; if (w) *w = ww; if (channels) *channels = cc < 0 ? -cc : cc; if (bits) *bits = bb; });
+}
+int pbd_image_decode_bgr8(const uint8_t* bytes, size_t n, uint8_t* dst, size_t dst_capacity, int32_t* h, int32_t* w) {
+  return guarded([&] { REQUIRE(bytes && dst, "null argument"); int hh, ww; image_decode_bgr8(bytes, n, dst, dst_capacity, &hh, &ww); if (h) *h = hh; if (w) *w = ww; });
+}
+int pbd_image_decode_depth_f32(const uint8_t* bytes, size_t n, float scale, float* dst, size_t dst_capacity, int32_t* h, int32_t* w) {
+  return guarded([&] { REQUIRE(bytes && dst, "null argument"); int hh, ww; image_decode_depth_f32(bytes, n, scale, dst, dst_capacity, &hh, &ww); if (h) *h = hh; if (w) *w = ww; });
+}
+int pbd_imread_bgr8(const char* path, uint8_t* dst, size_t dst_capacity, int32_t* h, int32_t* w) {
+  return guarded([&] {
+    REQUIRE(path && (dst || dst_capacity == 0), "null argument");
+    const std::vector<uint8_t> buf = slurp_bytes(path);
+    int hh, ww;
+    if (dst_capacity == 0) { int cc, bb; image_info(buf.data(), buf.size(), &hh, &ww, &cc, &bb); }     // size query
+    else image_decode_bgr8(buf.data(), buf.size(), dst, dst_capacity, &hh, &ww);
+    if (h) *h = hh;
+    if (w) *w = ww;
+  });
+}
+int pbd_ros_image_to_bgr8(const char* encoding, int h, int w, size_t step, int is_bigendian, const uint8_t* data, uint8_t* dst_bgr8) {
+  return guarded([&] { REQUIRE(encoding && data && dst_bgr8 && h > 0 && w > 0, "bad argument"); ros_image_to_bgr8(encoding, h, w, step, is_bigendian, data, dst_bgr8); });
+}
+int pbd_ros_depth_to_f32(const char* encoding, int h, int w, size_t step, int is_bigendian, const uint8_t* data, float* dst) {
+  return guarded([&] { REQUIRE(encoding && data && dst && h > 0 && w > 0, "bad argument"); ros_depth_to_f32(encoding, h, w, step, is_bigendian, data, dst); });
+}
+int pbd_host_alloc_pinned(size_t bytes, void** out) { return guarded([&] { REQUIRE(out, "null argument"); *out = pinned_alloc(bytes); }); }
+void pbd_host_free_pinned(void* p) { pinned_free(p); }
 
 long long pbd_launch_count(const pbd_detector* d) { return d ? d->e->launches() : 0; }
 int pbd_stage_times_ms(pbd_detector* d, float ms[6]) { return guarded([&] { DeviceGuard dg_(dev_of(d)); REQUIRE(d && ms, "null argument"); d->e->stage_times(ms); }); }

@@ -68,7 +68,10 @@ __device__ __forceinline__ void st_u16(unsigned short* base, unsigned idx, unsig
 #ifndef PBD_DT_MINBLOCKS
 #define PBD_DT_MINBLOCKS 6        // 80 registers: 6 CTAs of 4 warps per SM (7 CTAs at 72 registers measured 9 % slower)
 #endif
-template <int MAXN>
+// SCAN = 0: eager emission (the detector's kernel: fastest on real score maps, where ~95 % of the samples stay on the envelope);
+// SCAN > 0: lagged-scan emission with that lag (env::envelope_scan): one store per position unless a late pop rewinds the cursor --
+// the variant for rough inputs (white-noise maps: 3.4 instead of 24.6 stores per position), standalone transform impl 3.
+template <int MAXN, int SCAN>
 __global__ void __launch_bounds__(kPassWarps * 32, PBD_DT_MINBLOCKS)
 dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int nmaps, const float* __restrict__ inA, size_t strideA,
         const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out, unsigned short* __restrict__ ptr,
@@ -133,12 +136,12 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
     st_f32(dst, off, val); st_u16(dp, off, v);
   };
   const int os0 = M.os;
-#if defined(PBD_DT_SCAN)
-  // A/B switch (tools/build_variant.sh ... -DPBD_DT_SCAN=4): lagged-scan emission (env::envelope_scan<LAG>), one position per lane and
-  // step, the same index in all lanes.  Bit-identical on the host (tests/test_dt_envelope_host.py); not yet measured on a GPU.
-  env::envelope_scan<PBD_DT_SCAN>(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
-                                  [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
-#elif !defined(PBD_DT_WINDOWED_STORES)
+  if (SCAN > 0) {
+    env::envelope_scan<(SCAN > 0 ? SCAN : 1)>(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
+                                              [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
+    return;
+  }
+#if !defined(PBD_DT_WINDOWED_STORES)
   // every emission straight to global memory (the default, see below)
   env::envelope_stream(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
                        [&](int i, float val, int v) { store(i, val, (unsigned short)v); }, [](int) {});
@@ -366,15 +369,59 @@ root_select(const Geometry* __restrict__ g, const RootJob* __restrict__ roots, i
   rooti[((size_t)frame * ncomp + comp) * ct + idx] = (unsigned char)bi;
 }
 
-// Hits of the computed rootv (DynamicProgram::argmin threshold + Math::find, :208-211).
+// Optional epilogue of min(): nonMaximaSuppression(rootv[n][c], sz, maxima) of reference src/nms.cpp:84-129 (the call the reference
+// keeps commented out at src/PartsBasedDetector.cpp:86), one thread per root cell.  The map is cut into (sz+1)^2 blocks; a cell is
+// kept iff it is its block's FIRST maximum in row-major order (cv::minMaxLoc: strict >) and strictly greater than every cell of the
+// (2 sz + 1)^2 window centred on it that lies outside the block's rows x columns; an empty window compares against 0, as
+// cv::minMaxLoc over an empty selection does.
 __global__ void __launch_bounds__(256)
-hits_select(const Geometry* __restrict__ g, int ncomp, const float* __restrict__ rootv, float thresh, Hit* __restrict__ hits,
-            int* __restrict__ nhits, int max_hits) {
+root_nms(const Geometry* __restrict__ g, int ncomp, const float* __restrict__ rootv, int sz, unsigned char* __restrict__ keep) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g->cells_total) return;
+  const int comp = blockIdx.y, frame = blockIdx.z;
+  int l = 0;
+  while (l + 1 < g->n_levels && idx >= g->lv[l + 1].cell_off) ++l;
+  const int M = g->lv[l].oh, N = g->lv[l].ow;
+  const int local = idx - g->lv[l].cell_off, y = local / N, x = local - y * N;
+  const float* map = rootv + ((size_t)frame * ncomp + comp) * g->cells_total + g->lv[l].cell_off;
+  const float v = map[local];
+  const int m = y / (sz + 1) * (sz + 1), n = x / (sz + 1) * (sz + 1);                 // block origin
+  const int i1 = min(m + sz + 1, M), j1 = min(n + sz + 1, N);
+  bool cand = true;
+  for (int yy = m; yy < i1 && cand; ++yy)
+    for (int xx = n; xx < j1; ++xx) {
+      const float u = map[yy * N + xx];
+      const bool earlier = yy < y || (yy == y && xx < x);
+      if (earlier ? !(v > u) : u > v) { cand = false; break; }                           // first maximum of the block
+    }
+  unsigned char out = 0;
+  if (cand) {
+    const int in0 = max(y - sz, 0), in1 = min(y + sz + 1, M), jn0 = max(x - sz, 0), jn1 = min(x + sz + 1, N);
+    // the block's rows / columns as the reference clips them against the window (:111-113)
+    const int by0 = m, by1 = in0 + min(m - in0 + sz + 1, in1 - in0), bx0 = n, bx1 = jn0 + min(n - jn0 + sz + 1, jn1 - jn0);
+    float vn = 0.f;
+    bool any = false;
+    for (int yy = in0; yy < in1; ++yy)
+      for (int xx = jn0; xx < jn1; ++xx) {
+        if (yy >= by0 && yy < by1 && xx >= bx0 && xx < bx1) continue;
+        const float u = map[yy * N + xx];
+        if (!any || u > vn) { vn = u; any = true; }
+      }
+    out = v > vn ? 255 : 0;
+  }
+  keep[((size_t)frame * ncomp + comp) * g->cells_total + idx] = out;
+}
+
+// Hits of the computed rootv (DynamicProgram::argmin threshold + Math::find, :208-211); keep (optional): root-map NMS mask.
+__global__ void __launch_bounds__(256)
+hits_select(const Geometry* __restrict__ g, int ncomp, const float* __restrict__ rootv, const unsigned char* __restrict__ keep, float thresh,
+            Hit* __restrict__ hits, int* __restrict__ nhits, int max_hits) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g->cells_total) return;
   const int comp = blockIdx.y, frame = blockIdx.z;
   const float v = rootv[((size_t)frame * ncomp + comp) * g->cells_total + idx];
   if (!(v > thresh)) return;
+  if (keep && !keep[((size_t)frame * ncomp + comp) * g->cells_total + idx]) return;
   int l = 0;
   while (l + 1 < g->n_levels && idx >= g->lv[l + 1].cell_off) ++l;
   const int local = idx - g->lv[l].cell_off;
@@ -412,13 +459,15 @@ dt2d_compose(int h, int w, const unsigned short* __restrict__ ixraw, const unsig
 
 }  // namespace
 
-template <typename... A>
-static void launch_pass(int maxn, dim3 grid, cudaStream_t s, A... args) {
-  if (maxn <= 160) dt_pass<160><<<grid, kPassWarps * 32, 0, s>>>(args...);
-  else if (maxn <= 512) dt_pass<512><<<grid, kPassWarps * 32, 0, s>>>(args...);
-  else if (maxn <= 1024) dt_pass<1024><<<grid, kPassWarps * 32, 0, s>>>(args...);
-  else dt_pass<4096><<<grid, kPassWarps * 32, 0, s>>>(args...);
+template <int SCAN, typename... A>
+static void launch_pass_v(int maxn, dim3 grid, cudaStream_t s, A... args) {
+  if (maxn <= 160) dt_pass<160, SCAN><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else if (maxn <= 512) dt_pass<512, SCAN><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else if (maxn <= 1024) dt_pass<1024, SCAN><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else dt_pass<4096, SCAN><<<grid, kPassWarps * 32, 0, s>>>(args...);
 }
+template <typename... A>
+static void launch_pass(int maxn, dim3 grid, cudaStream_t s, A... args) { launch_pass_v<0>(maxn, grid, s, args...); }
 
 // number of warps a pass needs for `nmaps` maps
 static int pass_warps(const PassGeom& pg, int nmaps) {
@@ -465,16 +514,20 @@ static void launch_lines(const LineGeom& lg, dim3 grid, cudaStream_t s, A... arg
 int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
-                   cudaStream_t s, void (*mark)(void*, int), void* mark_ctx) {
+                   cudaStream_t s, void (*mark)(void*, int), void* mark_ctx, int scan) {
   if (nmaps <= 0 || njobs <= 0 || g.cells_total <= 0) return 0;
   const size_t ct = (size_t)g.cells_total;
   dim3 gr((pass_warps(pg_rows, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
-  launch_pass(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
-              ct * tmp_maps, b.ixdt, ct * ncm);
+  if (scan) launch_pass_v<4>(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
+                             ct * tmp_maps, b.ixdt, ct * ncm);
+  else launch_pass(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
+                   ct * tmp_maps, b.ixdt, ct * ncm);
   if (mark) mark(mark_ctx, 2);
   dim3 gc((pass_warps(pg_cols, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
-  launch_pass(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
-              ct * tmp_maps, b.iyraw, ct * ncm);
+  if (scan) launch_pass_v<4>(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
+                             ct * tmp_maps, b.iyraw, ct * ncm);
+  else launch_pass(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
+                   ct * tmp_maps, b.iyraw, ct * ncm);
   if (mark) mark(mark_ctx, 3);
   if (g.cells_total % 4 == 0) {
     dim3 gm((g.cells_total / 4 + 255) / 256, njobs, g.n_frames);
@@ -502,25 +555,33 @@ int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, 
 }
 
 int launch_hits(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int ncomp, float thresh, Hit* d_hits, int* d_nhits,
-                int max_hits, cudaStream_t s) {
+                int max_hits, cudaStream_t s, int root_nms_sz, unsigned char* d_keep) {
   if (g.cells_total <= 0) return 0;
   dim3 grid((g.cells_total + 255) / 256, ncomp, g.n_frames);
-  hits_select<<<grid, 256, 0, s>>>(d_g, ncomp, b.rootv, thresh, d_hits, d_nhits, max_hits);
-  return 1;
+  int n = 1;
+  if (root_nms_sz > 0 && d_keep) { root_nms<<<grid, 256, 0, s>>>(d_g, ncomp, b.rootv, root_nms_sz, d_keep); ++n; }
+  hits_select<<<grid, 256, 0, s>>>(d_g, ncomp, b.rootv, root_nms_sz > 0 ? d_keep : nullptr, thresh, d_hits, d_nhits, max_hits);
+  return n;
 }
 
 int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const PassGeom* d_pg2 /* [rows, cols] */, const PassMap* d_maps2,
                            float* d_tmp, float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
-                           cudaStream_t s) {
+                           cudaStream_t s, int scan) {
   if (n_maps <= 0 || h <= 0 || w <= 0) return 0;
   // maps are launched in chunks so that the warp index stays small; every map is h*w cells
   PassGeom pr{}, pc{};
   pr.n_levels = pc.n_levels = 1;
   pr.nlines[0] = h; pr.N[0] = w; pc.nlines[0] = w; pc.N[0] = h;
   dim3 gr((pass_warps(pr, n_maps) + kPassWarps - 1) / kPassWarps, 1), gc((pass_warps(pc, n_maps) + kPassWarps - 1) / kPassWarps, 1);
-  launch_pass(w, gr, s, d_pg2, d_maps2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0);
-  launch_pass(h, gc, s, d_pg2 + 1, d_maps2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out, (size_t)0,
-              d_iyraw, (size_t)0);
+  if (scan) {
+    launch_pass_v<4>(w, gr, s, d_pg2, d_maps2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0);
+    launch_pass_v<4>(h, gc, s, d_pg2 + 1, d_maps2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out, (size_t)0,
+                     d_iyraw, (size_t)0);
+  } else {
+    launch_pass(w, gr, s, d_pg2, d_maps2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0);
+    launch_pass(h, gc, s, d_pg2 + 1, d_maps2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out, (size_t)0,
+                d_iyraw, (size_t)0);
+  }
   for (int m0 = 0; m0 < n_maps; m0 += 65535) {                     // gridDim.z limit
     const int nm = std::min(65535, n_maps - m0);
     const size_t o = (size_t)m0 * h * w;

@@ -105,7 +105,7 @@ void Engine::release() {
   void* ptrs[] = {d_wtc_, d_wtc16_, d_f16_, d_fhi_, d_flo_, d_tc_levels_, d_tc_tiles_, d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
-                  d_scratch_i_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
+                  d_scratch_i_, d_rootkeep_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
                   slots_[1].d_hits, slots_[1].d_nhits, slots_[1].d_xym, d_ksize_, nms_.boxes, nms_.keys, nms_.skeys, nms_.sidx, nms_.kept_idx,
                   nms_.frame_count, nms_.fill, nms_.kept_count, nms_.out_off, nms_.seg_off, nms_.scratch, slots_[0].d_hits_out,
                   slots_[0].d_xym_out, slots_[0].d_total, slots_[1].d_hits_out, slots_[1].d_xym_out, slots_[1].d_total};
@@ -113,6 +113,7 @@ void Engine::release() {
   for (ResultSlot& S : slots_) if (S.done) cudaEventDestroy(S.done);
   for (auto& e : frames_free_ev_) if (e) cudaEventDestroy(e);
   if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+  if (capture_stream_) { cudaStreamDestroy(capture_stream_); capture_stream_ = nullptr; }
   if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
   for (cudaStream_t st : dp_aux_) cudaStreamDestroy(st);
   for (cudaEvent_t ev : dp_join_) cudaEventDestroy(ev);
@@ -730,7 +731,7 @@ void Engine::run_dp_min() {
       const int n = launch_dt_wave(gs, d_g_, bs, pg_rows_, d_pg_, pg_cols_, d_pg_ + 1, d_maps_rows_ + wave_map_first_[wv],
                                    d_maps_cols_ + wave_map_first_[wv], wave_map_count_[wv], max_ow_, max_oh_, d_jobs_ + wave_first_[wv],
                                    wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, sp == 0 ? stream_ : dp_aux_[sp - 1],
-                                   timing >= 2 ? +mark : nullptr, this);
+                                   timing >= 2 ? +mark : nullptr, this, dt_scan);
       launches_ += n;
     }
   }
@@ -751,7 +752,8 @@ void Engine::run_argmin() {
   ResultSlot& S = slots_[cur_slot_];
   ensure_slot(S);
   check_cuda(cudaMemsetAsync(S.d_nhits, 0, sizeof(int), stream_), "memset nhits");
-  launches_ += launch_hits(g_, d_g_, b_, model_.ncomponents(), (float)thresh, S.d_hits, S.d_nhits, S.max_candidates, stream_);
+  if (root_nms > 0) ensure(d_rootkeep_, cap_rootkeep_, (size_t)g_.n_frames * model_.ncomponents() * g_.cells_total);
+  launches_ += launch_hits(g_, d_g_, b_, model_.ncomponents(), (float)thresh, S.d_hits, S.d_nhits, S.max_candidates, stream_, root_nms, d_rootkeep_);
   BacktrackTables t{d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_};
   launches_ += launch_backtrack(g_, d_g_, b_, t, model_.ncomponents(), ncm_, npm_, S.d_hits, S.d_nhits, S.max_candidates, backptr, max_parts_,
                                 S.d_xym, stream_);
@@ -789,7 +791,7 @@ void Engine::enqueue_device(const uint8_t* d_frames, int n, int h, int w, int c)
   if (!use_graph || timing) { run_stages(); return; }
   GraphKey k;
   k.frames = d_frames; k.geom_serial = geom_serial_; k.n = n; k.resp_mode = resp_mode; k.backptr = backptr; k.max_candidates = max_candidates;
-  k.dp_streams = dp_streams; k.thresh = thresh; k.nms_overlap = nms_overlap;
+  k.dp_streams = dp_streams; k.thresh = thresh; k.nms_overlap = nms_overlap; k.root_nms = root_nms; k.dt_scan = dt_scan;
   if (graph_exec_ && k == graph_key_) {
     check_cuda(cudaGraphLaunch(graph_exec_, stream_), "cudaGraphLaunch");
     launches_ += graph_launches_;
@@ -800,16 +802,23 @@ void Engine::enqueue_device(const uint8_t* d_frames, int n, int h, int w, int c)
   if (!(k == warm_key_)) { warm_key_ = k; run_stages(); return; }          // first sight of this configuration: eager, allocates
   if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
   const long long l0 = launches_;
+  // Capture happens on a stream of our own (the caller's may be the legacy default stream, which cannot be captured): every stage
+  // launches on stream_, so it is swapped for the duration of the capture; the graph is then launched into the caller's stream.
+  if (!capture_stream_) check_cuda(cudaStreamCreateWithFlags(&capture_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+  cudaStream_t user = stream_;
   cudaGraph_t g = nullptr;
-  check_cuda(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+  check_cuda(cudaStreamBeginCapture(capture_stream_, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+  stream_ = capture_stream_;
   try {
     run_stages();
   } catch (...) {
-    cudaStreamEndCapture(stream_, &g);
+    stream_ = user;
+    cudaStreamEndCapture(capture_stream_, &g);
     if (g) cudaGraphDestroy(g);
     throw;
   }
-  check_cuda(cudaStreamEndCapture(stream_, &g), "cudaStreamEndCapture");
+  stream_ = user;
+  check_cuda(cudaStreamEndCapture(capture_stream_, &g), "cudaStreamEndCapture");
   const cudaError_t ie = cudaGraphInstantiate(&graph_exec_, g, 0);
   cudaGraphDestroy(g);
   check_cuda(ie, "cudaGraphInstantiate");

@@ -66,6 +66,11 @@ class Engine {
   // >= 0: detect() returns, per frame, the candidates sorted by score and greedily suppressed on the device (Candidate::sort +
   // Candidate::nonMaximaSuppression with this overlap); < 0 (default): the raw candidate list, as the reference's detect()
   double nms_overlap = -1.0;
+  // > 0: root-map non-maxima suppression with this window before the backtrack (reference src/nms.cpp, the call commented out at
+  // src/PartsBasedDetector.cpp:86); 0 (default): every root cell above the threshold is a candidate, as the reference's detect()
+  int root_nms = 0;
+  // 1: the distance-transform passes emit through the lagged scan (one store per position) instead of eagerly (dt.cu)
+  int dt_scan = 0;
   static constexpr int kMinFramesPerDpGroup = 4;
 
   // ---- batch set-up ----
@@ -207,6 +212,7 @@ class Engine {
   cudaEvent_t frames_free_ev_[2] = {};         // recorded when the pyramid stage has consumed frame buffer 0 / 1
   int frames_buf_ = 0;
   int* d_scratch_i_ = nullptr; size_t cap_scratch_i_ = 0;
+  unsigned char* d_rootkeep_ = nullptr; size_t cap_rootkeep_ = 0;
   std::vector<Hit> h_hits_;                    // host staging reused across batches
   std::vector<int> h_xym_;
   cudaStream_t copy_stream_ = nullptr;
@@ -223,15 +229,16 @@ class Engine {
   struct GraphKey {
     const uint8_t* frames = nullptr;
     long long geom_serial = -1;
-    int n = 0, resp_mode = -1, backptr = -1, max_candidates = 0, dp_streams = 0;
+    int n = 0, resp_mode = -1, backptr = -1, max_candidates = 0, dp_streams = 0, root_nms = 0, dt_scan = 0;
     double thresh = 0, nms_overlap = 0;
     bool operator==(const GraphKey& o) const {
       return frames == o.frames && geom_serial == o.geom_serial && n == o.n && resp_mode == o.resp_mode && backptr == o.backptr &&
-             max_candidates == o.max_candidates && dp_streams == o.dp_streams && thresh == o.thresh && nms_overlap == o.nms_overlap;
+             max_candidates == o.max_candidates && dp_streams == o.dp_streams && root_nms == o.root_nms && dt_scan == o.dt_scan && thresh == o.thresh && nms_overlap == o.nms_overlap;
     }
   };
   GraphKey graph_key_{}, warm_key_{};
   cudaGraphExec_t graph_exec_ = nullptr;
+  cudaStream_t capture_stream_ = nullptr;
   long long graph_launches_ = 0;
   int graph_slot_ = 0;
   void run_stages();

@@ -175,12 +175,14 @@ long long line_tasks(const LineGeom& lg, int units);     // warps (rows pass, un
 int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
-                   cudaStream_t s, void (*mark)(void*, int) = nullptr, void* mark_ctx = nullptr);   // mark(ctx, kernel id) after each kernel
+                   cudaStream_t s, void (*mark)(void*, int) = nullptr, void* mark_ctx = nullptr,   // mark(ctx, kernel id) after each kernel
+                   int scan = 0);                                                              // 1: lagged-scan emission in dt_pass
 int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const RootJob* d_roots, int ncomp, int nfilters, int nwork,
                 cudaStream_t s);
 
+// root_nms_sz > 0: only strict local maxima of the root map (window sz, reference src/nms.cpp) become hits; d_keep = [n][ncomp][cells] scratch
 int launch_hits(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int ncomp, float thresh, Hit* d_hits, int* d_nhits,
-                int max_hits, cudaStream_t s);
+                int max_hits, cudaStream_t s, int root_nms_sz = 0, unsigned char* d_keep = nullptr);
 
 struct BacktrackTables {       // per component, flattened with strides kMaxParts / kMaxMix
   const int* parent;           // [ncomp][kMaxParts]
@@ -198,7 +200,7 @@ int launch_expand_backptr(const Geometry& g, const DeviceBuffers& b, int frame, 
 // d_maps2 = n_maps row-pass maps followed by n_maps column-pass maps
 int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const PassGeom* d_pg2, const PassMap* d_maps2, float* d_tmp,
                            float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
-                           cudaStream_t s);
+                           cudaStream_t s, int scan = 0);   // scan: lagged-scan emission (rough inputs) instead of eager emission
 // the same transform through the parallel-in-q kernels (all maps [y][x]); d_lg2 = {rows, cols}
 int launch_dt2d_lines(const float* d_in, int n_maps, int h, int w, const LineGeom& lg_rows, const LineGeom& lg_cols, const LineGeom* d_lg2,
                       const PassMap* d_maps2, float* d_tmp, float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw,

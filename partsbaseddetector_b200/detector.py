@@ -217,6 +217,34 @@ class Candidate:
         return candidates
 
 
+def filterCandidatesByDepth(model, candidates, depth, zfactor=0.03):
+    """SearchSpacePruning<T>::filterCandidatesByDepth (src/SearchSpacePruning.cpp:73-95): `candidates` (a CandidateList or a list of
+    Candidate, all of ONE frame) filtered by the frame's depth image (h x w float32; 0 = no reading).  Returns a CandidateList."""
+    depth = np.ascontiguousarray(depth, np.float32)
+    if isinstance(candidates, CandidateList):
+        meta, scores, parts = candidates.meta, candidates.scores, candidates.parts
+    else:
+        n = len(candidates)
+        mp = max([len(c.x) for c in candidates] + [1])
+        meta, scores, parts = np.zeros((n, 4), np.int32), np.zeros(n, np.float32), np.zeros((n, mp, 7), np.int32)
+        for i, c in enumerate(candidates):
+            k = len(c.x)
+            meta[i] = (c.frame, c.level, c.component_, k)
+            scores[i] = c.score()
+            parts[i, :k, 0], parts[i, :k, 1], parts[i, :k, 2] = c.x, c.y, c.m
+            parts[i, :k, 3:7] = c.parts_
+    hnd = C.c_void_p()
+    L = _lib.lib()
+    _lib.check(L.pbd_candidates_create(len(scores), parts.shape[1], np.ascontiguousarray(meta).reshape(-1), np.ascontiguousarray(scores),
+                                       np.ascontiguousarray(parts).reshape(-1), C.byref(hnd)))
+    try:
+        _lib.check(L.pbd_candidates_filter_by_depth(hnd, model.handle, depth.reshape(-1), depth.shape[0], depth.shape[1], 0, float(zfactor)))
+    except Exception:
+        L.pbd_candidates_free(hnd)
+        raise
+    return _unpack_candidates(hnd)
+
+
 class CandidateList:
     """Read-only sequence of Candidate backed by the arrays of one bulk export; Candidate objects are built on access.
     `meta` = (n,4) frame/level/component/nparts, `scores` = (n,), `parts` = (n, max_parts, 7) x,y,mixture,rect."""

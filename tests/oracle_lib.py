@@ -48,6 +48,9 @@ def lib():
     L.orc_dt2d_f64.argtypes = [_f64p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f64p, _i32p, _i32p]
     L.orc_nms.argtypes = [_i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _i32p]
     L.orc_nms.restype = C.c_int
+    L.orc_rootmap_nms.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, _u8p]
+    L.orc_filter_by_depth.argtypes = [_i32p, C.c_int, C.c_int, _i32p, _i32p, _f32p, C.c_int, C.c_int, C.c_float, _i32p]
+    L.orc_filter_by_depth.restype = C.c_int
     L.orc_create.argtypes = [_i32p, C.c_float, _i32p, _f64p, _f32p, _i32p, _f32p, _i32p, C.c_int]
     L.orc_create.restype = C.c_void_p
     L.orc_destroy.argtypes = [C.c_void_p]

@@ -46,6 +46,9 @@ def lib():
         L.ref_dp_candidate_nparts.argtypes = [C.c_void_p, C.c_int]
         L.ref_dp_get_candidate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), _i32p, _f32p]
         L.ref_dp_sort_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, _i32p, _f32p]
+        L.ref_rootmap_nms.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, _u8p]
+        L.ref_dp_filter_by_depth.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float, _i32p]
+        L.ref_dp_filter_by_depth.restype = C.c_int
         _lib = L
     return _lib
 
@@ -117,6 +120,22 @@ class RefDP:
             self.L.ref_dp_get_candidate(self.h, i, C.byref(comp), rects, conf)
             out.append((comp.value, rects.reshape(n, 4), conf))
         return out
+
+    def filter_by_depth(self, depth, zfactor):
+        """SearchSpacePruning<float>::filterCandidatesByDepth on the last run's candidates: 0/1 per candidate.  Math::median prints every
+        box it looks at to std::cerr (include/Math.hpp:70), so fd 2 is parked on /dev/null for the call."""
+        import os
+        depth = np.ascontiguousarray(depth, np.float32)
+        keep = np.zeros(max(self.ncand, 1), np.int32)
+        saved, null = os.dup(2), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null, 2)
+        try:
+            self.L.ref_dp_filter_by_depth(self.h, depth.reshape(-1), depth.shape[0], depth.shape[1], float(zfactor), keep)
+        finally:
+            os.dup2(saved, 2)
+            os.close(saved)
+            os.close(null)
+        return keep[:self.ncand]
 
     def sort_nms(self, im_h, im_w, overlap):
         n = max(self.L.ref_dp_candidate_nparts(self.h, 0), 1) if self.ncand else 1

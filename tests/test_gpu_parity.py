@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_lib
-from conftest import GOLDEN, load_flat
+from conftest import GOLDEN, golden_model_path, load_flat
 from partsbaseddetector_b200 import Model, PartsBasedDetector, PbdError, dt2d
 from partsbaseddetector_b200.synth import synth_frame, synth_frames, synth_score_map
 
@@ -140,11 +140,12 @@ def test_dt2d_bitexact(h, w, mode):
         assert np.array_equal(iy[i], y), i
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("h,w", [(1, 1), (3, 2), (33, 65), (118, 158), (268, 478), (60, 700)])
 def test_dt2d_both_kernel_generations_bitexact(h, w, impl):
     """The streaming envelope (impl 1: one lane per line) and the parallel-in-q kernels (impl 2: a warp per batch of lines in shared
-    memory; register window 8 / 16 / none by line length) against the oracle, through the pre-allocated plan API."""
+    memory; straight-line variants up to 256 samples, loops beyond) and the streaming envelope with lagged-scan emission (impl 3) against
+    the oracle, through the pre-allocated plan API."""
     import torch
     from partsbaseddetector_b200 import Dt2dPlan
     rng = np.random.default_rng(h * 977 + w + impl)
@@ -369,6 +370,70 @@ def test_determinism_and_stage_api_equivalence():
     assert [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m)) for k in a] == [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m)) for k in c]
 
 
+def test_cuda_graph_replay_equals_eager_launches():
+    """option graph=1: the second enqueue with the same frames pointer / geometry / options captures the launch sequence (frame groups
+    of the DP on forked streams included), later ones replay it; results equal the eager path, a changed option re-captures."""
+    import torch
+    frames = np.stack([synth_frame(300 + i, 120, 160) for i in range(8)])
+    dev = torch.from_numpy(frames).cuda()
+    d = PartsBasedDetector()
+    d.distributeModel(Model.load_bin(golden_model_path("Person_26parts")))
+    d.set_option("thresh", -1.3)
+    ref = d.detect(frames)
+    assert len(ref) > 20
+    d.set_option("graph", 1)
+    for it in range(4):                                   # eager (warm-up), capture + launch, replay, replay
+        d.enqueue_device(dev.data_ptr(), 8, 120, 160, 3)
+        got = d.collect()
+        assert len(got) == len(ref), it
+        for a, b in zip(got, ref):
+            assert a.frame == b.frame and a.level == b.level and np.array_equal(a.x, b.x) and np.array_equal(a.y, b.y) and np.array_equal(a.m, b.m)
+            assert a.score() == b.score() and np.array_equal(a.parts(), b.parts())
+    n_before = d.launch_count()
+    d.enqueue_device(dev.data_ptr(), 8, 120, 160, 3)
+    assert d.launch_count() > n_before                    # replayed kernels are counted
+    d.set_option("thresh", -1.2)                          # an option the captured sequence depends on: eager again, then a new graph
+    ref2 = d.detect(frames)
+    for it in range(3):
+        d.enqueue_device(dev.data_ptr(), 8, 120, 160, 3)
+        got = d.collect()
+        assert len(got) == len(ref2) and all(a.score() == b.score() and np.array_equal(a.parts(), b.parts()) for a, b in zip(got, ref2))
+    other = torch.from_numpy(frames[::-1].copy()).cuda()  # another frames pointer: must not replay the old graph
+    d.enqueue_device(other.data_ptr(), 8, 120, 160, 3)
+    got = d.collect()
+    assert [c.frame for c in got] != [] and sorted(float(c.score()) for c in got) == sorted(float(c.score()) for c in ref2)
+    d.close()
+
+
+@pytest.mark.parametrize("sz", [1, 3])
+def test_root_map_nms_option_equals_oracle(sz):
+    """option root_nms = sz: only the strict local maxima of every root map (nonMaximaSuppression of reference src/nms.cpp:84-129, window
+    sz) above the threshold are backtracked; equals the oracle's restatement of that function applied to the oracle's root maps."""
+    d, O = detector("Person_26parts"), oracle("Person_26parts")
+    img = synth_frame(77, 200, 280)
+    O.run(img, 1, 3)
+    thr = lowered_threshold(O, 400)
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    L = oracle_lib.lib()
+    keep = {}
+    for l in range(O.nlevels()):
+        rv = O.rootv(l)
+        k = np.empty(rv.shape, np.uint8)
+        L.orc_rootmap_nms(np.ascontiguousarray(rv).reshape(-1), rv.shape[0], rv.shape[1], sz, None, k.reshape(-1))
+        keep[l] = k
+    want = [o for o in O.candidates() if keep[o["level"]][o["y"][0], o["x"][0]]]
+    d.set_option("thresh", thr)
+    d.set_option("root_nms", sz)
+    got = d.detect(img)
+    assert 0 < len(want) < len(O.candidates()) and len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.level == b["level"] and np.array_equal(a.x, b["x"]) and np.array_equal(a.y, b["y"]) and np.array_equal(a.m, b["m"])
+        assert a.score() == b["score"] and np.array_equal(a.parts(), b["rects"])
+    d.set_option("root_nms", 0)
+    assert len(d.detect(img)) == len(O.candidates())
+
+
 def test_max_levels_and_candidate_sort():
     d, O = detector("Person_26parts"), oracle("Person_26parts")
     img = synth_frame(9, 240, 320)
@@ -426,6 +491,47 @@ def test_cpp_adapter_demo_matches_python(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------ BASELINE.json full sizes
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_stage_plugins_match_oracle(tmp_path, precision):
+    """CudaHOGFeatures : IFeatures and CudaConvolutionEngine : IConvolutionEngine (include/pbd_b200_plugins.hpp) driven through the
+    reference's signatures by examples/plugin_demo.cpp: pyramid() feature Mats and pdf() response Mats of every level equal the
+    oracle's bit for bit (T = double: the fp32 results widened, as documented)."""
+    import subprocess
+    from conftest import ROOT
+    libdir = os.path.join(ROOT, "partsbaseddetector_b200")
+    exe = str(tmp_path / "plugin_demo")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "ref_shim"),
+                           os.path.join(ROOT, "examples", "plugin_demo.cpp"), "-L" + libdir, "-lpbd_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    img = synth_frame(61, 150, 200)
+    (tmp_path / "f.raw").write_bytes(img.tobytes())
+    out = tmp_path / "o.bin"
+    r = subprocess.run([exe, golden_model_path("Person_26parts"), str(tmp_path / "f.raw"), "150", "200", "3", str(out)] + (["f64"] if precision == "f64" else []),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    O = oracle("Person_26parts")
+    O.run(img, 1, 2)
+    buf = out.read_bytes()
+    n, nf, es = np.frombuffer(buf, np.int32, 3, 0)
+    dt = np.float64 if es == 8 else np.float32
+    assert n == O.nlevels() and nf == 138 and es == (8 if precision == "f64" else 4)
+    off = 12
+    for l in range(n):
+        oh, owf = np.frombuffer(buf, np.int32, 2, off)
+        scale = np.frombuffer(buf, np.float32, 1, off + 8)[0]
+        off += 12
+        li = O.level_info(l)
+        assert oh == li["oh"] and owf == li["ow"] * 32 and scale == li["scale"]
+        feat = np.frombuffer(buf, dt, oh * owf, off).reshape(oh, owf // 32, 32)
+        off += oh * owf * es
+        assert np.array_equal(feat, O.features(l).astype(dt)), l
+        for f in range(nf):
+            resp = np.frombuffer(buf, dt, oh * owf // 32, off).reshape(oh, owf // 32)
+            off += oh * (owf // 32) * es
+            assert np.array_equal(resp, O.response(l, f).astype(dt)), (l, f)
+    assert off == len(buf)
+
+
 def test_config4_1080p_ten_levels_bitexact():
     """config 4: person model, 1920x1080, first 10 pyramid levels (340 400 cells)."""
     name = "Person_26parts"

@@ -86,6 +86,26 @@ def test_cpp_adapter_compiles_and_fails_loudly_without_gpu(tmp_path):
         assert r.returncode == 251 and "no CUDA device" in r.stdout          # the CUDA path is the only implementation
 
 
+def test_stage_plugins_compile_against_the_reference_interfaces(tmp_path):
+    """include/pbd_b200_plugins.hpp: CudaHOGFeatures : IFeatures and CudaConvolutionEngine : IConvolutionEngine compile (`override`
+    on every virtual) against the interface mirror AND, where /root/reference exists, against the reference's own
+    include/IFeatures.hpp / include/IConvolutionEngine.hpp; without a GPU the plug-ins fail loudly."""
+    libdir = os.path.join(ROOT, "partsbaseddetector_b200")
+    base = ["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "ref_shim"),
+            os.path.join(ROOT, "examples", "plugin_demo.cpp"), "-L" + libdir, "-lpbd_b200", "-Wl,-rpath," + libdir]
+    exe = str(tmp_path / "plugin_demo")
+    subprocess.check_call(base + ["-Wall", "-Werror", "-o", exe])
+    if os.path.isdir("/root/reference/include"):
+        subprocess.check_call(base + ["-w", "-I/root/reference/include", "-o", str(tmp_path / "plugin_demo_ref")])
+    import torch
+    if not torch.cuda.is_available():
+        raw = tmp_path / "f.raw"
+        raw.write_bytes(synth_frame(3, 60, 80).tobytes())
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "Person_26parts.pbdm"), str(raw), "60", "80", "3", str(tmp_path / "o.bin")],
+                           capture_output=True, text=True)
+        assert r.returncode == 251 and "no CUDA device" in r.stdout
+
+
 def test_bench_reference_arm_runs_on_cpu():
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                                   text=True, timeout=600)
@@ -163,6 +183,42 @@ def test_batch_sort_then_nms_keeps_frames_independent():
             want += [int(c.x[0]) for c in Candidate.nonMaximaSuppression((h, w), CandidateList(meta[sel], scores[sel], parts[sel]), overlap)]
         assert got == sorted(want) and 0 < len(got) < n
         assert [float(c.score()) for c in batch] == sorted((float(c.score()) for c in batch), reverse=True)   # list order survives
+
+
+def test_depth_pruning_matches_oracle_restatement():
+    """pbd_candidates_filter_by_depth (SearchSpacePruning::filterCandidatesByDepth, src/SearchSpacePruning.cpp:73-95) vs the oracle's
+    restatement -- itself pinned to the reference's compiled source in test_oracle_ref.py -- on random part boxes of the person tree,
+    boxes crossing the image border included (both clip)."""
+    import oracle_lib
+    from conftest import golden_model_path, load_flat
+    from partsbaseddetector_b200 import Model, filterCandidatesByDepth
+    from partsbaseddetector_b200.detector import CandidateList
+    fm = load_flat("Person_26parts")
+    model = Model.load_bin(golden_model_path("Person_26parts"))
+    comp = fm.comps[0]
+    parent = np.array([p.parentid for p in comp], np.int32)
+    anchor0 = np.array([fm.anchors[p.defid[0]] if p.defid else (0, 0) for p in comp], np.int32).reshape(-1)
+    rng = np.random.default_rng(21)
+    h, w, n, nparts = 120, 160, 150, len(comp)
+    yy, xx = np.mgrid[0:h, 0:w]
+    depth = (2.0 + 0.002 * xx + 0.5 * (yy > 70) + 0.003 * rng.standard_normal((h, w))).astype(np.float32)
+    depth[rng.random((h, w)) < 0.2] = 0.0
+    rects = np.zeros((n, nparts, 4), np.int32)
+    cx, cy = rng.integers(-10, w, n), rng.integers(-10, h, n)
+    for p in range(nparts):
+        rects[:, p, 0] = cx + rng.integers(-12, 12, n); rects[:, p, 1] = cy + rng.integers(-12, 12, n)
+        rects[:, p, 2] = rng.integers(4, 24, n); rects[:, p, 3] = rng.integers(4, 24, n)
+    meta = np.zeros((n, 4), np.int32); meta[:, 3] = nparts
+    parts = np.zeros((n, nparts, 7), np.int32); parts[:, :, 3:7] = rects; parts[:, :, 0] = np.arange(n)[:, None]
+    scores = rng.standard_normal(n).astype(np.float32)
+    seen = set()
+    for zf in (0.002, 0.03, 0.5):
+        keep = np.zeros(n, np.int32)
+        k = oracle_lib.lib().orc_filter_by_depth(np.ascontiguousarray(rects).reshape(-1), n, nparts, parent, anchor0, depth.reshape(-1), h, w, zf, keep)
+        out = filterCandidatesByDepth(model, CandidateList(meta, scores, parts), depth, zf)
+        assert [int(c.x[0]) for c in out] == np.nonzero(keep)[0].tolist() and len(out) == k
+        seen.add(k)
+    assert len(seen) > 1 and max(seen) > 0                       # the factor matters
 
 
 def test_pyramid_geometry_matches_oracle_over_many_sizes():

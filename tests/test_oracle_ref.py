@@ -156,3 +156,62 @@ def test_candidate_sort_and_nms_equal_reference_source():
         assert k == len(rects) > 0
         for j in range(k):
             assert np.array_equal(oc[keep[j]]["rects"], rects[j]) and np.float32(oc[keep[j]]["score"]) == scores[j]
+
+
+@pytest.mark.parametrize("h,w,sz", [(1, 1, 1), (7, 5, 1), (24, 31, 2), (58, 78, 3), (40, 40, 5), (13, 90, 9)])
+def test_rootmap_nms_equals_reference_source(h, w, sz):
+    """nonMaximaSuppression of src/nms.cpp (unmasked, and masked by a threshold that leaves every block an eligible element)."""
+    rng = np.random.default_rng(h * 17 + w + sz)
+    L, R = oracle_lib.lib(), ref_lib.lib()
+    for k in range(4):
+        m = synth_score_map(40 + k, h, w)
+        if k == 1:
+            m = np.round(m * 2) / 2                              # plateaus: ties are not maxima (strict >)
+        if k == 2:
+            m[:] = 0.5                                           # constant image: no local maxima
+        for mask in (None, (m > np.float32(-10.0)).astype(np.uint8) * 255):
+            o, r = np.empty((h, w), np.uint8), np.empty((h, w), np.uint8)
+            mp = None if mask is None else mask.ctypes.data
+            L.orc_rootmap_nms(m.reshape(-1), h, w, sz, mp, o.reshape(-1))
+            R.ref_rootmap_nms(m.reshape(-1), h, w, sz, mp, r.reshape(-1))
+            assert np.array_equal(o, r), (k, mask is None)
+            if k == 2 and h % (sz + 1) == 0 and w % (sz + 1) == 0 and h > sz + 1 and w > sz + 1:
+                assert not o.any()                               # full blocks only (a truncated border block can have an empty window: 0.5 > 0)
+            if k == 0 and h * w > 100:
+                assert 0 < np.count_nonzero(o) < h * w / ((sz + 1) ** 2) + 1
+
+
+def test_depth_pruning_equals_reference_source():
+    """SearchSpacePruning<float>::filterCandidatesByDepth + Math::median on real candidates of the person model (boxes kept inside the
+    depth image: the reference takes depth(box) unclipped)."""
+    fm = load_flat("Person_26parts")
+    rng = np.random.default_rng(9)
+    ohow = [(20, 26)]
+    scales = np.array([4.0], np.float32)
+    resp = _random_levels(fm, rng, ohow)
+    R = ref_lib.RefDP(fm, 32)
+    O = oracle_lib.OracleDetector(fm, 32)
+    R.set_levels(ohow, scales); O.set_levels(ohow, scales)
+    for f in range(fm.nfilters()):
+        R.set_response(0, f, resp[0][f]); O.set_response(0, f, resp[0][f])
+    O.run(None, 3, 3)
+    thr = float(np.sort(O.rootv(0).ravel())[-150])
+    assert R.run(thr) > 100
+    cands = R.candidates()
+    rects = np.stack([c[1] for c in cands]).astype(np.int32)
+    im_h, im_w = 400, 400
+    inside = np.array([(r[:, 0] >= 0).all() and (r[:, 1] >= 0).all() and ((r[:, 0] + r[:, 2]) <= im_w).all() and ((r[:, 1] + r[:, 3]) <= im_h).all()
+                       and (r[:, 2] > 0).all() and (r[:, 3] > 0).all() for r in rects])
+    assert inside.sum() > 30
+    yy, xx = np.mgrid[0:im_h, 0:im_w]
+    depth = (2.0 + 0.0003 * xx + 0.6 * (xx > 85) + 0.004 * rng.standard_normal((im_h, im_w))).astype(np.float32)   # a depth step
+    depth[rng.random((im_h, im_w)) < 0.3] = 0.0               # holes: no depth reading
+    comp = fm.comps[0]
+    parent = np.array([p.parentid for p in comp], np.int32)
+    anchor0 = np.array([fm.anchors[p.defid[0]] if p.defid else (0, 0) for p in comp], np.int32).reshape(-1)
+    for zf in (0.005, 0.03, 0.2):
+        want = R.filter_by_depth(depth, zf)
+        keep = np.zeros(len(cands), np.int32)
+        oracle_lib.lib().orc_filter_by_depth(np.ascontiguousarray(rects).reshape(-1), len(cands), 26, parent, anchor0, depth.reshape(-1), im_h, im_w, zf, keep)
+        assert np.array_equal(keep[inside], want[inside]), zf
+    assert 0 < R.filter_by_depth(depth, 0.03)[inside].sum() < inside.sum()
