@@ -120,7 +120,7 @@ def make_oracle(max_levels=0):
     return O, oracle_lib.use_all_cores()
 
 
-def cpu_frames_per_sec(frames, max_levels=0, budget_s=20.0, max_frames=8, warmup=1):
+def cpu_frames_per_sec(frames, max_levels=0, budget_s=20.0, max_frames=64, warmup=1):
     """Times the restated reference CPU path (oracle, OpenMP over all host threads) on a bounded sample."""
     O, cores = make_oracle(max_levels)
     for i in range(warmup):

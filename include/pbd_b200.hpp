@@ -8,8 +8,10 @@
 //   Candidate::sort(candidates);                                                 // :111
 //
 // Images are passed as `pbd_b200::Mat` (rows, cols, channels, step, 8-bit data pointer); when OpenCV headers are
-// available a cv::Mat converts implicitly.  All numerics run in libpbd_b200.so on the GPU in single precision
-// (the reference's PartsBasedDetector<float>, src/demo.cpp:85); PartsBasedDetector<double> is intentionally not provided.
+// available a cv::Mat converts implicitly.  All numerics run in libpbd_b200.so on the GPU in single precision (the reference's
+// PartsBasedDetector<float>, src/demo.cpp:85).  PartsBasedDetector<double> (ros/Node.hpp:121, cells/detect.cpp:180) is accepted
+// and runs the same fp32 path: scores agree with the reference's double pipeline to ~1e-6 relative (north star: 1e-4), but
+// bit-identical integer outputs are only claimed against PartsBasedDetector<float>.
 #ifndef PBD_B200_HPP_
 #define PBD_B200_HPP_
 #include <algorithm>
@@ -160,7 +162,7 @@ typedef std::vector<Candidate> vectorCandidate;
 // reference include/PartsBasedDetector.hpp:152-175
 template <typename T>
 class PartsBasedDetector {
-  static_assert(sizeof(T) == sizeof(float), "the CUDA path computes in single precision (reference PartsBasedDetector<float>)");
+  static_assert(sizeof(T) == sizeof(float) || sizeof(T) == sizeof(double), "T is float or double (the device computes in single precision either way)");
   pbd_detector* d_ = nullptr;
   std::string name_;
 
@@ -237,6 +239,88 @@ class PartsBasedDetector {
   void need() const { if (!d_) throw Error(PBD_E_STATE, "distributeModel() has not been called"); }
   int device_;
   void* stream_;
+};
+
+// depth image view (cv::Mat CV_32FC1), metres; 0 = no reading
+struct DepthMat {
+  int rows = 0, cols = 0;
+  size_t step = 0;                 // bytes per row
+  const float* data = nullptr;
+  DepthMat() {}
+  DepthMat(int r, int c, const float* d, size_t s = 0) : rows(r), cols(c), step(s ? s : (size_t)c * sizeof(float)), data(d) {}
+  bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+#ifdef PBD_B200_HAVE_OPENCV
+  DepthMat(const cv::Mat& m) : rows(m.rows), cols(m.cols), step(m.step), data(reinterpret_cast<const float*>(m.data)) {   // NOLINT
+    if (!m.empty() && m.type() != CV_32F) throw Error(PBD_E_UNSUPPORTED, "depth image must be CV_32FC1");
+  }
+#endif
+};
+
+// reference include/SearchSpacePruning.hpp / src/SearchSpacePruning.cpp:73-95 (the call detect() keeps commented out, zfactor 0.03)
+template <typename T>
+class SearchSpacePruning {
+ public:
+  // candidates of ONE frame; the model replaces the reference's `Parts&` argument (it holds the same tree and anchors)
+  void filterCandidatesByDepth(const Model& model, vectorCandidate& candidates, const DepthMat& depth, const float zfactor) {
+    if (depth.empty()) throw Error(PBD_E_ARG, "empty depth image");
+    const int n = (int)candidates.size();
+    size_t mp = 1;
+    for (const Candidate& c : candidates) mp = std::max(mp, c.parts().size());
+    std::vector<int32_t> meta((size_t)n * 4), parts((size_t)n * mp * 7, 0);
+    std::vector<float> scores(n);
+    for (int i = 0; i < n; ++i) {
+      const Candidate& c = candidates[i];
+      meta[4 * i] = c.frame; meta[4 * i + 1] = c.level; meta[4 * i + 2] = c.component(); meta[4 * i + 3] = (int32_t)c.parts().size();
+      scores[i] = c.score();
+      for (size_t p = 0; p < c.parts().size(); ++p) {
+        int32_t* o = &parts[((size_t)i * mp + p) * 7];
+        o[0] = i;                                                    // tag: which input candidate this is
+        o[3] = c.parts()[p].x; o[4] = c.parts()[p].y; o[5] = c.parts()[p].width; o[6] = c.parts()[p].height;
+      }
+    }
+    pbd_candidates* h = nullptr;
+    check(pbd_candidates_create(n, (int)mp, meta.data(), scores.data(), parts.data(), &h));
+    const int rc = pbd_candidates_filter_by_depth(h, model.handle(), depth.data, depth.rows, depth.cols, depth.step, zfactor);
+    if (rc != PBD_OK) { pbd_candidates_free(h); check(rc); }
+    const int k = pbd_candidates_count(h);
+    std::vector<int32_t> m2((size_t)k * 4), p2((size_t)k * mp * 7);
+    std::vector<float> s2(k);
+    if (k) check(pbd_candidates_export(h, m2.data(), s2.data(), p2.data(), (int)mp));
+    pbd_candidates_free(h);
+    vectorCandidate out;
+    for (int j = 0; j < k; ++j) out.push_back(candidates[p2[(size_t)j * mp * 7]]);
+    candidates.swap(out);
+  }
+};
+
+// cv::imread for the containers the library decodes itself (PNG, binary PNM): packed BGR pixels (src/demo.cpp:90)
+inline std::vector<uint8_t> imread(const std::string& path, int& rows, int& cols) {
+  int32_t h = 0, w = 0;
+  check(pbd_imread_bgr8(path.c_str(), nullptr, 0, &h, &w));
+  std::vector<uint8_t> px((size_t)h * w * 3);
+  check(pbd_imread_bgr8(path.c_str(), px.data(), px.size(), &h, &w));
+  rows = h; cols = w;
+  return px;
+}
+
+// the fields of a sensor_msgs/Image message (ros/Node.cpp:144-183 receives them as ImageConstPtr): converts like
+// cv_bridge::toCvCopy(msg, enc::BGR8) / toCvCopy(msg, enc::TYPE_32FC1) without ROS or OpenCV
+struct RosImage {
+  uint32_t height = 0, width = 0;
+  std::string encoding;
+  uint8_t is_bigendian = 0;
+  uint32_t step = 0;
+  const uint8_t* data = nullptr;
+  std::vector<uint8_t> toBgr8() const {
+    std::vector<uint8_t> out((size_t)height * width * 3);
+    check(pbd_ros_image_to_bgr8(encoding.c_str(), (int)height, (int)width, step, is_bigendian, data, out.data()));
+    return out;
+  }
+  std::vector<float> toDepth32F() const {
+    std::vector<float> out((size_t)height * width);
+    check(pbd_ros_depth_to_f32(encoding.c_str(), (int)height, (int)width, step, is_bigendian, data, out.data()));
+    return out;
+  }
 };
 
 }  // namespace pbd_b200

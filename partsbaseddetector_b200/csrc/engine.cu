@@ -76,6 +76,10 @@ Engine::Engine(const Model& m, int device, cudaStream_t stream) : thresh((double
     check_cuda(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
     build_tables();
     check_cuda(cudaMalloc(&d_g_, sizeof(Geometry)), "cudaMalloc geometry");
+    check_cuda(cudaMalloc(&d_orient_lut_, hog_orient_lut_bytes()), "cudaMalloc orientation table");
+    launches_ += launch_hog_orient_lut(d_orient_lut_, stream_);
+    check_cuda(cudaGetLastError(), "orientation table launch");
+    dev_bytes_ += hog_orient_lut_bytes();
     for (ResultSlot& S : slots_) {
       check_cuda(cudaMalloc(&S.d_nhits, sizeof(int)), "cudaMalloc nhits");
       check_cuda(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming), "cudaEventCreate");
@@ -105,7 +109,7 @@ void Engine::release() {
   void* ptrs[] = {d_wtc_, d_wtc16_, d_f16_, d_fhi_, d_flo_, d_tc_levels_, d_tc_tiles_, d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
-                  d_scratch_i_, d_rootkeep_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
+                  d_scratch_i_, d_rootkeep_, d_orient_lut_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
                   slots_[1].d_hits, slots_[1].d_nhits, slots_[1].d_xym, d_ksize_, nms_.boxes, nms_.keys, nms_.skeys, nms_.sidx, nms_.kept_idx,
                   nms_.frame_count, nms_.fill, nms_.kept_count, nms_.out_off, nms_.seg_off, nms_.scratch, slots_[0].d_hits_out,
                   slots_[0].d_xym_out, slots_[0].d_total, slots_[1].d_hits_out, slots_[1].d_xym_out, slots_[1].d_total};
@@ -344,7 +348,9 @@ void Engine::set_frames_geometry(int n, int h, int w, int c) {
   for (int l = 0; l < g.n_levels; ++l) {
     LevelDesc& L = g.lv[l];
     if (L.img_h < 3 || L.img_w < 3) throw ArgError("pyramid level smaller than 3 pixels");
-    L.img_off = img_off; img_off += (long long)L.img_w * L.img_h * c;
+    L.identity = (L.src_level < 0 && L.img_w == w && L.img_h == h) ? 1 : 0;
+    L.img_off = img_off;
+    if (!L.identity) img_off += (long long)L.img_w * L.img_h * c;
     img_off = (img_off + 15) / 16 * 16;
     L.block_off = block_off; block_off += L.bw * L.bh;
     L.cell_off = cell_off; cell_off += L.ow * L.oh;
@@ -488,7 +494,7 @@ void Engine::alloc_batch() {
   const size_t n = g.n_frames, ct = g.cells_total, bt = g.blocks_total;
   const int ncomp = model_.ncomponents();
   if (have_images_) {
-    ensure(b_.pyr, cap_pyr_, n * (size_t)g.img_bytes);
+    ensure(b_.pyr, cap_pyr_, n * (size_t)std::max<long long>(g.img_bytes, 16));
     ensure(b_.hist, cap_hist_, n * bt * 18);
     ensure(b_.norm, cap_norm_, n * bt);
   }
@@ -561,7 +567,7 @@ void Engine::chunked_upload_pyramid(const uint8_t* frames, uint8_t* d_dst, cudaE
     check_cuda(cudaEventRecord(copy_ev_[c], copy_stream_), "event");
     check_cuda(cudaStreamWaitEvent(stream_, copy_ev_[c], 0), "wait");
     launches_ += launch_pyramid(g_, d_g_, b_, d_xofs_, d_xalpha_, d_yofs_, d_ybeta_, f0, f1 - f0, stream_);
-    launches_ += launch_hog(g_, d_g_, b_, model_.sbin, f0, f1 - f0, stream_);
+    launches_ += launch_hog(g_, d_g_, b_, d_orient_lut_, model_.sbin, f0, f1 - f0, stream_);
   }
   if (record_after) check_cuda(cudaEventRecord(record_after, stream_), "event");   // frames consumed
   check_cuda(cudaGetLastError(), "pyramid/HOG launch");
@@ -632,7 +638,7 @@ void Engine::run_pyramid() {
   if (timing) { check_cuda(cudaEventRecord(ev_[1], stream_), "event"); ev_valid_[1] = true; }
   launches_ += launch_pyramid(g_, d_g_, b_, d_xofs_, d_xalpha_, d_yofs_, d_ybeta_, 0, g_.n_frames, stream_);
   if (timing) { check_cuda(cudaEventRecord(ev_[2], stream_), "event"); ev_valid_[2] = true; }
-  launches_ += launch_hog(g_, d_g_, b_, model_.sbin, 0, g_.n_frames, stream_);
+  launches_ += launch_hog(g_, d_g_, b_, d_orient_lut_, model_.sbin, 0, g_.n_frames, stream_);
   check_cuda(cudaGetLastError(), "pyramid/HOG launch");
   feat_from_hog_ = true;
   stage_ = 2;
@@ -895,8 +901,8 @@ void Engine::get_pyramid_image(int frame, int level, uint8_t* dst) {
   if (!have_images_) throw StateError("no pyramid images in a manually defined batch");
   check_idx(frame >= 0 && frame < g_.n_frames && level >= 0 && level < g_.n_levels, "get_pyramid_image");
   const LevelDesc& L = g_.lv[level];
-  check_cuda(cudaMemcpyAsync(dst, b_.pyr + (size_t)frame * g_.img_bytes + L.img_off, (size_t)L.img_w * L.img_h * g_.in_c,
-                             cudaMemcpyDeviceToHost, stream_), "D2H image");
+  const uint8_t* src = L.identity ? b_.frames + (size_t)frame * g_.in_h * g_.in_w * g_.in_c : b_.pyr + (size_t)frame * g_.img_bytes + L.img_off;
+  check_cuda(cudaMemcpyAsync(dst, src, (size_t)L.img_w * L.img_h * g_.in_c, cudaMemcpyDeviceToHost, stream_), "D2H image");
   check_cuda(cudaStreamSynchronize(stream_), "sync");
 }
 void Engine::get_features(int frame, int level, float* dst) {

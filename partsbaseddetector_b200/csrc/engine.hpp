@@ -213,6 +213,7 @@ class Engine {
   int frames_buf_ = 0;
   int* d_scratch_i_ = nullptr; size_t cap_scratch_i_ = 0;
   unsigned char* d_rootkeep_ = nullptr; size_t cap_rootkeep_ = 0;
+  unsigned char* d_orient_lut_ = nullptr;      // snapped orientation of every (dx, dy) gradient (hog.cu)
   std::vector<Hit> h_hits_;                    // host staging reused across batches
   std::vector<int> h_xym_;
   cudaStream_t copy_stream_ = nullptr;

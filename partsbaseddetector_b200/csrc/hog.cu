@@ -30,9 +30,36 @@ __device__ __forceinline__ float bin_coord(int p, int sbin, double dsb, double i
 
 constexpr int HB_X = 16, HB_Y = 8;                 // HOG blocks per CTA (one thread per block)
 
+// Orientation snap (reference :243-249): best of 9 directions and their opposites by the separately rounded dot product
+// uu[o]*dx + vv[o]*dy.  dx, dy are differences of 8-bit samples, so there are only 511 x 511 distinct inputs: the snapped
+// orientation is tabulated once per detector BY THIS VERY CODE (bit-identical decisions, ties included) and hog_hist looks it up
+// instead of evaluating 9 dot products per pixel.
+__device__ __forceinline__ int snap_orientation(float dx, float dy) {
+  const float uu[9] = {(float)1.000, (float)0.9397, (float)0.7660, (float)0.5000, (float)0.1736,
+                       (float)-0.1736, (float)-0.5000, (float)-0.7660, (float)-0.9397};
+  const float vv[9] = {(float)0.000, (float)0.3420, (float)0.6428, (float)0.8660, (float)0.9848,
+                       (float)0.9848, (float)0.8660, (float)0.6428, (float)0.3420};
+  float best_dot = 0.f;
+  int best_o = 0;
+#pragma unroll
+  for (int o = 0; o < 9; ++o) {
+    const float dot = __fadd_rn(__fmul_rn(uu[o], dx), __fmul_rn(vv[o], dy));
+    if (dot > best_dot) { best_dot = dot; best_o = o; }
+    else if (-dot > best_dot) { best_dot = -dot; best_o = o + 9; }
+  }
+  return best_o;
+}
+constexpr int kGradSpan = 511;                     // dx, dy in [-255, 255]
+__global__ void __launch_bounds__(256) hog_orient_lut(unsigned char* __restrict__ lut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kGradSpan * kGradSpan) return;
+  lut[i] = (unsigned char)snap_orientation((float)(i % kGradSpan - 255), (float)(i / kGradSpan - 255));
+}
+
 template <int CN>
 __global__ void __launch_bounds__(HB_X * HB_Y)
-hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float* __restrict__ hist, float* __restrict__ norm, int sbin, int frame0) {
+hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, const uint8_t* __restrict__ pyr, const unsigned char* __restrict__ orient_lut,
+         float* __restrict__ hist, float* __restrict__ norm, int sbin, int frame0) {
   extern __shared__ __align__(16) unsigned char hsm[];
   // ---- which tile of which level ----
   int tile = blockIdx.x, l = 0, tiles_x = 0;
@@ -48,7 +75,7 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float*
   const int bx0 = (tile % tiles_x) * HB_X, by0 = (tile / tiles_x) * HB_Y;
   const int cols = L.img_w, rows = L.img_h;
   const int vis_w = L.bw * sbin, vis_h = L.bh * sbin;
-  const uint8_t* im = pyr + (size_t)frame * g->img_bytes + L.img_off;
+  const uint8_t* im = L.identity ? frames + (size_t)frame * g->in_h * g->in_w * CN : pyr + (size_t)frame * g->img_bytes + L.img_off;
   const size_t stride = (size_t)cols * CN;
   // pixel region that can scatter into this tile's blocks: floor((p+0.5)/sbin - 0.5) in {b-1, b}
   const int marg = (sbin + 1) / 2 + 1;
@@ -58,48 +85,46 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float*
   float* shist = smag + PH * PW;                                     // [18][HB_X*HB_Y] histogram of each thread's block
   float* sfx = shist + 18 * HB_X * HB_Y;                             // [PW] fractional bin coordinate vx0 of every column of the region
   float* sfy = sfx + PW;                                             // [PH] ... vy0 of every row
-  int* sbx = reinterpret_cast<int*>(sfy + PH);                       // [PW] floor(xp) of every column, [PH] floor(yp) of every row
+  float* sgx = sfy + PH;                                             // [PW] vx1 = (float)(1.0 - vx0), :258-259
+  float* sgy = sgx + PW;                                             // [PH] vy1
+  int* sbx = reinterpret_cast<int*>(sgy + PH);                       // [PW] floor(xp) of every column, [PH] floor(yp) of every row
   int* sby = sbx + PW;
   unsigned char* sbo = reinterpret_cast<unsigned char*>(sby + PH);   // [PH][PW] snapped orientation
 
-  const float uu[9] = {(float)1.000, (float)0.9397, (float)0.7660, (float)0.5000, (float)0.1736,
-                       (float)-0.1736, (float)-0.5000, (float)-0.7660, (float)-0.9397};
-  const float vv[9] = {(float)0.000, (float)0.3420, (float)0.6428, (float)0.8660, (float)0.9848,
-                       (float)0.9848, (float)0.8660, (float)0.6428, (float)0.3420};
   // ---- phase 1: per pixel gradient, channel pick, orientation snap (each pixel of the region exactly once) ----
+  int rx = threadIdx.x % PW, ry = threadIdx.x / PW;                  // position inside the region, advanced without divisions
+  const int stepx = (HB_X * HB_Y) % PW, stepy = (HB_X * HB_Y) / PW;
   for (int i = threadIdx.x; i < PW * PH; i += HB_X * HB_Y) {
-    const int x = px0 + i % PW, y = py0 + i / PW;
+    const int x = px0 + rx, y = py0 + ry;
+    rx += stepx; ry += stepy;
+    if (rx >= PW) { rx -= PW; ++ry; }
     float mag = -1.f;
     int best_o = 0;
     if (x >= 1 && x <= vis_w - 2 && y >= 1 && y <= vis_h - 2) {       // the reference's pixel loops, :202-203
       const int sx = min(x, cols - 2), sy = min(y, rows - 2);
       const uint8_t* s = im + (size_t)sy * stride + sx * CN;
-      float dx, dy, v;
+      // dx, dy are integers of magnitude <= 255: dx*dx + dy*dy <= 130050 is exact in float (and in int), so the reference's float
+      // comparisons of the squared magnitudes (:221-239) are integer comparisons
+      int dx, dy, v;
       if (CN == 1) {                                                   // :207-212
-        dy = (float)((int)s[stride] - (int)*(s - stride));
-        dx = (float)((int)s[1] - (int)*(s - 1));
-        v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        dy = (int)s[stride] - (int)*(s - stride);
+        dx = (int)s[1] - (int)*(s - 1);
+        v = dx * dx + dy * dy;
       } else {                                                         // :217-240
-        const float dyb = (float)((int)s[stride] - (int)*(s - stride));
-        const float dxb = (float)((int)s[3] - (int)*(s - 3));
-        const float vb = __fadd_rn(__fmul_rn(dxb, dxb), __fmul_rn(dyb, dyb));
-        const float dyg = (float)((int)s[stride + 1] - (int)*(s - stride + 1));
-        const float dxg = (float)((int)s[4] - (int)*(s - 2));
-        const float vg = __fadd_rn(__fmul_rn(dxg, dxg), __fmul_rn(dyg, dyg));
-        dy = (float)((int)s[stride + 2] - (int)*(s - stride + 2));
-        dx = (float)((int)s[5] - (int)*(s - 1));
-        v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const int dyb = (int)s[stride] - (int)*(s - stride);
+        const int dxb = (int)s[3] - (int)*(s - 3);
+        const int vb = dxb * dxb + dyb * dyb;
+        const int dyg = (int)s[stride + 1] - (int)*(s - stride + 1);
+        const int dxg = (int)s[4] - (int)*(s - 2);
+        const int vg = dxg * dxg + dyg * dyg;
+        dy = (int)s[stride + 2] - (int)*(s - stride + 2);
+        dx = (int)s[5] - (int)*(s - 1);
+        v = dx * dx + dy * dy;
         if (vg > v) { v = vg; dx = dxg; dy = dyg; }
         if (vb > v) { v = vb; dx = dxb; dy = dyb; }
       }
-      float best_dot = 0.f;                                            // :243-249
-#pragma unroll
-      for (int o = 0; o < 9; ++o) {
-        const float dot = __fadd_rn(__fmul_rn(uu[o], dx), __fmul_rn(vv[o], dy));
-        if (dot > best_dot) { best_dot = dot; best_o = o; }
-        else if (-dot > best_dot) { best_dot = -dot; best_o = o + 9; }
-      }
-      mag = __fsqrt_rn(v);                                             // :260
+      best_o = __ldg(orient_lut + (dy + 255) * kGradSpan + (dx + 255));   // :243-249, tabulated
+      mag = __fsqrt_rn((float)v);                                      // :260
     }
     smag[i] = mag;
     sbo[i] = (unsigned char)best_o;
@@ -116,7 +141,8 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float*
       const float c = bin_coord(p, sbin, dsb, inv_sb, pow2);
       const int ic = (int)floorf(c);
       const float f = __fsub_rn(c, (float)ic);
-      if (isx) { sfx[i] = f; sbx[i] = ic; } else { sfy[i - PW] = f; sby[i - PW] = ic; }
+      const float fc = (float)(1.0 - (double)f);                       // vx1 / vy1, :258-259
+      if (isx) { sfx[i] = f; sgx[i] = fc; sbx[i] = ic; } else { sfy[i - PW] = f; sgy[i - PW] = fc; sby[i - PW] = ic; }
     }
   }
   __syncthreads();
@@ -129,19 +155,17 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ pyr, float*
   float* myh = shist + threadIdx.x;
   for (int y = y_lo; y <= y_hi; ++y) {
     const int iyp = sby[y - py0];                                      // :252
-    const float vy0 = sfy[y - py0];
     float wy;
-    if (iyp == by) wy = (float)(1.0 - (double)vy0);                    // vy1, :258
-    else if (iyp == by - 1) wy = vy0;
+    if (iyp == by) wy = sgy[y - py0];                                  // vy1, :258
+    else if (iyp == by - 1) wy = sfy[y - py0];
     else continue;
     const float* mrow = smag + (y - py0) * PW - px0;
     const unsigned char* brow = sbo + (y - py0) * PW - px0;
     for (int x = x_lo; x <= x_hi; ++x) {
       const int ixp = sbx[x - px0];
-      const float vx0 = sfx[x - px0];
       float wx;
-      if (ixp == bx) wx = (float)(1.0 - (double)vx0);
-      else if (ixp == bx - 1) wx = vx0;
+      if (ixp == bx) wx = sgx[x - px0];
+      else if (ixp == bx - 1) wx = sfx[x - px0];
       else continue;
       const float term = __fmul_rn(__fmul_rn(wy, wx), mrow[x]);         // :262-265
       float* hb = myh + brow[x] * (HB_X * HB_Y);
@@ -212,19 +236,25 @@ __global__ void __launch_bounds__(128) hog_feat(const Geometry* __restrict__ g, 
 
 }  // namespace
 
-int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int sbin, int frame0, int nframes, cudaStream_t s) {
+size_t hog_orient_lut_bytes() { return (size_t)kGradSpan * kGradSpan; }
+int launch_hog_orient_lut(unsigned char* d_lut, cudaStream_t s) {
+  hog_orient_lut<<<(kGradSpan * kGradSpan + 255) / 256, 256, 0, s>>>(d_lut);
+  return 1;
+}
+
+int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const unsigned char* d_orient_lut, int sbin, int frame0, int nframes, cudaStream_t s) {
   if (g.blocks_total <= 0) return 0;
   int ntiles = 0;
   for (int l = 0; l < g.n_levels; ++l) ntiles += ((g.lv[l].bw + HB_X - 1) / HB_X) * ((g.lv[l].bh + HB_Y - 1) / HB_Y);
   const int marg = (sbin + 1) / 2 + 1;
   const int PW = HB_X * sbin + sbin + 2 * marg, PH = HB_Y * sbin + sbin + 2 * marg;
-  const size_t smem = (size_t)PW * PH * 5 + (size_t)18 * HB_X * HB_Y * 4 + (size_t)(PW + PH) * 8 + 16;   // + the coordinate tables
+  const size_t smem = (size_t)PW * PH * 5 + (size_t)18 * HB_X * HB_Y * 4 + (size_t)(PW + PH) * 16 + 16;   // + the coordinate tables
   // per launch: the attribute is per device and a process may drive several devices
   if (g.in_c == 1) cudaFuncSetAttribute(hog_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   else cudaFuncSetAttribute(hog_hist<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 gh(ntiles, nframes);
-  if (g.in_c == 1) hog_hist<1><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin, frame0);
-  else hog_hist<3><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.pyr, b.hist, b.norm, sbin, frame0);
+  if (g.in_c == 1) hog_hist<1><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.frames, b.pyr, d_orient_lut, b.hist, b.norm, sbin, frame0);
+  else hog_hist<3><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.frames, b.pyr, d_orient_lut, b.hist, b.norm, sbin, frame0);
   int n = 1;
   if (g.cells_total > 0) {
     dim3 gf((g.cells_total + 127) / 128, nframes);

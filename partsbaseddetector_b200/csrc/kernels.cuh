@@ -28,6 +28,7 @@ struct LevelDesc {
   int ow, oh;            // HOG cells   (reference `outsize`, :175)
   float scale;           // reference scales_[l], :118,124
   int src_level;         // -1: resized from the input frame, else pyrDown of that level
+  int identity;          // 1: the level IS the input frame (same size: cv::resize copies): read in place from `frames`, no pyramid copy
   long long img_off;     // byte offset of the level image inside one frame's pyramid buffer
   int block_off;         // offset (in blocks) inside one frame's hist/norm arrays
   int cell_off;          // offset (in cells) inside one map
@@ -91,7 +92,11 @@ struct Hit {
 // ---- launchers (each enqueues on `s`, returns the number of kernels launched) ----
 int launch_pyramid(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_xofs, const short* d_xalpha,
                    const int* d_yofs, const short* d_ybeta, int frame0, int nframes, cudaStream_t s);
-int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, int sbin, int frame0, int nframes, cudaStream_t s);
+// d_orient_lut: hog_orient_lut_bytes() bytes filled once by launch_hog_orient_lut (the snapped orientation of every possible gradient)
+size_t hog_orient_lut_bytes();
+int launch_hog_orient_lut(unsigned char* d_lut, cudaStream_t s);
+int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const unsigned char* d_orient_lut, int sbin, int frame0, int nframes,
+               cudaStream_t s);
 
 // device copy of the model's filters (converted to float, reference src/PartsBasedDetector.cpp:115-117)
 struct FilterBank {

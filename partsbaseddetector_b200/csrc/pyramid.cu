@@ -3,6 +3,9 @@
 // chains of cv::pyrDown (5x5 binomial, BORDER_REFLECT_101, 8U).  Pure integer arithmetic => bit-exact.
 // HBM-bound: every output pixel is written once, sources are read through L1/L2 (a pyrDown tap
 // footprint is re-read by 6.25 outputs on average, all hits).
+#include <algorithm>
+#include <vector>
+
 #include "kernels.cuh"
 
 namespace pbd {
@@ -19,7 +22,8 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 __global__ void __launch_bounds__(256) pyr_resize_u8(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames,
                                                      uint8_t* __restrict__ pyr, const int* __restrict__ xofs,
                                                      const short* __restrict__ xalpha, const int* __restrict__ yofs,
-                                                     const short* __restrict__ ybeta, int level, int frame0) {
+                                                     const short* __restrict__ ybeta, int4 levels, int frame0) {
+  const int level = blockIdx.z == 0 ? levels.x : blockIdx.z == 1 ? levels.y : blockIdx.z == 2 ? levels.z : levels.w;   // independent levels share a launch
   const LevelDesc& L = g->lv[level];
   const int dw = L.img_w, dh = L.img_h, cn = g->in_c, sw = g->in_w, sh = g->in_h;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -44,7 +48,9 @@ __global__ void __launch_bounds__(256) pyr_resize_u8(const Geometry* __restrict_
 }
 
 // One thread per destination pixel: out = (sum_{i,j} k[i]k[j] src[2y+i-2][2x+j-2] + 128) >> 8, k = [1 4 6 4 1].
-__global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ g, uint8_t* __restrict__ pyr, int level, int frame0) {
+__global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, uint8_t* __restrict__ pyr, int4 levels,
+                                                   int frame0) {
+  const int level = blockIdx.z == 0 ? levels.x : blockIdx.z == 1 ? levels.y : blockIdx.z == 2 ? levels.z : levels.w;
   const LevelDesc& L = g->lv[level];
   const LevelDesc& P = g->lv[L.src_level];
   const int dw = L.img_w, dh = L.img_h, cn = g->in_c, sw = P.img_w, sh = P.img_h;
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ 
   if (idx >= dw * dh) return;
   const int x = idx % dw, y = idx / dw;
   const int frame = frame0 + blockIdx.y;
-  const uint8_t* S = pyr + (size_t)frame * g->img_bytes + P.img_off;
+  const uint8_t* S = P.identity ? frames + (size_t)frame * sh * sw * cn : pyr + (size_t)frame * g->img_bytes + P.img_off;   // level 0 is the frame itself
   uint8_t* D = pyr + (size_t)frame * g->img_bytes + L.img_off + (size_t)idx * cn;
   const int k[5] = {1, 4, 6, 4, 1};
   int xs[5];
@@ -77,16 +83,29 @@ __global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ 
 int launch_pyramid(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const int* d_xofs, const short* d_xalpha,
                    const int* d_yofs, const short* d_ybeta, int frame0, int nframes, cudaStream_t s) {
   int launches = 0;
-  // resized levels depend only on the frame; pyrDown level l depends on level l - interval, so
-  // launching levels in increasing order on one stream satisfies every dependency.
-  for (int l = 0; l < g.n_levels; ++l) {
-    const LevelDesc& L = g.lv[l];
-    const int npx = L.img_w * L.img_h;
-    if (npx <= 0) continue;
-    dim3 grid((npx + 255) / 256, nframes);
-    if (L.src_level < 0) pyr_resize_u8<<<grid, 256, 0, s>>>(d_g, b.frames, b.pyr, d_xofs, d_xalpha, d_yofs, d_ybeta, l, frame0);
-    else pyr_down_u8<<<grid, 256, 0, s>>>(d_g, b.pyr, l, frame0);
-    ++launches;
+  // Resized levels depend only on the frame; pyrDown level l depends on level l - interval.  Levels of the same "generation"
+  // (all resizes; then the pyrDowns whose sources exist) are independent and share one launch (blockIdx.z picks the level, up to 4
+  // per launch), generations follow each other on the stream.
+  std::vector<int> gen(g.n_levels, 0);
+  int ngen = 0;
+  for (int l = 0; l < g.n_levels; ++l) { gen[l] = g.lv[l].src_level < 0 ? 0 : gen[g.lv[l].src_level] + 1; ngen = std::max(ngen, gen[l] + 1); }
+  for (int k = 0; k < ngen; ++k) {
+    std::vector<int> ls;
+    for (int l = 0; l < g.n_levels; ++l)
+      if (gen[l] == k && g.lv[l].img_w * g.lv[l].img_h > 0 && !g.lv[l].identity) ls.push_back(l);   // a level of the frame's own size is read in place
+    for (size_t i = 0; i < ls.size(); i += 4) {
+      const int n = (int)std::min<size_t>(4, ls.size() - i);
+      int npx = 0;
+      int4 lv = make_int4(ls[i], ls[i], ls[i], ls[i]);
+      for (int j = 0; j < n; ++j) {
+        npx = std::max(npx, g.lv[ls[i + j]].img_w * g.lv[ls[i + j]].img_h);
+        (j == 0 ? lv.x : j == 1 ? lv.y : j == 2 ? lv.z : lv.w) = ls[i + j];
+      }
+      dim3 grid((npx + 255) / 256, nframes, n);
+      if (k == 0) pyr_resize_u8<<<grid, 256, 0, s>>>(d_g, b.frames, b.pyr, d_xofs, d_xalpha, d_yofs, d_ybeta, lv, frame0);
+      else pyr_down_u8<<<grid, 256, 0, s>>>(d_g, b.frames, b.pyr, lv, frame0);
+      ++launches;
+    }
   }
   return launches;
 }

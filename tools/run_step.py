@@ -19,6 +19,8 @@ ap.add_argument("--fast", action="store_true")
 ap.add_argument("--mode", type=int, default=-1, help="response mode 0 exact, 1 ffma, 2 tensor (tf32), 3 tensor (fp16)")
 ap.add_argument("--G", type=int, default=0)
 ap.add_argument("--max-levels", type=int, default=0)
+ap.add_argument("--nms", type=float, default=-1.0, help="device Candidate::sort + NMS with this overlap")
+ap.add_argument("--root-nms", type=int, default=0, help="root-map NMS window")
 a = ap.parse_args()
 frames = synth_frames(min(a.batch, 4), a.h, a.w)
 frames = np.ascontiguousarray(np.concatenate([frames] * ((a.batch + 3) // 4))[:a.batch])
@@ -31,6 +33,9 @@ if a.mode >= 0:
     det.set_option("tc_taps_per_partial", a.G)
 det.set_option("max_levels", a.max_levels)
 det.set_option("thresh", -1.14)
+if a.nms >= 0:
+    det.set_option("nms_overlap", a.nms)
+det.set_option("root_nms", a.root_nms)
 det.set_option("timing", 1)
 for _ in range(a.steps):
     det.enqueue_device(dev.data_ptr(), a.batch, a.h, a.w, 3)
