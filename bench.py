@@ -262,7 +262,7 @@ def run_gpu_arm(args):
     det.distributeModel(Model.load_bin(MODEL))
     det.set_option("max_candidates", 1 << 20)
     det.set_option("max_levels", cfg["max_levels"])
-    for kv in args.opt:                                        # experiments: --opt dt_scan=1
+    for kv in args.opt:                                        # experiments: --opt dt_variant=1
         k, v = kv.split("=")
         det.set_option(k, float(v))
     mode = MODES[args.mode]

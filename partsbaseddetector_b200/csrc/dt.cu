@@ -24,6 +24,7 @@
 // mixture (u16) and composed lazily by the backtrack (backtrack.cu).
 #include <algorithm>
 #include <cfloat>
+#include <type_traits>
 #include "kernels.cuh"
 #include "dt_envelope.cuh"
 #include "dt_lines.cuh"
@@ -68,7 +69,10 @@ __device__ __forceinline__ void st_u16(unsigned short* base, unsigned idx, unsig
 #ifndef PBD_DT_MINBLOCKS
 #define PBD_DT_MINBLOCKS 6        // 80 registers: 6 CTAs of 4 warps per SM (7 CTAs at 72 registers measured 9 % slower)
 #endif
-// SCAN = 0: eager emission (the detector's kernel: fastest on real score maps, where ~95 % of the samples stay on the envelope);
+// SCAN = 0: eager emission, every break point through the reference's double expression -- the detector's kernel;
+// SCAN = -1: eager emission with certified fp32 break points (env::envelope_stream_cert; option dt_variant 1).  Bit-identical, but
+//            measured 12 % SLOWER on B200 (dt_rows + dt_cols 8.2 vs 7.3 ms per 64 frames): the fp32 path saves ~15 instructions per
+//            step, the bound bookkeeping, the extra ring column and the larger loop body (the double path stays as fallback) cost more;
 // SCAN > 0: lagged-scan emission with that lag (env::envelope_scan): one store per position unless a late pop rewinds the cursor --
 // the variant for rough inputs (white-noise maps: 3.4 instead of 24.6 stores per position), standalone transform impl 3.
 template <int MAXN, int SCAN>
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(kPassWarps * 32, PBD_DT_MINBLOCKS)
 dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int nmaps, const float* __restrict__ inA, size_t strideA,
         const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out, unsigned short* __restrict__ ptr,
         size_t stride_ptr) {
-  __shared__ Ring rings[kPassWarps];
+  __shared__ typename std::conditional<SCAN < 0, env::RingE, Ring>::type rings[kPassWarps];
   __shared__ float tiles[kPassWarps][2][32][kTileW + 1];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int w = blockIdx.x * kPassWarps + wib;                          // warp index -> (level, first item)
@@ -136,11 +140,14 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
     st_f32(dst, off, val); st_u16(dp, off, v);
   };
   const int os0 = M.os;
-  if (SCAN > 0) {
+  if constexpr (SCAN > 0) {
     env::envelope_scan<(SCAN > 0 ? SCAN : 1)>(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
                                               [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
     return;
-  }
+  } else if constexpr (SCAN < 0) {
+    env::envelope_stream_cert(N, f, os0, rings[wib], lane, zb, pb, loady, reload, [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
+    return;
+  } else {
 #if !defined(PBD_DT_WINDOWED_STORES)
   // every emission straight to global memory (the default, see below)
   env::envelope_stream(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
@@ -159,6 +166,7 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
                        [&](int i, float val, int v) { win.put(i, val, v, store); }, [&](int q) { win.step(q, os0, store); });
   win.finish(store);
 #endif
+  }
 }
 
 // E[j] = a x^2 + b x for x = j - tab_bias, j in [0, tab_len - kDtRcp): the position-independent part of Quadratic::operator()(x, y);
@@ -518,14 +526,18 @@ int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
   if (nmaps <= 0 || njobs <= 0 || g.cells_total <= 0) return 0;
   const size_t ct = (size_t)g.cells_total;
   dim3 gr((pass_warps(pg_rows, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
-  if (scan) launch_pass_v<4>(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
-                             ct * tmp_maps, b.ixdt, ct * ncm);
+  if (scan == 2) launch_pass_v<4>(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
+                                  ct * tmp_maps, b.ixdt, ct * ncm);
+  else if (scan == 1) launch_pass_v<-1>(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
+                                       ct * tmp_maps, b.ixdt, ct * ncm);
   else launch_pass(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
                    ct * tmp_maps, b.ixdt, ct * ncm);
   if (mark) mark(mark_ctx, 2);
   dim3 gc((pass_warps(pg_cols, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
-  if (scan) launch_pass_v<4>(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
-                             ct * tmp_maps, b.iyraw, ct * ncm);
+  if (scan == 2) launch_pass_v<4>(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
+                                  ct * tmp_maps, b.iyraw, ct * ncm);
+  else if (scan == 1) launch_pass_v<-1>(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
+                                       ct * tmp_maps, b.iyraw, ct * ncm);
   else launch_pass(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
                    ct * tmp_maps, b.iyraw, ct * ncm);
   if (mark) mark(mark_ctx, 3);

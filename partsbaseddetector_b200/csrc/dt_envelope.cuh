@@ -212,6 +212,129 @@ PBD_ENV_FN void envelope_stream(int N, const Quad& f, int os0, Ring& R, int lane
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// envelope_stream with CERTIFIED fp32 break points (round 2).  Only decisions depend on the break points -- the pop test s <= z and
+// the integer ranges floor(z) -- the values never leave the lane.  So s is first computed in fp32,
+//     adjacent:  s = (yq - yt) * fl(R) + fl(q + C0),                R = 1/(2a), C0 = -1/2 - b R
+//     general:   s = (yq - yt) * fl(R/dd) + fl((q + v)/2 + Cb),     Cb = -b R, dd = q - v < kRcp
+// together with a bound e = 2^-20 (|product| + |offset| + |constant|) on its distance to the reference's float(double) value (the
+// roundings of the difference, the reciprocal, the product, the offset and the sum add up to < 5 * 2^-24 of that magnitude, the
+// reference's own float rounding included).  A comparison is taken from the fp32 values only if they differ by more than the sum of
+// their bounds, floor(s) only if no integer lies within e of s; anything else is recomputed with the reference's double
+// expression (isect_adjacent / isect_far, bound 0), the compared break point of the top included.  Every decision therefore
+// equals the reference's; every stored entry carries its bound (RingE::e; entries reloaded from the backing store are
+// recomputed exactly).  Non-finite values fail every certificate.
+struct RingE {
+  float z[kRing][32];
+  float y[kRing][32];
+  unsigned int vp[kRing][32];
+  float e[kRing][32];
+};
+#if defined(__CUDA_ARCH__)
+PBD_ENV_FN float fmul_r(float a, float b) { return __fmul_rn(a, b); }
+PBD_ENV_FN float fadd_r(float a, float b) { return __fadd_rn(a, b); }
+PBD_ENV_FN float fsub_r(float a, float b) { return __fsub_rn(a, b); }
+PBD_ENV_FN float frint(float v) { return rintf(v); }
+#else
+PBD_ENV_FN float fmul_r(float a, float b) { return a * b; }
+PBD_ENV_FN float fadd_r(float a, float b) { return a + b; }
+PBD_ENV_FN float fsub_r(float a, float b) { return a - b; }
+PBD_ENV_FN float frint(float v) { return std::nearbyintf(v); }
+#endif
+PBD_ENV_FN bool floor_is_certain(float s, float e) { return fabsf(fsub_r(s, frint(s))) > e; }   // false for NaN / inf / huge
+
+template <typename LoadY, typename Reload, typename Emit>
+PBD_ENV_FN void envelope_stream_cert(int N, const Quad& f, int os0, RingE& R, int lane, float* zb, unsigned short* pb, LoadY loady,
+                                     Reload reload, Emit emit) {
+  const int pos_last = os0 + N - 1;
+  const float kEps = 9.5367431640625e-07f;                          // 2^-20
+  const float rf = (float)f.r1;                                     // fl(1 / (2a))
+  const double cbd = dsub(0.0, dmul(f.b, f.r1));                    // -b / (2a)
+  const float cb = (float)cbd, c0 = (float)dsub(cbd, 0.5);
+  const float acb = fabsf(cb), ac0 = fabsf(c0);
+  auto emit_run = [&](int lo, int hi, int v, double yd, double e0, double e1) {
+    if (hi >= lo) {
+      int i = lo - os0;
+      emit(i, (float)dadd(e0, yd), v);
+      if (hi > lo) {
+        emit(++i, (float)dadd(e1, yd), v);
+        int x = lo - v + 2;
+#pragma unroll 1
+        for (int pos = lo + 2; pos <= hi; ++pos, ++x) emit(++i, (float)dadd(ld_table(f.E, x), yd), v);
+      }
+    }
+  };
+  int k = 0, base = 0;                                            // stack depth of the top; lowest depth still valid in the ring
+  int vt = 0, pt = 0xFFFF;                                        // the top's sample and the sample below it
+  float ytf = loady(0), zt = -INFINITY, et = 0.f;                 // ... its value, break point and the bound of the break point
+  double yt = (double)ytf;
+  R.z[0][lane] = zt; R.y[0][lane] = ytf; R.vp[0][lane] = 0xFFFF0000u; R.e[0][lane] = 0.f;
+  zb[0] = zt; pb[0] = 0xFFFF;
+  // the reference's own break point of the current top (depth k >= 1, sample vt above sample pt)
+  auto exact_top = [&]() -> float {
+    const float ypf = (k - 1 >= base) ? R.y[(k - 1) & (kRing - 1)][lane] : reload(pt);
+    return vt - pt == 1 ? isect_adjacent(f, vt, (double)ypf, yt) : isect_far(f, pt, vt, (double)ypf, yt);
+  };
+  int lo = os0;
+  double e0 = ld_table(f.E, lo - vt), e1 = ld_table(f.E, lo - vt + 1);
+  for (int q = 1; q < N; ++q) {                                   // :160-170
+    const float yqf = loady(q);
+    const double yq = (double)yqf;
+    // ---- first intersection: the top is sample q - 1 ----
+    const float t = fmul_r(fsub_r(yqf, ytf), rf), qc = fadd_r((float)q, c0);
+    float s = fadd_r(t, qc);
+    float es = fmul_r(fadd_r(fadd_r(fabsf(t), fabsf(qc)), ac0), kEps);
+    if (!(floor_is_certain(s, es) && (k == 0 || fabsf(fsub_r(s, zt)) > fadd_r(es, et)))) {
+      PBD_ENV_STAT(exact)
+      s = isect_adjacent(f, q, yt, yq); es = 0.f;
+      if (k > 0 && et > 0.f && !(fabsf(fsub_r(s, zt)) > et)) { zt = exact_top(); et = 0.f; R.z[k & (kRing - 1)][lane] = zt; R.e[k & (kRing - 1)][lane] = 0.f; }
+    }
+    if (s <= zt && k > 0) {
+      do {
+        --k;
+        PBD_ENV_STAT(pop)
+        const int slot = k & (kRing - 1);
+        bool reloaded = false;
+        if (k < base) {                                           // popped below the ring: reload from the backing store
+          base = k;
+          const int vv = pt;                                      // the entry below the one just popped
+          R.vp[slot][lane] = (unsigned)vv | ((unsigned)pb[vv] << 16); R.z[slot][lane] = zb[vv]; R.y[slot][lane] = reload(vv); R.e[slot][lane] = 0.f;
+          reloaded = true;
+        }
+        const unsigned vp = R.vp[slot][lane];
+        vt = vp & 0xFFFF; pt = vp >> 16; ytf = R.y[slot][lane]; yt = (double)ytf; zt = R.z[slot][lane]; et = R.e[slot][lane];
+        if (reloaded && k > 0) { zt = exact_top(); R.z[slot][lane] = zt; }   // the backing store keeps no bound: recompute the break point
+        const int dd = q - vt;
+        bool certain = false;
+        if (dd < kRcp) {
+          const float tt = fmul_r(fsub_r(yqf, ytf), (float)ld_table(f.Rcp, dd)), m = fadd_r(0.5f * (float)(q + vt), cb);
+          s = fadd_r(tt, m);
+          es = fmul_r(fadd_r(fadd_r(fabsf(tt), fabsf(m)), acb), kEps);
+          certain = floor_is_certain(s, es) && (k == 0 || fabsf(fsub_r(s, zt)) > fadd_r(es, et));
+        }
+        if (!certain) {
+          PBD_ENV_STAT(exact)
+          s = isect_far(f, vt, q, yt, yq); es = 0.f;
+          if (k > 0 && et > 0.f && !(fabsf(fsub_r(s, zt)) > et)) { zt = exact_top(); et = 0.f; R.z[slot][lane] = zt; R.e[slot][lane] = 0.f; }
+        }
+      } while (s <= zt && k > 0);
+      lo = imax(imin(f2i_floor(zt), pos_last) + 1, os0);
+      e0 = ld_table(f.E, lo - vt); e1 = ld_table(f.E, lo - vt + 1);
+    }
+    const int hi = imin(f2i_floor(s), pos_last);
+    emit_run(lo, hi, vt, yt, e0, e1);                             // the top's positions up to the new break point
+    ++k;
+    base = imax(base, k - (kRing - 1));                           // the slot of depth k - kRing is overwritten
+    const int slot = k & (kRing - 1);
+    R.vp[slot][lane] = (unsigned)q | ((unsigned)vt << 16); R.y[slot][lane] = yqf; R.z[slot][lane] = s; R.e[slot][lane] = es;
+    zb[q] = s; pb[q] = (unsigned short)vt;
+    pt = vt; vt = q; ytf = yqf; yt = yq; zt = s; et = es;
+    lo = imax(hi + 1, os0);                                       // = max(min(floor(s), pos_last) + 1, os0)
+    e0 = ld_table(f.E, lo - q); e1 = ld_table(f.E, lo - q + 1);
+  }
+  emit_run(lo, pos_last, vt, yt, e0, e1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // Lagged-scan variant (an experiment for the next round; not used by dt_pass yet).  Same stack construction as envelope_stream,
 // but instead of emitting the top's whole range when its successor is pushed (and again after every pop), every step emits exactly
 // the positions up to q - LAG through a cursor that walks up the stack: in steady state ONE position per lane per step, the same

@@ -69,7 +69,8 @@ class Engine {
   // > 0: root-map non-maxima suppression with this window before the backtrack (reference src/nms.cpp, the call commented out at
   // src/PartsBasedDetector.cpp:86); 0 (default): every root cell above the threshold is a candidate, as the reference's detect()
   int root_nms = 0;
-  // 1: the distance-transform passes emit through the lagged scan (one store per position) instead of eagerly (dt.cu)
+  // dt_pass variant: 0 eager emission with double break points (default), 1 eager emission with certified fp32 break points (12 %
+  // slower on B200), 2 lagged-scan emission (15 % slower on real score maps, 6.8x faster on white noise); results are identical
   int dt_scan = 0;
   static constexpr int kMinFramesPerDpGroup = 4;
 

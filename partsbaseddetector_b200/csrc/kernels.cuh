@@ -181,7 +181,7 @@ int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
                    cudaStream_t s, void (*mark)(void*, int) = nullptr, void* mark_ctx = nullptr,   // mark(ctx, kernel id) after each kernel
-                   int scan = 0);                                                              // 1: lagged-scan emission in dt_pass
+                   int scan = 0);                       // dt_pass variant: 0 double break points (default), 1 certified fp32 break points, 2 lagged-scan emission
 int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const RootJob* d_roots, int ncomp, int nfilters, int nwork,
                 cudaStream_t s);
 

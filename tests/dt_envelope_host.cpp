@@ -5,6 +5,7 @@
 
 // per-step loop statistics of the lock-step (warp) execution model: see envh_stats below
 static thread_local int g_stat_pop = 0, g_stat_adv = 0;
+static thread_local long long g_stat_exact = 0;
 #define PBD_ENV_STAT(name) ++g_stat_##name;
 #include "../partsbaseddetector_b200/csrc/dt_envelope.cuh"
 
@@ -16,7 +17,8 @@ extern "C" {
 // (dt_table_len / dt_table_bias of kernels.cuh).  dst/ptr are written [line][pos - os]; every position not stored stays
 // at the caller's fill value.  *stores (optional) counts the emit calls.
 // window = 0: emissions go straight to dst/ptr; window = 1: through the write-back window (OutWindow<8, 5>);
-// window = 2 / 3 / 4: the lagged-scan variant envelope_scan with LAG = 4 / 1 / 12
+// window = 2 / 3 / 4: the lagged-scan variant envelope_scan with LAG = 4 / 1 / 12; window = 5: envelope_stream_cert (certified fp32
+// break points, option dt_variant 1); *stores then also receives, in stores[1], the number of intersections that took the double path
 int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int os, int maxn, float* dst, uint16_t* ptr, long long* stores,
               int window) {
   if (N < 1 || N > maxn || nlines < 1 || nlines > 32) return -1;
@@ -27,9 +29,11 @@ int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int 
   for (int j = 0; j < kRcp; ++j) tab[ne + j] = table_rcp(a, j);
   const Quad f = make_quad(w_sq, w_lin, tab.data() + bias, tab.data() + ne);
   Ring R;
+  RingE RE;
   std::vector<float> zb(N);
   std::vector<unsigned short> pb(N);
   long long n = 0;
+  g_stat_exact = 0;
   for (int lane = 0; lane < nlines; ++lane) {
     const float* s = src + (size_t)lane * N;
     float* d = dst + (size_t)lane * N;
@@ -38,7 +42,10 @@ int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int 
       if (i < 0 || i >= N) __builtin_trap();
       d[i] = val; p[i] = v; ++n;
     };
-    if (window >= 2) {
+    if (window == 5) {
+      auto ld = [&](int q) { return s[q]; };
+      envelope_stream_cert(N, f, os, RE, lane, zb.data(), pb.data(), ld, ld, [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
+    } else if (window >= 2) {
       auto ld = [&](int q) { return s[q]; };
       auto em = [&](int i, float val, int v) { store(i, val, (unsigned short)v); };
       if (window == 2) envelope_scan<4>(N, f, os, R, lane, zb.data(), pb.data(), ld, ld, em);
@@ -57,7 +64,7 @@ int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int 
       win.finish(store);
     }
   }
-  if (stores) *stores = n;
+  if (stores) { stores[0] = n; if (window == 5) stores[1] = g_stat_exact; }
   return 0;
 }
 // Loop iterations per (line, sample step) of one variant (0 = eager envelope_stream, 2 = envelope_scan<4>): pops, emissions and cursor

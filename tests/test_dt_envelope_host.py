@@ -43,17 +43,19 @@ def run_both(src, w_sq, w_lin, os_, maxn=None):
     maxn = maxn or N
     L = oracle_lib.lib()
     counts = []
-    for window in (0, 1, 2, 3, 4):                 # direct, write-back window, lagged scan with LAG = 4 / 1 / 12
+    for window in (0, 1, 2, 3, 4, 5):              # direct, write-back window, lagged scan with LAG = 4 / 1 / 12, certified fp32 break points
         dst = np.full((nl, N), np.nan, np.float32)
         ptr = np.full((nl, N), 0xFFFF, np.uint16)
-        stores = C.c_longlong(0)
-        assert envlib().envh_dt1d(np.ascontiguousarray(src), nl, N, w_sq, w_lin, os_, maxn, dst, ptr, C.byref(stores), window) == 0
+        stores = (C.c_longlong * 2)(0, 0)
+        assert envlib().envh_dt1d(np.ascontiguousarray(src), nl, N, w_sq, w_lin, os_, maxn, dst, ptr, stores, window) == 0
         for i in range(nl):
             rd, rp = np.empty(N, np.float32), np.empty(N, np.int32)
             L.orc_dt1d_f32(np.ascontiguousarray(src[i]), N, -float(np.float32(w_sq)), -float(np.float32(w_lin)), os_, rd, rp)
             assert np.array_equal(dst[i], rd), (window, i, N, os_)
             assert np.array_equal(ptr[i].astype(np.int32), rp), (window, i, N, os_)
-        counts.append(stores.value)
+        counts.append(stores[0])
+        if window == 5:
+            run_both.exact = stores[1]
     # the parallel-in-q schedule of the same algorithm (prototype for the next kernel generation)
     dst = np.full((nl, N), np.nan, np.float32)
     ptr = np.full((nl, N), 0xFFFF, np.uint16)
@@ -128,6 +130,22 @@ def test_eager_emission_store_overhead_is_small():
     assert 32 * 158 <= n <= 3 * 32 * 158
     x = np.tile(np.linspace(1, 0, 158, dtype=np.float32) ** 2, (4, 1))      # smooth and monotone: no pops, exactly one store per position
     assert run_both(x, 0.012, 0.0, 0) == 4 * 158
+
+
+def test_certified_fp32_break_points_fall_back_when_they_must():
+    """envelope_stream_cert: on score-map-like inputs the double path is the exception; with huge magnitudes nothing can be certified
+    a large share of the intersections is the reference's double expression; dyadic inputs put break points exactly on integers."""
+    rng = np.random.default_rng(29)
+    x = gen(rng, "smooth", 32, 158)
+    run_both(x, 0.012, 0.005, 1)
+    assert run_both.exact < 0.02 * x.size
+    small = run_both.exact
+    run_both(x * 3e4, 0.012, 0.005, 1)                            # the bound grows with the magnitudes: many more fall back
+    assert run_both.exact > 10 * max(small, 1)
+    run_both((np.round(x * 8) / 8).astype(np.float32), 0.0625, 0.0, 0)
+    assert run_both.exact > 0
+    run_both(gen(rng, "spikes", 8, 500), 0.03125, 0.25, -2)       # deep pops through the backing store: entries recomputed exactly
+    run_both(gen(rng, "convex", 8, 300), 0.02, -0.01, 3)
 
 
 def test_markstein_quotient_equals_exact_division():

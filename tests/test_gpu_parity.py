@@ -22,7 +22,7 @@ def detector(name):
         d.distributeModel(Model.load_bin(os.path.join(GOLDEN, name + ".pbdm")))
         _det_cache[name] = d
     d = _det_cache[name]
-    for k, v in (("exact", 1), ("backptr", 0), ("max_levels", 0), ("thresh", load_flat(name).thresh)):
+    for k, v in (("exact", 1), ("backptr", 0), ("max_levels", 0), ("thresh", load_flat(name).thresh), ("dt_variant", 0), ("root_nms", 0), ("graph", 0)):
         d.set_option(k, v)
     return d
 
@@ -368,6 +368,26 @@ def test_determinism_and_stage_api_equivalence():
     d.min()
     c = d.argmin()
     assert [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m)) for k in a] == [(k.frame, k.level, tuple(k.x), tuple(k.y), tuple(k.m)) for k in c]
+
+
+def test_dt_kernel_variants_give_identical_results():
+    """option dt_variant: 0 = every break point in double (default), 1 = certified fp32 break points, 2 = lagged-scan
+    emission: root maps, back-pointers and candidates are the same bits (and equal the oracle's, tested elsewhere for the default)."""
+    img = np.stack([synth_frame(900 + i, 150, 210) for i in range(3)])
+    img[2, 40:90, 30:120] = 17                                   # a flat patch: exact ties between break points
+    outs = []
+    for variant in (0, 1, 2):
+        d = detector("Person_26parts")
+        d.set_option("dt_variant", variant)
+        d.set_option("thresh", -1.25)
+        c = d.detect(img)
+        maps = [d.rootv(f, l) for f in range(3) for l in range(d.nscales())] + [np.stack(d.backptr(2, 0, 0, p, 1)) for p in (1, 7, 25)]
+        outs.append((maps, [(a.frame, a.level, a.x.tolist(), a.y.tolist(), a.m.tolist(), float(a.score())) for a in c]))
+        d.set_option("dt_variant", 0)                            # the helper's detectors are shared between tests
+    assert len(outs[0][1]) > 20
+    for other in outs[1:]:
+        assert other[1] == outs[0][1]
+        assert all(np.array_equal(a, b) for a, b in zip(other[0], outs[0][0]))
 
 
 def test_cuda_graph_replay_equals_eager_launches():
