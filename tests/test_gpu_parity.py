@@ -236,6 +236,41 @@ def test_committed_golden_vectors():
     assert np.array_equal(np.array([c.parts() for c in cands], np.int32), g["p26_cand_rects"])
 
 
+def test_cuda_path_equals_vectors_from_the_reference_sources():
+    """tests/golden/ref_golden.npz holds outputs of the reference's OWN compiled sources (HOGFeatures.cpp, DistanceTransform.hpp,
+    DynamicProgram.cpp, nms.cpp through oracle/_ref; generator: tests/golden/make_golden.py).  The CUDA path reproduces them bit for bit:
+    HOG pyramid features and scales, 2-D distance transforms, DP root maps / back-pointers / candidates, root-map NMS."""
+    g = np.load(os.path.join(GOLDEN, "ref_golden.npz"))
+    fm = load_flat("Person_26parts")
+    d = detector("Person_26parts")
+    d.pyramid(synth_frame(11, 120, 160))
+    assert d.nscales() == int(g["hog_nlevels"])
+    for l in range(d.nscales()):
+        assert np.array_equal(d.features(0, l), g["hog_feat%d" % l]) and d.level_info(l)["scale"] == g["hog_scales"][l]
+    out, ix, iy = dt2d(g["dt_in"], g["dt_defw"], g["dt_anchor"], 0)
+    assert np.array_equal(out, g["dt_out"]) and np.array_equal(ix, g["dt_ix"]) and np.array_equal(iy, g["dt_iy"])
+    ohow = [tuple(int(v) for v in r) for r in g["dp_ohow"]]
+    thr = float(g["dp_thresh"])
+    d.set_levels(1, ohow, g["dp_scales"])
+    for l, shp in enumerate(ohow):
+        for f in range(fm.nfilters()):
+            d.set_response(0, l, f, (np.random.default_rng(1000 * l + f).standard_normal(shp) * 0.3).astype(np.float32))
+    d.set_option("thresh", thr)
+    d.min()
+    for l in range(2):
+        assert np.array_equal(d.rootv(0, l), g["dp_rootv%d" % l]) and np.array_equal(d.rooti(0, l), g["dp_rooti%d" % l])
+    for (p, pm) in ((1, 0), (3, 2), (14, 4), (25, 1)):
+        assert np.array_equal(np.stack(d.backptr(0, 0, 0, p, pm)), g["dp_bp_p%d_m%d" % (p, pm)])
+    cands = sorted(d.argmin(), key=lambda c: (float(c.score()), np.ascontiguousarray(c.parts(), np.int32).tobytes()))
+    assert np.array_equal(np.stack([c.parts() for c in cands]), g["dp_cand_rects"])
+    assert np.array_equal(np.array([c.score() for c in cands], np.float32), g["dp_cand_scores"])
+    d.set_option("root_nms", 2)
+    kept = [c for c in d.argmin() if c.level == 0]
+    mask = (g["dp_rootv0"] > np.float32(thr)) & (g["dp_rootnms2_level0"] > 0)
+    assert len(kept) == int(mask.sum()) > 0 and all(mask[c.y[0], c.x[0]] for c in kept)
+    d.set_option("root_nms", 0)
+
+
 def test_fast_mode_integer_outputs_and_score_tolerance():
     # fused multiply-add responses: scores within 1e-4 relative (north_star), integer outputs expected identical
     name = "Person_26parts"

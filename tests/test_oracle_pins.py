@@ -311,3 +311,41 @@ def test_oracle_thread_count_invariance():
                 "print(hashlib.sha256(b''.join(D.rootv(l).tobytes() for l in range(D.nlevels()))).hexdigest())")
         res.append(subprocess.check_output([sys.executable, "-c", code], cwd=os.path.dirname(GOLDEN) + "/..", env=dict(os.environ)).strip())
     assert res[0] == res[1]
+
+
+def test_oracle_equals_vectors_from_the_reference_sources():
+    """tests/golden/ref_golden.npz was produced by the reference's own compiled sources (tests/golden/make_golden.py through
+    oracle/_ref): the oracle reproduces it bit for bit -- also where /root/reference and oracle/_ref do not exist."""
+    import os
+    from conftest import GOLDEN, load_flat
+    g = np.load(os.path.join(GOLDEN, "ref_golden.npz"))
+    fm = load_flat("Person_26parts")
+    O = oracle_lib.OracleDetector(fm, 32)
+    O.run(synth_frame(11, 120, 160), 1, 1)
+    assert O.nlevels() == int(g["hog_nlevels"])
+    for l in range(O.nlevels()):
+        assert np.array_equal(O.features(l), g["hog_feat%d" % l]) and O.level_info(l)["scale"] == g["hog_scales"][l]
+    L = oracle_lib.lib()
+    for i in range(4):
+        m = np.ascontiguousarray(g["dt_in"][i])
+        o, x, y = np.empty_like(m), np.empty(m.shape, np.int32), np.empty(m.shape, np.int32)
+        L.orc_dt2d_f32(m.reshape(-1), m.shape[0], m.shape[1], np.ascontiguousarray(g["dt_defw"][i]), int(g["dt_anchor"][i, 0]), int(g["dt_anchor"][i, 1]), 0,
+                       o.reshape(-1), x.reshape(-1), y.reshape(-1))
+        assert np.array_equal(o, g["dt_out"][i]) and np.array_equal(x, g["dt_ix"][i]) and np.array_equal(y, g["dt_iy"][i])
+    ohow = [tuple(int(v) for v in r) for r in g["dp_ohow"]]
+    O.set_levels(ohow, g["dp_scales"])
+    for l, shp in enumerate(ohow):
+        for f in range(fm.nfilters()):
+            O.set_response(l, f, (np.random.default_rng(1000 * l + f).standard_normal(shp) * 0.3).astype(np.float32))
+    O.set_thresh(float(g["dp_thresh"]))
+    O.run(None, 3, 4)
+    for l in range(2):
+        assert np.array_equal(O.rootv(l), g["dp_rootv%d" % l]) and np.array_equal(O.rooti(l), g["dp_rooti%d" % l])
+    for (p, pm) in ((1, 0), (3, 2), (14, 4), (25, 1)):
+        assert np.array_equal(np.stack(O.backptr(0, 0, p, pm)), g["dp_bp_p%d_m%d" % (p, pm)])
+    oc = sorted(O.candidates(), key=lambda o: (float(o["score"]), o["rects"].astype(np.int32).tobytes()))
+    assert np.array_equal(np.stack([o["rects"] for o in oc]), g["dp_cand_rects"])
+    assert np.array_equal(np.array([o["score"] for o in oc], np.float32), g["dp_cand_scores"])
+    keep = np.empty(ohow[0], np.uint8)
+    L.orc_rootmap_nms(np.ascontiguousarray(g["dp_rootv0"]).reshape(-1), ohow[0][0], ohow[0][1], 2, None, keep.reshape(-1))
+    assert np.array_equal(keep, g["dp_rootnms2_level0"])
