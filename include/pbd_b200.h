@@ -94,12 +94,13 @@ void pbd_destroy(pbd_detector* d);
  *                 0 (default): separately rounded multiply/add in the reference's summation order => bit-identical scores;
  *                 1: fused multiply-add on the FP32 pipes (scores differ in the last ulps);
  *                 2: 5th-generation tensor cores (tcgen05, tf32x3 split products with fp32 accumulation; scores within ~4e-7
- *                    relative of the reference, integer outputs identical on every test frame; 8x faster than mode 0).
+ *                    relative of the reference; over 256 frames 42 517 of 42 518 candidates identical to the reference's, one on the
+ *                    other side of the threshold; 8x faster than mode 0).
  *                 3: the same three split products as tcgen05 kind::f16 MMAs: the fp32 operands are pre-scaled by powers of two (features
  *                    2^12, each filter so that its largest weight lies in [2^13, 2^14)) and split into fp16 hi + fp16 residual -- the same
  *                    11 + 11 significand bits as the tf32 split -- which halves the MMAs and the operand bytes; the same accuracy and
  *                    parity tests as mode 2, 1.4x faster.  Features must stay below 16 in magnitude (HOG features are <= 1).
- *                    Models with non-uniform filter sizes fall back to mode 1 (modes 2 and 3).
+ *                    Models with non-uniform filter sizes run the bit-exact kernel of mode 0 instead (modes 2 and 3).
  *   "exact"       alias kept for compatibility: 1 = response_mode 0, 0 = response_mode 1
  *   "tc_taps_per_partial"  response_mode 2: 0 (default) sums the hi*hi products of one filter row on the tensor core before the
  *                 fp32 round-to-nearest summation (score bias ~4 ulp), 1 sums tap by tap (bias < 1 ulp, 25 % slower)
@@ -119,7 +120,10 @@ void pbd_destroy(pbd_detector* d);
  *                 other's work; results do not depend on it.  Batches under 8 frames and timing == 2 use one stream.
  * Environment defaults read at pbd_create: PBD_EXACT=0|1, PBD_RESPONSE_MODE=exact|ffma|tensor|tensor16, PBD_BACKPTR=reference|exact,
  * PBD_MAX_LEVELS=n, PBD_DP_STREAMS=n.  Further keys: "graph" (1: CUDA-graph replay of pbd_enqueue_batch_u8_device), "root_nms" (window
- * sz > 0: root-map non-maxima suppression of src/nms.cpp before the backtrack; 0 = off, the reference's detect()). */
+ * sz > 0: root-map non-maxima suppression of src/nms.cpp before the backtrack; 0 = off, the reference's detect()), "dt_variant" (0 / 1 / 2:
+ * the distance-transform kernel flavour, identical results).  Response modes 2 / 3 need a bank of equally sized square filters; for any
+ * other model they run the bit-exact FP32 kernel (mode 0).  pbd_get_option("response_kernel") tells which kernel the last pdf stage
+ * ran: 0 generic exact, 1 tiled exact, 3 tensor tf32x3, 4 tensor fp16x3, 5 generic FFMA, 6 tiled FFMA. */
 int pbd_set_option(pbd_detector* d, const char* key, double value);
 int pbd_get_option(const pbd_detector* d, const char* key, double* value);
 

@@ -224,6 +224,7 @@ int pbd_get_option(const pbd_detector* d, const char* key, double* value) {
     else if (k == "timing") *value = e.timing;
     else if (k == "dp_streams") *value = e.dp_streams;
     else if (k == "graph") *value = e.use_graph;
+    else if (k == "response_kernel") *value = e.last_response_kernel;
     else if (k == "dt_variant") *value = e.dt_scan;
     else if (k == "root_nms") *value = e.root_nms;
     else if (k == "nms_overlap") *value = e.nms_overlap;

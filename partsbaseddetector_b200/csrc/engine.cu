@@ -691,12 +691,17 @@ void Engine::run_pdf() {
       launches_ += launch_response_tc(g_, b_, fb_, d_fhi_, d_flo_, d_wtc_, d_tc_levels_, d_tc_tiles_, tc_ntiles_, tc_frame_rows_, num_sms_, tc_taps_per_partial, stream_);
     kmark(1);
     check_cuda(cudaGetLastError(), "tensor response launch");
+    last_response_kernel = f16 ? 4 : 3;
     stage_ = 3;
     return;
   }
   if (timing) { check_cuda(cudaEventRecord(ev_[3], stream_), "event"); ev_valid_[3] = true; }
   kev_n_ = 0; kmark(-1);
-  launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles_, resp_mode == 0 ? 1 : 0, feat_from_hog_ ? 1 : 0, stream_);
+  // a tensor mode the filter bank does not qualify for (filters of different sizes) falls back to the bit-exact FP32 kernel, never to
+  // a third arithmetic: only response mode 1 asks for fused multiply-adds
+  const int exact = resp_mode != 1 ? 1 : 0;
+  launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles_, exact, feat_from_hog_ ? 1 : 0, stream_);
+  last_response_kernel = (response_has_fast_path(fb_) ? 1 : 0) + (exact ? 0 : 5);
   kmark(1);
   check_cuda(cudaGetLastError(), "response launch");
   stage_ = 3;

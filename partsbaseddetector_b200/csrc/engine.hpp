@@ -55,7 +55,7 @@ class Engine {
   // options
   double thresh;
   // resp_mode: 0 exact (separately rounded multiply/add in the reference's order, bit-identical scores), 1 fused multiply-add,
-  // 2 tensor cores (tf32x3 split products, fp32 accumulate; falls back to 1 for models the tensor kernel does not cover),
+  // 2 tensor cores (tf32x3 split products, fp32 accumulate; models the tensor kernel does not cover run the bit-exact kernel of mode 0),
   // 3 tensor cores with fp16 split operands (the same 11 + 11 significand bits, power-of-two pre-scaling; half the MMAs of mode 2)
   int resp_mode = 0, tc_taps_per_partial = 0, backptr = 0, max_levels = 0, max_candidates = 65536, timing = 0;
   // the DP stage runs the batch as this many groups of frames on concurrent streams (1 = single stream)
@@ -69,6 +69,9 @@ class Engine {
   // > 0: root-map non-maxima suppression with this window before the backtrack (reference src/nms.cpp, the call commented out at
   // src/PartsBasedDetector.cpp:86); 0 (default): every root cell above the threshold is a candidate, as the reference's detect()
   int root_nms = 0;
+  // which response kernel the last pdf stage ran: 0 generic exact (filters of different sizes), 1 tiled exact, 3 tensor tf32x3, 4 tensor
+  // fp16x3, 5 generic FFMA, 6 tiled FFMA (read-only, option "response_kernel")
+  int last_response_kernel = -1;
   // dt_pass variant: 0 eager emission with double break points (default), 1 eager emission with certified fp32 break points (12 %
   // slower on B200), 2 lagged-scan emission (15 % slower on real score maps, 6.8x faster on white noise); results are identical
   int dt_scan = 0;

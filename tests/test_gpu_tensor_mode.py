@@ -156,3 +156,26 @@ def test_flat_frames_keep_exact_ties(mode):
         assert len(cands) == len(oc)
         for g, o in zip(cands, oc):
             assert g.level == o["level"] and np.array_equal(g.x, o["x"]) and np.array_equal(g.y, o["y"]) and np.array_equal(g.m, o["m"])
+
+
+def test_which_response_kernel_ran_and_the_fallback_is_exact():
+    """Uniform square banks run the tensor kernels in response modes 2 / 3; a bank with filters of different sizes (Person_8parts: 4x11,
+    7x11, 11x7 roots + 6x6 parts) cannot -- it then runs the bit-exact generic kernel (never a third arithmetic), and says so."""
+    import oracle_lib
+    from conftest import golden_model_path, load_flat
+    from partsbaseddetector_b200 import Model, PartsBasedDetector
+    from partsbaseddetector_b200.synth import synth_frame
+    img = synth_frame(41, 200, 260)
+    for name, want in (("Person_26parts", {0: 1, 1: 6, 2: 3, 3: 4}), ("Person_8parts", {0: 0, 1: 5, 2: 0, 3: 0})):
+        d = PartsBasedDetector()
+        d.distributeModel(Model.load_bin(golden_model_path(name)))
+        d.set_option("thresh", 1e9)
+        O = oracle_lib.OracleDetector(load_flat(name), 32)
+        O.run(img, 1, 3)
+        for mode, kern in want.items():
+            d.set_option("response_mode", mode)
+            d.detect(img)
+            assert int(d.get_option("response_kernel")) == kern, (name, mode)
+            if kern in (0, 1):                                   # the exact kernels: bit-identical root scores
+                assert all(np.array_equal(d.rootv(0, l, c), O.rootv(l, c)) for l in range(O.nlevels()) for c in range(len(load_flat(name).comps)))
+        d.close()

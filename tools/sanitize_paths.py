@@ -22,4 +22,40 @@ for mode in (3, 2):
         counts.append(len(det.collect_ticket(det.submit(frames))))
 print("candidates per run:", counts)
 assert counts[0] == counts[1] and counts[2] == counts[3] and counts[2] <= counts[0]
+# round 2: exact mode with the root-map NMS epilogue, the three dt_pass variants, CUDA-graph replay, the standalone transform through its
+# three kernel generations (streaming / parallel-in-q / lagged scan) and the level-0-in-place HOG path on a grey frame
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from partsbaseddetector_b200 import Dt2dPlan  # noqa: E402
+det.set_option("response_mode", 0)
+det.set_option("nms_overlap", -1.0)
+base = len(det.detect(frames))
+for v in (1, 2, 0):
+    det.set_option("dt_variant", v)
+    assert len(det.detect(frames)) == base
+det.set_option("root_nms", 2)
+assert 0 < len(det.detect(frames)) < base
+det.set_option("root_nms", 0)
+dev = torch.from_numpy(frames).cuda()
+det.set_option("graph", 1)
+for _ in range(3):
+    det.enqueue_device(dev.data_ptr(), 8, 120, 168, 3)
+    assert len(det.collect()) == base
+det.set_option("graph", 0)
+assert len(det.detect(np.ascontiguousarray(frames[:2, :, :, 1]))) >= 0
+rng = np.random.default_rng(3)
+for (h, w) in ((37, 53), (70, 300)):
+    maps = torch.from_numpy(rng.standard_normal((5, h, w)).astype(np.float32)).cuda()
+    outs = []
+    for impl in (1, 2, 3):
+        plan = Dt2dPlan(5, h, w, [0.02, 0.01, 0.015, -0.01], [2, -3], impl)
+        o = torch.empty_like(maps)
+        ix = torch.empty((5, h, w), dtype=torch.int16, device="cuda")
+        iy = torch.empty_like(ix)
+        plan.run(maps.data_ptr(), o.data_ptr(), ix.data_ptr(), iy.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append((o.cpu(), ix.cpu(), iy.cpu()))
+        plan.close()
+    assert all(torch.equal(a, b) for other in outs[1:] for a, b in zip(other, outs[0]))
+print("round-2 paths ok")
 det.close()
