@@ -158,6 +158,53 @@ def test_flat_frames_keep_exact_ties(mode):
             assert g.level == o["level"] and np.array_equal(g.x, o["x"]) and np.array_equal(g.y, o["y"]) and np.array_equal(g.m, o["m"])
 
 
+def _compare_candidates(d, O, img, keep):
+    """Candidates of the tensor path against the oracle's at a threshold in the middle of a gap between neighbouring root scores; returns
+    (candidates, differing) where differing counts one-sided candidates and integer-output mismatches."""
+    O.run(img, 1, 3)
+    rv_all = np.sort(np.concatenate([O.rootv(l, c).ravel() for l in range(O.nlevels()) for c in range(len(O.model.comps))]))
+    k = rv_all.size - keep
+    thr = float(0.5 * (float(rv_all[k - 1]) + float(rv_all[k])))
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    d.set_option("thresh", thr)
+    key = lambda lv, c, x, y: (int(lv), int(c), int(x[0]), int(y[0]))
+    oc = {key(o["level"], o["component"], o["x"], o["y"]): o for o in O.candidates()}
+    gc = {key(g.level, g.component(), g.x, g.y): g for g in d.detect(img)}
+    bad = len(set(oc) ^ set(gc))
+    for kk in set(oc) & set(gc):
+        o, g = oc[kk], gc[kk]
+        if not (np.array_equal(g.x, o["x"]) and np.array_equal(g.y, o["y"]) and np.array_equal(g.m, o["m"]) and np.array_equal(g.parts(), o["rects"])):
+            bad += 1
+        assert abs(float(g.score()) - float(o["score"])) <= SCORE_TOL * abs(float(o["score"]))
+    return len(oc), bad
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_config4_1080p_ten_levels_tensor_modes(mode):
+    """BASELINE config 4 in the tensor modes: 1920x1080, first 10 levels (340 400 cells), candidates against the oracle."""
+    name = "Person_26parts"
+    img = synth_frame(404, 1080, 1920)
+    d, O = detector(name, 0, mode), oracle(name)
+    d.set_option("max_levels", 10)
+    O.set_max_levels(10)
+    n, bad = _compare_candidates(d, O, img, 300)
+    assert int(d.get_option("response_kernel")) == (3 if mode == 2 else 4)
+    assert d.nscales() == 10 and n == 300 and bad == 0
+    d.set_option("max_levels", 0)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_face_model_end_to_end_tensor_modes(mode):
+    """Face_99filters (13 components of 39 / 68 single-mixture parts, interval 10: 36 levels at QVGA) end to end in the tensor modes."""
+    name = "Face_99filters"
+    img = synth_frame(77, 240, 320)
+    d, O = detector(name, 0, mode), oracle(name)
+    n, bad = _compare_candidates(d, O, img, 200)
+    assert int(d.get_option("response_kernel")) == (3 if mode == 2 else 4)
+    assert n == 200 and bad == 0
+
+
 def test_which_response_kernel_ran_and_the_fallback_is_exact():
     """Uniform square banks run the tensor kernels in response modes 2 / 3; a bank with filters of different sizes (Person_8parts: 4x11,
     7x11, 11x7 roots + 6x6 parts) cannot -- it then runs the bit-exact generic kernel (never a third arithmetic), and says so."""
