@@ -578,7 +578,10 @@ int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int
     *out = P.release();
   });
 }
-void pbd_dt2d_plan_destroy(pbd_dt2d_plan* p) { delete p; }
+void pbd_dt2d_plan_destroy(pbd_dt2d_plan* p) {
+  if (!p) return;
+  try { DeviceGuard dg_(p->device); delete p; } catch (...) { delete p; }   // the plan's buffers live on the device it was created on
+}
 int pbd_dt2d_plan_impl(const pbd_dt2d_plan* p) { return p ? p->impl : 0; }
 
 // enqueue only (no allocation, no synchronisation): rows pass, columns pass, back-pointer composition
@@ -586,6 +589,7 @@ int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* 
   return guarded([&] {
     REQUIRE(p && d_in && d_out && d_ix && d_iy, "null argument");
     REQUIRE(backptr_mode == 0 || backptr_mode == 1, "backptr_mode must be 0 or 1");
+    DeviceGuard dg_(p->device);
     cudaStream_t s = (cudaStream_t)stream;
     if (p->impl != 2) {
       launch_dt2d_standalone(d_in, p->n_maps, p->h, p->w, p->geom.as<PassGeom>(), p->maps.as<PassMap>(), p->tmp.as<float>(), d_out, d_ix, d_iy,

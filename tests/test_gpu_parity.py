@@ -271,6 +271,38 @@ def test_cuda_path_equals_vectors_from_the_reference_sources():
     d.set_option("root_nms", 0)
 
 
+def test_cuda_stages_feed_the_reference_dynamic_program():
+    """Mixed pipeline, as a host that swaps single stages would run it: image pyramid + HOG + part responses on the GPU (the IFeatures /
+    IConvolutionEngine stages), then the REFERENCE'S OWN DynamicProgram<float>::min / argmin (src/DynamicProgram.cpp compiled unmodified
+    in oracle/_ref) on those responses.  Its root maps, back-pointers and candidates equal the all-CUDA path's bit for bit."""
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref/libpbd_ref.so not built")
+    fm = load_flat("Person_26parts")
+    d = detector("Person_26parts")
+    img = synth_frame(123, 120, 160)
+    d.set_option("thresh", 1e9)
+    d.detect(img)
+    nl = d.nscales()
+    rv = np.sort(np.concatenate([d.rootv(0, l).ravel() for l in range(nl)]))
+    thr = float(0.5 * (float(rv[-41]) + float(rv[-40])))
+    d.set_option("thresh", thr)
+    cands = d.detect(img)
+    R = ref_lib.RefDP(fm, 32)
+    R.set_levels([(d.level_info(l)["oh"], d.level_info(l)["ow"]) for l in range(nl)], np.array(d.scales(), np.float32))
+    for l in range(nl):
+        for f in range(fm.nfilters()):
+            R.set_response(l, f, d.response(0, l, f))
+    assert R.run(thr) == len(cands) == 40
+    for l in range(nl):
+        v, i = R.root(l)
+        assert np.array_equal(v.astype(np.float32), d.rootv(0, l)) and np.array_equal(i, d.rooti(0, l))
+    for (p, pm) in ((2, 3), (13, 0), (25, 4)):
+        assert all(np.array_equal(a, b) for a, b in zip(R.backptr(0, 0, p, pm), d.backptr(0, 0, 0, p, pm)))
+    key = lambda rects, score: (float(score), np.ascontiguousarray(rects, np.int32).tobytes())
+    assert sorted(key(r, c[0]) for _, r, c in R.candidates()) == sorted(key(c.parts(), c.score()) for c in cands)
+
+
 def test_fast_mode_integer_outputs_and_score_tolerance():
     # fused multiply-add responses: scores within 1e-4 relative (north_star), integer outputs expected identical
     name = "Person_26parts"
