@@ -28,6 +28,7 @@
 #include "kernels.cuh"
 #include "dt_envelope.cuh"
 #include "dt_lines.cuh"
+#include "dt_window.cuh"
 
 namespace pbd {
 namespace {
@@ -167,6 +168,140 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
   win.finish(store);
 #endif
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dt_variant 3: the same pass (same lane = line packing, same staging, same transposed output) with the WINDOWED CERTIFIED evaluation
+// of dt_window.cuh instead of the stack: a lane walks along its line keeping the last 2W+1 samples in a 16-slot circular register
+// window; the position whose window has just been completed, q = s - os - W, is decided by tier 1 (2W+1 adds, a NaN-propagating max
+// tree, 2W+1 compare-and-count) or the rare tier 2, its value formed with the reference's double add, and stored.  No data-dependent
+// control flow, all lanes busy.  A lane whose line cannot be certified somewhere (near-tie against a rounded break point, arg-max at
+// the window's edge, NaN / inf sample, map not eligible) replays the line afterwards with the literal stack algorithm
+// (env::envelope_stream, direct global loads) and overwrites its own stores -- same thread, so no ordering question arises.
+// Real score maps: 0.2 % of the lines are replayed (6 % of the warps run the second phase for one or two lanes).
+// ---------------------------------------------------------------------------------------------------
+// tier 2, out of line; the window is re-read from the lane's shared-memory ring (slot0 = slot of candidate 0) so that the hot path
+// never has to materialise it in local memory
+template <int W>
+__device__ __noinline__ int win_pick_exact_slow(const float* __restrict__ myring, int slot0, const dtw::WinParams* __restrict__ wp) {
+  float w[2 * W + 1];
+#pragma unroll
+  for (int j = 0; j <= 2 * W; ++j) w[j] = myring[((slot0 + j) & 15) * 32];
+  return dtw::pick_exact<W>(w, wp->ed, wp->margin1, wp->cmax, wp->ylim);
+}
+
+#ifndef PBD_DTW_MINBLOCKS
+#define PBD_DTW_MINBLOCKS 5       // 102 registers: the 16-slot window, the 2W+1 table values and the 2W+1 candidates stay in registers
+#endif
+template <int MAXN, int W>
+__global__ void __launch_bounds__(kPassWarps * 32, PBD_DTW_MINBLOCKS)
+dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, const dtw::WinParams* __restrict__ wps, int nmaps,
+            const float* __restrict__ inA, size_t strideA, const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out,
+            unsigned short* __restrict__ ptr, size_t stride_ptr, int* __restrict__ counter) {
+  static_assert(2 * W + 1 <= 16, "the circular window has 16 slots");
+  // per warp: the double-buffered input tile (the replay's stack ring reuses it) and the 16-sample ring the winner's sample is re-read from
+  constexpr int kTileFloats = 2 * 32 * (kTileW + 1);
+  static_assert(sizeof(Ring) <= kTileFloats * sizeof(float), "the replay ring must fit the tile buffers");
+  __shared__ __align__(16) float tile_mem[kPassWarps][kTileFloats];
+  __shared__ float ring[kPassWarps][16][32];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float (*tiles)[32][kTileW + 1] = reinterpret_cast<float (*)[32][kTileW + 1]>(tile_mem[wib]);
+  int w = blockIdx.x * kPassWarps + wib;                          // warp index -> (level, first item)
+  int l = 0, nlines = 0, items = 0;
+  for (; l < pg->n_levels; ++l) {
+    nlines = pg->nlines[l];
+    items = nlines * nmaps;
+    const int nw = (items + 31) >> 5;
+    if (w < nw) break;
+    w -= nw;
+  }
+  if (l >= pg->n_levels) return;                                  // warp-uniform
+  const int frame = blockIdx.y;
+  const int N = pg->N[l];
+  const size_t cell_off = (size_t)pg->cell_off[l];
+  const int t0 = w * 32;
+  const bool active = t0 + lane < items;
+  const int t = active ? t0 + lane : t0;                          // inactive lanes shadow the warp's first item
+  const int mi = t / nlines, line = t - mi * nlines;
+  const PassMap M = maps[mi];
+  const dtw::WinParams* wp = wps + mi;
+  const float* src = (M.in_buf ? inB + (size_t)frame * strideB : inA + (size_t)frame * strideA) + M.in_off + cell_off + (size_t)line * N;
+  float* dst = out + (size_t)frame * stride_out + M.out_off + cell_off + line;
+  unsigned short* dp = ptr + (size_t)frame * stride_ptr + M.ptr_off + cell_off + line;
+  const int c_col = lane & (kTileW - 1), c_row0 = lane / kTileW;
+  auto prefetch = [&](int q, int buf) {
+#pragma unroll
+    for (int i = 0; i < 32 * kTileW / 32; ++i) {
+      const int r = c_row0 + i * (32 / kTileW);
+      const float* p = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
+      if (q + c_col < N) cp_async4(&tiles[buf][r][c_col], p + q + c_col);
+    }
+    cp_async_commit();
+  };
+  auto loady = [&](int q) -> float {                              // q = 0, 1, 2, ... in lock step across the warp
+    if ((q & (kTileW - 1)) == 0) {
+      if (q == 0) prefetch(0, 0);
+      cp_async_wait_all();
+      __syncwarp();
+      if (q + kTileW < N) prefetch(q + kTileW, ((q / kTileW) + 1) & 1);
+    }
+    return tiles[(q / kTileW) & 1][lane][q & (kTileW - 1)];
+  };
+  asm volatile("" : "+l"(dst), "+l"(dp));
+  auto store = [&](int i, float val, unsigned short v) {
+    const unsigned off = (unsigned)i * (unsigned)nlines;
+    st_f32(dst, off, val); st_u16(dp, off, v);
+  };
+  const int os = M.os;
+  bool refused = wp->ok == 0;
+  float ef[2 * W + 1];
+#pragma unroll
+  for (int j = 0; j <= 2 * W; ++j) ef[j] = wp->ef[j];
+  const float tau0 = wp->tau0, ylim = wp->ylim;
+  const double* ed = wp->ed;
+  float buf[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) buf[k] = -INFINITY;
+  unsigned mx = 0u;                                               // largest |sample| bit pattern: NaN / inf samples refuse the line
+  float* myring = &ring[wib][0][lane];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) myring[k * 32] = -INFINITY;        // tier 2 reads the window from here: samples before the line's start do not exist
+  const int steps = N + 2 * W;                                    // sample index s = 0 .. N-1, then 2W virtual -inf samples flush the window
+  for (int s0 = 0; s0 < steps; s0 += 16) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int s = s0 + u;
+      if (s < steps) {                                            // warp-uniform
+        float y = -INFINITY;
+        if (s < N) { y = loady(s); mx = max(mx, __float_as_uint(y) & 0x7fffffffu); }
+        buf[u] = y;
+        myring[u * 32] = y;
+        const int q = s - os - W;                                 // the position whose last candidate is sample s
+        if (q >= 0 && q < N) {
+          float c[2 * W + 1];
+#pragma unroll
+          for (int j = 0; j <= 2 * W; ++j) c[j] = __fadd_rn(buf[(u + 16 - 2 * W + j) & 15], ef[j]);
+          int j = dtw::pick<W>(c, tau0, ylim);
+          if (j < 0) j = win_pick_exact_slow<W>(myring, (u + 16 - 2 * W) & 15, wp);
+          if (j >= 0 && !dtw::edge_ok(j, W, q, N)) j = -1;
+          if (j < 0) { refused = true; j = W; }
+          const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
+          store(q, dtw::value_of(__ldg(ed + j), yv), (unsigned short)(s - 2 * W + j));
+        }
+      }
+    }
+  }
+  if (mx >= 0x7f800000u) refused = true;
+  if (!(refused && active)) return;
+  // ---- replay: the reference's stack algorithm for this lane's line ----
+  __syncwarp(__activemask());
+  Ring& R = *reinterpret_cast<Ring*>(tile_mem[wib]);              // the tiles are dead (every lane of the warp has finished its walk)
+  const Quad f = env::make_quad(M.w_sq, M.w_lin, M.etab + M.tab_bias, M.etab + (M.tab_len - kDtRcp));
+  float zb[MAXN];
+  unsigned short pb[MAXN];
+  auto ld = [&](int q) -> float { return __ldg(src + q); };
+  env::envelope_stream(N, f, os, R, lane, zb, pb, ld, ld, [&](int i, float val, int v) { store(i, val, (unsigned short)v); }, [](int) {});
+  if (counter) atomicAdd(counter, 1);
 }
 
 // E[j] = a x^2 + b x for x = j - tab_bias, j in [0, tab_len - kDtRcp): the position-independent part of Quadratic::operator()(x, y);
@@ -476,6 +611,14 @@ static void launch_pass_v(int maxn, dim3 grid, cudaStream_t s, A... args) {
 }
 template <typename... A>
 static void launch_pass(int maxn, dim3 grid, cudaStream_t s, A... args) { launch_pass_v<0>(maxn, grid, s, args...); }
+template <typename... A>
+static void launch_pass_win(int maxn, dim3 grid, cudaStream_t s, A... args) {
+  constexpr int W = kDtWindowW;
+  if (maxn <= 160) dt_pass_win<160, W><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else if (maxn <= 512) dt_pass_win<512, W><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else if (maxn <= 1024) dt_pass_win<1024, W><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else dt_pass_win<4096, W><<<grid, kPassWarps * 32, 0, s>>>(args...);
+}
 
 // number of warps a pass needs for `nmaps` maps
 static int pass_warps(const PassGeom& pg, int nmaps) {
@@ -522,11 +665,14 @@ static void launch_lines(const LineGeom& lg, dim3 grid, cudaStream_t s, A... arg
 int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
-                   cudaStream_t s, void (*mark)(void*, int), void* mark_ctx, int scan) {
+                   cudaStream_t s, void (*mark)(void*, int), void* mark_ctx, int scan, const dtw::WinParams* d_wp_rows,
+                   const dtw::WinParams* d_wp_cols, int* d_replayed) {
   if (nmaps <= 0 || njobs <= 0 || g.cells_total <= 0) return 0;
   const size_t ct = (size_t)g.cells_total;
   dim3 gr((pass_warps(pg_rows, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
-  if (scan == 2) launch_pass_v<4>(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
+  if (scan == 3) launch_pass_win(max_ow, gr, s, d_pg_rows, d_maps_rows, d_wp_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork,
+                                 b.tmp, ct * tmp_maps, b.ixdt, ct * ncm, d_replayed);
+  else if (scan == 2) launch_pass_v<4>(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
                                   ct * tmp_maps, b.ixdt, ct * ncm);
   else if (scan == 1) launch_pass_v<-1>(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
                                        ct * tmp_maps, b.ixdt, ct * ncm);
@@ -534,7 +680,9 @@ int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
                    ct * tmp_maps, b.ixdt, ct * ncm);
   if (mark) mark(mark_ctx, 2);
   dim3 gc((pass_warps(pg_cols, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
-  if (scan == 2) launch_pass_v<4>(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
+  if (scan == 3) launch_pass_win(max_oh, gc, s, d_pg_cols, d_maps_cols, d_wp_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps,
+                                 b.val, ct * tmp_maps, b.iyraw, ct * ncm, d_replayed);
+  else if (scan == 2) launch_pass_v<4>(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
                                   ct * tmp_maps, b.iyraw, ct * ncm);
   else if (scan == 1) launch_pass_v<-1>(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
                                        ct * tmp_maps, b.iyraw, ct * ncm);

@@ -10,7 +10,7 @@
 
 #if defined(__CUDACC__)
 #define PBD_ENV_FN __device__ __forceinline__
-#define PBD_ENV_NOINLINE __device__ __noinline__
+#define PBD_ENV_NOINLINE static __device__ __noinline__
 #else
 #define PBD_ENV_FN inline
 #define PBD_ENV_NOINLINE inline

@@ -1,0 +1,167 @@
+// dt_window.cuh -- windowed, CERTIFIED evaluation of the 1-D generalised distance transform (DistanceTransform<float>::computeRow,
+// reference include/DistanceTransform.hpp:152-182) at one output position, shared by the device kernels (dt_window.cu) and the host
+// harness (tests/dt_window_host.cpp, plain g++ with -ffp-contract=off, compared with the oracle on the CPU).
+//
+// What the reference computes.  With a = -w0 < 0 its stack algorithm builds the UPPER envelope of the parabolas
+// f_v(p) = a (p-v)^2 + b (p-v) + y_v and reports, for position p = os + q, the parabola v[k] with z[k] < p <= z[k+1], where every
+// break point z is the double expression of Quadratic::operator()(x0,x1,y0,y1) (:98-100) rounded to float.  Near-ties are decided
+// by those rounded values, which is why dt_pass replays the stack literally.  Away from near-ties the result is simply the arg-max
+// over v, and "away" can be decided locally:
+//
+//   Lemma.  Let delta bound the distance between any computed (float) break point near p and the real intersection abscissa.  If
+//   f_v*(p) - f_u(p) > 2|a| |u - v*| delta for every sample u != v*, the reference reports v* at p.
+//   Proof.  f_w - f_u (w > u) is linear in p with slope 2|a|(w-u), so the real intersection of v* with any u lies more than delta
+//   from p, on the far side of p.  v* is pushed when its sample is reached; it is popped by q only if fl(s(v*,q)) <= z = fl(s(u,v*))
+//   for the entry u below it at that time, but fl(s(v*,q)) > p > fl(s(u,v*)) -- never.  In the final stack (break points strictly
+//   increasing) z[k*] = fl(s(pred,v*)) < p and z[k*+1] = fl(s(v*,succ)) > p (or +inf), so the scan (:171-176) stops at k*.
+//
+//   The margin need only be checked inside a window: if for EVERY position p of a line the best sample within |v - p| <= W leads
+//   every other sample of that window by the margin and is not at the window's edge (|v* - p| <= W-1; the edge facing outwards is
+//   allowed at the first / last position), and |os| <= W, then it leads every sample of the line.  (Consecutive owners
+//   v(p) <= v(p+1) are in each other's windows, so adjacent envelope members beat each other with margin at their boundary positions; a sample between two consecutive owners is in the windows of both
+//   boundary positions; differences being linear in p, the margins add up along the chain of owners.  Samples before the first /
+//   after the last owner are inside the first / last position's window because |os| <= W.)  Maps with a larger anchor keep dt_pass.
+//
+// delta.  The float spacing at |p| <= Pmax is d32 = 2^(floor(log2 Pmax) - 23): a real number more than d32 below (above) the integer p
+// cannot round to p or beyond.  The double expression itself is within e64 <= 1.01 * 2^-53 (5 Ymax/|a| + 2.5 |b|/|a| + 4 N) of the real
+// abscissa (five roundings in the numerator, divisor and quotient one each); samples are required to satisfy |y| <= ylim, chosen so
+// that e64 <= d32 / 4, and delta = 1.25 d32.
+//
+// Tier 1 (fp32, every position): c_j = fl(y_j + fl(E_j)) is within 2^-24 (|E_j| + |c_j|) of f_j(p); the position is accepted when
+// exactly one c_j lies at or above  best - tau,  tau = tau0 + 2^-21 |best|,  tau0 = 1.01 (4 |a| W delta) + 2^-22 max|E_j|  (the worst
+// margin 2|a| 2W delta plus both evaluation errors plus the rounding of the threshold itself).  Tier 2 (double, the few positions
+// tier 1 leaves open): f_j = E_j + y_j in double, accepted when the best leads candidate j by more than
+// 1.01 (2 |a| delta) |j - j*| + 2^-50 (|best| + max|E_j|).  A position neither tier accepts marks its LINE for the literal stack
+// algorithm (dt_fix in dt_window.cu); nothing is ever guessed.
+//
+// The reported value is (float)(E[x] + (double)y_v) with E[x] = a x^2 + b x formed like the reference (:102-104): the same expression
+// dt_pass evaluates.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "dt_envelope.cuh"
+
+namespace pbd {
+namespace dtw {
+
+constexpr int kWMax = 8;                       // largest half window the parameter block is sized for
+
+// One map, one direction.  Candidate j in [0, 2W] of position p is sample v = p - W + j, i.e. x = p - v = W - j.
+struct WinParams {
+  double ed[2 * kWMax + 1];                    // E[W - j] = a x^2 + b x, rounded like the reference (env::table_E)
+  double margin1;                              // tier 2: required lead per unit of sample distance
+  double cmax;                                 // max |ed[j]|
+  float ef[2 * kWMax + 1];                     // (float)ed[j]
+  float tau0, ylim;
+  int W;
+  int ok;                                      // 0: this map / direction cannot use the window (a >= 0, |os| > W, non-finite weights, lines too long for the bound)
+};
+
+// Host-side construction (the engine builds the table once per model geometry; tests/dt_window_host.cpp uses the same function).
+inline WinParams make_params(float w_sq, float w_lin, int os, int N, int W) {
+  WinParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.W = W;
+  const double a = (double)(-w_sq), b = (double)(-w_lin);
+  const double A = -a;
+  bool ok = W >= 1 && W <= kWMax && N >= 1 && a < 0.0 && std::isfinite(a) && std::isfinite(b) && (os < 0 ? -os : os) <= W;
+  if (!ok) return P;
+  double cmax = 0.0;
+  for (int j = 0; j <= 2 * W; ++j) {
+    const int x = W - j;                                             // env::table_E's expression; the volatiles keep a host compiler from fusing
+    volatile double t1 = a * (double)(x * x);
+    volatile double t2 = b * (double)x;
+    P.ed[j] = t1 + t2;
+    P.ef[j] = (float)P.ed[j];
+    cmax = std::fmax(cmax, std::fabs(P.ed[j]));
+  }
+  int pmax = std::max(std::max(os < 0 ? -os : os, std::abs(os + N - 1)), 1);
+  int e = 0;
+  std::frexp((double)pmax, &e);                // pmax = m 2^e, m in [0.5, 1): floor(log2 pmax) = e - 1
+  const double d32 = std::ldexp(1.0, e - 1 - 23);
+  const double delta = 1.25 * d32;
+  const double u = std::ldexp(1.0, -53);
+  const double ylim = (0.25 * d32 / (1.01 * u) - 2.5 * std::fabs(b) / A - 4.0 * N) * A / 5.0;
+  if (!(ylim > 1.0)) return P;
+  P.ylim = (float)std::fmin(ylim * 0.999, 1e30);
+  P.cmax = cmax;
+  P.margin1 = 1.01 * 2.0 * A * delta;
+  const double tau0 = 1.01 * 4.0 * A * W * delta + 1.01 * std::ldexp(cmax, -22) + 1e-37;
+  P.tau0 = std::nextafterf((float)tau0, INFINITY);
+  if (!std::isfinite(P.tau0) || !std::isfinite(cmax)) return P;
+  P.ok = 1;
+  return P;
+}
+
+// NaN-propagating maximum (a NaN sample must refuse the position: fmaxf would silently drop it) and the counting step of tier 1
+#if defined(__CUDA_ARCH__)
+PBD_ENV_FN float max3_nan(float a, float b, float c) { float d; asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+template <int K> PBD_ENV_FN void count_ge(int& acc, float c, float thr) {       // FSETP + predicated add (the compiler's own choice is a 3-instruction select)
+  asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p add.s32 %0, %0, %3; }" : "+r"(acc) : "f"(c), "f"(thr), "n"(K));
+}
+#else
+PBD_ENV_FN float max3_nan(float a, float b, float c) {
+  if (a != a || b != b || c != c) return NAN;
+  return fmaxf(a, fmaxf(b, c));
+}
+template <int K> PBD_ENV_FN void count_ge(int& acc, float c, float thr) { if (c >= thr) acc += K; }
+#endif
+
+template <int W, int J>
+PBD_ENV_FN void count_all(const float (&c)[2 * W + 1], float thr, int& a0, int& a1) {
+  if constexpr (J <= 2 * W) {
+    if constexpr (J & 1) count_ge<0x100 + J>(a1, c[J], thr); else count_ge<0x100 + J>(a0, c[J], thr);
+    count_all<W, J + 1>(c, thr, a0, a1);
+  }
+}
+
+// Tier 1.  c[j] = fl(y_j + ef[j]) (-inf where the sample does not exist).  Returns the certified candidate or -1.
+template <int W>
+PBD_ENV_FN int pick(const float (&c)[2 * W + 1], float tau0, float ylim) {
+  float best = c[0];
+#pragma unroll
+  for (int j = 1; j + 1 <= 2 * W; j += 2) best = max3_nan(best, c[j], c[j + 1]);       // 2W + 1 is odd: pairs after c[0]
+  const float thr = env::fsub_r(env::fsub_r(best, tau0), env::fmul_r(fabsf(best), 4.76837158203125e-07f));   // 2^-21
+  int a0 = 0, a1 = 0;
+  count_all<W, 0>(c, thr, a0, a1);
+  const int acc = a0 + a1;
+  return ((acc >> 8) == 1 && fabsf(best) <= ylim) ? (acc & 0xff) : -1;                 // NaN best: both comparisons false
+}
+
+// Tier 2.  y[j] = the window's samples (-inf where none).  Returns the certified candidate or -1.
+template <int W>
+PBD_ENV_FN int pick_exact(const float (&y)[2 * W + 1], const double* ed, double margin1, double cmax, float ylim) {
+  double f[2 * W + 1];
+  double best = -INFINITY;
+  int jb = -1;
+#pragma unroll
+  for (int j = 0; j <= 2 * W; ++j) {
+    f[j] = env::dadd(ed[j], (double)y[j]);
+    if (f[j] != f[j]) return -1;                                                       // a NaN sample in the window
+    if (f[j] > best) { best = f[j]; jb = j; }
+  }
+  if (jb < 0 || !(fabs(best) <= (double)ylim)) return -1;
+  const double slack = env::dmul(env::dadd(fabs(best), cmax), 8.8817841970012523e-16);                        // 2^-50
+#pragma unroll
+  for (int j = 0; j <= 2 * W; ++j) {
+    if (j == jb) continue;
+    const int dist = j > jb ? j - jb : jb - j;
+    if (!(env::dsub(best, f[j]) > env::dadd(env::dmul(margin1, (double)dist), slack))) return -1;
+  }
+  return jb;
+}
+
+// The owner of position index q (0 <= q < N) must also lie in the windows of the neighbouring positions: the window's first candidate
+// (j = 0, v = p - W) is acceptable only when there is no next position, the last (j = 2W) only when there is no previous one.
+PBD_ENV_FN bool edge_ok(int j, int W, int q, int N) {
+  if (j != 0 && j != 2 * W) return true;                             // the common case: one compare pair
+  return j == 0 ? q == N - 1 : q == 0;
+}
+
+// the reference's value of position p for the certified sample: Quadratic::operator()(p - v, y_v), :102-104, rounded to float (:177)
+PBD_ENV_FN float value_of(double ed_j, float y) { return (float)env::dadd(ed_j, (double)y); }
+
+}  // namespace dtw
+}  // namespace pbd

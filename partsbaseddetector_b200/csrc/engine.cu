@@ -1,5 +1,6 @@
 // engine.cu -- see engine.hpp.
 #include "engine.hpp"
+#include "dt_window.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -109,7 +110,7 @@ void Engine::release() {
   void* ptrs[] = {d_wtc_, d_wtc16_, d_f16_, d_fhi_, d_flo_, d_tc_levels_, d_tc_tiles_, d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
-                  d_scratch_i_, d_rootkeep_, d_orient_lut_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
+                  d_scratch_i_, d_rootkeep_, d_orient_lut_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_wp_rows_, d_wp_cols_, d_dtw_ctr_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
                   slots_[1].d_hits, slots_[1].d_nhits, slots_[1].d_xym, d_ksize_, nms_.boxes, nms_.keys, nms_.skeys, nms_.sidx, nms_.kept_idx,
                   nms_.frame_count, nms_.fill, nms_.kept_count, nms_.out_off, nms_.seg_off, nms_.scratch, slots_[0].d_hits_out,
                   slots_[0].d_xym_out, slots_[0].d_total, slots_[1].d_hits_out, slots_[1].d_xym_out, slots_[1].d_total};
@@ -453,6 +454,7 @@ void Engine::build_batch_tables() {
   if (!d_pg_) { check_cuda(cudaMalloc(&d_pg_, 2 * sizeof(PassGeom)), "cudaMalloc pass geometry"); dev_bytes_ += 2 * sizeof(PassGeom); }
   check_cuda(cudaMemcpyAsync(d_pg_, pgs, sizeof(pgs), cudaMemcpyHostToDevice, stream_), "upload pass geometry");
   std::vector<PassMap> mr, mc;
+  std::vector<dtw::WinParams> wr, wc;                           // dt_variant 3: per-map parameters of the windowed certified evaluation
   wave_map_first_.assign(wave_first_.size(), 0); wave_map_count_.assign(wave_first_.size(), 0);
   const unsigned long long ct = (unsigned long long)g.cells_total;
   for (size_t wv = 0; wv < wave_first_.size(); ++wv) {
@@ -469,9 +471,21 @@ void Engine::build_batch_tables() {
         R.tab_len = dt_table_len(max_ow_); R.tab_bias = dt_table_bias(max_ow_, R.os);
         C.tab_len = dt_table_len(max_oh_); C.tab_bias = dt_table_bias(max_oh_, C.os);
         mr.push_back(R); mc.push_back(C);
+        // a map / direction the window cannot serve (anchor beyond +-W, a >= 0) has ok = 0: its lines go straight to the stack algorithm
+        wr.push_back(dtw::make_params(R.w_sq, R.w_lin, R.os, std::max(max_ow_, 1), kDtWindowW));
+        wc.push_back(dtw::make_params(C.w_sq, C.w_lin, C.os, std::max(max_oh_, 1), kDtWindowW));
       }
     }
     wave_map_count_[wv] = (int)mr.size() - wave_map_first_[wv];
+  }
+  ensure(d_wp_rows_, cap_wp_rows_, wr.size()); ensure(d_wp_cols_, cap_wp_cols_, wc.size());
+  if (!wr.empty()) {
+    check_cuda(cudaMemcpyAsync(d_wp_rows_, wr.data(), wr.size() * sizeof(dtw::WinParams), cudaMemcpyHostToDevice, stream_), "upload window parameters");
+    check_cuda(cudaMemcpyAsync(d_wp_cols_, wc.data(), wc.size() * sizeof(dtw::WinParams), cudaMemcpyHostToDevice, stream_), "upload window parameters");
+  }
+  if (!d_dtw_ctr_) {
+    check_cuda(cudaMalloc(&d_dtw_ctr_, 64 * sizeof(int)), "cudaMalloc replay counters"); dev_bytes_ += 64 * sizeof(int);
+    check_cuda(cudaMemsetAsync(d_dtw_ctr_, 0, 64 * sizeof(int), stream_), "clear replay counters");
   }
   ensure(d_maps_rows_, cap_maps_rows_, mr.size()); ensure(d_maps_cols_, cap_maps_cols_, mc.size());
   ensure(d_etab_, cap_etab_, mr.size() * (size_t)(dt_table_len(max_ow_) + dt_table_len(max_oh_)));
@@ -742,7 +756,8 @@ void Engine::run_dp_min() {
       const int n = launch_dt_wave(gs, d_g_, bs, pg_rows_, d_pg_, pg_cols_, d_pg_ + 1, d_maps_rows_ + wave_map_first_[wv],
                                    d_maps_cols_ + wave_map_first_[wv], wave_map_count_[wv], max_ow_, max_oh_, d_jobs_ + wave_first_[wv],
                                    wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, sp == 0 ? stream_ : dp_aux_[sp - 1],
-                                   timing >= 2 ? +mark : nullptr, this, dt_scan);
+                                   timing >= 2 ? +mark : nullptr, this, dt_scan, d_wp_rows_ + wave_map_first_[wv], d_wp_cols_ + wave_map_first_[wv],
+                                   d_dtw_ctr_ + (sp & 63));
       launches_ += n;
     }
   }
@@ -755,6 +770,17 @@ void Engine::run_dp_min() {
   kmark(5);
   check_cuda(cudaGetLastError(), "DP launch");
   stage_ = 4;
+}
+
+long long Engine::dt_replayed_lines() {
+  if (!d_dtw_ctr_) return 0;
+  int h[64];
+  check_cuda(cudaStreamSynchronize(stream_), "sync");
+  check_cuda(cudaMemcpy(h, d_dtw_ctr_, sizeof(h), cudaMemcpyDeviceToHost), "D2H replay counters");
+  long long tot = 0;
+  for (int i = 0; i < 64; ++i) tot += h[i];
+  check_cuda(cudaMemset(d_dtw_ctr_, 0, sizeof(h)), "clear replay counters");
+  return tot;
 }
 
 void Engine::run_argmin() {

@@ -75,6 +75,7 @@ class Engine {
   // dt_pass variant: 0 eager emission with double break points (default), 1 eager emission with certified fp32 break points (12 %
   // slower on B200), 2 lagged-scan emission (15 % slower on real score maps, 6.8x faster on white noise); results are identical
   int dt_scan = 0;
+  long long dt_replayed_lines();               // lines the windowed transform handed to the stack algorithm since the last call (synchronises)
   static constexpr int kMinFramesPerDpGroup = 4;
 
   // ---- batch set-up ----
@@ -190,6 +191,9 @@ class Engine {
   PassMap *d_maps_rows_ = nullptr, *d_maps_cols_ = nullptr; size_t cap_maps_rows_ = 0, cap_maps_cols_ = 0;
   double* d_etab_ = nullptr; size_t cap_etab_ = 0;   // per-map parabola tables of both passes
   std::vector<int> wave_map_first_, wave_map_count_;
+  // dt_variant 3 (dt_pass_win): per-map window parameters, parallel to d_maps_rows_ / d_maps_cols_; counters of replayed lines
+  dtw::WinParams *d_wp_rows_ = nullptr, *d_wp_cols_ = nullptr; size_t cap_wp_rows_ = 0, cap_wp_cols_ = 0;
+  int* d_dtw_ctr_ = nullptr;                   // [64] one per frame group
   // candidates
   // Result slots: the synchronous API uses slot 0; the pipelined submit/collect API alternates between the two so that the
   // candidates of batch i can be downloaded while batch i+1 is being computed.

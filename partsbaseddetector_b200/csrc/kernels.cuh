@@ -177,11 +177,15 @@ struct LineGeom {
 // fills b / nblk / kreg / region_bytes from nlines / N for a per-warp shared-memory budget
 void plan_line_geom(LineGeom& lg, int budget_bytes, bool stash);   // stash: the kernel parks u16 arg-maxes per sample (column kernels)
 long long line_tasks(const LineGeom& lg, int units);     // warps (rows pass, units = maps) or CTAs (fused columns pass, units = jobs)
+namespace dtw { struct WinParams; }
+constexpr int kDtWindowW = 5;       // half window of dt_variant 3: candidates within 5 samples of the position (anchors up to +-5 are eligible)
 int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const PassGeom& pg_rows, const PassGeom* d_pg_rows,
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
                    cudaStream_t s, void (*mark)(void*, int) = nullptr, void* mark_ctx = nullptr,   // mark(ctx, kernel id) after each kernel
-                   int scan = 0);                       // dt_pass variant: 0 double break points (default), 1 certified fp32 break points, 2 lagged-scan emission
+                   int scan = 0,                        // dt_pass variant: 0 double break points, 1 certified fp32 break points, 2 lagged-scan emission,
+                                                        // 3 windowed certified evaluation (dt_pass_win; needs the per-map window parameters)
+                   const dtw::WinParams* d_wp_rows = nullptr, const dtw::WinParams* d_wp_cols = nullptr, int* d_replayed = nullptr);
 int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const RootJob* d_roots, int ncomp, int nfilters, int nwork,
                 cudaStream_t s);
 

@@ -1,0 +1,63 @@
+// Host build of the windowed certified distance transform (partsbaseddetector_b200/csrc/dt_window.cuh): the same tier-1 / tier-2
+// functions the device kernels call, driven one line at a time so that the CPU suite can compare every ACCEPTED line with the oracle
+// and count the lines handed to the literal stack algorithm.  Test infrastructure only.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "../partsbaseddetector_b200/csrc/dt_window.cuh"
+
+using namespace pbd;
+
+template <int W>
+static int line_w(const float* src, int N, const dtw::WinParams& P, int os, float* dst, uint16_t* ptr, long long* tier2) {
+  int dirty = 0;
+  for (int v = 0; v < N; ++v)
+    if (!std::isfinite(src[v])) dirty = 1;                           // the kernels refuse a line with a NaN / +-inf sample while staging it
+  for (int q = 0; q < N; ++q) {
+    const int p = os + q;
+    float y[2 * W + 1], c[2 * W + 1];
+    for (int j = 0; j <= 2 * W; ++j) {
+      const int v = p - W + j;
+      y[j] = (v >= 0 && v < N) ? src[v] : -INFINITY;
+      c[j] = env::fadd_r(y[j], P.ef[j]);
+    }
+    int j = dtw::pick<W>(c, P.tau0, P.ylim);
+    if (j < 0) {
+      if (tier2) ++*tier2;
+      j = dtw::pick_exact<W>(y, P.ed, P.margin1, P.cmax, P.ylim);
+    }
+    if (j >= 0 && !dtw::edge_ok(j, W, q, N)) j = -1;
+    if (j < 0) { dirty = 1; continue; }
+    dst[q] = dtw::value_of(P.ed[j], y[j]);
+    ptr[q] = (uint16_t)(p - W + j);
+  }
+  return dirty;
+}
+
+extern "C" {
+// nl lines of N samples; dirty[line] = 1 when the line must go to the stack algorithm (its dst / ptr are then unspecified).
+// returns -1 when the map cannot use the window at all (params.ok == 0)
+int wnd_dt1d(const float* src, int nl, int N, float w_sq, float w_lin, int os, int W, float* dst, uint16_t* ptr, uint8_t* dirty,
+             long long* tier2) {
+  const dtw::WinParams P = dtw::make_params(w_sq, w_lin, os, N, W);
+  if (!P.ok) return -1;
+  for (int l = 0; l < nl; ++l) {
+    const float* s = src + (size_t)l * N;
+    float* d = dst + (size_t)l * N;
+    uint16_t* p = ptr + (size_t)l * N;
+    int r;
+    switch (W) {
+      case 3: r = line_w<3>(s, N, P, os, d, p, tier2); break;
+      case 4: r = line_w<4>(s, N, P, os, d, p, tier2); break;
+      case 5: r = line_w<5>(s, N, P, os, d, p, tier2); break;
+      case 6: r = line_w<6>(s, N, P, os, d, p, tier2); break;
+      case 8: r = line_w<8>(s, N, P, os, d, p, tier2); break;
+      default: return -2;
+    }
+    dirty[l] = (uint8_t)r;
+  }
+  return 0;
+}
+}

@@ -439,11 +439,12 @@ def test_determinism_and_stage_api_equivalence():
 
 def test_dt_kernel_variants_give_identical_results():
     """option dt_variant: 0 = every break point in double (default), 1 = certified fp32 break points, 2 = lagged-scan
-    emission: root maps, back-pointers and candidates are the same bits (and equal the oracle's, tested elsewhere for the default)."""
+    emission, 3 = windowed certified transform: root maps, back-pointers and candidates are the same bits (and equal the oracle's,
+    tested elsewhere for the default)."""
     img = np.stack([synth_frame(900 + i, 150, 210) for i in range(3)])
     img[2, 40:90, 30:120] = 17                                   # a flat patch: exact ties between break points
     outs = []
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         d = detector("Person_26parts")
         d.set_option("dt_variant", variant)
         d.set_option("thresh", -1.25)
@@ -455,6 +456,47 @@ def test_dt_kernel_variants_give_identical_results():
     for other in outs[1:]:
         assert other[1] == outs[0][1]
         assert all(np.array_equal(a, b) for a, b in zip(other[0], outs[0][0]))
+
+
+@pytest.mark.parametrize("name", ["Person_26parts", "Person_8parts", "Face_99filters", "Willowcoffee_5parts", "Face_frontal_sparse"])
+@pytest.mark.parametrize("backptr", [0, 1])
+def test_windowed_transform_equals_the_stack_algorithm(name, backptr):
+    """dt_variant 3 (dt_window.cu): maps whose anchors fit the window go through the certified position-parallel kernels, refused
+    lines through the replay kernel, the other maps (large anchors: the face models, Person_8parts) keep dt_pass -- a mixed wave.
+    Smooth frames, a noise frame (many refusals), a constant frame (every break point a tie) and a frame with flat patches; root
+    maps, arg-max maps of every part and candidates must be the bits of variant 0; and they equal the oracle on the first frame."""
+    rng = np.random.default_rng(77)
+    frames = np.stack([synth_frame(500 + i, 140, 200) for i in range(6)])
+    frames[1] = rng.integers(0, 256, frames[1].shape, dtype=np.uint8)
+    frames[2] = 93
+    frames[3, 30:100, 20:150] = 200
+    fm = load_flat(name)
+    res = {}
+    for variant in (0, 3):
+        d = detector(name)
+        d.set_option("dt_variant", variant); d.set_option("backptr", backptr)
+        if variant == 3:
+            d.get_option("dt_replayed_lines")                        # reset the counter
+        c = d.detect(frames)
+        maps = []
+        for f in range(6):
+            for l in range(d.nscales()):
+                for comp in range(len(fm.comps)):
+                    maps.append(d.rootv(f, l, comp)); maps.append(d.rooti(f, l, comp))
+        for f in (0, 1, 2, 3):
+            for p in range(1, len(fm.comps[0])):
+                npm = len(fm.comps[0][fm.comps[0][p].parentid].filterid)
+                maps.append(np.stack(d.backptr(f, 0, 0, p, npm - 1)))
+        res[variant] = (maps, [(a.frame, a.level, a.x.tolist(), a.y.tolist(), a.m.tolist(), float(a.score())) for a in c])
+        if variant == 3:
+            replayed = d.get_option("dt_replayed_lines")
+        d.set_option("dt_variant", 0); d.set_option("backptr", 0)
+    assert len(res[0][0]) == len(res[3][0])
+    for i, (a, b) in enumerate(zip(res[0][0], res[3][0])):
+        assert np.array_equal(a, b), (name, i)
+    assert res[0][1] == res[3][1]
+    if name in ("Person_26parts", "Willowcoffee_5parts"):
+        assert replayed > 0                                          # the noise / constant frames cannot be certified everywhere
 
 
 def test_cuda_graph_replay_equals_eager_launches():

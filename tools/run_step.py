@@ -21,6 +21,7 @@ ap.add_argument("--G", type=int, default=0)
 ap.add_argument("--max-levels", type=int, default=0)
 ap.add_argument("--nms", type=float, default=-1.0, help="device Candidate::sort + NMS with this overlap")
 ap.add_argument("--root-nms", type=int, default=0, help="root-map NMS window")
+ap.add_argument("--opt", action="append", default=[], help="detector option key=value")
 a = ap.parse_args()
 frames = synth_frames(min(a.batch, 4), a.h, a.w)
 frames = np.ascontiguousarray(np.concatenate([frames] * ((a.batch + 3) // 4))[:a.batch])
@@ -36,6 +37,9 @@ det.set_option("thresh", -1.14)
 if a.nms >= 0:
     det.set_option("nms_overlap", a.nms)
 det.set_option("root_nms", a.root_nms)
+for kv in a.opt:
+    k, v = kv.split("=")
+    det.set_option(k, float(v))
 det.set_option("timing", 1)
 for _ in range(a.steps):
     det.enqueue_device(dev.data_ptr(), a.batch, a.h, a.w, 3)
@@ -44,4 +48,6 @@ st = det.stage_times_ms()
 tot = sum(st.values())
 print("batch %d %dx%d levels %d: stage_ms %s total %.3f ms => %.1f frames/s (last step, per-stage events), launches %d"
       % (a.batch, a.h, a.w, det.nscales(), {k: round(v, 3) for k, v in st.items()}, tot, a.batch / tot * 1e3, det.launch_count()))
+if any(kv.startswith('dt_variant') for kv in a.opt):
+    print('replayed lines (all steps):', det.get_option('dt_replayed_lines'))
 det.close()
