@@ -120,8 +120,10 @@ void pbd_destroy(pbd_detector* d);
  *                 other's work; results do not depend on it.  Batches under 8 frames and timing == 2 use one stream.
  * Environment defaults read at pbd_create: PBD_EXACT=0|1, PBD_RESPONSE_MODE=exact|ffma|tensor|tensor16, PBD_BACKPTR=reference|exact,
  * PBD_MAX_LEVELS=n, PBD_DP_STREAMS=n.  Further keys: "graph" (1: CUDA-graph replay of pbd_enqueue_batch_u8_device), "root_nms" (window
- * sz > 0: root-map non-maxima suppression of src/nms.cpp before the backtrack; 0 = off, the reference's detect()), "dt_variant" (0 / 1 / 2:
- * the distance-transform kernel flavour, identical results).  Response modes 2 / 3 need a bank of equally sized square filters; for any
+ * sz > 0: root-map non-maxima suppression of src/nms.cpp before the backtrack; 0 = off, the reference's detect()), "dt_variant" (3, the
+ * default: windowed certified evaluation with in-kernel replay of the lines it cannot certify; 0 / 1 / 2: the stack-algorithm kernels
+ * -- double break points, certified fp32 break points, lagged scan; identical results for all four), get-only "dt_replayed_lines"
+ * (lines variant 3 handed to the stack algorithm since the last query; synchronises).  Response modes 2 / 3 need a bank of equally sized square filters; for any
  * other model they run the bit-exact FP32 kernel (mode 0).  pbd_get_option("response_kernel") tells which kernel the last pdf stage
  * ran: 0 generic exact, 1 tiled exact, 3 tensor tf32x3, 4 tensor fp16x3, 5 generic FFMA, 6 tiled FFMA. */
 int pbd_set_option(pbd_detector* d, const char* key, double value);

@@ -58,6 +58,18 @@ __device__ __forceinline__ void st_u16(unsigned short* base, unsigned idx, unsig
   asm volatile("{ .reg .u64 a; mad.wide.u32 a, %1, 2, %0; st.global.u16 [a], %2; }" ::"l"(base), "r"(idx), "h"(v) : "memory");
 }
 
+// predicated forms (dt_pass_win keeps its walk free of branches)
+__device__ __forceinline__ void st_f32_if(float* base, unsigned idx, float v, bool p) {
+  asm volatile("{ .reg .pred p; .reg .u64 a; setp.ne.u32 p, %3, 0; mad.wide.u32 a, %1, 4, %0; @p st.global.f32 [a], %2; }" ::"l"(base), "r"(idx), "f"(v),
+               "r"((unsigned)p)
+               : "memory");
+}
+__device__ __forceinline__ void st_u16_if(unsigned short* base, unsigned idx, unsigned short v, bool p) {
+  asm volatile("{ .reg .pred p; .reg .u64 a; setp.ne.u32 p, %3, 0; mad.wide.u32 a, %1, 2, %0; @p st.global.u16 [a], %2; }" ::"l"(base), "r"(idx), "h"(v),
+               "r"((unsigned)p)
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One pass of the separable transform over every map of a wave: each lane owns one contiguous line of N samples
 // of some (map, line); lines of all maps of a level are packed 32 per warp so that small pyramid levels still
@@ -180,14 +192,19 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
 // (env::envelope_stream, direct global loads) and overwrites its own stores -- same thread, so no ordering question arises.
 // Real score maps: 0.2 % of the lines are replayed (6 % of the warps run the second phase for one or two lanes).
 // ---------------------------------------------------------------------------------------------------
-// tier 2, out of line; the window is re-read from the lane's shared-memory ring (slot0 = slot of candidate 0) so that the hot path
-// never has to materialise it in local memory
+// tier 2 for a position tier 1 left open, run after the walk (so that the walk itself is straight-line code): the window is read
+// again from the line in global memory
 template <int W>
-__device__ __noinline__ int win_pick_exact_slow(const float* __restrict__ myring, int slot0, const dtw::WinParams* __restrict__ wp) {
+__device__ __noinline__ int win_pick_exact_slow(const float* __restrict__ src, int N, int v0, const dtw::WinParams* __restrict__ wp, float* ywin) {
   float w[2 * W + 1];
 #pragma unroll
-  for (int j = 0; j <= 2 * W; ++j) w[j] = myring[((slot0 + j) & 15) * 32];
-  return dtw::pick_exact<W>(w, wp->ed, wp->margin1, wp->cmax, wp->ylim);
+  for (int j = 0; j <= 2 * W; ++j) { const int v = v0 + j; w[j] = (unsigned)v < (unsigned)N ? __ldg(src + v) : -INFINITY; }
+  const int jb = dtw::pick_exact<W>(w, wp->ed, wp->margin1, wp->cmax, wp->ylim);
+  float y = 0.f;
+#pragma unroll
+  for (int j = 0; j <= 2 * W; ++j) if (j == jb) y = w[j];
+  *ywin = y;
+  return jb;
 }
 
 #ifndef PBD_DTW_MINBLOCKS
@@ -266,29 +283,45 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
   float* myring = &ring[wib][0][lane];
 #pragma unroll
   for (int k = 0; k < 16; ++k) myring[k * 32] = -INFINITY;        // tier 2 reads the window from here: samples before the line's start do not exist
-  const int steps = N + 2 * W;                                    // sample index s = 0 .. N-1, then 2W virtual -inf samples flush the window
+  // sample index s = 0 .. N-1, then 2W (rounded up to the unroll) virtual -inf samples flush the window; no branch inside a step
+  const int steps = (N + 2 * W + 15) & ~15;
+  int nd = 0, dq0 = 0, dq1 = 0;                                   // positions tier 1 left open (decided after the walk; more than two: replay)
   for (int s0 = 0; s0 < steps; s0 += 16) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int s = s0 + u;
-      if (s < steps) {                                            // warp-uniform
-        float y = -INFINITY;
-        if (s < N) { y = loady(s); mx = max(mx, __float_as_uint(y) & 0x7fffffffu); }
-        buf[u] = y;
-        myring[u * 32] = y;
-        const int q = s - os - W;                                 // the position whose last candidate is sample s
-        if (q >= 0 && q < N) {
-          float c[2 * W + 1];
+      float y = -INFINITY;
+      if (s < N) { y = loady(s); mx = max(mx, __float_as_uint(y) & 0x7fffffffu); }   // warp-uniform
+      buf[u] = y;
+      myring[u * 32] = y;
+      const int q = s - os - W;                                   // the position whose last candidate is sample s
+      const bool valid = (unsigned)q < (unsigned)N;
+      float c[2 * W + 1];
 #pragma unroll
-          for (int j = 0; j <= 2 * W; ++j) c[j] = __fadd_rn(buf[(u + 16 - 2 * W + j) & 15], ef[j]);
-          int j = dtw::pick<W>(c, tau0, ylim);
-          if (j < 0) j = win_pick_exact_slow<W>(myring, (u + 16 - 2 * W) & 15, wp);
-          if (j >= 0 && !dtw::edge_ok(j, W, q, N)) j = -1;
-          if (j < 0) { refused = true; j = W; }
-          const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
-          store(q, dtw::value_of(__ldg(ed + j), yv), (unsigned short)(s - 2 * W + j));
-        }
-      }
+      for (int j = 0; j <= 2 * W; ++j) c[j] = __fadd_rn(buf[(u + 16 - 2 * W + j) & 15], ef[j]);
+      const int jj = dtw::pick<W>(c, tau0, ylim);
+      const bool open = valid & (jj < 0);
+      dq1 = (open & (nd != 0)) ? q : dq1;
+      dq0 = (open & (nd == 0)) ? q : dq0;
+      nd += open ? 1 : 0;
+      // the owner must lie in the neighbouring positions' windows (dtw::edge_ok)
+      refused |= valid & (((jj == 0) & (q != N - 1)) | ((jj == 2 * W) & (q != 0)));
+      const int j = jj < 0 ? W : jj;
+      const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
+      const float val = dtw::value_of(__ldg(ed + j), yv);
+      const unsigned off = (unsigned)q * (unsigned)nlines;
+      st_f32_if(dst, off, val, valid);
+      st_u16_if(dp, off, (unsigned short)(s - 2 * W + j), valid);
+    }
+  }
+  if (nd > 2) refused = true;
+  if (nd > 0 && !refused) {                                       // ~2 % of the lines: tier 2 for the open positions
+    for (int k = 0; k < nd; ++k) {
+      const int q = k == 0 ? dq0 : dq1;
+      float yv;
+      const int j = win_pick_exact_slow<W>(src, N, q + os - W, wp, &yv);
+      if (j < 0 || !dtw::edge_ok(j, W, q, N)) { refused = true; break; }
+      store(q, dtw::value_of(__ldg(ed + j), yv), (unsigned short)(q + os - W + j));
     }
   }
   if (mx >= 0x7f800000u) refused = true;

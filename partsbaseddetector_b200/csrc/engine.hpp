@@ -74,7 +74,7 @@ class Engine {
   int last_response_kernel = -1;
   // dt_pass variant: 0 eager emission with double break points (default), 1 eager emission with certified fp32 break points (12 %
   // slower on B200), 2 lagged-scan emission (15 % slower on real score maps, 6.8x faster on white noise); results are identical
-  int dt_scan = 0;
+  int dt_scan = 3;                             // dt_variant: 3 = windowed certified evaluation with replay (dt_pass_win), 0 / 1 / 2 = stack kernels
   long long dt_replayed_lines();               // lines the windowed transform handed to the stack algorithm since the last call (synchronises)
   static constexpr int kMinFramesPerDpGroup = 4;
 

@@ -22,7 +22,7 @@ def detector(name):
         d.distributeModel(Model.load_bin(os.path.join(GOLDEN, name + ".pbdm")))
         _det_cache[name] = d
     d = _det_cache[name]
-    for k, v in (("exact", 1), ("backptr", 0), ("max_levels", 0), ("thresh", load_flat(name).thresh), ("dt_variant", 0), ("root_nms", 0), ("graph", 0)):
+    for k, v in (("exact", 1), ("backptr", 0), ("max_levels", 0), ("thresh", load_flat(name).thresh), ("dt_variant", 3), ("root_nms", 0), ("graph", 0)):
         d.set_option(k, v)
     return d
 
@@ -451,7 +451,7 @@ def test_dt_kernel_variants_give_identical_results():
         c = d.detect(img)
         maps = [d.rootv(f, l) for f in range(3) for l in range(d.nscales())] + [np.stack(d.backptr(2, 0, 0, p, 1)) for p in (1, 7, 25)]
         outs.append((maps, [(a.frame, a.level, a.x.tolist(), a.y.tolist(), a.m.tolist(), float(a.score())) for a in c]))
-        d.set_option("dt_variant", 0)                            # the helper's detectors are shared between tests
+        d.set_option("dt_variant", 3)                            # the helper's detectors are shared between tests (3 = the default)
     assert len(outs[0][1]) > 20
     for other in outs[1:]:
         assert other[1] == outs[0][1]
@@ -490,7 +490,7 @@ def test_windowed_transform_equals_the_stack_algorithm(name, backptr):
         res[variant] = (maps, [(a.frame, a.level, a.x.tolist(), a.y.tolist(), a.m.tolist(), float(a.score())) for a in c])
         if variant == 3:
             replayed = d.get_option("dt_replayed_lines")
-        d.set_option("dt_variant", 0); d.set_option("backptr", 0)
+        d.set_option("dt_variant", 3); d.set_option("backptr", 0)
     assert len(res[0][0]) == len(res[3][0])
     for i, (a, b) in enumerate(zip(res[0][0], res[3][0])):
         assert np.array_equal(a, b), (name, i)

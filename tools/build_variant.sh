@@ -11,5 +11,5 @@ cp $SRC $C/_variant_dt.cu
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --fmad=false "$@" -Xptxas -v -c $C/_variant_dt.cu -o $ROOT/build/variants/dt_$NAME.o 2>&1 | grep -E "Used" | head -1
 rm -f $C/_variant_dt.cu
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/build/variants/libpbd_b200_$NAME.so $C/pyramid.o $C/hog.o $C/response.o $C/response_tc.o \
-  $ROOT/build/variants/dt_$NAME.o $C/backtrack.o $C/nms.o $C/engine.o $C/model.o $C/matfile.o $C/abi.o -lz -Xlinker --no-undefined
+  $ROOT/build/variants/dt_$NAME.o $C/backtrack.o $C/nms.o $C/engine.o $C/model.o $C/matfile.o $C/ingest.o $C/abi.o -lz -Xlinker --no-undefined
 echo built $NAME
