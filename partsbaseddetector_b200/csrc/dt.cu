@@ -192,19 +192,36 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
 // (env::envelope_stream, direct global loads) and overwrites its own stores -- same thread, so no ordering question arises.
 // Real score maps: 0.2 % of the lines are replayed (6 % of the warps run the second phase for one or two lanes).
 // ---------------------------------------------------------------------------------------------------
-// tier 2 for a position tier 1 left open, run after the walk (so that the walk itself is straight-line code): the window is read
-// again from the line in global memory
+// The positions tier 1 left open, decided after the walk (so that the walk itself is straight-line code): tier 2 on the window read
+// again from the line in global memory, then tier 3, the local replay between the certified neighbours (dt_window.cuh).  Returns
+// false if the line has to be replayed as a whole.
 template <int W>
-__device__ __noinline__ int win_pick_exact_slow(const float* __restrict__ src, int N, int v0, const dtw::WinParams* __restrict__ wp, float* ywin) {
-  float w[2 * W + 1];
+__device__ __noinline__ bool win_resolve_open(const float* __restrict__ src, int N, int os, int nlines, const PassMap& M,
+                                              const dtw::WinParams* __restrict__ wp, float* dst, unsigned short* dp, int nd, int dq0, int dq1) {
+  const Quad f = env::make_quad(M.w_sq, M.w_lin, M.etab + M.tab_bias, M.etab + (M.tab_len - kDtRcp));
+  for (int k = 0; k < nd; ++k) {
+    const int q0 = k == 0 ? dq0 : dq1, p0 = q0 + os;
+    float w[2 * W + 1];
 #pragma unroll
-  for (int j = 0; j <= 2 * W; ++j) { const int v = v0 + j; w[j] = (unsigned)v < (unsigned)N ? __ldg(src + v) : -INFINITY; }
-  const int jb = dtw::pick_exact<W>(w, wp->ed, wp->margin1, wp->cmax, wp->ylim);
-  float y = 0.f;
+    for (int j = 0; j <= 2 * W; ++j) { const int v = p0 - W + j; w[j] = (unsigned)v < (unsigned)N ? __ldg(src + v) : -INFINITY; }
+    const int jb = dtw::pick_exact<W>(w, wp->ed, wp->margin1, wp->cmax, wp->ylim);
+    int v;
+    float yv = 0.f;
+    if (jb >= 0) {
+      if (!dtw::edge_ok(jb, W, q0, N)) return false;
 #pragma unroll
-  for (int j = 0; j <= 2 * W; ++j) if (j == jb) y = w[j];
-  *ywin = y;
-  return jb;
+      for (int j = 0; j <= 2 * W; ++j) if (j == jb) yv = w[j];
+      v = p0 - W + jb;
+    } else {
+      // neighbours: certified (the open positions of a line are never adjacent here) -- their owners were stored by this thread
+      const int uL = q0 > 0 ? (int)dp[(size_t)(q0 - 1) * nlines] : 0, uR = q0 < N - 1 ? (int)dp[(size_t)(q0 + 1) * nlines] : N - 1;
+      if (!dtw::local_ok(W, os, N, q0, uL, uR)) return false;
+      v = dtw::local_owner(f, p0, uL, uR, [&](int u) { return __ldg(src + u); }, &yv);
+    }
+    dst[(size_t)q0 * nlines] = dtw::value_of(env::ld_table(f.E, p0 - v), yv);
+    dp[(size_t)q0 * nlines] = (unsigned short)v;
+  }
+  return true;
 }
 
 #ifndef PBD_DTW_MINBLOCKS
@@ -314,16 +331,9 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
       st_u16_if(dp, off, (unsigned short)(s - 2 * W + j), valid);
     }
   }
-  if (nd > 2) refused = true;
-  if (nd > 0 && !refused) {                                       // ~2 % of the lines: tier 2 for the open positions
-    for (int k = 0; k < nd; ++k) {
-      const int q = k == 0 ? dq0 : dq1;
-      float yv;
-      const int j = win_pick_exact_slow<W>(src, N, q + os - W, wp, &yv);
-      if (j < 0 || !dtw::edge_ok(j, W, q, N)) { refused = true; break; }
-      store(q, dtw::value_of(__ldg(ed + j), yv), (unsigned short)(q + os - W + j));
-    }
-  }
+  if (nd > 2 || (nd == 2 && (dq1 - dq0 == 1 || dq0 - dq1 == 1))) refused = true;
+  if (nd > 0 && !refused)                                         // ~2 % of the lines: tier 2, then the local replay, for the open positions
+    refused = !win_resolve_open<W>(src, N, os, nlines, M, wp, dst, dp, nd, dq0, dq1);
   if (mx >= 0x7f800000u) refused = true;
   if (!(refused && active)) return;
   // ---- replay: the reference's stack algorithm for this lane's line ----

@@ -153,6 +153,48 @@ PBD_ENV_FN int pick_exact(const float (&y)[2 * W + 1], const double* ed, double 
   return jb;
 }
 
+// Tier 3: LOCAL REPLAY of an isolated open position p0 (neither tier certifies it: a break point lies within delta of p0).  Its
+// neighbours p0 - 1 and p0 + 1 are certified with owners uL <= uR, so (lemma) both are in the reference's final stack and are never
+// popped.  Entries are only ever popped from the top, so whatever lies between uL and uR in the final stack is exactly what the
+// reference's loop (:160-170) leaves there when it pushes the samples uL+1 .. uR on top of uL -- a computation that involves nothing
+// but those samples and the reference's own break-point expression (env::isect_adjacent / env::isect_far): a pop test against uL
+// itself is false by the lemma (at a line's start uL = sample 0, which the loop never pops), and nothing after uR can reach below uR.
+// The scan (:171-176) stands at uL when it arrives at p0 (it chose uL for p0 - 1; at the first position it starts at sample 0) and
+// advances while the next entry's break point is < p0.  At a line's end the replay simply runs to the last sample.
+// The certified positions on either side keep their global margins: uL, uR and every sample between them must lie in the windows of
+// BOTH p0 - 1 and p0 + 1 (checked by the caller: uR - (p0-1) <= W and (p0+1) - uL <= W), so the chain argument steps over p0.
+constexpr int kLocalMax = 2 * kWMax + 4;
+template <typename LoadY>
+PBD_ENV_FN int local_owner(const env::Quad& f, int p0, int uL, int uR, LoadY loady, float* y_owner) {
+  int v[kLocalMax];
+  float z[kLocalMax], y[kLocalMax];
+  int k = 0;
+  v[0] = uL; y[0] = loady(uL); z[0] = -INFINITY;
+  for (int q = uL + 1; q <= uR; ++q) {
+    const float yq = loady(q);
+    auto isect = [&](int kk) -> float {
+      return q - v[kk] == 1 ? env::isect_adjacent(f, q, (double)y[kk], (double)yq) : env::isect_far(f, v[kk], q, (double)y[kk], (double)yq);
+    };
+    float s = isect(k);
+    while (k > 0 && s <= z[k]) { --k; s = isect(k); }
+    ++k;
+    v[k] = q; y[k] = yq; z[k] = s;
+  }
+  int kk = 0;
+  while (kk < k && z[kk + 1] < (float)p0) ++kk;
+  *y_owner = y[kk];
+  return v[kk];
+}
+// the caller's conditions for local_owner at position index q0 of a line of N samples (p0 = q0 + os); has_l / has_r: the neighbouring
+// position exists and is certified with owner uL / uR (at the ends: uL = 0 / uR = N - 1 and the anchor must leave the window room)
+PBD_ENV_FN bool local_ok(int W, int os, int N, int q0, int uL, int uR) {
+  const int p0 = q0 + os;
+  if (uL > uR || uR - uL > kLocalMax - 2) return false;
+  if (q0 > 0 ? uR - (p0 - 1) > W : os > W - 1) return false;         // left side: uR inside the window of p0 - 1 / every sample inside that of p0 + 1
+  if (q0 < N - 1 ? (p0 + 1) - uL > W : -os > W - 1) return false;
+  return true;
+}
+
 // The owner of position index q (0 <= q < N) must also lie in the windows of the neighbouring positions: the window's first candidate
 // (j = 0, v = p - W) is acceptable only when there is no next position, the last (j = 2W) only when there is no previous one.
 PBD_ENV_FN bool edge_ok(int j, int W, int q, int N) {

@@ -5,16 +5,27 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../partsbaseddetector_b200/csrc/dt_window.cuh"
 
 using namespace pbd;
 
+static long long g_cause[8];   // refusal causes (diagnostics): 0 non-finite, 1 local replay conditions, 2 edge, 3 third open position, 4 open neighbour
+
 template <int W>
-static int line_w(const float* src, int N, const dtw::WinParams& P, int os, float* dst, uint16_t* ptr, long long* tier2) {
+static int line_w(const float* src, int N, const dtw::WinParams& P, float w_sq, float w_lin, int os, float* dst, uint16_t* ptr, long long* tier2) {
   int dirty = 0;
   for (int v = 0; v < N; ++v)
-    if (!std::isfinite(src[v])) dirty = 1;                           // the kernels refuse a line with a NaN / +-inf sample while staging it
+    if (!std::isfinite(src[v])) { dirty = 1; ++g_cause[0]; }                           // the kernels refuse a line with a NaN / +-inf sample while staging it
+  // the parabola tables the stack kernels use (tier 3 forms the reference's break point with env::isect_*)
+  const double a = (double)(-w_sq), b = (double)(-w_lin);
+  double rcp[env::kRcp];
+  for (int d = 0; d < env::kRcp; ++d) rcp[d] = env::table_rcp(a, d);
+  const env::Quad f = env::make_quad(w_sq, w_lin, nullptr, rcp);
+  int open[2];
+  int nopen = 0;
+  std::vector<int> state(N, 0);                                      // 1: certified by tier 1 / 2
   for (int q = 0; q < N; ++q) {
     const int p = os + q;
     float y[2 * W + 1], c[2 * W + 1];
@@ -28,15 +39,31 @@ static int line_w(const float* src, int N, const dtw::WinParams& P, int os, floa
       if (tier2) ++*tier2;
       j = dtw::pick_exact<W>(y, P.ed, P.margin1, P.cmax, P.ylim);
     }
-    if (j >= 0 && !dtw::edge_ok(j, W, q, N)) j = -1;
-    if (j < 0) { dirty = 1; continue; }
+    if (j < 0) {                                                     // open: decided after the walk, like the device kernel does
+      if (nopen == 2) { dirty = 1; ++g_cause[3]; continue; }
+      open[nopen++] = q;
+      continue;
+    }
+    if (!dtw::edge_ok(j, W, q, N)) { dirty = 1; ++g_cause[2]; continue; }
     dst[q] = dtw::value_of(P.ed[j], y[j]);
     ptr[q] = (uint16_t)(p - W + j);
+    state[q] = 1;
+  }
+  for (int k = 0; k < nopen && !dirty; ++k) {
+    const int q0 = open[k], p0 = os + q0;
+    if ((q0 > 0 && !state[q0 - 1]) || (q0 < N - 1 && !state[q0 + 1])) { dirty = 1; ++g_cause[4]; break; }
+    const int uL = q0 > 0 ? ptr[q0 - 1] : 0, uR = q0 < N - 1 ? ptr[q0 + 1] : N - 1;
+    if (!dtw::local_ok(W, os, N, q0, uL, uR)) { dirty = 1; ++g_cause[1]; break; }
+    float yo;
+    const int v = dtw::local_owner(f, p0, uL, uR, [&](int u) { return src[u]; }, &yo);
+    dst[q0] = dtw::value_of(env::table_E(a, b, p0 - v), yo);
+    ptr[q0] = (uint16_t)v;
   }
   return dirty;
 }
 
 extern "C" {
+void wnd_causes(long long* out, int reset) { for (int i = 0; i < 8; ++i) { out[i] = g_cause[i]; if (reset) g_cause[i] = 0; } }
 // nl lines of N samples; dirty[line] = 1 when the line must go to the stack algorithm (its dst / ptr are then unspecified).
 // returns -1 when the map cannot use the window at all (params.ok == 0)
 int wnd_dt1d(const float* src, int nl, int N, float w_sq, float w_lin, int os, int W, float* dst, uint16_t* ptr, uint8_t* dirty,
@@ -49,11 +76,11 @@ int wnd_dt1d(const float* src, int nl, int N, float w_sq, float w_lin, int os, i
     uint16_t* p = ptr + (size_t)l * N;
     int r;
     switch (W) {
-      case 3: r = line_w<3>(s, N, P, os, d, p, tier2); break;
-      case 4: r = line_w<4>(s, N, P, os, d, p, tier2); break;
-      case 5: r = line_w<5>(s, N, P, os, d, p, tier2); break;
-      case 6: r = line_w<6>(s, N, P, os, d, p, tier2); break;
-      case 8: r = line_w<8>(s, N, P, os, d, p, tier2); break;
+      case 3: r = line_w<3>(s, N, P, w_sq, w_lin, os, d, p, tier2); break;
+      case 4: r = line_w<4>(s, N, P, w_sq, w_lin, os, d, p, tier2); break;
+      case 5: r = line_w<5>(s, N, P, w_sq, w_lin, os, d, p, tier2); break;
+      case 6: r = line_w<6>(s, N, P, w_sq, w_lin, os, d, p, tier2); break;
+      case 8: r = line_w<8>(s, N, P, w_sq, w_lin, os, d, p, tier2); break;
       default: return -2;
     }
     dirty[l] = (uint8_t)r;

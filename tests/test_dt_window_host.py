@@ -145,3 +145,23 @@ def test_near_tie_sweep_around_integer_break_points():
     src = np.stack(lines)
     r = run_window(src, w_sq, w_lin, 0, W)
     assert r is not None
+
+
+def test_fuzz_short_quantised_lines_local_replay():
+    """many short lines on coarse value grids with 'round' parabolas: nearly every line has positions only the local replay (tier 3)
+    can decide -- isolated ties, ties at the line ends, runs of ties (refused) -- and every accepted line must equal the oracle."""
+    rng = np.random.default_rng(2024)
+    refused = total = 0
+    for it in range(160):
+        N = int(rng.integers(1, 48))
+        W = int(rng.choice([3, 5, 8]))
+        os_ = int(rng.integers(-W, W + 1))
+        w_sq = float(rng.choice([0.0625, 0.125, 0.03125, 0.25, 0.0156, 0.0101]))
+        w_lin = float(rng.choice([0.0, 0.0625, -0.125, 0.014, -0.0037]))
+        q = float(rng.choice([0.03125, 0.125, 0.5, 1e-4]))
+        amp = float(rng.choice([0.05, 0.3, 1.5]))
+        src = (np.round(smooth(rng, 96, N, amp, int(rng.integers(1, 6))) / q) * q).astype(np.float32)
+        r = run_window(src, w_sq, w_lin, os_, W)
+        assert r is not None
+        refused += r[0]; total += 96
+    assert 0 < refused < total

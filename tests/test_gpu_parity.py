@@ -495,8 +495,8 @@ def test_windowed_transform_equals_the_stack_algorithm(name, backptr):
     for i, (a, b) in enumerate(zip(res[0][0], res[3][0])):
         assert np.array_equal(a, b), (name, i)
     assert res[0][1] == res[3][1]
-    if name in ("Person_26parts", "Willowcoffee_5parts"):
-        assert replayed > 0                                          # the noise / constant frames cannot be certified everywhere
+    if name in ("Person_8parts", "Face_99filters", "Face_frontal_sparse"):
+        assert replayed > 0                                          # anchors beyond the window: those maps' lines all take the replay path
 
 
 def test_cuda_graph_replay_equals_eager_launches():
