@@ -302,7 +302,8 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
   for (int k = 0; k < 16; ++k) myring[k * 32] = -INFINITY;        // tier 2 reads the window from here: samples before the line's start do not exist
   // sample index s = 0 .. N-1, then 2W (rounded up to the unroll) virtual -inf samples flush the window; no branch inside a step
   const int steps = (N + 2 * W + 15) & ~15;
-  int nd = 0, dq0 = 0, dq1 = 0;                                   // positions tier 1 left open (decided after the walk; more than two: replay)
+  int nd = 0, dq0 = 0, dsum = 0;                                  // positions left open by the walk (one or two: decided afterwards; more: replay)
+  unsigned off = (unsigned)(-os - W) * (unsigned)nlines;          // q * nlines of the current step's position (wraps while q < 0: never stored)
   for (int s0 = 0; s0 < steps; s0 += 16) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
@@ -317,20 +318,22 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
 #pragma unroll
       for (int j = 0; j <= 2 * W; ++j) c[j] = __fadd_rn(buf[(u + 16 - 2 * W + j) & 15], ef[j]);
       const int jj = dtw::pick<W>(c, tau0, ylim);
-      const bool open = valid & (jj < 0);
-      dq1 = (open & (nd != 0)) ? q : dq1;
-      dq0 = (open & (nd == 0)) ? q : dq0;
+      // decided here only if certified strictly inside the window; anything else (tier 1 open, owner at the window's edge) is an
+      // open position, resolved after the walk (a second open position of the same line: the line is replayed)
+      const bool inner = (unsigned)(jj - 1) <= (unsigned)(2 * W - 2);
+      const bool open = valid & !inner;
+      dq0 = open ? q : dq0;                                       // the last open position; with two, the other one is dsum - dq0
+      dsum += open ? q : 0;
       nd += open ? 1 : 0;
-      // the owner must lie in the neighbouring positions' windows (dtw::edge_ok)
-      refused |= valid & (((jj == 0) & (q != N - 1)) | ((jj == 2 * W) & (q != 0)));
-      const int j = jj < 0 ? W : jj;
+      const int j = inner ? jj : W;
       const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
       const float val = dtw::value_of(__ldg(ed + j), yv);
-      const unsigned off = (unsigned)q * (unsigned)nlines;
       st_f32_if(dst, off, val, valid);
       st_u16_if(dp, off, (unsigned short)(s - 2 * W + j), valid);
+      off += (unsigned)nlines;
     }
   }
+  const int dq1 = dsum - dq0;
   if (nd > 2 || (nd == 2 && (dq1 - dq0 == 1 || dq0 - dq1 == 1))) refused = true;
   if (nd > 0 && !refused)                                         // ~2 % of the lines: tier 2, then the local replay, for the open positions
     refused = !win_resolve_open<W>(src, N, os, nlines, M, wp, dst, dp, nd, dq0, dq1);

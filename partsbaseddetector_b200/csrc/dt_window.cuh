@@ -95,39 +95,43 @@ inline WinParams make_params(float w_sq, float w_lin, int os, int N, int W) {
   return P;
 }
 
-// NaN-propagating maximum (a NaN sample must refuse the position: fmaxf would silently drop it) and the counting step of tier 1
+// NaN-propagating maximum (a NaN sample must refuse the position: fmaxf would silently drop it) and the counting step of tier 1.
+// On the device the count is a float accumulated with a PREDICATED FADD: the walk is bound by the integer/compare (ALU) pipe, which
+// issues at half the rate of the FP32 pipe the FADD goes to (256 + j is exact in a float; eleven terms stay far below 2^24).
 #if defined(__CUDA_ARCH__)
 PBD_ENV_FN float max3_nan(float a, float b, float c) { float d; asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
-template <int K> PBD_ENV_FN void count_ge(int& acc, float c, float thr) {       // FSETP + predicated add (the compiler's own choice is a 3-instruction select)
-  asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p add.s32 %0, %0, %3; }" : "+r"(acc) : "f"(c), "f"(thr), "n"(K));
+template <int K> PBD_ENV_FN void count_ge(float& acc, float c, float thr) {
+  asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p add.rn.f32 %0, %0, %3; }" : "+f"(acc) : "f"(c), "f"(thr), "f"((float)K));
 }
 #else
 PBD_ENV_FN float max3_nan(float a, float b, float c) {
   if (a != a || b != b || c != c) return NAN;
   return fmaxf(a, fmaxf(b, c));
 }
-template <int K> PBD_ENV_FN void count_ge(int& acc, float c, float thr) { if (c >= thr) acc += K; }
+template <int K> PBD_ENV_FN void count_ge(float& acc, float c, float thr) { if (c >= thr) acc += (float)K; }
 #endif
 
 template <int W, int J>
-PBD_ENV_FN void count_all(const float (&c)[2 * W + 1], float thr, int& a0, int& a1) {
+PBD_ENV_FN void count_all(const float (&c)[2 * W + 1], float thr, float& a0, float& a1) {
   if constexpr (J <= 2 * W) {
     if constexpr (J & 1) count_ge<0x100 + J>(a1, c[J], thr); else count_ge<0x100 + J>(a0, c[J], thr);
     count_all<W, J + 1>(c, thr, a0, a1);
   }
 }
 
-// Tier 1.  c[j] = fl(y_j + ef[j]) (-inf where the sample does not exist).  Returns the certified candidate or -1.
+// Tier 1.  c[j] = fl(y_j + ef[j]) (-inf where the sample does not exist).  Returns the certified candidate or a negative number.
 template <int W>
 PBD_ENV_FN int pick(const float (&c)[2 * W + 1], float tau0, float ylim) {
   float best = c[0];
 #pragma unroll
   for (int j = 1; j + 1 <= 2 * W; j += 2) best = max3_nan(best, c[j], c[j + 1]);       // 2W + 1 is odd: pairs after c[0]
   const float thr = env::fsub_r(env::fsub_r(best, tau0), env::fmul_r(fabsf(best), 4.76837158203125e-07f));   // 2^-21
-  int a0 = 0, a1 = 0;
+  float a0 = 0.f, a1 = 0.f;
   count_all<W, 0>(c, thr, a0, a1);
-  const int acc = a0 + a1;
-  return ((acc >> 8) == 1 && fabsf(best) <= ylim) ? (acc & 0xff) : -1;                 // NaN best: both comparisons false
+  // exactly one candidate at or above the threshold <=> the sum is 256 + j; none: 0; two or more: >= 512.  A NaN or too large best
+  // fails the second test (and a NaN threshold counts nothing).
+  const int j = (int)env::fadd_r(a0, a1) - 0x100;
+  return ((unsigned)j <= (unsigned)(2 * W) && fabsf(best) <= ylim) ? j : -1;
 }
 
 // Tier 2.  y[j] = the window's samples (-inf where none).  Returns the certified candidate or -1.
