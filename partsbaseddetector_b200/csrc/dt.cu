@@ -59,15 +59,13 @@ __device__ __forceinline__ void st_u16(unsigned short* base, unsigned idx, unsig
 }
 
 // predicated forms (dt_pass_win keeps its walk free of branches)
-__device__ __forceinline__ void st_f32_if(float* base, unsigned idx, float v, bool p) {
-  asm volatile("{ .reg .pred p; .reg .u64 a; setp.ne.u32 p, %3, 0; mad.wide.u32 a, %1, 4, %0; @p st.global.f32 [a], %2; }" ::"l"(base), "r"(idx), "f"(v),
-               "r"((unsigned)p)
-               : "memory");
-}
-__device__ __forceinline__ void st_u16_if(unsigned short* base, unsigned idx, unsigned short v, bool p) {
-  asm volatile("{ .reg .pred p; .reg .u64 a; setp.ne.u32 p, %3, 0; mad.wide.u32 a, %1, 2, %0; @p st.global.u16 [a], %2; }" ::"l"(base), "r"(idx), "h"(v),
-               "r"((unsigned)p)
-               : "memory");
+// value + arg-max of position q, stored only if q < n (unsigned compare: q "negative" while the window fills); one predicate, no branch
+__device__ __forceinline__ void st_pair_if_lt(float* vbase, unsigned short* pbase, unsigned idx, float v, unsigned short a, unsigned q, unsigned n) {
+  asm volatile(
+      "{ .reg .pred p; .reg .u64 a, b; setp.lt.u32 p, %5, %6; mad.wide.u32 a, %2, 4, %0; mad.wide.u32 b, %2, 2, %1;\n"
+      "  @p st.global.f32 [a], %3; @p st.global.u16 [b], %4; }" ::"l"(vbase),
+      "l"(pbase), "r"(idx), "f"(v), "h"(a), "r"(q), "r"(n)
+      : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -296,10 +294,10 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
   float buf[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) buf[k] = -INFINITY;
-  unsigned mx = 0u;                                               // largest |sample| bit pattern: NaN / inf samples refuse the line
+  float chk = 0.f;                                                // fma(y, 0, chk): NaN as soon as one sample is NaN or +-inf (they refuse the line)
   float* myring = &ring[wib][0][lane];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) myring[k * 32] = -INFINITY;        // tier 2 reads the window from here: samples before the line's start do not exist
+  for (int k = 0; k < 16; ++k) myring[k * 32] = -INFINITY;        // samples before the line's start do not exist
   // sample index s = 0 .. N-1, then 2W (rounded up to the unroll) virtual -inf samples flush the window; no branch inside a step
   const int steps = (N + 2 * W + 15) & ~15;
   int nd = 0, dq0 = 0, dsum = 0;                                  // positions left open by the walk (one or two: decided afterwards; more: replay)
@@ -309,7 +307,7 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
     for (int u = 0; u < 16; ++u) {
       const int s = s0 + u;
       float y = -INFINITY;
-      if (s < N) { y = loady(s); mx = max(mx, __float_as_uint(y) & 0x7fffffffu); }   // warp-uniform
+      if (s < N) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }  // warp-uniform
       buf[u] = y;
       myring[u * 32] = y;
       const int q = s - os - W;                                   // the position whose last candidate is sample s
@@ -328,8 +326,7 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
       const int j = inner ? jj : W;
       const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
       const float val = dtw::value_of(__ldg(ed + j), yv);
-      st_f32_if(dst, off, val, valid);
-      st_u16_if(dp, off, (unsigned short)(s - 2 * W + j), valid);
+      st_pair_if_lt(dst, dp, off, val, (unsigned short)(s - 2 * W + j), (unsigned)q, (unsigned)N);
       off += (unsigned)nlines;
     }
   }
@@ -337,7 +334,7 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
   if (nd > 2 || (nd == 2 && (dq1 - dq0 == 1 || dq0 - dq1 == 1))) refused = true;
   if (nd > 0 && !refused)                                         // ~2 % of the lines: tier 2, then the local replay, for the open positions
     refused = !win_resolve_open<W>(src, N, os, nlines, M, wp, dst, dp, nd, dq0, dq1);
-  if (mx >= 0x7f800000u) refused = true;
+  if (chk != chk) refused = true;
   if (!(refused && active)) return;
   // ---- replay: the reference's stack algorithm for this lane's line ----
   __syncwarp(__activemask());
