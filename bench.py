@@ -398,13 +398,17 @@ def run_gpu_arm(args):
         resp_ms = kt.get("part_response", 0.0)
         resp_flops = 2.0 * 800 * 138 * cells * B                  # the reference's multiply-adds
         step_ms = ms_max / steps
-        roof_dt = {"kernel": "dt_pass (22 launches per step: 11 waves x rows/columns)", "bound": "hbm", "achieved": dt_bytes / (dt_ms * 1e-3) / 1e9 if dt_ms else None,
+        variant = next((kv.split("=")[1] for kv in args.opt if kv.startswith("dt_variant=")), "3")
+        win = variant == "3"
+        roof_dt = {"kernel": ("dt_pass_win" if win else "dt_pass") + " (22 launches per frame group and step: 11 waves x rows/columns)", "bound": "hbm", "achieved": dt_bytes / (dt_ms * 1e-3) / 1e9 if dt_ms else None,
                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dt_bytes / (dt_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if dt_ms else None, "traffic": None,
                    "peak_source": peak_src, "ms_per_launch": dt_ms / nlaunch_dt, "share_of_step": dt_ms / step_ms,
                    "algorithmic_bytes": "16 B per map cell (SURVEY 8d) x 133 maps x cells x batch; as implemented 20 B (the row->column intermediate) with u16 pointers",
-                   "note": "sequential lower-envelope scan with fp64 break points, one lane per line: bounded by instruction issue / latency, not by HBM "
-                           "(DESIGN.md section 3.2 incl. the measured parallel-in-q alternative)"}
-        tp = os.path.join(ROOT, "profiles", "dt_pass_traffic.json")
+                   "note": ("windowed certified evaluation (11 candidates per position, certificate per position, replay of uncertifiable lines), one lane "
+                            "per line: bounded by instruction issue (ALU pipe 66 % busy, 86 instructions per position), not by HBM (DESIGN.md section 3.2)") if win else
+                           ("sequential lower-envelope scan with fp64 break points, one lane per line: bounded by instruction issue / latency, not by HBM "
+                            "(DESIGN.md section 3.2 incl. the measured parallel-in-q alternative)")}
+        tp = os.path.join(ROOT, "profiles", "dt_pass_win_traffic.json" if win else "dt_pass_traffic.json")
         if os.path.exists(tp) and H <= 480:
             tr = json.load(open(tp))
             # the capture holds launches of the largest wave: scale to this run's batch and to the average number of maps per launch
