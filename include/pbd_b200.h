@@ -228,10 +228,14 @@ int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, 
  * `stream` (no allocation, no synchronisation): what the DT microbenchmark times.  impl: 0 = default (1), 1 = streaming envelope
  * (one lane per line, any length <= 4096; the kernels the detector runs), 2 = parallel-in-q (a warp per batch of lines in shared
  * memory, lines <= 1024; bit-identical, kept as a measured alternative), 3 = streaming envelope with lagged-scan emission (one store
- * per position: the variant for rough inputs such as the white-noise maps of the microbenchmark). */
+ * per position: the variant for rough inputs such as the white-noise maps of the microbenchmark), 4 = windowed certified evaluation
+ * with replay of the lines it cannot certify (the detector's default transform, dt_variant 3: fast on score-like maps whose arg-max
+ * stays within 4 samples of the position, slower than 1 on maps where it does not); pbd_dt2d_plan_replayed: lines impl 4 handed to
+ * the stack algorithm since the last call (synchronises; 0 for the other impls).  All impls give identical results. */
 typedef struct pbd_dt2d_plan pbd_dt2d_plan;
 int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, int impl, pbd_dt2d_plan** out);
 int pbd_dt2d_plan_impl(const pbd_dt2d_plan* p);
+long long pbd_dt2d_plan_replayed(pbd_dt2d_plan* p);
 int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode);
 void pbd_dt2d_plan_destroy(pbd_dt2d_plan* p);
 

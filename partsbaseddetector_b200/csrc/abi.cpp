@@ -9,6 +9,7 @@
 
 #include "../../include/pbd_b200.h"
 #include "engine.hpp"
+#include "dt_window.cuh"
 #include "ingest.hpp"
 #include "model.hpp"
 
@@ -521,14 +522,14 @@ extern "C" {
 struct pbd_dt2d_plan {
   int n_maps = 0, h = 0, w = 0, impl = 0, device = 0;
   LineGeom lg[2];
-  DevBuf geom, maps, etab, tmp, ixr, iyr;
+  DevBuf geom, maps, etab, tmp, ixr, iyr, wp, ctr;   // wp / ctr: window parameters and the replay counter of impl 4
 };
 
 int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, int impl, pbd_dt2d_plan** out) {
   return guarded([&] {
     REQUIRE(defw4 && anchor_xy && out, "null argument");
     REQUIRE(n_maps > 0 && n_maps <= (1 << 20) && h > 0 && w > 0 && h <= 4096 && w <= 4096, "map shape out of range (<= 4096 x 4096, <= 2^20 maps)");
-    REQUIRE(impl >= 0 && impl <= 3, "impl must be 0 (default), 1 (streaming, eager emission), 2 (parallel-in-q) or 3 (streaming, lagged-scan emission)");
+    REQUIRE(impl >= 0 && impl <= 4, "impl must be 0 (default), 1 (streaming, eager emission), 2 (parallel-in-q), 3 (streaming, lagged-scan emission) or 4 (windowed certified evaluation with replay)");
     for (int i = 0; i < n_maps; ++i) {
       REQUIRE(defw4[4 * i] > 0.f && defw4[4 * i + 2] > 0.f, "quadratic weights must be > 0");
       REQUIRE(std::abs(anchor_xy[2 * i]) <= 4096 && std::abs(anchor_xy[2 * i + 1]) <= 4096, "anchor out of range");
@@ -554,6 +555,17 @@ int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int
     }
     P->maps.alloc(maps.size() * sizeof(PassMap));
     P->tmp.alloc(cells * sizeof(float)); P->ixr.alloc(cells * 2); P->iyr.alloc(cells * 2);
+    if (P->impl == 4) {                        // the detector's default transform (dt_pass_win): certificate parameters per map and direction
+      std::vector<dtw::WinParams> wp(2 * (size_t)n_maps);
+      for (int i = 0; i < n_maps; ++i) {
+        wp[i] = dtw::make_params(maps[i].w_sq, maps[i].w_lin, maps[i].os, w, kDtWindowW);
+        wp[n_maps + i] = dtw::make_params(maps[n_maps + i].w_sq, maps[n_maps + i].w_lin, maps[n_maps + i].os, h, kDtWindowW);
+      }
+      P->wp.alloc(wp.size() * sizeof(dtw::WinParams));
+      cu(cudaMemcpy(P->wp.p, wp.data(), wp.size() * sizeof(dtw::WinParams), cudaMemcpyHostToDevice), "H2D");
+      P->ctr.alloc(sizeof(int));
+      cu(cudaMemset(P->ctr.p, 0, sizeof(int)), "memset");
+    }
     cu(cudaMemcpy(P->maps.p, maps.data(), maps.size() * sizeof(PassMap), cudaMemcpyHostToDevice), "H2D");
     if (P->impl != 2) {
       PassGeom pgs[2];
@@ -584,6 +596,17 @@ void pbd_dt2d_plan_destroy(pbd_dt2d_plan* p) {
   try { DeviceGuard dg_(p->device); delete p; } catch (...) { delete p; }   // the plan's buffers live on the device it was created on
 }
 int pbd_dt2d_plan_impl(const pbd_dt2d_plan* p) { return p ? p->impl : 0; }
+// impl 4: lines replayed with the stack algorithm since the last call (synchronises the device); other impls: 0
+long long pbd_dt2d_plan_replayed(pbd_dt2d_plan* p) {
+  if (!p || p->impl != 4) return 0;
+  int v = 0;
+  try {
+    DeviceGuard dg_(p->device);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&v, p->ctr.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    cudaMemset(p->ctr.p, 0, sizeof(int));
+  } catch (...) { return -1; }
+  return v;
+}
 
 // enqueue only (no allocation, no synchronisation): rows pass, columns pass, back-pointer composition
 int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode) {
@@ -594,7 +617,8 @@ int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* 
     cudaStream_t s = (cudaStream_t)stream;
     if (p->impl != 2) {
       launch_dt2d_standalone(d_in, p->n_maps, p->h, p->w, p->geom.as<PassGeom>(), p->maps.as<PassMap>(), p->tmp.as<float>(), d_out, d_ix, d_iy,
-                             p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s, p->impl == 3);
+                             p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s, p->impl == 4 ? 3 : (p->impl == 3 ? 1 : 0),
+                             p->impl == 4 ? p->wp.as<dtw::WinParams>() : nullptr, p->impl == 4 ? p->ctr.as<int>() : nullptr);
     } else {
       launch_dt2d_lines(d_in, p->n_maps, p->h, p->w, p->lg[0], p->lg[1], p->geom.as<LineGeom>(), p->maps.as<PassMap>(), p->tmp.as<float>(), d_out,
                         d_ix, d_iy, p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s);

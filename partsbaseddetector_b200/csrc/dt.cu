@@ -190,34 +190,43 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
 // (env::envelope_stream, direct global loads) and overwrites its own stores -- same thread, so no ordering question arises.
 // Real score maps: 0.2 % of the lines are replayed (6 % of the warps run the second phase for one or two lanes).
 // ---------------------------------------------------------------------------------------------------
-// The positions tier 1 left open, decided after the walk (so that the walk itself is straight-line code): tier 2 on the window read
-// again from the line in global memory, then tier 3, the local replay between the certified neighbours (dt_window.cuh).  Returns
-// false if the line has to be replayed as a whole.
+// The positions the walk left open (tier 1 undecided, or decided by the window's edge), resolved afterwards so that the walk itself is
+// straight-line code: tier 2 on the window read again from the line in global memory, then tier 3, the local replay of what is still
+// open between its certified neighbours (dt_window.cuh).  olist holds the nd open position indices in increasing order.  Returns false
+// if the line has to be replayed as a whole.
+constexpr int kOpenCap = 256;
 template <int W>
 __device__ __noinline__ bool win_resolve_open(const float* __restrict__ src, int N, int os, int nlines, const PassMap& M,
-                                              const dtw::WinParams* __restrict__ wp, float* dst, unsigned short* dp, int nd, int dq0, int dq1) {
+                                              const dtw::WinParams* __restrict__ wp, float* dst, unsigned short* dp, int* olist, int nd) {
   const Quad f = env::make_quad(M.w_sq, M.w_lin, M.etab + M.tab_bias, M.etab + (M.tab_len - kDtRcp));
-  for (int k = 0; k < nd; ++k) {
-    const int q0 = k == 0 ? dq0 : dq1, p0 = q0 + os;
+  int left = 0;
+  for (int k = 0; k < nd; ++k) {                                  // tier 2
+    const int q0 = olist[k], p0 = q0 + os;
     float w[2 * W + 1];
 #pragma unroll
     for (int j = 0; j <= 2 * W; ++j) { const int v = p0 - W + j; w[j] = (unsigned)v < (unsigned)N ? __ldg(src + v) : -INFINITY; }
     const int jb = dtw::pick_exact<W>(w, wp->ed, wp->margin1, wp->cmax, wp->ylim);
-    int v;
+    if (jb < 0) { olist[left++] = q0; continue; }                 // stays open
+    if (!dtw::edge_ok(jb, W, q0, N)) return false;
     float yv = 0.f;
-    if (jb >= 0) {
-      if (!dtw::edge_ok(jb, W, q0, N)) return false;
 #pragma unroll
-      for (int j = 0; j <= 2 * W; ++j) if (j == jb) yv = w[j];
-      v = p0 - W + jb;
-    } else {
-      // neighbours: certified (the open positions of a line are never adjacent here) -- their owners were stored by this thread
-      const int uL = q0 > 0 ? (int)dp[(size_t)(q0 - 1) * nlines] : 0, uR = q0 < N - 1 ? (int)dp[(size_t)(q0 + 1) * nlines] : N - 1;
-      if (!dtw::local_ok(W, os, N, q0, uL, uR)) return false;
-      v = dtw::local_owner(f, p0, uL, uR, [&](int u) { return __ldg(src + u); }, &yv);
-    }
+    for (int j = 0; j <= 2 * W; ++j) if (j == jb) yv = w[j];
+    const int v = p0 - W + jb;
     dst[(size_t)q0 * nlines] = dtw::value_of(env::ld_table(f.E, p0 - v), yv);
     dp[(size_t)q0 * nlines] = (unsigned short)v;
+  }
+  for (int k = 0; k < left;) {                                    // tier 3: runs of consecutive open positions
+    int e = k;
+    while (e + 1 < left && olist[e + 1] == olist[e] + 1) ++e;
+    const int qa = olist[k], qb = olist[e];
+    // the neighbours of the run are certified (walk or tier 2): their owners were stored by this thread
+    const int uL = qa > 0 ? (int)dp[(size_t)(qa - 1) * nlines] : 0, uR = qb < N - 1 ? (int)dp[(size_t)(qb + 1) * nlines] : N - 1;
+    if (!dtw::local_ok(W, os, N, qa, qb, uL, uR)) return false;
+    dtw::local_owners(f, qa + os, qb + os, uL, uR, [&](int u) { return __ldg(src + u); }, [&](int p, int v, float yo) {
+      dst[(size_t)(p - os) * nlines] = dtw::value_of(env::ld_table(f.E, p - v), yo);
+      dp[(size_t)(p - os) * nlines] = (unsigned short)v;
+    });
+    k = e + 1;
   }
   return true;
 }
@@ -300,7 +309,8 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
   for (int k = 0; k < 16; ++k) myring[k * 32] = -INFINITY;        // samples before the line's start do not exist
   // sample index s = 0 .. N-1, then 2W (rounded up to the unroll) virtual -inf samples flush the window; no branch inside a step
   const int steps = (N + 2 * W + 15) & ~15;
-  int nd = 0, dq0 = 0, dsum = 0;                                  // positions left open by the walk (one or two: decided afterwards; more: replay)
+  int nd = 0;                                                     // positions left open by the walk, listed in olist (decided afterwards)
+  int olist[kOpenCap];
   unsigned off = (unsigned)(-os - W) * (unsigned)nlines;          // q * nlines of the current step's position (wraps while q < 0: never stored)
   for (int s0 = 0; s0 < steps; s0 += 16) {
 #pragma unroll
@@ -320,8 +330,7 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
       // open position, resolved after the walk (a second open position of the same line: the line is replayed)
       const bool inner = (unsigned)(jj - 1) <= (unsigned)(2 * W - 2);
       const bool open = valid & !inner;
-      dq0 = open ? q : dq0;                                       // the last open position; with two, the other one is dsum - dq0
-      dsum += open ? q : 0;
+      if (open) olist[min(nd, kOpenCap - 1)] = q;                 // rare (2e-4 of the positions on score maps): a local-memory store
       nd += open ? 1 : 0;
       const int j = inner ? jj : W;
       const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
@@ -330,10 +339,9 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
       off += (unsigned)nlines;
     }
   }
-  const int dq1 = dsum - dq0;
-  if (nd > 2 || (nd == 2 && (dq1 - dq0 == 1 || dq0 - dq1 == 1))) refused = true;
-  if (nd > 0 && !refused)                                         // ~2 % of the lines: tier 2, then the local replay, for the open positions
-    refused = !win_resolve_open<W>(src, N, os, nlines, M, wp, dst, dp, nd, dq0, dq1);
+  if (nd > kOpenCap) refused = true;
+  if (nd > 0 && !refused)                                         // ~2 % of the VGA lines: tier 2, then the local replay, for the open positions
+    refused = !win_resolve_open<W>(src, N, os, nlines, M, wp, dst, dp, olist, nd);
   if (chk != chk) refused = true;
   if (!(refused && active)) return;
   // ---- replay: the reference's stack algorithm for this lane's line ----
@@ -769,14 +777,18 @@ int launch_hits(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, 
 
 int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const PassGeom* d_pg2 /* [rows, cols] */, const PassMap* d_maps2,
                            float* d_tmp, float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
-                           cudaStream_t s, int scan) {
+                           cudaStream_t s, int scan, const dtw::WinParams* d_wp2, int* d_replayed) {
   if (n_maps <= 0 || h <= 0 || w <= 0) return 0;
   // maps are launched in chunks so that the warp index stays small; every map is h*w cells
   PassGeom pr{}, pc{};
   pr.n_levels = pc.n_levels = 1;
   pr.nlines[0] = h; pr.N[0] = w; pc.nlines[0] = w; pc.N[0] = h;
   dim3 gr((pass_warps(pr, n_maps) + kPassWarps - 1) / kPassWarps, 1), gc((pass_warps(pc, n_maps) + kPassWarps - 1) / kPassWarps, 1);
-  if (scan) {
+  if (scan == 3 && d_wp2) {                                         // windowed certified evaluation (dt_pass_win): rows, then columns
+    launch_pass_win(w, gr, s, d_pg2, d_maps2, d_wp2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0, d_replayed);
+    launch_pass_win(h, gc, s, d_pg2 + 1, d_maps2 + n_maps, d_wp2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out,
+                    (size_t)0, d_iyraw, (size_t)0, d_replayed);
+  } else if (scan) {
     launch_pass_v<4>(w, gr, s, d_pg2, d_maps2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0);
     launch_pass_v<4>(h, gc, s, d_pg2 + 1, d_maps2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out, (size_t)0,
                      d_iyraw, (size_t)0);

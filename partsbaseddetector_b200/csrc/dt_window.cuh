@@ -157,8 +157,8 @@ PBD_ENV_FN int pick_exact(const float (&y)[2 * W + 1], const double* ed, double 
   return jb;
 }
 
-// Tier 3: LOCAL REPLAY of an isolated open position p0 (neither tier certifies it: a break point lies within delta of p0).  Its
-// neighbours p0 - 1 and p0 + 1 are certified with owners uL <= uR, so (lemma) both are in the reference's final stack and are never
+// Tier 3: LOCAL REPLAY of an isolated open position p0 (neither tier certifies it: a break point lies within delta of p0), or of a
+// short run of them.  Its neighbours p0 - 1 and p0 + 1 are certified with owners uL <= uR, so (lemma) both are in the reference's final stack and are never
 // popped.  Entries are only ever popped from the top, so whatever lies between uL and uR in the final stack is exactly what the
 // reference's loop (:160-170) leaves there when it pushes the samples uL+1 .. uR on top of uL -- a computation that involves nothing
 // but those samples and the reference's own break-point expression (env::isect_adjacent / env::isect_far): a pop test against uL
@@ -167,9 +167,11 @@ PBD_ENV_FN int pick_exact(const float (&y)[2 * W + 1], const double* ed, double 
 // advances while the next entry's break point is < p0.  At a line's end the replay simply runs to the last sample.
 // The certified positions on either side keep their global margins: uL, uR and every sample between them must lie in the windows of
 // BOTH p0 - 1 and p0 + 1 (checked by the caller: uR - (p0-1) <= W and (p0+1) - uL <= W), so the chain argument steps over p0.
-constexpr int kLocalMax = 2 * kWMax + 4;
-template <typename LoadY>
-PBD_ENV_FN int local_owner(const env::Quad& f, int p0, int uL, int uR, LoadY loady, float* y_owner) {
+constexpr int kLocalMax = 2 * kWMax + 8;
+// A run of open positions pa .. pb (indices qa .. qb, usually a single one) between the certified positions pa - 1 (owner uL) and
+// pb + 1 (owner uR): one local replay, then the scan advances through the run.  emit(p, owner, y_owner) once per position of the run.
+template <typename LoadY, typename Emit>
+PBD_ENV_FN void local_owners(const env::Quad& f, int pa, int pb, int uL, int uR, LoadY loady, Emit emit) {
   int v[kLocalMax];
   float z[kLocalMax], y[kLocalMax];
   int k = 0;
@@ -185,17 +187,18 @@ PBD_ENV_FN int local_owner(const env::Quad& f, int p0, int uL, int uR, LoadY loa
     v[k] = q; y[k] = yq; z[k] = s;
   }
   int kk = 0;
-  while (kk < k && z[kk + 1] < (float)p0) ++kk;
-  *y_owner = y[kk];
-  return v[kk];
+  for (int p = pa; p <= pb; ++p) {
+    while (kk < k && z[kk + 1] < (float)p) ++kk;
+    emit(p, v[kk], y[kk]);
+  }
 }
-// the caller's conditions for local_owner at position index q0 of a line of N samples (p0 = q0 + os); has_l / has_r: the neighbouring
-// position exists and is certified with owner uL / uR (at the ends: uL = 0 / uR = N - 1 and the anchor must leave the window room)
-PBD_ENV_FN bool local_ok(int W, int os, int N, int q0, int uL, int uR) {
-  const int p0 = q0 + os;
+// the caller's conditions for local_owners on the run of position indices qa .. qb of a line of N samples: uL / uR are the owners of
+// the certified positions qa - 1 / qb + 1 (at the line's ends: uL = 0 / uR = N - 1, and the anchor must leave the window room)
+PBD_ENV_FN bool local_ok(int W, int os, int N, int qa, int qb, int uL, int uR) {
+  const int pa = qa + os, pb = qb + os;
   if (uL > uR || uR - uL > kLocalMax - 2) return false;
-  if (q0 > 0 ? uR - (p0 - 1) > W : os > W - 1) return false;         // left side: uR inside the window of p0 - 1 / every sample inside that of p0 + 1
-  if (q0 < N - 1 ? (p0 + 1) - uL > W : -os > W - 1) return false;
+  if (qa > 0 ? uR - (pa - 1) > W : os > W - 1) return false;         // uL, uR and everything between them inside the windows of BOTH certified
+  if (qb < N - 1 ? (pb + 1) - uL > W : -os > W - 1) return false;    // neighbours, so that the chain of margins steps over the run
   return true;
 }
 

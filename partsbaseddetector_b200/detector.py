@@ -509,7 +509,8 @@ class PartsBasedDetector:
 class Dt2dPlan:
     """Standalone generalised 2-D distance transform (DistanceTransform<float>::compute) of n maps of h x w with all tables and
     scratch buffers pre-allocated: run() only enqueues kernels (device pointers, e.g. torch tensors' data_ptr()).
-    impl: 0 default (1), 1 streaming envelope (any line length <= 4096; what the detector runs), 2 parallel-in-q (lines <= 1024)."""
+    impl: 0 default (1), 1 streaming envelope (any line length <= 4096), 2 parallel-in-q (lines <= 1024), 3 streaming with lagged-scan
+    emission, 4 windowed certified evaluation with replay (the detector's default transform).  Identical results."""
 
     def __init__(self, n, h, w, defw4, anchor_xy, impl=0):
         self.n, self.h, self.w = n, h, w
@@ -520,6 +521,10 @@ class Dt2dPlan:
 
     def impl(self):
         return _lib.lib().pbd_dt2d_plan_impl(self._p)
+
+    def replayed(self):
+        """impl 4: lines handed to the stack algorithm since the last call (synchronises)"""
+        return int(_lib.lib().pbd_dt2d_plan_replayed(self._p))
 
     def run(self, d_in, d_out, d_ix, d_iy, backptr_mode=0, stream=0):
         _lib.check(_lib.lib().pbd_dt2d_plan_run(self._p, C.c_void_p(stream), C.c_void_p(d_in), C.c_void_p(d_out), C.c_void_p(d_ix), C.c_void_p(d_iy),

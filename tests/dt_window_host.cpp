@@ -11,7 +11,7 @@
 
 using namespace pbd;
 
-static long long g_cause[8];   // refusal causes (diagnostics): 0 non-finite, 1 local replay conditions, 2 edge, 3 third open position, 4 open neighbour
+static long long g_cause[8];   // refusal causes (diagnostics): 0 non-finite, 1 local replay conditions, 2 edge, 3 more open positions than the list holds, 4 open neighbour
 
 template <int W>
 static int line_w(const float* src, int N, const dtw::WinParams& P, float w_sq, float w_lin, int os, float* dst, uint16_t* ptr, long long* tier2) {
@@ -23,9 +23,9 @@ static int line_w(const float* src, int N, const dtw::WinParams& P, float w_sq, 
   double rcp[env::kRcp];
   for (int d = 0; d < env::kRcp; ++d) rcp[d] = env::table_rcp(a, d);
   const env::Quad f = env::make_quad(w_sq, w_lin, nullptr, rcp);
-  int open[2];
-  int nopen = 0;
+  std::vector<int> open;                                             // positions no tier certified, in increasing order
   std::vector<int> state(N, 0);                                      // 1: certified by tier 1 / 2
+  constexpr int kCap = 256;                                          // the device kernel's list capacity
   for (int q = 0; q < N; ++q) {
     const int p = os + q;
     float y[2 * W + 1], c[2 * W + 1];
@@ -39,25 +39,25 @@ static int line_w(const float* src, int N, const dtw::WinParams& P, float w_sq, 
       if (tier2) ++*tier2;
       j = dtw::pick_exact<W>(y, P.ed, P.margin1, P.cmax, P.ylim);
     }
-    if (j < 0) {                                                     // open: decided after the walk, like the device kernel does
-      if (nopen == 2) { dirty = 1; ++g_cause[3]; continue; }
-      open[nopen++] = q;
-      continue;
-    }
+    if (j < 0) { open.push_back(q); continue; }
     if (!dtw::edge_ok(j, W, q, N)) { dirty = 1; ++g_cause[2]; continue; }
     dst[q] = dtw::value_of(P.ed[j], y[j]);
     ptr[q] = (uint16_t)(p - W + j);
     state[q] = 1;
   }
-  for (int k = 0; k < nopen && !dirty; ++k) {
-    const int q0 = open[k], p0 = os + q0;
-    if ((q0 > 0 && !state[q0 - 1]) || (q0 < N - 1 && !state[q0 + 1])) { dirty = 1; ++g_cause[4]; break; }
-    const int uL = q0 > 0 ? ptr[q0 - 1] : 0, uR = q0 < N - 1 ? ptr[q0 + 1] : N - 1;
-    if (!dtw::local_ok(W, os, N, q0, uL, uR)) { dirty = 1; ++g_cause[1]; break; }
-    float yo;
-    const int v = dtw::local_owner(f, p0, uL, uR, [&](int u) { return src[u]; }, &yo);
-    dst[q0] = dtw::value_of(env::table_E(a, b, p0 - v), yo);
-    ptr[q0] = (uint16_t)v;
+  if ((int)open.size() > kCap) { dirty = 1; ++g_cause[3]; }
+  for (size_t k = 0; k < open.size() && !dirty;) {
+    size_t e = k;
+    while (e + 1 < open.size() && open[e + 1] == open[e] + 1) ++e;   // a run of consecutive open positions
+    const int qa = open[k], qb = open[e];
+    if ((qa > 0 && !state[qa - 1]) || (qb < N - 1 && !state[qb + 1])) { dirty = 1; ++g_cause[4]; break; }
+    const int uL = qa > 0 ? ptr[qa - 1] : 0, uR = qb < N - 1 ? ptr[qb + 1] : N - 1;
+    if (!dtw::local_ok(W, os, N, qa, qb, uL, uR)) { dirty = 1; ++g_cause[1]; break; }
+    dtw::local_owners(f, qa + os, qb + os, uL, uR, [&](int u) { return src[u]; }, [&](int p, int v, float yo) {
+      dst[p - os] = dtw::value_of(env::table_E(a, b, p - v), yo);
+      ptr[p - os] = (uint16_t)v;
+    });
+    k = e + 1;
   }
   return dirty;
 }

@@ -165,3 +165,13 @@ def test_fuzz_short_quantised_lines_local_replay():
         assert r is not None
         refused += r[0]; total += 96
     assert 0 < refused < total
+
+
+def test_long_score_scale_lines_are_accepted():
+    """4096-sample lines at the scale of the model's response maps: the float spacing at positions up to 4095 is 16x that of a VGA
+    line, so several positions per line are open after tier 1 and a few after tier 2 -- the local replay must take care of them."""
+    rng = np.random.default_rng(77)
+    src = (rng.standard_normal((24, 4096)) * 0.01).astype(np.float32)
+    d, t2 = run_window(src, 0.015, 0.003, 2, 5)
+    assert d <= 2, d
+    assert t2 > 24                     # tier 1 does leave positions open on such lines

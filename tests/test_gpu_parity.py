@@ -140,12 +140,13 @@ def test_dt2d_bitexact(h, w, mode):
         assert np.array_equal(iy[i], y), i
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4])
 @pytest.mark.parametrize("h,w", [(1, 1), (3, 2), (33, 65), (118, 158), (268, 478), (60, 700)])
 def test_dt2d_both_kernel_generations_bitexact(h, w, impl):
     """The streaming envelope (impl 1: one lane per line) and the parallel-in-q kernels (impl 2: a warp per batch of lines in shared
-    memory; straight-line variants up to 256 samples, loops beyond) and the streaming envelope with lagged-scan emission (impl 3) against
-    the oracle, through the pre-allocated plan API."""
+    memory; straight-line variants up to 256 samples, loops beyond), the streaming envelope with lagged-scan emission (impl 3) and the
+    windowed certified evaluation (impl 4; maps whose anchors exceed the window replay every line) against the oracle, through the
+    pre-allocated plan API."""
     import torch
     from partsbaseddetector_b200 import Dt2dPlan
     rng = np.random.default_rng(h * 977 + w + impl)
@@ -173,6 +174,39 @@ def test_dt2d_both_kernel_generations_bitexact(h, w, impl):
             assert np.array_equal(out[i], o), (i, mode)
             assert np.array_equal(ix[i].astype(np.int32), x), (i, mode)
             assert np.array_equal(iy[i].astype(np.int32), y), (i, mode)
+    plan.close()
+
+
+@pytest.mark.parametrize("h,w", [(118, 158), (300, 1100), (2050, 64)])
+def test_dt2d_windowed_on_score_like_maps(h, w):
+    """impl 4 where it is meant to run: maps at the scale of the person model's responses (sigma 0.01 against deformation weights
+    0.01-0.02, anchors within the window): bit-identical to the oracle with (almost) no line replayed; plus one map of unit-variance
+    noise in the same plan, which is replayed wholesale and still exact."""
+    import torch
+    from partsbaseddetector_b200 import Dt2dPlan
+    rng = np.random.default_rng(h + 31 * w)
+    n = 6
+    maps = (rng.standard_normal((n, h, w)) * 0.01).astype(np.float32)
+    maps[1] += (np.add.outer(np.sin(np.arange(h) / 9.0), np.cos(np.arange(w) / 13.0)) * 0.2).astype(np.float32)
+    maps[5] = rng.standard_normal((h, w)).astype(np.float32)
+    defw = np.stack([rng.uniform(0.01, 0.02, n), rng.uniform(-0.02, 0.02, n), rng.uniform(0.01, 0.02, n), rng.uniform(-0.02, 0.02, n)], axis=1).astype(np.float32)
+    anchors = np.stack([rng.integers(-3, 4, n), rng.integers(-2, 6, n)], axis=1).astype(np.int32)
+    plan = Dt2dPlan(n, h, w, defw, anchors, 4)
+    d_in = torch.from_numpy(maps).cuda()
+    d_out = torch.empty_like(d_in)
+    d_ix = torch.empty((n, h, w), dtype=torch.int16, device="cuda")
+    d_iy = torch.empty_like(d_ix)
+    plan.replayed()
+    plan.run(d_in.data_ptr(), d_out.data_ptr(), d_ix.data_ptr(), d_iy.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    replayed = plan.replayed()
+    out, ix, iy = d_out.cpu().numpy(), d_ix.cpu().numpy().view(np.uint16), d_iy.cpu().numpy().view(np.uint16)
+    L = oracle_lib.lib()
+    for i in range(n):
+        o, x, y = np.empty((h, w), np.float32), np.empty((h, w), np.int32), np.empty((h, w), np.int32)
+        L.orc_dt2d_f32(maps[i].reshape(-1), h, w, defw[i], int(anchors[i, 0]), int(anchors[i, 1]), 0, o.reshape(-1), x.reshape(-1), y.reshape(-1))
+        assert np.array_equal(out[i], o), i
+        assert np.array_equal(ix[i].astype(np.int32), x) and np.array_equal(iy[i].astype(np.int32), y), i
+    assert (h + w) * 0.5 <= replayed <= (h + w) * 1.6, replayed       # the noise map's lines (most of them), hardly any of the others
     plan.close()
 
 
