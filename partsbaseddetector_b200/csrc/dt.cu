@@ -231,6 +231,9 @@ __device__ __noinline__ bool win_resolve_open(const float* __restrict__ src, int
   return true;
 }
 
+#ifndef PBD_DTW_RIN
+#define PBD_DTW_RIN 2             // tier 1 counts the candidates within this many samples of the position one by one; the outer ring only has to lie below the threshold (dt_window.cuh)
+#endif
 #ifndef PBD_DTW_MINBLOCKS
 #define PBD_DTW_MINBLOCKS 5       // 102 registers: the 16-slot window, the 2W+1 table values and the 2W+1 candidates stay in registers
 #endif
@@ -325,7 +328,7 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
       float c[2 * W + 1];
 #pragma unroll
       for (int j = 0; j <= 2 * W; ++j) c[j] = __fadd_rn(buf[(u + 16 - 2 * W + j) & 15], ef[j]);
-      const int jj = dtw::pick<W>(c, tau0, ylim);
+      const int jj = dtw::pick<W, (PBD_DTW_RIN < W ? PBD_DTW_RIN : W)>(c, tau0, ylim);
       // decided here only if certified strictly inside the window; anything else (tier 1 open, owner at the window's edge) is an
       // open position, resolved after the walk (a second open position of the same line: the line is replayed)
       const bool inner = (unsigned)(jj - 1) <= (unsigned)(2 * W - 2);

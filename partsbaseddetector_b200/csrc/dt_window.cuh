@@ -111,27 +111,47 @@ PBD_ENV_FN float max3_nan(float a, float b, float c) {
 template <int K> PBD_ENV_FN void count_ge(float& acc, float c, float thr) { if (c >= thr) acc += (float)K; }
 #endif
 
-template <int W, int J>
-PBD_ENV_FN void count_all(const float (&c)[2 * W + 1], float thr, float& a0, float& a1) {
-  if constexpr (J <= 2 * W) {
+template <int W, int J, int JEND>
+PBD_ENV_FN void count_range(const float (&c)[2 * W + 1], float thr, float& a0, float& a1) {
+  if constexpr (J <= JEND) {
     if constexpr (J & 1) count_ge<0x100 + J>(a1, c[J], thr); else count_ge<0x100 + J>(a0, c[J], thr);
-    count_all<W, J + 1>(c, thr, a0, a1);
+    count_range<W, J + 1, JEND>(c, thr, a0, a1);
   }
 }
 
 // Tier 1.  c[j] = fl(y_j + ef[j]) (-inf where the sample does not exist).  Returns the certified candidate or a negative number.
-template <int W>
+// The candidates within RIN samples of the position (j in [W - RIN, W + RIN]; on score maps 99.9 % of the owners: measured offsets
+// 0 / 1 / 2 / 3 = 75 % / 25 % / 0.2 % / 0.03 %) are counted one by one against the threshold; the candidates of the outer ring only have
+// to lie BELOW it, so one NaN-propagating maximum and one comparison stand for their 2 (W - RIN) compare-and-count pairs.  The
+// certificate is the same statement as before -- exactly one candidate of the whole window at or above best - tau -- restricted to
+// owners of the inner ring; an owner in the outer ring leaves the position to tier 2 (which looks at the whole window again).
+template <int W, int RIN = (W > 2 ? 2 : W)>
 PBD_ENV_FN int pick(const float (&c)[2 * W + 1], float tau0, float ylim) {
-  float best = c[0];
+  static_assert(RIN >= 1 && RIN <= W, "inner ring inside the window");
+  constexpr int LO = W - RIN, HI = W + RIN;
+  float best = c[LO];
 #pragma unroll
-  for (int j = 1; j + 1 <= 2 * W; j += 2) best = max3_nan(best, c[j], c[j + 1]);       // 2W + 1 is odd: pairs after c[0]
+  for (int j = LO + 1; j + 1 <= HI; j += 2) best = max3_nan(best, c[j], c[j + 1]);     // 2 RIN + 1 is odd: pairs after c[LO]
   const float thr = env::fsub_r(env::fsub_r(best, tau0), env::fmul_r(fabsf(best), 4.76837158203125e-07f));   // 2^-21
   float a0 = 0.f, a1 = 0.f;
-  count_all<W, 0>(c, thr, a0, a1);
-  // exactly one candidate at or above the threshold <=> the sum is 256 + j; none: 0; two or more: >= 512.  A NaN or too large best
-  // fails the second test (and a NaN threshold counts nothing).
+  count_range<W, LO, HI>(c, thr, a0, a1);
+  bool outer_below = true;
+  if constexpr (RIN < W) {
+    // outer ring: j in [0, LO) and (HI, 2W], an even number of candidates
+    float o[2 * (W - RIN)];
+#pragma unroll
+    for (int j = 0; j < LO; ++j) { o[j] = c[j]; o[LO + j] = c[HI + 1 + j]; }
+    float mo = o[0];
+    int i = 1;
+#pragma unroll
+    for (; i + 1 < 2 * (W - RIN); i += 2) mo = max3_nan(mo, o[i], o[i + 1]);
+    mo = max3_nan(mo, o[2 * (W - RIN) - 1], o[2 * (W - RIN) - 1]);                     // the count is even: one candidate is left over
+    outer_below = mo < thr;                                                            // false for a NaN candidate or a NaN threshold
+  }
+  // exactly one inner candidate at or above the threshold <=> the sum is 256 + j; none: 0; two or more: >= 512.  A NaN or too large
+  // best fails the last test (and a NaN threshold counts nothing).
   const int j = (int)env::fadd_r(a0, a1) - 0x100;
-  return ((unsigned)j <= (unsigned)(2 * W) && fabsf(best) <= ylim) ? j : -1;
+  return ((unsigned)(j - LO) <= (unsigned)(2 * RIN) && outer_below && fabsf(best) <= ylim) ? j : -1;
 }
 
 // Tier 2.  y[j] = the window's samples (-inf where none).  Returns the certified candidate or -1.

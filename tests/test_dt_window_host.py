@@ -80,7 +80,9 @@ def test_smooth_maps_are_mostly_accepted():
     for os_ in (1, -5, 5):
         d, t2 = run_window(src, 0.0156, -0.014, os_, 5)
         assert d <= 20, d              # < 5 % of the lines
-        assert t2 < 0.01 * src.size
+        # tier 1 counts only the candidates within 2 samples of the position: the |os| - 2 positions at a line's end whose window
+        # centre lies that far outside the line always go to tier 2
+        assert t2 < 0.01 * src.size + src.shape[0] * max(abs(os_) - 2, 0)
 
 
 @pytest.mark.parametrize("W", [3, 5])
