@@ -206,6 +206,7 @@ int pbd_set_option(pbd_detector* d, const char* key, double value) {
     else if (k == "dp_streams") { REQUIRE(value >= 1 && value <= 8, "dp_streams must be 1..8"); e.dp_streams = (int)value; }
     else if (k == "graph") e.use_graph = value != 0;
     else if (k == "dt_variant") { REQUIRE(value == 0 || value == 1 || value == 2 || value == 3, "dt_variant must be 0 (double break points), 1 (certified fp32 break points), 2 (lagged scan) or 3 (windowed certified transform)"); e.dt_scan = (int)value; }
+    else if (k == "dt_segment") { REQUIRE(value == -1 || value == 0 || (value >= 16 && value <= 4096 && (int)value % 16 == 0), "dt_segment must be -1 (automatic), 0 (off) or a multiple of 16 (steps per line segment)"); e.dt_segment = (int)value; }
     else if (k == "root_nms") { REQUIRE(value >= 0 && value <= 64, "root_nms window must be 0 (off) .. 64"); e.root_nms = (int)value; }
     else throw ArgError("unknown option '" + k + "'");
   });
@@ -227,6 +228,7 @@ int pbd_get_option(const pbd_detector* d, const char* key, double* value) {
     else if (k == "graph") *value = e.use_graph;
     else if (k == "response_kernel") *value = e.last_response_kernel;
     else if (k == "dt_variant") *value = e.dt_scan;
+    else if (k == "dt_segment") *value = e.dt_segment;
     else if (k == "dt_replayed_lines") *value = (double)const_cast<Engine&>(e).dt_replayed_lines();
     else if (k == "root_nms") *value = e.root_nms;
     else if (k == "nms_overlap") *value = e.nms_overlap;

@@ -197,7 +197,8 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
 constexpr int kOpenCap = 256;
 template <int W>
 __device__ __noinline__ bool win_resolve_open(const float* __restrict__ src, int N, int os, int nlines, const PassMap& M,
-                                              const dtw::WinParams* __restrict__ wp, float* dst, unsigned short* dp, int* olist, int nd) {
+                                              const dtw::WinParams* __restrict__ wp, float* dst, unsigned short* dp, int* olist, int nd,
+                                              int sqa, int sqb) {
   const Quad f = env::make_quad(M.w_sq, M.w_lin, M.etab + M.tab_bias, M.etab + (M.tab_len - kDtRcp));
   int left = 0;
   for (int k = 0; k < nd; ++k) {                                  // tier 2
@@ -219,8 +220,23 @@ __device__ __noinline__ bool win_resolve_open(const float* __restrict__ src, int
     int e = k;
     while (e + 1 < left && olist[e + 1] == olist[e] + 1) ++e;
     const int qa = olist[k], qb = olist[e];
-    // the neighbours of the run are certified (walk or tier 2): their owners were stored by this thread
-    const int uL = qa > 0 ? (int)dp[(size_t)(qa - 1) * nlines] : 0, uR = qb < N - 1 ? (int)dp[(size_t)(qb + 1) * nlines] : N - 1;
+    // the neighbours of the run are certified (walk or tier 2): their owners were stored by this thread -- unless the neighbour belongs
+    // to another segment of the line (segmented walk: this thread owns the positions sqa .. sqb-1 only), in which case it is certified
+    // here, by tier 2 on its own window
+    auto owner_at = [&](int q, int& u) -> bool {
+      if (q >= sqa && q < sqb) { u = (int)dp[(size_t)q * nlines]; return true; }
+      const int pn = q + os;
+      float w[2 * W + 1];
+#pragma unroll
+      for (int j = 0; j <= 2 * W; ++j) { const int v = pn - W + j; w[j] = (unsigned)v < (unsigned)N ? __ldg(src + v) : -INFINITY; }
+      const int jb = dtw::pick_exact<W>(w, wp->ed, wp->margin1, wp->cmax, wp->ylim);
+      if (jb < 0 || !dtw::edge_ok(jb, W, q, N)) return false;
+      u = pn - W + jb;
+      return true;
+    };
+    int uL = 0, uR = N - 1;
+    if (qa > 0 && !owner_at(qa - 1, uL)) return false;
+    if (qb < N - 1 && !owner_at(qb + 1, uR)) return false;
     if (!dtw::local_ok(W, os, N, qa, qb, uL, uR)) return false;
     dtw::local_owners(f, qa + os, qb + os, uL, uR, [&](int u) { return __ldg(src + u); }, [&](int p, int v, float yo) {
       dst[(size_t)(p - os) * nlines] = dtw::value_of(env::ld_table(f.E, p - v), yo);
@@ -237,11 +253,22 @@ __device__ __noinline__ bool win_resolve_open(const float* __restrict__ src, int
 #ifndef PBD_DTW_MINBLOCKS
 #define PBD_DTW_MINBLOCKS 5       // 102 registers: the 16-slot window, the 2W+1 table values and the 2W+1 candidates stay in registers
 #endif
-template <int MAXN, int W>
+// SEG = true: the SEGMENTED walk for launches that cannot fill the GPU (a single frame: the pass otherwise lasts as long as one lane needs
+// for the longest line of the pyramid, 50 us at VGA).  The windowed decision of a position depends on nothing but its 2W+1 samples, so a
+// line is cut into segments of seg_steps - 2W positions, each walked by its own lane over the samples [qa + os - W, qb - 1 + os + W]
+// (seg_steps steps, the first 2W of which only fill the window).  Samples that do not exist (beyond either end of the line) are staged
+// as kVirt, a finite value below every admissible sample.  Open positions are resolved as before; a neighbour that belongs to another
+// segment is certified on the spot (win_resolve_open).  The certificate is a statement about the WHOLE line (the margins of the
+// windows chain from position to position, dt_window.cuh), so a line is accepted only if all of its segments are: every lane adds its
+// verdict to the line's counter (seg_ctr, one int per line: segments done in the low half, refusals in the high half), and the lane
+// that finishes a line last replays the whole line with the stack algorithm if any segment refused it -- ordered after the other
+// segments' stores by the fence / atomic pair -- and leaves the counter at zero for the next launch.
+constexpr float kVirt = -3.0e38f;
+template <int MAXN, int W, bool SEG>
 __global__ void __launch_bounds__(kPassWarps * 32, PBD_DTW_MINBLOCKS)
 dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, const dtw::WinParams* __restrict__ wps, int nmaps,
             const float* __restrict__ inA, size_t strideA, const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out,
-            unsigned short* __restrict__ ptr, size_t stride_ptr, int* __restrict__ counter) {
+            unsigned short* __restrict__ ptr, size_t stride_ptr, int* __restrict__ counter, int seg_steps, int* __restrict__ seg_ctr, int seg_lines_total) {
   static_assert(2 * W + 1 <= 16, "the circular window has 16 slots");
   // per warp: the double-buffered input tile (the replay's stack ring reuses it) and the 16-sample ring the winner's sample is re-read from
   constexpr int kTileFloats = 2 * 32 * (kTileW + 1);
@@ -251,43 +278,71 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float (*tiles)[32][kTileW + 1] = reinterpret_cast<float (*)[32][kTileW + 1]>(tile_mem[wib]);
   int w = blockIdx.x * kPassWarps + wib;                          // warp index -> (level, first item)
-  int l = 0, nlines = 0, items = 0;
+  const int seglen = SEG ? seg_steps - 2 * W : 1;                 // positions per segment
+  int l = 0, nlines = 0, items = 0, nseg = 1;
+  int line_base = 0, lines_total = 0;                             // SEG: index of the level's first line / lines of one frame in seg_ctr
   for (; l < pg->n_levels; ++l) {
     nlines = pg->nlines[l];
-    items = nlines * nmaps;
+    if constexpr (SEG) nseg = (pg->N[l] + seglen - 1) / seglen;
+    items = nlines * nmaps * nseg;
     const int nw = (items + 31) >> 5;
     if (w < nw) break;
     w -= nw;
+    line_base += nlines * nmaps;
   }
   if (l >= pg->n_levels) return;                                  // warp-uniform
+  if constexpr (SEG) lines_total = seg_lines_total;
   const int frame = blockIdx.y;
   const int N = pg->N[l];
   const size_t cell_off = (size_t)pg->cell_off[l];
   const int t0 = w * 32;
   const bool active = t0 + lane < items;
   const int t = active ? t0 + lane : t0;                          // inactive lanes shadow the warp's first item
-  const int mi = t / nlines, line = t - mi * nlines;
+  int mi, line, qa = 0, qb = N;
+  if (SEG) {                                                      // item = (map, segment, line): the lanes of a warp mostly share a segment
+    const int per_map = nlines * nseg;
+    mi = t / per_map;
+    const int r = t - mi * per_map, sg = r / nlines;
+    line = r - sg * nlines;
+    qa = sg * seglen; qb = min(N, qa + seglen);
+  } else {
+    mi = t / nlines; line = t - mi * nlines;
+  }
   const PassMap M = maps[mi];
   const dtw::WinParams* wp = wps + mi;
   const float* src = (M.in_buf ? inB + (size_t)frame * strideB : inA + (size_t)frame * strideA) + M.in_off + cell_off + (size_t)line * N;
   float* dst = out + (size_t)frame * stride_out + M.out_off + cell_off + line;
   unsigned short* dp = ptr + (size_t)frame * stride_ptr + M.ptr_off + cell_off + line;
+  const int os = M.os;
+  // step i of the segmented walk reads sample sbase + i and completes the window of position qa + i - 2W
+  const int sbase = SEG ? qa + os - W : 0;
+  const long long srcw = (long long)src + (long long)sbase * 4;   // address of the (possibly virtual) sample of step 0
+  const int lohi = SEG ? (max(0, -sbase) | (min(max(N - sbase, 0), 0xffff) << 8)) : 0;   // steps [lo, hi) have a sample (lo <= 2W < 256)
   const int c_col = lane & (kTileW - 1), c_row0 = lane / kTileW;
   auto prefetch = [&](int q, int buf) {
 #pragma unroll
     for (int i = 0; i < 32 * kTileW / 32; ++i) {
       const int r = c_row0 + i * (32 / kTileW);
-      const float* p = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
-      if (q + c_col < N) cp_async4(&tiles[buf][r][c_col], p + q + c_col);
+      if (SEG) {
+        const float* p = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)srcw, r);
+        const int lh = __shfl_sync(0xffffffffu, lohi, r);
+        const int k = q + c_col;
+        if (k >= (lh & 0xff) && k < (lh >> 8)) cp_async4(&tiles[buf][r][c_col], p + k);
+        else tiles[buf][r][c_col] = kVirt;
+      } else {
+        const float* p = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
+        if (q + c_col < N) cp_async4(&tiles[buf][r][c_col], p + q + c_col);
+      }
     }
     cp_async_commit();
   };
+  const int steps = SEG ? seg_steps : (N + 2 * W + 15) & ~15;
   auto loady = [&](int q) -> float {                              // q = 0, 1, 2, ... in lock step across the warp
     if ((q & (kTileW - 1)) == 0) {
       if (q == 0) prefetch(0, 0);
       cp_async_wait_all();
       __syncwarp();
-      if (q + kTileW < N) prefetch(q + kTileW, ((q / kTileW) + 1) & 1);
+      if (q + kTileW < (SEG ? steps : N)) prefetch(q + kTileW, ((q / kTileW) + 1) & 1);
     }
     return tiles[(q / kTileW) & 1][lane][q & (kTileW - 1)];
   };
@@ -296,7 +351,6 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
     const unsigned off = (unsigned)i * (unsigned)nlines;
     st_f32(dst, off, val); st_u16(dp, off, v);
   };
-  const int os = M.os;
   bool refused = wp->ok == 0;
   float ef[2 * W + 1];
 #pragma unroll
@@ -311,20 +365,29 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
 #pragma unroll
   for (int k = 0; k < 16; ++k) myring[k * 32] = -INFINITY;        // samples before the line's start do not exist
   // sample index s = 0 .. N-1, then 2W (rounded up to the unroll) virtual -inf samples flush the window; no branch inside a step
-  const int steps = (N + 2 * W + 15) & ~15;
   int nd = 0;                                                     // positions left open by the walk, listed in olist (decided afterwards)
   int olist[kOpenCap];
-  unsigned off = (unsigned)(-os - W) * (unsigned)nlines;          // q * nlines of the current step's position (wraps while q < 0: never stored)
+  // q * nlines of the current step's position (wraps while q is outside the line / segment: never stored)
+  unsigned off = (unsigned)(SEG ? qa - 2 * W : -os - W) * (unsigned)nlines;
+  const int q0 = SEG ? qa - 2 * W : -os - W;                      // position of step 0
+  // positions stored: qlo <= q < qlo + qn.  In the segmented walk the shadow lanes of a warp's last, partly filled batch store nothing
+  // (the line's last finisher may rewrite it, and only the stores of lanes that vote are ordered before that)
+  const unsigned qlo = SEG ? (unsigned)qa : 0u, qn = (SEG && !active) ? 0u : (unsigned)(qb - qa);
+  const int vbase = SEG ? sbase - 2 * W : -2 * W;                 // owner = vbase + step + j
+  // the walk needs N + 2W steps (segmented: seg_steps, a multiple of 16); the unroll of 16 comes from the register window's static
+  // indexing, so a line may stop in the middle of the last round: one warp-uniform test per 16 steps
+  const int steps_needed = SEG ? steps : N + 2 * W;
   for (int s0 = 0; s0 < steps; s0 += 16) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int s = s0 + u;
       float y = -INFINITY;
-      if (s < N) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }  // warp-uniform
+      if (SEG) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }    // kVirt where the line has no sample: finite, passes the check
+      else if (s < N) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }  // warp-uniform
       buf[u] = y;
       myring[u * 32] = y;
-      const int q = s - os - W;                                   // the position whose last candidate is sample s
-      const bool valid = (unsigned)q < (unsigned)N;
+      const int q = q0 + s;                                       // the position whose last candidate is this step's sample
+      const bool valid = (unsigned)q - qlo < qn;
       float c[2 * W + 1];
 #pragma unroll
       for (int j = 0; j <= 2 * W; ++j) c[j] = __fadd_rn(buf[(u + 16 - 2 * W + j) & 15], ef[j]);
@@ -338,16 +401,54 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
       const int j = inner ? jj : W;
       const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
       const float val = dtw::value_of(__ldg(ed + j), yv);
-      st_pair_if_lt(dst, dp, off, val, (unsigned short)(s - 2 * W + j), (unsigned)q, (unsigned)N);
+      st_pair_if_lt(dst, dp, off, val, (unsigned short)(vbase + s + j), (unsigned)q - qlo, qn);
+      off += (unsigned)nlines;
+    }
+    if (s0 + 8 >= steps_needed) break;
+#pragma unroll
+    for (int u = 8; u < 16; ++u) {
+      const int s = s0 + u;
+      float y = -INFINITY;
+      if (SEG) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }    // kVirt where the line has no sample: finite, passes the check
+      else if (s < N) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }  // warp-uniform
+      buf[u] = y;
+      myring[u * 32] = y;
+      const int q = q0 + s;                                       // the position whose last candidate is this step's sample
+      const bool valid = (unsigned)q - qlo < qn;
+      float c[2 * W + 1];
+#pragma unroll
+      for (int j = 0; j <= 2 * W; ++j) c[j] = __fadd_rn(buf[(u + 16 - 2 * W + j) & 15], ef[j]);
+      const int jj = dtw::pick<W, (PBD_DTW_RIN < W ? PBD_DTW_RIN : W)>(c, tau0, ylim);
+      // decided here only if certified strictly inside the window; anything else (tier 1 open, owner at the window's edge) is an
+      // open position, resolved after the walk (a second open position of the same line: the line is replayed)
+      const bool inner = (unsigned)(jj - 1) <= (unsigned)(2 * W - 2);
+      const bool open = valid & !inner;
+      if (open) olist[min(nd, kOpenCap - 1)] = q;                 // rare (2e-4 of the positions on score maps): a local-memory store
+      nd += open ? 1 : 0;
+      const int j = inner ? jj : W;
+      const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
+      const float val = dtw::value_of(__ldg(ed + j), yv);
+      st_pair_if_lt(dst, dp, off, val, (unsigned short)(vbase + s + j), (unsigned)q - qlo, qn);
       off += (unsigned)nlines;
     }
   }
   if (nd > kOpenCap) refused = true;
   if (nd > 0 && !refused)                                         // ~2 % of the VGA lines: tier 2, then the local replay, for the open positions
-    refused = !win_resolve_open<W>(src, N, os, nlines, M, wp, dst, dp, olist, nd);
+    refused = !win_resolve_open<W>(src, N, os, nlines, M, wp, dst, dp, olist, nd, qa, qb);
   if (chk != chk) refused = true;
-  if (!(refused && active)) return;
-  // ---- replay: the reference's stack algorithm for this lane's line ----
+  if (SEG && nseg > 1) {
+    if (!active) return;
+    int* ctr = seg_ctr + (size_t)frame * lines_total + line_base + mi * nlines + line;
+    __threadfence();                                              // this segment's stores before its verdict
+    const int old = atomicAdd(ctr, 1 + (refused ? 0x10000 : 0));
+    if ((old & 0xffff) != nseg - 1) return;                       // another segment of the line is still at work: its lane decides
+    *ctr = 0;                                                     // last one: clean for the next launch
+    if (!refused && (old >> 16) == 0) return;                     // every segment certified: the line stands
+    __threadfence();
+  } else {
+    if (!(refused && active)) return;
+  }
+  // ---- replay: the reference's stack algorithm for this lane's line (all of it, also in the segmented walk) ----
   __syncwarp(__activemask());
   Ring& R = *reinterpret_cast<Ring*>(tile_mem[wib]);              // the tiles are dead (every lane of the warp has finished its walk)
   const Quad f = env::make_quad(M.w_sq, M.w_lin, M.etab + M.tab_bias, M.etab + (M.tab_len - kDtRcp));
@@ -482,7 +583,10 @@ dt_lines(const LineGeom* __restrict__ lg, const PassMap* __restrict__ maps, int 
 // ---------------------------------------------------------------------------------------------------
 // V = cells per thread: 4 (128-bit loads / stores, one 32-bit store of four Ik bytes) when cells_total is a multiple of 4 so that
 // every map base stays 16-byte aligned, else 1.  The job's bias matrix and slot tables are staged in shared memory once per block.
-template <int V>
+// PRE = true (launches too small to fill the GPU: single frames): the parent's maps are read before anything is written, so that the
+// loads of all parent mixtures are in flight together -- such a launch is a chain of memory latencies otherwise; large launches are
+// bandwidth-bound and keep the leaner register footprint (measured: PRE costs 2 % of the DP stage at 64 frames, saves 12 % of mix_max at 1).
+template <int V, bool PRE>
 __global__ void __launch_bounds__(256)
 mix_max(const Geometry* __restrict__ g, const PartJob* __restrict__ jobs, const float* __restrict__ resp, float* __restrict__ work,
         const float* __restrict__ val, unsigned char* __restrict__ ik, int nfilters, int nwork, int npm, int tmp_maps) {
@@ -511,7 +615,23 @@ mix_max(const Geometry* __restrict__ g, const PartJob* __restrict__ jobs, const 
       }
     }
   }
-  for (int pm = 0; pm < pnmix; ++pm) {
+  // the parent's maps are read before anything is written (a map is only ever rewritten in place, so the loads of all parent
+  // mixtures can be in flight together: a single frame's launch is a chain of memory latencies otherwise)
+  float pb[PRE ? kMaxMix : 1][V];
+#pragma unroll
+  for (int pm = 0; pm < kMaxMix; ++pm) {
+    if (PRE && pm < pnmix) {
+      const float* bp = J.first_touch ? resp + ((size_t)frame * nfilters + J.out_resp_fid[pm]) * ct + idx
+                                      : work + ((size_t)frame * nwork + J.out_work_slot[pm]) * ct + idx;
+      if (V == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(bp);
+        pb[pm][0] = t.x; pb[pm][1 % V] = t.y; pb[pm][2 % V] = t.z; pb[pm][3 % V] = t.w;
+      } else {
+        pb[pm][0] = *bp;
+      }
+    }
+  }
+  auto one_parent_mixture = [&](int pm, const float (&b)[V]) {
     float best[V];
     int bi[V];
 #pragma unroll
@@ -529,16 +649,32 @@ mix_max(const Geometry* __restrict__ g, const PartJob* __restrict__ jobs, const 
     }
     unsigned char* ikp = ik + ((size_t)frame * npm + J.pm_slot[pm]) * ct + idx;
     float* wp = work + ((size_t)frame * nwork + J.out_work_slot[pm]) * ct + idx;
-    const float* bp = J.first_touch ? resp + ((size_t)frame * nfilters + J.out_resp_fid[pm]) * ct + idx : wp;
     if (V == 4) {
       *reinterpret_cast<uchar4*>(ikp) = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1 % V], (unsigned char)bi[2 % V], (unsigned char)bi[3 % V]);
-      const float4 b4 = *reinterpret_cast<const float4*>(bp);
       float4 o;                                                     // parent.score += maxv, :155-156
-      o.x = __fadd_rn(b4.x, best[0]); o.y = __fadd_rn(b4.y, best[1 % V]); o.z = __fadd_rn(b4.z, best[2 % V]); o.w = __fadd_rn(b4.w, best[3 % V]);
+      o.x = __fadd_rn(b[0], best[0]); o.y = __fadd_rn(b[1 % V], best[1 % V]); o.z = __fadd_rn(b[2 % V], best[2 % V]); o.w = __fadd_rn(b[3 % V], best[3 % V]);
       *reinterpret_cast<float4*>(wp) = o;
     } else {
       *ikp = (unsigned char)bi[0];
-      *wp = __fadd_rn(*bp, best[0]);
+      *wp = __fadd_rn(b[0], best[0]);
+    }
+  };
+  if constexpr (PRE) {
+#pragma unroll
+    for (int pm = 0; pm < kMaxMix; ++pm)
+      if (pm < pnmix) one_parent_mixture(pm, pb[pm]);
+  } else {
+    for (int pm = 0; pm < pnmix; ++pm) {
+      const float* bp = J.first_touch ? resp + ((size_t)frame * nfilters + J.out_resp_fid[pm]) * ct + idx
+                                      : work + ((size_t)frame * nwork + J.out_work_slot[pm]) * ct + idx;
+      float b[V];
+      if (V == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(bp);
+        b[0] = t.x; b[1 % V] = t.y; b[2 % V] = t.z; b[3 % V] = t.w;
+      } else {
+        b[0] = *bp;
+      }
+      one_parent_mixture(pm, b);
     }
   }
 }
@@ -665,20 +801,55 @@ static void launch_pass_v(int maxn, dim3 grid, cudaStream_t s, A... args) {
 }
 template <typename... A>
 static void launch_pass(int maxn, dim3 grid, cudaStream_t s, A... args) { launch_pass_v<0>(maxn, grid, s, args...); }
-template <typename... A>
-static void launch_pass_win(int maxn, dim3 grid, cudaStream_t s, A... args) {
+template <bool SEG, typename... A>
+static void launch_pass_win_v(int maxn, dim3 grid, cudaStream_t s, A... args) {
   constexpr int W = kDtWindowW;
-  if (maxn <= 160) dt_pass_win<160, W><<<grid, kPassWarps * 32, 0, s>>>(args...);
-  else if (maxn <= 512) dt_pass_win<512, W><<<grid, kPassWarps * 32, 0, s>>>(args...);
-  else if (maxn <= 1024) dt_pass_win<1024, W><<<grid, kPassWarps * 32, 0, s>>>(args...);
-  else dt_pass_win<4096, W><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  if (maxn <= 160) dt_pass_win<160, W, SEG><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else if (maxn <= 512) dt_pass_win<512, W, SEG><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else if (maxn <= 1024) dt_pass_win<1024, W, SEG><<<grid, kPassWarps * 32, 0, s>>>(args...);
+  else dt_pass_win<4096, W, SEG><<<grid, kPassWarps * 32, 0, s>>>(args...);
+}
+// seg_steps = 0: one lane per line; otherwise lines are cut into segments of seg_steps - 2W positions (dt_pass_win<.., SEG = true>)
+template <typename... A>
+static void launch_pass_win(int maxn, int seg_steps, int* d_seg_ctr, int lines_total, dim3 grid, cudaStream_t s, A... args) {
+  if (seg_steps > 0 && d_seg_ctr) launch_pass_win_v<true>(maxn, grid, s, args..., seg_steps, d_seg_ctr, lines_total);
+  else launch_pass_win_v<false>(maxn, grid, s, args..., 0, (int*)nullptr, 0);
+}
+static int pass_lines(const PassGeom& pg, int nmaps) {
+  int n = 0;
+  for (int l = 0; l < pg.n_levels; ++l) n += pg.nlines[l] * nmaps;
+  return n;
 }
 
-// number of warps a pass needs for `nmaps` maps
-static int pass_warps(const PassGeom& pg, int nmaps) {
+// number of warps a pass needs for `nmaps` maps; seg_steps > 0: lines cut into segments of seg_steps - 2W positions (dt_pass_win<.., true>)
+static int pass_warps(const PassGeom& pg, int nmaps, int seg_steps = 0) {
   int w = 0;
-  for (int l = 0; l < pg.n_levels; ++l) w += (pg.nlines[l] * nmaps + 31) / 32;
+  const int seglen = seg_steps - 2 * kDtWindowW;
+  for (int l = 0; l < pg.n_levels; ++l) {
+    const int nseg = seg_steps > 0 ? (pg.N[l] + seglen - 1) / seglen : 1;
+    w += (pg.nlines[l] * nmaps * nseg + 31) / 32;
+  }
   return w;
+}
+// Segment length of the windowed walk for one pass.  A lane walks its line sequentially (about 0.3 us per sample), so a launch that
+// cannot fill the GPU lasts as long as the longest line of the pyramid; such launches (single frames, small batches) cut their lines
+// into the shortest segments that still fit the GPU's resident warps at once.  Launches that fill the GPU anyway keep one lane per line
+// (a segment re-reads 2W samples).  mode: -1 automatic, 0 never, otherwise the forced number of steps per segment (multiple of 16, >= 32).
+#ifndef PBD_DT_SEG_MIN
+#define PBD_DT_SEG_MIN 32
+#endif
+constexpr int kSegMinSteps = PBD_DT_SEG_MIN;      // shortest segment the automatic choice considers (steps; 2W of them fill the window)
+static int choose_seg_steps(const PassGeom& pg, int nmaps, int nframes, int warp_slots, int mode, const int* d_seg_ctr) {
+  int maxn = 1;
+  long long lines = 0;
+  for (int l = 0; l < pg.n_levels; ++l) { maxn = std::max(maxn, pg.N[l]); lines += (long long)pg.nlines[l] * nmaps; }
+  const int full = (maxn + 2 * kDtWindowW + 15) & ~15;              // steps of the unsegmented walk of the longest line
+  if (mode == 0 || !d_seg_ctr || lines * nframes > (long long)warp_slots * 32) return 0;   // one counter per line: warp_slots * 32 of them
+  if (mode > 0) return mode < full ? mode : 0;
+  if ((long long)pass_warps(pg, nmaps) * nframes * 2 > warp_slots) return 0;
+  for (int st = kSegMinSteps; st < full; st += 16)
+    if ((long long)pass_warps(pg, nmaps, st) * nframes <= warp_slots) return st;
+  return 0;
 }
 
 // ---- parallel-in-q launch plan ------------------------------------------------------------------------------------------
@@ -720,11 +891,13 @@ int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
                    const PassGeom& pg_cols, const PassGeom* d_pg_cols, const PassMap* d_maps_rows, const PassMap* d_maps_cols, int nmaps,
                    int max_ow, int max_oh, const PartJob* d_jobs, int njobs, int nfilters, int nwork, int ncm, int npm, int tmp_maps,
                    cudaStream_t s, void (*mark)(void*, int), void* mark_ctx, int scan, const dtw::WinParams* d_wp_rows,
-                   const dtw::WinParams* d_wp_cols, int* d_replayed) {
+                   const dtw::WinParams* d_wp_cols, int* d_replayed, int warp_slots, int seg_mode, int* d_seg_ctr) {
   if (nmaps <= 0 || njobs <= 0 || g.cells_total <= 0) return 0;
   const size_t ct = (size_t)g.cells_total;
-  dim3 gr((pass_warps(pg_rows, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
-  if (scan == 3) launch_pass_win(max_ow, gr, s, d_pg_rows, d_maps_rows, d_wp_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork,
+  const int seg_r = scan == 3 ? choose_seg_steps(pg_rows, nmaps, g.n_frames, warp_slots, seg_mode, d_seg_ctr) : 0;
+  const int seg_c = scan == 3 ? choose_seg_steps(pg_cols, nmaps, g.n_frames, warp_slots, seg_mode, d_seg_ctr) : 0;
+  dim3 gr((pass_warps(pg_rows, nmaps, seg_r) + kPassWarps - 1) / kPassWarps, g.n_frames);
+  if (scan == 3) launch_pass_win(max_ow, seg_r, d_seg_ctr, pass_lines(pg_rows, nmaps), gr, s, d_pg_rows, d_maps_rows, d_wp_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork,
                                  b.tmp, ct * tmp_maps, b.ixdt, ct * ncm, d_replayed);
   else if (scan == 2) launch_pass_v<4>(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
                                   ct * tmp_maps, b.ixdt, ct * ncm);
@@ -733,8 +906,8 @@ int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
   else launch_pass(max_ow, gr, s, d_pg_rows, d_maps_rows, nmaps, (const float*)b.resp, ct * nfilters, (const float*)b.work, ct * nwork, b.tmp,
                    ct * tmp_maps, b.ixdt, ct * ncm);
   if (mark) mark(mark_ctx, 2);
-  dim3 gc((pass_warps(pg_cols, nmaps) + kPassWarps - 1) / kPassWarps, g.n_frames);
-  if (scan == 3) launch_pass_win(max_oh, gc, s, d_pg_cols, d_maps_cols, d_wp_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps,
+  dim3 gc((pass_warps(pg_cols, nmaps, seg_c) + kPassWarps - 1) / kPassWarps, g.n_frames);
+  if (scan == 3) launch_pass_win(max_oh, seg_c, d_seg_ctr, pass_lines(pg_cols, nmaps), gc, s, d_pg_cols, d_maps_cols, d_wp_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps,
                                  b.val, ct * tmp_maps, b.iyraw, ct * ncm, d_replayed);
   else if (scan == 2) launch_pass_v<4>(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
                                   ct * tmp_maps, b.iyraw, ct * ncm);
@@ -743,12 +916,15 @@ int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
   else launch_pass(max_oh, gc, s, d_pg_cols, d_maps_cols, nmaps, (const float*)b.tmp, ct * tmp_maps, (const float*)b.tmp, ct * tmp_maps, b.val,
                    ct * tmp_maps, b.iyraw, ct * ncm);
   if (mark) mark(mark_ctx, 3);
+  const bool pre = (long long)g.cells_total * njobs * g.n_frames < (long long)warp_slots * 32 * 16;   // under ~16 cells per resident thread
   if (g.cells_total % 4 == 0) {
     dim3 gm((g.cells_total / 4 + 255) / 256, njobs, g.n_frames);
-    mix_max<4><<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
+    if (pre) mix_max<4, true><<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
+    else mix_max<4, false><<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
   } else {
     dim3 gm((g.cells_total + 255) / 256, njobs, g.n_frames);
-    mix_max<1><<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
+    if (pre) mix_max<1, true><<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
+    else mix_max<1, false><<<gm, 256, 0, s>>>(d_g, d_jobs, b.resp, b.work, b.val, b.ik, nfilters, nwork, npm, tmp_maps);
   }
   if (mark) mark(mark_ctx, 4);
   return 3;
@@ -788,8 +964,8 @@ int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const Pa
   pr.nlines[0] = h; pr.N[0] = w; pc.nlines[0] = w; pc.N[0] = h;
   dim3 gr((pass_warps(pr, n_maps) + kPassWarps - 1) / kPassWarps, 1), gc((pass_warps(pc, n_maps) + kPassWarps - 1) / kPassWarps, 1);
   if (scan == 3 && d_wp2) {                                         // windowed certified evaluation (dt_pass_win): rows, then columns
-    launch_pass_win(w, gr, s, d_pg2, d_maps2, d_wp2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0, d_replayed);
-    launch_pass_win(h, gc, s, d_pg2 + 1, d_maps2 + n_maps, d_wp2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out,
+    launch_pass_win(w, 0, (int*)nullptr, 0, gr, s, d_pg2, d_maps2, d_wp2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0, d_replayed);
+    launch_pass_win(h, 0, (int*)nullptr, 0, gc, s, d_pg2 + 1, d_maps2 + n_maps, d_wp2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out,
                     (size_t)0, d_iyraw, (size_t)0, d_replayed);
   } else if (scan) {
     launch_pass_v<4>(w, gr, s, d_pg2, d_maps2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0);

@@ -110,7 +110,7 @@ void Engine::release() {
   void* ptrs[] = {d_wtc_, d_wtc16_, d_f16_, d_fhi_, d_flo_, d_tc_levels_, d_tc_tiles_, d_wpacked_, d_wgeneric_, d_foff_, d_fkh_, d_fkw_, d_jobs_, d_roots_, d_parent_, d_nparts_, d_cm_slot_, d_pm_slot_,
                   d_g_, d_frames_own_, b_.pyr, b_.hist, b_.norm, b_.feat, b_.resp, b_.work, b_.tmp, b_.val, b_.ixdt, b_.iyraw, b_.ik,
                   b_.rootv, b_.rooti, d_xofs_, d_yofs_, d_xalpha_, d_ybeta_, d_tile_level_, d_tile_first_,
-                  d_scratch_i_, d_rootkeep_, d_orient_lut_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_wp_rows_, d_wp_cols_, d_dtw_ctr_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
+                  d_scratch_i_, d_rootkeep_, d_orient_lut_, d_pg_, d_maps_rows_, d_maps_cols_, d_etab_, d_wp_rows_, d_wp_cols_, d_dtw_ctr_, d_seg_ctr_, d_frames_alt_, slots_[0].d_hits, slots_[0].d_nhits, slots_[0].d_xym,
                   slots_[1].d_hits, slots_[1].d_nhits, slots_[1].d_xym, d_ksize_, nms_.boxes, nms_.keys, nms_.skeys, nms_.sidx, nms_.kept_idx,
                   nms_.frame_count, nms_.fill, nms_.kept_count, nms_.out_off, nms_.seg_off, nms_.scratch, slots_[0].d_hits_out,
                   slots_[0].d_xym_out, slots_[0].d_total, slots_[1].d_hits_out, slots_[1].d_xym_out, slots_[1].d_total};
@@ -483,6 +483,11 @@ void Engine::build_batch_tables() {
     check_cuda(cudaMemcpyAsync(d_wp_rows_, wr.data(), wr.size() * sizeof(dtw::WinParams), cudaMemcpyHostToDevice, stream_), "upload window parameters");
     check_cuda(cudaMemcpyAsync(d_wp_cols_, wc.data(), wc.size() * sizeof(dtw::WinParams), cudaMemcpyHostToDevice, stream_), "upload window parameters");
   }
+  if (!d_seg_ctr_) {                                              // segmented walk: per-line verdict counters, one region per frame group (self-cleaning)
+    const size_t n = (size_t)kSegGroups * seg_lines_per_group();
+    check_cuda(cudaMalloc(&d_seg_ctr_, n * sizeof(int)), "cudaMalloc segment counters"); dev_bytes_ += n * sizeof(int);
+    check_cuda(cudaMemsetAsync(d_seg_ctr_, 0, n * sizeof(int), stream_), "clear segment counters");
+  }
   if (!d_dtw_ctr_) {
     check_cuda(cudaMalloc(&d_dtw_ctr_, 64 * sizeof(int)), "cudaMalloc replay counters"); dev_bytes_ += 64 * sizeof(int);
     check_cuda(cudaMemsetAsync(d_dtw_ctr_, 0, 64 * sizeof(int), stream_), "clear replay counters");
@@ -757,7 +762,7 @@ void Engine::run_dp_min() {
                                    d_maps_cols_ + wave_map_first_[wv], wave_map_count_[wv], max_ow_, max_oh_, d_jobs_ + wave_first_[wv],
                                    wave_count_[wv], nf, nwork_, ncm_, npm_, tmp_maps_, sp == 0 ? stream_ : dp_aux_[sp - 1],
                                    timing >= 2 ? +mark : nullptr, this, dt_scan, d_wp_rows_ + wave_map_first_[wv], d_wp_cols_ + wave_map_first_[wv],
-                                   d_dtw_ctr_ + (sp & 63));
+                                   d_dtw_ctr_ + (sp & 63), num_sms_ * 20, dt_segment, sp < kSegGroups ? d_seg_ctr_ + (size_t)sp * seg_lines_per_group() : nullptr);
       launches_ += n;
     }
   }
@@ -828,7 +833,7 @@ void Engine::enqueue_device(const uint8_t* d_frames, int n, int h, int w, int c)
   if (!use_graph || timing) { run_stages(); return; }
   GraphKey k;
   k.frames = d_frames; k.geom_serial = geom_serial_; k.n = n; k.resp_mode = resp_mode; k.backptr = backptr; k.max_candidates = max_candidates;
-  k.dp_streams = dp_streams; k.thresh = thresh; k.nms_overlap = nms_overlap; k.root_nms = root_nms; k.dt_scan = dt_scan;
+  k.dp_streams = dp_streams; k.thresh = thresh; k.nms_overlap = nms_overlap; k.root_nms = root_nms; k.dt_scan = dt_scan; k.dt_segment = dt_segment;
   if (graph_exec_ && k == graph_key_) {
     check_cuda(cudaGraphLaunch(graph_exec_, stream_), "cudaGraphLaunch");
     launches_ += graph_launches_;

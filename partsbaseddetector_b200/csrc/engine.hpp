@@ -74,6 +74,7 @@ class Engine {
   int last_response_kernel = -1;
   // dt_pass variant: 0 eager emission with double break points (default), 1 eager emission with certified fp32 break points (12 %
   // slower on B200), 2 lagged-scan emission (15 % slower on real score maps, 6.8x faster on white noise); results are identical
+  int dt_segment = -1;                         // dt_variant 3: lines cut into segments for launches that cannot fill the GPU: -1 automatic, 0 off, n = steps per segment
   int dt_scan = 3;                             // dt_variant: 3 = windowed certified evaluation with replay (dt_pass_win), 0 / 1 / 2 = stack kernels
   long long dt_replayed_lines();               // lines the windowed transform handed to the stack algorithm since the last call (synchronises)
   static constexpr int kMinFramesPerDpGroup = 4;
@@ -194,6 +195,9 @@ class Engine {
   // dt_variant 3 (dt_pass_win): per-map window parameters, parallel to d_maps_rows_ / d_maps_cols_; counters of replayed lines
   dtw::WinParams *d_wp_rows_ = nullptr, *d_wp_cols_ = nullptr; size_t cap_wp_rows_ = 0, cap_wp_cols_ = 0;
   int* d_dtw_ctr_ = nullptr;                   // [64] one per frame group
+  static constexpr int kSegGroups = 8;         // dp_streams <= 8
+  size_t seg_lines_per_group() const { return (size_t)num_sms_ * 20 * 32; }
+  int* d_seg_ctr_ = nullptr;                   // [kSegGroups][seg_lines_per_group()] per-line counters of the segmented windowed walk (dt.cu)
   // candidates
   // Result slots: the synchronous API uses slot 0; the pipelined submit/collect API alternates between the two so that the
   // candidates of batch i can be downloaded while batch i+1 is being computed.
@@ -238,11 +242,11 @@ class Engine {
   struct GraphKey {
     const uint8_t* frames = nullptr;
     long long geom_serial = -1;
-    int n = 0, resp_mode = -1, backptr = -1, max_candidates = 0, dp_streams = 0, root_nms = 0, dt_scan = 0;
+    int n = 0, resp_mode = -1, backptr = -1, max_candidates = 0, dp_streams = 0, root_nms = 0, dt_scan = 0, dt_segment = 0;
     double thresh = 0, nms_overlap = 0;
     bool operator==(const GraphKey& o) const {
       return frames == o.frames && geom_serial == o.geom_serial && n == o.n && resp_mode == o.resp_mode && backptr == o.backptr &&
-             max_candidates == o.max_candidates && dp_streams == o.dp_streams && root_nms == o.root_nms && dt_scan == o.dt_scan && thresh == o.thresh && nms_overlap == o.nms_overlap;
+             max_candidates == o.max_candidates && dp_streams == o.dp_streams && root_nms == o.root_nms && dt_scan == o.dt_scan && dt_segment == o.dt_segment && thresh == o.thresh && nms_overlap == o.nms_overlap;
     }
   };
   GraphKey graph_key_{}, warm_key_{};

@@ -185,7 +185,10 @@ int launch_dt_wave(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
                    cudaStream_t s, void (*mark)(void*, int) = nullptr, void* mark_ctx = nullptr,   // mark(ctx, kernel id) after each kernel
                    int scan = 0,                        // dt_pass variant: 0 double break points, 1 certified fp32 break points, 2 lagged-scan emission,
                                                         // 3 windowed certified evaluation (dt_pass_win; needs the per-map window parameters)
-                   const dtw::WinParams* d_wp_rows = nullptr, const dtw::WinParams* d_wp_cols = nullptr, int* d_replayed = nullptr);
+                   const dtw::WinParams* d_wp_rows = nullptr, const dtw::WinParams* d_wp_cols = nullptr, int* d_replayed = nullptr,
+                   int warp_slots = 0,                  // resident warps of dt_pass_win on the device (SMs x CTAs per SM x warps per CTA)
+                   int seg_mode = -1,                   // dt_variant 3, segmented walk: -1 automatic, 0 off, else steps per segment (dt.cu)
+                   int* d_seg_ctr = nullptr);           // warp_slots * 32 zeroed ints private to this stream: per-line verdict counters of the segmented walk
 int launch_root(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const RootJob* d_roots, int ncomp, int nfilters, int nwork,
                 cudaStream_t s);
 

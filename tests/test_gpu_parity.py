@@ -22,7 +22,7 @@ def detector(name):
         d.distributeModel(Model.load_bin(os.path.join(GOLDEN, name + ".pbdm")))
         _det_cache[name] = d
     d = _det_cache[name]
-    for k, v in (("exact", 1), ("backptr", 0), ("max_levels", 0), ("thresh", load_flat(name).thresh), ("dt_variant", 3), ("root_nms", 0), ("graph", 0)):
+    for k, v in (("exact", 1), ("backptr", 0), ("max_levels", 0), ("thresh", load_flat(name).thresh), ("dt_variant", 3), ("dt_segment", -1), ("root_nms", 0), ("graph", 0)):
         d.set_option(k, v)
     return d
 
@@ -506,9 +506,11 @@ def test_windowed_transform_equals_the_stack_algorithm(name, backptr):
     frames[3, 30:100, 20:150] = 200
     fm = load_flat(name)
     res = {}
-    for variant in (0, 3):
+    # (variant, dt_segment): the stack kernel, the windowed walk with one lane per line, and the SEGMENTED walk (lines of the 33 x 48
+    # cell level cut into 3 / 2 segments of 22 / 38 positions, as the detector does by itself for launches that cannot fill the GPU)
+    for variant, seg in ((0, 0), (3, 0), (3, 32), (3, 48), (3, -1)):
         d = detector(name)
-        d.set_option("dt_variant", variant); d.set_option("backptr", backptr)
+        d.set_option("dt_variant", variant); d.set_option("backptr", backptr); d.set_option("dt_segment", seg)
         if variant == 3:
             d.get_option("dt_replayed_lines")                        # reset the counter
         c = d.detect(frames)
@@ -521,16 +523,50 @@ def test_windowed_transform_equals_the_stack_algorithm(name, backptr):
             for p in range(1, len(fm.comps[0])):
                 npm = len(fm.comps[0][fm.comps[0][p].parentid].filterid)
                 maps.append(np.stack(d.backptr(f, 0, 0, p, npm - 1)))
-        res[variant] = (maps, [(a.frame, a.level, a.x.tolist(), a.y.tolist(), a.m.tolist(), float(a.score())) for a in c])
-        if variant == 3:
+        res[(variant, seg)] = (maps, [(a.frame, a.level, a.x.tolist(), a.y.tolist(), a.m.tolist(), float(a.score())) for a in c])
+        if (variant, seg) == (3, 0):
             replayed = d.get_option("dt_replayed_lines")
-        d.set_option("dt_variant", 3); d.set_option("backptr", 0)
-    assert len(res[0][0]) == len(res[3][0])
-    for i, (a, b) in enumerate(zip(res[0][0], res[3][0])):
-        assert np.array_equal(a, b), (name, i)
-    assert res[0][1] == res[3][1]
+        d.set_option("dt_variant", 3); d.set_option("backptr", 0); d.set_option("dt_segment", -1)
+    for key in ((3, 0), (3, 32), (3, 48), (3, -1)):
+        assert len(res[(0, 0)][0]) == len(res[key][0])
+        for i, (a, b) in enumerate(zip(res[(0, 0)][0], res[key][0])):
+            assert np.array_equal(a, b), (name, key, i)
+        assert res[(0, 0)][1] == res[key][1], key
     if name in ("Person_8parts", "Face_99filters", "Face_frontal_sparse"):
         assert replayed > 0                                          # anchors beyond the window: those maps' lines all take the replay path
+
+
+def test_segmented_walk_single_vga_frame_equals_the_oracle():
+    """A single VGA frame: the DP launches cannot fill the GPU, so dt_variant 3 cuts the lines into segments by itself (dt_segment -1).
+    Root maps, every arg-max map of the first and a middle level and the candidates must equal the CPU oracle; the forced segment
+    lengths give the same bits."""
+    name = "Person_26parts"
+    fm = load_flat(name)
+    img = synth_frame(4242)
+    O = oracle(name)
+    O.run(img, 1, 3)
+    thr = lowered_threshold(O)
+    O.set_thresh(thr)
+    O.run(None, 4, 4)
+    oc = O.candidates()
+    assert len(oc) > 0
+    for seg in (-1, 32, 64, 0):
+        d = detector(name)
+        d.set_option("thresh", thr); d.set_option("dt_segment", seg)
+        cands = d.detect(img)
+        for l in range(O.nlevels()):
+            assert np.array_equal(d.rootv(0, l, 0), O.rootv(l, 0)), (seg, l)
+            assert np.array_equal(d.rooti(0, l, 0), O.rooti(l, 0)), (seg, l)
+        for l in (0, 5):
+            for p in range(1, len(fm.comps[0])):
+                for pm in range(fm.nmix(0, fm.comps[0][p].parentid)):
+                    for a, b, what in zip(d.backptr(0, l, 0, p, pm), O.backptr(l, 0, p, pm), ("Ix", "Iy", "Ik")):
+                        assert np.array_equal(a, b), (seg, what, l, p, pm)
+        assert len(cands) == len(oc)
+        for g, o in zip(cands, oc):
+            assert g.level == o["level"] and np.array_equal(g.x, o["x"]) and np.array_equal(g.y, o["y"]) and np.array_equal(g.m, o["m"])
+            assert g.score() == o["score"]
+        d.set_option("dt_segment", -1)
 
 
 def test_cuda_graph_replay_equals_eager_launches():
