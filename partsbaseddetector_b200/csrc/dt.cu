@@ -247,6 +247,12 @@ __device__ __noinline__ bool win_resolve_open(const float* __restrict__ src, int
   return true;
 }
 
+// the walk's rare path: lists an open position (out of line on purpose: the walk pays one vote and one branch per step for it)
+__device__ __noinline__ int win_note_open(int* olist, int nd, int q, bool open) {
+  if (open) { olist[min(nd, kOpenCap - 1)] = q; ++nd; }
+  return nd;
+}
+
 #ifndef PBD_DTW_RIN
 #define PBD_DTW_RIN 2             // tier 1 counts the candidates within this many samples of the position one by one; the outer ring only has to lie below the threshold (dt_window.cuh)
 #endif
@@ -270,11 +276,11 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
             const float* __restrict__ inA, size_t strideA, const float* __restrict__ inB, size_t strideB, float* __restrict__ out, size_t stride_out,
             unsigned short* __restrict__ ptr, size_t stride_ptr, int* __restrict__ counter, int seg_steps, int* __restrict__ seg_ctr, int seg_lines_total) {
   static_assert(2 * W + 1 <= 16, "the circular window has 16 slots");
-  // per warp: the double-buffered input tile (the replay's stack ring reuses it) and the 16-sample ring the winner's sample is re-read from
+  // per warp: the double-buffered input tile (the replay's stack ring reuses it)
   constexpr int kTileFloats = 2 * 32 * (kTileW + 1);
   static_assert(sizeof(Ring) <= kTileFloats * sizeof(float), "the replay ring must fit the tile buffers");
   __shared__ __align__(16) float tile_mem[kPassWarps][kTileFloats];
-  __shared__ float ring[kPassWarps][16][32];
+  constexpr int RIN = PBD_DTW_RIN < W ? PBD_DTW_RIN : W;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float (*tiles)[32][kTileW + 1] = reinterpret_cast<float (*)[32][kTileW + 1]>(tile_mem[wib]);
   int w = blockIdx.x * kPassWarps + wib;                          // warp index -> (level, first item)
@@ -361,9 +367,6 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
 #pragma unroll
   for (int k = 0; k < 16; ++k) buf[k] = -INFINITY;
   float chk = 0.f;                                                // fma(y, 0, chk): NaN as soon as one sample is NaN or +-inf (they refuse the line)
-  float* myring = &ring[wib][0][lane];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) myring[k * 32] = -INFINITY;        // samples before the line's start do not exist
   // sample index s = 0 .. N-1, then 2W (rounded up to the unroll) virtual -inf samples flush the window; no branch inside a step
   int nd = 0;                                                     // positions left open by the walk, listed in olist (decided afterwards)
   int olist[kOpenCap];
@@ -385,22 +388,20 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
       if (SEG) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }    // kVirt where the line has no sample: finite, passes the check
       else if (s < N) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }  // warp-uniform
       buf[u] = y;
-      myring[u * 32] = y;
       const int q = q0 + s;                                       // the position whose last candidate is this step's sample
       const bool valid = (unsigned)q - qlo < qn;
-      float c[2 * W + 1];
+      float c[2 * W + 1], yin[2 * RIN + 1];
 #pragma unroll
       for (int j = 0; j <= 2 * W; ++j) c[j] = __fadd_rn(buf[(u + 16 - 2 * W + j) & 15], ef[j]);
-      const int jj = dtw::pick<W, (PBD_DTW_RIN < W ? PBD_DTW_RIN : W)>(c, tau0, ylim);
-      // decided here only if certified strictly inside the window; anything else (tier 1 open, owner at the window's edge) is an
-      // open position, resolved after the walk (a second open position of the same line: the line is replayed)
-      const bool inner = (unsigned)(jj - 1) <= (unsigned)(2 * W - 2);
-      const bool open = valid & !inner;
-      if (open) olist[min(nd, kOpenCap - 1)] = q;                 // rare (2e-4 of the positions on score maps): a local-memory store
-      nd += open ? 1 : 0;
-      const int j = inner ? jj : W;
-      const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
-      const float val = dtw::value_of(__ldg(ed + j), yv);
+#pragma unroll
+      for (int k = 0; k <= 2 * RIN; ++k) yin[k] = buf[(u + 16 - W - RIN + k) & 15];
+      // decided here only if certified inside the inner ring (tier 1 carries the winner's sample along); anything else is an open
+      // position, listed and resolved after the walk.  Open positions are rare (7e-4 on score maps): one warp-uniform branch
+      const dtw::Pick pk = dtw::pick_walk<W, RIN>(c, yin, tau0, ylim);
+      const bool open = valid & !pk.ok;
+      if (__any_sync(0xffffffffu, open)) nd = win_note_open(olist, nd, q, open);   // a call, so that the compiler keeps the branch
+      const int j = pk.ok ? pk.j : W;
+      const float val = dtw::value_of(__ldg(ed + j), pk.yv);
       st_pair_if_lt(dst, dp, off, val, (unsigned short)(vbase + s + j), (unsigned)q - qlo, qn);
       off += (unsigned)nlines;
     }
@@ -412,22 +413,20 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
       if (SEG) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }    // kVirt where the line has no sample: finite, passes the check
       else if (s < N) { y = loady(s); chk = __fmaf_rn(y, 0.f, chk); }  // warp-uniform
       buf[u] = y;
-      myring[u * 32] = y;
       const int q = q0 + s;                                       // the position whose last candidate is this step's sample
       const bool valid = (unsigned)q - qlo < qn;
-      float c[2 * W + 1];
+      float c[2 * W + 1], yin[2 * RIN + 1];
 #pragma unroll
       for (int j = 0; j <= 2 * W; ++j) c[j] = __fadd_rn(buf[(u + 16 - 2 * W + j) & 15], ef[j]);
-      const int jj = dtw::pick<W, (PBD_DTW_RIN < W ? PBD_DTW_RIN : W)>(c, tau0, ylim);
-      // decided here only if certified strictly inside the window; anything else (tier 1 open, owner at the window's edge) is an
-      // open position, resolved after the walk (a second open position of the same line: the line is replayed)
-      const bool inner = (unsigned)(jj - 1) <= (unsigned)(2 * W - 2);
-      const bool open = valid & !inner;
-      if (open) olist[min(nd, kOpenCap - 1)] = q;                 // rare (2e-4 of the positions on score maps): a local-memory store
-      nd += open ? 1 : 0;
-      const int j = inner ? jj : W;
-      const float yv = myring[((u + 16 - 2 * W + j) & 15) * 32];
-      const float val = dtw::value_of(__ldg(ed + j), yv);
+#pragma unroll
+      for (int k = 0; k <= 2 * RIN; ++k) yin[k] = buf[(u + 16 - W - RIN + k) & 15];
+      // decided here only if certified inside the inner ring (tier 1 carries the winner's sample along); anything else is an open
+      // position, listed and resolved after the walk.  Open positions are rare (7e-4 on score maps): one warp-uniform branch
+      const dtw::Pick pk = dtw::pick_walk<W, RIN>(c, yin, tau0, ylim);
+      const bool open = valid & !pk.ok;
+      if (__any_sync(0xffffffffu, open)) nd = win_note_open(olist, nd, q, open);   // a call, so that the compiler keeps the branch
+      const int j = pk.ok ? pk.j : W;
+      const float val = dtw::value_of(__ldg(ed + j), pk.yv);
       st_pair_if_lt(dst, dp, off, val, (unsigned short)(vbase + s + j), (unsigned)q - qlo, qn);
       off += (unsigned)nlines;
     }

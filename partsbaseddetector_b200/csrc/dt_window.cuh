@@ -111,30 +111,42 @@ PBD_ENV_FN float max3_nan(float a, float b, float c) {
 template <int K> PBD_ENV_FN void count_ge(float& acc, float c, float thr) { if (c >= thr) acc += (float)K; }
 #endif
 
-template <int W, int J, int JEND>
-PBD_ENV_FN void count_range(const float (&c)[2 * W + 1], float thr, float& a0, float& a1) {
+// counting step that also carries the winner's SAMPLE: ysel starts at -0.0f and y is added under the same predicate, so that after
+// a count of exactly one candidate ysel == y of that candidate, bit for bit (-0 + y = y for every y, zeros of either sign included)
+#if defined(__CUDA_ARCH__)
+template <int K> PBD_ENV_FN void count_ge_y(float& acc, float& ysel, float c, float thr, float y) {
+  asm("{ .reg .pred p; setp.ge.f32 p, %2, %3; @p add.rn.f32 %0, %0, %4; @p add.rn.f32 %1, %1, %5; }"
+      : "+f"(acc), "+f"(ysel) : "f"(c), "f"(thr), "f"((float)K), "f"(y));
+}
+#else
+template <int K> PBD_ENV_FN void count_ge_y(float& acc, float& ysel, float c, float thr, float y) { if (c >= thr) { acc += (float)K; ysel += y; } }
+#endif
+template <int W, int LO, int J, int JEND>
+PBD_ENV_FN void count_range(const float (&c)[2 * W + 1], const float (&y)[JEND - LO + 1], float thr, float& a0, float& a1, float& y0, float& y1) {
   if constexpr (J <= JEND) {
-    if constexpr (J & 1) count_ge<0x100 + J>(a1, c[J], thr); else count_ge<0x100 + J>(a0, c[J], thr);
-    count_range<W, J + 1, JEND>(c, thr, a0, a1);
+    if constexpr (J & 1) count_ge_y<0x100 + J>(a1, y1, c[J], thr, y[J - LO]); else count_ge_y<0x100 + J>(a0, y0, c[J], thr, y[J - LO]);
+    count_range<W, LO, J + 1, JEND>(c, y, thr, a0, a1, y0, y1);
   }
 }
 
-// Tier 1.  c[j] = fl(y_j + ef[j]) (-inf where the sample does not exist).  Returns the certified candidate or a negative number.
+// Tier 1.  c[j] = fl(y_j + ef[j]) (-inf where the sample does not exist), yin[k] = the sample of inner candidate j = W - RIN + k.
+// Returns whether the position is certified, the certified candidate j and its sample yv (both meaningless otherwise).
 // The candidates within RIN samples of the position (j in [W - RIN, W + RIN]; on score maps 99.9 % of the owners: measured offsets
 // 0 / 1 / 2 / 3 = 75 % / 25 % / 0.2 % / 0.03 %) are counted one by one against the threshold; the candidates of the outer ring only have
 // to lie BELOW it, so one NaN-propagating maximum and one comparison stand for their 2 (W - RIN) compare-and-count pairs.  The
 // certificate is the same statement as before -- exactly one candidate of the whole window at or above best - tau -- restricted to
 // owners of the inner ring; an owner in the outer ring leaves the position to tier 2 (which looks at the whole window again).
+struct Pick { bool ok; int j; float yv; };
 template <int W, int RIN = (W > 2 ? 2 : W)>
-PBD_ENV_FN int pick(const float (&c)[2 * W + 1], float tau0, float ylim) {
+PBD_ENV_FN Pick pick_walk(const float (&c)[2 * W + 1], const float (&yin)[2 * RIN + 1], float tau0, float ylim) {
   static_assert(RIN >= 1 && RIN <= W, "inner ring inside the window");
   constexpr int LO = W - RIN, HI = W + RIN;
   float best = c[LO];
 #pragma unroll
   for (int j = LO + 1; j + 1 <= HI; j += 2) best = max3_nan(best, c[j], c[j + 1]);     // 2 RIN + 1 is odd: pairs after c[LO]
   const float thr = env::fsub_r(env::fsub_r(best, tau0), env::fmul_r(fabsf(best), 4.76837158203125e-07f));   // 2^-21
-  float a0 = 0.f, a1 = 0.f;
-  count_range<W, LO, HI>(c, thr, a0, a1);
+  float a0 = 0.f, a1 = 0.f, y0 = -0.f, y1 = -0.f;
+  count_range<W, LO, LO, HI>(c, yin, thr, a0, a1, y0, y1);
   bool outer_below = true;
   if constexpr (RIN < W) {
     // outer ring: j in [0, LO) and (HI, 2W], an even number of candidates
@@ -150,8 +162,19 @@ PBD_ENV_FN int pick(const float (&c)[2 * W + 1], float tau0, float ylim) {
   }
   // exactly one inner candidate at or above the threshold <=> the sum is 256 + j; none: 0; two or more: >= 512.  A NaN or too large
   // best fails the last test (and a NaN threshold counts nothing).
-  const int j = (int)env::fadd_r(a0, a1) - 0x100;
-  return ((unsigned)(j - LO) <= (unsigned)(2 * RIN) && outer_below && fabsf(best) <= ylim) ? j : -1;
+  Pick r;
+  r.j = (int)env::fadd_r(a0, a1) - 0x100;
+  r.ok = (unsigned)(r.j - LO) <= (unsigned)(2 * RIN) && outer_below && fabsf(best) <= ylim;
+  r.yv = env::fadd_r(y0, y1);
+  return r;
+}
+// the certified candidate or a negative number (host harness, tests)
+template <int W, int RIN = (W > 2 ? 2 : W)>
+PBD_ENV_FN int pick(const float (&c)[2 * W + 1], float tau0, float ylim) {
+  float yin[2 * RIN + 1];
+  for (int k = 0; k <= 2 * RIN; ++k) yin[k] = 0.f;
+  const Pick r = pick_walk<W, RIN>(c, yin, tau0, ylim);
+  return r.ok ? r.j : -1;
 }
 
 // Tier 2.  y[j] = the window's samples (-inf where none).  Returns the certified candidate or -1.

@@ -34,7 +34,12 @@ static int line_w(const float* src, int N, const dtw::WinParams& P, float w_sq, 
       y[j] = (v >= 0 && v < N) ? src[v] : -INFINITY;
       c[j] = env::fadd_r(y[j], P.ef[j]);
     }
-    int j = dtw::pick<W>(c, P.tau0, P.ylim);
+    constexpr int RIN = W > 2 ? 2 : W;
+    float yin[2 * RIN + 1];
+    for (int k = 0; k <= 2 * RIN; ++k) yin[k] = y[W - RIN + k];
+    const dtw::Pick pk = dtw::pick_walk<W, RIN>(c, yin, P.tau0, P.ylim);
+    int j = pk.ok ? pk.j : -1;
+    if (pk.ok && std::memcmp(&pk.yv, &y[pk.j], sizeof(float)) != 0) { ++g_cause[5]; return 2; }   // the carried sample must be the winner's, bit for bit
     if (j < 0) {
       if (tier2) ++*tier2;
       j = dtw::pick_exact<W>(y, P.ed, P.margin1, P.cmax, P.ylim);

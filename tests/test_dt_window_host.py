@@ -43,6 +43,7 @@ def run_window(src, w_sq, w_lin, os_, W):
     if rc == -1:
         return None
     assert rc == 0
+    assert not (dirty == 2).any()          # tier 1 carries the winner's sample along: it must be that sample, bit for bit
     L = oracle_lib.lib()
     for i in range(nl):
         if dirty[i]:
@@ -51,7 +52,7 @@ def run_window(src, w_sq, w_lin, os_, W):
         L.orc_dt1d_f32(np.ascontiguousarray(src[i]), N, -float(np.float32(w_sq)), -float(np.float32(w_lin)), os_, rd, rp)
         assert np.array_equal(dst[i], rd), (i, N, os_, W)
         assert np.array_equal(ptr[i].astype(np.int32), rp), (i, N, os_, W)
-    return int(dirty.sum()), int(t2.value)
+    return int((dirty != 0).sum()), int(t2.value)
 
 
 def smooth(rng, nl, N, amp=1.0, corr=6):
