@@ -56,7 +56,13 @@ __global__ void __launch_bounds__(256) hog_orient_lut(unsigned char* __restrict_
   lut[i] = (unsigned char)snap_orientation((float)(i % kGradSpan - 255), (float)(i / kGradSpan - 255));
 }
 
-template <int CN>
+// SB = the bin size for the specialised gather (even bin sizes 4 and 8: every shipped model), 0 = any bin size.
+// For an even bin size 2h the pixels that scatter into block b are exactly the 2 sbin pixels [sbin b - h, sbin b + 3h - 1]
+// (floor((x + 0.5) / sbin - 0.5) = floor((x - h) / sbin): (2x + 1 - 2h) / (2 sbin) is never an integer, so no rounding of the
+// reference's expression can move a pixel across a bin boundary), the first sbin of them with weight vx0, the others with vx1.  The
+// gather of a block is then a fixed 2 sbin x 2 sbin loop without tests: pixels the reference does not visit (outside [1, visible - 2])
+// are staged with magnitude +0, and adding +0 to a bin (never -0: bins start at +0 and receive non-negative terms) changes nothing.
+template <int CN, int SB>
 __global__ void __launch_bounds__(HB_X * HB_Y)
 hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, const uint8_t* __restrict__ pyr, const unsigned char* __restrict__ orient_lut,
          float* __restrict__ hist, float* __restrict__ norm, int sbin, int frame0) {
@@ -78,9 +84,10 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, con
   const uint8_t* im = L.identity ? frames + (size_t)frame * g->in_h * g->in_w * CN : pyr + (size_t)frame * g->img_bytes + L.img_off;
   const size_t stride = (size_t)cols * CN;
   // pixel region that can scatter into this tile's blocks: floor((p+0.5)/sbin - 0.5) in {b-1, b}
-  const int marg = (sbin + 1) / 2 + 1;
+  // SB: the region is exactly the union of the blocks' windows, rows 16-byte aligned per block column (PW = 17 sbin, a multiple of 4)
+  const int marg = SB ? SB / 2 : (sbin + 1) / 2 + 1;
   const int px0 = bx0 * sbin - marg, py0 = by0 * sbin - marg;
-  const int PW = HB_X * sbin + sbin + 2 * marg, PH = HB_Y * sbin + sbin + 2 * marg;
+  const int PW = SB ? (HB_X + 1) * SB : HB_X * sbin + sbin + 2 * marg, PH = SB ? (HB_Y + 1) * SB : HB_Y * sbin + sbin + 2 * marg;
   float* smag = reinterpret_cast<float*>(hsm);                       // [PH][PW] gradient magnitude (sqrt(v)); < 0 = pixel not visited
   float* shist = smag + PH * PW;                                     // [18][HB_X*HB_Y] histogram of each thread's block
   float* sfx = shist + 18 * HB_X * HB_Y;                             // [PW] fractional bin coordinate vx0 of every column of the region
@@ -98,7 +105,7 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, con
     const int x = px0 + rx, y = py0 + ry;
     rx += stepx; ry += stepy;
     if (rx >= PW) { rx -= PW; ++ry; }
-    float mag = -1.f;
+    float mag = SB ? 0.f : -1.f;
     int best_o = 0;
     if (x >= 1 && x <= vis_w - 2 && y >= 1 && y <= vis_h - 2) {       // the reference's pixel loops, :202-203
       const int sx = min(x, cols - 2), sy = min(y, rows - 2);
@@ -150,9 +157,33 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, con
   // ---- phase 2: one thread per block gathers its window in raster order (bit-identical to the sequential scatter) ----
   const int bx = bx0 + threadIdx.x % HB_X, by = by0 + threadIdx.x / HB_X;
   if (bx >= L.bw || by >= L.bh) return;
+  float* myh = shist + threadIdx.x;
+  if constexpr (SB > 0) {
+    const int lx0 = SB * (threadIdx.x % HB_X), ly0 = SB * (threadIdx.x / HB_X);   // window origin inside the region
+    float wx[2 * SB];
+#pragma unroll
+    for (int i = 0; i < 2 * SB; ++i) wx[i] = i < SB ? sfx[lx0 + i] : sgx[lx0 + i];   // vx0 for ixp = bx - 1, vx1 for ixp = bx
+#pragma unroll 2
+    for (int yy = 0; yy < 2 * SB; ++yy) {
+      const float wy = yy < SB ? sfy[ly0 + yy] : sgy[ly0 + yy];
+      const float4* mrow = reinterpret_cast<const float4*>(smag + (ly0 + yy) * PW + lx0);
+      const unsigned* brow = reinterpret_cast<const unsigned*>(sbo + (ly0 + yy) * PW + lx0);
+#pragma unroll
+      for (int k = 0; k < 2 * SB / 4; ++k) {
+        const float4 m4 = mrow[k];
+        const unsigned o4 = brow[k];
+        const float m[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float term = __fmul_rn(__fmul_rn(wy, wx[4 * k + i]), m[i]);      // :262-265
+          float* hb = myh + ((o4 >> (8 * i)) & 0xffu) * (HB_X * HB_Y);
+          *hb = __fadd_rn(*hb, term);
+        }
+      }
+    }
+  } else {
   const int y_lo = max(1, by * sbin - marg), y_hi = min(vis_h - 2, by * sbin + sbin + marg - 1);
   const int x_lo = max(1, bx * sbin - marg), x_hi = min(vis_w - 2, bx * sbin + sbin + marg - 1);
-  float* myh = shist + threadIdx.x;
   for (int y = y_lo; y <= y_hi; ++y) {
     const int iyp = sby[y - py0];                                      // :252
     float wy;
@@ -171,6 +202,7 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, con
       float* hb = myh + brow[x] * (HB_X * HB_Y);
       *hb = __fadd_rn(*hb, term);
     }
+  }
   }
   const int idx = L.block_off + by * L.bw + bx;
   float* hp = hist + ((size_t)frame * g->blocks_total + idx) * 18;
@@ -246,15 +278,18 @@ int launch_hog(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, c
   if (g.blocks_total <= 0) return 0;
   int ntiles = 0;
   for (int l = 0; l < g.n_levels; ++l) ntiles += ((g.lv[l].bw + HB_X - 1) / HB_X) * ((g.lv[l].bh + HB_Y - 1) / HB_Y);
-  const int marg = (sbin + 1) / 2 + 1;
-  const int PW = HB_X * sbin + sbin + 2 * marg, PH = HB_Y * sbin + sbin + 2 * marg;
+  const int SB = (sbin == 4 || sbin == 8) ? sbin : 0;
+  const int marg = SB ? SB / 2 : (sbin + 1) / 2 + 1;
+  const int PW = SB ? (HB_X + 1) * SB : HB_X * sbin + sbin + 2 * marg, PH = SB ? (HB_Y + 1) * SB : HB_Y * sbin + sbin + 2 * marg;
   const size_t smem = (size_t)PW * PH * 5 + (size_t)18 * HB_X * HB_Y * 4 + (size_t)(PW + PH) * 16 + 16;   // + the coordinate tables
-  // per launch: the attribute is per device and a process may drive several devices
-  if (g.in_c == 1) cudaFuncSetAttribute(hog_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  else cudaFuncSetAttribute(hog_hist<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 gh(ntiles, nframes);
-  if (g.in_c == 1) hog_hist<1><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.frames, b.pyr, d_orient_lut, b.hist, b.norm, sbin, frame0);
-  else hog_hist<3><<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.frames, b.pyr, d_orient_lut, b.hist, b.norm, sbin, frame0);
+  auto go = [&](auto kernel) {
+    // per launch: the attribute is per device and a process may drive several devices
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<gh, HB_X * HB_Y, smem, s>>>(d_g, b.frames, b.pyr, d_orient_lut, b.hist, b.norm, sbin, frame0);
+  };
+  if (g.in_c == 1) { if (SB == 4) go(hog_hist<1, 4>); else if (SB == 8) go(hog_hist<1, 8>); else go(hog_hist<1, 0>); }
+  else { if (SB == 4) go(hog_hist<3, 4>); else if (SB == 8) go(hog_hist<3, 8>); else go(hog_hist<3, 0>); }
   int n = 1;
   if (g.cells_total > 0) {
     dim3 gf((g.cells_total + 127) / 128, nframes);

@@ -57,5 +57,14 @@ for (h, w) in ((37, 53), (70, 300)):
         outs.append((o.cpu(), ix.cpu(), iy.cpu()))
         plan.close()
     assert all(torch.equal(a, b) for other in outs[1:] for a, b in zip(other, outs[0]))
+# round 2, second session: the windowed transform (dt_variant 3) with its lines cut into segments -- forced for the 8-frame batch, chosen
+# automatically for a single frame -- and the specialised HOG gather (sbin 4)
+det.set_option("dt_variant", 3)
+ref = [(c.frame, c.level, c.x.tolist(), c.y.tolist()) for c in det.detect(frames)]
+for seg in (32, 48, -1):
+    det.set_option("dt_segment", seg)
+    assert [(c.frame, c.level, c.x.tolist(), c.y.tolist()) for c in det.detect(frames)] == ref
+one = [(c.level, c.x.tolist(), c.y.tolist()) for c in det.detect(frames[3])]
+assert one == [(l, x, y) for f, l, x, y in ref if f == 3]
 print("round-2 paths ok")
 det.close()
