@@ -101,40 +101,59 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, con
   // ---- phase 1: per pixel gradient, channel pick, orientation snap (each pixel of the region exactly once) ----
   int rx = threadIdx.x % PW, ry = threadIdx.x / PW;                  // position inside the region, advanced without divisions
   const int stepx = (HB_X * HB_Y) % PW, stepy = (HB_X * HB_Y) / PW;
-  for (int i = threadIdx.x; i < PW * PH; i += HB_X * HB_Y) {
-    const int x = px0 + rx, y = py0 + ry;
-    rx += stepx; ry += stepy;
-    if (rx >= PW) { rx -= PW; ++ry; }
-    float mag = SB ? 0.f : -1.f;
-    int best_o = 0;
-    if (x >= 1 && x <= vis_w - 2 && y >= 1 && y <= vis_h - 2) {       // the reference's pixel loops, :202-203
-      const int sx = min(x, cols - 2), sy = min(y, rows - 2);
+  // The loop is bound by the latency of its byte loads (twelve per colour pixel), and the slow-path branch inside the correctly rounded
+  // square root keeps the compiler from overlapping iterations: so the loads of KP pixels are issued first, then the arithmetic.
+  // Pixels the reference does not visit (:202-203) read a clamped, valid address and are masked afterwards.
+  constexpr int KP = 4, NB = CN == 1 ? 4 : 12;
+  for (int i0 = threadIdx.x; i0 < PW * PH; i0 += KP * HB_X * HB_Y) {
+    int raw[KP][NB];
+    bool visited[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int x = px0 + rx, y = py0 + ry;
+      rx += stepx; ry += stepy;
+      if (rx >= PW) { rx -= PW; ++ry; }
+      visited[k] = x >= 1 && x <= vis_w - 2 && y >= 1 && y <= vis_h - 2 && i0 + k * (HB_X * HB_Y) < PW * PH;
+      const int sx = min(max(x, 1), cols - 2), sy = min(max(y, 1), rows - 2);   // = min(x, cols - 2), min(y, rows - 2) for a visited pixel
       const uint8_t* s = im + (size_t)sy * stride + sx * CN;
+      if (CN == 1) {
+        raw[k][0] = s[stride]; raw[k][1] = *(s - stride); raw[k][2] = s[1]; raw[k][3] = *(s - 1);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          raw[k][4 * c + 0] = s[stride + c]; raw[k][4 * c + 1] = *(s - stride + c);
+          raw[k][4 * c + 2] = s[3 + c]; raw[k][4 * c + 3] = *(s - 3 + c);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
       // dx, dy are integers of magnitude <= 255: dx*dx + dy*dy <= 130050 is exact in float (and in int), so the reference's float
       // comparisons of the squared magnitudes (:221-239) are integer comparisons
       int dx, dy, v;
       if (CN == 1) {                                                   // :207-212
-        dy = (int)s[stride] - (int)*(s - stride);
-        dx = (int)s[1] - (int)*(s - 1);
+        dy = raw[k][0] - raw[k][1];
+        dx = raw[k][2] - raw[k][3];
         v = dx * dx + dy * dy;
-      } else {                                                         // :217-240
-        const int dyb = (int)s[stride] - (int)*(s - stride);
-        const int dxb = (int)s[3] - (int)*(s - 3);
+      } else {                                                         // :217-240: blue, green, then red is the starting point
+        const int dyb = raw[k][0] - raw[k][1], dxb = raw[k][2] - raw[k][3];
         const int vb = dxb * dxb + dyb * dyb;
-        const int dyg = (int)s[stride + 1] - (int)*(s - stride + 1);
-        const int dxg = (int)s[4] - (int)*(s - 2);
+        const int dyg = raw[k][4] - raw[k][5], dxg = raw[k][6] - raw[k][7];
         const int vg = dxg * dxg + dyg * dyg;
-        dy = (int)s[stride + 2] - (int)*(s - stride + 2);
-        dx = (int)s[5] - (int)*(s - 1);
+        dy = raw[k][8] - raw[k][9];
+        dx = raw[k][10] - raw[k][11];
         v = dx * dx + dy * dy;
         if (vg > v) { v = vg; dx = dxg; dy = dyg; }
         if (vb > v) { v = vb; dx = dxb; dy = dyb; }
       }
-      best_o = __ldg(orient_lut + (dy + 255) * kGradSpan + (dx + 255));   // :243-249, tabulated
-      mag = __fsqrt_rn((float)v);                                      // :260
+      const int lut_o = __ldg(orient_lut + (dy + 255) * kGradSpan + (dx + 255));   // :243-249, tabulated
+      const float root = __fsqrt_rn((float)v);                          // :260
+      const int i = i0 + k * (HB_X * HB_Y);
+      if (i < PW * PH) {
+        smag[i] = visited[k] ? root : (SB ? 0.f : -1.f);
+        sbo[i] = (unsigned char)(visited[k] ? lut_o : 0);
+      }
     }
-    smag[i] = mag;
-    sbo[i] = (unsigned char)best_o;
   }
 #pragma unroll
   for (int o = 0; o < 18; ++o) shist[o * (HB_X * HB_Y) + threadIdx.x] = 0.f;
