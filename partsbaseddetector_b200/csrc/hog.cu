@@ -104,7 +104,10 @@ hog_hist(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, con
   // The loop is bound by the latency of its byte loads (twelve per colour pixel), and the slow-path branch inside the correctly rounded
   // square root keeps the compiler from overlapping iterations: so the loads of KP pixels are issued first, then the arithmetic.
   // Pixels the reference does not visit (:202-203) read a clamped, valid address and are masked afterwards.
-  constexpr int KP = 4, NB = CN == 1 ? 4 : 12;
+#ifndef PBD_HOG_KP
+#define PBD_HOG_KP 4
+#endif
+  constexpr int KP = PBD_HOG_KP, NB = CN == 1 ? 4 : 12;
   for (int i0 = threadIdx.x; i0 < PW * PH; i0 += KP * HB_X * HB_Y) {
     int raw[KP][NB];
     bool visited[KP];

@@ -47,7 +47,11 @@ __global__ void __launch_bounds__(256) pyr_resize_u8(const Geometry* __restrict_
   }
 }
 
-// One thread per destination pixel: out = (sum_{i,j} k[i]k[j] src[2y+i-2][2x+j-2] + 128) >> 8, k = [1 4 6 4 1].
+// out = (sum_{i,j} k[i]k[j] src[2y+i-2][2x+j-2] + 128) >> 8, k = [1 4 6 4 1] (integer arithmetic: any summation order gives cv::pyrDown's
+// bits).  One thread per VY = 4 vertically adjacent destination pixels: their windows span 2 VY + 3 = 11 source rows, so the horizontal
+// 5-tap sum of a source row is formed once and enters up to three of the four outputs -- 41 byte loads per destination pixel instead
+// of 75 (the kernel is bound by instruction issue).  Threads of a warp still walk along x: loads and stores stay coalesced.
+constexpr int kPyrVY = 4;
 __global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ g, const uint8_t* __restrict__ frames, uint8_t* __restrict__ pyr, int4 levels,
                                                    int frame0) {
   const int level = blockIdx.z == 0 ? levels.x : blockIdx.z == 1 ? levels.y : blockIdx.z == 2 ? levels.z : levels.w;
@@ -55,27 +59,47 @@ __global__ void __launch_bounds__(256) pyr_down_u8(const Geometry* __restrict__ 
   const LevelDesc& P = g->lv[L.src_level];
   const int dw = L.img_w, dh = L.img_h, cn = g->in_c, sw = P.img_w, sh = P.img_h;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= dw * dh) return;
-  const int x = idx % dw, y = idx / dw;
+  const int nyq = (dh + kPyrVY - 1) / kPyrVY;                            // groups of VY rows
+  if (idx >= dw * nyq) return;
+  const int x = idx % dw, y0 = (idx / dw) * kPyrVY;
   const int frame = frame0 + blockIdx.y;
   const uint8_t* S = P.identity ? frames + (size_t)frame * sh * sw * cn : pyr + (size_t)frame * g->img_bytes + P.img_off;   // level 0 is the frame itself
-  uint8_t* D = pyr + (size_t)frame * g->img_bytes + L.img_off + (size_t)idx * cn;
+  uint8_t* D = pyr + (size_t)frame * g->img_bytes + L.img_off;
   const int k[5] = {1, 4, 6, 4, 1};
   int xs[5];
 #pragma unroll
   for (int j = 0; j < 5; ++j) xs[j] = reflect101(2 * x + j - 2, sw) * cn;
-  int acc[3] = {0, 0, 0};
+  int acc[kPyrVY][3];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const uint8_t* row = S + (size_t)reflect101(2 * y + i - 2, sh) * sw * cn;
-    for (int c = 0; c < cn; ++c) {
-      int h = 0;
+  for (int v = 0; v < kPyrVY; ++v) acc[v][0] = acc[v][1] = acc[v][2] = 0;
 #pragma unroll
-      for (int j = 0; j < 5; ++j) h += k[j] * row[xs[j] + c];
-      acc[c] += k[i] * h;
+  for (int r = 0; r < 2 * kPyrVY + 3; ++r) {                             // source row 2 y0 - 2 + r
+    const uint8_t* row = S + (size_t)reflect101(2 * y0 - 2 + r, sh) * sw * cn;
+    int h[3] = {0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c < cn) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) h[c] += k[j] * row[xs[j] + c];
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < kPyrVY; ++v) {
+      const int i = r - 2 * v;                                           // tap of output y0 + v that this row feeds
+      if (i >= 0 && i < 5) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[v][c] += k[i] * h[c];
+      }
     }
   }
-  for (int c = 0; c < cn; ++c) D[c] = (uint8_t)((acc[c] + 128) >> 8);
+#pragma unroll
+  for (int v = 0; v < kPyrVY; ++v) {
+    if (y0 + v >= dh) break;
+    uint8_t* d = D + ((size_t)(y0 + v) * dw + x) * cn;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c < cn) d[c] = (uint8_t)((acc[v][c] + 128) >> 8);
+  }
 }
 
 }  // namespace
@@ -98,7 +122,8 @@ int launch_pyramid(const Geometry& g, const Geometry* d_g, const DeviceBuffers& 
       int npx = 0;
       int4 lv = make_int4(ls[i], ls[i], ls[i], ls[i]);
       for (int j = 0; j < n; ++j) {
-        npx = std::max(npx, g.lv[ls[i + j]].img_w * g.lv[ls[i + j]].img_h);
+        const LevelDesc& Lj = g.lv[ls[i + j]];
+        npx = std::max(npx, k == 0 ? Lj.img_w * Lj.img_h : Lj.img_w * ((Lj.img_h + kPyrVY - 1) / kPyrVY));   // pyr_down: a thread per VY rows
         (j == 0 ? lv.x : j == 1 ? lv.y : j == 2 ? lv.z : lv.w) = ls[i + j];
       }
       dim3 grid((npx + 255) / 256, nframes, n);
