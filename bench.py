@@ -405,7 +405,8 @@ def run_gpu_arm(args):
                    "peak_source": peak_src, "ms_per_launch": dt_ms / nlaunch_dt, "share_of_step": dt_ms / step_ms,
                    "algorithmic_bytes": "16 B per map cell (SURVEY 8d) x 133 maps x cells x batch; as implemented 20 B (the row->column intermediate) with u16 pointers",
                    "note": ("windowed certified evaluation (11 candidates per position, certificate per position, replay of uncertifiable lines), one lane "
-                            "per line: bounded by instruction issue (ALU pipe 66 % busy, 86 instructions per position), not by HBM (DESIGN.md section 3.2)") if win else
+                            "per line (per line segment for launches that cannot fill the GPU): bounded by instruction issue (74 instructions per position, "
+                            "issue slots 68 % busy, ALU pipe 59 %), not by HBM (DESIGN.md section 3.4)") if win else
                            ("sequential lower-envelope scan with fp64 break points, one lane per line: bounded by instruction issue / latency, not by HBM "
                             "(DESIGN.md section 3.2 incl. the measured parallel-in-q alternative)")}
         tp = os.path.join(ROOT, "profiles", "dt_pass_win_traffic.json" if win else "dt_pass_traffic.json")

@@ -122,7 +122,10 @@ void pbd_destroy(pbd_detector* d);
  * PBD_MAX_LEVELS=n, PBD_DP_STREAMS=n.  Further keys: "graph" (1: CUDA-graph replay of pbd_enqueue_batch_u8_device), "root_nms" (window
  * sz > 0: root-map non-maxima suppression of src/nms.cpp before the backtrack; 0 = off, the reference's detect()), "dt_variant" (3, the
  * default: windowed certified evaluation with in-kernel replay of the lines it cannot certify; 0 / 1 / 2: the stack-algorithm kernels
- * -- double break points, certified fp32 break points, lagged scan; identical results for all four), get-only "dt_replayed_lines"
+ * -- double break points, certified fp32 break points, lagged scan; identical results for all four), "dt_segment" (dt_variant 3: -1, the
+ * default: launches that cannot fill the GPU -- single frames, small batches -- cut every line into segments walked by separate lanes, a
+ * line being accepted only if all of its segments are; 0: never; n, a multiple of 16: n steps per segment; identical results),
+ * get-only "dt_replayed_lines"
  * (lines variant 3 handed to the stack algorithm since the last query; synchronises).  Response modes 2 / 3 need a bank of equally sized square filters; for any
  * other model they run the bit-exact FP32 kernel (mode 0).  pbd_get_option("response_kernel") tells which kernel the last pdf stage
  * ran: 0 generic exact, 1 tiled exact, 3 tensor tf32x3, 4 tensor fp16x3, 5 generic FFMA, 6 tiled FFMA. */
