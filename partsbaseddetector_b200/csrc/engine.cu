@@ -426,15 +426,8 @@ void Engine::build_batch_tables() {
   max_ow_ = max_oh_ = 0;
   for (int l = 0; l < g.n_levels; ++l) { max_ow_ = std::max(max_ow_, g.lv[l].ow); max_oh_ = std::max(max_oh_, g.lv[l].oh); }
   if (max_ow_ > kMaxDim || max_oh_ > kMaxDim) throw UnsupportedError("pyramid level larger than 1024 cells in one dimension");
-  int tx, ty;
-  response_tile_dims(response_has_fast_path(fb_) ? 1 : 0, &tx, &ty);
-  std::vector<int> tl, tf(g.n_levels);
-  for (int l = 0; l < g.n_levels; ++l) {
-    const LevelDesc& L = g.lv[l];
-    tf[l] = (int)tl.size();
-    const int nt = ((L.oh + ty - 1) / ty) * ((L.ow + tx - 1) / tx);
-    for (int i = 0; i < nt; ++i) tl.push_back(l);
-  }
+  std::vector<int> tl, tf;
+  ntiles0_ = response_plan_tiles(g, fb_, tl, tf);
   ntiles_ = (int)tl.size();
   auto up = [&](int*& d, size_t& cap, const std::vector<int>& h) {
     ensure(d, cap, h.size());
@@ -719,7 +712,7 @@ void Engine::run_pdf() {
   // a tensor mode the filter bank does not qualify for (filters of different sizes) falls back to the bit-exact FP32 kernel, never to
   // a third arithmetic: only response mode 1 asks for fused multiply-adds
   const int exact = resp_mode != 1 ? 1 : 0;
-  launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles_, exact, feat_from_hog_ ? 1 : 0, stream_);
+  launches_ += launch_response_tiles(g_, d_g_, b_, fb_, d_tile_level_, d_tile_first_, ntiles0_, ntiles_, exact, feat_from_hog_ ? 1 : 0, stream_);
   last_response_kernel = (response_has_fast_path(fb_) ? 1 : 0) + (exact ? 0 : 5);
   kmark(1);
   check_cuda(cudaGetLastError(), "response launch");

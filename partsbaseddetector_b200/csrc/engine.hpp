@@ -185,7 +185,7 @@ class Engine {
   // tables depending on the batch geometry
   int *d_xofs_ = nullptr, *d_yofs_ = nullptr; short *d_xalpha_ = nullptr, *d_ybeta_ = nullptr;
   size_t cap_xofs_ = 0, cap_yofs_ = 0, cap_xalpha_ = 0, cap_ybeta_ = 0;
-  int *d_tile_level_ = nullptr, *d_tile_first_ = nullptr; size_t cap_tile_level_ = 0, cap_tile_first_ = 0; int ntiles_ = 0;
+  int *d_tile_level_ = nullptr, *d_tile_first_ = nullptr; size_t cap_tile_level_ = 0, cap_tile_first_ = 0; int ntiles_ = 0, ntiles0_ = 0;   // tiles [0, ntiles0_) : 8 x 4-quad tiles, the rest 6 x 5 (response.cu)
   int max_ow_ = 0, max_oh_ = 0;
   PassGeom pg_rows_{}, pg_cols_{};
   PassGeom* d_pg_ = nullptr;                   // [rows, cols]

@@ -16,6 +16,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include <vector>
+
 namespace pbd {
 
 constexpr int kMaxLevels = 96;
@@ -110,10 +112,10 @@ struct FilterBank {
   const int* fkw;
   int khm, kwm;                // largest filter (generic path halo)
 };
-int response_tile_dims(int uniform_fast, int* tx, int* ty);
+int response_plan_tiles(const Geometry& g, const FilterBank& fb, std::vector<int>& tile_level, std::vector<int>& level_first);   // returns the number of shape-0 tiles
 bool response_has_fast_path(const FilterBank& fb);
 int launch_response_tiles(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const FilterBank& fb, const int* d_tile_level,
-                          const int* d_tile_first, int ntiles, int exact, int trunc_zero, cudaStream_t s);
+                          const int* d_tile_first, int ntiles0, int ntiles, int exact, int trunc_zero, cudaStream_t s);
 
 // ---- tensor-core response path (response_tc.cu): padded strip layout of the HOG cells + work list ----
 struct TcLevel { int R, Wp, ow, oh, cell_off; };   // R: strip row of real cell (0,0); Wp: strip rows per image row (ow + ax)

@@ -16,14 +16,22 @@
 // double-buffered TMA bulk-copy stage (cp.async.bulk + mbarrier, one 6.4 KB copy per filter group and channel chunk),
 // so a thread's 8 filter taps are two broadcast 128-bit loads.  Each
 // thread keeps 4 cells x 8 filters in registers: 64 FMUL+FADD (or 32..64 FFMA) per 6 shared-memory loads.
+#include <vector>
+
 #include "kernels.cuh"
 
 namespace pbd {
 namespace {
 
-constexpr int TX = 16, TY = 8;       // cells per CTA tile (8x16 pads the VGA pyramid to 89 % real cells; 8x32 only 84 %)
 constexpr int P = 4, Q = 8;          // register tile: cells (along x) x filters
-constexpr int POSW = (TX / P) * TY / 32;   // warps covering the tile's cells (= 1)
+// Cells per CTA tile = one warp of quads (P adjacent cells per lane).  Two shapes, chosen PER LEVEL by response_plan_tiles: 8 rows x 4
+// quads (32 lanes) and 6 rows x 5 quads (30 lanes; lanes 30, 31 idle) -- whichever needs fewer tiles for the level's size: the VGA
+// pyramid takes 420 tiles instead of 428 (8x16 alone pads it to 90 % real cells; 8x32 only 84 %).  Both stage 240 floats per channel
+// (12 x 20 / 10 x 24), and each shape is its own kernel instance with compile-time strides, launched over its own tile list.
+template <int SHAPE> struct TileShape;
+template <> struct TileShape<0> { static constexpr int TY = 8, LX = 4; };
+template <> struct TileShape<1> { static constexpr int TY = 6, LX = 5; };
+constexpr int POSW = 1;              // warps covering the tile's cells
 constexpr int WF = 6;                // filter groups (of Q) processed per pass by different warps
 constexpr int NT = POSW * WF * 32;   // threads per CTA (192)
 constexpr int CCH = 8;               // channels per weight stage
@@ -49,11 +57,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   } while (!done);
 }
 
-template <int KH, int KW, bool EXACT>
+template <int KH, int KW, bool EXACT, int SHAPE>
 __global__ void __launch_bounds__(NT, 2)
 part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level, const int* __restrict__ tile_first,
               const float* __restrict__ feat, const float* __restrict__ wbank, int nfilters, int ngroups, int trunc_zero,
               float* __restrict__ resp) {
+  constexpr int TY = TileShape<SHAPE>::TY, LX = TileShape<SHAPE>::LX, TX = LX * P;
   constexpr int TAPS = KH * KW;
   constexpr int HY = TY + KH - 1;                       // tile rows incl. halo
   constexpr int ROWP = ((TX + KW - 1 + 3) / 4) * 4;     // padded row pitch (words), 16-byte aligned rows
@@ -67,7 +76,7 @@ part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level
   const int l = tile_level[tile];
   const LevelDesc& L = g->lv[l];
   const int tiles_x = (L.ow + TX - 1) / TX;
-  const int tl = tile - tile_first[l];
+  const int tl = tile - tile_first[l];                  // tile_first: first tile of the level within this shape's list
   const int y0 = (tl / tiles_x) * TY, x0 = (tl % tiles_x) * TX;
   const int ow = L.ow, oh = L.oh;
   constexpr int AY = KH / 2, AX = KW / 2;               // anchor, include/filterengine.hpp:310-318
@@ -95,10 +104,10 @@ part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level
   const bool interior = trunc_zero && (y0 - AY >= 0) && (x0 - AX >= 0) && (y0 + TY - 1 - AY + KH - 1 < oh) && (x0 + ROWP - 1 - AX < ow);
   const int nch_last = interior ? CCH - 1 : CCH;
   const int warp = tid >> 5, lane = tid & 31;
-  const int wpos = warp % POSW, wf = warp / POSW;       // which cells / which filter group of the pass (group = POSW adjacent warps)
-  constexpr int LX = TX / P, LY = 32 / LX;              // lanes along x / y inside a warp
-  const int lx = lane % LX, ly = lane / LX;
-  const int cy = wpos * LY + ly;                        // tile-local cell row
+  const int wf = warp;                                  // which filter group of the pass
+  const int lx = lane % LX, lyr = lane / LX;            // lanes along x / y inside the warp
+  const bool lane_on = lyr < TY;                        // 6 x 5: lanes 30 and 31 shadow the last row and store nothing
+  const int cy = lane_on ? lyr : TY - 1;                // tile-local cell row
   const int cx = lx * P;                                // tile-local first cell column
   const int npass = (ngroups + WF - 1) / WF;
 
@@ -188,7 +197,7 @@ part_response(const Geometry* __restrict__ g, const int* __restrict__ tile_level
     // ---- write the pass's responses: resp[frame][f][cell] ----
     const int gq = pass * WF + wf;
     const int gy = y0 + cy;
-    if (gq < ngroups && gy < oh) {
+    if (gq < ngroups && gy < oh && lane_on) {
 #pragma unroll
       for (int j = 0; j < Q; ++j) {
         const int f = gq * Q + j;
@@ -254,22 +263,31 @@ part_response_generic(const Geometry* __restrict__ g, const int* __restrict__ ti
   }
 }
 
-template <int KH, int KW>
+template <int KH, int KW, int SHAPE>
 size_t fast_smem_bytes() {
-  constexpr int HY = TY + KH - 1, ROWP = ((TX + KW - 1 + 3) / 4) * 4;
+  constexpr int HY = TileShape<SHAPE>::TY + KH - 1, ROWP = ((TileShape<SHAPE>::LX * P + KW - 1 + 3) / 4) * 4;
   return (size_t)(32 * HY * ROWP + 2 * WF * CCH * KH * KW * Q) * sizeof(float);
 }
 
-template <int KH, int KW>
-void launch_fast(const Geometry* d_g, const int* d_tl, const int* d_tf, int ntiles, int nframes, const DeviceBuffers& b,
-                 const FilterBank& fb, int exact, int trunc_zero, cudaStream_t s) {
-  const size_t smem = fast_smem_bytes<KH, KW>();
+template <int KH, int KW, int SHAPE>
+void launch_fast_shape(const Geometry* d_g, const int* d_tl, const int* d_tf, int ntiles, int nframes, const DeviceBuffers& b,
+                       const FilterBank& fb, int exact, int trunc_zero, cudaStream_t s) {
+  if (ntiles <= 0) return;
+  const size_t smem = fast_smem_bytes<KH, KW, SHAPE>();
   // per launch: the attribute is per device and a process may drive several devices
-  if (exact) cudaFuncSetAttribute(part_response<KH, KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  else cudaFuncSetAttribute(part_response<KH, KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (exact) cudaFuncSetAttribute(part_response<KH, KW, true, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  else cudaFuncSetAttribute(part_response<KH, KW, false, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ntiles, nframes);
-  if (exact) part_response<KH, KW, true><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, trunc_zero, b.resp);
-  else part_response<KH, KW, false><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, trunc_zero, b.resp);
+  if (exact) part_response<KH, KW, true, SHAPE><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, trunc_zero, b.resp);
+  else part_response<KH, KW, false, SHAPE><<<grid, NT, smem, s>>>(d_g, d_tl, d_tf, b.feat, fb.w, fb.nfilters, fb.ngroups, trunc_zero, b.resp);
+}
+// tiles [0, ntiles0) of the list are 8 x 4-quad tiles, the rest 6 x 5; d_tf holds the first-tile table of either shape (n_levels ints each)
+template <int KH, int KW>
+int launch_fast(const Geometry* d_g, const int* d_tl, const int* d_tf, int n_levels, int ntiles0, int ntiles, int nframes, const DeviceBuffers& b,
+                const FilterBank& fb, int exact, int trunc_zero, cudaStream_t s) {
+  launch_fast_shape<KH, KW, 0>(d_g, d_tl, d_tf, ntiles0, nframes, b, fb, exact, trunc_zero, s);
+  launch_fast_shape<KH, KW, 1>(d_g, d_tl + ntiles0, d_tf + n_levels, ntiles - ntiles0, nframes, b, fb, exact, trunc_zero, s);
+  return (ntiles0 > 0) + (ntiles > ntiles0);
 }
 
 }  // namespace
@@ -282,20 +300,34 @@ bool response_has_fast_path(const FilterBank& fb) {
   return fb.uniform && fb.flen == 32 && fb.kh == fb.kw && (fb.kh == 4 || fb.kh == 5 || fb.kh == 6);
 }
 
-int response_tile_dims(int uniform, int* tx, int* ty) {
-  if (uniform) { *tx = TX; *ty = TY; } else { *tx = 16; *ty = 8; }
-  return 0;
+// Tiles of the response kernels.  tile_level = [tiles of shape 0 ..., tiles of shape 1 ...] (level of every tile), level_first =
+// [first tile of level l within the shape-0 list ... | ... within the shape-1 list] (2 n_levels ints).  A level uses the shape that
+// needs fewer tiles (ties: 8 x 4); the generic kernel (filters of different sizes) keeps 8 x 16 cells for every level.
+int response_plan_tiles(const Geometry& g, const FilterBank& fb, std::vector<int>& tile_level, std::vector<int>& level_first) {
+  const bool fast = response_has_fast_path(fb);
+  std::vector<int> t0, t1;
+  level_first.assign((size_t)2 * g.n_levels, 0);
+  for (int l = 0; l < g.n_levels; ++l) {
+    const LevelDesc& L = g.lv[l];
+    const int qw = (L.ow + P - 1) / P;
+    const int n0 = fast ? ((L.oh + 7) / 8) * ((qw + 3) / 4) : ((L.oh + 7) / 8) * ((L.ow + 15) / 16);
+    const int n1 = ((L.oh + 5) / 6) * ((qw + 4) / 5);
+    level_first[l] = (int)t0.size(); level_first[g.n_levels + l] = (int)t1.size();
+    if (fast && n1 < n0) t1.insert(t1.end(), n1, l); else t0.insert(t0.end(), n0, l);
+  }
+  tile_level = t0;
+  tile_level.insert(tile_level.end(), t1.begin(), t1.end());
+  return (int)t0.size();
 }
 
 int launch_response_tiles(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, const FilterBank& fb, const int* d_tile_level,
-                          const int* d_tile_first, int ntiles, int exact, int trunc_zero, cudaStream_t s) {
+                          const int* d_tile_first, int ntiles0, int ntiles, int exact, int trunc_zero, cudaStream_t s) {
   if (ntiles <= 0 || g.n_frames <= 0) return 0;
   const int khm = fb.khm, kwm = fb.kwm;
   if (response_has_fast_path(fb)) {
-    if (fb.kh == 5) launch_fast<5, 5>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, trunc_zero, s);
-    else if (fb.kh == 4) launch_fast<4, 4>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, trunc_zero, s);
-    else launch_fast<6, 6>(d_g, d_tile_level, d_tile_first, ntiles, g.n_frames, b, fb, exact, trunc_zero, s);
-    return 1;
+    if (fb.kh == 5) return launch_fast<5, 5>(d_g, d_tile_level, d_tile_first, g.n_levels, ntiles0, ntiles, g.n_frames, b, fb, exact, trunc_zero, s);
+    if (fb.kh == 4) return launch_fast<4, 4>(d_g, d_tile_level, d_tile_first, g.n_levels, ntiles0, ntiles, g.n_frames, b, fb, exact, trunc_zero, s);
+    return launch_fast<6, 6>(d_g, d_tile_level, d_tile_first, g.n_levels, ntiles0, ntiles, g.n_frames, b, fb, exact, trunc_zero, s);
   }
   const int HYm = 8 + khm - 1, ROWm = 16 + kwm - 1;
   const size_t smem = (size_t)32 * (HYm * ROWm + 1) * sizeof(float);
