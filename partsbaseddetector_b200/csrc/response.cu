@@ -307,13 +307,23 @@ int response_plan_tiles(const Geometry& g, const FilterBank& fb, std::vector<int
   const bool fast = response_has_fast_path(fb);
   std::vector<int> t0, t1;
   level_first.assign((size_t)2 * g.n_levels, 0);
+  // the second shape is a second launch: worth it only when the launches are many waves of CTAs long (a single VGA frame is 1.4 waves:
+  // measured 0.66 ms with two launches, 0.48 ms with one)
+  // ... and when it saves at least 1 % of the tiles (1080p / 10 levels: 4 of 2 755 tiles -- the second launch's tail costs more)
+  long long all0 = 0, best = 0;
+  for (int l = 0; l < g.n_levels; ++l) {
+    const long long n0 = (long long)((g.lv[l].oh + 7) / 8) * ((g.lv[l].ow + 15) / 16);
+    const long long n1 = (long long)((g.lv[l].oh + 5) / 6) * (((g.lv[l].ow + P - 1) / P + 4) / 5);
+    all0 += n0; best += n1 < n0 ? n1 : n0;
+  }
+  const bool two_shapes = fast && all0 * g.n_frames >= 2400 && (all0 - best) * 100 >= all0;
   for (int l = 0; l < g.n_levels; ++l) {
     const LevelDesc& L = g.lv[l];
     const int qw = (L.ow + P - 1) / P;
     const int n0 = fast ? ((L.oh + 7) / 8) * ((qw + 3) / 4) : ((L.oh + 7) / 8) * ((L.ow + 15) / 16);
     const int n1 = ((L.oh + 5) / 6) * ((qw + 4) / 5);
     level_first[l] = (int)t0.size(); level_first[g.n_levels + l] = (int)t1.size();
-    if (fast && n1 < n0) t1.insert(t1.end(), n1, l); else t0.insert(t0.end(), n0, l);
+    if (two_shapes && n1 < n0) t1.insert(t1.end(), n1, l); else t0.insert(t0.end(), n0, l);
   }
   tile_level = t0;
   tile_level.insert(tile_level.end(), t1.begin(), t1.end());
