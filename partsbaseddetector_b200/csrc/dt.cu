@@ -184,11 +184,12 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
 // dt_variant 3: the same pass (same lane = line packing, same staging, same transposed output) with the WINDOWED CERTIFIED evaluation
 // of dt_window.cuh instead of the stack: a lane walks along its line keeping the last 2W+1 samples in a 16-slot circular register
 // window; the position whose window has just been completed, q = s - os - W, is decided by tier 1 (2W+1 adds, a NaN-propagating max
-// tree, 2W+1 compare-and-count) or the rare tier 2, its value formed with the reference's double add, and stored.  No data-dependent
-// control flow, all lanes busy.  A lane whose line cannot be certified somewhere (near-tie against a rounded break point, arg-max at
-// the window's edge, NaN / inf sample, map not eligible) replays the line afterwards with the literal stack algorithm
-// (env::envelope_stream, direct global loads) and overwrites its own stores -- same thread, so no ordering question arises.
-// Real score maps: 0.2 % of the lines are replayed (6 % of the warps run the second phase for one or two lanes).
+// tree over the five candidates within two samples of the position, their compare-and-count, one more max tree + one compare for the
+// six outer candidates: dtw::pick_walk), its value formed with the reference's double add, and stored.  No data-dependent control
+// flow except one warp-uniform branch for the rare open positions, all lanes busy.  A lane whose line cannot be certified somewhere
+// (near-tie against a rounded break point, arg-max at the window's edge, NaN / inf sample, map not eligible) replays the line afterwards
+// with the literal stack algorithm (env::envelope_stream, direct global loads) and overwrites its own stores -- same thread, so no
+// ordering question arises (segmented walk: see below).  Real score maps: 0.07 % of the lines are replayed.
 // ---------------------------------------------------------------------------------------------------
 // The positions the walk left open (tier 1 undecided, or decided by the window's edge), resolved afterwards so that the walk itself is
 // straight-line code: tier 2 on the window read again from the line in global memory, then tier 3, the local replay of what is still
@@ -367,7 +368,7 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
 #pragma unroll
   for (int k = 0; k < 16; ++k) buf[k] = -INFINITY;
   float chk = 0.f;                                                // fma(y, 0, chk): NaN as soon as one sample is NaN or +-inf (they refuse the line)
-  // sample index s = 0 .. N-1, then 2W (rounded up to the unroll) virtual -inf samples flush the window; no branch inside a step
+  // sample index s = 0 .. N-1, then 2W virtual -inf samples flush the window; no branch inside a step but the rare-path vote
   int nd = 0;                                                     // positions left open by the walk, listed in olist (decided afterwards)
   int olist[kOpenCap];
   // q * nlines of the current step's position (wraps while q is outside the line / segment: never stored)
