@@ -134,7 +134,7 @@ class Engine {
   void ensure_slot(ResultSlot& S);
   void ensure_tc(bool f16);
   void download_slot(ResultSlot& S, cudaStream_t st, CandidateSet& out);
-  void chunked_upload_pyramid(const uint8_t* frames, uint8_t* d_dst, cudaEvent_t wait_before_copy, cudaEvent_t record_after);
+  void chunked_upload_pyramid(const uint8_t* frames, uint8_t* d_dst, cudaEvent_t wait_before_copy, cudaEvent_t record_after, bool pipeline_busy = false);
 
   Model model_;
   int device_;
