@@ -221,7 +221,9 @@ int pbd_set_response(pbd_detector* d, int frame, int level, int filter, const fl
 /* ------------------------------------------------- standalone DT (config 5) ---
  * Generalised distance transform of n_maps score maps of h x w (device pointers), one (w0..w3, ax, ay)
  * per map: out[m] = DT(in[m]), ix/iy = back-pointers (uint16) with the reference composition.
- * Reference: DistanceTransform<float>::compute, include/DistanceTransform.hpp:203-245. */
+ * Reference: DistanceTransform<float>::compute, include/DistanceTransform.hpp:203-245.  Samples may be any float but NaN (+-inf
+ * included: results equal the reference's); what the reference's loops make of a NaN sample is an accident of its comparisons that the
+ * streaming kernels do not reproduce (the detector never produces one: features and filters are finite). */
 int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int w, const float* h_defw4,
                         const int32_t* h_anchor_xy, float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode);
 /* host-buffer convenience wrapper of the above (allocates, copies, runs, copies back) */
@@ -238,6 +240,9 @@ int pbd_dt2d_f32(const float* in, int n_maps, int h, int w, const float* defw4, 
 typedef struct pbd_dt2d_plan pbd_dt2d_plan;
 int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, int impl, pbd_dt2d_plan** out);
 int pbd_dt2d_plan_impl(const pbd_dt2d_plan* p);
+/* impl 4 only: cut every line into segments of `steps` walk steps (a multiple of 16, 0 = off: the default) -- the form the detector
+ * chooses by itself for launches that cannot fill the GPU (option "dt_segment"); identical results. */
+int pbd_dt2d_plan_set_segment(pbd_dt2d_plan* p, int steps);
 long long pbd_dt2d_plan_replayed(pbd_dt2d_plan* p);
 int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode);
 void pbd_dt2d_plan_destroy(pbd_dt2d_plan* p);

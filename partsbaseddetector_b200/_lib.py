@@ -29,7 +29,7 @@ EXPORTS = [
     "pbd_candidates_sort", "pbd_candidates_nms", "pbd_candidates_filter_by_depth", "pbd_candidates_create", "pbd_stage_pyramid", "pbd_stage_pdf", "pbd_stage_dp_min", "pbd_stage_dp_argmin",
     "pbd_pyramid_geometry", "pbd_num_frames", "pbd_num_levels", "pbd_level_info", "pbd_get_pyramid_image", "pbd_get_features",
     "pbd_get_response", "pbd_get_rootv", "pbd_get_rooti", "pbd_get_backptr", "pbd_set_levels",
-    "pbd_set_features", "pbd_set_response", "pbd_dt2d_f32_device", "pbd_dt2d_f32", "pbd_dt2d_plan_create", "pbd_dt2d_plan_impl", "pbd_dt2d_plan_replayed",
+    "pbd_set_features", "pbd_set_response", "pbd_dt2d_f32_device", "pbd_dt2d_f32", "pbd_dt2d_plan_create", "pbd_dt2d_plan_impl", "pbd_dt2d_plan_set_segment", "pbd_dt2d_plan_replayed",
     "pbd_dt2d_plan_run", "pbd_dt2d_plan_destroy", "pbd_image_info", "pbd_image_decode_bgr8", "pbd_image_decode_depth_f32", "pbd_imread_bgr8",
     "pbd_ros_image_to_bgr8", "pbd_ros_depth_to_f32", "pbd_host_alloc_pinned", "pbd_host_free_pinned", "pbd_launch_count",
     "pbd_stage_times_ms", "pbd_kernel_times_ms", "pbd_device_bytes",
@@ -121,6 +121,7 @@ def lib():
     L.pbd_dt2d_f32.argtypes = [_f32p, ci, ci, ci, _f32p, _i32p, _f32p, _i32p, _i32p, ci]
     L.pbd_dt2d_plan_create.argtypes = [ci, ci, ci, _f32p, _i32p, ci, P(vp)]
     L.pbd_dt2d_plan_impl.argtypes = [vp]
+    L.pbd_dt2d_plan_set_segment.argtypes = [vp, ci]
     L.pbd_dt2d_plan_replayed.argtypes = [vp]
     L.pbd_dt2d_plan_replayed.restype = C.c_longlong
     L.pbd_dt2d_plan_run.argtypes = [vp, vp, vp, vp, vp, vp, ci]

@@ -525,6 +525,7 @@ struct pbd_dt2d_plan {
   int n_maps = 0, h = 0, w = 0, impl = 0, device = 0;
   LineGeom lg[2];
   DevBuf geom, maps, etab, tmp, ixr, iyr, wp, ctr;   // wp / ctr: window parameters and the replay counter of impl 4
+  DevBuf segctr; int seg_steps = 0;                  // impl 4: per-line verdict counters of the segmented walk (pbd_dt2d_plan_set_segment)
 };
 
 int pbd_dt2d_plan_create(int n_maps, int h, int w, const float* defw4, const int32_t* anchor_xy, int impl, pbd_dt2d_plan** out) {
@@ -598,6 +599,22 @@ void pbd_dt2d_plan_destroy(pbd_dt2d_plan* p) {
   try { DeviceGuard dg_(p->device); delete p; } catch (...) { delete p; }   // the plan's buffers live on the device it was created on
 }
 int pbd_dt2d_plan_impl(const pbd_dt2d_plan* p) { return p ? p->impl : 0; }
+// impl 4: cut every line into segments of `steps` walk steps (a multiple of 16; 0 = one lane per line, the default of a plan) -- the
+// form the detector uses by itself for launches that cannot fill the GPU; results are identical
+int pbd_dt2d_plan_set_segment(pbd_dt2d_plan* p, int steps) {
+  return guarded([&] {
+    REQUIRE(p, "null argument");
+    REQUIRE(p->impl == 4, "segments exist for impl 4 (windowed certified evaluation) only");
+    REQUIRE(steps == 0 || (steps >= 16 && steps <= 4096 && steps % 16 == 0), "steps must be 0 or a multiple of 16");
+    DeviceGuard dg_(p->device);
+    if (steps && !p->segctr.p) {
+      const size_t n = (size_t)p->n_maps * std::max(p->h, p->w);
+      p->segctr.alloc(n * sizeof(int));
+      cu(cudaMemset(p->segctr.p, 0, n * sizeof(int)), "memset");
+    }
+    p->seg_steps = steps;
+  });
+}
 // impl 4: lines replayed with the stack algorithm since the last call (synchronises the device); other impls: 0
 long long pbd_dt2d_plan_replayed(pbd_dt2d_plan* p) {
   if (!p || p->impl != 4) return 0;
@@ -620,7 +637,8 @@ int pbd_dt2d_plan_run(pbd_dt2d_plan* p, void* stream, const float* d_in, float* 
     if (p->impl != 2) {
       launch_dt2d_standalone(d_in, p->n_maps, p->h, p->w, p->geom.as<PassGeom>(), p->maps.as<PassMap>(), p->tmp.as<float>(), d_out, d_ix, d_iy,
                              p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s, p->impl == 4 ? 3 : (p->impl == 3 ? 1 : 0),
-                             p->impl == 4 ? p->wp.as<dtw::WinParams>() : nullptr, p->impl == 4 ? p->ctr.as<int>() : nullptr);
+                             p->impl == 4 ? p->wp.as<dtw::WinParams>() : nullptr, p->impl == 4 ? p->ctr.as<int>() : nullptr,
+                             p->seg_steps, p->seg_steps ? p->segctr.as<int>() : nullptr);
     } else {
       launch_dt2d_lines(d_in, p->n_maps, p->h, p->w, p->lg[0], p->lg[1], p->geom.as<LineGeom>(), p->maps.as<PassMap>(), p->tmp.as<float>(), d_out,
                         d_ix, d_iy, p->ixr.as<uint16_t>(), p->iyr.as<uint16_t>(), backptr_mode, s);

@@ -956,16 +956,19 @@ int launch_hits(const Geometry& g, const Geometry* d_g, const DeviceBuffers& b, 
 
 int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const PassGeom* d_pg2 /* [rows, cols] */, const PassMap* d_maps2,
                            float* d_tmp, float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
-                           cudaStream_t s, int scan, const dtw::WinParams* d_wp2, int* d_replayed) {
+                           cudaStream_t s, int scan, const dtw::WinParams* d_wp2, int* d_replayed, int seg_steps, int* d_seg_ctr) {
   if (n_maps <= 0 || h <= 0 || w <= 0) return 0;
   // maps are launched in chunks so that the warp index stays small; every map is h*w cells
   PassGeom pr{}, pc{};
   pr.n_levels = pc.n_levels = 1;
   pr.nlines[0] = h; pr.N[0] = w; pc.nlines[0] = w; pc.N[0] = h;
-  dim3 gr((pass_warps(pr, n_maps) + kPassWarps - 1) / kPassWarps, 1), gc((pass_warps(pc, n_maps) + kPassWarps - 1) / kPassWarps, 1);
+  // seg_steps > 0 (tests): the windowed transform with its lines cut into segments, as the detector does for launches that cannot fill the GPU
+  const int seg = (scan == 3 && d_wp2 && d_seg_ctr && seg_steps > 2 * kDtWindowW) ? seg_steps : 0;
+  const int seg_r = seg && seg < ((w + 2 * kDtWindowW + 15) & ~15) ? seg : 0, seg_c = seg && seg < ((h + 2 * kDtWindowW + 15) & ~15) ? seg : 0;
+  dim3 gr((pass_warps(pr, n_maps, seg_r) + kPassWarps - 1) / kPassWarps, 1), gc((pass_warps(pc, n_maps, seg_c) + kPassWarps - 1) / kPassWarps, 1);
   if (scan == 3 && d_wp2) {                                         // windowed certified evaluation (dt_pass_win): rows, then columns
-    launch_pass_win(w, 0, (int*)nullptr, 0, gr, s, d_pg2, d_maps2, d_wp2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0, d_replayed);
-    launch_pass_win(h, 0, (int*)nullptr, 0, gc, s, d_pg2 + 1, d_maps2 + n_maps, d_wp2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out,
+    launch_pass_win(w, seg_r, d_seg_ctr, pass_lines(pr, n_maps), gr, s, d_pg2, d_maps2, d_wp2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0, d_replayed);
+    launch_pass_win(h, seg_c, d_seg_ctr, pass_lines(pc, n_maps), gc, s, d_pg2 + 1, d_maps2 + n_maps, d_wp2 + n_maps, n_maps, (const float*)d_tmp, (size_t)0, (const float*)d_tmp, (size_t)0, d_out,
                     (size_t)0, d_iyraw, (size_t)0, d_replayed);
   } else if (scan) {
     launch_pass_v<4>(w, gr, s, d_pg2, d_maps2, n_maps, d_in, (size_t)0, d_in, (size_t)0, d_tmp, (size_t)0, d_ixraw, (size_t)0);

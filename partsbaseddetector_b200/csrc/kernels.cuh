@@ -215,7 +215,8 @@ int launch_expand_backptr(const Geometry& g, const DeviceBuffers& b, int frame, 
 int launch_dt2d_standalone(const float* d_in, int n_maps, int h, int w, const PassGeom* d_pg2, const PassMap* d_maps2, float* d_tmp,
                            float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw, int backptr_mode,
                            cudaStream_t s, int scan = 0,   // 0 eager streaming, 1 lagged scan, 3 (with d_wp2) windowed certified
-                           const dtw::WinParams* d_wp2 = nullptr, int* d_replayed = nullptr);
+                           const dtw::WinParams* d_wp2 = nullptr, int* d_replayed = nullptr,
+                           int seg_steps = 0, int* d_seg_ctr = nullptr);  // scan 3: lines cut into segments (one zeroed int per line in d_seg_ctr)
 // the same transform through the parallel-in-q kernels (all maps [y][x]); d_lg2 = {rows, cols}
 int launch_dt2d_lines(const float* d_in, int n_maps, int h, int w, const LineGeom& lg_rows, const LineGeom& lg_cols, const LineGeom* d_lg2,
                       const PassMap* d_maps2, float* d_tmp, float* d_out, uint16_t* d_ix, uint16_t* d_iy, uint16_t* d_ixraw, uint16_t* d_iyraw,

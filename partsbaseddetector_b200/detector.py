@@ -522,6 +522,10 @@ class Dt2dPlan:
     def impl(self):
         return _lib.lib().pbd_dt2d_plan_impl(self._p)
 
+    def set_segment(self, steps):
+        """impl 4: lines cut into segments of `steps` walk steps (multiple of 16; 0 = off), as the detector does for small launches"""
+        _lib.check(_lib.lib().pbd_dt2d_plan_set_segment(self._p, int(steps)))
+
     def replayed(self):
         """impl 4: lines handed to the stack algorithm since the last call (synchronises)"""
         return int(_lib.lib().pbd_dt2d_plan_replayed(self._p))

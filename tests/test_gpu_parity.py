@@ -210,6 +210,59 @@ def test_dt2d_windowed_on_score_like_maps(h, w):
     plan.close()
 
 
+@pytest.mark.parametrize("seg", [16, 32, 48])
+@pytest.mark.parametrize("h,w", [(37, 53), (118, 158), (64, 300)])
+def test_dt2d_segmented_walk_on_adversarial_maps(h, w, seg):
+    """The segmented walk (lines cut into segments of seg - 10 positions, each walked by its own lane; a line is accepted only if all
+    of its segments are) on the inputs built to break a windowed certificate: score-like maps, maps quantised to a coarse binary grid
+    with weights 2^-k so that break points fall exactly on integers and neighbouring candidates tie exactly, constant maps, a map with
+    isolated huge spikes (owners far outside the window), noise, infinities of either sign, anchors up to the window's limit.  Every map
+    must equal the oracle bit for bit, exactly as with one lane per line."""
+    import torch
+    from partsbaseddetector_b200 import Dt2dPlan
+    rng = np.random.default_rng(h * 131 + w + seg)
+    n = 10
+    maps = (rng.standard_normal((n, h, w)) * 0.01).astype(np.float32)
+    maps[1] += (np.add.outer(np.sin(np.arange(h) / 7.0), np.cos(np.arange(w) / 11.0)) * 0.2).astype(np.float32)
+    maps[2] = np.round(rng.standard_normal((h, w)) * 2) / 4                    # quantised: exact ties, integer break points (weights 2^-k below)
+    maps[3] = np.round(rng.standard_normal((h, w)) * 8) / 16
+    maps[4] = 0.375                                                           # constant: every neighbour pair meets at a half integer
+    maps[5, ::7, ::5] += 3.0                                                  # spikes: their parabolas own positions far beyond the window
+    maps[6] = rng.standard_normal((h, w)).astype(np.float32)                  # noise
+    maps[7, h // 2, w // 3] = -np.inf                                          # non-finite samples refuse their lines (NaN is outside the
+    maps[8, h // 3, w // 2] = np.inf                                           # transform's contract: include/pbd_b200.h)
+    defw = np.stack([rng.uniform(0.01, 0.02, n), rng.uniform(-0.02, 0.02, n), rng.uniform(0.01, 0.02, n), rng.uniform(-0.02, 0.02, n)], axis=1).astype(np.float32)
+    defw[2] = (0.0625, 0.0, 0.125, -0.125)
+    defw[3] = (0.03125, 0.0625, 0.5, 0.0)
+    defw[4] = (0.0625, 0.0, 0.0625, 0.0625)
+    anchors = np.stack([rng.integers(-3, 4, n), rng.integers(-2, 6, n)], axis=1).astype(np.int32)
+    anchors[0] = (5, -5)
+    anchors[9] = (-5, 5)
+    L = oracle_lib.lib()
+    ref = []
+    for i in range(n):
+        o, x, y = np.empty((h, w), np.float32), np.empty((h, w), np.int32), np.empty((h, w), np.int32)
+        L.orc_dt2d_f32(maps[i].reshape(-1), h, w, defw[i], int(anchors[i, 0]), int(anchors[i, 1]), 0, o.reshape(-1), x.reshape(-1), y.reshape(-1))
+        ref.append((o, x, y))
+    plan = Dt2dPlan(n, h, w, defw, anchors, 4)
+    d_in = torch.from_numpy(maps).cuda()
+    d_out = torch.empty_like(d_in)
+    d_ix = torch.empty((n, h, w), dtype=torch.int16, device="cuda")
+    d_iy = torch.empty_like(d_ix)
+    for steps in (seg, 0, seg):                                               # segmented, one lane per line, segmented again (counters left clean)
+        plan.set_segment(steps)
+        d_out.zero_(); d_ix.zero_(); d_iy.zero_()
+        plan.run(d_in.data_ptr(), d_out.data_ptr(), d_ix.data_ptr(), d_iy.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        out, ix, iy = d_out.cpu().numpy(), d_ix.cpu().numpy().view(np.uint16), d_iy.cpu().numpy().view(np.uint16)
+        for i in range(n):
+            o, x, y = ref[i]
+            assert np.array_equal(out[i], o, equal_nan=True), (i, steps)
+            assert np.array_equal(ix[i].astype(np.int32), x) and np.array_equal(iy[i].astype(np.int32), y), (i, steps)
+    assert plan.replayed() > 0
+    plan.close()
+
+
 def test_dt2d_rejects_bad_arguments():
     with pytest.raises(PbdError):
         dt2d(np.zeros((4, 4), np.float32), [0.0, 0.0, 0.01, 0.0], [0, 0])       # a = -w0 must be < 0
