@@ -221,9 +221,9 @@ int pbd_set_response(pbd_detector* d, int frame, int level, int filter, const fl
 /* ------------------------------------------------- standalone DT (config 5) ---
  * Generalised distance transform of n_maps score maps of h x w (device pointers), one (w0..w3, ax, ay)
  * per map: out[m] = DT(in[m]), ix/iy = back-pointers (uint16) with the reference composition.
- * Reference: DistanceTransform<float>::compute, include/DistanceTransform.hpp:203-245.  Samples may be any float but NaN (+-inf
- * included: results equal the reference's); what the reference's loops make of a NaN sample is an accident of its comparisons that the
- * streaming kernels do not reproduce (the detector never produces one: features and filters are finite). */
+ * Reference: DistanceTransform<float>::compute, include/DistanceTransform.hpp:203-245.  Samples may be any float: a line with a
+ * NaN or an infinity is redone with the reference's two loops, literally, so the result is whatever the reference's comparisons make
+ * of such a sample (plan impl 2, the parallel-in-q alternative, is the exception: finite samples only). */
 int pbd_dt2d_f32_device(void* stream, const float* d_in, int n_maps, int h, int w, const float* h_defw4,
                         const int32_t* h_anchor_xy, float* d_out, uint16_t* d_ix, uint16_t* d_iy, int backptr_mode);
 /* host-buffer convenience wrapper of the above (allocates, copies, runs, copies back) */

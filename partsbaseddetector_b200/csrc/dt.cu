@@ -133,6 +133,7 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
     cp_async_commit();
   };
   // sequential reads: q = 0, 1, 2, ... in lock step across the warp; a new tile becomes current every kTileW samples
+  float chk = 0.f;                                                // fma(y, 0, chk): NaN as soon as one sample is NaN or +-inf
   auto loady = [&](int q) -> float {
     if ((q & (kTileW - 1)) == 0) {
       if (q == 0) prefetch(0, 0);
@@ -140,7 +141,9 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
       __syncwarp();
       if (q + kTileW < N) prefetch(q + kTileW, ((q / kTileW) + 1) & 1);
     }
-    return tiles[wib][(q / kTileW) & 1][lane][q & (kTileW - 1)];
+    const float y = tiles[wib][(q / kTileW) & 1][lane][q & (kTileW - 1)];
+    chk = __fmaf_rn(y, 0.f, chk);
+    return y;
   };
   // deep-pop reloads of older samples: global memory (the tile that held them may already be refilled)
   auto reload = [&](int v) -> float { return __ldg(src + v); };
@@ -151,12 +154,19 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
     st_f32(dst, off, val); st_u16(dp, off, v);
   };
   const int os0 = M.os;
+  // a line with a non-finite sample is redone with the reference's two loops, literally (env::envelope_literal): what its comparisons
+  // make of a NaN is not what the streaming formulations make of it
+  auto redo_if_not_finite = [&]() {
+    if (chk != chk) env::envelope_literal(N, f, os0, zb, pb, reload, [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
+  };
   if constexpr (SCAN > 0) {
     env::envelope_scan<(SCAN > 0 ? SCAN : 1)>(N, f, os0, rings[wib], lane, zb, pb, loady, reload,
                                               [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
+    redo_if_not_finite();
     return;
   } else if constexpr (SCAN < 0) {
     env::envelope_stream_cert(N, f, os0, rings[wib], lane, zb, pb, loady, reload, [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
+    redo_if_not_finite();
     return;
   } else {
 #if !defined(PBD_DT_WINDOWED_STORES)
@@ -177,6 +187,7 @@ dt_pass(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, int n
                        [&](int i, float val, int v) { win.put(i, val, v, store); }, [&](int q) { win.step(q, os0, store); });
   win.finish(store);
 #endif
+  redo_if_not_finite();
   }
 }
 
@@ -455,7 +466,16 @@ dt_pass_win(const PassGeom* __restrict__ pg, const PassMap* __restrict__ maps, c
   float zb[MAXN];
   unsigned short pb[MAXN];
   auto ld = [&](int q) -> float { return __ldg(src + q); };
-  env::envelope_stream(N, f, os, R, lane, zb, pb, ld, ld, [&](int i, float val, int v) { store(i, val, (unsigned short)v); }, [](int) {});
+  // a line with a non-finite sample goes through the reference's two loops literally (dt_envelope.cuh); a segment has only seen its
+  // own samples, so the lane that replays a segmented line looks at the whole line first
+  bool not_finite = chk != chk;
+  if (SEG && !not_finite) {
+    float c2 = 0.f;
+    for (int q = 0; q < N; ++q) c2 = __fmaf_rn(ld(q), 0.f, c2);
+    not_finite = c2 != c2;
+  }
+  if (not_finite) env::envelope_literal(N, f, os, zb, pb, ld, [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
+  else env::envelope_stream(N, f, os, R, lane, zb, pb, ld, ld, [&](int i, float val, int v) { store(i, val, (unsigned short)v); }, [](int) {});
   if (counter) atomicAdd(counter, 1);
 }
 

@@ -211,6 +211,35 @@ PBD_ENV_FN void envelope_stream(int N, const Quad& f, int os0, Ring& R, int lane
   emit_run(lo, pos_last, vt, yt, e0, e1);
 }
 
+// The reference's two loops, LITERALLY (include/DistanceTransform.hpp:160-181): build the stack, then scan it.  For lines with a
+// non-finite sample: what the reference's comparisons make of a NaN (every test false: nothing is popped, the scan never advances
+// past a NaN break point) is an accident of its control flow that the streaming formulations above do not share, so the kernels hand
+// such lines to this function (z / v: the lane's N-entry scratch arrays; y(i) = src[i]; emit(i, val, v) once per position index).
+template <typename LoadY, typename Emit>
+PBD_ENV_FN void envelope_literal(int N, const Quad& f, int os0, float* z, unsigned short* v, LoadY y, Emit emit) {
+  int k = 0;
+  v[0] = 0; z[0] = -INFINITY;
+  for (int q = 1; q < N; ++q) {                                   // :160-170
+    const double yq = (double)y(q);
+    auto isect = [&](int vk) -> float {
+      const double yv = (double)y(vk);
+      return q - vk == 1 ? isect_adjacent(f, q, yv, yq) : isect_far(f, vk, q, yv, yq);
+    };
+    float s = isect((int)v[k]);
+    while (s <= z[k] && k > 0) { --k; s = isect((int)v[k]); }
+    ++k;
+    v[k] = (unsigned short)q; z[k] = s;
+  }
+  const int top = k;                                              // z[top + 1] = +inf
+  k = 0;
+  int p = os0;
+  for (int q = 0; q < N; ++q, ++p) {                              // :172-181
+    while (k < top && z[k + 1] < (float)p) ++k;
+    const int vk = (int)v[k];
+    emit(q, (float)dadd(ld_table(f.E, p - vk), (double)y(vk)), vk);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // envelope_stream with CERTIFIED fp32 break points (round 2).  Only decisions depend on the break points -- the pop test s <= z and
 // the integer ranges floor(z) -- the values never leave the lane.  So s is first computed in fp32,

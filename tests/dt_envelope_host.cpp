@@ -42,7 +42,9 @@ int envh_dt1d(const float* src, int nlines, int N, float w_sq, float w_lin, int 
       if (i < 0 || i >= N) __builtin_trap();
       d[i] = val; p[i] = v; ++n;
     };
-    if (window == 5) {
+    if (window == 6) {                                  // the literal two-loop form the kernels use for lines with a non-finite sample
+      envelope_literal(N, f, os, zb.data(), pb.data(), [&](int q) { return s[q]; }, [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
+    } else if (window == 5) {
       auto ld = [&](int q) { return s[q]; };
       envelope_stream_cert(N, f, os, RE, lane, zb.data(), pb.data(), ld, ld, [&](int i, float val, int v) { store(i, val, (unsigned short)v); });
     } else if (window >= 2) {

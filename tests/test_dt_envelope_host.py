@@ -165,3 +165,28 @@ def test_markstein_quotient_equals_exact_division():
     for a, b in ((0.0, -0.02), (np.inf, -0.02), (-np.inf, -0.02), (1e-310, -0.02), (1e300, -1e-9)):
         assert L.envh_quotient_fast(a, b) == L.envh_quotient_exact(a, b)
     assert np.isnan(L.envh_quotient_fast(np.nan, -0.02))
+
+
+def test_literal_form_equals_oracle_on_non_finite_lines():
+    """envelope_literal (what dt_pass / dt_pass_win run for a line with a NaN or an infinity): bit-identical to the oracle's
+    restatement of computeRow on lines with NaN, +inf and -inf samples at the ends and in the middle, and on ordinary lines."""
+    rng = np.random.default_rng(606)
+    L = oracle_lib.lib()
+    for N in (1, 2, 5, 33, 160, 300):
+        for os_ in (0, 3, -2, 7):
+            src = (rng.standard_normal((32, N)) * 0.3).astype(np.float32)
+            bad = [np.nan, np.inf, -np.inf]
+            for i in range(1, 32):
+                for _ in range(1 + i % 3):
+                    src[i, rng.integers(0, N)] = bad[(i + _) % 3]
+            if N > 2:
+                src[5, 0] = np.nan; src[6, N - 1] = np.nan; src[7, 0] = np.inf; src[8, N - 1] = -np.inf
+            for w_sq, w_lin in ((0.0156, -0.014), (0.05, 0.0), (0.3, 0.2)):
+                dst = np.full((32, N), -7.0, np.float32)
+                ptr = np.full((32, N), 0xFFFF, np.uint16)
+                assert envlib().envh_dt1d(np.ascontiguousarray(src), 32, N, w_sq, w_lin, os_, N, dst, ptr, None, 6) == 0
+                for i in range(32):
+                    rd, rp = np.empty(N, np.float32), np.empty(N, np.int32)
+                    L.orc_dt1d_f32(np.ascontiguousarray(src[i]), N, -float(np.float32(w_sq)), -float(np.float32(w_lin)), os_, rd, rp)
+                    assert np.array_equal(dst[i], rd, equal_nan=True), (i, N, os_)
+                    assert np.array_equal(ptr[i].astype(np.int32), rp), (i, N, os_)

@@ -216,7 +216,7 @@ def test_dt2d_segmented_walk_on_adversarial_maps(h, w, seg):
     """The segmented walk (lines cut into segments of seg - 10 positions, each walked by its own lane; a line is accepted only if all
     of its segments are) on the inputs built to break a windowed certificate: score-like maps, maps quantised to a coarse binary grid
     with weights 2^-k so that break points fall exactly on integers and neighbouring candidates tie exactly, constant maps, a map with
-    isolated huge spikes (owners far outside the window), noise, infinities of either sign, anchors up to the window's limit.  Every map
+    isolated huge spikes (owners far outside the window), noise, a NaN and infinities of either sign, anchors up to the window's limit.  Every map
     must equal the oracle bit for bit, exactly as with one lane per line."""
     import torch
     from partsbaseddetector_b200 import Dt2dPlan
@@ -229,8 +229,9 @@ def test_dt2d_segmented_walk_on_adversarial_maps(h, w, seg):
     maps[4] = 0.375                                                           # constant: every neighbour pair meets at a half integer
     maps[5, ::7, ::5] += 3.0                                                  # spikes: their parabolas own positions far beyond the window
     maps[6] = rng.standard_normal((h, w)).astype(np.float32)                  # noise
-    maps[7, h // 2, w // 3] = -np.inf                                          # non-finite samples refuse their lines (NaN is outside the
-    maps[8, h // 3, w // 2] = np.inf                                           # transform's contract: include/pbd_b200.h)
+    maps[7, h // 2, w // 3] = np.nan                                           # non-finite samples: their lines go through the reference's
+    maps[7, h // 4, w - 1] = -np.inf                                           # two loops literally (env::envelope_literal)
+    maps[8, h // 3, w // 2] = np.inf
     defw = np.stack([rng.uniform(0.01, 0.02, n), rng.uniform(-0.02, 0.02, n), rng.uniform(0.01, 0.02, n), rng.uniform(-0.02, 0.02, n)], axis=1).astype(np.float32)
     defw[2] = (0.0625, 0.0, 0.125, -0.125)
     defw[3] = (0.03125, 0.0625, 0.5, 0.0)
@@ -260,6 +261,39 @@ def test_dt2d_segmented_walk_on_adversarial_maps(h, w, seg):
             assert np.array_equal(out[i], o, equal_nan=True), (i, steps)
             assert np.array_equal(ix[i].astype(np.int32), x) and np.array_equal(iy[i].astype(np.int32), y), (i, steps)
     assert plan.replayed() > 0
+    plan.close()
+
+
+@pytest.mark.parametrize("impl", [1, 3, 4])
+def test_dt2d_non_finite_samples_equal_the_oracle(impl):
+    """NaN and +-inf samples through the streaming kernels (eager and lagged-scan emission) and the windowed transform: their lines are
+    redone with the reference's two loops, literally, so the result is whatever the reference's comparisons make of such a sample
+    (the oracle is pinned to the compiled reference source on these inputs: tests/test_oracle_ref.py)."""
+    import torch
+    from partsbaseddetector_b200 import Dt2dPlan
+    rng = np.random.default_rng(4711 + impl)
+    n, h, w = 4, 45, 170
+    maps = (rng.standard_normal((n, h, w)) * 0.3).astype(np.float32)
+    for i in range(n):
+        for k in range(5):
+            maps[i, rng.integers(0, h), rng.integers(0, w)] = (np.nan, np.inf, -np.inf)[(i + k) % 3]
+    maps[1, 0, 0] = np.nan; maps[2, h - 1, w - 1] = np.nan
+    defw = np.stack([rng.uniform(0.01, 0.05, n), rng.uniform(-0.02, 0.02, n), rng.uniform(0.01, 0.05, n), rng.uniform(-0.02, 0.02, n)], axis=1).astype(np.float32)
+    anchors = np.stack([rng.integers(-3, 4, n), rng.integers(-2, 6, n)], axis=1).astype(np.int32)
+    plan = Dt2dPlan(n, h, w, defw, anchors, impl)
+    d_in = torch.from_numpy(maps).cuda()
+    d_out = torch.empty_like(d_in)
+    d_ix = torch.empty((n, h, w), dtype=torch.int16, device="cuda")
+    d_iy = torch.empty_like(d_ix)
+    plan.run(d_in.data_ptr(), d_out.data_ptr(), d_ix.data_ptr(), d_iy.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    out, ix, iy = d_out.cpu().numpy(), d_ix.cpu().numpy().view(np.uint16), d_iy.cpu().numpy().view(np.uint16)
+    L = oracle_lib.lib()
+    for i in range(n):
+        o, x, y = np.empty((h, w), np.float32), np.empty((h, w), np.int32), np.empty((h, w), np.int32)
+        L.orc_dt2d_f32(maps[i].reshape(-1), h, w, defw[i], int(anchors[i, 0]), int(anchors[i, 1]), 0, o.reshape(-1), x.reshape(-1), y.reshape(-1))
+        assert np.array_equal(out[i], o, equal_nan=True), i
+        assert np.array_equal(ix[i].astype(np.int32), x) and np.array_equal(iy[i].astype(np.int32), y), i
     plan.close()
 
 

@@ -44,6 +44,25 @@ def test_distance_transform_equals_reference_source(h, w):
             assert np.array_equal(o, r) and np.array_equal(ox, rx) and np.array_equal(oy, ry), (k, dt)
 
 
+def test_distance_transform_with_non_finite_samples_equals_reference_source():
+    """NaN and +-inf samples: whatever the reference's comparisons make of them (nothing is popped past a NaN break point, the scan
+    never advances beyond one), the oracle's restatement makes the same -- the pin behind the kernels' literal fallback for such lines."""
+    rng = np.random.default_rng(99)
+    L, R = oracle_lib.lib(), ref_lib.lib()
+    for h, w in ((9, 31), (40, 57)):
+        for k in range(4):
+            m = (rng.standard_normal((h, w)) * 0.3).astype(np.float32)
+            for _ in range(6):
+                m[rng.integers(0, h), rng.integers(0, w)] = (np.nan, np.inf, -np.inf)[(k + _) % 3]
+            w4 = np.array([rng.uniform(0.01, 0.08), rng.uniform(-0.03, 0.03), rng.uniform(0.01, 0.08), rng.uniform(-0.03, 0.03)], np.float32)
+            ax, ay = int(rng.integers(-4, 5)), int(rng.integers(-5, 6))
+            o, ox, oy = np.empty((h, w), np.float32), np.empty((h, w), np.int32), np.empty((h, w), np.int32)
+            r, rx, ry = np.empty((h, w), np.float32), np.empty((h, w), np.int32), np.empty((h, w), np.int32)
+            L.orc_dt2d_f32(m.reshape(-1), h, w, w4, ax, ay, 0, o.reshape(-1), ox.reshape(-1), oy.reshape(-1))
+            R.ref_dt2d_f32(m.reshape(-1), h, w, w4, ax, ay, r.reshape(-1), rx.reshape(-1), ry.reshape(-1))
+            assert np.array_equal(o, r, equal_nan=True) and np.array_equal(ox, rx) and np.array_equal(oy, ry), (h, w, k)
+
+
 def test_reduce_max_and_pick_index_equal_reference_source():
     rng = np.random.default_rng(5)
     for K in (1, 2, 5, 6):
