@@ -1,3 +1,5 @@
+"""Instruction and stall-sample shares per source line of one kernel of an .ncu-rep (captured with --import-source on, built with
+-lineinfo), summed over all captured launches and template instances.  usage: python tools/ncu_lines_agg.py report.ncu-rep kernel_regex top"""
 import csv, subprocess, sys, collections
 rep, rx = sys.argv[1], sys.argv[2]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + rx], capture_output=True, text=True).stdout
